@@ -1,0 +1,325 @@
+/* kjb.h — C-ABI of the B200-native kajiya ReSTIR-GI hot path.
+ *
+ * kajiya has no FFI: its extension point is the Rust closure handed to
+ * `PassBuilder::render` (crates/lib/kajiya-rg/src/pass_builder.rs:325-337), normally built
+ * with `SimpleRenderPass` (crates/lib/kajiya-rg/src/hl.rs:104-406).  Every entry point below
+ * replaces the body of ONE such closure — the `vkCmdDispatch` / `vkCmdTraceRaysKHR` that
+ * `SimpleRenderPass::{dispatch,trace_rays}` records (hl.rs:133-253) — and is named after the
+ * render-graph pass label the reference gives it (`rg.add_pass("rtdgi trace")`, ...).
+ * The fields of each `*_args` struct are the resources in the reference's BINDING ORDER
+ * (binding index = call order of .read/.write/.constants, hl.rs:266,324,354-359) followed by the
+ * constants tuple byte-for-byte.
+ *
+ * Conventions:
+ *   - plain pointers and sizes, no C++/torch types; all structs are POD;
+ *   - every call returns 0 on success, non-zero on error (`kjb_last_error` gives the text);
+ *     nothing unwinds across the boundary (the Rust closure maps non-zero to BackendError);
+ *   - every call only ENQUEUES work on the context's CUDA stream, in call order (the reference
+ *     records passes serially in declaration order, graph.rs:865-867); `kjb_sync` waits;
+ *   - image memory is owned by whoever allocated it (`kjb_image_alloc` for the library's
+ *     allocator); the library never frees caller-owned handles;
+ *   - images are tightly packed row-major linear buffers of the texel formats below
+ *     (the Vulkan formats the reference creates them with), temporal images are zero-filled
+ *     at allocation (the reference leaves them undefined, temporal.rs:204-205).
+ */
+#ifndef KJB_H
+#define KJB_H
+
+#include <stdint.h>
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KJB_ABI_VERSION 1
+
+/* ------------------------------------------------------------------ formats */
+typedef enum kjb_format {
+    KJB_FMT_UNKNOWN = 0,
+    KJB_FMT_R32_FLOAT = 1,          /* depth (D32_SFLOAT), half depth                          4 B */
+    KJB_FMT_RG32_UINT = 2,          /* reservoirs (rtdgi.rs:286)                                8 B */
+    KJB_FMT_RGBA32_FLOAT = 3,       /* gbuffer, ray_orig (world_render_passes.rs:49, rtdgi.rs:261) 16 B */
+    KJB_FMT_RGBA32_UINT = 4,        /* temporal_reservoir_packed (rtdgi.rs:232)                16 B */
+    KJB_FMT_RGBA16_FLOAT = 5,       /* most colour targets                                      8 B */
+    KJB_FMT_RG16_FLOAT = 6,         /* invalidity, variance                                     4 B */
+    KJB_FMT_RGBA8_UNORM = 7,        /* hit_normal (rtdgi.rs:211)                                4 B */
+    KJB_FMT_RGBA8_SNORM = 8,        /* half view normal, candidate normal                       4 B */
+    KJB_FMT_R8_UNORM = 9,           /* rt_history_validity, ssao                                1 B */
+    KJB_FMT_R8_SNORM = 10,          /* half ssao (rtdgi.rs:190)                                 1 B */
+    KJB_FMT_RGBA16_SNORM = 11,      /* reprojection map (reprojection.rs)                       8 B */
+    KJB_FMT_A2R10G10B10_UNORM = 12, /* geometric normal (world_render_passes.rs:44)             4 B */
+    KJB_FMT_R11G11B10_UFLOAT = 13,  /* rtr resolve output                                       4 B */
+    KJB_FMT_R32_UINT = 14,
+    KJB_FMT_R16_FLOAT = 15,
+    KJB_FMT_RG32_FLOAT = 16,
+    KJB_FMT_COUNT_
+} kjb_format;
+
+/* A 2D image (or, with `layers` > 1, a 2D array / cube stored layer after layer). */
+typedef struct kjb_image {
+    void    *data;      /* device pointer (CUDA build) / host pointer (oracle, emulator) */
+    uint32_t width;
+    uint32_t height;
+    uint32_t format;    /* kjb_format */
+    uint32_t layers;    /* 1 for plain 2D, 6 for cubes */
+} kjb_image;
+
+typedef struct kjb_buffer {
+    void    *data;
+    uint64_t size_bytes;
+} kjb_buffer;
+
+/* ------------------------------------------------------------------ frame constants
+ * Byte-identical to rust-shaders-shared: ViewConstants (view_constants.rs:4-23),
+ * FrameConstants (frame_constants.rs:13-37), HLSL twin inc/frame_constants.hlsl:8-82.
+ * Matrices are glam column-major: element (row r, col c) = m[c*4 + r].                */
+typedef struct kjb_mat4 { float m[16]; } kjb_mat4;
+
+typedef struct kjb_view_constants {
+    kjb_mat4 view_to_clip, clip_to_view, view_to_sample, sample_to_view, world_to_view, view_to_world;
+    kjb_mat4 clip_to_prev_clip;
+    kjb_mat4 prev_view_to_prev_clip, prev_clip_to_prev_view, prev_world_to_prev_view, prev_view_to_prev_world;
+    float sample_offset_pixels[2];
+    float sample_offset_clip[2];
+} kjb_view_constants;
+
+#define KJB_IRCACHE_CASCADE_COUNT 12
+typedef struct kjb_ircache_cascade_constants {
+    int32_t origin[4];
+    int32_t voxels_scrolled_this_frame[4];
+} kjb_ircache_cascade_constants;
+
+#define KJB_OVERRIDE_FORCE_FACE_NORMALS 1u
+#define KJB_OVERRIDE_NO_NORMAL_MAPS 2u
+#define KJB_OVERRIDE_FLIP_NORMAL_MAP_YZ 4u
+#define KJB_OVERRIDE_NO_METAL 8u
+
+typedef struct kjb_frame_constants {
+    kjb_view_constants view_constants;
+    float    sun_direction[4];
+    uint32_t frame_index;
+    float    delta_time_seconds;
+    float    sun_angular_radius_cos;
+    uint32_t triangle_light_count;
+    float    sun_color_multiplier[4];
+    float    sky_ambient[4];
+    float    pre_exposure;
+    float    pre_exposure_prev;
+    float    pre_exposure_delta;
+    float    pad0;
+    uint32_t render_override_flags;
+    float    render_override_material_roughness_scale;
+    uint32_t render_override_pad0, render_override_pad1;
+    float    ircache_grid_center[4];
+    kjb_ircache_cascade_constants ircache_cascades[KJB_IRCACHE_CASCADE_COUNT];
+} kjb_frame_constants;   /* 1216 bytes */
+
+/* world_renderer.rs:107-136 / inc/lights/packed.hlsl */
+typedef struct kjb_triangle_light { float verts[3][3]; float radiance[3]; } kjb_triangle_light;
+
+/* ------------------------------------------------------------------ scene (bindless set 1 + TLAS set 3)
+ * `GpuMesh` (world_renderer.rs:43-54, inc/mesh.hlsl:10-18): byte offsets into the unified vertex buffer. */
+typedef struct kjb_gpu_mesh {
+    uint32_t vertex_core_offset, vertex_uv_offset, vertex_mat_offset, vertex_aux_offset,
+             vertex_tangent_offset, mat_data_offset, index_offset;
+} kjb_gpu_mesh;
+
+/* inc/mesh.hlsl:52-61, kajiya-asset/src/mesh.rs:73-84 — 152 bytes */
+typedef struct kjb_mesh_material {
+    float    base_color_mult[4];
+    uint32_t maps[4];              /* normal, spec, albedo, emissive (bindless texture ids) */
+    float    roughness_mult;
+    float    metalness_factor;
+    float    emissive[3];
+    uint32_t flags;
+    float    map_transforms[24];
+} kjb_mesh_material;
+
+/* RayTracingInstanceDesc (world_renderer.rs:843-851): 3x4 row-major object-to-world + mesh index */
+typedef struct kjb_instance {
+    float    transform[12];        /* row-major 3x4, like VkTransformMatrixKHR */
+    uint32_t mesh_index;           /* InstanceID() in gbuffer.rchit.hlsl:54 */
+    float    emissive_multiplier;  /* instance_dynamic_parameters_dyn (frame_constants.hlsl:86-90) */
+} kjb_instance;
+
+/* A bindless texture: RGBA8 texels already decoded to linear floats-in-bytes semantics
+ * (sRGB decode done at import), full mip chain stored mip after mip. */
+typedef struct kjb_texture_desc {
+    const uint8_t *texels;         /* host pointer at upload time */
+    uint32_t width, height, mip_count;
+    uint32_t srgb;                 /* 1: texels are sRGB-encoded, decode on fetch */
+} kjb_texture_desc;
+
+typedef struct kjb_context kjb_context;
+
+/* ------------------------------------------------------------------ context / memory */
+int  kjb_abi_version(void);
+/* device < 0: the emulator/oracle builds ignore it; the CUDA build requires a valid ordinal. */
+int  kjb_create(int device, kjb_context **out_ctx);
+void kjb_destroy(kjb_context *ctx);
+int  kjb_sync(kjb_context *ctx);
+const char *kjb_last_error(kjb_context *ctx);
+/* which implementation is behind the pointer: "cuda-sm100a", "emu-cpu", "oracle-cpu" */
+const char *kjb_backend_name(void);
+/* number of device kernels launched through this context so far (0 for the oracle) */
+uint64_t kjb_launch_count(kjb_context *ctx);
+/* the cudaStream_t all passes are enqueued on (NULL for CPU backends) */
+void *kjb_stream(kjb_context *ctx);
+
+uint32_t kjb_format_texel_bytes(uint32_t format);
+int  kjb_image_alloc(kjb_context *ctx, uint32_t width, uint32_t height, uint32_t layers, uint32_t format, kjb_image *out);
+int  kjb_image_free(kjb_context *ctx, kjb_image *img);
+int  kjb_image_clear(kjb_context *ctx, const kjb_image *img);
+int  kjb_image_copy(kjb_context *ctx, const kjb_image *dst, const kjb_image *src);       /* same extent+format ("copy depth", reprojection.rs:42-48) */
+int  kjb_image_fill_u8(kjb_context *ctx, const kjb_image *img, uint32_t byte_value);     /* memset of every byte (constant ssao input) */
+int  kjb_image_upload(kjb_context *ctx, const kjb_image *dst, const void *host_src);     /* async on the stream */
+int  kjb_image_download(kjb_context *ctx, const kjb_image *src, void *host_dst);         /* async on the stream */
+int  kjb_buffer_alloc(kjb_context *ctx, uint64_t size_bytes, kjb_buffer *out);           /* zero-filled (temporal.rs:270-275) */
+int  kjb_buffer_free(kjb_context *ctx, kjb_buffer *buf);
+int  kjb_buffer_upload(kjb_context *ctx, const kjb_buffer *dst, uint64_t dst_offset, const void *host_src, uint64_t size);
+int  kjb_buffer_download(kjb_context *ctx, const kjb_buffer *src, uint64_t src_offset, void *host_dst, uint64_t size);
+
+/* ------------------------------------------------------------------ scene upload
+ * kjb_scene_set_geometry replaces WorldRenderer::add_mesh's buffer uploads + BLAS builds
+ * (world_renderer.rs:604-776): the unified `vertices` byte buffer, the `meshes` table and, per mesh,
+ * the index count (the BLAS geometry, ray_tracing.rs:96-170: OPAQUE triangles, u32 indices,
+ * float3 positions at vertex_core_offset with 16-byte stride). */
+int  kjb_scene_set_geometry(kjb_context *ctx, const void *vertex_buffer, uint64_t vertex_buffer_bytes,
+                            const kjb_gpu_mesh *meshes, const uint32_t *mesh_index_counts, uint32_t mesh_count);
+int  kjb_scene_set_textures(kjb_context *ctx, const kjb_texture_desc *textures, uint32_t texture_count);
+/* "rebuild tlas" (world_renderer.rs:865-911): instance transforms -> TLAS, every frame in the reference. */
+int  kjb_rebuild_tlas(kjb_context *ctx, const kjb_instance *instances, uint32_t instance_count);
+/* set 2 of every pass (renderer.rs:45-78): FrameConstants + triangle lights. */
+int  kjb_set_frame_constants(kjb_context *ctx, const kjb_frame_constants *fc,
+                             const kjb_triangle_light *lights, uint32_t light_count);
+/* bindless LUT slots 0 and 1 (inc/bindless_textures.hlsl:8-12): BRDF FG LUT 64x64 RGBA16F, blue noise 256x256 RGBA8 */
+int  kjb_set_luts(kjb_context *ctx, const kjb_image *brdf_fg_lut, const kjb_image *blue_noise_rgba8);
+
+/* ray statistics accumulated by tracing passes since the last reset: [0] closest-hit rays, [1] any-hit (shadow) rays */
+int  kjb_ray_counters(kjb_context *ctx, uint64_t out_counts[2], int reset);
+
+/* ------------------------------------------------------------------ input producers (needed to feed the path) */
+typedef struct kjb_raster_gbuffer_args {   /* replaces "raster simple" (raster_simple_ps.hlsl:39-140) by primary-ray casting */
+    kjb_image geometric_normal_out;        /* A2R10G10B10_UNORM, view-space normal *0.5+0.5 */
+    kjb_image gbuffer_out;                 /* RGBA32_FLOAT (packed GbufferData) */
+    kjb_image depth_out;                   /* R32_FLOAT reverse-Z, 0 = sky */
+    kjb_image velocity_out;                /* RGBA16_FLOAT view-space motion (0 for static scenes) */
+} kjb_raster_gbuffer_args;
+int kjb_pass_raster_gbuffer(kjb_context *ctx, const kjb_raster_gbuffer_args *a);
+
+typedef struct kjb_reprojection_map_args { /* calculate_reprojection_map.hlsl:9-16 */
+    kjb_image depth_tex, geometric_normal_tex, prev_depth_tex, velocity_tex, output_tex;
+    float output_tex_size[4];
+} kjb_reprojection_map_args;
+int kjb_pass_reprojection_map(kjb_context *ctx, const kjb_reprojection_map_args *a);
+
+typedef struct kjb_sky_cube_args { kjb_image output_tex; } kjb_sky_cube_args;            /* sky/comp_cube.hlsl */
+int kjb_pass_sky_cube(kjb_context *ctx, const kjb_sky_cube_args *a);
+typedef struct kjb_convolve_sky_args { kjb_image input_tex, output_tex; uint32_t face_width; } kjb_convolve_sky_args; /* convolve_cube.hlsl */
+int kjb_pass_convolve_sky(kjb_context *ctx, const kjb_convolve_sky_args *a);
+typedef struct kjb_brdf_fg_lut_args { kjb_image output_tex; } kjb_brdf_fg_lut_args;       /* lut/brdf_fg.hlsl */
+int kjb_pass_brdf_fg_lut(kjb_context *ctx, const kjb_brdf_fg_lut_args *a);
+
+/* ------------------------------------------------------------------ half-res extracts (renderers/half_res.rs, rtdgi.rs:185-202) */
+typedef struct kjb_extract_half_res_args { kjb_image input_tex, output_tex; } kjb_extract_half_res_args;
+int kjb_pass_extract_half_res_depth(kjb_context *ctx, const kjb_extract_half_res_args *a);        /* "extract half depth" */
+int kjb_pass_extract_half_res_view_normal(kjb_context *ctx, const kjb_extract_half_res_args *a);  /* "extract view normal/2" */
+int kjb_pass_extract_half_res_ssao(kjb_context *ctx, const kjb_extract_half_res_args *a);         /* "extract ssao/2" */
+
+/* ------------------------------------------------------------------ ircache binding block (ircache/bindings.hlsl, ircache.rs:59-78).
+ * NULL `meta_buf.data` = irradiance cache not bound: lookups return 0 and allocate nothing. */
+typedef struct kjb_ircache_bindings {
+    kjb_buffer meta_buf, grid_meta_buf, entry_cell_buf, spatial_buf, irradiance_buf, aux_buf,
+               life_buf, pool_buf, reposition_proposal_buf, reposition_proposal_count_buf;
+} kjb_ircache_bindings;
+
+/* ------------------------------------------------------------------ rtdgi (renderers/rtdgi.rs) */
+typedef struct kjb_rtdgi_reproject_args {            /* "rtdgi reproject", fullres_reproject.hlsl:10-15, rtdgi.rs:156-164 */
+    kjb_image input_tex, reprojection_tex, output_tex;
+    float output_tex_size[4];
+} kjb_rtdgi_reproject_args;
+int kjb_pass_rtdgi_reproject(kjb_context *ctx, const kjb_rtdgi_reproject_args *a);
+
+typedef struct kjb_rtdgi_validate_args {             /* "rtdgi validate", diffuse_validate.rgen.hlsl:20-39, rtdgi.rs:293-316 */
+    kjb_image half_view_normal_tex, depth_tex, reprojected_gi_tex;
+    kjb_image reservoir_tex;                          /* read-write: history reservoirs */
+    kjb_image reservoir_ray_history_tex, reprojection_tex;
+    kjb_ircache_bindings ircache;
+    kjb_image sky_cube_tex;
+    kjb_image irradiance_history_tex;                 /* read-write */
+    kjb_image ray_orig_history_tex;
+    kjb_image rt_history_invalidity_out_tex;
+    float gbuffer_tex_size[4];
+} kjb_rtdgi_validate_args;
+int kjb_pass_rtdgi_validate(kjb_context *ctx, const kjb_rtdgi_validate_args *a);
+
+typedef struct kjb_rtdgi_trace_args {                /* "rtdgi trace", trace_diffuse.rgen.hlsl:23-41, rtdgi.rs:321-345 */
+    kjb_image half_view_normal_tex, depth_tex, reprojected_gi_tex, reprojection_tex;
+    kjb_ircache_bindings ircache;
+    kjb_image sky_cube_tex, ray_orig_history_tex;
+    kjb_image candidate_irradiance_out_tex, candidate_normal_out_tex, candidate_hit_out_tex;
+    kjb_image rt_history_invalidity_in_tex, rt_history_invalidity_out_tex;
+    float gbuffer_tex_size[4];
+} kjb_rtdgi_trace_args;
+int kjb_pass_rtdgi_trace(kjb_context *ctx, const kjb_rtdgi_trace_args *a);
+
+typedef struct kjb_rtdgi_validity_integrate_args {   /* "validity integrate", temporal_validity_integrate.hlsl:10-19 */
+    kjb_image input_tex, history_tex, reprojection_tex, half_view_normal_tex, half_depth_tex, output_tex;
+    float gbuffer_tex_size[4], output_tex_size[4];
+} kjb_rtdgi_validity_integrate_args;
+int kjb_pass_rtdgi_validity_integrate(kjb_context *ctx, const kjb_rtdgi_validity_integrate_args *a);
+
+typedef struct kjb_rtdgi_restir_temporal_args {      /* "restir temporal", restir_temporal.hlsl:18-40, rtdgi.rs:363-389 */
+    kjb_image half_view_normal_tex, depth_tex, candidate_radiance_tex, candidate_normal_tex, candidate_hit_tex,
+              radiance_history_tex, ray_orig_history_tex, ray_history_tex, reservoir_history_tex, reprojection_tex,
+              hit_normal_history_tex, candidate_history_tex, rt_invalidity_tex;
+    kjb_image radiance_out_tex, ray_orig_output_tex, ray_output_tex, hit_normal_output_tex, reservoir_out_tex,
+              candidate_out_tex, temporal_reservoir_packed_tex;
+    float gbuffer_tex_size[4];
+} kjb_rtdgi_restir_temporal_args;
+int kjb_pass_rtdgi_restir_temporal(kjb_context *ctx, const kjb_rtdgi_restir_temporal_args *a);
+
+typedef struct kjb_rtdgi_restir_spatial_args {       /* "restir spatial", restir_spatial.hlsl:15-32, rtdgi.rs:428-476 */
+    kjb_image reservoir_input_tex, bounced_radiance_input_tex, half_view_normal_tex, half_depth_tex, depth_tex,
+              half_ssao_tex, temporal_reservoir_packed_tex, reprojected_gi_tex;
+    kjb_image reservoir_output_tex, bounced_radiance_output_tex;
+    float gbuffer_tex_size[4], output_tex_size[4];
+    uint32_t spatial_reuse_pass_idx, perform_occlusion_raymarch, occlusion_raymarch_importance_only;
+} kjb_rtdgi_restir_spatial_args;
+int kjb_pass_rtdgi_restir_spatial(kjb_context *ctx, const kjb_rtdgi_restir_spatial_args *a);
+
+typedef struct kjb_rtdgi_restir_resolve_args {       /* "restir resolve", restir_resolve.hlsl:16-31, rtdgi.rs:502-523 */
+    kjb_image radiance_tex, reservoir_input_tex, gbuffer_tex, depth_tex, half_view_normal_tex, half_depth_tex,
+              ssao_tex, candidate_radiance_tex, candidate_hit_tex, temporal_reservoir_packed_tex,
+              bounced_radiance_input_tex;
+    kjb_image irradiance_output_tex;
+    float gbuffer_tex_size[4], output_tex_size[4];
+} kjb_rtdgi_restir_resolve_args;
+int kjb_pass_rtdgi_restir_resolve(kjb_context *ctx, const kjb_rtdgi_restir_resolve_args *a);
+
+typedef struct kjb_rtdgi_temporal_args {             /* "rtdgi temporal", temporal_filter.hlsl:23-35, rtdgi.rs:96-112 */
+    kjb_image input_tex, history_tex, variance_history_tex, reprojection_tex, rt_history_invalidity_tex;
+    kjb_image output_tex, history_output_tex, variance_history_output_tex;
+    float output_tex_size[4], gbuffer_tex_size[4];
+} kjb_rtdgi_temporal_args;
+int kjb_pass_rtdgi_temporal(kjb_context *ctx, const kjb_rtdgi_temporal_args *a);
+
+typedef struct kjb_rtdgi_spatial_args {              /* "rtdgi spatial", spatial_filter.hlsl:10-17, rtdgi.rs:127-138 */
+    kjb_image input_tex, depth_tex, ssao_tex, geometric_normal_tex, output_tex;
+    float output_tex_size[4];
+} kjb_rtdgi_spatial_args;
+int kjb_pass_rtdgi_spatial(kjb_context *ctx, const kjb_rtdgi_spatial_args *a);
+
+/* ------------------------------------------------------------------ reference path tracer (the oracle's quantity, also a GPU pass)
+ * "reference pt" (renderers/reference.rs:8-25, rt/reference_path_trace.rgen.hlsl:75-377): accumulates into RGBA32F. */
+typedef struct kjb_reference_pt_args {
+    kjb_image output_tex;          /* RGBA32_FLOAT, read-write accumulation */
+    uint32_t indirect_only;        /* the shader's INDIRECT_ONLY compile-time switch (:33), runtime here */
+} kjb_reference_pt_args;
+int kjb_pass_reference_path_trace(kjb_context *ctx, const kjb_reference_pt_args *a);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KJB_H */

@@ -1,0 +1,88 @@
+/* kjb_world.h — host-side frame driver above the per-pass C-ABI (kjb.h).
+ *
+ * kajiya's host for this path is Rust (not available here): `WorldRenderer`
+ * (crates/lib/kajiya/src/world_renderer.rs), the per-frame pass list
+ * `prepare_render_graph_standard` (crates/lib/kajiya/src/world_render_passes.rs:13-292) and the
+ * per-effect modules `renderers/{rtdgi,ircache,rtr,taa}.rs`.  This is their C++ mirror: same scene
+ * API (add_mesh / add_instance), same temporal resources and ping-pong keys, same pass order, same
+ * constants tuples — it only ever talks to the GPU through the `kjb_pass_*` entry points, so a Rust
+ * render-graph closure and this driver are interchangeable callers of the drop-in boundary.
+ * The same source is linked into the CUDA library, the CPU-emulation test build and the oracle, so
+ * frame sequences can be replayed against any of them.
+ */
+#ifndef KJB_WORLD_H
+#define KJB_WORLD_H
+#include "kjb.h"
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct kjb_world kjb_world;
+
+typedef struct kjb_world_desc {
+    uint32_t render_width, render_height;         /* WorldFrameDesc::render_extent */
+    uint32_t temporal_upscale_width, temporal_upscale_height;   /* TAA output extent; 0 = same as render */
+    uint32_t spatial_reuse_pass_count;            /* RtdgiRenderer::spatial_reuse_pass_count (default 2) */
+    uint32_t use_raytraced_reservoir_visibility;  /* RtdgiRenderer (default 0) */
+    uint32_t enable_ircache, enable_rtr, enable_taa;
+    /* Tile sharding: this process renders half-res rows [tile_y0, tile_y1) plus a halo. 0,0 = whole frame. */
+    uint32_t tile_y0, tile_y1;
+} kjb_world_desc;
+
+/* TriangleMesh as the asset pipeline hands it to add_mesh (kajiya-asset/src/mesh.rs:85-98) */
+typedef struct kjb_mesh_desc {
+    const float    *positions;      /* 3 per vertex */
+    const float    *normals;        /* 3 per vertex */
+    const float    *uvs;            /* 2 per vertex, may be NULL (zeros) */
+    const float    *colors;         /* 4 per vertex, may be NULL (ones) */
+    const uint32_t *material_ids;   /* 1 per vertex */
+    const uint32_t *indices;
+    uint32_t vertex_count, index_count;
+    const kjb_mesh_material *materials;   /* `maps` index this mesh's own map list */
+    uint32_t material_count;
+    const kjb_texture_desc *maps;
+    uint32_t map_count;
+    uint32_t use_lights;            /* AddMeshOptions::use_lights */
+} kjb_mesh_desc;
+
+typedef struct kjb_world_frame {
+    float camera_position[3];
+    float camera_rotation[4];       /* quaternion xyzw */
+    float vertical_fov_deg;         /* CameraLens (camera.rs:40-55): default 52 */
+    float near_plane;               /* default 0.01 */
+    float sun_direction[3];         /* direction TOWARDS the sun */
+    float delta_time_seconds;
+    /* Optional host-resident G-buffer inputs (pinned memory recommended).  When `host_gbuffer` is non-NULL the
+     * raster stand-in is skipped and these are uploaded inside the call: gbuffer RGBA32F, depth R32F,
+     * geometric normal A2R10G10B10, velocity RGBA16F — i.e. what kajiya's raster pass would hand over. */
+    const void *host_gbuffer, *host_depth, *host_geometric_normal, *host_velocity;
+    /* Optional host destination for the frame's result (rtdgi screen irradiance, RGBA16F full-res; the TAA
+     * output RGBA16F when TAA is enabled).  Copied device->host inside the call when non-NULL. */
+    void *host_result;
+} kjb_world_frame;
+
+int  kjb_world_create(kjb_context *ctx, const kjb_world_desc *desc, kjb_world **out);
+void kjb_world_destroy(kjb_world *w);
+/* WorldRenderer::add_mesh (world_renderer.rs:604-776) / add_instance (:778-). transform = row-major 3x4. */
+int  kjb_world_add_mesh(kjb_world *w, const kjb_mesh_desc *mesh, uint32_t *out_mesh_handle);
+int  kjb_world_add_instance(kjb_world *w, uint32_t mesh_handle, const float transform[12], uint32_t *out_instance_handle);
+/* the 256x256 RGBA8 blue-noise LUT (bindless slot 1; assets/images/bluenoise/256_256/LDR_RGBA_0.png in the reference) */
+int  kjb_world_set_blue_noise(kjb_world *w, const uint8_t *rgba8_256x256);
+/* one frame of prepare_render_graph_standard's hot-path passes; enqueues, does not sync (unless host_result is set) */
+int  kjb_world_render_frame(kjb_world *w, const kjb_world_frame *frame);
+/* one frame of prepare_render_graph_reference (world_render_passes.rs:294-330): the path tracer accumulating in place */
+int  kjb_world_render_reference(kjb_world *w, const kjb_world_frame *frame, uint32_t indirect_only);
+uint32_t kjb_world_frame_index(kjb_world *w);
+/* Look up a live image by its reference resource name ("rtdgi.radiance:0", "gbuffer", "rtdgi.irradiance", ...). */
+int  kjb_world_get_image(kjb_world *w, const char *name, kjb_image *out);
+/* names of all live images, '\n' separated (test harness iterates them for per-pass parity) */
+const char *kjb_world_image_names(kjb_world *w);
+/* kernel launches / rays of the last frame */
+int  kjb_world_last_frame_stats(kjb_world *w, uint64_t out[4]);   /* launches, closest rays, any-hit rays, passes */
+/* Run frames only up to (and including) the pass with this rg label, for per-pass debugging ("" = all). */
+int  kjb_world_set_stop_after(kjb_world *w, const char *pass_label);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,518 @@
+// Host-side frame driver: C++ mirror of kajiya's Rust host for the ReSTIR-GI hot path.
+//   WorldRenderer scene store / add_mesh        crates/lib/kajiya/src/world_renderer.rs:604-776
+//   prepare_frame_constants                     world_renderer.rs:1001-1108
+//   prepare_render_graph_standard (pass order)  crates/lib/kajiya/src/world_render_passes.rs:13-292
+//   RtdgiRenderer::{reproject,render,temporal,spatial}   crates/lib/kajiya/src/renderers/rtdgi.rs
+//   PingPongTemporalResource                    crates/lib/kajiya/src/renderers/mod.rs:73-103
+//   camera / view constants                     crates/lib/kajiya/src/camera.rs, rust-shaders-shared/src/view_constants.rs
+// It only calls the C-ABI in include/kjb.h.  No GPU, CUDA or oracle symbols are referenced directly.
+#include "../../../include/kjb_world.h"
+#include <cmath>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+namespace {
+
+// ---------------------------------------------------------------- small column-major mat4 helpers (glam conventions)
+struct M4 { float m[16]; };
+M4 m4_identity() { M4 r{}; r.m[0] = r.m[5] = r.m[10] = r.m[15] = 1; return r; }
+M4 m4_mul(const M4& a, const M4& b) {
+    M4 r{};
+    for (int c = 0; c < 4; ++c) for (int rr = 0; rr < 4; ++rr) {
+        float s = 0; for (int k = 0; k < 4; ++k) s += a.m[k * 4 + rr] * b.m[c * 4 + k];
+        r.m[c * 4 + rr] = s;
+    }
+    return r;
+}
+M4 m4_from_quat(const float q[4]) {   // glam Mat4::from_quat
+    const float x = q[0], y = q[1], z = q[2], w = q[3];
+    const float x2 = x + x, y2 = y + y, z2 = z + z;
+    const float xx = x * x2, xy = x * y2, xz = x * z2, yy = y * y2, yz = y * z2, zz = z * z2, wx = w * x2, wy = w * y2, wz = w * z2;
+    M4 r = m4_identity();
+    r.m[0] = 1 - (yy + zz); r.m[1] = xy + wz; r.m[2] = xz - wy;
+    r.m[4] = xy - wz; r.m[5] = 1 - (xx + zz); r.m[6] = yz + wx;
+    r.m[8] = xz + wy; r.m[9] = yz - wx; r.m[10] = 1 - (xx + yy);
+    return r;
+}
+M4 m4_translation(float x, float y, float z) { M4 r = m4_identity(); r.m[12] = x; r.m[13] = y; r.m[14] = z; return r; }
+void m4_store(kjb_mat4& d, const M4& s) { memcpy(d.m, s.m, sizeof(d.m)); }
+
+struct CameraMatrices { M4 view_to_clip, clip_to_view, world_to_view, view_to_world; };
+
+CameraMatrices camera_matrices(const kjb_world_frame& f, float aspect) {   // camera.rs:71-125
+    CameraMatrices c;
+    const float q[4] = {f.camera_rotation[0], f.camera_rotation[1], f.camera_rotation[2], f.camera_rotation[3]};
+    const float qc[4] = {-q[0], -q[1], -q[2], q[3]};
+    c.view_to_world = m4_mul(m4_translation(f.camera_position[0], f.camera_position[1], f.camera_position[2]), m4_from_quat(q));
+    c.world_to_view = m4_mul(m4_from_quat(qc), m4_translation(-f.camera_position[0], -f.camera_position[1], -f.camera_position[2]));
+    const float fov = (f.vertical_fov_deg > 0 ? f.vertical_fov_deg : 52.0f) * 3.14159265358979323846f / 180.0f;
+    const float znear = f.near_plane > 0 ? f.near_plane : 0.01f;
+    const float h = std::cos(0.5f * fov) / std::sin(0.5f * fov);
+    const float w = h / aspect;
+    M4 v2c{}; v2c.m[0] = w; v2c.m[5] = h; v2c.m[11] = -1.0f; v2c.m[14] = znear;
+    M4 c2v{}; c2v.m[0] = 1.0f / w; c2v.m[5] = 1.0f / h; c2v.m[11] = 1.0f / znear; c2v.m[14] = -1.0f;
+    c.view_to_clip = v2c; c.clip_to_view = c2v;
+    return c;
+}
+
+float radical_inverse(uint32_t n, uint32_t base) {   // world_renderer.rs:1116-1129
+    float val = 0.0f; const float inv_base = 1.0f / float(base); float inv_bi = inv_base;
+    while (n > 0) { uint32_t d = n % base; val += float(d) * inv_bi; n = uint32_t(float(n) * inv_base); inv_bi *= inv_base; }
+    return val;
+}
+
+uint32_t pack_unit_direction_11_10_11(float x, float y, float z) {   // kajiya-asset/src/mesh.rs:452-458 (truncating!)
+    auto cl = [](float v) { return v < -1.0f ? -1.0f : (v > 1.0f ? 1.0f : v); };
+    uint32_t xi = uint32_t((cl(x) * 0.5f + 0.5f) * float((1u << 11) - 1u));
+    uint32_t yi = uint32_t((cl(y) * 0.5f + 0.5f) * float((1u << 10) - 1u));
+    uint32_t zi = uint32_t((cl(z) * 0.5f + 0.5f) * float((1u << 11) - 1u));
+    return (zi << 21) | (yi << 11) | xi;
+}
+
+struct PingPong {   // renderers/mod.rs:73-103
+    std::string output_key, history_key;
+    explicit PingPong(const std::string& name) : output_key(name + ":0"), history_key(name + ":1") {}
+};
+
+}  // namespace
+
+struct kjb_world {
+    kjb_context* ctx = nullptr;
+    kjb_world_desc desc{};
+    uint32_t W = 0, H = 0, HW = 0, HH = 0;
+    uint32_t frame_idx = 0;
+    bool have_prev_camera = false;
+    CameraMatrices prev_camera{};
+
+    // scene (WorldRenderer fields)
+    std::vector<uint8_t> vertex_buffer;
+    std::vector<kjb_gpu_mesh> meshes;
+    std::vector<uint32_t> mesh_index_counts;
+    std::vector<std::vector<kjb_triangle_light>> mesh_lights;
+    std::vector<kjb_instance> instances;
+    std::vector<std::vector<uint8_t>> texture_storage;
+    std::vector<kjb_texture_desc> textures;
+    bool geometry_dirty = true;
+
+    std::map<std::string, kjb_image> images;
+    std::string names_cache;
+    std::string stop_after;
+    bool stopped = false;
+    uint64_t stats[4] = {0, 0, 0, 0};
+    uint64_t launches_at_frame_start = 0;
+    bool sky_valid = false; float sky_sun[3] = {0, 0, 0};
+    bool lut_ready = false, noise_ready = false, ssao_filled = false;
+
+    PingPong temporal_radiance_tex{"rtdgi.radiance"}, temporal_ray_orig_tex{"rtdgi.ray_orig"}, temporal_ray_tex{"rtdgi.ray"},
+        temporal_reservoir_tex{"rtdgi.reservoir"}, temporal_candidate_tex{"rtdgi.candidate"}, temporal_invalidity_tex{"rtdgi.invalidity"},
+        temporal2_tex{"rtdgi.temporal2"}, temporal2_variance_tex{"rtdgi.temporal2_var"}, temporal_hit_normal_tex{"rtdgi.hit_normal"};
+
+    int err = 0;
+
+    // rg.create / get_or_create_temporal: allocate once per name, zero-filled
+    kjb_image& img(const std::string& name, uint32_t w, uint32_t h, uint32_t fmt, uint32_t layers = 1) {
+        auto it = images.find(name);
+        if (it != images.end()) return it->second;
+        kjb_image i{};
+        if (kjb_image_alloc(ctx, w, h, layers, fmt, &i)) err = 1;
+        names_cache.clear();
+        return images.emplace(name, i).first->second;
+    }
+    void get_output_and_history(PingPong& pp, uint32_t w, uint32_t h, uint32_t fmt, kjb_image*& out, kjb_image*& hist) {
+        out = &img(pp.output_key, w, h, fmt);
+        hist = &img(pp.history_key, w, h, fmt);
+        std::swap(pp.output_key, pp.history_key);
+    }
+    // returns true if passes should keep running
+    bool pass_done(const char* label, int rc) {
+        if (rc) err = rc;
+        stats[3]++;
+        if (!stop_after.empty() && stop_after == label) stopped = true;
+        return !stopped && !err;
+    }
+};
+
+#define RUN(label, call) do { if (w->stopped || w->err) break; if (!w->pass_done(label, (call))) {} } while (0)
+
+static void size4(float out[4], const kjb_image& i) { out[0] = float(i.width); out[1] = float(i.height); out[2] = 1.0f / float(i.width); out[3] = 1.0f / float(i.height); }
+
+extern "C" {
+
+int kjb_world_create(kjb_context* ctx, const kjb_world_desc* desc, kjb_world** out) {
+    kjb_world* w = new kjb_world();
+    w->ctx = ctx; w->desc = *desc;
+    if (w->desc.spatial_reuse_pass_count == 0) w->desc.spatial_reuse_pass_count = 2;
+    w->W = desc->render_width; w->H = desc->render_height;
+    w->HW = (w->W + 1) / 2; w->HH = (w->H + 1) / 2;   // ImageDesc::half_res = div_up (image.rs:140-142)
+    *out = w;
+    return 0;
+}
+void kjb_world_destroy(kjb_world* w) {
+    if (!w) return;
+    for (auto& kv : w->images) kjb_image_free(w->ctx, &kv.second);
+    delete w;
+}
+
+int kjb_world_add_mesh(kjb_world* w, const kjb_mesh_desc* mesh, uint32_t* out_handle) {
+    const uint32_t mesh_idx = uint32_t(w->meshes.size());
+    // bindless textures: one id per map of this mesh (add_mesh dedups identical assets; ids are per-upload here)
+    const uint32_t tex_base = uint32_t(w->textures.size());
+    for (uint32_t i = 0; i < mesh->map_count; ++i) {
+        const kjb_texture_desc& t = mesh->maps[i];
+        size_t bytes = 0; for (uint32_t m = 0; m < t.mip_count; ++m) bytes += size_t(std::max(1u, t.width >> m)) * std::max(1u, t.height >> m) * 4;
+        w->texture_storage.emplace_back(t.texels, t.texels + bytes);
+        kjb_texture_desc d = t; d.texels = nullptr; w->textures.push_back(d);
+    }
+    std::vector<kjb_mesh_material> materials(mesh->materials, mesh->materials + mesh->material_count);
+    for (auto& mat : materials) {
+        for (int k = 0; k < 4; ++k) mat.maps[k] = tex_base + mat.maps[k];
+        if (mesh->use_lights) mat.flags |= 1u;   // MESH_MATERIAL_FLAG_EMISSIVE_USED_AS_LIGHT (world_renderer.rs:649-654)
+    }
+    // BufferBuilder::append order (world_renderer.rs:657-672): indices, verts, uvs, material ids, colors, tangents, materials
+    auto append = [&](const void* p, size_t bytes, size_t align) -> uint32_t {
+        size_t off = (w->vertex_buffer.size() + align - 1) / align * align;
+        w->vertex_buffer.resize(off + bytes);
+        if (bytes) memcpy(&w->vertex_buffer[off], p, bytes);
+        return uint32_t(off);
+    };
+    if (w->vertex_buffer.empty()) w->vertex_buffer.resize(16);   // keep offset 0 unused so `vertex_aux_offset != 0` stays meaningful
+    kjb_gpu_mesh gm{};
+    gm.index_offset = append(mesh->indices, size_t(mesh->index_count) * 4, 16);
+    std::vector<float> verts(size_t(mesh->vertex_count) * 4);
+    for (uint32_t i = 0; i < mesh->vertex_count; ++i) {
+        verts[i * 4 + 0] = mesh->positions[i * 3 + 0]; verts[i * 4 + 1] = mesh->positions[i * 3 + 1]; verts[i * 4 + 2] = mesh->positions[i * 3 + 2];
+        uint32_t pn = pack_unit_direction_11_10_11(mesh->normals[i * 3 + 0], mesh->normals[i * 3 + 1], mesh->normals[i * 3 + 2]);
+        memcpy(&verts[i * 4 + 3], &pn, 4);
+    }
+    gm.vertex_core_offset = append(verts.data(), verts.size() * 4, 16);
+    std::vector<float> uvs(size_t(mesh->vertex_count) * 2, 0.0f);
+    if (mesh->uvs) memcpy(uvs.data(), mesh->uvs, uvs.size() * 4);
+    gm.vertex_uv_offset = append(uvs.data(), uvs.size() * 4, 16);
+    gm.vertex_mat_offset = append(mesh->material_ids, size_t(mesh->vertex_count) * 4, 16);
+    std::vector<float> colors(size_t(mesh->vertex_count) * 4, 1.0f);
+    if (mesh->colors) memcpy(colors.data(), mesh->colors, colors.size() * 4);
+    gm.vertex_aux_offset = append(colors.data(), colors.size() * 4, 16);
+    gm.vertex_tangent_offset = 0;   // tangents only feed the (disabled, `#if 0`) normal-map branch of gbuffer.rchit.hlsl:117-158
+    gm.mat_data_offset = append(materials.data(), materials.size() * sizeof(kjb_mesh_material), 16);
+    w->meshes.push_back(gm);
+    w->mesh_index_counts.push_back(mesh->index_count);
+
+    // triangle-light extraction (world_renderer.rs:741-769)
+    std::vector<kjb_triangle_light> lights;
+    if (mesh->use_lights) {
+        for (uint32_t t = 0; t + 2 < mesh->index_count; t += 3) {
+            const uint32_t i0 = mesh->indices[t], i1 = mesh->indices[t + 1], i2 = mesh->indices[t + 2];
+            const kjb_mesh_material& mat = mesh->materials[mesh->material_ids[i0]];
+            if (!(mat.emissive[0] > 0 || mat.emissive[1] > 0 || mat.emissive[2] > 0)) continue;
+            kjb_triangle_light l{};
+            const uint32_t ids[3] = {i0, i1, i2};
+            for (int k = 0; k < 3; ++k) for (int c = 0; c < 3; ++c) l.verts[k][c] = mesh->positions[ids[k] * 3 + c];
+            for (int c = 0; c < 3; ++c) l.radiance[c] = mat.emissive[c];
+            lights.push_back(l);
+        }
+    }
+    w->mesh_lights.push_back(lights);
+    w->geometry_dirty = true;
+    if (out_handle) *out_handle = mesh_idx;
+    return 0;
+}
+
+int kjb_world_add_instance(kjb_world* w, uint32_t mesh, const float transform[12], uint32_t* out_handle) {
+    if (mesh >= w->meshes.size()) return 1;
+    kjb_instance i{}; memcpy(i.transform, transform, sizeof(i.transform)); i.mesh_index = mesh; i.emissive_multiplier = 1.0f;
+    w->instances.push_back(i);
+    if (out_handle) *out_handle = uint32_t(w->instances.size() - 1);
+    return 0;
+}
+
+int kjb_world_set_blue_noise(kjb_world* w, const uint8_t* rgba) {
+    kjb_image& bn = w->img("lut.blue_noise", 256, 256, KJB_FMT_RGBA8_UNORM);
+    int rc = kjb_image_upload(w->ctx, &bn, rgba);
+    w->noise_ready = true;
+    return rc | w->err;
+}
+
+uint32_t kjb_world_frame_index(kjb_world* w) { return w->frame_idx; }
+int kjb_world_get_image(kjb_world* w, const char* name, kjb_image* out) {
+    auto it = w->images.find(name); if (it == w->images.end()) return 1; *out = it->second; return 0;
+}
+const char* kjb_world_image_names(kjb_world* w) {
+    if (w->names_cache.empty()) for (auto& kv : w->images) { w->names_cache += kv.first; w->names_cache += '\n'; }
+    return w->names_cache.c_str();
+}
+int kjb_world_last_frame_stats(kjb_world* w, uint64_t out[4]) { memcpy(out, w->stats, sizeof(w->stats)); return 0; }
+int kjb_world_set_stop_after(kjb_world* w, const char* label) { w->stop_after = label ? label : ""; return 0; }
+
+// ---------------------------------------------------------------- per-frame constants (world_renderer.rs:1001-1108)
+static int begin_frame(kjb_world* w, const kjb_world_frame* f, kjb_frame_constants& fc, bool jitter) {
+    kjb_context* ctx = w->ctx;
+    w->stopped = false; w->stats[3] = 0;
+    w->launches_at_frame_start = kjb_launch_count(ctx);
+    if (w->geometry_dirty) {
+        for (size_t i = 0; i < w->textures.size(); ++i) w->textures[i].texels = w->texture_storage[i].data();
+        if (kjb_scene_set_geometry(ctx, w->vertex_buffer.data(), w->vertex_buffer.size(), w->meshes.data(), w->mesh_index_counts.data(), uint32_t(w->meshes.size()))) return 1;
+        if (kjb_scene_set_textures(ctx, w->textures.data(), uint32_t(w->textures.size()))) return 1;
+        w->geometry_dirty = false;
+    }
+    // "rebuild tlas" every frame (world_render_passes.rs:19); the library skips the rebuild when nothing moved
+    if (kjb_rebuild_tlas(ctx, w->instances.data(), uint32_t(w->instances.size()))) return 1;
+
+    const CameraMatrices cam = camera_matrices(*f, float(w->W) / float(w->H));
+    const CameraMatrices prev = w->have_prev_camera ? w->prev_camera : cam;
+    memset(&fc, 0, sizeof(fc));
+    kjb_view_constants& vc = fc.view_constants;
+    m4_store(vc.view_to_clip, cam.view_to_clip); m4_store(vc.clip_to_view, cam.clip_to_view);
+    m4_store(vc.world_to_view, cam.world_to_view); m4_store(vc.view_to_world, cam.view_to_world);
+    m4_store(vc.clip_to_prev_clip, m4_mul(m4_mul(m4_mul(prev.view_to_clip, prev.world_to_view), cam.view_to_world), cam.clip_to_view));
+    m4_store(vc.prev_view_to_prev_clip, prev.view_to_clip); m4_store(vc.prev_clip_to_prev_view, prev.clip_to_view);
+    m4_store(vc.prev_world_to_prev_view, prev.world_to_view); m4_store(vc.prev_view_to_prev_world, prev.view_to_world);
+    // TAA jitter: Halton(2,3) - 0.5 over 128 frames (world_renderer.rs:425-428, :979-981); none for the reference path tracer (:989)
+    float off[2] = {0, 0};
+    if (jitter) { const uint32_t i = (w->frame_idx % 128u) + 1u; off[0] = radical_inverse(i, 2) - 0.5f; off[1] = radical_inverse(i, 3) - 0.5f; }
+    vc.sample_offset_pixels[0] = off[0]; vc.sample_offset_pixels[1] = off[1];
+    vc.sample_offset_clip[0] = (2.0f * off[0]) / float(w->W); vc.sample_offset_clip[1] = (2.0f * off[1]) / float(w->H);
+    M4 jm = m4_identity(); jm.m[12] = -vc.sample_offset_clip[0]; jm.m[13] = -vc.sample_offset_clip[1];
+    M4 jmi = m4_identity(); jmi.m[12] = vc.sample_offset_clip[0]; jmi.m[13] = vc.sample_offset_clip[1];
+    m4_store(vc.view_to_sample, m4_mul(jm, cam.view_to_clip));
+    m4_store(vc.sample_to_view, m4_mul(cam.clip_to_view, jmi));
+
+    float sl = std::sqrt(f->sun_direction[0] * f->sun_direction[0] + f->sun_direction[1] * f->sun_direction[1] + f->sun_direction[2] * f->sun_direction[2]);
+    for (int c = 0; c < 3; ++c) fc.sun_direction[c] = f->sun_direction[c] / sl;
+    fc.frame_index = w->frame_idx;
+    fc.delta_time_seconds = f->delta_time_seconds > 0 ? f->delta_time_seconds : 1.0f / 60.0f;
+    fc.sun_angular_radius_cos = std::cos(1.0f * (0.53f * 3.14159265358979323846f / 180.0f) * 0.5f);
+    for (int c = 0; c < 3; ++c) { fc.sun_color_multiplier[c] = 1.0f; fc.sky_ambient[c] = 0.0f; }
+    fc.pre_exposure = fc.pre_exposure_prev = fc.pre_exposure_delta = 1.0f;   // dynamic exposure lives in post (out of scope): EV 0
+    fc.render_override_flags = 0; fc.render_override_material_roughness_scale = 1.0f;
+
+    // triangle lights: instance-transformed copies of each mesh's light set (world_renderer.rs:1036-1056)
+    std::vector<kjb_triangle_light> lights;
+    for (const kjb_instance& inst : w->instances) for (kjb_triangle_light l : w->mesh_lights[inst.mesh_index]) {
+        // to_scale_rotation_translation(): rotation = normalised columns, translation = last column; the scale is DROPPED (as upstream)
+        float rot[9];
+        for (int c = 0; c < 3; ++c) {
+            float cx = inst.transform[0 * 4 + c], cy = inst.transform[1 * 4 + c], cz = inst.transform[2 * 4 + c];
+            float len = std::sqrt(cx * cx + cy * cy + cz * cz); if (len == 0) len = 1;
+            rot[0 * 3 + c] = cx / len; rot[1 * 3 + c] = cy / len; rot[2 * 3 + c] = cz / len;
+        }
+        for (int k = 0; k < 3; ++k) {
+            float v[3] = {l.verts[k][0], l.verts[k][1], l.verts[k][2]};
+            for (int r = 0; r < 3; ++r) l.verts[k][r] = rot[r * 3 + 0] * v[0] + rot[r * 3 + 1] * v[1] + rot[r * 3 + 2] * v[2] + inst.transform[r * 4 + 3];
+        }
+        for (int c = 0; c < 3; ++c) l.radiance[c] *= inst.emissive_multiplier;
+        lights.push_back(l);
+    }
+    fc.triangle_light_count = uint32_t(lights.size());
+    if (kjb_set_frame_constants(ctx, &fc, lights.data(), fc.triangle_light_count)) return 1;
+    w->prev_camera = cam; w->have_prev_camera = true;
+
+    // bindless LUTs (default_world_renderer.rs:22-51): BRDF FG LUT computed once, blue noise supplied by the caller
+    kjb_image& fg = w->img("lut.brdf_fg", 64, 64, KJB_FMT_RGBA16_FLOAT);
+    kjb_image& bn = w->img("lut.blue_noise", 256, 256, KJB_FMT_RGBA8_UNORM);
+    if (!w->lut_ready) {
+        kjb_brdf_fg_lut_args la{}; la.output_tex = fg;
+        if (kjb_pass_brdf_fg_lut(ctx, &la)) return 1;
+        w->lut_ready = true;
+    }
+    if (kjb_set_luts(ctx, &fg, &bn)) return 1;
+    return w->err;
+}
+
+static void end_frame(kjb_world* w) {
+    uint64_t rays[2] = {0, 0};
+    kjb_ray_counters(w->ctx, rays, 1);
+    w->stats[0] = kjb_launch_count(w->ctx) - w->launches_at_frame_start;
+    w->stats[1] = rays[0]; w->stats[2] = rays[1];
+    w->frame_idx += 1;   // retire_frame (world_renderer.rs:1110-1113)
+}
+
+// ---------------------------------------------------------------- RtdgiRenderer::render (rtdgi.rs:173-554)
+static void rtdgi_render(kjb_world* w, kjb_image& reprojected_history_tex, kjb_image& temporal_output_tex, kjb_image& gbuffer, kjb_image& depth,
+                         kjb_image& geometric_normal, kjb_image& reprojection_map, kjb_image& sky_cube, kjb_image& ssao_tex) {
+    kjb_context* ctx = w->ctx;
+    const uint32_t HW = w->HW, HH = w->HH, W = w->W, H = w->H;
+    float gbuffer_size[4]; size4(gbuffer_size, gbuffer);
+    kjb_ircache_bindings no_ircache{};   // TODO(ircache): bind IrcacheRenderState when enable_ircache
+
+    kjb_image& half_ssao_tex = w->img("rtdgi.half_ssao", HW, HH, KJB_FMT_R8_SNORM);
+    { kjb_extract_half_res_args a{ssao_tex, half_ssao_tex}; RUN("extract ssao/2", kjb_pass_extract_half_res_ssao(ctx, &a)); }
+
+    kjb_image *hit_normal_output_tex, *hit_normal_history_tex; w->get_output_and_history(w->temporal_hit_normal_tex, HW, HH, KJB_FMT_RGBA8_UNORM, hit_normal_output_tex, hit_normal_history_tex);
+    kjb_image *candidate_output_tex, *candidate_history_tex; w->get_output_and_history(w->temporal_candidate_tex, HW, HH, KJB_FMT_RGBA16_FLOAT, candidate_output_tex, candidate_history_tex);
+    kjb_image& candidate_radiance_tex = w->img("rtdgi.candidate_radiance", HW, HH, KJB_FMT_RGBA16_FLOAT);
+    kjb_image& candidate_normal_tex = w->img("rtdgi.candidate_normal", HW, HH, KJB_FMT_RGBA8_SNORM);
+    kjb_image& candidate_hit_tex = w->img("rtdgi.candidate_hit", HW, HH, KJB_FMT_RGBA16_FLOAT);
+    kjb_image& temporal_reservoir_packed_tex = w->img("rtdgi.temporal_reservoir_packed", HW, HH, KJB_FMT_RGBA32_UINT);
+
+    kjb_image& half_depth_tex = w->img("half_depth", HW, HH, KJB_FMT_R32_FLOAT);
+    { kjb_extract_half_res_args a{depth, half_depth_tex}; RUN("extract half depth", kjb_pass_extract_half_res_depth(ctx, &a)); }
+
+    kjb_image *invalidity_output_tex, *invalidity_history_tex; w->get_output_and_history(w->temporal_invalidity_tex, HW, HH, KJB_FMT_RG16_FLOAT, invalidity_output_tex, invalidity_history_tex);
+    kjb_image *radiance_output_tex, *radiance_history_tex; w->get_output_and_history(w->temporal_radiance_tex, HW, HH, KJB_FMT_RGBA16_FLOAT, radiance_output_tex, radiance_history_tex);
+    kjb_image *ray_orig_output_tex, *ray_orig_history_tex; w->get_output_and_history(w->temporal_ray_orig_tex, HW, HH, KJB_FMT_RGBA32_FLOAT, ray_orig_output_tex, ray_orig_history_tex);
+    kjb_image *ray_output_tex, *ray_history_tex; w->get_output_and_history(w->temporal_ray_tex, HW, HH, KJB_FMT_RGBA16_FLOAT, ray_output_tex, ray_history_tex);
+
+    kjb_image& half_view_normal_tex = w->img("half_view_normal", HW, HH, KJB_FMT_RGBA8_SNORM);
+    { kjb_extract_half_res_args a{gbuffer, half_view_normal_tex}; RUN("extract view normal/2", kjb_pass_extract_half_res_view_normal(ctx, &a)); }
+
+    kjb_image& rt_history_validity_pre_input_tex = w->img("rtdgi.rt_history_validity_pre_input", HW, HH, KJB_FMT_R8_UNORM);
+    kjb_image *reservoir_output_tex, *reservoir_history_tex; w->get_output_and_history(w->temporal_reservoir_tex, HW, HH, KJB_FMT_RG32_UINT, reservoir_output_tex, reservoir_history_tex);
+
+    {   // "rtdgi validate" (rtdgi.rs:293-316)
+        kjb_rtdgi_validate_args a{};
+        a.half_view_normal_tex = half_view_normal_tex; a.depth_tex = depth; a.reprojected_gi_tex = reprojected_history_tex;
+        a.reservoir_tex = *reservoir_history_tex; a.reservoir_ray_history_tex = *ray_history_tex; a.reprojection_tex = reprojection_map;
+        a.ircache = no_ircache; a.sky_cube_tex = sky_cube; a.irradiance_history_tex = *radiance_history_tex; a.ray_orig_history_tex = *ray_orig_history_tex;
+        a.rt_history_invalidity_out_tex = rt_history_validity_pre_input_tex; memcpy(a.gbuffer_tex_size, gbuffer_size, 16);
+        RUN("rtdgi validate", kjb_pass_rtdgi_validate(ctx, &a));
+    }
+    kjb_image& rt_history_validity_input_tex = w->img("rtdgi.rt_history_validity_input", HW, HH, KJB_FMT_R8_UNORM);
+    {   // "rtdgi trace" (rtdgi.rs:321-345)
+        kjb_rtdgi_trace_args a{};
+        a.half_view_normal_tex = half_view_normal_tex; a.depth_tex = depth; a.reprojected_gi_tex = reprojected_history_tex; a.reprojection_tex = reprojection_map;
+        a.ircache = no_ircache; a.sky_cube_tex = sky_cube; a.ray_orig_history_tex = *ray_orig_history_tex;
+        a.candidate_irradiance_out_tex = candidate_radiance_tex; a.candidate_normal_out_tex = candidate_normal_tex; a.candidate_hit_out_tex = candidate_hit_tex;
+        a.rt_history_invalidity_in_tex = rt_history_validity_pre_input_tex; a.rt_history_invalidity_out_tex = rt_history_validity_input_tex;
+        memcpy(a.gbuffer_tex_size, gbuffer_size, 16);
+        RUN("rtdgi trace", kjb_pass_rtdgi_trace(ctx, &a));
+    }
+    {   // "validity integrate" (rtdgi.rs:347-361)
+        kjb_rtdgi_validity_integrate_args a{};
+        a.input_tex = rt_history_validity_input_tex; a.history_tex = *invalidity_history_tex; a.reprojection_tex = reprojection_map;
+        a.half_view_normal_tex = half_view_normal_tex; a.half_depth_tex = half_depth_tex; a.output_tex = *invalidity_output_tex;
+        memcpy(a.gbuffer_tex_size, gbuffer_size, 16); size4(a.output_tex_size, *invalidity_output_tex);
+        RUN("validity integrate", kjb_pass_rtdgi_validity_integrate(ctx, &a));
+    }
+    {   // "restir temporal" (rtdgi.rs:363-389)
+        kjb_rtdgi_restir_temporal_args a{};
+        a.half_view_normal_tex = half_view_normal_tex; a.depth_tex = depth; a.candidate_radiance_tex = candidate_radiance_tex; a.candidate_normal_tex = candidate_normal_tex;
+        a.candidate_hit_tex = candidate_hit_tex; a.radiance_history_tex = *radiance_history_tex; a.ray_orig_history_tex = *ray_orig_history_tex; a.ray_history_tex = *ray_history_tex;
+        a.reservoir_history_tex = *reservoir_history_tex; a.reprojection_tex = reprojection_map; a.hit_normal_history_tex = *hit_normal_history_tex;
+        a.candidate_history_tex = *candidate_history_tex; a.rt_invalidity_tex = *invalidity_output_tex;
+        a.radiance_out_tex = *radiance_output_tex; a.ray_orig_output_tex = *ray_orig_output_tex; a.ray_output_tex = *ray_output_tex; a.hit_normal_output_tex = *hit_normal_output_tex;
+        a.reservoir_out_tex = *reservoir_output_tex; a.candidate_out_tex = *candidate_output_tex; a.temporal_reservoir_packed_tex = temporal_reservoir_packed_tex;
+        memcpy(a.gbuffer_tex_size, gbuffer_size, 16);
+        RUN("restir temporal", kjb_pass_rtdgi_restir_temporal(ctx, &a));
+    }
+    kjb_image& radiance_tex = *radiance_output_tex;
+    kjb_image* reservoir_input_tex = reservoir_output_tex;
+    kjb_image* reservoir_output_tex0 = &w->img("rtdgi.reservoir_output0", HW, HH, KJB_FMT_RG32_UINT);
+    kjb_image* reservoir_output_tex1 = &w->img("rtdgi.reservoir_output1", HW, HH, KJB_FMT_RG32_UINT);
+    kjb_image none{};   // bounced radiance images only exist with RTDGI_RESTIR_SPATIAL_USE_RAYMARCH_COLOR_BOUNCE (off, rtdgi_restir_settings.hlsl:17)
+    for (uint32_t pass_idx = 0; pass_idx < w->desc.spatial_reuse_pass_count; ++pass_idx) {   // rtdgi.rs:428-476
+        kjb_rtdgi_restir_spatial_args a{};
+        a.reservoir_input_tex = *reservoir_input_tex; a.bounced_radiance_input_tex = none; a.half_view_normal_tex = half_view_normal_tex; a.half_depth_tex = half_depth_tex;
+        a.depth_tex = depth; a.half_ssao_tex = half_ssao_tex; a.temporal_reservoir_packed_tex = temporal_reservoir_packed_tex; a.reprojected_gi_tex = reprojected_history_tex;
+        a.reservoir_output_tex = *reservoir_output_tex0; a.bounced_radiance_output_tex = none;
+        memcpy(a.gbuffer_tex_size, gbuffer_size, 16); size4(a.output_tex_size, *reservoir_output_tex0);
+        a.spatial_reuse_pass_idx = pass_idx;
+        a.perform_occlusion_raymarch = (pass_idx + 1 == w->desc.spatial_reuse_pass_count) ? 1u : 0u;
+        a.occlusion_raymarch_importance_only = w->desc.use_raytraced_reservoir_visibility ? 1u : 0u;
+        RUN("restir spatial", kjb_pass_rtdgi_restir_spatial(ctx, &a));
+        std::swap(reservoir_output_tex0, reservoir_output_tex1);
+        reservoir_input_tex = reservoir_output_tex1;
+    }
+    kjb_image& irradiance_output_tex = w->img("rtdgi.irradiance", W, H, KJB_FMT_RGBA16_FLOAT);
+    {   // "restir resolve" (rtdgi.rs:502-523)
+        kjb_rtdgi_restir_resolve_args a{};
+        a.radiance_tex = radiance_tex; a.reservoir_input_tex = *reservoir_input_tex; a.gbuffer_tex = gbuffer; a.depth_tex = depth; a.half_view_normal_tex = half_view_normal_tex;
+        a.half_depth_tex = half_depth_tex; a.ssao_tex = ssao_tex; a.candidate_radiance_tex = candidate_radiance_tex; a.candidate_hit_tex = candidate_hit_tex;
+        a.temporal_reservoir_packed_tex = temporal_reservoir_packed_tex; a.bounced_radiance_input_tex = none; a.irradiance_output_tex = irradiance_output_tex;
+        memcpy(a.gbuffer_tex_size, gbuffer_size, 16); size4(a.output_tex_size, irradiance_output_tex);
+        RUN("restir resolve", kjb_pass_rtdgi_restir_resolve(ctx, &a));
+    }
+    // RtdgiRenderer::temporal (rtdgi.rs:71-115)
+    kjb_image *temporal_variance_output_tex, *variance_history_tex; w->get_output_and_history(w->temporal2_variance_tex, W, H, KJB_FMT_RG16_FLOAT, temporal_variance_output_tex, variance_history_tex);
+    kjb_image& temporal_filtered_tex = w->img("rtdgi.temporal_filtered", W, H, KJB_FMT_RGBA16_FLOAT);
+    {
+        kjb_rtdgi_temporal_args a{};
+        a.input_tex = irradiance_output_tex; a.history_tex = reprojected_history_tex; a.variance_history_tex = *variance_history_tex; a.reprojection_tex = reprojection_map;
+        a.rt_history_invalidity_tex = *invalidity_output_tex; a.output_tex = temporal_filtered_tex; a.history_output_tex = temporal_output_tex;
+        a.variance_history_output_tex = *temporal_variance_output_tex;
+        size4(a.output_tex_size, temporal_output_tex); memcpy(a.gbuffer_tex_size, gbuffer_size, 16);
+        RUN("rtdgi temporal", kjb_pass_rtdgi_temporal(ctx, &a));
+    }
+    // RtdgiRenderer::spatial (rtdgi.rs:117-141)
+    kjb_image& spatial_filtered_tex = w->img("rtdgi.spatial_filtered", W, H, KJB_FMT_RGBA16_FLOAT);
+    {
+        kjb_rtdgi_spatial_args a{};
+        a.input_tex = temporal_filtered_tex; a.depth_tex = depth; a.ssao_tex = ssao_tex; a.geometric_normal_tex = geometric_normal; a.output_tex = spatial_filtered_tex;
+        size4(a.output_tex_size, spatial_filtered_tex);
+        RUN("rtdgi spatial", kjb_pass_rtdgi_spatial(ctx, &a));
+    }
+}
+
+int kjb_world_render_frame(kjb_world* w, const kjb_world_frame* f) {
+    kjb_context* ctx = w->ctx;
+    kjb_frame_constants fc;
+    if (begin_frame(w, f, fc, true)) return 1;
+    const uint32_t W = w->W, H = w->H;
+
+    // sky cube + convolved sky (world_render_passes.rs:33-38, renderers/sky.rs); recomputed only when the sun moves
+    kjb_image& sky_cube = w->img("sky_cube", 64, 64, KJB_FMT_RGBA16_FLOAT, 6);
+    kjb_image& convolved_sky_cube = w->img("convolved_sky_cube", 16, 16, KJB_FMT_RGBA16_FLOAT, 6);
+    if (!w->sky_valid || memcmp(w->sky_sun, fc.sun_direction, 12) != 0) {
+        { kjb_sky_cube_args a{sky_cube}; RUN("sky cube", kjb_pass_sky_cube(ctx, &a)); }
+        { kjb_convolve_sky_args a{sky_cube, convolved_sky_cube, 16}; RUN("convolve sky", kjb_pass_convolve_sky(ctx, &a)); }
+        w->sky_valid = true; memcpy(w->sky_sun, fc.sun_direction, 12);
+    }
+
+    // G-buffer + depth + geometric normal + velocity (world_render_passes.rs:40-82)
+    kjb_image& geometric_normal = w->img("geometric_normal", W, H, KJB_FMT_A2R10G10B10_UNORM);
+    kjb_image& gbuffer = w->img("gbuffer", W, H, KJB_FMT_RGBA32_FLOAT);
+    kjb_image& depth = w->img("depth", W, H, KJB_FMT_R32_FLOAT);
+    kjb_image& velocity = w->img("velocity", W, H, KJB_FMT_RGBA16_FLOAT);
+    if (f->host_gbuffer) {
+        int rc = kjb_image_upload(ctx, &gbuffer, f->host_gbuffer) | kjb_image_upload(ctx, &depth, f->host_depth)
+               | kjb_image_upload(ctx, &geometric_normal, f->host_geometric_normal) | kjb_image_upload(ctx, &velocity, f->host_velocity);
+        if (rc) return rc;
+    } else {
+        kjb_raster_gbuffer_args a{geometric_normal, gbuffer, depth, velocity};
+        RUN("raster simple", kjb_pass_raster_gbuffer(ctx, &a));
+    }
+    // reprojection map + copy depth (renderers/reprojection.rs:6-52)
+    kjb_image& reprojection_map = w->img("reprojection_map", W, H, KJB_FMT_RGBA16_SNORM);
+    kjb_image& prev_depth = w->img("reprojection.prev_depth", W, H, KJB_FMT_R32_FLOAT);
+    {
+        kjb_reprojection_map_args a{}; a.depth_tex = depth; a.geometric_normal_tex = geometric_normal; a.prev_depth_tex = prev_depth; a.velocity_tex = velocity; a.output_tex = reprojection_map;
+        size4(a.output_tex_size, reprojection_map);
+        RUN("reprojection map", kjb_pass_reprojection_map(ctx, &a));
+        RUN("copy depth", kjb_image_copy(ctx, &prev_depth, &depth));
+    }
+    // SSAO guides the rtdgi kernels only; ssgi.rs is outside the hot path: constant 1.0 ("no occlusion"), SURVEY §8d input 2
+    kjb_image& ssao_tex = w->img("ssao", W, H, KJB_FMT_R8_UNORM);
+    if (!w->ssao_filled) { kjb_image_fill_u8(ctx, &ssao_tex, 255); w->ssao_filled = true; }
+
+    // rtdgi.reproject (world_render_passes.rs:129, rtdgi.rs:143-171)
+    kjb_image *temporal_output_tex, *history_tex; w->get_output_and_history(w->temporal2_tex, W, H, KJB_FMT_RGBA16_FLOAT, temporal_output_tex, history_tex);
+    kjb_image& reprojected_history_tex = w->img("rtdgi.reprojected_history", W, H, KJB_FMT_RGBA16_FLOAT);
+    {
+        kjb_rtdgi_reproject_args a{}; a.input_tex = *history_tex; a.reprojection_tex = reprojection_map; a.output_tex = reprojected_history_tex;
+        size4(a.output_tex_size, reprojected_history_tex);
+        RUN("rtdgi reproject", kjb_pass_rtdgi_reproject(ctx, &a));
+    }
+    // rtdgi.render (world_render_passes.rs:146-160): diffuse rays use the convolved sky cube
+    rtdgi_render(w, reprojected_history_tex, *temporal_output_tex, gbuffer, depth, geometric_normal, reprojection_map, convolved_sky_cube, ssao_tex);
+
+    if (f->host_result && !w->err) {
+        kjb_image result{};
+        if (kjb_world_get_image(w, "rtdgi.spatial_filtered", &result) == 0) { kjb_image_download(ctx, &result, f->host_result); kjb_sync(ctx); }
+    }
+    end_frame(w);
+    return w->err;
+}
+
+int kjb_world_render_reference(kjb_world* w, const kjb_world_frame* f, uint32_t indirect_only) {
+    kjb_frame_constants fc;
+    if (begin_frame(w, f, fc, false)) return 1;
+    kjb_image& accum = w->img("refpt.accum", w->W, w->H, KJB_FMT_RGBA32_FLOAT);
+    kjb_reference_pt_args a{accum, indirect_only};
+    RUN("reference pt", kjb_pass_reference_path_trace(w->ctx, &a));
+    if (f->host_result && !w->err) { kjb_image_download(w->ctx, &accum, f->host_result); kjb_sync(w->ctx); }
+    end_frame(w);
+    return w->err;
+}
+
+}  // extern "C"

@@ -1,0 +1,179 @@
+// C-ABI entry points: context, memory, scene upload, "rebuild tlas", frame constants (include/kjb.h).
+#include "kjb_context.h"
+
+using namespace kjb;
+
+extern "C" {
+
+int kjb_abi_version(void) { return KJB_ABI_VERSION; }
+#if defined(KJB_EMU)
+const char* kjb_backend_name(void) { return "emu-cpu"; }
+#else
+const char* kjb_backend_name(void) { return "cuda-sm100a"; }
+#endif
+
+static thread_local std::string g_create_error;
+
+int kjb_create(int device, kjb_context** out) {
+    *out = nullptr;
+#if !defined(KJB_EMU)
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) { g_create_error = "kjb_create: no CUDA device (this library has no CPU fallback)"; return 1; }
+    if (device < 0 || device >= n) { g_create_error = "kjb_create: invalid device ordinal"; return 1; }
+    if (cudaSetDevice(device) != cudaSuccess) { g_create_error = "kjb_create: cudaSetDevice failed"; return 1; }
+#endif
+    kjb_context* c = new kjb_context();
+    c->device = device;
+#if !defined(KJB_EMU)
+    if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; g_create_error = "kjb_create: stream creation failed"; return 1; }
+#endif
+    memset(&c->g, 0, sizeof(c->g));
+    c->d_ray_counters = (unsigned long long*)dev_alloc(2 * sizeof(unsigned long long));
+    c->g.scene.ray_counters = c->d_ray_counters;
+    c->g.scene.root = ~int32_t(0);
+    *out = c;
+    return 0;
+}
+void kjb_destroy(kjb_context* c) {
+    if (!c) return;
+    dev_sync(c);
+    dev_free(c->d_vertices); dev_free(c->d_meshes); dev_free(c->d_instances); dev_free(c->d_nodes); dev_free(c->d_tris); dev_free(c->d_tri_info);
+    dev_free(c->d_tex_data); dev_free(c->d_tex_desc); dev_free(c->d_lights); dev_free(c->d_ray_counters);
+#if !defined(KJB_EMU)
+    if (c->pinned_staging) cudaFreeHost(c->pinned_staging);
+    if (c->stream) cudaStreamDestroy(c->stream);
+#endif
+    delete c;
+}
+int kjb_sync(kjb_context* c) {
+    if (dev_sync(c)) return c->fail("kjb_sync: stream synchronize failed");
+    const char* e = dev_check(c); if (e) return c->fail(std::string("kjb_sync: ") + e);
+    return 0;
+}
+const char* kjb_last_error(kjb_context* c) { return c ? c->last_error.c_str() : g_create_error.c_str(); }
+uint64_t kjb_launch_count(kjb_context* c) { return c->launches; }
+void* kjb_stream(kjb_context* c) { return (void*)c->stream; }
+uint32_t kjb_format_texel_bytes(uint32_t f) { return texel_bytes(f); }
+
+int kjb_image_alloc(kjb_context* c, uint32_t w, uint32_t h, uint32_t layers, uint32_t fmt, kjb_image* out) {
+    if (!texel_bytes(fmt) || !w || !h) return c->fail("kjb_image_alloc: bad format or extent");
+    out->width = w; out->height = h; out->format = fmt; out->layers = layers ? layers : 1;
+    out->data = dev_alloc(image_bytes(*out));   // zero-filled
+    return out->data ? 0 : c->fail("kjb_image_alloc: out of device memory");
+}
+int kjb_image_free(kjb_context*, kjb_image* img) { dev_free(img->data); img->data = nullptr; return 0; }
+int kjb_image_clear(kjb_context* c, const kjb_image* img) { return dev_memset(c, img->data, 0, image_bytes(*img)); }
+int kjb_image_fill_u8(kjb_context* c, const kjb_image* img, uint32_t v) { return dev_memset(c, img->data, int(v), image_bytes(*img)); }
+int kjb_image_copy(kjb_context* c, const kjb_image* dst, const kjb_image* src) {
+    if (image_bytes(*dst) != image_bytes(*src) || dst->format != src->format) return c->fail("kjb_image_copy: extent/format mismatch");
+    return dev_d2d(c, dst->data, src->data, image_bytes(*dst));
+}
+int kjb_image_upload(kjb_context* c, const kjb_image* dst, const void* src) { return dev_h2d(c, dst->data, src, image_bytes(*dst)); }
+int kjb_image_download(kjb_context* c, const kjb_image* src, void* dst) { return dev_d2h(c, dst, src->data, image_bytes(*src)); }
+int kjb_buffer_alloc(kjb_context* c, uint64_t n, kjb_buffer* out) { out->data = dev_alloc(n); out->size_bytes = n; return out->data ? 0 : c->fail("kjb_buffer_alloc: out of device memory"); }
+int kjb_buffer_free(kjb_context*, kjb_buffer* b) { dev_free(b->data); b->data = nullptr; return 0; }
+int kjb_buffer_upload(kjb_context* c, const kjb_buffer* dst, uint64_t off, const void* src, uint64_t n) { return dev_h2d(c, (char*)dst->data + off, src, n); }
+int kjb_buffer_download(kjb_context* c, const kjb_buffer* src, uint64_t off, void* dst, uint64_t n) { return dev_d2h(c, dst, (const char*)src->data + off, n); }
+
+// ---------------------------------------------------------------------------------------------------------- scene
+int kjb_scene_set_geometry(kjb_context* c, const void* vb, uint64_t vb_bytes, const kjb_gpu_mesh* meshes, const uint32_t* counts, uint32_t n) {
+    dev_sync(c);
+    dev_free(c->d_vertices); dev_free(c->d_meshes);
+    c->h_vertices.assign((const uint8_t*)vb, (const uint8_t*)vb + vb_bytes);
+    c->h_meshes.assign(meshes, meshes + n); c->h_index_counts.assign(counts, counts + n);
+    c->d_vertices = (uint8_t*)dev_alloc(vb_bytes); c->d_meshes = (kjb_gpu_mesh*)dev_alloc(n * sizeof(kjb_gpu_mesh));
+    if (!c->d_vertices || !c->d_meshes) return c->fail("kjb_scene_set_geometry: out of device memory");
+    dev_h2d(c, c->d_vertices, c->h_vertices.data(), vb_bytes); dev_h2d(c, c->d_meshes, c->h_meshes.data(), n * sizeof(kjb_gpu_mesh));
+    c->g.scene.vertices = c->d_vertices; c->g.scene.meshes = c->d_meshes;
+    c->tlas_valid = false;
+    return dev_sync(c);
+}
+int kjb_scene_set_textures(kjb_context* c, const kjb_texture_desc* t, uint32_t n) {
+    dev_sync(c);
+    dev_free(c->d_tex_data); dev_free(c->d_tex_desc); c->d_tex_data = nullptr; c->d_tex_desc = nullptr;
+    std::vector<uint8_t> data; std::vector<uint4> desc(n);
+    for (uint32_t i = 0; i < n; ++i) {
+        size_t bytes = 0; for (uint32_t m = 0; m < t[i].mip_count; ++m) bytes += size_t(t[i].width >> m ? t[i].width >> m : 1) * (t[i].height >> m ? t[i].height >> m : 1) * 4;
+        desc[i] = u4(uint32_t(data.size()), t[i].width, t[i].height, t[i].mip_count | (t[i].srgb << 16));
+        data.insert(data.end(), t[i].texels, t[i].texels + bytes);
+        while (data.size() & 15) data.push_back(0);
+    }
+    c->tex_count = n;
+    if (n) {
+        c->d_tex_data = (uint8_t*)dev_alloc(data.size()); c->d_tex_desc = (uint4*)dev_alloc(n * sizeof(uint4));
+        if (!c->d_tex_data || !c->d_tex_desc) return c->fail("kjb_scene_set_textures: out of device memory");
+        dev_h2d(c, c->d_tex_data, data.data(), data.size()); dev_h2d(c, c->d_tex_desc, desc.data(), n * sizeof(uint4));
+    }
+    c->g.scene.tex_data = c->d_tex_data; c->g.scene.tex_desc = c->d_tex_desc; c->g.scene.tex_count = n;
+    return dev_sync(c);
+}
+
+// "rebuild tlas": flatten every instance's triangles to world space and rebuild the BVH.  Skipped when the instance
+// list is bit-identical to the previous call (static scenes), which is the steady state of every benchmark config.
+int kjb_rebuild_tlas(kjb_context* c, const kjb_instance* inst, uint32_t n) {
+    if (c->tlas_valid && c->h_instances.size() == n && (n == 0 || memcmp(c->h_instances.data(), inst, n * sizeof(kjb_instance)) == 0)) return 0;
+    dev_sync(c);
+    c->h_instances.assign(inst, inst + n);
+    std::vector<float> wt; std::vector<TriInfo> info;
+    for (uint32_t i = 0; i < n; ++i) {
+        if (inst[i].mesh_index >= c->h_meshes.size()) return c->fail("kjb_rebuild_tlas: instance references an unknown mesh");
+        const kjb_gpu_mesh& m = c->h_meshes[inst[i].mesh_index];
+        const uint32_t ntri = c->h_index_counts[inst[i].mesh_index] / 3;
+        const uint8_t* vb = c->h_vertices.data();
+        for (uint32_t p = 0; p < ntri; ++p) {
+            for (int k = 0; k < 3; ++k) {
+                uint32_t idx; memcpy(&idx, vb + m.index_offset + (p * 3 + k) * 4, 4);
+                float v[3]; memcpy(v, vb + m.vertex_core_offset + size_t(idx) * 16, 12);
+                const float3 w = xform_point(inst[i].transform, f3(v[0], v[1], v[2]));
+                wt.push_back(w.x); wt.push_back(w.y); wt.push_back(w.z);
+            }
+            TriInfo ti; ti.instance = i; ti.prim = p; info.push_back(ti);
+        }
+    }
+    HostBvh bvh;
+    build_bvh(wt.data(), info.data(), uint32_t(info.size()), bvh);
+    dev_free(c->d_nodes); dev_free(c->d_tris); dev_free(c->d_tri_info); dev_free(c->d_instances);
+    c->d_nodes = bvh.nodes.empty() ? nullptr : (BvhNode*)dev_alloc(bvh.nodes.size() * sizeof(BvhNode));
+    c->d_tris = (BvhTri*)dev_alloc(bvh.tris.size() * sizeof(BvhTri));
+    c->d_tri_info = (TriInfo*)dev_alloc((bvh.info.size() + 1) * sizeof(TriInfo));
+    c->d_instances = (kjb_instance*)dev_alloc((n + 1) * sizeof(kjb_instance));
+    if (c->d_nodes) dev_h2d(c, c->d_nodes, bvh.nodes.data(), bvh.nodes.size() * sizeof(BvhNode));
+    dev_h2d(c, c->d_tris, bvh.tris.data(), bvh.tris.size() * sizeof(BvhTri));
+    if (!bvh.info.empty()) dev_h2d(c, c->d_tri_info, bvh.info.data(), bvh.info.size() * sizeof(TriInfo));
+    if (n) dev_h2d(c, c->d_instances, inst, n * sizeof(kjb_instance));
+    c->g.scene.nodes = c->d_nodes; c->g.scene.tris = c->d_tris; c->g.scene.tri_info = c->d_tri_info; c->g.scene.instances = c->d_instances;
+    c->g.scene.tri_count = uint32_t(info.size()); c->g.scene.root = bvh.root_child;
+    c->tlas_valid = true;
+    return dev_sync(c);
+}
+
+int kjb_set_frame_constants(kjb_context* c, const kjb_frame_constants* fc, const kjb_triangle_light* lights, uint32_t n) {
+    if (fc->triangle_light_count != n) return c->fail("kjb_set_frame_constants: triangle_light_count mismatch");
+    c->g.fc = *fc;
+    // SUN_COLOR is a pure function of the frame constants (sun.hlsl:21-29): evaluate once here with the contract's math
+    const float3 sc = sun_color_in_direction(*fc, sun_direction(*fc));
+    c->g.sun_color[0] = sc.x; c->g.sun_color[1] = sc.y; c->g.sun_color[2] = sc.z; c->g.sun_color[3] = 0;
+    if (n > c->lights_capacity) { dev_sync(c); dev_free(c->d_lights); c->d_lights = (kjb_triangle_light*)dev_alloc(n * sizeof(kjb_triangle_light)); c->lights_capacity = n; }
+    if (n) {
+        // lights change rarely; a synchronous small copy keeps the host buffer lifetime trivial
+        dev_h2d(c, c->d_lights, lights, n * sizeof(kjb_triangle_light)); dev_sync(c);
+    }
+    c->g.lights = c->d_lights;
+    return 0;
+}
+int kjb_set_luts(kjb_context* c, const kjb_image* fg, const kjb_image* bn) {
+    if (!check_img(c, *fg, KJB_FMT_RGBA16_FLOAT, "kjb_set_luts", "brdf_fg_lut", 64, 64)) return 1;
+    if (!check_img(c, *bn, KJB_FMT_RGBA8_UNORM, "kjb_set_luts", "blue_noise", 256, 256)) return 1;
+    c->g.brdf_fg_lut = img_ro(*fg); c->g.blue_noise = img_ro(*bn);
+    return 0;
+}
+int kjb_ray_counters(kjb_context* c, uint64_t out[2], int reset) {
+    unsigned long long v[2] = {0, 0};
+    dev_d2h(c, v, c->d_ray_counters, sizeof(v));
+    if (dev_sync(c)) return c->fail("kjb_ray_counters: sync failed");
+    out[0] = v[0]; out[1] = v[1];
+    if (reset) dev_memset(c, c->d_ray_counters, 0, sizeof(v));
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,99 @@
+// Library context + the thin device-runtime layer the entry points use.
+// In the product this is the CUDA runtime on one stream of one B200.  When the translation unit is compiled by the
+// test-only CPU launch emulator (KJB_EMU, tests/emu/), the same six calls map to libc — that build is never shipped,
+// never loaded by kajiya_b200, and reports itself as "emu-cpu".
+#pragma once
+#include "kjb_trace.cuh"
+#include <string>
+#include <vector>
+#include <cstdio>
+#include <cstring>
+#include <cstdlib>
+
+#if defined(KJB_EMU)
+typedef void* kjb_stream_t;
+#else
+#include <cuda_runtime.h>
+typedef cudaStream_t kjb_stream_t;
+#endif
+
+struct kjb_context {
+    int device = 0;
+    kjb_stream_t stream = nullptr;
+    std::string last_error;
+    uint64_t launches = 0;
+
+    // scene
+    uint8_t* d_vertices = nullptr; size_t vertices_bytes = 0;
+    kjb_gpu_mesh* d_meshes = nullptr;
+    std::vector<uint8_t> h_vertices; std::vector<kjb_gpu_mesh> h_meshes; std::vector<uint32_t> h_index_counts;
+    kjb_instance* d_instances = nullptr; std::vector<kjb_instance> h_instances; bool tlas_valid = false;
+    kjb::BvhNode* d_nodes = nullptr; kjb::BvhTri* d_tris = nullptr; kjb::TriInfo* d_tri_info = nullptr;
+    uint8_t* d_tex_data = nullptr; uint4* d_tex_desc = nullptr; uint32_t tex_count = 0;
+    kjb_triangle_light* d_lights = nullptr; uint32_t lights_capacity = 0;
+    unsigned long long* d_ray_counters = nullptr;
+    void* pinned_staging = nullptr; size_t pinned_bytes = 0;
+
+    kjb::Globals g;   // host copy, passed by value to every kernel
+
+    int fail(const std::string& msg) { last_error = msg; return 1; }
+};
+
+namespace kjb {
+
+#if defined(KJB_EMU)
+inline void* dev_alloc(size_t n) { return calloc(n ? n : 1, 1); }
+inline void dev_free(void* p) { free(p); }
+inline int dev_h2d(kjb_context*, void* d, const void* h, size_t n) { memcpy(d, h, n); return 0; }
+inline int dev_d2h(kjb_context*, void* h, const void* d, size_t n) { memcpy(h, d, n); return 0; }
+inline int dev_d2d(kjb_context*, void* d, const void* s, size_t n) { memcpy(d, s, n); return 0; }
+inline int dev_memset(kjb_context*, void* d, int v, size_t n) { memset(d, v, n); return 0; }
+inline int dev_sync(kjb_context*) { return 0; }
+inline const char* dev_check(kjb_context*) { return nullptr; }
+#else
+inline void* dev_alloc(size_t n) { void* p = nullptr; if (cudaMalloc(&p, n ? n : 1) != cudaSuccess) return nullptr; cudaMemset(p, 0, n ? n : 1); return p; }
+inline void dev_free(void* p) { if (p) cudaFree(p); }
+inline int dev_h2d(kjb_context* c, void* d, const void* h, size_t n) { return cudaMemcpyAsync(d, h, n, cudaMemcpyHostToDevice, c->stream) != cudaSuccess; }
+inline int dev_d2h(kjb_context* c, void* h, const void* d, size_t n) { return cudaMemcpyAsync(h, d, n, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess; }
+inline int dev_d2d(kjb_context* c, void* d, const void* s, size_t n) { return cudaMemcpyAsync(d, s, n, cudaMemcpyDeviceToDevice, c->stream) != cudaSuccess; }
+inline int dev_memset(kjb_context* c, void* d, int v, size_t n) { return cudaMemsetAsync(d, v, n, c->stream) != cudaSuccess; }
+inline int dev_sync(kjb_context* c) { return cudaStreamSynchronize(c->stream) != cudaSuccess; }
+inline const char* dev_check(kjb_context*) { cudaError_t e = cudaGetLastError(); return e == cudaSuccess ? nullptr : cudaGetErrorString(e); }
+#endif
+
+inline uint32_t texel_bytes(uint32_t f) {
+    switch (f) {
+        case KJB_FMT_R32_FLOAT: case KJB_FMT_RG16_FLOAT: case KJB_FMT_RGBA8_UNORM: case KJB_FMT_RGBA8_SNORM:
+        case KJB_FMT_A2R10G10B10_UNORM: case KJB_FMT_R11G11B10_UFLOAT: case KJB_FMT_R32_UINT: return 4;
+        case KJB_FMT_RG32_UINT: case KJB_FMT_RGBA16_FLOAT: case KJB_FMT_RGBA16_SNORM: case KJB_FMT_RG32_FLOAT: return 8;
+        case KJB_FMT_RGBA32_FLOAT: case KJB_FMT_RGBA32_UINT: return 16;
+        case KJB_FMT_R8_UNORM: case KJB_FMT_R8_SNORM: return 1;
+        case KJB_FMT_R16_FLOAT: return 2;
+        default: return 0;
+    }
+}
+inline size_t image_bytes(const kjb_image& i) { return size_t(i.width) * i.height * (i.layers ? i.layers : 1) * texel_bytes(i.format); }
+
+// argument validation shared by all pass entry points: format + non-null + (optionally) extent
+inline bool check_img(kjb_context* c, const kjb_image& i, uint32_t fmt, const char* pass, const char* name, uint32_t w = 0, uint32_t h = 0) {
+    if (!i.data) { c->fail(std::string(pass) + ": image '" + name + "' is null"); return false; }
+    if (i.format != fmt) { c->fail(std::string(pass) + ": image '" + name + "' has format " + std::to_string(i.format) + ", expected " + std::to_string(fmt)); return false; }
+    if (w && (i.width != w || i.height != h)) { c->fail(std::string(pass) + ": image '" + name + "' has the wrong extent"); return false; }
+    return true;
+}
+
+}  // namespace kjb
+
+// ---- kernel launch: <<<>>> in the product; a serial block/thread loop under the test emulator
+#if defined(KJB_EMU)
+#define KJB_KERNEL(bounds) static void
+#define KJB_LAUNCH(ctx, kernel, dims, ...) do { kjb_emu::launch(dims, [&]() { kernel(__VA_ARGS__); }); (ctx)->launches++; } while (0)
+#else
+#define KJB_KERNEL(bounds) __global__ void __launch_bounds__(bounds)
+#define KJB_LAUNCH(ctx, kernel, dims, ...) do { kernel<<<dims, 0, (ctx)->stream>>>(__VA_ARGS__); (ctx)->launches++; } while (0)
+#endif
+#define KJB_DIMS(...) __VA_ARGS__
+#define KJB_GRID2D(W, H, BX, BY) dim3(((W) + (BX) - 1) / (BX), ((H) + (BY) - 1) / (BY), 1), dim3((BX), (BY), 1)
+#define KJB_PX int x = int(blockIdx.x * blockDim.x + threadIdx.x), y = int(blockIdx.y * blockDim.y + threadIdx.y)
+
+#define KJB_PASS_EPILOGUE(ctx, name) do { const char* e__ = kjb::dev_check(ctx); if (e__) return (ctx)->fail(std::string(name) + ": " + e__); return 0; } while (0)

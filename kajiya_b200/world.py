@@ -1,0 +1,133 @@
+"""Host-side mirror of kajiya's `WorldRenderer` for the hot path (crates/lib/kajiya/src/world_renderer.rs):
+add_mesh / add_instance / per-frame render, over the `kjb_world_*` C-ABI."""
+import ctypes as C
+import numpy as np
+from ._abi import Image, WorldDesc, WorldFrame, MeshDesc, MeshMaterial, TextureDesc, FMT_NUMPY, KjbError
+
+
+def quat_from_rotation_x(angle):
+    return (float(np.sin(angle / 2)), 0.0, 0.0, float(np.cos(angle / 2)))
+
+
+class World:
+    def __init__(self, lib, width, height, device=0, spatial_reuse_pass_count=2, enable_ircache=False, enable_rtr=False, enable_taa=False,
+                 upscale=None, tile=None):
+        self.lib = lib
+        self.d = lib.dll
+        self.ctx = C.c_void_p()
+        if self.d.kjb_create(device, C.byref(self.ctx)):
+            raise KjbError("kjb_create failed: " + (self.d.kjb_last_error(None) or b"").decode())
+        desc = WorldDesc(width, height, (upscale or (0, 0))[0], (upscale or (0, 0))[1], spatial_reuse_pass_count, 0,
+                         int(enable_ircache), int(enable_rtr), int(enable_taa), (tile or (0, 0))[0], (tile or (0, 0))[1])
+        self.w = C.c_void_p()
+        self._check(self.d.kjb_world_create(self.ctx, C.byref(desc), C.byref(self.w)))
+        self.width, self.height = width, height
+        self._keep = []
+
+    def _check(self, rc):
+        if rc:
+            raise KjbError(f"{self.lib.backend}: rc={rc}: " + (self.d.kjb_last_error(self.ctx) or b"").decode())
+
+    def close(self):
+        if self.w:
+            self.d.kjb_world_destroy(self.w); self.w = None
+        if self.ctx:
+            self.d.kjb_destroy(self.ctx); self.ctx = None
+
+    # -- scene -------------------------------------------------------------------------------------------------
+    def add_mesh(self, mesh, use_lights=False):
+        """mesh: dict(positions[n,3], normals[n,3], indices[m], material_ids[n], materials=[dict], uvs?, colors?)"""
+        pos = np.ascontiguousarray(mesh["positions"], np.float32); nrm = np.ascontiguousarray(mesh["normals"], np.float32)
+        idx = np.ascontiguousarray(mesh["indices"], np.uint32); mid = np.ascontiguousarray(mesh["material_ids"], np.uint32)
+        uvs = np.ascontiguousarray(mesh["uvs"], np.float32) if mesh.get("uvs") is not None else None
+        col = np.ascontiguousarray(mesh["colors"], np.float32) if mesh.get("colors") is not None else None
+        mats = (MeshMaterial * len(mesh["materials"]))()
+        maps = []
+        texel_keep = []
+        for i, m in enumerate(mesh["materials"]):
+            mm = mats[i]
+            mm.base_color_mult[:] = m.get("base_color", [1, 1, 1, 1])
+            mm.roughness_mult = m.get("roughness", 1.0); mm.metalness_factor = m.get("metallic", 1.0)
+            mm.emissive[:] = m.get("emissive", [0, 0, 0]); mm.flags = 0
+            for k in range(4):
+                mm.map_transforms[k * 6:(k + 1) * 6] = [1, 0, 0, 1, 0, 0]
+            # load_gltf_material (kajiya-asset/src/mesh.rs:120-255): placeholders for missing maps, order normal/spec/albedo/emissive
+            placeholders = [(127, 127, 255, 255), (255, 255, 127, 255), (255, 255, 255, 255), (255, 255, 255, 255)]
+            for k, key in enumerate(("normal_map", "spec_map", "albedo_map", "emissive_map")):
+                tex = m.get(key)
+                if tex is None:
+                    texels = np.array([placeholders[k]], np.uint8); w = h = mips = 1; srgb = 0
+                else:
+                    texels, w, h, mips, srgb = tex
+                texels = np.ascontiguousarray(texels, np.uint8); texel_keep.append(texels)
+                maps.append(TextureDesc(texels.ctypes.data, w, h, mips, srgb))
+                mm.maps[k] = len(maps) - 1
+        maps_arr = (TextureDesc * len(maps))(*maps)
+        md = MeshDesc(pos.ctypes.data, nrm.ctypes.data, uvs.ctypes.data if uvs is not None else None, col.ctypes.data if col is not None else None,
+                      mid.ctypes.data, idx.ctypes.data, len(pos), len(idx), mats, len(mats), maps_arr, len(maps), int(use_lights))
+        h = C.c_uint32()
+        self._check(self.d.kjb_world_add_mesh(self.w, C.byref(md), C.byref(h)))
+        return h.value
+
+    def add_instance(self, mesh, transform3x4):
+        t = (C.c_float * 12)(*np.asarray(transform3x4, np.float32).reshape(12))
+        h = C.c_uint32()
+        self._check(self.d.kjb_world_add_instance(self.w, mesh, C.byref(t), C.byref(h)))
+        return h.value
+
+    def set_blue_noise(self, rgba8):
+        a = np.ascontiguousarray(rgba8, np.uint8); assert a.size == 256 * 256 * 4
+        self._check(self.d.kjb_world_set_blue_noise(self.w, a.ctypes.data))
+
+    # -- frames ------------------------------------------------------------------------------------------------
+    def _frame(self, camera_position, camera_rotation, sun_direction, vfov=52.0, host_inputs=None, host_result=None):
+        f = WorldFrame()
+        f.camera_position[:] = camera_position; f.camera_rotation[:] = camera_rotation
+        f.vertical_fov_deg = vfov; f.near_plane = 0.01; f.sun_direction[:] = sun_direction; f.delta_time_seconds = 1.0 / 60.0
+        if host_inputs is not None:
+            f.host_gbuffer, f.host_depth, f.host_geometric_normal, f.host_velocity = host_inputs
+        if host_result is not None:
+            f.host_result = host_result
+        return f
+
+    def render_frame(self, camera_position, camera_rotation, sun_direction, **kw):
+        f = self._frame(camera_position, camera_rotation, sun_direction, **kw)
+        self._check(self.d.kjb_world_render_frame(self.w, C.byref(f)))
+
+    def render_reference(self, camera_position, camera_rotation, sun_direction, indirect_only=False, **kw):
+        f = self._frame(camera_position, camera_rotation, sun_direction, **kw)
+        self._check(self.d.kjb_world_render_reference(self.w, C.byref(f), int(indirect_only)))
+
+    def sync(self):
+        self._check(self.d.kjb_sync(self.ctx))
+
+    def stop_after(self, label):
+        self.d.kjb_world_set_stop_after(self.w, (label or "").encode())
+
+    @property
+    def frame_index(self):
+        return self.d.kjb_world_frame_index(self.w)
+
+    def stats(self):
+        s = (C.c_uint64 * 4)()
+        self.d.kjb_world_last_frame_stats(self.w, C.byref(s))
+        return dict(launches=s[0], closest_rays=s[1], any_hit_rays=s[2], passes=s[3])
+
+    # -- images ------------------------------------------------------------------------------------------------
+    def image_names(self):
+        return [n for n in self.d.kjb_world_image_names(self.w).decode().split("\n") if n]
+
+    def image_handle(self, name):
+        img = Image()
+        if self.d.kjb_world_get_image(self.w, name.encode(), C.byref(img)):
+            raise KeyError(name)
+        return img
+
+    def image(self, name):
+        """Download an image as a numpy array [layers*height, width, components] of its storage dtype."""
+        img = self.image_handle(name)
+        dt, comps = FMT_NUMPY[img.format]
+        out = np.empty((img.layers * img.height, img.width, comps), dt)
+        self._check(self.d.kjb_image_download(self.ctx, C.byref(img), out.ctypes.data))
+        self.sync()
+        return out

@@ -1,0 +1,83 @@
+// ORACLE — TEST INFRASTRUCTURE ONLY (see kj_math.h header).
+// The oracle exports the same C-ABI (include/kjb.h) as the CUDA library so the test harness and the
+// host-side frame driver can run either behind identical calls.  "Device" memory is host memory here.
+#include "kj_ctx.h"
+#include <cstdlib>
+
+namespace kjo {
+
+extern "C" {
+
+int kjb_abi_version(void) { return KJB_ABI_VERSION; }
+const char* kjb_backend_name(void) { return "oracle-cpu"; }
+int kjb_create(int, kjb_context** out) { *out = new kjb_context(); const char* e = getenv("KJO_THREADS"); if (e) (*out)->num_threads = atoi(e); return 0; }
+void kjb_destroy(kjb_context* c) { delete c; }
+int kjb_sync(kjb_context*) { return 0; }
+const char* kjb_last_error(kjb_context* c) { return c ? c->last_error.c_str() : ""; }
+uint64_t kjb_launch_count(kjb_context*) { return 0; }
+void* kjb_stream(kjb_context*) { return nullptr; }
+uint32_t kjb_format_texel_bytes(uint32_t f) { return format_texel_bytes(f); }
+
+int kjb_image_alloc(kjb_context*, uint32_t w, uint32_t h, uint32_t layers, uint32_t fmt, kjb_image* out) {
+    size_t bytes = size_t(w) * h * (layers ? layers : 1) * format_texel_bytes(fmt);
+    out->data = calloc(bytes ? bytes : 1, 1); out->width = w; out->height = h; out->format = fmt; out->layers = layers ? layers : 1;
+    return out->data ? 0 : 1;
+}
+int kjb_image_free(kjb_context*, kjb_image* img) { free(img->data); img->data = nullptr; return 0; }
+static size_t img_bytes(const kjb_image* i) { return size_t(i->width) * i->height * i->layers * format_texel_bytes(i->format); }
+int kjb_image_clear(kjb_context*, const kjb_image* img) { memset(img->data, 0, img_bytes(img)); return 0; }
+int kjb_image_copy(kjb_context*, const kjb_image* dst, const kjb_image* src) { memcpy(dst->data, src->data, img_bytes(dst)); return 0; }
+int kjb_image_fill_u8(kjb_context*, const kjb_image* img, uint32_t v) { memset(img->data, int(v), img_bytes(img)); return 0; }
+int kjb_image_upload(kjb_context*, const kjb_image* dst, const void* src) { memcpy(dst->data, src, img_bytes(dst)); return 0; }
+int kjb_image_download(kjb_context*, const kjb_image* src, void* dst) { memcpy(dst, src->data, img_bytes(src)); return 0; }
+int kjb_buffer_alloc(kjb_context*, uint64_t n, kjb_buffer* out) { out->data = calloc(n ? n : 1, 1); out->size_bytes = n; return out->data ? 0 : 1; }
+int kjb_buffer_free(kjb_context*, kjb_buffer* b) { free(b->data); b->data = nullptr; return 0; }
+int kjb_buffer_upload(kjb_context*, const kjb_buffer* dst, uint64_t off, const void* src, uint64_t n) { memcpy((char*)dst->data + off, src, n); return 0; }
+int kjb_buffer_download(kjb_context*, const kjb_buffer* src, uint64_t off, void* dst, uint64_t n) { memcpy(dst, (char*)src->data + off, n); return 0; }
+
+int kjb_scene_set_geometry(kjb_context* c, const void* vb, uint64_t vb_bytes, const kjb_gpu_mesh* meshes, const uint32_t* counts, uint32_t n) {
+    c->scene.vertices.assign((const uint8_t*)vb, (const uint8_t*)vb + vb_bytes);
+    c->scene.meshes.assign(meshes, meshes + n);
+    c->scene.mesh_index_counts.assign(counts, counts + n);
+    return 0;
+}
+int kjb_scene_set_textures(kjb_context* c, const kjb_texture_desc* t, uint32_t n) {
+    c->scene.textures.clear();
+    for (uint32_t i = 0; i < n; ++i) {
+        Texture tx; tx.width = t[i].width; tx.height = t[i].height; tx.mip_count = t[i].mip_count; tx.srgb = t[i].srgb;
+        const uint8_t* p = t[i].texels;
+        for (uint32_t m = 0; m < tx.mip_count; ++m) {
+            size_t w = std::max(1u, tx.width >> m), h = std::max(1u, tx.height >> m);
+            tx.mips.emplace_back(p, p + w * h * 4); p += w * h * 4;
+        }
+        c->scene.textures.push_back(std::move(tx));
+    }
+    return 0;
+}
+int kjb_rebuild_tlas(kjb_context* c, const kjb_instance* inst, uint32_t n) { c->scene.rebuild_tlas(inst, n); return 0; }
+int kjb_set_frame_constants(kjb_context* c, const kjb_frame_constants* fc, const kjb_triangle_light* lights, uint32_t n) {
+    c->g.fc = *fc; c->g.lights.assign(lights, lights + n);
+    if (fc->triangle_light_count != n) { c->last_error = "triangle_light_count mismatch"; return 1; }
+    return 0;
+}
+int kjb_set_luts(kjb_context* c, const kjb_image* fg, const kjb_image* bn) { c->g.brdf_fg_lut = Img(*fg); c->g.blue_noise = Img(*bn); return 0; }
+int kjb_ray_counters(kjb_context* c, uint64_t out[2], int reset) {
+    out[0] = c->scene.n_closest.load(); out[1] = c->scene.n_any.load();
+    if (reset) { c->scene.n_closest = 0; c->scene.n_any = 0; }
+    return 0;
+}
+
+// test-only helpers (not part of kjb.h): brute-force vs BVH closest hit for the traversal self-check
+int kjo_trace_closest(kjb_context* c, const float* rays /* n x 8: o.xyz, tmin, d.xyz, tmax */, uint32_t n, int brute, float* out_t, uint32_t* out_tri) {
+    for (uint32_t i = 0; i < n; ++i) {
+        Ray r; r.origin = float3(rays[i * 8], rays[i * 8 + 1], rays[i * 8 + 2]); r.tmin = rays[i * 8 + 3];
+        r.dir = float3(rays[i * 8 + 4], rays[i * 8 + 5], rays[i * 8 + 6]); r.tmax = rays[i * 8 + 7];
+        Scene::HitInfo h = brute ? c->scene.closest_brute(r, false) : c->scene.closest(r, false);
+        out_t[i] = h.hit ? h.t : -1.0f; out_tri[i] = h.tri;
+    }
+    return 0;
+}
+
+}  // extern "C"
+
+}  // namespace kjo
