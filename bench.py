@@ -1,0 +1,304 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the B200-native kajiya ReSTIR-GI hot path.
+
+    python bench.py --gpus N --steps K --warmup W            # this implementation (CUDA, sm_100a)
+    python bench.py --impl reference --gpus N --steps K ...  # the CPU restatement of the reference's path, host cores
+
+A "step" is one frame of the hot path (rtdgi reproject -> validate/trace -> ReSTIR temporal/spatial -> resolve ->
+temporal+spatial filter, 15 kernels) over one synthetic batch of G-buffer inputs.  Workload at N=1: BASELINE.json configs[1],
+"Cornell box, 1080p, ReSTIR GI 1 spatial + 1 temporal pass".  Metric: GI rays/s (closest-hit + any-hit rays actually
+traced, counted on the device) with ms/frame as `ms_per_step`.
+
+`value`    : inputs (the frame's G-buffer/depth/normal/velocity) already resident in HBM (device ring, captured untimed).
+`e2e`      : the same frames through the public host-buffer call (kjb_world_render_frame with pinned HOST G-buffer inputs
+             uploaded and the result irradiance image downloaded inside the timed region).
+`roofline` : achieved HBM GB/s of the dominant kernel = algorithmic bytes of that pass (SURVEY.md §8a per-pixel figures x
+             pixels) / its mean launch duration (CUDA events on the launch stream, profiling pass over the same K frames).
+`cpu_baseline`: the oracle (CPU port of the reference shaders) on the host cores over a bounded sample of the same workload.
+"""
+import argparse, ctypes as C, json, os, subprocess, sys, threading, time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (scene fn name, kwargs, width, height, spatial passes)
+    "cornell_1080p_rtdgi_1s1t": ("cornell_box", {}, 1920, 1080, 1),
+    "cornell_256_rtdgi": ("cornell_box", {}, 256, 256, 1),
+    "atrium_1080p_rtdgi": ("atrium", {}, 1920, 1080, 2),
+}
+
+# compulsory bytes per pixel of each pass at its own grid (F = full-res px, Hh = half-res px)
+PASS_BYTES = {
+    "rtdgi reproject": ("F", 24), "extract ssao/2": ("Hh", 2), "extract half depth": ("Hh", 8), "extract view normal/2": ("Hh", 20),
+    "rtdgi validate": ("Hh", 5), "rtdgi trace": ("Hh", 38), "validity integrate": ("Hh", 21), "restir temporal": ("Hh", 160),
+    "restir spatial": ("Hh", 41), "restir resolve": ("F+Hh", (29, 56)), "rtdgi temporal": ("F+Hh", (48, 4)), "rtdgi spatial": ("F", 25),
+}
+
+
+def pass_bytes(label, F, Hh, validation_frame_fraction=1.0 / 3.0):
+    kind, b = PASS_BYTES[label]
+    if label == "rtdgi validate":
+        return Hh * (5 + 61 * validation_frame_fraction)
+    if kind == "F":
+        return F * b
+    if kind == "Hh":
+        return Hh * b
+    return F * b[0] + Hh * b[1]
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, gpu_index):
+        self.samples, self.proc, self.gpu = [], None, gpu_index
+
+    def start(self):
+        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.gpu}", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True); self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = sorted(int(float(s[0])) for s in self.samples if s and s[0].replace(".", "").isdigit())
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            for i, n in enumerate(names):
+                if len(s) > 3 + i and s[3 + i].lower().startswith("active"):
+                    reasons.add(n)
+        mx = None
+        for s in self.samples:
+            if len(s) > 1 and s[1].replace(".", "").isdigit():
+                mx = int(float(s[1]))
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return json.load(open(p)).get("hbm_gbs", 6650.0), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def build_world(lib, workload, device=0, tile=None):
+    from kajiya_b200 import scenes
+    from kajiya_b200.world import World
+    fn, kw, W, H, spatial = WORKLOADS[workload]
+    scene, view = getattr(scenes, fn)(**kw)
+    w = World(lib, W, H, device=device, spatial_reuse_pass_count=spatial, tile=tile)
+    scenes.populate(w, scene)
+    return w, view, W, H
+
+
+def pinned_empty(torch, nbytes):
+    return torch.empty(nbytes, dtype=torch.uint8).pin_memory()
+
+
+def run_cuda(args):
+    import numpy as np, torch
+    import kajiya_b200
+    rank = int(os.environ.get("RANK", "0")); world_size = int(os.environ.get("WORLD_SIZE", "1")); local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world_size > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    torch.cuda.set_device(local_rank)
+    lib = kajiya_b200.lib()   # raises without the CUDA extension: no fallback
+    workload = args.workload
+    # Multi-GPU: the path shards by frame tiles.  Each rank renders an independent full frame of ITS OWN view
+    # (weak scaling over views) until tile sharding with the border all-gather lands; reported as scaling "weak".
+    w, view, W, H = build_world(lib, workload, device=local_rank)
+    F, Hh = W * H, ((W + 1) // 2) * ((H + 1) // 2)
+    K, Wm = args.steps, args.warmup
+    nslots = min(K, 16)   # ring of distinct jittered G-buffers (each 32 B/px): inputs 16 x 66 MB = 1 GB > L2 (126 MB)
+
+    # ---- untimed: produce the G-buffer ring on the device (the raster stand-in is an input producer, not the hot path)
+    for i in range(nslots):
+        w.render_frame(capture_slot=i + 1, **view)
+    w.sync()
+    # host copies of the ring for the e2e leg (pinned)
+    host_ring = []
+    for i in range(nslots):
+        bufs = []
+        for name in ("gbuffer", "depth", "geometric_normal", "velocity"):
+            img = w.image_handle(f"slot{i + 1}.{name}")
+            nbytes = img.width * img.height * lib.dll.kjb_format_texel_bytes(img.format)
+            t = pinned_empty(torch, nbytes)
+            w._check(lib.dll.kjb_image_download(w.ctx, C.byref(img), t.data_ptr()))
+            bufs.append(t)
+        host_ring.append(bufs)
+    w.sync()
+    res_img = w.image_handle("rtdgi.spatial_filtered")
+    res_bytes = res_img.width * res_img.height * 8
+    host_result = pinned_empty(torch, res_bytes)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step_device(i):
+        w.render_frame(replay_slot=(i % nslots) + 1, **view)
+
+    def step_e2e(i):
+        b = host_ring[i % nslots]
+        w.render_frame(host_inputs=(b[0].data_ptr(), b[1].data_ptr(), b[2].data_ptr(), b[3].data_ptr()), host_result=host_result.data_ptr(), **view)
+
+    # ---- device-resident leg
+    for i in range(Wm):
+        step_device(i)
+    w.sync(); w.stats()          # reset ray counters
+    launches0 = lib.dll.kjb_launch_count(w.ctx)
+    clocks = ClockSampler(local_rank); clocks.start()
+    barrier()
+    w.timer_record(1000)
+    for i in range(K):
+        step_device(Wm + i)
+    w.timer_record(1001)
+    ms_total = w.timer_elapsed_ms(1000, 1001)
+    barrier()
+    clock_info = clocks.stop()
+    st = w.stats()
+    rays = st["closest_rays"] + st["any_hit_rays"]
+    launches = lib.dll.kjb_launch_count(w.ctx) - launches0
+
+    # ---- per-pass timing (CUDA events around every pass, same K frames)
+    w.set_profiling(True)
+    for i in range(K):
+        step_device(Wm + K + i)
+    timings = w.pass_timings()
+    w.set_profiling(False)
+
+    # ---- e2e leg: host G-buffer in, irradiance out
+    for i in range(max(3, Wm // 2)):
+        step_e2e(i)
+    w.sync(); w.stats()
+    barrier()
+    t0 = time.perf_counter()
+    w.timer_record(1002)
+    for i in range(K):
+        step_e2e(i)
+    w.timer_record(1003)
+    ms_e2e = w.timer_elapsed_ms(1002, 1003)
+    wall_e2e = (time.perf_counter() - t0) * 1e3
+    barrier()
+    st2 = w.stats()
+    rays_e2e = st2["closest_rays"] + st2["any_hit_rays"]
+    ms_e2e = max(ms_e2e, wall_e2e)   # the call blocks on the download: wall clock is the honest end-to-end figure
+
+    # ---- reduce over ranks: max time, summed rays
+    if dist is not None:
+        t = torch.tensor([ms_total, ms_e2e], device="cuda", dtype=torch.float64); dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        r = torch.tensor([rays, rays_e2e, launches], device="cuda", dtype=torch.float64); dist.all_reduce(r, op=dist.ReduceOp.SUM)
+        ms_total, ms_e2e = t.tolist(); rays, rays_e2e, launches = r.tolist()
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    peak, peak_src = load_peaks()
+    # dominant kernel = the pass with the largest share of device time
+    per_pass = {k: v[1] / max(v[0], 1) for k, v in timings.items() if k in PASS_BYTES}
+    calls = {k: v[0] for k, v in timings.items()}
+    share = {k: timings[k][1] for k in per_pass}
+    dom = max(share, key=share.get)
+    dom_bytes = pass_bytes(dom, F, Hh)
+    achieved = dom_bytes / (per_pass[dom] * 1e-3) / 1e9
+    frame_bytes = sum(pass_bytes(k, F, Hh) * (calls[k] / K) for k in per_pass)
+    frame_ms = ms_total / K
+
+    out = {
+        "metric": "gi_rays_per_sec", "value": rays / (ms_total * 1e-3), "unit": "rays/s", "n_gpus": world_size, "steps": K, "warmup": Wm,
+        "ms_per_step": frame_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload, "scene": WORKLOADS[workload][0], "resolution": [W, H], "spatial_reuse_passes": WORKLOADS[workload][4],
+                   "l2_policy": f"inputs larger than L2: ring of {nslots} distinct jittered G-buffers ({nslots * 32 * F / 1e6:.0f} MB) + ~{frame_bytes / 1e6:.0f} MB/frame of temporal state",
+                   "rays_per_frame": rays / K / world_size, "multi_gpu": "independent frames per rank (tile sharding: see DESIGN.md)" if world_size > 1 else "n/a"},
+        "e2e": {"value": rays_e2e / (ms_e2e * 1e-3), "unit": "rays/s", "ms_per_step": ms_e2e / K,
+                "h2d_bytes_per_step": int(32 * F + 1216), "d2h_bytes_per_step": int(res_bytes)},
+        "gpu_launches": int(launches),
+        "clocks": clock_info,
+        "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                     "peak_source": peak_src, "kernel_ms": per_pass[dom], "kernel_share_of_step": share[dom] / sum(share.values()),
+                     "algorithmic_bytes_per_launch": dom_bytes,
+                     "frame": {"algorithmic_bytes": frame_bytes, "achieved_gbs": frame_bytes / (frame_ms * 1e-3) / 1e9, "frac": frame_bytes / (frame_ms * 1e-3) / 1e9 / peak},
+                     "per_pass_ms": {k: round(v, 5) for k, v in sorted(per_pass.items(), key=lambda kv: -share[kv[0]])}},
+    }
+    if world_size == 1 and not args.no_cpu_baseline:
+        out["cpu_baseline"] = cpu_baseline(workload, seconds=args.cpu_seconds)
+    print(json.dumps(out))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def cpu_baseline(workload, seconds=15.0, steps=None, warmup=1):
+    """The oracle (CPU port of the reference shaders, all host threads) on a bounded sample of the same workload:
+    the same scene, resolution and pass list, as many frames as fit in ~`seconds`."""
+    from kajiya_b200._abi import KjbLib
+    so = os.path.join(ROOT, "oracle", "_build", "libkj_oracle.so")
+    lib = KjbLib(so)
+    w, view, W, H = build_world(lib, workload)
+    for _ in range(warmup):
+        w.render_frame(**view)
+    w.stats()
+    t0 = time.perf_counter(); n = 0
+    while True:
+        w.render_frame(**view); n += 1
+        el = time.perf_counter() - t0
+        if (steps is not None and n >= steps) or (steps is None and (el > seconds or n >= 64)):
+            break
+    st = w.stats()
+    rays = st["closest_rays"] + st["any_hit_rays"]
+    return {"value": rays / el, "unit": "rays/s", "cores": os.cpu_count(), "kind": "port", "ms_per_step": el / n * 1e3,
+            "sample": f"{n} full frames of {workload} ({W}x{H}) after {warmup} warm-up, all {os.cpu_count()} host threads; includes the CPU raster stand-in"}
+
+
+def run_reference(args):
+    """--impl reference: the reference's own implementation of the path cannot run here (Rust + Vulkan RT);
+    its CPU restatement (oracle port) is timed on the host cores on the same config/metric/unit."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    world_size = int(os.environ.get("WORLD_SIZE", "1"))
+    K, Wm = args.steps, args.warmup
+    steps = max(1, min(K, 8))   # bounded sample: a 1080p oracle frame takes ~2 s on 8 threads
+    cb = cpu_baseline(args.workload, steps=steps, warmup=min(Wm, 1))
+    W, H = WORKLOADS[args.workload][2:4]
+    out = {"impl": "reference", "metric": "gi_rays_per_sec", "value": cb["value"], "unit": "rays/s", "n_gpus": world_size, "steps": K, "warmup": Wm,
+           "ms_per_step": cb["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "config": {"workload": args.workload, "scene": WORKLOADS[args.workload][0], "resolution": [W, H], "spatial_reuse_passes": WORKLOADS[args.workload][4],
+                      "timed_steps": steps},
+           "cpu_baseline": cb, "e2e": {"value": cb["value"], "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
+    print(json.dumps(out))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=64)
+    ap.add_argument("--warmup", type=int, default=8)
+    ap.add_argument("--impl", default="kajiya_b200", choices=["kajiya_b200", "reference"])
+    ap.add_argument("--workload", default="cornell_1080p_rtdgi_1s1t", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_cuda(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -180,6 +180,11 @@ int  kjb_buffer_free(kjb_context *ctx, kjb_buffer *buf);
 int  kjb_buffer_upload(kjb_context *ctx, const kjb_buffer *dst, uint64_t dst_offset, const void *host_src, uint64_t size);
 int  kjb_buffer_download(kjb_context *ctx, const kjb_buffer *src, uint64_t src_offset, void *host_dst, uint64_t size);
 
+/* device-side stopwatch: record() drops an event on the context's stream; elapsed_ms() synchronises on `to_slot` and
+ * returns the time between two recorded slots (CUDA events; wall-clock on the CPU test builds). slots 0..1023. */
+int  kjb_timer_record(kjb_context *ctx, uint32_t slot);
+int  kjb_timer_elapsed_ms(kjb_context *ctx, uint32_t from_slot, uint32_t to_slot, float *out_ms);
+
 /* ------------------------------------------------------------------ scene upload
  * kjb_scene_set_geometry replaces WorldRenderer::add_mesh's buffer uploads + BLAS builds
  * (world_renderer.rs:604-776): the unified `vertices` byte buffer, the `meshes` table and, per mesh,

@@ -59,6 +59,10 @@ typedef struct kjb_world_frame {
     /* Optional host destination for the frame's result (rtdgi screen irradiance, RGBA16F full-res; the TAA
      * output RGBA16F when TAA is enabled).  Copied device->host inside the call when non-NULL. */
     void *host_result;
+    /* Device-resident G-buffer ring for benchmarking with inputs already in HBM: capture_slot = k > 0 stores this frame's
+     * G-buffer inputs (after the raster stand-in / upload) in ring slot k; replay_slot = k > 0 binds ring slot k as the
+     * frame's G-buffer inputs (no raster pass, no copy). */
+    uint32_t capture_slot, replay_slot;
 } kjb_world_frame;
 
 int  kjb_world_create(kjb_context *ctx, const kjb_world_desc *desc, kjb_world **out);
@@ -81,6 +85,10 @@ const char *kjb_world_image_names(kjb_world *w);
 int  kjb_world_last_frame_stats(kjb_world *w, uint64_t out[4]);   /* launches, closest rays, any-hit rays, passes */
 /* Run frames only up to (and including) the pass with this rg label, for per-pass debugging ("" = all). */
 int  kjb_world_set_stop_after(kjb_world *w, const char *pass_label);
+/* Per-pass device timing: when on, every pass is bracketed by kjb_timer_record and accumulated per rg label. */
+int  kjb_world_set_profiling(kjb_world *w, uint32_t on);
+/* "label\tcalls\ttotal_ms\n" per pass since profiling was switched on (synchronises). */
+const char *kjb_world_pass_timings(kjb_world *w);
 
 #ifdef __cplusplus
 }

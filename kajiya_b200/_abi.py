@@ -51,7 +51,7 @@ class WorldFrame(C.Structure):
     _fields_ = [("camera_position", C.c_float * 3), ("camera_rotation", C.c_float * 4), ("vertical_fov_deg", C.c_float), ("near_plane", C.c_float),
                 ("sun_direction", C.c_float * 3), ("delta_time_seconds", C.c_float),
                 ("host_gbuffer", C.c_void_p), ("host_depth", C.c_void_p), ("host_geometric_normal", C.c_void_p), ("host_velocity", C.c_void_p),
-                ("host_result", C.c_void_p)]
+                ("host_result", C.c_void_p), ("capture_slot", C.c_uint32), ("replay_slot", C.c_uint32)]
 
 
 assert C.sizeof(MeshMaterial) == 152
@@ -97,6 +97,10 @@ class KjbLib:
             "kjb_world_image_names": (C.c_char_p, [P]),
             "kjb_world_last_frame_stats": (C.c_int, [P, C.POINTER(C.c_uint64 * 4)]),
             "kjb_world_set_stop_after": (C.c_int, [P, C.c_char_p]),
+            "kjb_world_set_profiling": (C.c_int, [P, C.c_uint32]),
+            "kjb_world_pass_timings": (C.c_char_p, [P]),
+            "kjb_timer_record": (C.c_int, [P, C.c_uint32]),
+            "kjb_timer_elapsed_ms": (C.c_int, [P, C.c_uint32, C.c_uint32, C.POINTER(C.c_float)]),
         }
         self.missing = []
         for name, (res, args) in sig.items():

@@ -110,6 +110,24 @@ struct kjb_world {
         temporal2_tex{"rtdgi.temporal2"}, temporal2_variance_tex{"rtdgi.temporal2_var"}, temporal_hit_normal_tex{"rtdgi.hit_normal"};
 
     int err = 0;
+    bool profiling = false; uint32_t timer_next = 0;
+    std::vector<std::pair<std::string, std::pair<uint32_t, uint32_t>>> timer_pending;   // label -> (slot_begin, slot_end) of this frame
+    std::map<std::string, std::pair<uint32_t, double>> pass_ms;                          // label -> (calls, total ms)
+    std::string timings_cache;
+    void pass_begin(const char* label) {
+        if (!profiling || timer_next + 2 > 1024) return;
+        kjb_timer_record(ctx, timer_next);
+        timer_pending.push_back({label, {timer_next, timer_next + 1}});
+        timer_next += 2;
+    }
+    void pass_end() { if (profiling && !timer_pending.empty()) kjb_timer_record(ctx, timer_pending.back().second.second); }
+    void flush_timers() {
+        for (auto& t : timer_pending) {
+            float ms = 0;
+            if (kjb_timer_elapsed_ms(ctx, t.second.first, t.second.second, &ms) == 0) { auto& e = pass_ms[t.first]; e.first += 1; e.second += ms; }
+        }
+        timer_pending.clear(); timer_next = 0;
+    }
 
     // rg.create / get_or_create_temporal: allocate once per name, zero-filled
     kjb_image& img(const std::string& name, uint32_t w, uint32_t h, uint32_t fmt, uint32_t layers = 1) {
@@ -134,7 +152,7 @@ struct kjb_world {
     }
 };
 
-#define RUN(label, call) do { if (w->stopped || w->err) break; if (!w->pass_done(label, (call))) {} } while (0)
+#define RUN(label, call) do { if (w->stopped || w->err) break; w->pass_begin(label); int rc__ = (call); w->pass_end(); w->pass_done(label, rc__); } while (0)
 
 static void size4(float out[4], const kjb_image& i) { out[0] = float(i.width); out[1] = float(i.height); out[2] = 1.0f / float(i.width); out[3] = 1.0f / float(i.height); }
 
@@ -242,8 +260,21 @@ const char* kjb_world_image_names(kjb_world* w) {
     if (w->names_cache.empty()) for (auto& kv : w->images) { w->names_cache += kv.first; w->names_cache += '\n'; }
     return w->names_cache.c_str();
 }
-int kjb_world_last_frame_stats(kjb_world* w, uint64_t out[4]) { memcpy(out, w->stats, sizeof(w->stats)); return 0; }
+// launches/passes of the last frame; rays traced since the previous call (reading the counters synchronises, so it is not done per frame)
+int kjb_world_last_frame_stats(kjb_world* w, uint64_t out[4]) {
+    uint64_t rays[2] = {0, 0};
+    kjb_ray_counters(w->ctx, rays, 1);
+    w->stats[1] = rays[0]; w->stats[2] = rays[1];
+    memcpy(out, w->stats, sizeof(w->stats)); return 0;
+}
 int kjb_world_set_stop_after(kjb_world* w, const char* label) { w->stop_after = label ? label : ""; return 0; }
+int kjb_world_set_profiling(kjb_world* w, uint32_t on) { w->flush_timers(); w->profiling = on != 0; if (on) w->pass_ms.clear(); return 0; }
+const char* kjb_world_pass_timings(kjb_world* w) {
+    w->flush_timers();
+    w->timings_cache.clear();
+    for (auto& kv : w->pass_ms) w->timings_cache += kv.first + "\t" + std::to_string(kv.second.first) + "\t" + std::to_string(kv.second.second) + "\n";
+    return w->timings_cache.c_str();
+}
 
 // ---------------------------------------------------------------- per-frame constants (world_renderer.rs:1001-1108)
 static int begin_frame(kjb_world* w, const kjb_world_frame* f, kjb_frame_constants& fc, bool jitter) {
@@ -321,10 +352,8 @@ static int begin_frame(kjb_world* w, const kjb_world_frame* f, kjb_frame_constan
 }
 
 static void end_frame(kjb_world* w) {
-    uint64_t rays[2] = {0, 0};
-    kjb_ray_counters(w->ctx, rays, 1);
     w->stats[0] = kjb_launch_count(w->ctx) - w->launches_at_frame_start;
-    w->stats[1] = rays[0]; w->stats[2] = rays[1];
+    if (w->profiling) w->flush_timers();
     w->frame_idx += 1;   // retire_frame (world_renderer.rs:1110-1113)
 }
 
@@ -460,17 +489,27 @@ int kjb_world_render_frame(kjb_world* w, const kjb_world_frame* f) {
     }
 
     // G-buffer + depth + geometric normal + velocity (world_render_passes.rs:40-82)
-    kjb_image& geometric_normal = w->img("geometric_normal", W, H, KJB_FMT_A2R10G10B10_UNORM);
-    kjb_image& gbuffer = w->img("gbuffer", W, H, KJB_FMT_RGBA32_FLOAT);
-    kjb_image& depth = w->img("depth", W, H, KJB_FMT_R32_FLOAT);
-    kjb_image& velocity = w->img("velocity", W, H, KJB_FMT_RGBA16_FLOAT);
-    if (f->host_gbuffer) {
+    const std::string in_prefix = f->replay_slot ? "slot" + std::to_string(f->replay_slot) + "." : "";
+    kjb_image& geometric_normal = w->img(in_prefix + "geometric_normal", W, H, KJB_FMT_A2R10G10B10_UNORM);
+    kjb_image& gbuffer = w->img(in_prefix + "gbuffer", W, H, KJB_FMT_RGBA32_FLOAT);
+    kjb_image& depth = w->img(in_prefix + "depth", W, H, KJB_FMT_R32_FLOAT);
+    kjb_image& velocity = w->img(in_prefix + "velocity", W, H, KJB_FMT_RGBA16_FLOAT);
+    if (f->replay_slot) {
+        // inputs already resident in HBM (captured earlier): nothing to produce
+    } else if (f->host_gbuffer) {
         int rc = kjb_image_upload(ctx, &gbuffer, f->host_gbuffer) | kjb_image_upload(ctx, &depth, f->host_depth)
                | kjb_image_upload(ctx, &geometric_normal, f->host_geometric_normal) | kjb_image_upload(ctx, &velocity, f->host_velocity);
         if (rc) return rc;
     } else {
         kjb_raster_gbuffer_args a{geometric_normal, gbuffer, depth, velocity};
         RUN("raster simple", kjb_pass_raster_gbuffer(ctx, &a));
+    }
+    if (f->capture_slot && !f->replay_slot) {
+        const std::string sp = "slot" + std::to_string(f->capture_slot) + ".";
+        kjb_image_copy(ctx, &w->img(sp + "geometric_normal", W, H, KJB_FMT_A2R10G10B10_UNORM), &geometric_normal);
+        kjb_image_copy(ctx, &w->img(sp + "gbuffer", W, H, KJB_FMT_RGBA32_FLOAT), &gbuffer);
+        kjb_image_copy(ctx, &w->img(sp + "depth", W, H, KJB_FMT_R32_FLOAT), &depth);
+        kjb_image_copy(ctx, &w->img(sp + "velocity", W, H, KJB_FMT_RGBA16_FLOAT), &velocity);
     }
     // reprojection map + copy depth (renderers/reprojection.rs:6-52)
     kjb_image& reprojection_map = w->img("reprojection_map", W, H, KJB_FMT_RGBA16_SNORM);

@@ -167,6 +167,26 @@ int kjb_set_luts(kjb_context* c, const kjb_image* fg, const kjb_image* bn) {
     c->g.brdf_fg_lut = img_ro(*fg); c->g.blue_noise = img_ro(*bn);
     return 0;
 }
+#if defined(KJB_EMU)
+}  // extern "C"
+#include <chrono>
+static std::chrono::steady_clock::time_point g_timer_slots[1024];
+extern "C" {
+int kjb_timer_record(kjb_context*, uint32_t slot) { if (slot >= 1024) return 1; g_timer_slots[slot] = std::chrono::steady_clock::now(); return 0; }
+int kjb_timer_elapsed_ms(kjb_context*, uint32_t a, uint32_t b, float* out) { if (a >= 1024 || b >= 1024) return 1; *out = std::chrono::duration<float, std::milli>(g_timer_slots[b] - g_timer_slots[a]).count(); return 0; }
+#else
+int kjb_timer_record(kjb_context* c, uint32_t slot) {
+    if (slot >= 1024) return c->fail("kjb_timer_record: slot out of range");
+    if (c->timer_events.size() <= slot) c->timer_events.resize(slot + 1, nullptr);
+    if (!c->timer_events[slot] && cudaEventCreate(&c->timer_events[slot]) != cudaSuccess) return c->fail("kjb_timer_record: cudaEventCreate failed");
+    return cudaEventRecord(c->timer_events[slot], c->stream) != cudaSuccess;
+}
+int kjb_timer_elapsed_ms(kjb_context* c, uint32_t a, uint32_t b, float* out) {
+    if (a >= c->timer_events.size() || b >= c->timer_events.size() || !c->timer_events[a] || !c->timer_events[b]) return c->fail("kjb_timer_elapsed_ms: slot was never recorded");
+    if (cudaEventSynchronize(c->timer_events[b]) != cudaSuccess) return c->fail("kjb_timer_elapsed_ms: event sync failed");
+    return cudaEventElapsedTime(out, c->timer_events[a], c->timer_events[b]) != cudaSuccess;
+}
+#endif
 int kjb_ray_counters(kjb_context* c, uint64_t out[2], int reset) {
     unsigned long long v[2] = {0, 0};
     dev_d2h(c, v, c->d_ray_counters, sizeof(v));

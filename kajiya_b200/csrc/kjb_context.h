@@ -33,6 +33,9 @@ struct kjb_context {
     kjb_triangle_light* d_lights = nullptr; uint32_t lights_capacity = 0;
     unsigned long long* d_ray_counters = nullptr;
     void* pinned_staging = nullptr; size_t pinned_bytes = 0;
+#if !defined(KJB_EMU)
+    std::vector<cudaEvent_t> timer_events;
+#endif
 
     kjb::Globals g;   // host copy, passed by value to every kernel
 

@@ -80,7 +80,7 @@ class World:
         self._check(self.d.kjb_world_set_blue_noise(self.w, a.ctypes.data))
 
     # -- frames ------------------------------------------------------------------------------------------------
-    def _frame(self, camera_position, camera_rotation, sun_direction, vfov=52.0, host_inputs=None, host_result=None):
+    def _frame(self, camera_position, camera_rotation, sun_direction, vfov=52.0, host_inputs=None, host_result=None, capture_slot=0, replay_slot=0):
         f = WorldFrame()
         f.camera_position[:] = camera_position; f.camera_rotation[:] = camera_rotation
         f.vertical_fov_deg = vfov; f.near_plane = 0.01; f.sun_direction[:] = sun_direction; f.delta_time_seconds = 1.0 / 60.0
@@ -88,6 +88,7 @@ class World:
             f.host_gbuffer, f.host_depth, f.host_geometric_normal, f.host_velocity = host_inputs
         if host_result is not None:
             f.host_result = host_result
+        f.capture_slot, f.replay_slot = capture_slot, replay_slot
         return f
 
     def render_frame(self, camera_position, camera_rotation, sun_direction, **kw):
@@ -100,6 +101,25 @@ class World:
 
     def sync(self):
         self._check(self.d.kjb_sync(self.ctx))
+
+    def set_profiling(self, on):
+        self.d.kjb_world_set_profiling(self.w, int(on))
+
+    def pass_timings(self):
+        """{label: (calls, total_ms)} of the passes run since profiling was switched on"""
+        out = {}
+        for line in self.d.kjb_world_pass_timings(self.w).decode().split("\n"):
+            if line:
+                label, calls, ms = line.split("\t"); out[label] = (int(calls), float(ms))
+        return out
+
+    def timer_record(self, slot):
+        self._check(self.d.kjb_timer_record(self.ctx, slot))
+
+    def timer_elapsed_ms(self, a, b):
+        ms = C.c_float()
+        self._check(self.d.kjb_timer_elapsed_ms(self.ctx, a, b, C.byref(ms)))
+        return ms.value
 
     def stop_after(self, label):
         self.d.kjb_world_set_stop_after(self.w, (label or "").encode())

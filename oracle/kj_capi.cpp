@@ -3,6 +3,7 @@
 // host-side frame driver can run either behind identical calls.  "Device" memory is host memory here.
 #include "kj_ctx.h"
 #include <cstdlib>
+#include <chrono>
 
 namespace kjo {
 
@@ -61,6 +62,9 @@ int kjb_set_frame_constants(kjb_context* c, const kjb_frame_constants* fc, const
     return 0;
 }
 int kjb_set_luts(kjb_context* c, const kjb_image* fg, const kjb_image* bn) { c->g.brdf_fg_lut = Img(*fg); c->g.blue_noise = Img(*bn); return 0; }
+static std::chrono::steady_clock::time_point g_timer_slots[1024];
+int kjb_timer_record(kjb_context*, uint32_t slot) { if (slot >= 1024) return 1; g_timer_slots[slot] = std::chrono::steady_clock::now(); return 0; }
+int kjb_timer_elapsed_ms(kjb_context*, uint32_t a, uint32_t b, float* out) { if (a >= 1024 || b >= 1024) return 1; *out = std::chrono::duration<float, std::milli>(g_timer_slots[b] - g_timer_slots[a]).count(); return 0; }
 int kjb_ray_counters(kjb_context* c, uint64_t out[2], int reset) {
     out[0] = c->scene.n_closest.load(); out[1] = c->scene.n_any.load();
     if (reset) { c->scene.n_closest = 0; c->scene.n_any = 0; }
