@@ -316,6 +316,42 @@ typedef struct kjb_rtdgi_spatial_args {              /* "rtdgi spatial", spatial
 } kjb_rtdgi_spatial_args;
 int kjb_pass_rtdgi_spatial(kjb_context *ctx, const kjb_rtdgi_spatial_args *a);
 
+/* ------------------------------------------------------------------ taa (renderers/taa.rs:41-185; shaders under assets/shaders/taa/) */
+typedef struct kjb_taa_reproject_args {              /* "reproject taa", reproject_history.hlsl:8-16, taa.rs:66-79 */
+    kjb_image history_tex, reprojection_tex, depth_tex, output_tex, closest_velocity_output;
+    float input_tex_size[4], output_tex_size[4];
+} kjb_taa_reproject_args;
+int kjb_pass_taa_reproject(kjb_context *ctx, const kjb_taa_reproject_args *a);
+
+typedef struct kjb_taa_filter_input_args {           /* "taa filter input", filter_input.hlsl:9-12, taa.rs:98-106 */
+    kjb_image input_tex, depth_tex, output_tex, dev_output_tex;
+} kjb_taa_filter_input_args;
+int kjb_pass_taa_filter_input(kjb_context *ctx, const kjb_taa_filter_input_args *a);
+
+typedef struct kjb_taa_filter_history_args {         /* "taa filter history", filter_history.hlsl:8-13, taa.rs:112-122 */
+    kjb_image input_tex, output_tex;
+    float input_tex_size[4], output_tex_size[4];      /* = (reprojected history extent, taa input extent), as the host pushes them */
+} kjb_taa_filter_history_args;
+int kjb_pass_taa_filter_history(kjb_context *ctx, const kjb_taa_filter_history_args *a);
+
+typedef struct kjb_taa_input_prob_args {             /* "taa input prob", input_prob.hlsl:11-23, taa.rs:129-144 */
+    kjb_image input_tex, filtered_input_tex, filtered_input_dev_tex, history_tex, filtered_history_tex, reprojection_tex, depth_tex,
+              smooth_var_history_tex, velocity_history_tex, output_tex;
+    float input_tex_size[4];
+} kjb_taa_input_prob_args;
+int kjb_pass_taa_input_prob(kjb_context *ctx, const kjb_taa_input_prob_args *a);
+
+typedef struct kjb_taa_prob_filter_args { kjb_image input_tex, output_tex; } kjb_taa_prob_filter_args;
+int kjb_pass_taa_prob_filter(kjb_context *ctx, const kjb_taa_prob_filter_args *a);    /* "taa prob filter", filter_prob.hlsl */
+int kjb_pass_taa_prob_filter2(kjb_context *ctx, const kjb_taa_prob_filter_args *a);   /* "taa prob filter2", filter_prob2.hlsl */
+
+typedef struct kjb_taa_args {                        /* "taa", taa.hlsl:10-26, taa.rs:168-185 */
+    kjb_image input_tex, history_tex, reprojection_tex, closest_velocity_tex, velocity_history_tex, depth_tex, smooth_var_history_tex, input_prob_tex;
+    kjb_image temporal_output_tex, output_tex, smooth_var_output_tex, velocity_output_tex;
+    float input_tex_size[4], output_tex_size[4];
+} kjb_taa_args;
+int kjb_pass_taa(kjb_context *ctx, const kjb_taa_args *a);
+
 /* ------------------------------------------------------------------ reference path tracer (the oracle's quantity, also a GPU pass)
  * "reference pt" (renderers/reference.rs:8-25, rt/reference_path_trace.rgen.hlsl:75-377): accumulates into RGBA32F. */
 typedef struct kjb_reference_pt_args {

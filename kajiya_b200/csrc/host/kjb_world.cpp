@@ -108,6 +108,8 @@ struct kjb_world {
     PingPong temporal_radiance_tex{"rtdgi.radiance"}, temporal_ray_orig_tex{"rtdgi.ray_orig"}, temporal_ray_tex{"rtdgi.ray"},
         temporal_reservoir_tex{"rtdgi.reservoir"}, temporal_candidate_tex{"rtdgi.candidate"}, temporal_invalidity_tex{"rtdgi.invalidity"},
         temporal2_tex{"rtdgi.temporal2"}, temporal2_variance_tex{"rtdgi.temporal2_var"}, temporal_hit_normal_tex{"rtdgi.hit_normal"};
+    PingPong taa_temporal_tex{"taa"}, taa_temporal_velocity_tex{"taa.velocity"}, taa_temporal_smooth_var_tex{"taa.smooth_var"};   // taa.rs:19-27
+    uint32_t OW = 0, OH = 0;   // temporal_upscale_extent
 
     int err = 0;
     bool profiling = false; uint32_t timer_next = 0;
@@ -164,6 +166,7 @@ int kjb_world_create(kjb_context* ctx, const kjb_world_desc* desc, kjb_world** o
     if (w->desc.spatial_reuse_pass_count == 0) w->desc.spatial_reuse_pass_count = 2;
     w->W = desc->render_width; w->H = desc->render_height;
     w->HW = (w->W + 1) / 2; w->HH = (w->H + 1) / 2;   // ImageDesc::half_res = div_up (image.rs:140-142)
+    w->OW = desc->temporal_upscale_width ? desc->temporal_upscale_width : w->W; w->OH = desc->temporal_upscale_height ? desc->temporal_upscale_height : w->H;
     *out = w;
     return 0;
 }
@@ -473,6 +476,51 @@ static void rtdgi_render(kjb_world* w, kjb_image& reprojected_history_tex, kjb_i
     }
 }
 
+// ---------------------------------------------------------------- TaaRenderer::render (taa.rs:41-185)
+static kjb_image* taa_render(kjb_world* w, kjb_image& input_tex, kjb_image& reprojection_map, kjb_image& depth_tex) {
+    kjb_context* ctx = w->ctx;
+    const uint32_t OW = w->OW, OH = w->OH, IW = input_tex.width, IH = input_tex.height;
+    kjb_image *temporal_output_tex, *history_tex; w->get_output_and_history(w->taa_temporal_tex, OW, OH, KJB_FMT_RGBA16_FLOAT, temporal_output_tex, history_tex);
+    kjb_image *temporal_velocity_output_tex, *velocity_history_tex; w->get_output_and_history(w->taa_temporal_velocity_tex, OW, OH, KJB_FMT_RG16_FLOAT, temporal_velocity_output_tex, velocity_history_tex);
+    kjb_image& reprojected_history_img = w->img("taa.reprojected_history", OW, OH, KJB_FMT_RGBA16_FLOAT);
+    kjb_image& closest_velocity_img = w->img("taa.closest_velocity", OW, OH, KJB_FMT_RG16_FLOAT);
+    {
+        kjb_taa_reproject_args a{}; a.history_tex = *history_tex; a.reprojection_tex = reprojection_map; a.depth_tex = depth_tex; a.output_tex = reprojected_history_img;
+        a.closest_velocity_output = closest_velocity_img; size4(a.input_tex_size, input_tex); size4(a.output_tex_size, reprojected_history_img);
+        RUN("reproject taa", kjb_pass_taa_reproject(ctx, &a));
+    }
+    kjb_image *smooth_var_output_tex, *smooth_var_history_tex; w->get_output_and_history(w->taa_temporal_smooth_var_tex, OW, OH, KJB_FMT_RGBA16_FLOAT, smooth_var_output_tex, smooth_var_history_tex);
+    kjb_image& filtered_input_img = w->img("taa.filtered_input", IW, IH, KJB_FMT_RGBA16_FLOAT);
+    kjb_image& filtered_input_deviation_img = w->img("taa.filtered_input_deviation", IW, IH, KJB_FMT_RGBA16_FLOAT);
+    { kjb_taa_filter_input_args a{input_tex, depth_tex, filtered_input_img, filtered_input_deviation_img}; RUN("taa filter input", kjb_pass_taa_filter_input(ctx, &a)); }
+    kjb_image& filtered_history_img = w->img("taa.filtered_history", IW, IH, KJB_FMT_RGBA16_FLOAT);
+    {
+        kjb_taa_filter_history_args a{}; a.input_tex = reprojected_history_img; a.output_tex = filtered_history_img;
+        size4(a.input_tex_size, reprojected_history_img); size4(a.output_tex_size, input_tex);
+        RUN("taa filter history", kjb_pass_taa_filter_history(ctx, &a));
+    }
+    kjb_image& input_prob_img = w->img("taa.input_prob", IW, IH, KJB_FMT_R16_FLOAT);
+    {
+        kjb_taa_input_prob_args a{}; a.input_tex = input_tex; a.filtered_input_tex = filtered_input_img; a.filtered_input_dev_tex = filtered_input_deviation_img;
+        a.history_tex = reprojected_history_img; a.filtered_history_tex = filtered_history_img; a.reprojection_tex = reprojection_map; a.depth_tex = depth_tex;
+        a.smooth_var_history_tex = *smooth_var_history_tex; a.velocity_history_tex = *velocity_history_tex; a.output_tex = input_prob_img; size4(a.input_tex_size, input_tex);
+        RUN("taa input prob", kjb_pass_taa_input_prob(ctx, &a));
+    }
+    kjb_image& prob_filtered1_img = w->img("taa.prob_filtered1", IW, IH, KJB_FMT_R16_FLOAT);
+    { kjb_taa_prob_filter_args a{input_prob_img, prob_filtered1_img}; RUN("taa prob filter", kjb_pass_taa_prob_filter(ctx, &a)); }
+    kjb_image& prob_filtered2_img = w->img("taa.prob_filtered2", IW, IH, KJB_FMT_R16_FLOAT);
+    { kjb_taa_prob_filter_args a{prob_filtered1_img, prob_filtered2_img}; RUN("taa prob filter2", kjb_pass_taa_prob_filter2(ctx, &a)); }
+    kjb_image& this_frame_output_img = w->img("taa.this_frame_out", OW, OH, KJB_FMT_RGBA16_FLOAT);
+    {
+        kjb_taa_args a{}; a.input_tex = input_tex; a.history_tex = reprojected_history_img; a.reprojection_tex = reprojection_map; a.closest_velocity_tex = closest_velocity_img;
+        a.velocity_history_tex = *velocity_history_tex; a.depth_tex = depth_tex; a.smooth_var_history_tex = *smooth_var_history_tex; a.input_prob_tex = prob_filtered2_img;
+        a.temporal_output_tex = *temporal_output_tex; a.output_tex = this_frame_output_img; a.smooth_var_output_tex = *smooth_var_output_tex; a.velocity_output_tex = *temporal_velocity_output_tex;
+        size4(a.input_tex_size, input_tex); size4(a.output_tex_size, *temporal_output_tex);
+        RUN("taa", kjb_pass_taa(ctx, &a));
+    }
+    return &this_frame_output_img;
+}
+
 int kjb_world_render_frame(kjb_world* w, const kjb_world_frame* f) {
     kjb_context* ctx = w->ctx;
     kjb_frame_constants fc;
@@ -535,9 +583,16 @@ int kjb_world_render_frame(kjb_world* w, const kjb_world_frame* f) {
     // rtdgi.render (world_render_passes.rs:146-160): diffuse rays use the convolved sky cube
     rtdgi_render(w, reprojected_history_tex, *temporal_output_tex, gbuffer, depth, geometric_normal, reprojection_map, convolved_sky_cube, ssao_tex);
 
+    // taa.render (world_render_passes.rs:253-263).  light_gbuffer (the composite that normally feeds TAA) is outside the hot
+    // path: TAA consumes the GI result directly.
+    const char* result_name = "rtdgi.spatial_filtered";
+    if (w->desc.enable_taa) {
+        kjb_image gi{};
+        if (kjb_world_get_image(w, "rtdgi.spatial_filtered", &gi) == 0) { taa_render(w, gi, reprojection_map, depth); result_name = "taa.this_frame_out"; }
+    }
     if (f->host_result && !w->err) {
         kjb_image result{};
-        if (kjb_world_get_image(w, "rtdgi.spatial_filtered", &result) == 0) { kjb_image_download(ctx, &result, f->host_result); kjb_sync(ctx); }
+        if (kjb_world_get_image(w, result_name, &result) == 0) { kjb_image_download(ctx, &result, f->host_result); kjb_sync(ctx); }
     }
     end_frame(w);
     return w->err;

@@ -91,9 +91,11 @@ inline bool check_img(kjb_context* c, const kjb_image& i, uint32_t fmt, const ch
 #if defined(KJB_EMU)
 #define KJB_KERNEL(bounds) static void
 #define KJB_LAUNCH(ctx, kernel, dims, ...) do { kjb_emu::launch(dims, [&]() { kernel(__VA_ARGS__); }); (ctx)->launches++; } while (0)
+#define KJB_LAUNCH_SYNC(ctx, kernel, dims, ...) do { kjb_emu::launch_sync(dims, [&]() { kernel(__VA_ARGS__); }); (ctx)->launches++; } while (0)
 #else
 #define KJB_KERNEL(bounds) __global__ void __launch_bounds__(bounds)
 #define KJB_LAUNCH(ctx, kernel, dims, ...) do { kernel<<<dims, 0, (ctx)->stream>>>(__VA_ARGS__); (ctx)->launches++; } while (0)
+#define KJB_LAUNCH_SYNC KJB_LAUNCH   /* kernels that use __syncthreads(): only the test emulator needs to know */
 #endif
 #define KJB_DIMS(...) __VA_ARGS__
 #define KJB_GRID2D(W, H, BX, BY) dim3(((W) + (BX) - 1) / (BX), ((H) + (BY) - 1) / (BY), 1), dim3((BX), (BY), 1)

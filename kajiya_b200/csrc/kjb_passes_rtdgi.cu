@@ -221,10 +221,10 @@ KJB_KERNEL(128) k_rtdgi_trace(Globals g, Img half_view_normal_tex, Img depth_tex
 // The shader exchanges values between lanes of its 8x8 group (WaveReadLaneAt ^2, ^16, ^1, ^8; lane = x + 8*y in 32-wide waves):
 // partners are pixels (x^2,y), (x,y^2), (x^1,y), (x,y^1).  Instead of shuffles tied to a block shape we evaluate the
 // pre-exchange value for the four pixels involved (25 one-byte taps each, all L1 hits) — same result, any block shape.
-KJB_DEV float d5_blur(const Img& input_tex, int x, int y) {
+KJB_DEV float d5_blur(const Img& input_tex, int x, int y, const float* w25) {   // w25[(yy+2)*5+(xx+2)] = exp2(-0.1 * r^2), host-evaluated
     float2 acc = f2(0.0f);
     for (int yy = -2; yy <= 2; ++yy) for (int xx = -2; xx <= 2; ++xx) {
-        const float w = kjb_exp2(-0.1f * float(xx * xx + yy * yy));
+        const float w = w25[(yy + 2) * 5 + (xx + 2)];
         acc += f2(ld_r8u(input_tex, x + xx, y + yy), 1) * w;
     }
     return (acc / acc.y).x;
@@ -240,10 +240,11 @@ KJB_DEV float d5_edge(const Img& reprojection_tex, const Img& half_depth_tex, in
     }
     return edge;
 }
-KJB_KERNEL(256) k_rtdgi_validity_integrate(Globals g, Img input_tex, Img history_tex, Img reprojection_tex, Img half_depth_tex, ImgW output_tex, float4 gts) {
+struct Weights25v { float w[25]; };
+KJB_KERNEL(256) k_rtdgi_validity_integrate(Globals g, Img input_tex, Img history_tex, Img reprojection_tex, Img half_depth_tex, ImgW output_tex, float4 gts, Weights25v wt) {
     KJB_PX; if (x >= output_tex.w || y >= output_tex.h) return;
-    const float b0 = kjb_lerp(d5_blur(input_tex, x, y), d5_blur(input_tex, x ^ 2, y), 0.5f);
-    const float b1 = kjb_lerp(d5_blur(input_tex, x, y ^ 2), d5_blur(input_tex, x ^ 2, y ^ 2), 0.5f);
+    const float b0 = kjb_lerp(d5_blur(input_tex, x, y, wt.w), d5_blur(input_tex, x ^ 2, y, wt.w), 0.5f);
+    const float b1 = kjb_lerp(d5_blur(input_tex, x, y ^ 2, wt.w), d5_blur(input_tex, x ^ 2, y ^ 2, wt.w), 0.5f);
     float inv = kjb_lerp(b0, b1, 0.5f);
     inv = kjb_smoothstep(0.0f, 1.0f, inv);
     const float e0 = kjb_max(d5_edge(reprojection_tex, half_depth_tex, x, y), d5_edge(reprojection_tex, half_depth_tex, x ^ 1, y));
@@ -595,22 +596,43 @@ KJB_KERNEL(256) k_rtdgi_restir_resolve(Globals g, ResolveImgs t, ImgW irradiance
 }
 
 // ------------------------------------------------------------------ D10 temporal_filter.hlsl:39-252
-KJB_KERNEL(256) k_rtdgi_temporal(Globals g, Img input_tex, Img history_tex, Img variance_history_tex, Img reprojection_tex, Img rt_history_invalidity_tex,
-                                 ImgW output_tex, ImgW history_output_tex, ImgW variance_history_output_tex, float4 ots) {
-    KJB_PX; const int W = output_tex.w, H = output_tex.h; if (x >= W || y >= H) return;
-    const float s4[4] = {ots.x, ots.y, ots.z, ots.w};
+// 5x5 moments over two images.  Each CTA stages its (32+4)x(16+4) footprint of BOTH images in shared memory already
+// converted to the crunched luma-chroma working space (sRGB->YCbCr, sqrt, divide), so the conversion runs once per texel
+// instead of once per tap (25x fewer), and the 50 taps per pixel become LDS instead of L1 requests.  The 25 Gaussian
+// weights exp(-3 r^2 / 9) are evaluated once on the host with the contract's kjb_exp and arrive as a kernel parameter.
+struct Weights25 { float w[25]; };
+#define D10_BX 32
+#define D10_BY 16
+#define D10_TW (D10_BX + 4)
+#define D10_TH (D10_BY + 4)
+KJB_KERNEL(512) k_rtdgi_temporal(Globals g, Img input_tex, Img history_tex, Img variance_history_tex, Img reprojection_tex, Img rt_history_invalidity_tex,
+                                 ImgW output_tex, ImgW history_output_tex, ImgW variance_history_output_tex, float4 ots, Weights25 wt) {
+    __shared__ float4 s_in[D10_TH * D10_TW];
+    __shared__ float s_hist_luma[D10_TH * D10_TW];
+    const int W = output_tex.w, H = output_tex.h;
+    const int bx0 = int(blockIdx.x) * D10_BX - 2, by0 = int(blockIdx.y) * D10_BY - 2;
     const float ped = g.fc.pre_exposure_delta;
-    const float2 uv = get_uv(x, y, s4);
-    const float4 center = linear_to_working(ld_rgba16f(input_tex, x, y));
-    const float4 reproj = ld_rgba16s(reprojection_tex, x, y);
     const float4 history_mult = f4(ped, ped, ped, 1);
+    for (int i = int(threadIdx.y) * D10_BX + int(threadIdx.x); i < D10_TW * D10_TH; i += D10_BX * D10_BY) {
+        const int tx = i % D10_TW, ty = i / D10_TW;
+        s_in[i] = linear_to_working(ld_rgba16f(input_tex, bx0 + tx, by0 + ty));
+        s_hist_luma[i] = linear_to_working(ld_rgba16f(history_tex, bx0 + tx, by0 + ty) * history_mult).x;
+    }
+    __syncthreads();
+    const int x = int(blockIdx.x) * D10_BX + int(threadIdx.x), y = int(blockIdx.y) * D10_BY + int(threadIdx.y);
+    if (x >= W || y >= H) return;
+    const float s4[4] = {ots.x, ots.y, ots.z, ots.w};
+    const float2 uv = get_uv(x, y, s4);
+    const int tcx = int(threadIdx.x) + 2, tcy = int(threadIdx.y) + 2;
+    const float4 center = s_in[tcy * D10_TW + tcx];
+    const float4 reproj = ld_rgba16s(reprojection_tex, x, y);
     const float4 history = linear_to_working(ld_rgba16f(history_tex, x, y) * history_mult);
     float4 vsum = f4(0.0f), vsum2 = f4(0.0f); float wsum = 0, hist_vsum = 0, hist_vsum2 = 0;
     for (int yy = -2; yy <= 2; ++yy) for (int xx = -2; xx <= 2; ++xx) {
-        const float4 neigh = linear_to_working(ld_rgba16f(input_tex, x + xx, y + yy));
-        const float4 hist_neigh = linear_to_working(ld_rgba16f(history_tex, x + xx, y + yy) * history_mult);
-        const float hist_luma = hist_neigh.x;
-        const float w = kjb_exp(-3.0f * float(xx * xx + yy * yy) / float((2 + 1.) * (2 + 1.)));
+        const int ti = (tcy + yy) * D10_TW + (tcx + xx);
+        const float4 neigh = s_in[ti];
+        const float hist_luma = s_hist_luma[ti];
+        const float w = wt.w[(yy + 2) * 5 + (xx + 2)];
         vsum += neigh * w; vsum2 += neigh * neigh * w; wsum += w;
         hist_vsum += hist_luma * w; hist_vsum2 += hist_luma * hist_luma * w;
     }
@@ -721,8 +743,10 @@ int kjb_pass_rtdgi_validity_integrate(kjb_context* c, const kjb_rtdgi_validity_i
     const char* P = "validity integrate"; const uint32_t W = a->output_tex.width, H = a->output_tex.height;
     CHK(a->output_tex, KJB_FMT_RG16_FLOAT, "output_tex"); CHKE(a->input_tex, KJB_FMT_R8_UNORM, "input_tex", W, H); CHKE(a->history_tex, KJB_FMT_RG16_FLOAT, "history_tex", W, H);
     CHK(a->reprojection_tex, KJB_FMT_RGBA16_SNORM, "reprojection_tex"); CHKE(a->half_depth_tex, KJB_FMT_R32_FLOAT, "half_depth_tex", W, H);
+    Weights25v wt;
+    for (int yy = -2; yy <= 2; ++yy) for (int xx = -2; xx <= 2; ++xx) wt.w[(yy + 2) * 5 + (xx + 2)] = kjb_exp2(-0.1f * float(xx * xx + yy * yy));
     KJB_LAUNCH(c, k_rtdgi_validity_integrate, KJB_GRID2D(W, H, 32, 8), c->g, img_ro(a->input_tex), img_ro(a->history_tex), img_ro(a->reprojection_tex), img_ro(a->half_depth_tex), img_rw(a->output_tex),
-               F4A(a->gbuffer_tex_size));
+               F4A(a->gbuffer_tex_size), wt);
     KJB_PASS_EPILOGUE(c, P);
 }
 int kjb_pass_rtdgi_restir_temporal(kjb_context* c, const kjb_rtdgi_restir_temporal_args* a) {
@@ -779,8 +803,10 @@ int kjb_pass_rtdgi_temporal(kjb_context* c, const kjb_rtdgi_temporal_args* a) {
     CHKE(a->variance_history_tex, KJB_FMT_RG16_FLOAT, "variance_history_tex", W, H); CHKE(a->reprojection_tex, KJB_FMT_RGBA16_SNORM, "reprojection_tex", W, H);
     CHK(a->rt_history_invalidity_tex, KJB_FMT_RG16_FLOAT, "rt_history_invalidity_tex"); CHKE(a->history_output_tex, KJB_FMT_RGBA16_FLOAT, "history_output_tex", W, H);
     CHKE(a->variance_history_output_tex, KJB_FMT_RG16_FLOAT, "variance_history_output_tex", W, H);
-    KJB_LAUNCH(c, k_rtdgi_temporal, KJB_GRID2D(W, H, 32, 8), c->g, img_ro(a->input_tex), img_ro(a->history_tex), img_ro(a->variance_history_tex), img_ro(a->reprojection_tex), img_ro(a->rt_history_invalidity_tex),
-               img_rw(a->output_tex), img_rw(a->history_output_tex), img_rw(a->variance_history_output_tex), F4A(a->output_tex_size));
+    Weights25 wt;
+    for (int yy = -2; yy <= 2; ++yy) for (int xx = -2; xx <= 2; ++xx) wt.w[(yy + 2) * 5 + (xx + 2)] = kjb_exp(-3.0f * float(xx * xx + yy * yy) / float((2 + 1.) * (2 + 1.)));
+    KJB_LAUNCH_SYNC(c, k_rtdgi_temporal, KJB_GRID2D(W, H, D10_BX, D10_BY), c->g, img_ro(a->input_tex), img_ro(a->history_tex), img_ro(a->variance_history_tex), img_ro(a->reprojection_tex), img_ro(a->rt_history_invalidity_tex),
+               img_rw(a->output_tex), img_rw(a->history_output_tex), img_rw(a->variance_history_output_tex), F4A(a->output_tex_size), wt);
     KJB_PASS_EPILOGUE(c, P);
 }
 int kjb_pass_rtdgi_spatial(kjb_context* c, const kjb_rtdgi_spatial_args* a) {

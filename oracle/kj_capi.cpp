@@ -71,6 +71,26 @@ int kjb_ray_counters(kjb_context* c, uint64_t out[2], int reset) {
     return 0;
 }
 
+// test-only known-answer hooks for the numeric core (tests/test_oracle_kat.py, vectors in tests/golden/kat_vectors.json)
+uint32_t kjo_hash1(uint32_t x) { return hash1(x); }
+uint32_t kjo_hash3(uint32_t x, uint32_t y, uint32_t z) { return hash3(x, y, z); }
+uint32_t kjo_hash_combine2(uint32_t x, uint32_t y) { return hash_combine2(x, y); }
+float kjo_u01(uint32_t h) { return uint_to_u01_float(h); }
+uint32_t kjo_pack_normal_11_10_11(float x, float y, float z) { return asuint(pack_normal_11_10_11(float3(x, y, z))); }
+void kjo_unpack_normal_11_10_11_no_normalize(uint32_t p, float* o) { float3 v = unpack_normal_11_10_11_no_normalize(asfloat(p)); o[0] = v.x; o[1] = v.y; o[2] = v.z; }
+uint32_t kjo_float3_to_rgb9e5(float x, float y, float z) { return float3_to_rgb9e5(float3(x, y, z)); }
+void kjo_rgb9e5_to_float3(uint32_t p, float* o) { float3 v = rgb9e5_to_float3(p); o[0] = v.x; o[1] = v.y; o[2] = v.z; }
+uint32_t kjo_pack_color_888(float x, float y, float z) { return pack_color_888(float3(x, y, z)); }
+uint32_t kjo_pack_2x16f(float a, float b) { return pack_2x16f_uint(float2(a, b)); }
+// streams `n` (w, payload) candidates through Reservoir1spp::update with rng seed; returns payload, writes M, w_sum, rng
+uint32_t kjo_reservoir_stream(uint32_t seed, const float* w, const uint32_t* payload, uint32_t n, float* out_m_wsum, uint32_t* out_rng) {
+    Reservoir1spp r; uint32_t rng = seed;
+    for (uint32_t i = 0; i < n; ++i) r.update(w[i], payload[i], rng);
+    out_m_wsum[0] = r.M; out_m_wsum[1] = r.w_sum; *out_rng = rng;
+    return r.payload;
+}
+void kjo_halfres_offset(uint32_t frame, int* o) { int2 v = halfres_subsample_offset(frame); o[0] = v.x; o[1] = v.y; }
+
 // test-only helpers (not part of kjb.h): brute-force vs BVH closest hit for the traversal self-check
 int kjo_trace_closest(kjb_context* c, const float* rays /* n x 8: o.xyz, tmin, d.xyz, tmax */, uint32_t n, int brute, float* out_t, uint32_t* out_tri) {
     for (uint32_t i = 0; i < n; ++i) {

@@ -20,6 +20,7 @@
 #define __forceinline__ inline
 #define __launch_bounds__(...)
 #define __restrict__
+#define __shared__ static thread_local
 
 struct float2 { float x, y; };
 struct float3 { float x, y, z; };
@@ -60,4 +61,27 @@ template <typename F> inline void launch(dim3 grid, dim3 block, F body) {
     for (int i = 0; i < n; ++i) th.emplace_back(worker);
     for (auto& t : th) t.join();
 }
+// Kernels that use __syncthreads(): every thread of a block runs as a ucontext fiber; a barrier yields to the block
+// scheduler, which resumes each unfinished fiber once per barrier phase.
+void fiber_run_block(unsigned nthreads, dim3 block, void (*thread_body)(void*), void* arg);
+void fiber_barrier();
+template <typename F> inline void launch_sync(dim3 grid, dim3 block, F body) {
+    const long nblocks = long(grid.x) * grid.y * grid.z;
+    std::atomic<long> next{0};
+    auto worker = [&]() {
+        for (;;) {
+            const long b = next.fetch_add(1);
+            if (b >= nblocks) break;
+            gridDim = grid; blockDim = block;
+            blockIdx.x = unsigned(b % grid.x); blockIdx.y = unsigned((b / grid.x) % grid.y); blockIdx.z = unsigned(b / (long(grid.x) * grid.y));
+            fiber_run_block(block.x * block.y * block.z, block, [](void* p) { (*static_cast<F*>(p))(); }, &body);
+        }
+    };
+    const int n = nblocks < 4 ? 1 : num_workers();
+    if (n <= 1) { worker(); return; }
+    std::vector<std::thread> th;
+    for (int i = 0; i < n; ++i) th.emplace_back(worker);
+    for (auto& t : th) t.join();
+}
 }  // namespace kjb_emu
+inline void __syncthreads() { kjb_emu::fiber_barrier(); }

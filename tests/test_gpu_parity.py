@@ -67,3 +67,11 @@ def test_full_size_properties(cuda_lib):
     res = w1.image("rtdgi.reservoir_output0")
     px, py = res[..., 0] & 0xffff, res[..., 0] >> 16
     assert (px < 960).all() and (py < 540).all()
+
+
+def test_taa_native_and_upscaled(oracle_lib, cuda_lib):
+    scene, view = scenes.cornell_box()
+    for kw in (dict(enable_taa=True), dict(enable_taa=True, upscale=(240, 135))):
+        _, wb, report = parity.run_lockstep(oracle_lib, cuda_lib, scene, view, 160, 90, 6, **kw)
+        _assert_clean(report)
+        assert "taa.this_frame_out" in wb.image_names()
