@@ -204,6 +204,23 @@ int  kjb_set_luts(kjb_context *ctx, const kjb_image *brdf_fg_lut, const kjb_imag
 /* ray statistics accumulated by tracing passes since the last reset: [0] closest-hit rays, [1] any-hit (shadow) rays */
 int  kjb_ray_counters(kjb_context *ctx, uint64_t out_counts[2], int reset);
 
+/* ------------------------------------------------------------------ multi-GPU plumbing for tile-sharded frames
+ * One process per GPU.  The only data-path collective of a frame is ONE all-gather of packed row strips (tile borders of the
+ * temporal ReSTIR/TAA state + each rank's band of the full-res GI history).  The CUDA build performs it with NCCL on the
+ * context's stream (ncclAllGather; libnccl is dlopen'ed by kjb_comm_init_nccl, the unique id is distributed by the caller,
+ * e.g. with torch.distributed); CPU test builds and custom transports register a callback instead. */
+typedef int (*kjb_allgather_fn)(void *user, const void *send, void *recv, uint64_t bytes_per_rank);
+int  kjb_comm_nccl_unique_id(void *out_128_bytes);
+int  kjb_comm_init_nccl(kjb_context *ctx, const void *unique_id_128_bytes, uint32_t rank, uint32_t nranks);
+int  kjb_comm_set_callback(kjb_context *ctx, kjb_allgather_fn fn, void *user, uint32_t rank, uint32_t nranks);
+int  kjb_comm_rank(kjb_context *ctx, uint32_t *rank, uint32_t *nranks);
+int  kjb_allgather(kjb_context *ctx, const void *send, void *recv, uint64_t bytes_per_rank);     /* enqueued on the stream */
+int  kjb_memcpy_d2d(kjb_context *ctx, void *dst, const void *src, uint64_t bytes);                /* enqueued on the stream */
+
+/* Tile-sharded frames: restrict the FOLLOWING passes to rows [y0, y1) of their own output grid
+ * (each rank of a multi-GPU frame computes its band plus the halo a pass's consumers need).  (0, 0) = whole image. */
+int  kjb_set_scissor(kjb_context *ctx, uint32_t y0, uint32_t y1);
+
 /* ------------------------------------------------------------------ input producers (needed to feed the path) */
 typedef struct kjb_raster_gbuffer_args {   /* replaces "raster simple" (raster_simple_ps.hlsl:39-140) by primary-ray casting */
     kjb_image geometric_normal_out;        /* A2R10G10B10_UNORM, view-space normal *0.5+0.5 */

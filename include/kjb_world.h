@@ -27,6 +27,9 @@ typedef struct kjb_world_desc {
     uint32_t enable_ircache, enable_rtr, enable_taa;
     /* Tile sharding: this process renders half-res rows [tile_y0, tile_y1) plus a halo. 0,0 = whole frame. */
     uint32_t tile_y0, tile_y1;
+    /* Tile sharding by rank: with tile_count > 1 this world renders the tile_rank-th of tile_count horizontal bands (balanced
+     * split of the half-res rows) and exchanges band borders once per frame through kjb_allgather. Overrides tile_y0/y1. */
+    uint32_t tile_rank, tile_count;
 } kjb_world_desc;
 
 /* TriangleMesh as the asset pipeline hands it to add_mesh (kajiya-asset/src/mesh.rs:85-98) */

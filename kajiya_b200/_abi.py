@@ -38,7 +38,8 @@ class TextureDesc(C.Structure):
 class WorldDesc(C.Structure):
     _fields_ = [("render_width", C.c_uint32), ("render_height", C.c_uint32), ("temporal_upscale_width", C.c_uint32), ("temporal_upscale_height", C.c_uint32),
                 ("spatial_reuse_pass_count", C.c_uint32), ("use_raytraced_reservoir_visibility", C.c_uint32),
-                ("enable_ircache", C.c_uint32), ("enable_rtr", C.c_uint32), ("enable_taa", C.c_uint32), ("tile_y0", C.c_uint32), ("tile_y1", C.c_uint32)]
+                ("enable_ircache", C.c_uint32), ("enable_rtr", C.c_uint32), ("enable_taa", C.c_uint32), ("tile_y0", C.c_uint32), ("tile_y1", C.c_uint32),
+                ("tile_rank", C.c_uint32), ("tile_count", C.c_uint32)]
 
 
 class MeshDesc(C.Structure):
@@ -98,6 +99,9 @@ class KjbLib:
             "kjb_world_last_frame_stats": (C.c_int, [P, C.POINTER(C.c_uint64 * 4)]),
             "kjb_world_set_stop_after": (C.c_int, [P, C.c_char_p]),
             "kjb_world_set_profiling": (C.c_int, [P, C.c_uint32]),
+            "kjb_comm_nccl_unique_id": (C.c_int, [P]),
+            "kjb_comm_init_nccl": (C.c_int, [P, P, C.c_uint32, C.c_uint32]),
+            "kjb_comm_set_callback": (C.c_int, [P, P, P, C.c_uint32, C.c_uint32]),
             "kjb_world_pass_timings": (C.c_char_p, [P]),
             "kjb_timer_record": (C.c_int, [P, C.c_uint32]),
             "kjb_timer_elapsed_ms": (C.c_int, [P, C.c_uint32, C.c_uint32, C.POINTER(C.c_float)]),

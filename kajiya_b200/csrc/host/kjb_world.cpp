@@ -8,6 +8,7 @@
 // It only calls the C-ABI in include/kjb.h.  No GPU, CUDA or oracle symbols are referenced directly.
 #include "../../../include/kjb_world.h"
 #include <cmath>
+#include <algorithm>
 #include <cstring>
 #include <map>
 #include <string>
@@ -112,6 +113,24 @@ struct kjb_world {
     uint32_t OW = 0, OH = 0;   // temporal_upscale_extent
 
     int err = 0;
+    // ---- tile sharding: this world owns half-res rows [ty0, ty1) of every frame
+    bool tiled = false; uint32_t trank = 0, tcount = 1, ty0 = 0, ty1 = 0;
+    kjb_buffer xchg_send{}, xchg_recv{}; uint64_t xchg_bytes_per_rank = 0;
+    void band(uint32_t r, uint32_t rows, uint32_t& b0, uint32_t& b1) const { b0 = uint32_t(uint64_t(rows) * r / tcount); b1 = uint32_t(uint64_t(rows) * (r + 1) / tcount); }
+    // restrict the next pass to the owned band grown by `e` half-res rows; `scale` = 2 for full-res passes
+    uint32_t cur_row0 = 0;   // first row of the scissor last set by rows()
+    void rows(uint32_t e, uint32_t scale) {
+        if (!tiled) return;
+        const uint32_t a = ty0 > e ? ty0 - e : 0, b = ty1 + e;
+        cur_row0 = a * scale;
+        kjb_set_scissor(ctx, a * scale, b * scale);
+    }
+    void rows_all() { if (tiled) kjb_set_scissor(ctx, 0, 0); }
+    void rows_full(uint32_t e_full) {   // full-res pass: owned full-res rows grown by e_full rows
+        if (!tiled) return;
+        const uint32_t a = ty0 * 2 > e_full ? ty0 * 2 - e_full : 0, b = ty1 * 2 + e_full;
+        kjb_set_scissor(ctx, a, b);
+    }
     bool profiling = false; uint32_t timer_next = 0;
     std::vector<std::pair<std::string, std::pair<uint32_t, uint32_t>>> timer_pending;   // label -> (slot_begin, slot_end) of this frame
     std::map<std::string, std::pair<uint32_t, double>> pass_ms;                          // label -> (calls, total ms)
@@ -154,6 +173,9 @@ struct kjb_world {
     }
 };
 
+// tile mode: additionally run the pass on rows [0, top) when the main range starts below them (pixel (0,0) dependency)
+#define RUN_TOP(label, call, top) do { if (w->tiled && !w->stopped && !w->err) { const uint32_t e__ = w->cur_row0; if (e__ > 0) { \
+        kjb_set_scissor(w->ctx, 0, std::min<uint32_t>((top), e__)); int rc2__ = (call); if (rc2__) w->err = rc2__; } } } while (0)
 #define RUN(label, call) do { if (w->stopped || w->err) break; w->pass_begin(label); int rc__ = (call); w->pass_end(); w->pass_done(label, rc__); } while (0)
 
 static void size4(float out[4], const kjb_image& i) { out[0] = float(i.width); out[1] = float(i.height); out[2] = 1.0f / float(i.width); out[3] = 1.0f / float(i.height); }
@@ -167,6 +189,11 @@ int kjb_world_create(kjb_context* ctx, const kjb_world_desc* desc, kjb_world** o
     w->W = desc->render_width; w->H = desc->render_height;
     w->HW = (w->W + 1) / 2; w->HH = (w->H + 1) / 2;   // ImageDesc::half_res = div_up (image.rs:140-142)
     w->OW = desc->temporal_upscale_width ? desc->temporal_upscale_width : w->W; w->OH = desc->temporal_upscale_height ? desc->temporal_upscale_height : w->H;
+    if (desc->tile_count > 1) {
+        if (w->OW != w->W || w->OH != w->H || (w->H & 1)) { delete w; return 1; }   // tiles + temporal upscaling / odd heights: not supported
+        w->tiled = true; w->trank = desc->tile_rank; w->tcount = desc->tile_count;
+        w->band(w->trank, w->HH, w->ty0, w->ty1);
+    }
     *out = w;
     return 0;
 }
@@ -360,6 +387,91 @@ static void end_frame(kjb_world* w) {
     w->frame_idx += 1;   // retire_frame (world_renderer.rs:1110-1113)
 }
 
+
+// ---------------------------------------------------------------- tile sharding: halos and the per-frame border exchange
+// Half-res rows a pass must compute beyond the owned band so that every later pass of the SAME frame finds valid inputs
+// (derived from the shaders' stencils: restir_spatial.hlsl:89-92 radii 32/16/8, payload indirection `spx`, resolve ~3,
+// temporal filter 5x5, spatial filter <=16 px, taa 3x3..5x5).  History older than this frame comes from the exchange.
+struct TileHalos { uint32_t d11, d10, d9, spatial_last, d6, d5, d4, halo, border; };
+static TileHalos tile_halos(const kjb_world* w) {
+    TileHalos h{};
+    const uint32_t x = w->desc.enable_taa ? 6u : 0u;
+    uint32_t sum_r = 0;
+    for (uint32_t i = 0; i < w->desc.spatial_reuse_pass_count; ++i) sum_r += i == 0 ? 32u : (i == 1 ? 16u : 8u);
+    h.d11 = x; h.d10 = x + 8; h.d9 = x + 9; h.spatial_last = x + 12;
+    h.d6 = x + 12 + sum_r; h.d5 = h.d6; h.d4 = h.d6 + 4; h.halo = h.d6 + 8; h.border = h.halo + 4;
+    return h;
+}
+static uint32_t spatial_radius(uint32_t pass_idx) { return pass_idx == 0 ? 32u : (pass_idx == 1 ? 16u : 8u); }
+
+static const uint32_t TILE_TOP_ROWS = 16;   // half-res rows at the top of the image kept valid on every rank (pixel (0,0) dependency)
+
+struct XchgItem { kjb_image img; uint32_t scale; uint32_t border; };   // border in image rows; 0 = whole band
+
+// ONE all-gather per frame: every rank contributes the top and bottom `border` rows of its band of each temporal image (its
+// whole band for the full-res GI history, which the next frame's rays sample at arbitrary screen positions), and copies the
+// strips it needs from the other ranks' contributions into its own images.  Row strips of row-major images are contiguous.
+static int tile_exchange(kjb_world* w, const std::vector<XchgItem>& items) {
+    kjb_context* ctx = w->ctx;
+    const uint32_t n = w->tcount;
+    uint32_t band_max = 0;
+    for (uint32_t r = 0; r < n; ++r) { uint32_t b0, b1; w->band(r, w->HH, b0, b1); band_max = std::max(band_max, b1 - b0); }
+    // layout of one rank's contribution
+    std::vector<uint64_t> off(items.size()), strip_bytes(items.size());
+    uint64_t total = 0;
+    for (size_t i = 0; i < items.size(); ++i) {
+        const uint64_t row_bytes = uint64_t(items[i].img.width) * kjb_format_texel_bytes(items[i].img.format);
+        const uint32_t rows_max = items[i].border ? std::min(items[i].border, band_max * items[i].scale) : band_max * items[i].scale;
+        strip_bytes[i] = row_bytes * rows_max;
+        off[i] = total; total += strip_bytes[i] * (items[i].border ? 2 : 1);
+    }
+    total = (total + 255) / 256 * 256;
+    if (w->xchg_bytes_per_rank != total) {
+        if (w->xchg_send.data) { kjb_sync(ctx); kjb_buffer_free(ctx, &w->xchg_send); kjb_buffer_free(ctx, &w->xchg_recv); }
+        if (kjb_buffer_alloc(ctx, total, &w->xchg_send) || kjb_buffer_alloc(ctx, total * n, &w->xchg_recv)) return 1;
+        w->xchg_bytes_per_rank = total;
+    }
+    auto strips_of = [&](uint32_t r, const XchgItem& it, uint32_t out[2][2]) {   // [strip][row0,row1) in image rows
+        uint32_t b0, b1; w->band(r, w->HH, b0, b1); b0 *= it.scale; b1 *= it.scale;
+        if (!it.border) { out[0][0] = b0; out[0][1] = b1; out[1][0] = out[1][1] = 0; return; }
+        const uint32_t k = std::min(it.border, b1 - b0);
+        out[0][0] = b0; out[0][1] = b0 + k; out[1][0] = b1 - k; out[1][1] = b1;
+    };
+    // pack
+    for (size_t i = 0; i < items.size(); ++i) {
+        const uint64_t row_bytes = uint64_t(items[i].img.width) * kjb_format_texel_bytes(items[i].img.format);
+        uint32_t st[2][2]; strips_of(w->trank, items[i], st);
+        for (int k = 0; k < (items[i].border ? 2 : 1); ++k)
+            if (kjb_memcpy_d2d(ctx, (char*)w->xchg_send.data + off[i] + strip_bytes[i] * k, (const char*)items[i].img.data + row_bytes * st[k][0], row_bytes * (st[k][1] - st[k][0]))) return 1;
+    }
+    if (kjb_allgather(ctx, w->xchg_send.data, w->xchg_recv.data, total)) return 1;
+    // unpack what this rank reads next frame: its band grown by `border` rows (everything for whole-band items)
+    for (uint32_t r = 0; r < n; ++r) {
+        if (r == w->trank) continue;
+        const char* base = (const char*)w->xchg_recv.data + total * r;
+        for (size_t i = 0; i < items.size(); ++i) {
+            const uint64_t row_bytes = uint64_t(items[i].img.width) * kjb_format_texel_bytes(items[i].img.format);
+            uint32_t mine[2][2]; strips_of(w->trank, items[i], mine);
+            const uint32_t my0 = mine[0][0], my1 = items[i].border ? mine[1][1] : mine[0][1];
+            const uint32_t need0 = items[i].border ? (my0 > items[i].border ? my0 - items[i].border : 0) : 0;
+            const uint32_t need1 = items[i].border ? my1 + items[i].border : 0xffffffffu;
+            uint32_t st[2][2]; strips_of(r, items[i], st);
+            // Reservoirs that never selected a sample keep payload 0 == pixel (0,0) (reservoir.hlsl:18-24), so restir_temporal /
+            // restir_spatial / restir_resolve dereference the state of pixel (0,0) from anywhere on screen: the first rows of the
+            // image are a global dependency and travel to every rank.
+            const uint32_t top = items[i].border ? TILE_TOP_ROWS * items[i].scale : 0;
+            const uint32_t iv[2][2] = {{need0, need1}, {0, need0 > top ? top : 0}};
+            for (int k = 0; k < (items[i].border ? 2 : 1); ++k) for (int v = 0; v < 2; ++v) {
+                uint32_t a = std::max(st[k][0], iv[v][0]), b = std::min(st[k][1], iv[v][1]);
+                if (k == 1 && items[i].border) a = std::max(a, st[0][1]);   // rows already delivered by the top strip (band <= 2*border)
+                if (a >= b) continue;
+                if (kjb_memcpy_d2d(ctx, (char*)items[i].img.data + row_bytes * a, base + off[i] + strip_bytes[i] * k + row_bytes * (a - st[k][0]), row_bytes * (b - a))) return 1;
+            }
+        }
+    }
+    return 0;
+}
+
 // ---------------------------------------------------------------- RtdgiRenderer::render (rtdgi.rs:173-554)
 static void rtdgi_render(kjb_world* w, kjb_image& reprojected_history_tex, kjb_image& temporal_output_tex, kjb_image& gbuffer, kjb_image& depth,
                          kjb_image& geometric_normal, kjb_image& reprojection_map, kjb_image& sky_cube, kjb_image& ssao_tex) {
@@ -367,6 +479,8 @@ static void rtdgi_render(kjb_world* w, kjb_image& reprojected_history_tex, kjb_i
     const uint32_t HW = w->HW, HH = w->HH, W = w->W, H = w->H;
     float gbuffer_size[4]; size4(gbuffer_size, gbuffer);
     kjb_ircache_bindings no_ircache{};   // TODO(ircache): bind IrcacheRenderState when enable_ircache
+    const TileHalos th = tile_halos(w);
+    w->rows_all();   // the half-res extracts are cheap and read at arbitrary screen positions (ray march): whole image
 
     kjb_image& half_ssao_tex = w->img("rtdgi.half_ssao", HW, HH, KJB_FMT_R8_SNORM);
     { kjb_extract_half_res_args a{ssao_tex, half_ssao_tex}; RUN("extract ssao/2", kjb_pass_extract_half_res_ssao(ctx, &a)); }
@@ -398,7 +512,9 @@ static void rtdgi_render(kjb_world* w, kjb_image& reprojected_history_tex, kjb_i
         a.reservoir_tex = *reservoir_history_tex; a.reservoir_ray_history_tex = *ray_history_tex; a.reprojection_tex = reprojection_map;
         a.ircache = no_ircache; a.sky_cube_tex = sky_cube; a.irradiance_history_tex = *radiance_history_tex; a.ray_orig_history_tex = *ray_orig_history_tex;
         a.rt_history_invalidity_out_tex = rt_history_validity_pre_input_tex; memcpy(a.gbuffer_tex_size, gbuffer_size, 16);
+        w->rows(th.d4, 1);
         RUN("rtdgi validate", kjb_pass_rtdgi_validate(ctx, &a));
+        RUN_TOP("rtdgi validate", kjb_pass_rtdgi_validate(ctx, &a), 12);
     }
     kjb_image& rt_history_validity_input_tex = w->img("rtdgi.rt_history_validity_input", HW, HH, KJB_FMT_R8_UNORM);
     {   // "rtdgi trace" (rtdgi.rs:321-345)
@@ -408,14 +524,18 @@ static void rtdgi_render(kjb_world* w, kjb_image& reprojected_history_tex, kjb_i
         a.candidate_irradiance_out_tex = candidate_radiance_tex; a.candidate_normal_out_tex = candidate_normal_tex; a.candidate_hit_out_tex = candidate_hit_tex;
         a.rt_history_invalidity_in_tex = rt_history_validity_pre_input_tex; a.rt_history_invalidity_out_tex = rt_history_validity_input_tex;
         memcpy(a.gbuffer_tex_size, gbuffer_size, 16);
+        w->rows(th.d4, 1);
         RUN("rtdgi trace", kjb_pass_rtdgi_trace(ctx, &a));
+        RUN_TOP("rtdgi trace", kjb_pass_rtdgi_trace(ctx, &a), 12);
     }
     {   // "validity integrate" (rtdgi.rs:347-361)
         kjb_rtdgi_validity_integrate_args a{};
         a.input_tex = rt_history_validity_input_tex; a.history_tex = *invalidity_history_tex; a.reprojection_tex = reprojection_map;
         a.half_view_normal_tex = half_view_normal_tex; a.half_depth_tex = half_depth_tex; a.output_tex = *invalidity_output_tex;
         memcpy(a.gbuffer_tex_size, gbuffer_size, 16); size4(a.output_tex_size, *invalidity_output_tex);
+        w->rows(th.d5, 1);
         RUN("validity integrate", kjb_pass_rtdgi_validity_integrate(ctx, &a));
+        RUN_TOP("validity integrate", kjb_pass_rtdgi_validity_integrate(ctx, &a), 8);
     }
     {   // "restir temporal" (rtdgi.rs:363-389)
         kjb_rtdgi_restir_temporal_args a{};
@@ -426,7 +546,9 @@ static void rtdgi_render(kjb_world* w, kjb_image& reprojected_history_tex, kjb_i
         a.radiance_out_tex = *radiance_output_tex; a.ray_orig_output_tex = *ray_orig_output_tex; a.ray_output_tex = *ray_output_tex; a.hit_normal_output_tex = *hit_normal_output_tex;
         a.reservoir_out_tex = *reservoir_output_tex; a.candidate_out_tex = *candidate_output_tex; a.temporal_reservoir_packed_tex = temporal_reservoir_packed_tex;
         memcpy(a.gbuffer_tex_size, gbuffer_size, 16);
+        w->rows(th.d6, 1);
         RUN("restir temporal", kjb_pass_rtdgi_restir_temporal(ctx, &a));
+        RUN_TOP("restir temporal", kjb_pass_rtdgi_restir_temporal(ctx, &a), 2);
     }
     kjb_image& radiance_tex = *radiance_output_tex;
     kjb_image* reservoir_input_tex = reservoir_output_tex;
@@ -442,6 +564,7 @@ static void rtdgi_render(kjb_world* w, kjb_image& reprojected_history_tex, kjb_i
         a.spatial_reuse_pass_idx = pass_idx;
         a.perform_occlusion_raymarch = (pass_idx + 1 == w->desc.spatial_reuse_pass_count) ? 1u : 0u;
         a.occlusion_raymarch_importance_only = w->desc.use_raytraced_reservoir_visibility ? 1u : 0u;
+        { uint32_t e = th.spatial_last; for (uint32_t j = pass_idx + 1; j < w->desc.spatial_reuse_pass_count; ++j) e += spatial_radius(j); w->rows(e, 1); }
         RUN("restir spatial", kjb_pass_rtdgi_restir_spatial(ctx, &a));
         std::swap(reservoir_output_tex0, reservoir_output_tex1);
         reservoir_input_tex = reservoir_output_tex1;
@@ -453,6 +576,7 @@ static void rtdgi_render(kjb_world* w, kjb_image& reprojected_history_tex, kjb_i
         a.half_depth_tex = half_depth_tex; a.ssao_tex = ssao_tex; a.candidate_radiance_tex = candidate_radiance_tex; a.candidate_hit_tex = candidate_hit_tex;
         a.temporal_reservoir_packed_tex = temporal_reservoir_packed_tex; a.bounced_radiance_input_tex = none; a.irradiance_output_tex = irradiance_output_tex;
         memcpy(a.gbuffer_tex_size, gbuffer_size, 16); size4(a.output_tex_size, irradiance_output_tex);
+        w->rows(th.d9, 2);
         RUN("restir resolve", kjb_pass_rtdgi_restir_resolve(ctx, &a));
     }
     // RtdgiRenderer::temporal (rtdgi.rs:71-115)
@@ -464,6 +588,7 @@ static void rtdgi_render(kjb_world* w, kjb_image& reprojected_history_tex, kjb_i
         a.rt_history_invalidity_tex = *invalidity_output_tex; a.output_tex = temporal_filtered_tex; a.history_output_tex = temporal_output_tex;
         a.variance_history_output_tex = *temporal_variance_output_tex;
         size4(a.output_tex_size, temporal_output_tex); memcpy(a.gbuffer_tex_size, gbuffer_size, 16);
+        w->rows(th.d10, 2);
         RUN("rtdgi temporal", kjb_pass_rtdgi_temporal(ctx, &a));
     }
     // RtdgiRenderer::spatial (rtdgi.rs:117-141)
@@ -472,6 +597,7 @@ static void rtdgi_render(kjb_world* w, kjb_image& reprojected_history_tex, kjb_i
         kjb_rtdgi_spatial_args a{};
         a.input_tex = temporal_filtered_tex; a.depth_tex = depth; a.ssao_tex = ssao_tex; a.geometric_normal_tex = geometric_normal; a.output_tex = spatial_filtered_tex;
         size4(a.output_tex_size, spatial_filtered_tex);
+        w->rows(th.d11, 2);
         RUN("rtdgi spatial", kjb_pass_rtdgi_spatial(ctx, &a));
     }
 }
@@ -487,36 +613,36 @@ static kjb_image* taa_render(kjb_world* w, kjb_image& input_tex, kjb_image& repr
     {
         kjb_taa_reproject_args a{}; a.history_tex = *history_tex; a.reprojection_tex = reprojection_map; a.depth_tex = depth_tex; a.output_tex = reprojected_history_img;
         a.closest_velocity_output = closest_velocity_img; size4(a.input_tex_size, input_tex); size4(a.output_tex_size, reprojected_history_img);
-        RUN("reproject taa", kjb_pass_taa_reproject(ctx, &a));
+        w->rows_full(12); RUN("reproject taa", kjb_pass_taa_reproject(ctx, &a));
     }
     kjb_image *smooth_var_output_tex, *smooth_var_history_tex; w->get_output_and_history(w->taa_temporal_smooth_var_tex, OW, OH, KJB_FMT_RGBA16_FLOAT, smooth_var_output_tex, smooth_var_history_tex);
     kjb_image& filtered_input_img = w->img("taa.filtered_input", IW, IH, KJB_FMT_RGBA16_FLOAT);
     kjb_image& filtered_input_deviation_img = w->img("taa.filtered_input_deviation", IW, IH, KJB_FMT_RGBA16_FLOAT);
-    { kjb_taa_filter_input_args a{input_tex, depth_tex, filtered_input_img, filtered_input_deviation_img}; RUN("taa filter input", kjb_pass_taa_filter_input(ctx, &a)); }
+    { kjb_taa_filter_input_args a{input_tex, depth_tex, filtered_input_img, filtered_input_deviation_img}; w->rows_full(10); RUN("taa filter input", kjb_pass_taa_filter_input(ctx, &a)); }
     kjb_image& filtered_history_img = w->img("taa.filtered_history", IW, IH, KJB_FMT_RGBA16_FLOAT);
     {
         kjb_taa_filter_history_args a{}; a.input_tex = reprojected_history_img; a.output_tex = filtered_history_img;
         size4(a.input_tex_size, reprojected_history_img); size4(a.output_tex_size, input_tex);
-        RUN("taa filter history", kjb_pass_taa_filter_history(ctx, &a));
+        w->rows_full(8); RUN("taa filter history", kjb_pass_taa_filter_history(ctx, &a));
     }
     kjb_image& input_prob_img = w->img("taa.input_prob", IW, IH, KJB_FMT_R16_FLOAT);
     {
         kjb_taa_input_prob_args a{}; a.input_tex = input_tex; a.filtered_input_tex = filtered_input_img; a.filtered_input_dev_tex = filtered_input_deviation_img;
         a.history_tex = reprojected_history_img; a.filtered_history_tex = filtered_history_img; a.reprojection_tex = reprojection_map; a.depth_tex = depth_tex;
         a.smooth_var_history_tex = *smooth_var_history_tex; a.velocity_history_tex = *velocity_history_tex; a.output_tex = input_prob_img; size4(a.input_tex_size, input_tex);
-        RUN("taa input prob", kjb_pass_taa_input_prob(ctx, &a));
+        w->rows_full(6); RUN("taa input prob", kjb_pass_taa_input_prob(ctx, &a));
     }
     kjb_image& prob_filtered1_img = w->img("taa.prob_filtered1", IW, IH, KJB_FMT_R16_FLOAT);
-    { kjb_taa_prob_filter_args a{input_prob_img, prob_filtered1_img}; RUN("taa prob filter", kjb_pass_taa_prob_filter(ctx, &a)); }
+    { kjb_taa_prob_filter_args a{input_prob_img, prob_filtered1_img}; w->rows_full(5); RUN("taa prob filter", kjb_pass_taa_prob_filter(ctx, &a)); }
     kjb_image& prob_filtered2_img = w->img("taa.prob_filtered2", IW, IH, KJB_FMT_R16_FLOAT);
-    { kjb_taa_prob_filter_args a{prob_filtered1_img, prob_filtered2_img}; RUN("taa prob filter2", kjb_pass_taa_prob_filter2(ctx, &a)); }
+    { kjb_taa_prob_filter_args a{prob_filtered1_img, prob_filtered2_img}; w->rows_full(0); RUN("taa prob filter2", kjb_pass_taa_prob_filter2(ctx, &a)); }
     kjb_image& this_frame_output_img = w->img("taa.this_frame_out", OW, OH, KJB_FMT_RGBA16_FLOAT);
     {
         kjb_taa_args a{}; a.input_tex = input_tex; a.history_tex = reprojected_history_img; a.reprojection_tex = reprojection_map; a.closest_velocity_tex = closest_velocity_img;
         a.velocity_history_tex = *velocity_history_tex; a.depth_tex = depth_tex; a.smooth_var_history_tex = *smooth_var_history_tex; a.input_prob_tex = prob_filtered2_img;
         a.temporal_output_tex = *temporal_output_tex; a.output_tex = this_frame_output_img; a.smooth_var_output_tex = *smooth_var_output_tex; a.velocity_output_tex = *temporal_velocity_output_tex;
         size4(a.input_tex_size, input_tex); size4(a.output_tex_size, *temporal_output_tex);
-        RUN("taa", kjb_pass_taa(ctx, &a));
+        w->rows_full(0); RUN("taa", kjb_pass_taa(ctx, &a));
     }
     return &this_frame_output_img;
 }
@@ -527,6 +653,7 @@ int kjb_world_render_frame(kjb_world* w, const kjb_world_frame* f) {
     if (begin_frame(w, f, fc, true)) return 1;
     const uint32_t W = w->W, H = w->H;
 
+    w->rows_all();
     // sky cube + convolved sky (world_render_passes.rs:33-38, renderers/sky.rs); recomputed only when the sun moves
     kjb_image& sky_cube = w->img("sky_cube", 64, 64, KJB_FMT_RGBA16_FLOAT, 6);
     kjb_image& convolved_sky_cube = w->img("convolved_sky_cube", 16, 16, KJB_FMT_RGBA16_FLOAT, 6);
@@ -589,6 +716,22 @@ int kjb_world_render_frame(kjb_world* w, const kjb_world_frame* f) {
     if (w->desc.enable_taa) {
         kjb_image gi{};
         if (kjb_world_get_image(w, "rtdgi.spatial_filtered", &gi) == 0) { taa_render(w, gi, reprojection_map, depth); result_name = "taa.this_frame_out"; }
+    }
+    if (w->tiled && !w->err && !w->stopped) {
+        // the frame's single collective: borders of every temporal image (what is history next frame) + this band of the GI history
+        const TileHalos th2 = tile_halos(w);
+        std::vector<XchgItem> items;
+        auto add = [&](const PingPong& pp, uint32_t scale, uint32_t border) { auto it = w->images.find(pp.history_key); if (it != w->images.end()) items.push_back({it->second, scale, border}); };
+        add(w->temporal2_tex, 2, 0);
+        add(w->temporal2_variance_tex, 2, 2 * (th2.d10 + 2));
+        add(w->temporal_radiance_tex, 1, th2.border); add(w->temporal_ray_orig_tex, 1, th2.border); add(w->temporal_ray_tex, 1, th2.border);
+        add(w->temporal_reservoir_tex, 1, th2.border); add(w->temporal_candidate_tex, 1, th2.border); add(w->temporal_invalidity_tex, 1, th2.border);
+        add(w->temporal_hit_normal_tex, 1, th2.border);
+        if (w->desc.enable_taa) { add(w->taa_temporal_tex, 2, 16); add(w->taa_temporal_velocity_tex, 2, 16); add(w->taa_temporal_smooth_var_tex, 2, 16); }
+        w->pass_begin("tile border all-gather");
+        if (tile_exchange(w, items)) w->err = 1;
+        w->pass_end();
+        w->rows_all();
     }
     if (f->host_result && !w->err) {
         kjb_image result{};

@@ -39,6 +39,18 @@ struct kjb_context {
 
     kjb::Globals g;   // host copy, passed by value to every kernel
 
+    // multi-GPU transport (tile-sharded frames)
+    kjb_allgather_fn ag_fn = nullptr; void* ag_user = nullptr; uint32_t rank = 0, nranks = 1; void* nccl_comm = nullptr;
+
+    // Row scissor for tile-sharded frames: the next pass only computes rows [scissor_y0, scissor_y1) of ITS output
+    // grid (0,0 = whole image).  Set by kjb_set_scissor, consumed (and kept) by every kjb_pass_* launch.
+    uint32_t scissor_y0 = 0, scissor_y1 = 0;
+    kjb::Rows rows_for(uint32_t H) const {
+        kjb::Rows r; r.y0 = 0; r.y1 = int(H);
+        if (scissor_y1 > scissor_y0) { r.y0 = int(scissor_y0 < H ? scissor_y0 : H); r.y1 = int(scissor_y1 < H ? scissor_y1 : H); }
+        return r;
+    }
+
     int fail(const std::string& msg) { last_error = msg; return 1; }
 };
 
@@ -54,7 +66,16 @@ inline int dev_memset(kjb_context*, void* d, int v, size_t n) { memset(d, v, n);
 inline int dev_sync(kjb_context*) { return 0; }
 inline const char* dev_check(kjb_context*) { return nullptr; }
 #else
-inline void* dev_alloc(size_t n) { void* p = nullptr; if (cudaMalloc(&p, n ? n : 1) != cudaSuccess) return nullptr; cudaMemset(p, 0, n ? n : 1); return p; }
+// Zero-filled allocation.  cudaMemset runs on the legacy default stream, which does NOT order against the context's
+// non-blocking stream: wait for it here (allocation is a set-up time operation), or a later async copy/kernel on the
+// context stream could be overtaken by the memset.
+inline void* dev_alloc(size_t n) {
+    void* p = nullptr;
+    if (cudaMalloc(&p, n ? n : 1) != cudaSuccess) return nullptr;
+    cudaMemset(p, 0, n ? n : 1);
+    cudaDeviceSynchronize();
+    return p;
+}
 inline void dev_free(void* p) { if (p) cudaFree(p); }
 inline int dev_h2d(kjb_context* c, void* d, const void* h, size_t n) { return cudaMemcpyAsync(d, h, n, cudaMemcpyHostToDevice, c->stream) != cudaSuccess; }
 inline int dev_d2h(kjb_context* c, void* h, const void* d, size_t n) { return cudaMemcpyAsync(h, d, n, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess; }
@@ -90,15 +111,17 @@ inline bool check_img(kjb_context* c, const kjb_image& i, uint32_t fmt, const ch
 // ---- kernel launch: <<<>>> in the product; a serial block/thread loop under the test emulator
 #if defined(KJB_EMU)
 #define KJB_KERNEL(bounds) static void
-#define KJB_LAUNCH(ctx, kernel, dims, ...) do { kjb_emu::launch(dims, [&]() { kernel(__VA_ARGS__); }); (ctx)->launches++; } while (0)
-#define KJB_LAUNCH_SYNC(ctx, kernel, dims, ...) do { kjb_emu::launch_sync(dims, [&]() { kernel(__VA_ARGS__); }); (ctx)->launches++; } while (0)
+#define KJB_LAUNCH(ctx, kernel, dims, ...) do { if (kjb__rows.y1 > kjb__rows.y0) { kjb_emu::launch(dims, [&]() { kernel(__VA_ARGS__, kjb__rows); }); (ctx)->launches++; } } while (0)
+#define KJB_LAUNCH_SYNC(ctx, kernel, dims, ...) do { if (kjb__rows.y1 > kjb__rows.y0) { kjb_emu::launch_sync(dims, [&]() { kernel(__VA_ARGS__, kjb__rows); }); (ctx)->launches++; } } while (0)
 #else
 #define KJB_KERNEL(bounds) __global__ void __launch_bounds__(bounds)
-#define KJB_LAUNCH(ctx, kernel, dims, ...) do { kernel<<<dims, 0, (ctx)->stream>>>(__VA_ARGS__); (ctx)->launches++; } while (0)
+#define KJB_LAUNCH(ctx, kernel, dims, ...) do { if (kjb__rows.y1 > kjb__rows.y0) { kernel<<<dims, 0, (ctx)->stream>>>(__VA_ARGS__, kjb__rows); (ctx)->launches++; } } while (0)
 #define KJB_LAUNCH_SYNC KJB_LAUNCH   /* kernels that use __syncthreads(): only the test emulator needs to know */
 #endif
 #define KJB_DIMS(...) __VA_ARGS__
-#define KJB_GRID2D(W, H, BX, BY) dim3(((W) + (BX) - 1) / (BX), ((H) + (BY) - 1) / (BY), 1), dim3((BX), (BY), 1)
-#define KJB_PX int x = int(blockIdx.x * blockDim.x + threadIdx.x), y = int(blockIdx.y * blockDim.y + threadIdx.y)
+// every kernel's last parameter is `Rows kjb_rows`: the row range of its grid this launch covers (tile sharding)
+#define KJB_ROWS(ctx, H) const kjb::Rows kjb__rows = (ctx)->rows_for(H)
+#define KJB_GRID2D(W, H, BX, BY) dim3(((W) + (BX) - 1) / (BX), (unsigned(kjb__rows.y1 - kjb__rows.y0) + (BY) - 1) / (BY), 1), dim3((BX), (BY), 1)
+#define KJB_PX int x = int(blockIdx.x * blockDim.x + threadIdx.x), y = kjb_rows.y0 + int(blockIdx.y * blockDim.y + threadIdx.y); if (y >= kjb_rows.y1) return
 
 #define KJB_PASS_EPILOGUE(ctx, name) do { const char* e__ = kjb::dev_check(ctx); if (e__) return (ctx)->fail(std::string(name) + ": " + e__); return 0; } while (0)

@@ -359,6 +359,8 @@ KJB_DEV float4 sample_cube_rgba16f(const Img& cube, float3 dir) {
     return bilinear_clamp(cube.w, cube.h, uv, [&](int x, int y) { return ld_rgba16f(cube, x, y, face); });
 }
 
+struct Rows { int y0, y1; };   // row range [y0, y1) of a pass's grid computed by one launch (tile-sharded frames)
+
 // ------------------------------------------------------------------------------------------------ per-launch globals
 // Passed BY VALUE to every kernel (lands in the constant bank: uniform, cached reads).  Stands in for descriptor
 // sets 1-3: bindless LUTs + mesh data, FrameConstants + lights, acceleration structure.

@@ -1,0 +1,77 @@
+// Multi-GPU transport for tile-sharded frames: one ncclAllGather per frame on the context's stream.
+// NCCL is dlopen'ed (no link-time dependency: the library must load in the GPU-less build container); the communicator is
+// created from a unique id the caller distributes (bench.py uses torch.distributed for that plumbing only).
+#include "kjb_context.h"
+#if !defined(KJB_EMU)
+#include <dlfcn.h>
+#endif
+
+using namespace kjb;
+
+namespace {
+#if !defined(KJB_EMU)
+struct NcclId { char b[128]; };   // ncclUniqueId
+struct NcclApi {
+    typedef NcclId Id;
+    void* lib = nullptr;
+    int (*GetUniqueId)(void*) = nullptr;
+    int (*CommInitRank)(void**, int, NcclId /* by value */, int) = nullptr;
+    int (*AllGather)(const void*, void*, size_t, int, void*, cudaStream_t) = nullptr;
+    int (*CommDestroy)(void*) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+    bool load() {
+        if (lib) return true;
+        const char* names[] = {"libnccl.so.2", "libnccl.so"};
+        for (const char* n : names) { lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL); if (lib) break; }
+        if (!lib) return false;
+        GetUniqueId = (int (*)(void*))dlsym(lib, "ncclGetUniqueId");
+        CommInitRank = (decltype(CommInitRank))dlsym(lib, "ncclCommInitRank");
+        AllGather = (decltype(AllGather))dlsym(lib, "ncclAllGather");
+        CommDestroy = (int (*)(void*))dlsym(lib, "ncclCommDestroy");
+        GetErrorString = (const char* (*)(int))dlsym(lib, "ncclGetErrorString");
+        return GetUniqueId && CommInitRank && AllGather;
+    }
+} g_nccl;
+#endif
+}  // namespace
+
+extern "C" {
+
+int kjb_comm_nccl_unique_id(void* out) {
+#if defined(KJB_EMU)
+    (void)out; return 1;
+#else
+    if (!g_nccl.load()) return 1;
+    return g_nccl.GetUniqueId(out);
+#endif
+}
+int kjb_comm_init_nccl(kjb_context* c, const void* id, uint32_t rank, uint32_t nranks) {
+#if defined(KJB_EMU)
+    (void)id; (void)rank; (void)nranks; return c->fail("emu: no NCCL");
+#else
+    if (!g_nccl.load()) return c->fail("kjb_comm_init_nccl: libnccl.so.2 not found");
+    NcclApi::Id uid; memcpy(uid.b, id, 128);
+    void* comm = nullptr;
+    const int rc = g_nccl.CommInitRank(&comm, int(nranks), uid, int(rank));
+    if (rc != 0) return c->fail(std::string("ncclCommInitRank: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "error"));
+    c->nccl_comm = comm; c->rank = rank; c->nranks = nranks;
+    return 0;
+#endif
+}
+int kjb_comm_set_callback(kjb_context* c, kjb_allgather_fn fn, void* user, uint32_t rank, uint32_t nranks) { c->ag_fn = fn; c->ag_user = user; c->rank = rank; c->nranks = nranks; return 0; }
+int kjb_comm_rank(kjb_context* c, uint32_t* r, uint32_t* n) { *r = c->rank; *n = c->nranks; return 0; }
+int kjb_allgather(kjb_context* c, const void* send, void* recv, uint64_t bytes) {
+    if (c->nranks <= 1) return dev_d2d(c, recv, send, bytes);
+#if !defined(KJB_EMU)
+    if (c->nccl_comm) {
+        const int rc = g_nccl.AllGather(send, recv, size_t(bytes), /* ncclInt8 */ 0, c->nccl_comm, c->stream);
+        return rc == 0 ? 0 : c->fail(std::string("ncclAllGather: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "error"));
+    }
+#endif
+    if (!c->ag_fn) return c->fail("kjb_allgather: no transport registered (kjb_comm_init_nccl / kjb_comm_set_callback)");
+    if (dev_sync(c)) return c->fail("kjb_allgather: sync failed");
+    return c->ag_fn(c->ag_user, send, recv, bytes);
+}
+int kjb_memcpy_d2d(kjb_context* c, void* dst, const void* src, uint64_t bytes) { return dev_d2d(c, dst, src, bytes); }
+
+}  // extern "C"

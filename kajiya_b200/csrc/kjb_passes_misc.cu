@@ -6,7 +6,7 @@ using namespace kjb;
 
 // ------------------------------------------------------------------ primary-visibility G-buffer by ray casting
 // (stand-in for raster_simple_ps.hlsl:39-140; hit shading = rt/gbuffer.rchit.hlsl)
-KJB_KERNEL(128) k_raster_gbuffer(Globals g, ImgW gn, ImgW gb, ImgW dp, ImgW vel) {
+KJB_KERNEL(128) k_raster_gbuffer(Globals g, ImgW gn, ImgW gb, ImgW dp, ImgW vel, Rows kjb_rows) {
     KJB_PX; if (x >= gb.w || y >= gb.h) return;
     const kjb_view_constants& vc = g.fc.view_constants;
     const float size[4] = {float(gb.w), float(gb.h), 1.0f / float(gb.w), 1.0f / float(gb.h)};
@@ -50,7 +50,7 @@ KJB_KERNEL(128) k_raster_gbuffer(Globals g, ImgW gn, ImgW gb, ImgW dp, ImgW vel)
 }
 
 // ------------------------------------------------------------------ calculate_reprojection_map.hlsl:17-142
-KJB_KERNEL(256) k_reprojection_map(Globals g, Img depth_tex, Img geometric_normal_tex, Img prev_depth_tex, Img velocity_tex, ImgW output_tex, float4 output_tex_size) {
+KJB_KERNEL(256) k_reprojection_map(Globals g, Img depth_tex, Img geometric_normal_tex, Img prev_depth_tex, Img velocity_tex, ImgW output_tex, float4 output_tex_size, Rows kjb_rows) {
     KJB_PX; if (x >= output_tex.w || y >= output_tex.h) return;
     const kjb_view_constants& vc = g.fc.view_constants;
     const float ots[4] = {output_tex_size.x, output_tex_size.y, output_tex_size.z, output_tex_size.w};
@@ -124,13 +124,13 @@ KJB_DEV float3 cube_dir(int face, float2 uv) {
     }
     return normalize(d);
 }
-KJB_KERNEL(64) k_sky_cube(Globals g, ImgW out) {
+KJB_KERNEL(64) k_sky_cube(Globals g, ImgW out, Rows kjb_rows) {
     KJB_PX; const int face = int(blockIdx.z); if (x >= out.w || y >= out.h) return;
     const float2 uv = (f2(float(x), float(y)) + 0.5f) / 64.0f;
     const float3 dir = cube_dir(face, uv);
     st_rgba16f(out, x, y, f4(atmosphere_default(g.fc, dir, sun_direction(g.fc)), 1), face);
 }
-KJB_KERNEL(64) k_convolve_sky(Img in, ImgW out, uint32_t face_width) {
+KJB_KERNEL(64) k_convolve_sky(Img in, ImgW out, uint32_t face_width, Rows kjb_rows) {
     KJB_PX; const int face = int(blockIdx.z); if (x >= out.w || y >= out.h) return;
     const float2 uv = (f2(float(x), float(y)) + 0.5f) / float(face_width);
     const float3 output_dir = cube_dir(face, uv);
@@ -144,7 +144,7 @@ KJB_KERNEL(64) k_convolve_sky(Img in, ImgW out, uint32_t face_width) {
 }
 
 // ------------------------------------------------------------------ lut/brdf_fg.hlsl:6-45
-KJB_KERNEL(64) k_brdf_fg_lut(ImgW out) {
+KJB_KERNEL(64) k_brdf_fg_lut(ImgW out, Rows kjb_rows) {
     KJB_PX; if (x >= 64 || y >= 64) return;
     const float ndotv = (float(x) / (64.0f - 1.0f)) * (1.0f - 1e-3f) + 1e-3f;
     const float roughness = kjb_max(1e-5f, float(y) / (64.0f - 1.0f));
@@ -165,15 +165,15 @@ KJB_KERNEL(64) k_brdf_fg_lut(ImgW out) {
 }
 
 // ------------------------------------------------------------------ extract_half_res_*.hlsl
-KJB_KERNEL(256) k_extract_half_depth(Img in, ImgW out, int2 off) {
+KJB_KERNEL(256) k_extract_half_depth(Img in, ImgW out, int2 off, Rows kjb_rows) {
     KJB_PX; if (x >= out.w || y >= out.h) return;
     st_r32f(out, x, y, ld_r32f(in, x * 2 + off.x, y * 2 + off.y));
 }
-KJB_KERNEL(256) k_extract_half_ssao(Img in, ImgW out, int2 off) {
+KJB_KERNEL(256) k_extract_half_ssao(Img in, ImgW out, int2 off, Rows kjb_rows) {
     KJB_PX; if (x >= out.w || y >= out.h) return;
     st_r8s(out, x, y, ld_r8u(in, x * 2 + off.x, y * 2 + off.y));
 }
-KJB_KERNEL(256) k_extract_half_view_normal(Globals g, Img in, ImgW out, int2 off) {
+KJB_KERNEL(256) k_extract_half_view_normal(Globals g, Img in, ImgW out, int2 off, Rows kjb_rows) {
     KJB_PX; if (x >= out.w || y >= out.h) return;
     const uint4 gbt = ld_rgba32u(in, x * 2 + off.x, y * 2 + off.y);
     const float3 normal_ws = unpack_normal_11_10_11_no_normalize(gbt.y);
@@ -188,6 +188,7 @@ int kjb_pass_raster_gbuffer(kjb_context* c, const kjb_raster_gbuffer_args* a) {
     const uint32_t W = a->gbuffer_out.width, H = a->gbuffer_out.height;
     if (!check_img(c, a->gbuffer_out, KJB_FMT_RGBA32_FLOAT, P, "gbuffer_out") || !check_img(c, a->geometric_normal_out, KJB_FMT_A2R10G10B10_UNORM, P, "geometric_normal_out", W, H)
         || !check_img(c, a->depth_out, KJB_FMT_R32_FLOAT, P, "depth_out", W, H) || !check_img(c, a->velocity_out, KJB_FMT_RGBA16_FLOAT, P, "velocity_out", W, H)) return 1;
+    KJB_ROWS(c, H);
     KJB_LAUNCH(c, k_raster_gbuffer, KJB_GRID2D(W, H, 16, 8), c->g, img_rw(a->geometric_normal_out), img_rw(a->gbuffer_out), img_rw(a->depth_out), img_rw(a->velocity_out));
     KJB_PASS_EPILOGUE(c, P);
 }
@@ -197,38 +198,45 @@ int kjb_pass_reprojection_map(kjb_context* c, const kjb_reprojection_map_args* a
     if (!check_img(c, a->output_tex, KJB_FMT_RGBA16_SNORM, P, "output_tex") || !check_img(c, a->depth_tex, KJB_FMT_R32_FLOAT, P, "depth_tex", W, H)
         || !check_img(c, a->geometric_normal_tex, KJB_FMT_A2R10G10B10_UNORM, P, "geometric_normal_tex", W, H) || !check_img(c, a->prev_depth_tex, KJB_FMT_R32_FLOAT, P, "prev_depth_tex", W, H)
         || !check_img(c, a->velocity_tex, KJB_FMT_RGBA16_FLOAT, P, "velocity_tex", W, H)) return 1;
+    KJB_ROWS(c, H);
     KJB_LAUNCH(c, k_reprojection_map, KJB_GRID2D(W, H, 32, 8), c->g, img_ro(a->depth_tex), img_ro(a->geometric_normal_tex), img_ro(a->prev_depth_tex), img_ro(a->velocity_tex),
                img_rw(a->output_tex), f4(a->output_tex_size[0], a->output_tex_size[1], a->output_tex_size[2], a->output_tex_size[3]));
     KJB_PASS_EPILOGUE(c, P);
 }
 int kjb_pass_sky_cube(kjb_context* c, const kjb_sky_cube_args* a) {
     if (!check_img(c, a->output_tex, KJB_FMT_RGBA16_FLOAT, "sky cube", "output_tex", 64, 64) || a->output_tex.layers != 6) return c->fail("sky cube: output must be a 64x64x6 RGBA16F cube");
+    const kjb::Rows kjb__rows = {0, 1 << 30};
     KJB_LAUNCH(c, k_sky_cube, KJB_DIMS(dim3(8, 8, 6), dim3(8, 8, 1)), c->g, img_rw(a->output_tex));
     KJB_PASS_EPILOGUE(c, "sky cube");
 }
 int kjb_pass_convolve_sky(kjb_context* c, const kjb_convolve_sky_args* a) {
     if (!check_img(c, a->input_tex, KJB_FMT_RGBA16_FLOAT, "convolve sky", "input_tex") || !check_img(c, a->output_tex, KJB_FMT_RGBA16_FLOAT, "convolve sky", "output_tex")) return 1;
     const uint32_t W = a->output_tex.width;
+    const kjb::Rows kjb__rows = {0, 1 << 30};
     KJB_LAUNCH(c, k_convolve_sky, KJB_DIMS(dim3((W + 7) / 8, (W + 7) / 8, 6), dim3(8, 8, 1)), img_ro(a->input_tex), img_rw(a->output_tex), a->face_width);
     KJB_PASS_EPILOGUE(c, "convolve sky");
 }
 int kjb_pass_brdf_fg_lut(kjb_context* c, const kjb_brdf_fg_lut_args* a) {
     if (!check_img(c, a->output_tex, KJB_FMT_RGBA16_FLOAT, "brdf fg lut", "output_tex", 64, 64)) return 1;
+    const kjb::Rows kjb__rows = {0, 1 << 30};
     KJB_LAUNCH(c, k_brdf_fg_lut, KJB_DIMS(dim3(8, 8, 1), dim3(8, 8, 1)), img_rw(a->output_tex));
     KJB_PASS_EPILOGUE(c, "brdf fg lut");
 }
 int kjb_pass_extract_half_res_depth(kjb_context* c, const kjb_extract_half_res_args* a) {
     if (!check_img(c, a->input_tex, KJB_FMT_R32_FLOAT, "extract half depth", "input_tex") || !check_img(c, a->output_tex, KJB_FMT_R32_FLOAT, "extract half depth", "output_tex")) return 1;
+    KJB_ROWS(c, a->output_tex.height);
     KJB_LAUNCH(c, k_extract_half_depth, KJB_GRID2D(a->output_tex.width, a->output_tex.height, 32, 8), img_ro(a->input_tex), img_rw(a->output_tex), halfres_subsample_offset(c->g.fc.frame_index));
     KJB_PASS_EPILOGUE(c, "extract half depth");
 }
 int kjb_pass_extract_half_res_ssao(kjb_context* c, const kjb_extract_half_res_args* a) {
     if (!check_img(c, a->input_tex, KJB_FMT_R8_UNORM, "extract ssao/2", "input_tex") || !check_img(c, a->output_tex, KJB_FMT_R8_SNORM, "extract ssao/2", "output_tex")) return 1;
+    KJB_ROWS(c, a->output_tex.height);
     KJB_LAUNCH(c, k_extract_half_ssao, KJB_GRID2D(a->output_tex.width, a->output_tex.height, 32, 8), img_ro(a->input_tex), img_rw(a->output_tex), halfres_subsample_offset(c->g.fc.frame_index));
     KJB_PASS_EPILOGUE(c, "extract ssao/2");
 }
 int kjb_pass_extract_half_res_view_normal(kjb_context* c, const kjb_extract_half_res_args* a) {
     if (!check_img(c, a->input_tex, KJB_FMT_RGBA32_FLOAT, "extract view normal/2", "input_tex") || !check_img(c, a->output_tex, KJB_FMT_RGBA8_SNORM, "extract view normal/2", "output_tex")) return 1;
+    KJB_ROWS(c, a->output_tex.height);
     KJB_LAUNCH(c, k_extract_half_view_normal, KJB_GRID2D(a->output_tex.width, a->output_tex.height, 32, 8), c->g, img_ro(a->input_tex), img_rw(a->output_tex), halfres_subsample_offset(c->g.fc.frame_index));
     KJB_PASS_EPILOGUE(c, "extract view normal/2");
 }

@@ -105,7 +105,7 @@ KJB_DEV float4 cubic_hermite(float4 A, float4 B, float4 C, float4 D, float t) { 
     const float4 c = -A / 2.0f + C / 2.0f;
     return a * t3 + b * t2 + c * t + B;
 }
-KJB_KERNEL(256) k_rtdgi_reproject(Img input_tex, Img reprojection_tex, ImgW output_tex, float4 ots) {
+KJB_KERNEL(256) k_rtdgi_reproject(Img input_tex, Img reprojection_tex, ImgW output_tex, float4 ots, Rows kjb_rows) {
     KJB_PX; const int W = output_tex.w, H = output_tex.h; if (x >= W || y >= H) return;
     const float s4[4] = {ots.x, ots.y, ots.z, ots.w};
     const float2 uv = get_uv(x, y, s4);
@@ -148,7 +148,7 @@ KJB_KERNEL(256) k_rtdgi_reproject(Img input_tex, Img reprojection_tex, ImgW outp
 
 // ------------------------------------------------------------------ D3 diffuse_validate.rgen.hlsl:46-111
 KJB_KERNEL(128) k_rtdgi_validate(Globals g, Img half_view_normal_tex, Img depth_tex, Img reprojected_gi_tex, ImgW reservoir_tex, Img reservoir_ray_history_tex,
-                                 Img sky_cube_tex, ImgW irradiance_history_tex, Img ray_orig_history_tex, ImgW out_tex, float4 gts) {
+                                 Img sky_cube_tex, ImgW irradiance_history_tex, Img ray_orig_history_tex, ImgW out_tex, float4 gts, Rows kjb_rows) {
     KJB_PX; if (x >= out_tex.w || y >= out_tex.h) return;
     const kjb_view_constants& vc = g.fc.view_constants;
     const int2 hso = halfres_subsample_offset(g.fc.frame_index);
@@ -182,7 +182,7 @@ KJB_KERNEL(128) k_rtdgi_validate(Globals g, Img half_view_normal_tex, Img depth_
 
 // ------------------------------------------------------------------ D4 trace_diffuse.rgen.hlsl:49-120
 KJB_KERNEL(128) k_rtdgi_trace(Globals g, Img half_view_normal_tex, Img depth_tex, Img reprojected_gi_tex, Img reprojection_tex, Img sky_cube_tex,
-                              ImgW cand_irr, ImgW cand_normal, ImgW cand_hit, Img inv_in, ImgW inv_out, float4 gts) {
+                              ImgW cand_irr, ImgW cand_normal, ImgW cand_hit, Img inv_in, ImgW inv_out, float4 gts, Rows kjb_rows) {
     KJB_PX; if (x >= cand_irr.w || y >= cand_irr.h) return;
     const kjb_view_constants& vc = g.fc.view_constants;
     const int2 hso = halfres_subsample_offset(g.fc.frame_index);
@@ -241,7 +241,7 @@ KJB_DEV float d5_edge(const Img& reprojection_tex, const Img& half_depth_tex, in
     return edge;
 }
 struct Weights25v { float w[25]; };
-KJB_KERNEL(256) k_rtdgi_validity_integrate(Globals g, Img input_tex, Img history_tex, Img reprojection_tex, Img half_depth_tex, ImgW output_tex, float4 gts, Weights25v wt) {
+KJB_KERNEL(256) k_rtdgi_validity_integrate(Globals g, Img input_tex, Img history_tex, Img reprojection_tex, Img half_depth_tex, ImgW output_tex, float4 gts, Weights25v wt, Rows kjb_rows) {
     KJB_PX; if (x >= output_tex.w || y >= output_tex.h) return;
     const float b0 = kjb_lerp(d5_blur(input_tex, x, y, wt.w), d5_blur(input_tex, x ^ 2, y, wt.w), 0.5f);
     const float b1 = kjb_lerp(d5_blur(input_tex, x, y ^ 2, wt.w), d5_blur(input_tex, x ^ 2, y ^ 2, wt.w), 0.5f);
@@ -271,7 +271,7 @@ struct RestirTemporalImgs {
         reservoir_history_tex, reprojection_tex, hit_normal_history_tex, candidate_history_tex, rt_invalidity_tex;
     ImgW radiance_out_tex, ray_orig_output_tex, ray_output_tex, hit_normal_output_tex, reservoir_out_tex, candidate_out_tex, temporal_reservoir_packed_tex;
 };
-KJB_KERNEL(256) k_rtdgi_restir_temporal(Globals g, RestirTemporalImgs t, float4 gts) {
+KJB_KERNEL(256) k_rtdgi_restir_temporal(Globals g, RestirTemporalImgs t, float4 gts, Rows kjb_rows) {
     KJB_PX; if (x >= t.radiance_out_tex.w || y >= t.radiance_out_tex.h) return;
     const kjb_view_constants& vc = g.fc.view_constants;
     const uint32_t frame_index = g.fc.frame_index;
@@ -388,7 +388,7 @@ KJB_KERNEL(256) k_rtdgi_restir_temporal(Globals g, RestirTemporalImgs t, float4 
 // ------------------------------------------------------------------ D7 restir_spatial.hlsl:48-372 + occlusion_raymarch.hlsl:69-146
 KJB_DEV float normal_influence_nonlinearity(float x, float b) { return x < -b ? 0.0f : (x + b) * (x + b) / (4 * b); }
 KJB_KERNEL(256) k_rtdgi_restir_spatial(Globals g, Img reservoir_input_tex, Img half_view_normal_tex, Img half_depth_tex, Img half_ssao_tex, Img temporal_reservoir_packed_tex,
-                                       ImgW reservoir_output_tex, float4 gts, float4 ots, uint32_t pass_idx, uint32_t perform_occlusion_raymarch, uint32_t importance_only) {
+                                       ImgW reservoir_output_tex, float4 gts, float4 ots, uint32_t pass_idx, uint32_t perform_occlusion_raymarch, uint32_t importance_only, Rows kjb_rows) {
     KJB_PX; if (x >= reservoir_output_tex.w || y >= reservoir_output_tex.h) return;
     const kjb_view_constants& vc = g.fc.view_constants;
     const int2 hso = halfres_subsample_offset(g.fc.frame_index);
@@ -506,7 +506,7 @@ KJB_KERNEL(256) k_rtdgi_restir_spatial(Globals g, Img reservoir_input_tex, Img h
 // ------------------------------------------------------------------ D9 restir_resolve.hlsl:42-205
 KJB_DEV float ggx_ndf_unnorm(float a2, float cos_theta) { const float ds = cos_theta * cos_theta * (a2 - 1.0f) + 1.0f; return a2 / (ds * ds); }
 struct ResolveImgs { Img radiance_tex, reservoir_input_tex, gbuffer_tex, depth_tex, half_view_normal_tex, half_depth_tex, ssao_tex, candidate_radiance_tex, candidate_hit_tex, temporal_reservoir_packed_tex; };
-KJB_KERNEL(256) k_rtdgi_restir_resolve(Globals g, ResolveImgs t, ImgW irradiance_output_tex, float4 gts, float4 ots) {
+KJB_KERNEL(256) k_rtdgi_restir_resolve(Globals g, ResolveImgs t, ImgW irradiance_output_tex, float4 gts, float4 ots, Rows kjb_rows) {
     KJB_PX; if (x >= irradiance_output_tex.w || y >= irradiance_output_tex.h) return;
     const kjb_view_constants& vc = g.fc.view_constants;
     const int2 hso = halfres_subsample_offset(g.fc.frame_index);
@@ -606,11 +606,11 @@ struct Weights25 { float w[25]; };
 #define D10_TW (D10_BX + 4)
 #define D10_TH (D10_BY + 4)
 KJB_KERNEL(512) k_rtdgi_temporal(Globals g, Img input_tex, Img history_tex, Img variance_history_tex, Img reprojection_tex, Img rt_history_invalidity_tex,
-                                 ImgW output_tex, ImgW history_output_tex, ImgW variance_history_output_tex, float4 ots, Weights25 wt) {
+                                 ImgW output_tex, ImgW history_output_tex, ImgW variance_history_output_tex, float4 ots, Weights25 wt, Rows kjb_rows) {
     __shared__ float4 s_in[D10_TH * D10_TW];
     __shared__ float s_hist_luma[D10_TH * D10_TW];
     const int W = output_tex.w, H = output_tex.h;
-    const int bx0 = int(blockIdx.x) * D10_BX - 2, by0 = int(blockIdx.y) * D10_BY - 2;
+    const int bx0 = int(blockIdx.x) * D10_BX - 2, by0 = kjb_rows.y0 + int(blockIdx.y) * D10_BY - 2;
     const float ped = g.fc.pre_exposure_delta;
     const float4 history_mult = f4(ped, ped, ped, 1);
     for (int i = int(threadIdx.y) * D10_BX + int(threadIdx.x); i < D10_TW * D10_TH; i += D10_BX * D10_BY) {
@@ -619,8 +619,8 @@ KJB_KERNEL(512) k_rtdgi_temporal(Globals g, Img input_tex, Img history_tex, Img 
         s_hist_luma[i] = linear_to_working(ld_rgba16f(history_tex, bx0 + tx, by0 + ty) * history_mult).x;
     }
     __syncthreads();
-    const int x = int(blockIdx.x) * D10_BX + int(threadIdx.x), y = int(blockIdx.y) * D10_BY + int(threadIdx.y);
-    if (x >= W || y >= H) return;
+    const int x = int(blockIdx.x) * D10_BX + int(threadIdx.x), y = kjb_rows.y0 + int(blockIdx.y) * D10_BY + int(threadIdx.y);
+    if (x >= W || y >= H || y >= kjb_rows.y1) return;
     const float s4[4] = {ots.x, ots.y, ots.z, ots.w};
     const float2 uv = get_uv(x, y, s4);
     const int tcx = int(threadIdx.x) + 2, tcy = int(threadIdx.y) + 2;
@@ -667,7 +667,7 @@ KJB_KERNEL(512) k_rtdgi_temporal(Globals g, Img input_tex, Img history_tex, Img 
 // ------------------------------------------------------------------ D11 spatial_filter.hlsl:33-101
 KJB_DEV float3 crunch(float3 v) { return v * kjb_rcp(max3(v.x, v.y, v.z) + 1.0f); }
 KJB_DEV float3 uncrunch(float3 v) { return v * kjb_rcp(1.0f - max3(v.x, v.y, v.z)); }
-KJB_KERNEL(256) k_rtdgi_spatial(Globals g, Img input_tex, Img depth_tex, Img ssao_tex, Img geometric_normal_tex, ImgW output_tex) {
+KJB_KERNEL(256) k_rtdgi_spatial(Globals g, Img input_tex, Img depth_tex, Img ssao_tex, Img geometric_normal_tex, ImgW output_tex, Rows kjb_rows) {
     KJB_PX; if (x >= output_tex.w || y >= output_tex.h) return;
     const float4 cin = ld_rgba16f(input_tex, x, y);
     const float center_validity = cin.w;
@@ -712,6 +712,7 @@ extern "C" {
 int kjb_pass_rtdgi_reproject(kjb_context* c, const kjb_rtdgi_reproject_args* a) {
     const char* P = "rtdgi reproject"; const uint32_t W = a->output_tex.width, H = a->output_tex.height;
     CHK(a->output_tex, KJB_FMT_RGBA16_FLOAT, "output_tex"); CHKE(a->input_tex, KJB_FMT_RGBA16_FLOAT, "input_tex", W, H); CHKE(a->reprojection_tex, KJB_FMT_RGBA16_SNORM, "reprojection_tex", W, H);
+    KJB_ROWS(c, H);
     KJB_LAUNCH(c, k_rtdgi_reproject, KJB_GRID2D(W, H, 32, 8), img_ro(a->input_tex), img_ro(a->reprojection_tex), img_rw(a->output_tex), F4A(a->output_tex_size));
     KJB_PASS_EPILOGUE(c, P);
 }
@@ -722,6 +723,7 @@ int kjb_pass_rtdgi_validate(kjb_context* c, const kjb_rtdgi_validate_args* a) {
     CHKE(a->reservoir_ray_history_tex, KJB_FMT_RGBA16_FLOAT, "reservoir_ray_history_tex", W, H); CHK(a->sky_cube_tex, KJB_FMT_RGBA16_FLOAT, "sky_cube_tex");
     CHKE(a->irradiance_history_tex, KJB_FMT_RGBA16_FLOAT, "irradiance_history_tex", W, H); CHKE(a->ray_orig_history_tex, KJB_FMT_RGBA32_FLOAT, "ray_orig_history_tex", W, H);
     if (a->ircache.meta_buf.data) return c->fail("rtdgi validate: irradiance cache bindings are not supported by this build yet");
+    KJB_ROWS(c, H);
     KJB_LAUNCH(c, k_rtdgi_validate, KJB_GRID2D(W, H, 16, 8), c->g, img_ro(a->half_view_normal_tex), img_ro(a->depth_tex), img_ro(a->reprojected_gi_tex), img_rw(a->reservoir_tex),
                img_ro(a->reservoir_ray_history_tex), img_ro(a->sky_cube_tex), img_rw(a->irradiance_history_tex), img_ro(a->ray_orig_history_tex), img_rw(a->rt_history_invalidity_out_tex), F4A(a->gbuffer_tex_size));
     KJB_PASS_EPILOGUE(c, P);
@@ -734,6 +736,7 @@ int kjb_pass_rtdgi_trace(kjb_context* c, const kjb_rtdgi_trace_args* a) {
     CHK(a->sky_cube_tex, KJB_FMT_RGBA16_FLOAT, "sky_cube_tex"); CHKE(a->rt_history_invalidity_in_tex, KJB_FMT_R8_UNORM, "rt_history_invalidity_in_tex", W, H);
     CHKE(a->rt_history_invalidity_out_tex, KJB_FMT_R8_UNORM, "rt_history_invalidity_out_tex", W, H);
     if (a->ircache.meta_buf.data) return c->fail("rtdgi trace: irradiance cache bindings are not supported by this build yet");
+    KJB_ROWS(c, H);
     KJB_LAUNCH(c, k_rtdgi_trace, KJB_GRID2D(W, H, 16, 8), c->g, img_ro(a->half_view_normal_tex), img_ro(a->depth_tex), img_ro(a->reprojected_gi_tex), img_ro(a->reprojection_tex), img_ro(a->sky_cube_tex),
                img_rw(a->candidate_irradiance_out_tex), img_rw(a->candidate_normal_out_tex), img_rw(a->candidate_hit_out_tex), img_ro(a->rt_history_invalidity_in_tex), img_rw(a->rt_history_invalidity_out_tex),
                F4A(a->gbuffer_tex_size));
@@ -745,6 +748,7 @@ int kjb_pass_rtdgi_validity_integrate(kjb_context* c, const kjb_rtdgi_validity_i
     CHK(a->reprojection_tex, KJB_FMT_RGBA16_SNORM, "reprojection_tex"); CHKE(a->half_depth_tex, KJB_FMT_R32_FLOAT, "half_depth_tex", W, H);
     Weights25v wt;
     for (int yy = -2; yy <= 2; ++yy) for (int xx = -2; xx <= 2; ++xx) wt.w[(yy + 2) * 5 + (xx + 2)] = kjb_exp2(-0.1f * float(xx * xx + yy * yy));
+    KJB_ROWS(c, H);
     KJB_LAUNCH(c, k_rtdgi_validity_integrate, KJB_GRID2D(W, H, 32, 8), c->g, img_ro(a->input_tex), img_ro(a->history_tex), img_ro(a->reprojection_tex), img_ro(a->half_depth_tex), img_rw(a->output_tex),
                F4A(a->gbuffer_tex_size), wt);
     KJB_PASS_EPILOGUE(c, P);
@@ -770,6 +774,7 @@ int kjb_pass_rtdgi_restir_temporal(kjb_context* c, const kjb_rtdgi_restir_tempor
     t.rt_invalidity_tex = img_ro(a->rt_invalidity_tex); t.radiance_out_tex = img_rw(a->radiance_out_tex); t.ray_orig_output_tex = img_rw(a->ray_orig_output_tex);
     t.ray_output_tex = img_rw(a->ray_output_tex); t.hit_normal_output_tex = img_rw(a->hit_normal_output_tex); t.reservoir_out_tex = img_rw(a->reservoir_out_tex);
     t.candidate_out_tex = img_rw(a->candidate_out_tex); t.temporal_reservoir_packed_tex = img_rw(a->temporal_reservoir_packed_tex);
+    KJB_ROWS(c, H);
     KJB_LAUNCH(c, k_rtdgi_restir_temporal, KJB_GRID2D(W, H, 32, 8), c->g, t, F4A(a->gbuffer_tex_size));
     KJB_PASS_EPILOGUE(c, P);
 }
@@ -779,6 +784,7 @@ int kjb_pass_rtdgi_restir_spatial(kjb_context* c, const kjb_rtdgi_restir_spatial
     CHKE(a->half_view_normal_tex, KJB_FMT_RGBA8_SNORM, "half_view_normal_tex", W, H); CHKE(a->half_depth_tex, KJB_FMT_R32_FLOAT, "half_depth_tex", W, H);
     CHKE(a->half_ssao_tex, KJB_FMT_R8_SNORM, "half_ssao_tex", W, H); CHKE(a->temporal_reservoir_packed_tex, KJB_FMT_RGBA32_UINT, "temporal_reservoir_packed_tex", W, H);
     if (a->reservoir_input_tex.data == a->reservoir_output_tex.data) return c->fail("restir spatial: input and output reservoirs must differ");
+    KJB_ROWS(c, H);
     KJB_LAUNCH(c, k_rtdgi_restir_spatial, KJB_GRID2D(W, H, 32, 8), c->g, img_ro(a->reservoir_input_tex), img_ro(a->half_view_normal_tex), img_ro(a->half_depth_tex), img_ro(a->half_ssao_tex),
                img_ro(a->temporal_reservoir_packed_tex), img_rw(a->reservoir_output_tex), F4A(a->gbuffer_tex_size), F4A(a->output_tex_size), a->spatial_reuse_pass_idx, a->perform_occlusion_raymarch,
                a->occlusion_raymarch_importance_only);
@@ -794,6 +800,7 @@ int kjb_pass_rtdgi_restir_resolve(kjb_context* c, const kjb_rtdgi_restir_resolve
     t.radiance_tex = img_ro(a->radiance_tex); t.reservoir_input_tex = img_ro(a->reservoir_input_tex); t.gbuffer_tex = img_ro(a->gbuffer_tex); t.depth_tex = img_ro(a->depth_tex);
     t.half_view_normal_tex = img_ro(a->half_view_normal_tex); t.half_depth_tex = img_ro(a->half_depth_tex); t.ssao_tex = img_ro(a->ssao_tex); t.candidate_radiance_tex = img_ro(a->candidate_radiance_tex);
     t.candidate_hit_tex = img_ro(a->candidate_hit_tex); t.temporal_reservoir_packed_tex = img_ro(a->temporal_reservoir_packed_tex);
+    KJB_ROWS(c, H);
     KJB_LAUNCH(c, k_rtdgi_restir_resolve, KJB_GRID2D(W, H, 32, 8), c->g, t, img_rw(a->irradiance_output_tex), F4A(a->gbuffer_tex_size), F4A(a->output_tex_size));
     KJB_PASS_EPILOGUE(c, P);
 }
@@ -805,6 +812,7 @@ int kjb_pass_rtdgi_temporal(kjb_context* c, const kjb_rtdgi_temporal_args* a) {
     CHKE(a->variance_history_output_tex, KJB_FMT_RG16_FLOAT, "variance_history_output_tex", W, H);
     Weights25 wt;
     for (int yy = -2; yy <= 2; ++yy) for (int xx = -2; xx <= 2; ++xx) wt.w[(yy + 2) * 5 + (xx + 2)] = kjb_exp(-3.0f * float(xx * xx + yy * yy) / float((2 + 1.) * (2 + 1.)));
+    KJB_ROWS(c, H);
     KJB_LAUNCH_SYNC(c, k_rtdgi_temporal, KJB_GRID2D(W, H, D10_BX, D10_BY), c->g, img_ro(a->input_tex), img_ro(a->history_tex), img_ro(a->variance_history_tex), img_ro(a->reprojection_tex), img_ro(a->rt_history_invalidity_tex),
                img_rw(a->output_tex), img_rw(a->history_output_tex), img_rw(a->variance_history_output_tex), F4A(a->output_tex_size), wt);
     KJB_PASS_EPILOGUE(c, P);
@@ -813,6 +821,7 @@ int kjb_pass_rtdgi_spatial(kjb_context* c, const kjb_rtdgi_spatial_args* a) {
     const char* P = "rtdgi spatial"; const uint32_t W = a->output_tex.width, H = a->output_tex.height;
     CHK(a->output_tex, KJB_FMT_RGBA16_FLOAT, "output_tex"); CHKE(a->input_tex, KJB_FMT_RGBA16_FLOAT, "input_tex", W, H); CHKE(a->depth_tex, KJB_FMT_R32_FLOAT, "depth_tex", W, H);
     CHKE(a->ssao_tex, KJB_FMT_R8_UNORM, "ssao_tex", W, H); CHKE(a->geometric_normal_tex, KJB_FMT_A2R10G10B10_UNORM, "geometric_normal_tex", W, H);
+    KJB_ROWS(c, H);
     KJB_LAUNCH(c, k_rtdgi_spatial, KJB_GRID2D(W, H, 32, 8), c->g, img_ro(a->input_tex), img_ro(a->depth_tex), img_ro(a->ssao_tex), img_ro(a->geometric_normal_tex), img_rw(a->output_tex));
     KJB_PASS_EPILOGUE(c, P);
 }

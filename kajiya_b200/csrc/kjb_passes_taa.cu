@@ -23,7 +23,7 @@ KJB_DEV bool t1_should_dilate0(const Img& reprojection_tex, int x, int y, float2
     const float2 d = vel_max - vel_min, thr = 0.1f * vmax(f2(its.z, its.w), vabs(vel_max + vel_min));
     return d.x > thr.x || d.y > thr.y;
 }
-KJB_KERNEL(256) k_taa_reproject(Globals g, Img history_tex, Img reprojection_tex, Img depth_tex, ImgW output_tex, ImgW closest_velocity_output, float4 its, float4 ots) {
+KJB_KERNEL(256) k_taa_reproject(Globals g, Img history_tex, Img reprojection_tex, Img depth_tex, ImgW output_tex, ImgW closest_velocity_output, float4 its, float4 ots, Rows kjb_rows) {
     KJB_PX; const int W = output_tex.w, H = output_tex.h; if (x >= W || y >= H) return;
     const float ped = g.fc.pre_exposure_delta;
     const float2 irs = f2(its.x, its.y) / f2(ots.x, ots.y);
@@ -90,7 +90,7 @@ KJB_DEV FilteredInput t2_inner(const Img& input_tex, const Img& depth_tex, int p
     r.var = vmax(f3(0.0f), iex2 - iex * iex);
     return r;
 }
-KJB_KERNEL(256) k_taa_filter_input(Img input_tex, Img depth_tex, ImgW output_tex, ImgW dev_output_tex, W9 dw) {
+KJB_KERNEL(256) k_taa_filter_input(Img input_tex, Img depth_tex, ImgW output_tex, ImgW dev_output_tex, W9 dw, Rows kjb_rows) {
     KJB_PX; if (x >= output_tex.w || y >= output_tex.h) return;
     const float center_depth = ld_r32f(depth_tex, x, y);
     const FilteredInput fi = t2_inner(input_tex, depth_tex, x, y, center_depth, 1e10f, 200.0f, dw.w);
@@ -112,7 +112,7 @@ KJB_DEV float3 t3_filter(const Img& input_tex, float2 uv, float4 its, float luma
     }
     return iex / iwsum;
 }
-KJB_KERNEL(256) k_taa_filter_history(Img input_tex, ImgW output_tex, float4 its, float4 ots, int k, W25t dw) {
+KJB_KERNEL(256) k_taa_filter_history(Img input_tex, ImgW output_tex, float4 its, float4 ots, int k, W25t dw, Rows kjb_rows) {
     KJB_PX; if (x >= output_tex.w || y >= output_tex.h) return;
     const float s4[4] = {ots.x, ots.y, ots.z, ots.w};
     const float2 uv = get_uv(x, y, s4);
@@ -122,7 +122,7 @@ KJB_KERNEL(256) k_taa_filter_history(Img input_tex, ImgW output_tex, float4 its,
 
 // ------------------------------------------------------------------ T4 input_prob.hlsl:47-109
 KJB_KERNEL(256) k_taa_input_prob(Globals g, Img filtered_input_tex, Img filtered_input_dev_tex, Img filtered_history_tex, Img reprojection_tex, Img smooth_var_history_tex,
-                                 Img velocity_history_tex, ImgW output_tex, float4 its) {
+                                 Img velocity_history_tex, ImgW output_tex, float4 its, Rows kjb_rows) {
     KJB_PX; if (x >= output_tex.w || y >= output_tex.h) return;
     float input_prob = 0;
     float3 ivar = f3(0.0f);
@@ -151,13 +151,13 @@ KJB_KERNEL(256) k_taa_input_prob(Globals g, Img filtered_input_tex, Img filtered
 
 KJB_DEV float ld_r16f(const Img& i, int x, int y) { return inb(i, x, y) ? kjb_f16_to_f32(ld_raw<uint16_t>(i, x, y)) : 0.0f; }
 // ------------------------------------------------------------------ T5 filter_prob.hlsl / T6 filter_prob2.hlsl
-KJB_KERNEL(256) k_taa_prob_filter(Img input_tex, ImgW output_tex) {
+KJB_KERNEL(256) k_taa_prob_filter(Img input_tex, ImgW output_tex, Rows kjb_rows) {
     KJB_PX; if (x >= output_tex.w || y >= output_tex.h) return;
     float prob = ld_r16f(input_tex, x, y);
     for (int yy = -1; yy <= 1; ++yy) for (int xx = -1; xx <= 1; ++xx) prob = kjb_max(prob, ld_r16f(input_tex, x + xx, y + yy));
     st_raw<uint16_t>(output_tex, x, y, uint16_t(kjb_f32_to_f16(prob)));
 }
-KJB_KERNEL(256) k_taa_prob_filter2(Img input_tex, ImgW output_tex) {
+KJB_KERNEL(256) k_taa_prob_filter2(Img input_tex, ImgW output_tex, Rows kjb_rows) {
     KJB_PX; if (x >= output_tex.w || y >= output_tex.h) return;
     float2 weighted_prob = f2(0.0f);
     for (int yy = -2; yy <= 2; ++yy) for (int xx = -2; xx <= 2; ++xx) {
@@ -192,7 +192,7 @@ KJB_DEV Unjittered sample_image_unjitter_taa(const Img& img, int ox, int oy, flo
 }
 struct TaaImgs { Img input_tex, history_tex, reprojection_tex, closest_velocity_tex, velocity_history_tex, smooth_var_history_tex, input_prob_tex;
                  ImgW temporal_output_tex, output_tex, smooth_var_output_tex, velocity_output_tex; };
-KJB_KERNEL(256) k_taa(Globals g, TaaImgs t, float4 its, float4 ots, W25t bw) {
+KJB_KERNEL(256) k_taa(Globals g, TaaImgs t, float4 its, float4 ots, W25t bw, Rows kjb_rows) {
     KJB_PX; if (x >= t.temporal_output_tex.w || y >= t.temporal_output_tex.h) return;
     const float2 sop = f2(g.fc.view_constants.sample_offset_pixels[0], g.fc.view_constants.sample_offset_pixels[1]);
     const float dt = g.fc.delta_time_seconds;
@@ -294,6 +294,7 @@ int kjb_pass_taa_reproject(kjb_context* c, const kjb_taa_reproject_args* a) {
     const char* P = "reproject taa"; const uint32_t W = a->output_tex.width, H = a->output_tex.height;
     CHK(a->output_tex, KJB_FMT_RGBA16_FLOAT, "output_tex"); CHKE(a->history_tex, KJB_FMT_RGBA16_FLOAT, "history_tex", W, H); CHK(a->reprojection_tex, KJB_FMT_RGBA16_SNORM, "reprojection_tex");
     CHK(a->depth_tex, KJB_FMT_R32_FLOAT, "depth_tex"); CHKE(a->closest_velocity_output, KJB_FMT_RG16_FLOAT, "closest_velocity_output", W, H);
+    KJB_ROWS(c, H);
     KJB_LAUNCH(c, k_taa_reproject, KJB_GRID2D(W, H, 32, 8), c->g, img_ro(a->history_tex), img_ro(a->reprojection_tex), img_ro(a->depth_tex), img_rw(a->output_tex), img_rw(a->closest_velocity_output),
                F4A(a->input_tex_size), F4A(a->output_tex_size));
     KJB_PASS_EPILOGUE(c, P);
@@ -303,6 +304,7 @@ int kjb_pass_taa_filter_input(kjb_context* c, const kjb_taa_filter_input_args* a
     CHK(a->output_tex, KJB_FMT_RGBA16_FLOAT, "output_tex"); CHKE(a->input_tex, KJB_FMT_RGBA16_FLOAT, "input_tex", W, H); CHKE(a->depth_tex, KJB_FMT_R32_FLOAT, "depth_tex", W, H);
     CHKE(a->dev_output_tex, KJB_FMT_RGBA16_FLOAT, "dev_output_tex", W, H);
     W9 dw; for (int y = -1; y <= 1; ++y) for (int x = -1; x <= 1; ++x) dw.w[(y + 1) * 3 + (x + 1)] = kjb_exp(-(0.8f / float(1 * 1)) * float(x * x + y * y));
+    KJB_ROWS(c, H);
     KJB_LAUNCH(c, k_taa_filter_input, KJB_GRID2D(W, H, 32, 8), img_ro(a->input_tex), img_ro(a->depth_tex), img_rw(a->output_tex), img_rw(a->dev_output_tex), dw);
     KJB_PASS_EPILOGUE(c, P);
 }
@@ -311,6 +313,7 @@ int kjb_pass_taa_filter_history(kjb_context* c, const kjb_taa_filter_history_arg
     CHK(a->output_tex, KJB_FMT_RGBA16_FLOAT, "output_tex"); CHK(a->input_tex, KJB_FMT_RGBA16_FLOAT, "input_tex");
     const int k = (a->input_tex_size[0] / a->output_tex_size[0] > 1.75f) ? 2 : 1;
     W25t dw; for (int y = -2; y <= 2; ++y) for (int x = -2; x <= 2; ++x) dw.w[(y + 2) * 5 + (x + 2)] = kjb_exp(-(0.8f / float(k * k)) * float(x * x + y * y));
+    KJB_ROWS(c, H);
     KJB_LAUNCH(c, k_taa_filter_history, KJB_GRID2D(W, H, 32, 8), img_ro(a->input_tex), img_rw(a->output_tex), F4A(a->input_tex_size), F4A(a->output_tex_size), k, dw);
     KJB_PASS_EPILOGUE(c, P);
 }
@@ -319,6 +322,7 @@ int kjb_pass_taa_input_prob(kjb_context* c, const kjb_taa_input_prob_args* a) {
     CHK(a->output_tex, KJB_FMT_R16_FLOAT, "output_tex"); CHKE(a->filtered_input_tex, KJB_FMT_RGBA16_FLOAT, "filtered_input_tex", W, H); CHKE(a->filtered_input_dev_tex, KJB_FMT_RGBA16_FLOAT, "filtered_input_dev_tex", W, H);
     CHKE(a->filtered_history_tex, KJB_FMT_RGBA16_FLOAT, "filtered_history_tex", W, H); CHKE(a->reprojection_tex, KJB_FMT_RGBA16_SNORM, "reprojection_tex", W, H);
     CHK(a->smooth_var_history_tex, KJB_FMT_RGBA16_FLOAT, "smooth_var_history_tex"); CHK(a->velocity_history_tex, KJB_FMT_RG16_FLOAT, "velocity_history_tex");
+    KJB_ROWS(c, H);
     KJB_LAUNCH(c, k_taa_input_prob, KJB_GRID2D(W, H, 32, 8), c->g, img_ro(a->filtered_input_tex), img_ro(a->filtered_input_dev_tex), img_ro(a->filtered_history_tex), img_ro(a->reprojection_tex),
                img_ro(a->smooth_var_history_tex), img_ro(a->velocity_history_tex), img_rw(a->output_tex), F4A(a->input_tex_size));
     KJB_PASS_EPILOGUE(c, P);
@@ -326,12 +330,14 @@ int kjb_pass_taa_input_prob(kjb_context* c, const kjb_taa_input_prob_args* a) {
 int kjb_pass_taa_prob_filter(kjb_context* c, const kjb_taa_prob_filter_args* a) {
     const char* P = "taa prob filter"; const uint32_t W = a->output_tex.width, H = a->output_tex.height;
     CHK(a->output_tex, KJB_FMT_R16_FLOAT, "output_tex"); CHKE(a->input_tex, KJB_FMT_R16_FLOAT, "input_tex", W, H);
+    KJB_ROWS(c, H);
     KJB_LAUNCH(c, k_taa_prob_filter, KJB_GRID2D(W, H, 32, 8), img_ro(a->input_tex), img_rw(a->output_tex));
     KJB_PASS_EPILOGUE(c, P);
 }
 int kjb_pass_taa_prob_filter2(kjb_context* c, const kjb_taa_prob_filter_args* a) {
     const char* P = "taa prob filter2"; const uint32_t W = a->output_tex.width, H = a->output_tex.height;
     CHK(a->output_tex, KJB_FMT_R16_FLOAT, "output_tex"); CHKE(a->input_tex, KJB_FMT_R16_FLOAT, "input_tex", W, H);
+    KJB_ROWS(c, H);
     KJB_LAUNCH(c, k_taa_prob_filter2, KJB_GRID2D(W, H, 32, 8), img_ro(a->input_tex), img_rw(a->output_tex));
     KJB_PASS_EPILOGUE(c, P);
 }
@@ -347,6 +353,7 @@ int kjb_pass_taa(kjb_context* c, const kjb_taa_args* a) {
     t.velocity_history_tex = img_ro(a->velocity_history_tex); t.smooth_var_history_tex = img_ro(a->smooth_var_history_tex); t.input_prob_tex = img_ro(a->input_prob_tex);
     t.temporal_output_tex = img_rw(a->temporal_output_tex); t.output_tex = img_rw(a->output_tex); t.smooth_var_output_tex = img_rw(a->smooth_var_output_tex); t.velocity_output_tex = img_rw(a->velocity_output_tex);
     W25t bw; for (int y = -2; y <= 2; ++y) for (int x = -2; x <= 2; ++x) { const float ox = float(x) * 1.0f, oy = float(y) * 1.0f; bw.w[(y + 2) * 5 + (x + 2)] = kjb_exp(-(ox * ox + oy * oy)); }
+    KJB_ROWS(c, H);
     KJB_LAUNCH(c, k_taa, KJB_GRID2D(W, H, 32, 8), c->g, t, F4A(a->input_tex_size), F4A(a->output_tex_size), bw);
     KJB_PASS_EPILOGUE(c, P);
 }

@@ -12,7 +12,7 @@ KJB_DEV float remap_unorm_to_gaussian(float xin, float truncation) {   // :60-72
     return kjb_sqrt(kjb_max(0.0f, kjb_sqrt(z * z - y * INV_ALPHA) - z)) * kjb_sign(x);
 }
 
-KJB_KERNEL(128) k_reference_pt(Globals g, ImgW output_tex, uint32_t indirect_only) {
+KJB_KERNEL(128) k_reference_pt(Globals g, ImgW output_tex, uint32_t indirect_only, Rows kjb_rows) {
     KJB_PX; const int W = output_tex.w, H = output_tex.h; if (x >= W || y >= H) return;
     const kjb_view_constants& vc = g.fc.view_constants;
     const float4 prev = ld_rgba32f(as_ro(output_tex), x, y);
@@ -100,6 +100,7 @@ KJB_KERNEL(128) k_reference_pt(Globals g, ImgW output_tex, uint32_t indirect_onl
 
 extern "C" int kjb_pass_reference_path_trace(kjb_context* c, const kjb_reference_pt_args* a) {
     if (!check_img(c, a->output_tex, KJB_FMT_RGBA32_FLOAT, "reference pt", "output_tex")) return 1;
+    KJB_ROWS(c, a->output_tex.height);
     KJB_LAUNCH(c, k_reference_pt, KJB_GRID2D(a->output_tex.width, a->output_tex.height, 16, 8), c->g, img_rw(a->output_tex), a->indirect_only);
     KJB_PASS_EPILOGUE(c, "reference pt");
 }

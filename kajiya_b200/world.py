@@ -17,8 +17,9 @@ class World:
         self.ctx = C.c_void_p()
         if self.d.kjb_create(device, C.byref(self.ctx)):
             raise KjbError("kjb_create failed: " + (self.d.kjb_last_error(None) or b"").decode())
+        tile_rank, tile_count = tile if tile else (0, 0)
         desc = WorldDesc(width, height, (upscale or (0, 0))[0], (upscale or (0, 0))[1], spatial_reuse_pass_count, 0,
-                         int(enable_ircache), int(enable_rtr), int(enable_taa), (tile or (0, 0))[0], (tile or (0, 0))[1])
+                         int(enable_ircache), int(enable_rtr), int(enable_taa), 0, 0, tile_rank, tile_count)
         self.w = C.c_void_p()
         self._check(self.d.kjb_world_create(self.ctx, C.byref(desc), C.byref(self.w)))
         self.width, self.height = width, height
@@ -33,6 +34,17 @@ class World:
             self.d.kjb_world_destroy(self.w); self.w = None
         if self.ctx:
             self.d.kjb_destroy(self.ctx); self.ctx = None
+
+    # -- multi-GPU transport (tile = (rank, count)) ------------------------------------------------------------
+    def comm_init_nccl(self, unique_id_bytes, rank, nranks):
+        buf = C.create_string_buffer(bytes(unique_id_bytes), 128)
+        self._check(self.d.kjb_comm_init_nccl(self.ctx, buf, rank, nranks))
+
+    def comm_set_callback(self, fn, rank, nranks):
+        """fn(send_ptr, recv_ptr, bytes_per_rank) -> 0; used by the CPU test builds (gloo) and custom transports"""
+        CB = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64)
+        self._cb = CB(lambda user, send, recv, n: int(fn(send, recv, n) or 0))
+        self._check(self.d.kjb_comm_set_callback(self.ctx, C.cast(self._cb, C.c_void_p), None, rank, nranks))
 
     # -- scene -------------------------------------------------------------------------------------------------
     def add_mesh(self, mesh, use_lights=False):

@@ -61,6 +61,17 @@ int kjb_set_frame_constants(kjb_context* c, const kjb_frame_constants* fc, const
     if (fc->triangle_light_count != n) { c->last_error = "triangle_light_count mismatch"; return 1; }
     return 0;
 }
+int kjb_comm_nccl_unique_id(void*) { return 1; }
+int kjb_comm_init_nccl(kjb_context* c, const void*, uint32_t, uint32_t) { c->last_error = "oracle: no NCCL"; return 1; }
+int kjb_comm_set_callback(kjb_context* c, kjb_allgather_fn fn, void* user, uint32_t rank, uint32_t nranks) { c->ag_fn = fn; c->ag_user = user; c->rank = rank; c->nranks = nranks; return 0; }
+int kjb_comm_rank(kjb_context* c, uint32_t* r, uint32_t* n) { *r = c->rank; *n = c->nranks; return 0; }
+int kjb_allgather(kjb_context* c, const void* send, void* recv, uint64_t bytes) {
+    if (c->nranks <= 1) { memcpy(recv, send, bytes); return 0; }
+    if (!c->ag_fn) { c->last_error = "kjb_allgather: no transport registered"; return 1; }
+    return c->ag_fn(c->ag_user, send, recv, bytes);
+}
+int kjb_memcpy_d2d(kjb_context*, void* dst, const void* src, uint64_t bytes) { memmove(dst, src, bytes); return 0; }
+int kjb_set_scissor(kjb_context* c, uint32_t y0, uint32_t y1) { c->scissor_y0 = y0; c->scissor_y1 = y1; return 0; }
 int kjb_set_luts(kjb_context* c, const kjb_image* fg, const kjb_image* bn) { c->g.brdf_fg_lut = Img(*fg); c->g.blue_noise = Img(*bn); return 0; }
 static std::chrono::steady_clock::time_point g_timer_slots[1024];
 int kjb_timer_record(kjb_context*, uint32_t slot) { if (slot >= 1024) return 1; g_timer_slots[slot] = std::chrono::steady_clock::now(); return 0; }

@@ -10,6 +10,8 @@ struct kjb_context {
     kjo::Globals g;
     std::string last_error;
     int num_threads = 0;
+    kjb_allgather_fn ag_fn = nullptr; void* ag_user = nullptr; uint32_t rank = 0, nranks = 1;
+    uint32_t scissor_y0 = 0, scissor_y1 = 0;   // kjb_set_scissor: rows [y0, y1) of the pass's output grid (0,0 = all)
 };
 
 namespace kjo {
@@ -17,6 +19,12 @@ namespace kjo {
 // Row-parallel loop over a WxH grid (oracle passes are embarrassingly parallel over pixels;
 // every pass reads inputs and writes DIFFERENT output images, except the in-place validate pass
 // which only touches its own pixel).
+// rows of a pass's grid to compute under the context's scissor
+inline void scissor_rows(const kjb_context* c, int h, int& y0, int& y1) {
+    y0 = 0; y1 = h;
+    if (c->scissor_y1 > c->scissor_y0) { y0 = int(c->scissor_y0) < h ? int(c->scissor_y0) : h; y1 = int(c->scissor_y1) < h ? int(c->scissor_y1) : h; }
+}
+inline void parallel_rows_range(int y0, int y1, const std::function<void(int)>& row_fn, int nthreads = 0);
 inline void parallel_rows(int h, const std::function<void(int)>& row_fn, int nthreads = 0) {
     if (nthreads <= 0) nthreads = int(std::thread::hardware_concurrency());
     if (nthreads <= 1 || h < 8) { for (int y = 0; y < h; ++y) row_fn(y); return; }
@@ -24,6 +32,15 @@ inline void parallel_rows(int h, const std::function<void(int)>& row_fn, int nth
     std::vector<std::thread> th;
     for (int t = 0; t < nthreads; ++t) th.emplace_back([&]() { for (;;) { int y = next.fetch_add(1); if (y >= h) break; row_fn(y); } });
     for (auto& t : th) t.join();
+}
+
+inline void parallel_rows_range(int y0, int y1, const std::function<void(int)>& row_fn, int nthreads) {
+    parallel_rows(y1 - y0, [&](int y) { row_fn(y + y0); }, nthreads);
+}
+// every oracle pass iterates its output rows through this: honours the tile scissor
+inline void pass_rows(const kjb_context* ctx, int H, const std::function<void(int)>& row_fn, int nthreads = 0) {
+    int y0, y1; scissor_rows(ctx, H, y0, y1);
+    parallel_rows_range(y0, y1, row_fn, nthreads);
 }
 
 inline float4 f4(const float* p) { return float4(p[0], p[1], p[2], p[3]); }

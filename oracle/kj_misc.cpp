@@ -14,7 +14,7 @@ int kjb_pass_raster_gbuffer(kjb_context* ctx, const kjb_raster_gbuffer_args* a) 
     Img gn(a->geometric_normal_out), gb(a->gbuffer_out), dp(a->depth_out), vel(a->velocity_out);
     const int W = gb.w(), H = gb.h();
     const float4 size(float(W), float(H), 1.0f / float(W), 1.0f / float(H));
-    parallel_rows(H, [&](int y) { for (int x = 0; x < W; ++x) {
+    pass_rows(ctx, H, [&](int y) { for (int x = 0; x < W; ++x) {
         const float2 uv = get_uv(int2(x, y), size);
         const ViewRayContext vrc = ViewRayContext::from_uv(vc, uv);
         Ray r; r.origin = vrc.ray_origin_ws(); r.dir = vrc.ray_dir_ws(); r.tmin = 0; r.tmax = FLT_MAX_F;
@@ -47,7 +47,7 @@ int kjb_pass_reprojection_map(kjb_context* ctx, const kjb_reprojection_map_args*
     Img depth_tex(a->depth_tex), geometric_normal_tex(a->geometric_normal_tex), prev_depth_tex(a->prev_depth_tex), velocity_tex(a->velocity_tex), output_tex(a->output_tex);
     const float4 output_tex_size = f4(a->output_tex_size);
     const int W = output_tex.w(), H = output_tex.h();
-    parallel_rows(H, [&](int y) { for (int x = 0; x < W; ++x) {
+    pass_rows(ctx, H, [&](int y) { for (int x = 0; x < W; ++x) {
         const int2 px(x, y);
         float2 uv = get_uv(px, output_tex_size);
         if (depth_tex.load(px).x == 0.0f) {
@@ -175,7 +175,7 @@ int kjb_pass_brdf_fg_lut(kjb_context* ctx, const kjb_brdf_fg_lut_args* a) {
 // ------------------------------------------------------------------ extract_half_res_*.hlsl
 int kjb_pass_extract_half_res_depth(kjb_context* ctx, const kjb_extract_half_res_args* a) {
     Img in(a->input_tex), out(a->output_tex); const int2 o = halfres_subsample_offset(ctx->g.fc.frame_index);
-    for (int y = 0; y < out.h(); ++y) for (int x = 0; x < out.w(); ++x) out.store(x, y, float4(in.load(x * 2 + o.x, y * 2 + o.y).x));
+    pass_rows(ctx, out.h(), [&](int y) { for (int x = 0; x < out.w(); ++x) out.store(x, y, float4(in.load(x * 2 + o.x, y * 2 + o.y).x)); }, 1);
     return 0;
 }
 int kjb_pass_extract_half_res_ssao(kjb_context* ctx, const kjb_extract_half_res_args* a) {
@@ -184,12 +184,12 @@ int kjb_pass_extract_half_res_ssao(kjb_context* ctx, const kjb_extract_half_res_
 int kjb_pass_extract_half_res_view_normal(kjb_context* ctx, const kjb_extract_half_res_args* a) {   // extract_half_res_gbuffer_view_normal_rgba8.hlsl:15-53 ("tired" branch)
     Img in(a->input_tex), out(a->output_tex); const int2 o = halfres_subsample_offset(ctx->g.fc.frame_index);
     const kjb_view_constants& vc = ctx->g.fc.view_constants;
-    for (int y = 0; y < out.h(); ++y) for (int x = 0; x < out.w(); ++x) {
+    pass_rows(ctx, out.h(), [&](int y) { for (int x = 0; x < out.w(); ++x) {
         uint4 gbt = in.load_u(x * 2 + o.x, y * 2 + o.y);
         float3 normal_ws = unpack_normal_11_10_11_no_normalize(asfloat(gbt.y));
         float3 normal_vs = normalize(mul(vc.world_to_view, float4(normal_ws, 0)).xyz());
         out.store(x, y, float4(normal_vs, 1));
-    }
+    } }, 1);
     return 0;
 }
 

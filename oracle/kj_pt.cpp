@@ -27,7 +27,7 @@ extern "C" int kjb_pass_reference_path_trace(kjb_context* ctx, const kjb_referen
     Img output_tex(a->output_tex);
     const int W = output_tex.w(), H = output_tex.h();
     const bool INDIRECT_ONLY = a->indirect_only != 0;
-    parallel_rows(H, [&](int y) { for (int x = 0; x < W; ++x) {
+    pass_rows(ctx, H, [&](int y) { for (int x = 0; x < W; ++x) {
         float4 prev = output_tex.load(x, y);
         if (!(prev.w < 1000)) continue;
         float4 radiance_sample_count_packed(0.0f);

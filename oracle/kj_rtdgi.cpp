@@ -133,7 +133,7 @@ int kjb_pass_rtdgi_reproject(kjb_context* ctx, const kjb_rtdgi_reproject_args* a
     Img input_tex(a->input_tex), reprojection_tex(a->reprojection_tex), output_tex(a->output_tex);
     const float4 output_tex_size = f4(a->output_tex_size);
     const int W = output_tex.w(), H = output_tex.h();
-    parallel_rows(H, [&](int y) { for (int x = 0; x < W; ++x) {
+    pass_rows(ctx, H, [&](int y) { for (int x = 0; x < W; ++x) {
         int2 px(x, y);
         float2 uv = get_uv(px, output_tex_size);
         float4 reproj = reprojection_tex.load(px);
@@ -201,7 +201,7 @@ int kjb_pass_rtdgi_validate(kjb_context* ctx, const kjb_rtdgi_validate_args* a) 
     const float4 gbuffer_tex_size = f4(a->gbuffer_tex_size);
     const int W = out_tex.w(), H = out_tex.h();
     const int2 hi_px_offset = halfres_subsample_offset(g.fc.frame_index);
-    parallel_rows(H, [&](int y) { for (int x = 0; x < W; ++x) {
+    pass_rows(ctx, H, [&](int y) { for (int x = 0; x < W; ++x) {
         const int2 px(x, y); const int2 hi_px = px * 2 + hi_px_offset;
         if (0.0f == depth_tex.load(hi_px).x) { out_tex.store(px, float4(1.0f)); continue; }
         float invalidity = 0.0f;
@@ -248,7 +248,7 @@ int kjb_pass_rtdgi_trace(kjb_context* ctx, const kjb_rtdgi_trace_args* a) {
     const float4 gbuffer_tex_size = f4(a->gbuffer_tex_size);
     const int W = cand_irr.w(), H = cand_irr.h();
     const int2 hi_px_offset = halfres_subsample_offset(g.fc.frame_index);
-    parallel_rows(H, [&](int y) { for (int x = 0; x < W; ++x) {
+    pass_rows(ctx, H, [&](int y) { for (int x = 0; x < W; ++x) {
         const int2 px(x, y); const int2 hi_px = px * 2 + hi_px_offset;
         float depth = depth_tex.load(hi_px).x;
         if (0.0f == depth) {
@@ -320,7 +320,7 @@ int kjb_pass_rtdgi_validity_integrate(kjb_context* ctx, const kjb_rtdgi_validity
         B[size_t(y) * PW + x] = lerp(A[size_t(y) * PW + x], A[size_t(y) * PW + (x ^ 2)], 0.5f);
         E1[size_t(y) * PW + x] = max(E0[size_t(y) * PW + x], E0[size_t(y) * PW + (x ^ 1)]);
     }
-    parallel_rows(H, [&](int y) { for (int x = 0; x < W; ++x) {
+    pass_rows(ctx, H, [&](int y) { for (int x = 0; x < W; ++x) {
         float inv = lerp(B[size_t(y) * PW + x], B[size_t(y ^ 2) * PW + x], 0.5f);
         inv = smoothstep(0.0f, 1.0f, inv);
         float edge = max(E1[size_t(y) * PW + x], E1[size_t(y ^ 1) * PW + x]);
@@ -365,7 +365,7 @@ int kjb_pass_rtdgi_restir_temporal(kjb_context* ctx, const kjb_rtdgi_restir_temp
     const int2 hi_px_offset = halfres_subsample_offset(g.fc.frame_index);
     const uint frame_index = g.fc.frame_index;
 
-    parallel_rows(H, [&](int y) { for (int x = 0; x < W; ++x) {
+    pass_rows(ctx, H, [&](int y) { for (int x = 0; x < W; ++x) {
         const int2 px(x, y); const int2 hi_px = px * 2 + hi_px_offset;
         float depth = depth_tex.load(hi_px).x;
         if (0.0f == depth) {
@@ -527,7 +527,7 @@ int kjb_pass_rtdgi_restir_spatial(kjb_context* ctx, const kjb_rtdgi_restir_spati
     const int W = reservoir_output_tex.w(), H = reservoir_output_tex.h();
     const int2 hso = halfres_subsample_offset(g.fc.frame_index);
 
-    parallel_rows(H, [&](int y) { for (int x = 0; x < W; ++x) {
+    pass_rows(ctx, H, [&](int y) { for (int x = 0; x < W; ++x) {
         const int2 px(x, y); const int2 hi_px = px * 2 + hso;
         float depth = half_depth_tex.load(px).x;
         const uint seed = g.fc.frame_index + spatial_reuse_pass_idx * 123;
@@ -680,7 +680,7 @@ int kjb_pass_rtdgi_restir_resolve(kjb_context* ctx, const kjb_rtdgi_restir_resol
     const float4 gbuffer_tex_size = f4(a->gbuffer_tex_size), output_tex_size = f4(a->output_tex_size);
     const int W = irradiance_output_tex.w(), H = irradiance_output_tex.h();
     const int2 hso = halfres_subsample_offset(g.fc.frame_index);
-    parallel_rows(H, [&](int y) { for (int x = 0; x < W; ++x) {
+    pass_rows(ctx, H, [&](int y) { for (int x = 0; x < W; ++x) {
         const int2 px(x, y);
         float depth = depth_tex.load(px).x;
         if (0 == depth) { irradiance_output_tex.store(px, float4(0.0f)); continue; }
@@ -782,7 +782,7 @@ int kjb_pass_rtdgi_temporal(kjb_context* ctx, const kjb_rtdgi_temporal_args* a) 
     const float4 output_tex_size = f4(a->output_tex_size);
     const int W = output_tex.w(), H = output_tex.h();
     const float ped = g.fc.pre_exposure_delta;
-    parallel_rows(H, [&](int y) { for (int x = 0; x < W; ++x) {
+    pass_rows(ctx, H, [&](int y) { for (int x = 0; x < W; ++x) {
         const int2 px(x, y);
         float2 uv = get_uv(px, output_tex_size);
         float4 center = linear_rgb_to_crunched_luma_chroma(input_tex.load(px));
@@ -843,7 +843,7 @@ int kjb_pass_rtdgi_spatial(kjb_context* ctx, const kjb_rtdgi_spatial_args* a) {
     const int W = output_tex.w(), H = output_tex.h();
     auto crunch = [](float3 v) { return v * rcp(max3(v.x, v.y, v.z) + 1.0f); };
     auto uncrunch = [](float3 v) { return v * rcp(1.0f - max3(v.x, v.y, v.z)); };
-    parallel_rows(H, [&](int y) { for (int x = 0; x < W; ++x) {
+    pass_rows(ctx, H, [&](int y) { for (int x = 0; x < W; ++x) {
         const int2 px(x, y);
         float4 sum(0.0f);
         const float4 cin = input_tex.load(px);

@@ -83,7 +83,7 @@ int kjb_pass_taa_reproject(kjb_context* ctx, const kjb_taa_reproject_args* a) {
         const float2 d = vel_max - vel_min, thr = 0.1f * max(float2(input_tex_size.z, input_tex_size.w), abs(vel_max + vel_min));
         return d.x > thr.x || d.y > thr.y;
     };
-    parallel_rows(H, [&](int y) { for (int x = 0; x < W; ++x) {
+    pass_rows(ctx, H, [&](int y) { for (int x = 0; x < W; ++x) {
         const int2 reproj_px = reproj_px_of(x, y);
         float2 uv = get_uv(int2(x, y), output_tex_size);
         int2 closest_px = reproj_px;
@@ -129,7 +129,7 @@ int kjb_pass_taa_filter_input(kjb_context* ctx, const kjb_taa_filter_input_args*
         FilteredInput r; r.clamped_ex = clamped_iex; r.var = max(float3(0.0f), iex2 - iex * iex);
         return r;
     };
-    parallel_rows(H, [&](int y) { for (int x = 0; x < W; ++x) {
+    pass_rows(ctx, H, [&](int y) { for (int x = 0; x < W; ++x) {
         const float center_depth = depth_tex.load(x, y).x;
         FilteredInput fi = inner(x, y, center_depth, 1e10f, 200);
         FilteredInput cfi = inner(x, y, center_depth, fi.clamped_ex.x * 1.001f, 200);
@@ -158,7 +158,7 @@ int kjb_pass_taa_filter_history(kjb_context* ctx, const kjb_taa_filter_history_a
         return iex / iwsum;
     };
     const int k = (input_tex_size.x / output_tex_size.x > 1.75f) ? 2 : 1;
-    parallel_rows(H, [&](int y) { for (int x = 0; x < W; ++x) {
+    pass_rows(ctx, H, [&](int y) { for (int x = 0; x < W; ++x) {
         float2 uv = get_uv(int2(x, y), output_tex_size);
         float filtered_luma = filter_input(uv, 1e10f, k).x;
         output_tex.store(x, y, float4(filter_input(uv, filtered_luma * 1.001f, k), 0));
@@ -174,7 +174,7 @@ int kjb_pass_taa_input_prob(kjb_context* ctx, const kjb_taa_input_prob_args* a) 
     const float4 input_tex_size = f4(a->input_tex_size);
     const int W = output_tex.w(), H = output_tex.h();
     const float2 sop(g.fc.view_constants.sample_offset_pixels[0], g.fc.view_constants.sample_offset_pixels[1]);
-    parallel_rows(H, [&](int y) { for (int x = 0; x < W; ++x) {
+    pass_rows(ctx, H, [&](int y) { for (int x = 0; x < W; ++x) {
         float input_prob = 0;
         float3 ivar(0.0f);
         for (int yy = -1; yy <= 1; ++yy) for (int xx = -1; xx <= 1; ++xx) ivar = max(ivar, filtered_input_dev_tex.load(x + xx * 2, y + yy * 2).xyz());
@@ -201,7 +201,7 @@ int kjb_pass_taa_input_prob(kjb_context* ctx, const kjb_taa_input_prob_args* a) 
 // ------------------------------------------------------------------ T5 taa/filter_prob.hlsl, T6 taa/filter_prob2.hlsl
 int kjb_pass_taa_prob_filter(kjb_context* ctx, const kjb_taa_prob_filter_args* a) {
     Img input_tex(a->input_tex), output_tex(a->output_tex);
-    parallel_rows(output_tex.h(), [&](int y) { for (int x = 0; x < output_tex.w(); ++x) {
+    pass_rows(ctx, output_tex.h(), [&](int y) { for (int x = 0; x < output_tex.w(); ++x) {
         float prob = input_tex.load(x, y).x;
         for (int yy = -1; yy <= 1; ++yy) for (int xx = -1; xx <= 1; ++xx) prob = max(prob, input_tex.load(x + xx, y + yy).x);
         output_tex.store(x, y, float4(prob));
@@ -210,7 +210,7 @@ int kjb_pass_taa_prob_filter(kjb_context* ctx, const kjb_taa_prob_filter_args* a
 }
 int kjb_pass_taa_prob_filter2(kjb_context* ctx, const kjb_taa_prob_filter_args* a) {
     Img input_tex(a->input_tex), output_tex(a->output_tex);
-    parallel_rows(output_tex.h(), [&](int y) { for (int x = 0; x < output_tex.w(); ++x) {
+    pass_rows(ctx, output_tex.h(), [&](int y) { for (int x = 0; x < output_tex.w(); ++x) {
         float2 weighted_prob(0.0f);
         const float SQUISH_STRENGTH = 10;
         for (int yy = -2; yy <= 2; ++yy) for (int xx = -2; xx <= 2; ++xx) {
@@ -232,7 +232,7 @@ int kjb_pass_taa(kjb_context* ctx, const kjb_taa_args* a) {
     const int W = temporal_output_tex.w(), H = temporal_output_tex.h();
     const float2 sop(g.fc.view_constants.sample_offset_pixels[0], g.fc.view_constants.sample_offset_pixels[1]);
     const float dt = g.fc.delta_time_seconds;
-    parallel_rows(H, [&](int y) { for (int x = 0; x < W; ++x) {
+    pass_rows(ctx, H, [&](int y) { for (int x = 0; x < W; ++x) {
         const float2 irf = float2(input_tex_size.x, input_tex_size.y) / float2(output_tex_size.x, output_tex_size.y);
         const int2 reproj_px(int(kjb_cvt_u32((float(x) + 0.5f) * irf.x)), int(kjb_cvt_u32((float(y) + 0.5f) * irf.y)));
         float2 uv = get_uv(int2(x, y), output_tex_size);

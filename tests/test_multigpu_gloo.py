@@ -1,0 +1,67 @@
+"""Tile-sharded frames on CPU: world_size 2 and 3 over gloo.  Every rank renders its band of the frame with the
+kernel emulator, exchanges tile borders through ONE all-gather per frame (kjb_allgather -> gloo callback) and must reproduce,
+bit for bit, the rows of a single-process full-frame render."""
+import ctypes as C, os, socket, sys
+import numpy as np, pytest
+import torch, torch.distributed as dist, torch.multiprocessing as mp
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+
+W, H, FRAMES = 64, 640, 5      # tall and narrow: bands of 160/107 half-res rows vs halos of 64-76 rows: every pass runs on a PARTIAL row range
+
+
+def _free_port():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
+
+
+def _worker(rank, world_size, port, enable_taa, ret):
+    sys.path.insert(0, ROOT); sys.path.insert(0, HERE)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    os.environ["KJB_EMU_THREADS"] = "2"
+    dist.init_process_group("gloo", rank=rank, world_size=world_size)
+    from kajiya_b200._abi import KjbLib
+    from kajiya_b200 import scenes
+    import parity
+    lib = KjbLib(os.path.join(HERE, "emu", "_build", "libkjb_emu.so"))
+    scene, view = scenes.cornell_box()
+    view = dict(view, camera_position=(0.0, 1.0, 5.0))
+    kw = dict(enable_taa=enable_taa, spatial_reuse_pass_count=2)
+    tiled = parity.make_world(lib, scene, W, H, tile=(rank, world_size), **kw)
+    calls = [0]
+
+    def allgather(send, recv, n):
+        s = torch.frombuffer((C.c_uint8 * n).from_address(send), dtype=torch.uint8)
+        r = torch.frombuffer((C.c_uint8 * (n * world_size)).from_address(recv), dtype=torch.uint8)
+        dist.all_gather_into_tensor(r, s)
+        calls[0] += 1
+        return 0
+
+    tiled.comm_set_callback(allgather, rank, world_size)
+    full = parity.make_world(lib, scene, W, H, **kw)
+    for _ in range(FRAMES):
+        tiled.render_frame(**view); full.render_frame(**view)
+    hh = (H + 1) // 2
+    y0, y1 = hh * rank // world_size, hh * (rank + 1) // world_size
+    bad = []
+    names = ["rtdgi.spatial_filtered", "rtdgi.temporal_filtered", "rtdgi.irradiance"] + [n for n in full.image_names() if n.endswith(":0") or n.endswith(":1")]
+    if enable_taa:
+        names += ["taa.this_frame_out"]
+    for n in names:
+        a, b = tiled.image(n), full.image(n)
+        s = a.shape[0] // hh            # 1 for half-res images, 2 for full-res
+        ra, rb = a[y0 * s:y1 * s].view(np.uint8), b[y0 * s:y1 * s].view(np.uint8)
+        if not np.array_equal(ra, rb):
+            bad.append((n, int((ra != rb).any(-1).sum())))
+    ret[rank] = (bad, calls[0])
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world_size,enable_taa", [(2, False), (3, True)])
+def test_tile_sharded_frames_match_single_process(world_size, enable_taa, emu_lib):
+    ret = mp.Manager().dict()
+    mp.spawn(_worker, args=(world_size, _free_port(), enable_taa, ret), nprocs=world_size, join=True)
+    for rank in range(world_size):
+        bad, calls = ret[rank]
+        assert calls == FRAMES, "exactly one all-gather per frame"
+        assert not bad, f"rank {rank}: band differs from the single-process frame: {bad}"
