@@ -220,6 +220,9 @@ int  kjb_memcpy_d2d(kjb_context *ctx, void *dst, const void *src, uint64_t bytes
 /* Tile-sharded frames: restrict the FOLLOWING passes to rows [y0, y1) of their own output grid
  * (each rank of a multi-GPU frame computes its band plus the halo a pass's consumers need).  (0, 0) = whole image. */
 int  kjb_set_scissor(kjb_context *ctx, uint32_t y0, uint32_t y1);
+/* Determinism aid: while on, every pass that touches the (racy by design) irradiance cache runs on ONE device thread in the launch
+ * order of its parallel kernel. Orders of magnitude slower; for reproducing cache states and for bit-exact parity tests. */
+int  kjb_set_debug_serial(kjb_context *ctx, uint32_t on);
 
 /* ------------------------------------------------------------------ input producers (needed to feed the path) */
 typedef struct kjb_raster_gbuffer_args {   /* replaces "raster simple" (raster_simple_ps.hlsl:39-140) by primary-ray casting */
@@ -255,6 +258,47 @@ typedef struct kjb_ircache_bindings {
     kjb_buffer meta_buf, grid_meta_buf, entry_cell_buf, spatial_buf, irradiance_buf, aux_buf,
                life_buf, pool_buf, reposition_proposal_buf, reposition_proposal_count_buf;
 } kjb_ircache_bindings;
+
+/* ------------------------------------------------------------------ ircache (renderers/ircache.rs, shaders under assets/shaders/ircache/)
+ * Buffer sizes: ircache.rs:172-231 (MAX_ENTRIES 65536, 12 cascades x 32^3 cells).  Indirect dispatches of the reference
+ * (dispatch_indirect / trace_rays_indirect) become fixed-size launches that early-out on the counters in meta_buf, exactly like
+ * the reference's own fixed-size validate/trace dispatches (ircache.rs:438-447,471-476). */
+#define KJB_IRCACHE_MAX_ENTRIES 65536u
+#define KJB_IRCACHE_GRID_CELLS (32u * 32u * 32u * 12u)
+typedef struct kjb_ircache_clear_pool_args { kjb_buffer pool_buf, life_buf; } kjb_ircache_clear_pool_args;            /* "clear ircache pool" */
+int kjb_pass_ircache_clear_pool(kjb_context *ctx, const kjb_ircache_clear_pool_args *a);
+typedef struct kjb_ircache_scroll_cascades_args {     /* "scroll cascades", scroll_cascades.hlsl:4-10 */
+    kjb_buffer grid_meta_buf, grid_meta_buf2, entry_cell_buf, irradiance_buf, life_buf, pool_buf, meta_buf;
+} kjb_ircache_scroll_cascades_args;
+int kjb_pass_ircache_scroll_cascades(kjb_context *ctx, const kjb_ircache_scroll_cascades_args *a);
+typedef struct kjb_ircache_dispatch_args_args { kjb_buffer meta_buf, dispatch_args; } kjb_ircache_dispatch_args_args;
+int kjb_pass_ircache_prepare_age_dispatch_args(kjb_context *ctx, const kjb_ircache_dispatch_args_args *a);    /* "_ircache dispatch args" (prepare_age_dispatch_args.hlsl) */
+int kjb_pass_ircache_prepare_trace_dispatch_args(kjb_context *ctx, const kjb_ircache_dispatch_args_args *a);  /* "_ircache dispatch args" (prepare_trace_dispatch_args.hlsl) */
+typedef struct kjb_ircache_age_args {                 /* "age ircache entries", age_ircache_entries.hlsl:5-14 */
+    kjb_buffer meta_buf, grid_meta_buf, entry_cell_buf, life_buf, pool_buf, spatial_buf, reposition_proposal_buf,
+               reposition_proposal_count_buf, irradiance_buf, entry_occupancy_buf;
+} kjb_ircache_age_args;
+int kjb_pass_ircache_age_entries(kjb_context *ctx, const kjb_ircache_age_args *a);
+typedef struct kjb_prefix_scan_args { kjb_buffer inout_buf; uint32_t element_count; } kjb_prefix_scan_args;   /* "_prefix scan 1/2/merge" (prefix_scan.rs:10-39): inclusive u32 scan */
+int kjb_pass_inclusive_prefix_scan_u32(kjb_context *ctx, const kjb_prefix_scan_args *a);
+typedef struct kjb_ircache_compact_args { kjb_buffer meta_buf, life_buf, entry_occupancy_buf, entry_indirection_buf; } kjb_ircache_compact_args;   /* "ircache compact" */
+int kjb_pass_ircache_compact(kjb_context *ctx, const kjb_ircache_compact_args *a);
+typedef struct kjb_ircache_reset_args { kjb_buffer life_buf, meta_buf, irradiance_buf, aux_buf, entry_indirection_buf; } kjb_ircache_reset_args;   /* "ircache reset" */
+int kjb_pass_ircache_reset(kjb_context *ctx, const kjb_ircache_reset_args *a);
+typedef struct kjb_ircache_trace_access_args {        /* "ircache trace access", trace_accessibility.rgen.hlsl:14-19 */
+    kjb_buffer spatial_buf, life_buf, reposition_proposal_buf, meta_buf, aux_buf, entry_indirection_buf;
+} kjb_ircache_trace_access_args;
+int kjb_pass_ircache_trace_access(kjb_context *ctx, const kjb_ircache_trace_access_args *a);
+typedef struct kjb_ircache_trace_args {               /* "ircache validate" / "ircache trace", trace_irradiance.rgen.hlsl:21-33 */
+    kjb_buffer spatial_buf; kjb_image sky_cube_tex;
+    kjb_buffer grid_meta_buf, life_buf, reposition_proposal_buf, reposition_proposal_count_buf, meta_buf, aux_buf, pool_buf,
+               entry_indirection_buf, entry_cell_buf;
+    kjb_buffer irradiance_buf;                        /* lookup.hlsl reads it through DEFINE_IRCACHE_BINDINGS-equivalent globals */
+} kjb_ircache_trace_args;
+int kjb_pass_ircache_validate(kjb_context *ctx, const kjb_ircache_trace_args *a);
+int kjb_pass_ircache_trace(kjb_context *ctx, const kjb_ircache_trace_args *a);
+typedef struct kjb_ircache_sum_args { kjb_buffer life_buf, meta_buf, irradiance_buf, aux_buf, entry_indirection_buf; } kjb_ircache_sum_args;   /* "ircache sum" */
+int kjb_pass_ircache_sum(kjb_context *ctx, const kjb_ircache_sum_args *a);
 
 /* ------------------------------------------------------------------ rtdgi (renderers/rtdgi.rs) */
 typedef struct kjb_rtdgi_reproject_args {            /* "rtdgi reproject", fullres_reproject.hlsl:10-15, rtdgi.rs:156-164 */

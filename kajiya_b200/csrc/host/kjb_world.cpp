@@ -112,6 +112,10 @@ struct kjb_world {
     PingPong taa_temporal_tex{"taa"}, taa_temporal_velocity_tex{"taa.velocity"}, taa_temporal_smooth_var_tex{"taa.smooth_var"};   // taa.rs:19-27
     uint32_t OW = 0, OH = 0;   // temporal_upscale_extent
 
+    // IrcacheRenderer (renderers/ircache.rs:92-100)
+    bool ircache_initialized = false; uint32_t ircache_parity = 0;
+    float ircache_grid_center[3] = {0, 0, 0}; int32_t ircache_cur_scroll[12][3] = {}, ircache_prev_scroll[12][3] = {};
+
     int err = 0;
     // ---- tile sharding: this world owns half-res rows [ty0, ty1) of every frame
     bool tiled = false; uint32_t trank = 0, tcount = 1, ty0 = 0, ty1 = 0;
@@ -159,6 +163,13 @@ struct kjb_world {
         names_cache.clear();
         return images.emplace(name, i).first->second;
     }
+    // temporal_storage_buffer (ircache.rs:80-90): buffers live in the same name table, viewed as 1024-wide images so that the
+    // test harness can download and compare them like any other resource
+    kjb_buffer buf(const std::string& name, uint64_t elems, uint32_t fmt, uint32_t elem_bytes) {
+        const uint32_t wd = elems < 1024 ? uint32_t(elems) : 1024u, ht = uint32_t((elems + wd - 1) / wd);
+        kjb_image& i = img(name, wd, ht, fmt);
+        return kjb_buffer{i.data, uint64_t(wd) * ht * elem_bytes};
+    }
     void get_output_and_history(PingPong& pp, uint32_t w, uint32_t h, uint32_t fmt, kjb_image*& out, kjb_image*& hist) {
         out = &img(pp.output_key, w, h, fmt);
         hist = &img(pp.history_key, w, h, fmt);
@@ -189,6 +200,7 @@ int kjb_world_create(kjb_context* ctx, const kjb_world_desc* desc, kjb_world** o
     w->W = desc->render_width; w->H = desc->render_height;
     w->HW = (w->W + 1) / 2; w->HH = (w->H + 1) / 2;   // ImageDesc::half_res = div_up (image.rs:140-142)
     w->OW = desc->temporal_upscale_width ? desc->temporal_upscale_width : w->W; w->OH = desc->temporal_upscale_height ? desc->temporal_upscale_height : w->H;
+    if (desc->tile_count > 1 && desc->enable_ircache) { delete w; return 1; }   // the cache is one global racy structure: it does not shard by rows
     if (desc->tile_count > 1) {
         if (w->OW != w->W || w->OH != w->H || (w->H & 1)) { delete w; return 1; }   // tiles + temporal upscaling / odd heights: not supported
         w->tiled = true; w->trank = desc->tile_rank; w->tcount = desc->tile_count;
@@ -348,6 +360,23 @@ static int begin_frame(kjb_world* w, const kjb_world_frame* f, kjb_frame_constan
     fc.pre_exposure = fc.pre_exposure_prev = fc.pre_exposure_delta = 1.0f;   // dynamic exposure lives in post (out of scope): EV 0
     fc.render_override_flags = 0; fc.render_override_material_roughness_scale = 1.0f;
 
+    if (w->desc.enable_ircache) {
+        // IrcacheRenderer::update_eye_position + constants (ircache.rs:125-157, world_renderer.rs:1060-1092)
+        const float IRCACHE_GRID_CELL_DIAMETER = 0.16f * 0.125f;
+        for (int c = 0; c < 3; ++c) { w->ircache_grid_center[c] = f->camera_position[c]; fc.ircache_grid_center[c] = f->camera_position[c]; }
+        fc.ircache_grid_center[3] = 1.0f;
+        for (int cascade = 0; cascade < 12; ++cascade) {
+            const float cell_diameter = IRCACHE_GRID_CELL_DIAMETER * float(1u << cascade);
+            for (int c = 0; c < 3; ++c) {
+                const int32_t cascade_center = int32_t(std::floor(f->camera_position[c] / cell_diameter));
+                w->ircache_prev_scroll[cascade][c] = w->ircache_cur_scroll[cascade][c];
+                w->ircache_cur_scroll[cascade][c] = cascade_center - 16;
+                fc.ircache_cascades[cascade].origin[c] = w->ircache_cur_scroll[cascade][c];
+                fc.ircache_cascades[cascade].voxels_scrolled_this_frame[c] = w->ircache_cur_scroll[cascade][c] - w->ircache_prev_scroll[cascade][c];
+            }
+        }
+    }
+
     // triangle lights: instance-transformed copies of each mesh's light set (world_renderer.rs:1036-1056)
     std::vector<kjb_triangle_light> lights;
     for (const kjb_instance& inst : w->instances) for (kjb_triangle_light l : w->mesh_lights[inst.mesh_index]) {
@@ -473,12 +502,93 @@ static int tile_exchange(kjb_world* w, const std::vector<XchgItem>& items) {
 }
 
 // ---------------------------------------------------------------- RtdgiRenderer::render (rtdgi.rs:173-554)
+// ---------------------------------------------------------------- IrcacheRenderer / IrcacheRenderState (renderers/ircache.rs)
+struct IrcacheState {
+    kjb_buffer meta_buf, grid_meta_buf, grid_meta_buf2, entry_cell_buf, spatial_buf, irradiance_buf, aux_buf, life_buf, pool_buf,
+               entry_indirection_buf, reposition_proposal_buf, reposition_proposal_count_buf, trace_dispatch_args;
+    bool bound = false;
+    kjb_ircache_bindings bindings() const {   // bind_mut (ircache.rs:59-78)
+        kjb_ircache_bindings b{};
+        if (!bound) return b;
+        b.meta_buf = meta_buf; b.grid_meta_buf = grid_meta_buf; b.entry_cell_buf = entry_cell_buf; b.spatial_buf = spatial_buf; b.irradiance_buf = irradiance_buf;
+        b.aux_buf = aux_buf; b.life_buf = life_buf; b.pool_buf = pool_buf; b.reposition_proposal_buf = reposition_proposal_buf;
+        b.reposition_proposal_count_buf = reposition_proposal_count_buf;
+        return b;
+    }
+};
+
+// IrcacheRenderer::prepare (ircache.rs:166-351)
+static IrcacheState ircache_prepare(kjb_world* w) {
+    kjb_context* ctx = w->ctx;
+    const uint64_t MAX_ENTRIES = KJB_IRCACHE_MAX_ENTRIES, MAX_GRID_CELLS = KJB_IRCACHE_GRID_CELLS;
+    IrcacheState st;
+    st.meta_buf = w->buf("ircache.meta_buf", 8, KJB_FMT_R32_UINT, 4);
+    st.grid_meta_buf = w->buf("ircache.grid_meta_buf", MAX_GRID_CELLS, KJB_FMT_RG32_UINT, 8);
+    st.grid_meta_buf2 = w->buf("ircache.grid_meta_buf2", MAX_GRID_CELLS, KJB_FMT_RG32_UINT, 8);
+    st.entry_cell_buf = w->buf("ircache.entry_cell_buf", MAX_ENTRIES, KJB_FMT_R32_UINT, 4);
+    st.spatial_buf = w->buf("ircache.spatial_buf", MAX_ENTRIES, KJB_FMT_RGBA32_FLOAT, 16);
+    st.irradiance_buf = w->buf("ircache.irradiance_buf", 3 * MAX_ENTRIES, KJB_FMT_RGBA32_FLOAT, 16);
+    st.aux_buf = w->buf("ircache.aux_buf", 4 * 16 * MAX_ENTRIES, KJB_FMT_RGBA32_FLOAT, 16);
+    st.life_buf = w->buf("ircache.life_buf", MAX_ENTRIES, KJB_FMT_R32_UINT, 4);
+    st.pool_buf = w->buf("ircache.pool_buf", MAX_ENTRIES, KJB_FMT_R32_UINT, 4);
+    st.entry_indirection_buf = w->buf("ircache.entry_indirection_buf", 1024 * 1024, KJB_FMT_R32_UINT, 4);
+    st.reposition_proposal_buf = w->buf("ircache.reposition_proposal_buf", MAX_ENTRIES, KJB_FMT_RGBA32_FLOAT, 16);
+    st.reposition_proposal_count_buf = w->buf("ircache.reposition_proposal_count_buf", MAX_ENTRIES, KJB_FMT_R32_UINT, 4);
+    st.bound = true;
+    if (1 == w->ircache_parity) std::swap(st.grid_meta_buf, st.grid_meta_buf2);
+
+    if (!w->ircache_initialized) {
+        kjb_ircache_clear_pool_args a{st.pool_buf, st.life_buf};
+        RUN("clear ircache pool", kjb_pass_ircache_clear_pool(ctx, &a));
+        w->ircache_initialized = true;
+    } else {
+        kjb_ircache_scroll_cascades_args a{st.grid_meta_buf, st.grid_meta_buf2, st.entry_cell_buf, st.irradiance_buf, st.life_buf, st.pool_buf, st.meta_buf};
+        RUN("scroll cascades", kjb_pass_ircache_scroll_cascades(ctx, &a));
+        std::swap(st.grid_meta_buf, st.grid_meta_buf2);
+        w->ircache_parity = (w->ircache_parity + 1) % 2;
+    }
+    kjb_buffer age_args = w->buf("ircache.age_dispatch_args", 8, KJB_FMT_R32_UINT, 4);
+    { kjb_ircache_dispatch_args_args a{st.meta_buf, age_args}; RUN("_ircache dispatch args", kjb_pass_ircache_prepare_age_dispatch_args(ctx, &a)); }
+    kjb_buffer entry_occupancy_buf = w->buf("ircache.entry_occupancy_buf", MAX_ENTRIES, KJB_FMT_R32_UINT, 4);
+    {
+        kjb_ircache_age_args a{st.meta_buf, st.grid_meta_buf, st.entry_cell_buf, st.life_buf, st.pool_buf, st.spatial_buf, st.reposition_proposal_buf,
+                               st.reposition_proposal_count_buf, st.irradiance_buf, entry_occupancy_buf};
+        RUN("age ircache entries", kjb_pass_ircache_age_entries(ctx, &a));
+    }
+    { kjb_prefix_scan_args a{entry_occupancy_buf, uint32_t(MAX_ENTRIES)}; RUN("_prefix scan", kjb_pass_inclusive_prefix_scan_u32(ctx, &a)); }
+    { kjb_ircache_compact_args a{st.meta_buf, st.life_buf, entry_occupancy_buf, st.entry_indirection_buf}; RUN("ircache compact", kjb_pass_ircache_compact(ctx, &a)); }
+    return st;
+}
+
+// IrcacheRenderState::trace_irradiance (ircache.rs:360-487)
+static void ircache_trace_irradiance(kjb_world* w, IrcacheState& st, kjb_image& sky_cube) {
+    kjb_context* ctx = w->ctx;
+    st.trace_dispatch_args = w->buf("ircache.trace_dispatch_args", 16, KJB_FMT_R32_UINT, 4);
+    { kjb_ircache_dispatch_args_args a{st.meta_buf, st.trace_dispatch_args}; RUN("_ircache dispatch args", kjb_pass_ircache_prepare_trace_dispatch_args(ctx, &a)); }
+    { kjb_ircache_reset_args a{st.life_buf, st.meta_buf, st.irradiance_buf, st.aux_buf, st.entry_indirection_buf}; RUN("ircache reset", kjb_pass_ircache_reset(ctx, &a)); }
+    {
+        kjb_ircache_trace_access_args a{st.spatial_buf, st.life_buf, st.reposition_proposal_buf, st.meta_buf, st.aux_buf, st.entry_indirection_buf};
+        RUN("ircache trace access", kjb_pass_ircache_trace_access(ctx, &a));
+    }
+    kjb_ircache_trace_args t{};
+    t.spatial_buf = st.spatial_buf; t.sky_cube_tex = sky_cube; t.grid_meta_buf = st.grid_meta_buf; t.life_buf = st.life_buf; t.reposition_proposal_buf = st.reposition_proposal_buf;
+    t.reposition_proposal_count_buf = st.reposition_proposal_count_buf; t.meta_buf = st.meta_buf; t.aux_buf = st.aux_buf; t.pool_buf = st.pool_buf;
+    t.entry_indirection_buf = st.entry_indirection_buf; t.entry_cell_buf = st.entry_cell_buf; t.irradiance_buf = st.irradiance_buf;
+    RUN("ircache validate", kjb_pass_ircache_validate(ctx, &t));
+    RUN("ircache trace", kjb_pass_ircache_trace(ctx, &t));
+}
+
+// IrcacheRenderState::sum_up_irradiance_for_sampling (ircache.rs:493-511)
+static void ircache_sum_up_irradiance(kjb_world* w, IrcacheState& st) {
+    kjb_ircache_sum_args a{st.life_buf, st.meta_buf, st.irradiance_buf, st.aux_buf, st.entry_indirection_buf};
+    RUN("ircache sum", kjb_pass_ircache_sum(w->ctx, &a));
+}
+
 static void rtdgi_render(kjb_world* w, kjb_image& reprojected_history_tex, kjb_image& temporal_output_tex, kjb_image& gbuffer, kjb_image& depth,
-                         kjb_image& geometric_normal, kjb_image& reprojection_map, kjb_image& sky_cube, kjb_image& ssao_tex) {
+                         kjb_image& geometric_normal, kjb_image& reprojection_map, kjb_image& sky_cube, kjb_image& ssao_tex, const kjb_ircache_bindings& ircache) {
     kjb_context* ctx = w->ctx;
     const uint32_t HW = w->HW, HH = w->HH, W = w->W, H = w->H;
     float gbuffer_size[4]; size4(gbuffer_size, gbuffer);
-    kjb_ircache_bindings no_ircache{};   // TODO(ircache): bind IrcacheRenderState when enable_ircache
     const TileHalos th = tile_halos(w);
     w->rows_all();   // the half-res extracts are cheap and read at arbitrary screen positions (ray march): whole image
 
@@ -510,7 +620,7 @@ static void rtdgi_render(kjb_world* w, kjb_image& reprojected_history_tex, kjb_i
         kjb_rtdgi_validate_args a{};
         a.half_view_normal_tex = half_view_normal_tex; a.depth_tex = depth; a.reprojected_gi_tex = reprojected_history_tex;
         a.reservoir_tex = *reservoir_history_tex; a.reservoir_ray_history_tex = *ray_history_tex; a.reprojection_tex = reprojection_map;
-        a.ircache = no_ircache; a.sky_cube_tex = sky_cube; a.irradiance_history_tex = *radiance_history_tex; a.ray_orig_history_tex = *ray_orig_history_tex;
+        a.ircache = ircache; a.sky_cube_tex = sky_cube; a.irradiance_history_tex = *radiance_history_tex; a.ray_orig_history_tex = *ray_orig_history_tex;
         a.rt_history_invalidity_out_tex = rt_history_validity_pre_input_tex; memcpy(a.gbuffer_tex_size, gbuffer_size, 16);
         w->rows(th.d4, 1);
         RUN("rtdgi validate", kjb_pass_rtdgi_validate(ctx, &a));
@@ -520,7 +630,7 @@ static void rtdgi_render(kjb_world* w, kjb_image& reprojected_history_tex, kjb_i
     {   // "rtdgi trace" (rtdgi.rs:321-345)
         kjb_rtdgi_trace_args a{};
         a.half_view_normal_tex = half_view_normal_tex; a.depth_tex = depth; a.reprojected_gi_tex = reprojected_history_tex; a.reprojection_tex = reprojection_map;
-        a.ircache = no_ircache; a.sky_cube_tex = sky_cube; a.ray_orig_history_tex = *ray_orig_history_tex;
+        a.ircache = ircache; a.sky_cube_tex = sky_cube; a.ray_orig_history_tex = *ray_orig_history_tex;
         a.candidate_irradiance_out_tex = candidate_radiance_tex; a.candidate_normal_out_tex = candidate_normal_tex; a.candidate_hit_out_tex = candidate_hit_tex;
         a.rt_history_invalidity_in_tex = rt_history_validity_pre_input_tex; a.rt_history_invalidity_out_tex = rt_history_validity_input_tex;
         memcpy(a.gbuffer_tex_size, gbuffer_size, 16);
@@ -699,6 +809,10 @@ int kjb_world_render_frame(kjb_world* w, const kjb_world_frame* f) {
     kjb_image& ssao_tex = w->img("ssao", W, H, KJB_FMT_R8_UNORM);
     if (!w->ssao_filled) { kjb_image_fill_u8(ctx, &ssao_tex, 255); w->ssao_filled = true; }
 
+    // ircache.prepare + trace_irradiance (world_render_passes.rs:99-122): cache rays use the convolved sky cube
+    IrcacheState ircache_state;
+    if (w->desc.enable_ircache) { ircache_state = ircache_prepare(w); ircache_trace_irradiance(w, ircache_state, convolved_sky_cube); }
+
     // rtdgi.reproject (world_render_passes.rs:129, rtdgi.rs:143-171)
     kjb_image *temporal_output_tex, *history_tex; w->get_output_and_history(w->temporal2_tex, W, H, KJB_FMT_RGBA16_FLOAT, temporal_output_tex, history_tex);
     kjb_image& reprojected_history_tex = w->img("rtdgi.reprojected_history", W, H, KJB_FMT_RGBA16_FLOAT);
@@ -707,8 +821,9 @@ int kjb_world_render_frame(kjb_world* w, const kjb_world_frame* f) {
         size4(a.output_tex_size, reprojected_history_tex);
         RUN("rtdgi reproject", kjb_pass_rtdgi_reproject(ctx, &a));
     }
+    if (w->desc.enable_ircache) ircache_sum_up_irradiance(w, ircache_state);   // world_render_passes.rs:138-140
     // rtdgi.render (world_render_passes.rs:146-160): diffuse rays use the convolved sky cube
-    rtdgi_render(w, reprojected_history_tex, *temporal_output_tex, gbuffer, depth, geometric_normal, reprojection_map, convolved_sky_cube, ssao_tex);
+    rtdgi_render(w, reprojected_history_tex, *temporal_output_tex, gbuffer, depth, geometric_normal, reprojection_map, convolved_sky_cube, ssao_tex, ircache_state.bindings());
 
     // taa.render (world_render_passes.rs:253-263).  light_gbuffer (the composite that normally feeds TAA) is outside the hot
     // path: TAA consumes the GI result directly.

@@ -162,6 +162,7 @@ int kjb_set_frame_constants(kjb_context* c, const kjb_frame_constants* fc, const
     return 0;
 }
 int kjb_set_scissor(kjb_context* c, uint32_t y0, uint32_t y1) { c->scissor_y0 = y0; c->scissor_y1 = y1; return 0; }
+int kjb_set_debug_serial(kjb_context* c, uint32_t on) { c->debug_serial = on != 0; return 0; }
 int kjb_set_luts(kjb_context* c, const kjb_image* fg, const kjb_image* bn) {
     if (!check_img(c, *fg, KJB_FMT_RGBA16_FLOAT, "kjb_set_luts", "brdf_fg_lut", 64, 64)) return 1;
     if (!check_img(c, *bn, KJB_FMT_RGBA8_UNORM, "kjb_set_luts", "blue_noise", 256, 256)) return 1;

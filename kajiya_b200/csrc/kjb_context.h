@@ -45,6 +45,7 @@ struct kjb_context {
     // Row scissor for tile-sharded frames: the next pass only computes rows [scissor_y0, scissor_y1) of ITS output
     // grid (0,0 = whole image).  Set by kjb_set_scissor, consumed (and kept) by every kjb_pass_* launch.
     uint32_t scissor_y0 = 0, scissor_y1 = 0;
+    bool debug_serial = false;   // kjb_set_debug_serial: cache-touching passes run on one GPU thread in launch order
     kjb::Rows rows_for(uint32_t H) const {
         kjb::Rows r; r.y0 = 0; r.y1 = int(H);
         if (scissor_y1 > scissor_y0) { r.y0 = int(scissor_y0 < H ? scissor_y0 : H); r.y1 = int(scissor_y1 < H ? scissor_y1 : H); }
@@ -113,10 +114,14 @@ inline bool check_img(kjb_context* c, const kjb_image& i, uint32_t fmt, const ch
 #define KJB_KERNEL(bounds) static void
 #define KJB_LAUNCH(ctx, kernel, dims, ...) do { if (kjb__rows.y1 > kjb__rows.y0) { kjb_emu::launch(dims, [&]() { kernel(__VA_ARGS__, kjb__rows); }); (ctx)->launches++; } } while (0)
 #define KJB_LAUNCH_SYNC(ctx, kernel, dims, ...) do { if (kjb__rows.y1 > kjb__rows.y0) { kjb_emu::launch_sync(dims, [&]() { kernel(__VA_ARGS__, kjb__rows); }); (ctx)->launches++; } } while (0)
+// kernels that touch the (racy by design) irradiance cache: the emulator runs their blocks one after another in launch order, which
+// makes the test build deterministic and comparable with the oracle's serial schedule; on the GPU this is a plain launch
+#define KJB_LAUNCH_ORDERED(ctx, kernel, dims, ...) do { if (kjb__rows.y1 > kjb__rows.y0) { kjb_emu::g_serial++; kjb_emu::launch(dims, [&]() { kernel(__VA_ARGS__, kjb__rows); }); kjb_emu::g_serial--; (ctx)->launches++; } } while (0)
 #else
 #define KJB_KERNEL(bounds) __global__ void __launch_bounds__(bounds)
 #define KJB_LAUNCH(ctx, kernel, dims, ...) do { if (kjb__rows.y1 > kjb__rows.y0) { kernel<<<dims, 0, (ctx)->stream>>>(__VA_ARGS__, kjb__rows); (ctx)->launches++; } } while (0)
 #define KJB_LAUNCH_SYNC KJB_LAUNCH   /* kernels that use __syncthreads(): only the test emulator needs to know */
+#define KJB_LAUNCH_ORDERED KJB_LAUNCH
 #endif
 #define KJB_DIMS(...) __VA_ARGS__
 // every kernel's last parameter is `Rows kjb_rows`: the row range of its grid this launch covers (tile sharding)

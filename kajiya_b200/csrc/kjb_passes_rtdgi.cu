@@ -5,6 +5,7 @@
 // 16x8 blocks (register pressure of the traversal stack + BRDF state).  Neighbourhood taps go through L1/L2: the
 // half-res working set at 1080p (~40 MB for all ReSTIR state) is L2-resident on B200 (126 MB).
 #include "kjb_context.h"
+#include "kjb_ircache.cuh"
 
 using namespace kjb;
 
@@ -27,7 +28,7 @@ struct TraceResult { float3 out_value, hit_normal_ws; float hit_t, pdf; bool is_
 
 // rtdgi/diffuse_trace_common.inc.hlsl:38-221
 KJB_DEV TraceResult do_the_thing(const Globals& g, const Img& depth_tex, const Img& reprojected_gi_tex, const Img& sky_cube_tex, const float* gbuffer_tex_size,
-                                 uint32_t px, uint32_t py, float3 normal_ws, uint32_t& rng, const Ray& outgoing_ray) {
+                                 uint32_t px, uint32_t py, float3 normal_ws, uint32_t& rng, const Ray& outgoing_ray, const IrcacheBufs& ircache) {
     const kjb_view_constants& vc = g.fc.view_constants;
     float3 total_radiance = f3(0.0f);
     float3 hit_normal_ws = -outgoing_ray.dir;
@@ -88,7 +89,8 @@ KJB_DEV TraceResult do_the_thing(const Globals& g, const Img& depth_tex, const I
                     total_radiance += !is_shadowed ? (f3(tl.radiance[0], tl.radiance[1], tl.radiance[2]) * brdf_value / ls.pdf) : f3(0.0f);
                 }
             }
-            // USE_IRCACHE: lookup contributes 0 when no cache is bound (kjb_ircache_bindings.meta_buf == NULL)
+            // USE_IRCACHE: the lookup contributes 0 when no cache is bound (kjb_ircache_bindings.meta_buf == NULL)
+            total_radiance += ircache_lookup<false>(g, ircache, outgoing_ray.origin, primary_hit.position, gbuffer.normal, 1, rng) * gbuffer.albedo;
         }
     } else {
         total_radiance += xyz(sample_cube_rgba16f(sky_cube_tex, outgoing_ray.dir));
@@ -147,9 +149,8 @@ KJB_KERNEL(256) k_rtdgi_reproject(Img input_tex, Img reprojection_tex, ImgW outp
 }
 
 // ------------------------------------------------------------------ D3 diffuse_validate.rgen.hlsl:46-111
-KJB_KERNEL(128) k_rtdgi_validate(Globals g, Img half_view_normal_tex, Img depth_tex, Img reprojected_gi_tex, ImgW reservoir_tex, Img reservoir_ray_history_tex,
-                                 Img sky_cube_tex, ImgW irradiance_history_tex, Img ray_orig_history_tex, ImgW out_tex, float4 gts, Rows kjb_rows) {
-    KJB_PX; if (x >= out_tex.w || y >= out_tex.h) return;
+KJB_DEV void rtdgi_validate_px(const Globals& g, const Img& half_view_normal_tex, const Img& depth_tex, const Img& reprojected_gi_tex, const ImgW& reservoir_tex, const Img& reservoir_ray_history_tex,
+                               const Img& sky_cube_tex, const ImgW& irradiance_history_tex, const Img& ray_orig_history_tex, const ImgW& out_tex, float4 gts, const IrcacheBufs& ircache, int x, int y) {
     const kjb_view_constants& vc = g.fc.view_constants;
     const int2 hso = halfres_subsample_offset(g.fc.frame_index);
     if (0.0f == ld_r32f(depth_tex, x * 2 + hso.x, y * 2 + hso.y)) { st_r8u(out_tex, x, y, 1.0f); return; }
@@ -163,7 +164,7 @@ KJB_KERNEL(128) k_rtdgi_validate(Globals g, Img half_view_normal_tex, Img depth_
         const float3 prev_radiance = vmax(f3(0.0f), xyz(prev_radiance_packed));
         Ray prev_ray; prev_ray.dir = normalize(prev_hit_pos - prev_ray_orig); prev_ray.origin = prev_ray_orig; prev_ray.tmin = 0; prev_ray.tmax = SKY_DIST;
         uint32_t rng = hash3(uint32_t(x), uint32_t(y), 0u);
-        const TraceResult result = do_the_thing(g, depth_tex, reprojected_gi_tex, sky_cube_tex, s4, uint32_t(x), uint32_t(y), normal_ws, rng, prev_ray);
+        const TraceResult result = do_the_thing(g, depth_tex, reprojected_gi_tex, sky_cube_tex, s4, uint32_t(x), uint32_t(y), normal_ws, rng, prev_ray, ircache);
         const float3 new_radiance = vmax(f3(0.0f), result.out_value);
         const float rad_diff = length(vabs(prev_radiance - new_radiance) / vmax(f3(1e-3f), prev_radiance + new_radiance));
         invalidity = kjb_smoothstep(0.1f, 0.5f, rad_diff / length(f3(1.0f)));
@@ -179,11 +180,25 @@ KJB_KERNEL(128) k_rtdgi_validate(Globals g, Img half_view_normal_tex, Img depth_
     }
     st_r8u(out_tex, x, y, invalidity);
 }
+KJB_KERNEL(128) k_rtdgi_validate(Globals g, Img half_view_normal_tex, Img depth_tex, Img reprojected_gi_tex, ImgW reservoir_tex, Img reservoir_ray_history_tex,
+                                 Img sky_cube_tex, ImgW irradiance_history_tex, Img ray_orig_history_tex, ImgW out_tex, float4 gts, IrcacheBufs ircache, Rows kjb_rows) {
+    KJB_PX; if (x >= out_tex.w || y >= out_tex.h) return;
+    rtdgi_validate_px(g, half_view_normal_tex, depth_tex, reprojected_gi_tex, reservoir_tex, reservoir_ray_history_tex, sky_cube_tex, irradiance_history_tex, ray_orig_history_tex, out_tex, gts, ircache, x, y);
+}
+// `_serial` twins (kjb_set_debug_serial, see kjb_passes_ircache.cu): one thread walks the pixels in the launch order of the
+// parallel kernel — 16x8 blocks row-major, pixels row-major inside a block
+#define KJB_SERIAL_TILES(W, H, ...) do { if (blockIdx.x | blockIdx.y | threadIdx.x | threadIdx.y) return; \
+        for (int by = kjb_rows.y0; by < kjb_rows.y1; by += 8) for (int bx = 0; bx < (W); bx += 16) \
+            for (int y = by; y < by + 8 && y < kjb_rows.y1 && y < (H); ++y) for (int x = bx; x < bx + 16 && x < (W); ++x) { __VA_ARGS__; } } while (0)
+KJB_KERNEL(32) k_rtdgi_validate_serial(Globals g, Img half_view_normal_tex, Img depth_tex, Img reprojected_gi_tex, ImgW reservoir_tex, Img reservoir_ray_history_tex,
+                                       Img sky_cube_tex, ImgW irradiance_history_tex, Img ray_orig_history_tex, ImgW out_tex, float4 gts, IrcacheBufs ircache, Rows kjb_rows) {
+    KJB_SERIAL_TILES(out_tex.w, out_tex.h, rtdgi_validate_px(g, half_view_normal_tex, depth_tex, reprojected_gi_tex, reservoir_tex, reservoir_ray_history_tex, sky_cube_tex, irradiance_history_tex,
+                                                              ray_orig_history_tex, out_tex, gts, ircache, x, y));
+}
 
 // ------------------------------------------------------------------ D4 trace_diffuse.rgen.hlsl:49-120
-KJB_KERNEL(128) k_rtdgi_trace(Globals g, Img half_view_normal_tex, Img depth_tex, Img reprojected_gi_tex, Img reprojection_tex, Img sky_cube_tex,
-                              ImgW cand_irr, ImgW cand_normal, ImgW cand_hit, Img inv_in, ImgW inv_out, float4 gts, Rows kjb_rows) {
-    KJB_PX; if (x >= cand_irr.w || y >= cand_irr.h) return;
+KJB_DEV void rtdgi_trace_px(const Globals& g, const Img& half_view_normal_tex, const Img& depth_tex, const Img& reprojected_gi_tex, const Img& reprojection_tex, const Img& sky_cube_tex,
+                            const ImgW& cand_irr, const ImgW& cand_normal, const ImgW& cand_hit, const Img& inv_in, const ImgW& inv_out, float4 gts, const IrcacheBufs& ircache, int x, int y) {
     const kjb_view_constants& vc = g.fc.view_constants;
     const int2 hso = halfres_subsample_offset(g.fc.frame_index);
     const int hx = x * 2 + hso.x, hy = y * 2 + hso.y;
@@ -204,7 +219,7 @@ KJB_KERNEL(128) k_rtdgi_trace(Globals g, Img half_view_normal_tex, Img depth_tex
         Ray outgoing_ray; outgoing_ray.dir = outgoing_dir; outgoing_ray.origin = vrc.biased_secondary_ray_origin_ws_with_normal(normal_ws);
         outgoing_ray.tmin = 0; outgoing_ray.tmax = is_tracing_frame(g) ? SKY_DIST : NEAR_FIELD_FADE_OUT_END;
         uint32_t rng = hash3(uint32_t(x), uint32_t(y), g.fc.frame_index & 31u);
-        TraceResult result = do_the_thing(g, depth_tex, reprojected_gi_tex, sky_cube_tex, s4, uint32_t(x), uint32_t(y), normal_ws, rng, outgoing_ray);
+        TraceResult result = do_the_thing(g, depth_tex, reprojected_gi_tex, sky_cube_tex, s4, uint32_t(x), uint32_t(y), normal_ws, rng, outgoing_ray, ircache);
         if (!is_tracing_frame(g) && !result.is_hit) { result.out_value = f3(0.0f); result.hit_t = SKY_DIST; }
         const float3 hit_offset_ws = outgoing_ray.dir * result.hit_t;
         const float cos_theta = dot(normalize(outgoing_dir - vrc.ray_dir_ws()), normal_ws);
@@ -215,6 +230,15 @@ KJB_KERNEL(128) k_rtdgi_trace(Globals g, Img half_view_normal_tex, Img depth_tex
     const float4 reproj = ld_rgba16s(reprojection_tex, hx, hy);
     const int rx = kjb_cvt_i32(kjb_floor(float(x) + gts.x * reproj.x / 2 + 0.5f)), ry = kjb_cvt_i32(kjb_floor(float(y) + gts.y * reproj.y / 2 + 0.5f));
     st_r8u(inv_out, x, y, ld_r8u(inv_in, rx, ry));
+}
+KJB_KERNEL(128) k_rtdgi_trace(Globals g, Img half_view_normal_tex, Img depth_tex, Img reprojected_gi_tex, Img reprojection_tex, Img sky_cube_tex,
+                              ImgW cand_irr, ImgW cand_normal, ImgW cand_hit, Img inv_in, ImgW inv_out, float4 gts, IrcacheBufs ircache, Rows kjb_rows) {
+    KJB_PX; if (x >= cand_irr.w || y >= cand_irr.h) return;
+    rtdgi_trace_px(g, half_view_normal_tex, depth_tex, reprojected_gi_tex, reprojection_tex, sky_cube_tex, cand_irr, cand_normal, cand_hit, inv_in, inv_out, gts, ircache, x, y);
+}
+KJB_KERNEL(32) k_rtdgi_trace_serial(Globals g, Img half_view_normal_tex, Img depth_tex, Img reprojected_gi_tex, Img reprojection_tex, Img sky_cube_tex,
+                                    ImgW cand_irr, ImgW cand_normal, ImgW cand_hit, Img inv_in, ImgW inv_out, float4 gts, IrcacheBufs ircache, Rows kjb_rows) {
+    KJB_SERIAL_TILES(cand_irr.w, cand_irr.h, rtdgi_trace_px(g, half_view_normal_tex, depth_tex, reprojected_gi_tex, reprojection_tex, sky_cube_tex, cand_irr, cand_normal, cand_hit, inv_in, inv_out, gts, ircache, x, y));
 }
 
 // ------------------------------------------------------------------ D5 temporal_validity_integrate.hlsl:21-119
@@ -707,6 +731,20 @@ KJB_KERNEL(256) k_rtdgi_spatial(Globals g, Img input_tex, Img depth_tex, Img ssa
 #define CHK(img, fmt, name) if (!check_img(c, (img), (fmt), P, name)) return 1
 #define CHKE(img, fmt, name, w, h) if (!check_img(c, (img), (fmt), P, name, (w), (h))) return 1
 
+// the irradiance-cache binding block of a pass: all-or-nothing (NULL meta_buf = unbound), sizes per ircache.rs:172-231
+static int check_ircache_bindings(kjb_context* c, const char* P, const kjb_ircache_bindings& b, IrcacheBufs& out) {
+    out = IrcacheBufs{};
+    if (!b.meta_buf.data) return 0;
+    const uint64_t E = KJB_IRCACHE_MAX_ENTRIES;
+    const bool ok = b.meta_buf.size_bytes >= 32 && b.grid_meta_buf.data && b.grid_meta_buf.size_bytes >= 8ull * KJB_IRCACHE_GRID_CELLS && b.entry_cell_buf.data && b.entry_cell_buf.size_bytes >= 4 * E
+        && b.spatial_buf.data && b.spatial_buf.size_bytes >= 16 * E && b.irradiance_buf.data && b.irradiance_buf.size_bytes >= 48 * E && b.life_buf.data && b.life_buf.size_bytes >= 4 * E
+        && b.pool_buf.data && b.pool_buf.size_bytes >= 4 * E && b.reposition_proposal_buf.data && b.reposition_proposal_buf.size_bytes >= 16 * E
+        && b.reposition_proposal_count_buf.data && b.reposition_proposal_count_buf.size_bytes >= 4 * E;
+    if (!ok) return c->fail(std::string(P) + ": irradiance cache bindings are incomplete or too small");
+    out = ircache_bufs(b);
+    return 0;
+}
+
 extern "C" {
 
 int kjb_pass_rtdgi_reproject(kjb_context* c, const kjb_rtdgi_reproject_args* a) {
@@ -722,10 +760,17 @@ int kjb_pass_rtdgi_validate(kjb_context* c, const kjb_rtdgi_validate_args* a) {
     CHK(a->depth_tex, KJB_FMT_R32_FLOAT, "depth_tex"); CHK(a->reprojected_gi_tex, KJB_FMT_RGBA16_FLOAT, "reprojected_gi_tex"); CHKE(a->reservoir_tex, KJB_FMT_RG32_UINT, "reservoir_tex", W, H);
     CHKE(a->reservoir_ray_history_tex, KJB_FMT_RGBA16_FLOAT, "reservoir_ray_history_tex", W, H); CHK(a->sky_cube_tex, KJB_FMT_RGBA16_FLOAT, "sky_cube_tex");
     CHKE(a->irradiance_history_tex, KJB_FMT_RGBA16_FLOAT, "irradiance_history_tex", W, H); CHKE(a->ray_orig_history_tex, KJB_FMT_RGBA32_FLOAT, "ray_orig_history_tex", W, H);
-    if (a->ircache.meta_buf.data) return c->fail("rtdgi validate: irradiance cache bindings are not supported by this build yet");
+    IrcacheBufs ircache; if (check_ircache_bindings(c, P, a->ircache, ircache)) return 1;
     KJB_ROWS(c, H);
-    KJB_LAUNCH(c, k_rtdgi_validate, KJB_GRID2D(W, H, 16, 8), c->g, img_ro(a->half_view_normal_tex), img_ro(a->depth_tex), img_ro(a->reprojected_gi_tex), img_rw(a->reservoir_tex),
-               img_ro(a->reservoir_ray_history_tex), img_ro(a->sky_cube_tex), img_rw(a->irradiance_history_tex), img_ro(a->ray_orig_history_tex), img_rw(a->rt_history_invalidity_out_tex), F4A(a->gbuffer_tex_size));
+    if (ircache.bound() && c->debug_serial)
+        KJB_LAUNCH(c, k_rtdgi_validate_serial, KJB_DIMS(dim3(1), dim3(32)), c->g, img_ro(a->half_view_normal_tex), img_ro(a->depth_tex), img_ro(a->reprojected_gi_tex), img_rw(a->reservoir_tex),
+               img_ro(a->reservoir_ray_history_tex), img_ro(a->sky_cube_tex), img_rw(a->irradiance_history_tex), img_ro(a->ray_orig_history_tex), img_rw(a->rt_history_invalidity_out_tex), F4A(a->gbuffer_tex_size), ircache);
+    else if (ircache.bound())
+        KJB_LAUNCH_ORDERED(c, k_rtdgi_validate, KJB_GRID2D(W, H, 16, 8), c->g, img_ro(a->half_view_normal_tex), img_ro(a->depth_tex), img_ro(a->reprojected_gi_tex), img_rw(a->reservoir_tex),
+               img_ro(a->reservoir_ray_history_tex), img_ro(a->sky_cube_tex), img_rw(a->irradiance_history_tex), img_ro(a->ray_orig_history_tex), img_rw(a->rt_history_invalidity_out_tex), F4A(a->gbuffer_tex_size), ircache);
+    else
+        KJB_LAUNCH(c, k_rtdgi_validate, KJB_GRID2D(W, H, 16, 8), c->g, img_ro(a->half_view_normal_tex), img_ro(a->depth_tex), img_ro(a->reprojected_gi_tex), img_rw(a->reservoir_tex),
+               img_ro(a->reservoir_ray_history_tex), img_ro(a->sky_cube_tex), img_rw(a->irradiance_history_tex), img_ro(a->ray_orig_history_tex), img_rw(a->rt_history_invalidity_out_tex), F4A(a->gbuffer_tex_size), ircache);
     KJB_PASS_EPILOGUE(c, P);
 }
 int kjb_pass_rtdgi_trace(kjb_context* c, const kjb_rtdgi_trace_args* a) {
@@ -735,11 +780,20 @@ int kjb_pass_rtdgi_trace(kjb_context* c, const kjb_rtdgi_trace_args* a) {
     CHK(a->depth_tex, KJB_FMT_R32_FLOAT, "depth_tex"); CHK(a->reprojected_gi_tex, KJB_FMT_RGBA16_FLOAT, "reprojected_gi_tex"); CHK(a->reprojection_tex, KJB_FMT_RGBA16_SNORM, "reprojection_tex");
     CHK(a->sky_cube_tex, KJB_FMT_RGBA16_FLOAT, "sky_cube_tex"); CHKE(a->rt_history_invalidity_in_tex, KJB_FMT_R8_UNORM, "rt_history_invalidity_in_tex", W, H);
     CHKE(a->rt_history_invalidity_out_tex, KJB_FMT_R8_UNORM, "rt_history_invalidity_out_tex", W, H);
-    if (a->ircache.meta_buf.data) return c->fail("rtdgi trace: irradiance cache bindings are not supported by this build yet");
+    IrcacheBufs ircache; if (check_ircache_bindings(c, P, a->ircache, ircache)) return 1;
     KJB_ROWS(c, H);
-    KJB_LAUNCH(c, k_rtdgi_trace, KJB_GRID2D(W, H, 16, 8), c->g, img_ro(a->half_view_normal_tex), img_ro(a->depth_tex), img_ro(a->reprojected_gi_tex), img_ro(a->reprojection_tex), img_ro(a->sky_cube_tex),
+    if (ircache.bound() && c->debug_serial)
+        KJB_LAUNCH(c, k_rtdgi_trace_serial, KJB_DIMS(dim3(1), dim3(32)), c->g, img_ro(a->half_view_normal_tex), img_ro(a->depth_tex), img_ro(a->reprojected_gi_tex), img_ro(a->reprojection_tex), img_ro(a->sky_cube_tex),
                img_rw(a->candidate_irradiance_out_tex), img_rw(a->candidate_normal_out_tex), img_rw(a->candidate_hit_out_tex), img_ro(a->rt_history_invalidity_in_tex), img_rw(a->rt_history_invalidity_out_tex),
-               F4A(a->gbuffer_tex_size));
+               F4A(a->gbuffer_tex_size), ircache);
+    else if (ircache.bound())
+        KJB_LAUNCH_ORDERED(c, k_rtdgi_trace, KJB_GRID2D(W, H, 16, 8), c->g, img_ro(a->half_view_normal_tex), img_ro(a->depth_tex), img_ro(a->reprojected_gi_tex), img_ro(a->reprojection_tex), img_ro(a->sky_cube_tex),
+               img_rw(a->candidate_irradiance_out_tex), img_rw(a->candidate_normal_out_tex), img_rw(a->candidate_hit_out_tex), img_ro(a->rt_history_invalidity_in_tex), img_rw(a->rt_history_invalidity_out_tex),
+               F4A(a->gbuffer_tex_size), ircache);
+    else
+        KJB_LAUNCH(c, k_rtdgi_trace, KJB_GRID2D(W, H, 16, 8), c->g, img_ro(a->half_view_normal_tex), img_ro(a->depth_tex), img_ro(a->reprojected_gi_tex), img_ro(a->reprojection_tex), img_ro(a->sky_cube_tex),
+               img_rw(a->candidate_irradiance_out_tex), img_rw(a->candidate_normal_out_tex), img_rw(a->candidate_hit_out_tex), img_ro(a->rt_history_invalidity_in_tex), img_rw(a->rt_history_invalidity_out_tex),
+               F4A(a->gbuffer_tex_size), ircache);
     KJB_PASS_EPILOGUE(c, P);
 }
 int kjb_pass_rtdgi_validity_integrate(kjb_context* c, const kjb_rtdgi_validity_integrate_args* a) {

@@ -35,6 +35,10 @@ class World:
         if self.ctx:
             self.d.kjb_destroy(self.ctx); self.ctx = None
 
+    def set_debug_serial(self, on=True):
+        """cache-touching passes on one device thread in launch order (deterministic; slow)"""
+        self._check(self.d.kjb_set_debug_serial(self.ctx, int(on)))
+
     # -- multi-GPU transport (tile = (rank, count)) ------------------------------------------------------------
     def comm_init_nccl(self, unique_id_bytes, rank, nranks):
         buf = C.create_string_buffer(bytes(unique_id_bytes), 128)

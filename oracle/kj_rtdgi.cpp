@@ -1,7 +1,7 @@
 // ORACLE — TEST INFRASTRUCTURE ONLY (see kj_math.h header).  PARITY UNPINNED (no reference goldens).
 // CPU restatement of kajiya's ray-traced diffuse GI passes, one function per render-graph pass
 // (crates/lib/kajiya/src/renderers/rtdgi.rs).  Paths below are relative to /root/reference/assets/shaders/.
-#include "kj_ctx.h"
+#include "kj_ircache_lookup.h"
 
 namespace kjo {
 
@@ -36,7 +36,7 @@ struct TraceResult { float3 out_value, hit_normal_ws; float hit_t, pdf; bool is_
 
 // rtdgi/diffuse_trace_common.inc.hlsl:38-221  (USE_WORLD_RADIANCE_CACHE 0; ircache lookup handled by the caller-supplied hook)
 TraceResult do_the_thing(const kjb_context& ctx, const Img& depth_tex, const Img& reprojected_gi_tex, const Img& sky_cube_tex,
-                         float4 gbuffer_tex_size, uint2 px, float3 normal_ws, uint& rng, Ray outgoing_ray) {
+                         float4 gbuffer_tex_size, uint2 px, float3 normal_ws, uint& rng, Ray outgoing_ray, const IrcacheBufs& ircache) {
     const Globals& g = ctx.g; const kjb_view_constants& vc = g.fc.view_constants;
     float3 total_radiance(0.0f);
     float3 hit_normal_ws = -outgoing_ray.dir;
@@ -107,7 +107,10 @@ TraceResult do_the_thing(const kjb_context& ctx, const Img& depth_tex, const Img
                     }
                 }
             }
-            // USE_IRCACHE: no irradiance cache bound in this configuration (kjb_ircache_bindings.meta_buf == NULL) -> contributes 0.
+            {   // USE_IRCACHE (contributes 0 when no cache is bound: kjb_ircache_bindings.meta_buf == NULL)
+                const float3 gi = ircache_lookup(g, ircache, outgoing_ray.origin, primary_hit.position, gbuffer.normal, 1, rng, false);
+                total_radiance += gi * gbuffer.albedo;
+            }
         }
     } else {
         total_radiance += sky_cube_tex.sample_cube(outgoing_ray.dir).xyz();
@@ -201,9 +204,10 @@ int kjb_pass_rtdgi_validate(kjb_context* ctx, const kjb_rtdgi_validate_args* a) 
     const float4 gbuffer_tex_size = f4(a->gbuffer_tex_size);
     const int W = out_tex.w(), H = out_tex.h();
     const int2 hi_px_offset = halfres_subsample_offset(g.fc.frame_index);
-    pass_rows(ctx, H, [&](int y) { for (int x = 0; x < W; ++x) {
+    const IrcacheBufs ircache = IrcacheBufs::from(a->ircache);
+    pass_pixels(ctx, W, H, ircache.bound(), [&](int x, int y) { {
         const int2 px(x, y); const int2 hi_px = px * 2 + hi_px_offset;
-        if (0.0f == depth_tex.load(hi_px).x) { out_tex.store(px, float4(1.0f)); continue; }
+        if (0.0f == depth_tex.load(hi_px).x) { out_tex.store(px, float4(1.0f)); return; }
         float invalidity = 0.0f;
         if (is_rtdgi_validation_frame(g)) {
             const float3 normal_vs = half_view_normal_tex.load(px).xyz();
@@ -215,7 +219,7 @@ int kjb_pass_rtdgi_validate(kjb_context* ctx, const kjb_rtdgi_validate_args* a) 
 
             Ray prev_ray; prev_ray.dir = normalize(prev_hit_pos - prev_ray_orig); prev_ray.origin = prev_ray_orig; prev_ray.tmin = 0; prev_ray.tmax = SKY_DIST;
             uint rng = hash3(uint(x), uint(y), 0);
-            TraceResult result = do_the_thing(*ctx, depth_tex, reprojected_gi_tex, sky_cube_tex, gbuffer_tex_size, uint2(x, y), normal_ws, rng, prev_ray);
+            TraceResult result = do_the_thing(*ctx, depth_tex, reprojected_gi_tex, sky_cube_tex, gbuffer_tex_size, uint2(x, y), normal_ws, rng, prev_ray, ircache);
             const float3 new_radiance = max(float3(0.0f), result.out_value);
 
             const float rad_diff = length(abs(prev_radiance - new_radiance) / max(float3(1e-3f), prev_radiance + new_radiance));
@@ -235,7 +239,7 @@ int kjb_pass_rtdgi_validate(kjb_context* ctx, const kjb_rtdgi_validate_args* a) 
             }
         }
         out_tex.store(px, float4(invalidity));
-    } }, ctx->num_threads);
+    } });
     return 0;
 }
 
@@ -248,12 +252,13 @@ int kjb_pass_rtdgi_trace(kjb_context* ctx, const kjb_rtdgi_trace_args* a) {
     const float4 gbuffer_tex_size = f4(a->gbuffer_tex_size);
     const int W = cand_irr.w(), H = cand_irr.h();
     const int2 hi_px_offset = halfres_subsample_offset(g.fc.frame_index);
-    pass_rows(ctx, H, [&](int y) { for (int x = 0; x < W; ++x) {
+    const IrcacheBufs ircache = IrcacheBufs::from(a->ircache);
+    pass_pixels(ctx, W, H, ircache.bound(), [&](int x, int y) { {
         const int2 px(x, y); const int2 hi_px = px * 2 + hi_px_offset;
         float depth = depth_tex.load(hi_px).x;
         if (0.0f == depth) {
             cand_irr.store(px, float4(0.0f)); cand_normal.store(px, float4(0, 0, 1, 0)); inv_out.store(px, float4(0.0f));
-            continue;
+            return;
         }
         const float2 uv = get_uv(hi_px, gbuffer_tex_size);
         const ViewRayContext view_ray_context = ViewRayContext::from_uv_and_biased_depth(vc, uv, depth);
@@ -268,7 +273,7 @@ int kjb_pass_rtdgi_trace(kjb_context* ctx, const kjb_rtdgi_trace_args* a) {
             outgoing_ray.tmin = 0;
             outgoing_ray.tmax = is_rtdgi_tracing_frame(g) ? SKY_DIST : NEAR_FIELD_FADE_OUT_END;
             uint rng = hash3(uint(x), uint(y), g.fc.frame_index & 31);
-            TraceResult result = do_the_thing(*ctx, depth_tex, reprojected_gi_tex, sky_cube_tex, gbuffer_tex_size, uint2(x, y), normal_ws, rng, outgoing_ray);
+            TraceResult result = do_the_thing(*ctx, depth_tex, reprojected_gi_tex, sky_cube_tex, gbuffer_tex_size, uint2(x, y), normal_ws, rng, outgoing_ray, ircache);
             if (!is_rtdgi_tracing_frame(g) && !result.is_hit) { result.out_value = float3(0.0f); result.hit_t = SKY_DIST; }
             const float3 hit_offset_ws = outgoing_ray.dir * result.hit_t;
             const float cos_theta = dot(normalize(outgoing_dir - view_ray_context.ray_dir_ws()), normal_ws);
@@ -279,7 +284,7 @@ int kjb_pass_rtdgi_trace(kjb_context* ctx, const kjb_rtdgi_trace_args* a) {
         const float4 reproj = reprojection_tex.load(hi_px);
         const int2 reproj_px(kjb_cvt_i32(floor(float(x) + gbuffer_tex_size.x * reproj.x / 2 + 0.5f)), kjb_cvt_i32(floor(float(y) + gbuffer_tex_size.y * reproj.y / 2 + 0.5f)));
         inv_out.store(px, float4(inv_in.load(reproj_px).x));
-    } }, ctx->num_threads);
+    } });
     return 0;
 }
 

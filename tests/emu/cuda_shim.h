@@ -38,6 +38,7 @@ extern thread_local dim3 blockDim, gridDim;
 
 namespace kjb_emu {
 int num_workers();
+extern int g_serial;   // > 0: run blocks one after another in launch order (KJB_LAUNCH_ORDERED)
 template <typename F> inline void launch(dim3 grid, dim3 block, F body) {
     const long nblocks = long(grid.x) * grid.y * grid.z;
     std::atomic<long> next{0};
@@ -55,7 +56,7 @@ template <typename F> inline void launch(dim3 grid, dim3 block, F body) {
             }
         }
     };
-    const int n = nblocks < 16 ? 1 : num_workers();
+    const int n = (nblocks < 16 || g_serial > 0) ? 1 : num_workers();
     if (n <= 1) { worker(); return; }
     std::vector<std::thread> th;
     for (int i = 0; i < n; ++i) th.emplace_back(worker);

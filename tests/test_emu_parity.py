@@ -1,5 +1,6 @@
 """Kernel LOGIC parity without a GPU: the unmodified .cu sources compiled for the CPU by the launch emulator
 (tests/emu) against the oracle, frame by frame, every image bit-for-bit.  (The real CUDA build is checked by test_gpu_parity.py.)"""
+import numpy as np
 import parity
 from kajiya_b200 import scenes
 
@@ -63,3 +64,41 @@ def test_taa_native_and_upscaled(oracle_lib, emu_lib):
         wa, wb, report = parity.run_lockstep(oracle_lib, emu_lib, scene, view, 100, 64, 5, **kw)
         _clean(report)
         assert "taa.this_frame_out" in wb.image_names() and wb.stats()["launches"] == 22
+
+
+def _moving_views(view, frames):
+    cp = np.array(view["camera_position"], np.float32)
+    for f in range(frames):
+        v = dict(view); v["camera_position"] = tuple(cp + np.array([0.07 * f, 0.013 * f, -0.09 * f], np.float32))
+        if f >= 8:
+            v["camera_rotation"] = (0.0, float(np.sin(0.6)), 0.0, float(np.cos(0.6)))   # turn away: entries age out and are recycled
+        yield v
+
+
+def test_ircache_lockstep(oracle_lib, emu_lib):
+    """Irradiance cache on (ircache.rs): the emulator runs the cache-touching kernels block after block in launch order, the schedule
+    the oracle restates, so every image AND every cache buffer (grid, pool, reservoirs, SH) must agree bit for bit."""
+    scene, view = scenes.cornell_box()
+    wa, wb, report = parity.run_lockstep(oracle_lib, emu_lib, scene, view, 96, 64, 6, enable_ircache=True)
+    assert not [(f, b) for f, fr in enumerate(report) for b in fr]
+    meta = wb.image("ircache.meta_buf").ravel()
+    assert meta[3] > 100 and meta[2] >= meta[3]          # entries were allocated; entry_count >= alloc_count
+    assert np.abs(wb.image("ircache.irradiance_buf")).max() > 0
+    assert {"ircache.grid_meta_buf", "ircache.aux_buf", "ircache.entry_indirection_buf"} <= set(wb.image_names())
+
+
+def test_ircache_moving_camera_scroll_and_recycle(oracle_lib, emu_lib):
+    """Cascade scrolling (scroll_cascades.hlsl), deallocation of scrolled-out cells, aging and pool recycling, through the
+    one-thread `_serial` twin kernels (kjb_set_debug_serial) on the kernel side."""
+    scene, view = scenes.cornell_box()
+    kw = dict(enable_ircache=True, spatial_reuse_pass_count=1)
+    wa, wb = parity.make_world(oracle_lib, scene, 80, 48, **kw), parity.make_world(emu_lib, scene, 80, 48, **kw)
+    wb.set_debug_serial(True)
+    peak = 0
+    for f, v in enumerate(_moving_views(view, 16)):
+        wa.render_frame(**v); wb.render_frame(**v)
+        bad = parity.compare_images(wa, wb)
+        assert not bad, (f, bad[:5])
+        peak = max(peak, int(wb.image("ircache.meta_buf").ravel()[3]))
+    meta = wb.image("ircache.meta_buf").ravel()
+    assert meta[3] < peak and meta[2] > meta[3]           # entries were recycled: alloc_count fell below its peak and below entry_count

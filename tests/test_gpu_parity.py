@@ -75,3 +75,67 @@ def test_taa_native_and_upscaled(oracle_lib, cuda_lib):
         _, wb, report = parity.run_lockstep(oracle_lib, cuda_lib, scene, view, 160, 90, 6, **kw)
         _assert_clean(report)
         assert "taa.this_frame_out" in wb.image_names()
+
+
+def _moving_views(view, frames):
+    cp = np.array(view["camera_position"], np.float32)
+    for f in range(frames):
+        v = dict(view); v["camera_position"] = tuple(cp + np.array([0.07 * f, 0.013 * f, -0.09 * f], np.float32))
+        if f >= 8:
+            v["camera_rotation"] = (0.0, float(np.sin(0.6)), 0.0, float(np.cos(0.6)))
+        yield v
+
+
+def test_ircache_serial_schedule_bit_exact(oracle_lib, cuda_lib):
+    """The irradiance cache is racy by design (ircache.rs:68-76), so its state depends on GPU scheduling.  With
+    kjb_set_debug_serial the CUDA kernels that touch the cache run on one device thread in launch order — the schedule the
+    oracle restates — and then EVERYTHING (images + grid/pool/reservoir/SH buffers) must be bit-identical, including cascade
+    scrolling, deallocation, aging and recycling under a moving camera."""
+    scene, view = scenes.cornell_box()
+    kw = dict(enable_ircache=True, spatial_reuse_pass_count=1)
+    wa, wb = parity.make_world(oracle_lib, scene, 80, 48, **kw), parity.make_world(cuda_lib, scene, 80, 48, **kw)
+    wb.set_debug_serial(True)
+    for f, v in enumerate(_moving_views(view, 16)):
+        wa.render_frame(**v); wb.render_frame(**v)
+        bad = parity.compare_images(wa, wb)
+        assert not bad, (f, bad[:5])
+    meta = wb.image("ircache.meta_buf").ravel()
+    assert meta[3] > 100 and meta[2] > meta[3]
+
+
+def _cache_summary(w):
+    meta = w.image("ircache.meta_buf").ravel()
+    life = w.image("ircache.life_buf").ravel()
+    irr = w.image("ircache.irradiance_buf").reshape(-1, 3, 4)
+    valid = life < 12
+    return dict(alloc=int(meta[3]), entries=int(meta[2]), valid=valid, r0=irr[valid][:, :, 0])
+
+
+def test_ircache_parallel_statistical(oracle_lib, cuda_lib):
+    """Normal (parallel, racy) execution against the oracle's serial schedule: which thread wins an allocation or a reposition
+    vote differs, so parity is statistical.  Tolerances: live entry count 3 %, occupied-cell sets Jaccard >= 0.9 (either buffer
+    parity), mean L0 irradiance 5 %, mean of the final GI image 2 %, and the final image within 0.05 RMS of the oracle's."""
+    scene, view = scenes.cornell_box()
+    kw = dict(enable_ircache=True)
+    wa, wb = parity.make_world(oracle_lib, scene, 192, 108, **kw), parity.make_world(cuda_lib, scene, 192, 108, **kw)
+    for f in range(12):
+        wa.render_frame(**view); wb.render_frame(**view)
+    a, b = _cache_summary(wa), _cache_summary(wb)
+    assert abs(a["alloc"] - b["alloc"]) <= 0.03 * a["alloc"] + 2, (a["alloc"], b["alloc"])
+    # occupied cells: the ping-pong parity is the same on both sides, compare the current grid
+    def occupied(w):
+        best = None
+        for n in ("ircache.grid_meta_buf", "ircache.grid_meta_buf2"):
+            g = w.image(n).reshape(-1, 2)
+            occ = set(np.nonzero(g[:, 1] & 1)[0].tolist())
+            if best is None or len(occ) > len(best): best = occ
+        return best
+    oa, ob = occupied(wa), occupied(wb)
+    jac = len(oa & ob) / max(1, len(oa | ob))
+    assert jac >= 0.9, jac
+    ma, mb = float(a["r0"].mean()), float(b["r0"].mean())
+    assert abs(ma - mb) <= 0.05 * abs(ma), (ma, mb)
+    ia, ib = wa.image("rtdgi.spatial_filtered").astype(np.float64)[..., :3], wb.image("rtdgi.spatial_filtered").astype(np.float64)[..., :3]
+    assert np.isfinite(ib).all()
+    assert abs(ia.mean() - ib.mean()) <= 0.02 * ia.mean(), (ia.mean(), ib.mean())
+    assert np.sqrt(((ia - ib) ** 2).mean()) <= 0.05 * max(ia.mean(), 1e-6) + 0.05, np.sqrt(((ia - ib) ** 2).mean())
