@@ -12,6 +12,14 @@ using namespace kjb;
 
 KJB_DEV uint32_t tid1d() { return blockIdx.x * blockDim.x + threadIdx.x; }
 
+// Slot 0 of the indirection table is never written (the compaction scan is inclusive, ircache_compact_entries.hlsl:17), so it keeps
+// naming entry 0, which — when alive — is also slot 1.  On the reference's GPU both copies sit in adjacent lanes of one wave and run
+// in lockstep: same reads, same writes, i.e. the entry is processed ONCE.  We get the same effect schedule-independently by
+// skipping the stale slot when it duplicates slot 1.
+KJB_DEV bool ircache_slot_is_stale_duplicate(const uint32_t* indirection, uint32_t alloc_count, uint32_t slot) {
+    return slot == 0u && alloc_count > 1u && indirection[1] == indirection[0];
+}
+
 // ------------------------------------------------------------------ I1 clear_ircache_pool.hlsl
 KJB_KERNEL(256) k_ircache_clear_pool(uint32_t* pool, uint32_t* life, Rows kjb_rows) {
     const uint32_t idx = tid1d(); if (idx >= MAX_ENTRIES) return;
@@ -137,7 +145,8 @@ KJB_KERNEL(256) k_ircache_compact(const uint32_t* meta, const uint32_t* life, co
 KJB_KERNEL(256) k_ircache_reset(const uint32_t* meta, const float4* irradiance, float4* aux, const uint32_t* indirection, Rows kjb_rows) {
     // 64 threads per entry clear its 64 aux texels (coalesced 1 KB)
     const uint32_t gid = tid1d(), dispatch_idx = gid / IRCACHE_AUX_STRIDE, i = gid % IRCACHE_AUX_STRIDE;
-    if (dispatch_idx >= meta[IRCACHE_META_TRACING_ALLOC_COUNT]) return;
+    const uint32_t alloc_count = meta[IRCACHE_META_TRACING_ALLOC_COUNT];
+    if (dispatch_idx >= alloc_count || ircache_slot_is_stale_duplicate(indirection, alloc_count, dispatch_idx)) return;
     const uint32_t entry_idx = indirection[dispatch_idx];
     const float4 v = irradiance[entry_idx * IRCACHE_IRRADIANCE_STRIDE];
     if (v.x == 0.0f && v.y == 0.0f && v.z == 0.0f && v.w == 0.0f) aux[entry_idx * IRCACHE_AUX_STRIDE + i] = f4(0.0f);
@@ -146,7 +155,9 @@ KJB_KERNEL(256) k_ircache_reset(const uint32_t* meta, const float4* irradiance, 
 // ------------------------------------------------------------------ I8 trace_accessibility.rgen.hlsl:21-66
 KJB_KERNEL(128) k_ircache_trace_access(Globals g, const float4* spatial, const uint32_t* life, const uint32_t* meta, float4* aux, const uint32_t* indirection, Rows kjb_rows) {
     const uint32_t dispatch_idx = tid1d();
-    if (dispatch_idx >= meta[IRCACHE_META_TRACING_ALLOC_COUNT] * IRCACHE_OCTA_DIMS2 || dispatch_idx >= MAX_ENTRIES * IRCACHE_OCTA_DIMS2) return;
+    const uint32_t alloc_count = meta[IRCACHE_META_TRACING_ALLOC_COUNT];
+    if (dispatch_idx >= alloc_count * IRCACHE_OCTA_DIMS2 || dispatch_idx >= MAX_ENTRIES * IRCACHE_OCTA_DIMS2) return;
+    if (ircache_slot_is_stale_duplicate(indirection, alloc_count, dispatch_idx / IRCACHE_OCTA_DIMS2)) return;
     const uint32_t entry_idx = indirection[dispatch_idx / IRCACHE_OCTA_DIMS2], octa_idx = dispatch_idx % IRCACHE_OCTA_DIMS2;
     if (!is_ircache_entry_life_valid(life[entry_idx])) return;
     const IrcacheVertex entry = unpack_vertex(spatial[entry_idx]);
@@ -216,7 +227,9 @@ KJB_DEV float self_lighting_limiter(float3 dir, float3 normal) { return kjb_lerp
 
 // ------------------------------------------------------------------ I9 ircache_validate.rgen.hlsl:44-131
 KJB_DEV void ircache_validate_sample(const Globals& g, const IrcacheBufs& b, const Img& sky_cube_tex, const uint32_t* indirection, uint32_t dispatch_idx) {
-    if (dispatch_idx >= b.meta[IRCACHE_META_TRACING_ALLOC_COUNT] * IRCACHE_VALIDATION_SAMPLES_PER_FRAME || dispatch_idx >= MAX_ENTRIES * IRCACHE_VALIDATION_SAMPLES_PER_FRAME) return;
+    const uint32_t alloc_count = b.meta[IRCACHE_META_TRACING_ALLOC_COUNT];
+    if (dispatch_idx >= alloc_count * IRCACHE_VALIDATION_SAMPLES_PER_FRAME || dispatch_idx >= MAX_ENTRIES * IRCACHE_VALIDATION_SAMPLES_PER_FRAME) return;
+    if (ircache_slot_is_stale_duplicate(indirection, alloc_count, dispatch_idx / IRCACHE_VALIDATION_SAMPLES_PER_FRAME)) return;
     const uint32_t entry_idx = indirection[dispatch_idx / IRCACHE_VALIDATION_SAMPLES_PER_FRAME], sample_idx = dispatch_idx % IRCACHE_VALIDATION_SAMPLES_PER_FRAME;
     const uint32_t life = b.life[entry_idx];
     const SampleParams sample_params = SampleParams::from_spf_entry_sample_frame(IRCACHE_VALIDATION_SAMPLES_PER_FRAME, entry_idx, sample_idx, g.fc.frame_index);
@@ -248,7 +261,9 @@ KJB_KERNEL(32) k_ircache_validate_serial(Globals g, IrcacheBufs b, Img sky_cube_
 
 // ------------------------------------------------------------------ I10 trace_irradiance.rgen.hlsl:44-145
 KJB_DEV void ircache_trace_sample(const Globals& g, const IrcacheBufs& b, const Img& sky_cube_tex, const uint32_t* indirection, uint32_t dispatch_idx) {
-    if (dispatch_idx >= b.meta[IRCACHE_META_TRACING_ALLOC_COUNT] * IRCACHE_SAMPLES_PER_FRAME || dispatch_idx >= MAX_ENTRIES * IRCACHE_SAMPLES_PER_FRAME) return;
+    const uint32_t alloc_count = b.meta[IRCACHE_META_TRACING_ALLOC_COUNT];
+    if (dispatch_idx >= alloc_count * IRCACHE_SAMPLES_PER_FRAME || dispatch_idx >= MAX_ENTRIES * IRCACHE_SAMPLES_PER_FRAME) return;
+    if (ircache_slot_is_stale_duplicate(indirection, alloc_count, dispatch_idx / IRCACHE_SAMPLES_PER_FRAME)) return;
     const uint32_t entry_idx = indirection[dispatch_idx / IRCACHE_SAMPLES_PER_FRAME], sample_idx = dispatch_idx % IRCACHE_SAMPLES_PER_FRAME;
     const uint32_t life = b.life[entry_idx];
     const float4 packed_entry = b.spatial[entry_idx];
@@ -288,7 +303,8 @@ KJB_KERNEL(32) k_ircache_trace_serial(Globals g, IrcacheBufs b, Img sky_cube_tex
 // ------------------------------------------------------------------ I11 sum_up_irradiance.hlsl:34-89
 KJB_KERNEL(256) k_ircache_sum(Globals g, const uint32_t* meta, float4* irradiance, const float4* aux, const uint32_t* indirection, Rows kjb_rows) {
     const uint32_t dispatch_idx = tid1d();
-    if (dispatch_idx >= meta[IRCACHE_META_TRACING_ALLOC_COUNT] || dispatch_idx >= MAX_ENTRIES) return;
+    const uint32_t alloc_count = meta[IRCACHE_META_TRACING_ALLOC_COUNT];
+    if (dispatch_idx >= alloc_count || dispatch_idx >= MAX_ENTRIES || ircache_slot_is_stale_duplicate(indirection, alloc_count, dispatch_idx)) return;
     const uint32_t entry_idx = indirection[dispatch_idx];
     float4 sh_rgb[3] = {f4(0.0f), f4(0.0f), f4(0.0f)};
     float valid_samples = 0;

@@ -243,16 +243,11 @@ KJB_KERNEL(32) k_rtdgi_trace_serial(Globals g, Img half_view_normal_tex, Img dep
 
 // ------------------------------------------------------------------ D5 temporal_validity_integrate.hlsl:21-119
 // The shader exchanges values between lanes of its 8x8 group (WaveReadLaneAt ^2, ^16, ^1, ^8; lane = x + 8*y in 32-wide waves):
-// partners are pixels (x^2,y), (x,y^2), (x^1,y), (x,y^1).  Instead of shuffles tied to a block shape we evaluate the
-// pre-exchange value for the four pixels involved (25 one-byte taps each, all L1 hits) — same result, any block shape.
-KJB_DEV float d5_blur(const Img& input_tex, int x, int y, const float* w25) {   // w25[(yy+2)*5+(xx+2)] = exp2(-0.1 * r^2), host-evaluated
-    float2 acc = f2(0.0f);
-    for (int yy = -2; yy <= 2; ++yy) for (int xx = -2; xx <= 2; ++xx) {
-        const float w = w25[(yy + 2) * 5 + (xx + 2)];
-        acc += f2(ld_r8u(input_tex, x + xx, y + yy), 1) * w;
-    }
-    return (acc / acc.y).x;
-}
+// partners are pixels (x^2,y), (x,y^2), (x^1,y), (x,y^1).  A 32x8 block whose origin is a multiple of 4 rows holds every partner,
+// so each thread computes ITS pre-exchange blur / edge value once (threads past the image edge included, like the shader's
+// out-of-range lanes), parks it in shared memory, and the exchange is two shared-memory reads.  The 5x5 blur reads the R8 input
+// from a (32+4)x(8+4) tile decoded once per texel.
+struct Weights25v { float w[25]; float w_sum; };   // w[(yy+2)*5+(xx+2)] = exp2(-0.1 r^2) and their float sum in tap order, host-evaluated
 KJB_DEV float d5_edge(const Img& reprojection_tex, const Img& half_depth_tex, int x, int y) {
     const float center_depth = ld_r32f(half_depth_tex, x, y);
     float edge = 1;
@@ -264,15 +259,31 @@ KJB_DEV float d5_edge(const Img& reprojection_tex, const Img& half_depth_tex, in
     }
     return edge;
 }
-struct Weights25v { float w[25]; };
 KJB_KERNEL(256) k_rtdgi_validity_integrate(Globals g, Img input_tex, Img history_tex, Img reprojection_tex, Img half_depth_tex, ImgW output_tex, float4 gts, Weights25v wt, Rows kjb_rows) {
-    KJB_PX; if (x >= output_tex.w || y >= output_tex.h) return;
-    const float b0 = kjb_lerp(d5_blur(input_tex, x, y, wt.w), d5_blur(input_tex, x ^ 2, y, wt.w), 0.5f);
-    const float b1 = kjb_lerp(d5_blur(input_tex, x, y ^ 2, wt.w), d5_blur(input_tex, x ^ 2, y ^ 2, wt.w), 0.5f);
+    __shared__ float in_tile[12][36];
+    __shared__ float blur_s[8][32], edge_s[8][32];
+    const int tx = int(threadIdx.x), ty = int(threadIdx.y);
+    const int bx0 = int(blockIdx.x) * 32, by0 = (kjb_rows.y0 & ~3) + int(blockIdx.y) * 8;
+    const int x = bx0 + tx, y = by0 + ty;
+    for (int i = ty * 32 + tx; i < 12 * 36; i += 256) {
+        const int lx = i % 36, ly = i / 36;
+        in_tile[ly][lx] = ld_r8u(input_tex, bx0 + lx - 2, by0 + ly - 2);
+    }
+    __syncthreads();
+    {
+        float acc = 0.0f;
+        for (int yy = 0; yy < 5; ++yy) for (int xx = 0; xx < 5; ++xx) acc += in_tile[ty + yy][tx + xx] * wt.w[yy * 5 + xx];
+        blur_s[ty][tx] = acc / wt.w_sum;
+        edge_s[ty][tx] = d5_edge(reprojection_tex, half_depth_tex, x, y);
+    }
+    __syncthreads();
+    if (x >= output_tex.w || y >= output_tex.h || y < kjb_rows.y0 || y >= kjb_rows.y1) return;
+    const float b0 = kjb_lerp(blur_s[ty][tx], blur_s[ty][tx ^ 2], 0.5f);
+    const float b1 = kjb_lerp(blur_s[ty ^ 2][tx], blur_s[ty ^ 2][tx ^ 2], 0.5f);
     float inv = kjb_lerp(b0, b1, 0.5f);
     inv = kjb_smoothstep(0.0f, 1.0f, inv);
-    const float e0 = kjb_max(d5_edge(reprojection_tex, half_depth_tex, x, y), d5_edge(reprojection_tex, half_depth_tex, x ^ 1, y));
-    const float e1 = kjb_max(d5_edge(reprojection_tex, half_depth_tex, x, y ^ 1), d5_edge(reprojection_tex, half_depth_tex, x ^ 1, y ^ 1));
+    const float e0 = kjb_max(edge_s[ty][tx], edge_s[ty][tx ^ 1]);
+    const float e1 = kjb_max(edge_s[ty ^ 1][tx], edge_s[ty ^ 1][tx ^ 1]);
     inv += kjb_max(e0, e1);
     inv = kjb_saturate(inv);
     const float4 reproj = ld_rgba16s(reprojection_tex, x * 2, y * 2);
@@ -286,7 +297,7 @@ KJB_KERNEL(256) k_rtdgi_validity_integrate(Globals g, Img input_tex, Img history
         history += ld_rg16f(history_tex, kjb_cvt_i32(reproj_px.x + off.x), kjb_cvt_i32(reproj_px.y + off.y)).x;
     }
     history /= 8.0f;
-    st_rg16f(output_tex, x, y, kjb_max(history * 0.75f, inv), ld_r8u(input_tex, x, y));
+    st_rg16f(output_tex, x, y, kjb_max(history * 0.75f, inv), in_tile[ty + 2][tx + 2]);
 }
 
 // ------------------------------------------------------------------ D6 restir_temporal.hlsl:83-422
@@ -800,10 +811,11 @@ int kjb_pass_rtdgi_validity_integrate(kjb_context* c, const kjb_rtdgi_validity_i
     const char* P = "validity integrate"; const uint32_t W = a->output_tex.width, H = a->output_tex.height;
     CHK(a->output_tex, KJB_FMT_RG16_FLOAT, "output_tex"); CHKE(a->input_tex, KJB_FMT_R8_UNORM, "input_tex", W, H); CHKE(a->history_tex, KJB_FMT_RG16_FLOAT, "history_tex", W, H);
     CHK(a->reprojection_tex, KJB_FMT_RGBA16_SNORM, "reprojection_tex"); CHKE(a->half_depth_tex, KJB_FMT_R32_FLOAT, "half_depth_tex", W, H);
-    Weights25v wt;
-    for (int yy = -2; yy <= 2; ++yy) for (int xx = -2; xx <= 2; ++xx) wt.w[(yy + 2) * 5 + (xx + 2)] = kjb_exp2(-0.1f * float(xx * xx + yy * yy));
+    Weights25v wt; wt.w_sum = 0.0f;
+    for (int yy = -2; yy <= 2; ++yy) for (int xx = -2; xx <= 2; ++xx) { const float w = kjb_exp2(-0.1f * float(xx * xx + yy * yy)); wt.w[(yy + 2) * 5 + (xx + 2)] = w; wt.w_sum += w; }
     KJB_ROWS(c, H);
-    KJB_LAUNCH(c, k_rtdgi_validity_integrate, KJB_GRID2D(W, H, 32, 8), c->g, img_ro(a->input_tex), img_ro(a->history_tex), img_ro(a->reprojection_tex), img_ro(a->half_depth_tex), img_rw(a->output_tex),
+    // block rows start at a multiple of 4 so that the (y^1, y^2) exchange partners share the block
+    KJB_LAUNCH_SYNC(c, k_rtdgi_validity_integrate, KJB_DIMS(dim3((W + 31) / 32, unsigned(kjb__rows.y1 - (kjb__rows.y0 & ~3) + 7) / 8, 1), dim3(32, 8, 1)), c->g, img_ro(a->input_tex), img_ro(a->history_tex), img_ro(a->reprojection_tex), img_ro(a->half_depth_tex), img_rw(a->output_tex),
                F4A(a->gbuffer_tex_size), wt);
     KJB_PASS_EPILOGUE(c, P);
 }

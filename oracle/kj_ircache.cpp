@@ -8,6 +8,11 @@ namespace {
 
 struct IrcacheTraceResult { float3 incident_radiance, direction, hit_pos; };
 
+// Slot 0 of the indirection table is never written (inclusive scan, ircache_compact_entries.hlsl:17) and keeps naming entry 0, which
+// is also slot 1 when alive.  On the reference's GPU the two copies are adjacent lanes of one wave running in lockstep — same reads,
+// same writes — so the entry is effectively processed once; a serial loop would process it twice.  Skip the stale duplicate.
+inline bool slot_is_stale_duplicate(const uint32_t* ind, uint alloc_count, uint slot) { return slot == 0 && alloc_count > 1 && ind[1] == ind[0]; }
+
 // ircache/ircache_trace_common.inc.hlsl:37-227 (MAX_PATH_LENGTH 1, USE_WORLD_RADIANCE_CACHE 0, IRCACHE_LOOKUP_PRECISE)
 IrcacheTraceResult ircache_trace(const kjb_context& ctx, const IrcacheBufs& b, const Img& sky_cube_tex, const Vertex& entry, SampleParams sample_params, uint life) {
     const Globals& g = ctx.g;
@@ -180,6 +185,7 @@ int kjb_pass_ircache_reset(kjb_context*, const kjb_ircache_reset_args* a) {   //
     const float4* irradiance = (const float4*)a->irradiance_buf.data; float4* aux = (float4*)a->aux_buf.data;
     const uint total_alloc_count = meta[IRCACHE_META_TRACING_ALLOC_COUNT];
     for (uint di = 0; di < total_alloc_count; ++di) {
+        if (slot_is_stale_duplicate(ind, total_alloc_count, di)) continue;
         const uint entry_idx = ind[di];
         const float4 v = irradiance[entry_idx * 3];
         if (v.x == 0.0f && v.y == 0.0f && v.z == 0.0f && v.w == 0.0f) for (uint i = 0; i < IRCACHE_AUX_STRIDE; ++i) aux[entry_idx * IRCACHE_AUX_STRIDE + i] = float4(0.0f);
@@ -192,6 +198,7 @@ int kjb_pass_ircache_trace_access(kjb_context* ctx, const kjb_ircache_trace_acce
     const float4* spatial = (const float4*)a->spatial_buf.data; float4* aux = (float4*)a->aux_buf.data;
     const uint alloc_count = meta[IRCACHE_META_TRACING_ALLOC_COUNT];
     for (uint di = 0; di < alloc_count * IRCACHE_OCTA_DIMS2; ++di) {
+        if (slot_is_stale_duplicate(ind, alloc_count, di / IRCACHE_OCTA_DIMS2)) continue;
         const uint entry_idx = ind[di / IRCACHE_OCTA_DIMS2], octa_idx = di % IRCACHE_OCTA_DIMS2;
         if (!is_ircache_entry_life_valid(life[entry_idx])) continue;
         const Vertex entry = unpack_vertex(spatial[entry_idx]);
@@ -212,6 +219,7 @@ int kjb_pass_ircache_validate(kjb_context* ctx, const kjb_ircache_trace_args* a)
     const uint alloc_count = b.meta[IRCACHE_META_TRACING_ALLOC_COUNT];
     const float ped = ctx->g.fc.pre_exposure_delta;
     for (uint di = 0; di < alloc_count * IRCACHE_VALIDATION_SAMPLES_PER_FRAME; ++di) {
+        if (slot_is_stale_duplicate(ind, alloc_count, di / 4)) continue;
         const uint entry_idx = ind[di / 4], sample_idx = di % 4;
         const uint life = b.life[entry_idx];
         const SampleParams sample_params = SampleParams::from_spf_entry_sample_frame(4, entry_idx, sample_idx, ctx->g.fc.frame_index);
@@ -242,6 +250,7 @@ int kjb_pass_ircache_trace(kjb_context* ctx, const kjb_ircache_trace_args* a) { 
     const uint alloc_count = b.meta[IRCACHE_META_TRACING_ALLOC_COUNT];
     const float ped = ctx->g.fc.pre_exposure_delta;
     for (uint di = 0; di < alloc_count * IRCACHE_SAMPLES_PER_FRAME; ++di) {
+        if (slot_is_stale_duplicate(ind, alloc_count, di / 4)) continue;
         const uint entry_idx = ind[di / 4], sample_idx = di % 4;
         const uint life = b.life[entry_idx];
         const float4 packed_entry = b.spatial[entry_idx];
@@ -278,6 +287,7 @@ int kjb_pass_ircache_sum(kjb_context* ctx, const kjb_ircache_sum_args* a) {   //
     const uint total_alloc_count = meta[IRCACHE_META_TRACING_ALLOC_COUNT];
     const float ped = ctx->g.fc.pre_exposure_delta;
     for (uint di = 0; di < total_alloc_count; ++di) {
+        if (slot_is_stale_duplicate(ind, total_alloc_count, di)) continue;
         const uint entry_idx = ind[di];
         float4 sh_rgb[3] = {float4(0.0f), float4(0.0f), float4(0.0f)};
         float valid_samples = 0;
