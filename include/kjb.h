@@ -377,6 +377,60 @@ typedef struct kjb_rtdgi_spatial_args {              /* "rtdgi spatial", spatial
 } kjb_rtdgi_spatial_args;
 int kjb_pass_rtdgi_spatial(kjb_context *ctx, const kjb_rtdgi_spatial_args *a);
 
+/* ------------------------------------------------------------------ rtr (renderers/rtr.rs; shaders under assets/shaders/rtr/)
+ * Ray-traced specular reflections.  Half-res candidates go into the rtdgi candidate images (rtr.rs:105-109): radiance RGBA16F,
+ * hit RGBA16F, normal RGBA8_SNORM.  Temporal images are RGBA16F (temporal_tex_desc, rtr.rs:87-90) unless stated. */
+typedef struct kjb_rtr_trace_args {                  /* "reflection trace", reflection.rgen.hlsl:19-36, rtr.rs:132-156 */
+    kjb_image gbuffer_tex, depth_tex;
+    /* blue-noise-sampler spp64 tables (rtr.rs:66-68; crate blue-noise-sampler, not part of kajiya's tree): i32[128*128*8],
+     * i32[128*128*8], i32[256*256].  All three NULL = the shader's own `blue_noise_for_pixel` alternative (reflection.rgen.hlsl:98-100). */
+    kjb_buffer ranking_tile_buf, scambling_tile_buf, sobol_buf;
+    kjb_image rtdgi_tex, sky_cube_tex;
+    kjb_ircache_bindings ircache;
+    kjb_image out0_tex, out1_tex, out2_tex, rng_out_tex;   /* rng: R32_UINT half-res */
+    float gbuffer_tex_size[4];
+    uint32_t reuse_rtdgi_rays;
+} kjb_rtr_trace_args;
+int kjb_pass_rtr_trace(kjb_context *ctx, const kjb_rtr_trace_args *a);
+
+typedef struct kjb_rtr_validate_args {               /* "reflection validate", reflection_validate.rgen.hlsl:20-35, rtr.rs:208-231 */
+    kjb_image gbuffer_tex, depth_tex, rtdgi_tex, sky_cube_tex, refl_restir_invalidity_tex;   /* invalidity: R8_UNORM half-res */
+    kjb_ircache_bindings ircache;
+    kjb_image ray_orig_history_tex, ray_history_tex, rng_history_tex, irradiance_history_tex, reservoir_history_tex;   /* ray_orig RGBA32F; reservoir RG32_UINT */
+    float gbuffer_tex_size[4];
+} kjb_rtr_validate_args;
+int kjb_pass_rtr_validate(kjb_context *ctx, const kjb_rtr_validate_args *a);
+
+typedef struct kjb_rtr_restir_temporal_args {        /* "rtr restir temporal", rtr_restir_temporal.hlsl:43-65, rtr.rs:234-261 */
+    kjb_image gbuffer_tex, half_view_normal_tex, depth_tex, candidate0_tex, candidate1_tex, candidate2_tex, irradiance_history_tex, ray_orig_history_tex,
+              ray_history_tex, rng_history_tex, reservoir_history_tex, reprojection_tex, hit_normal_history_tex;
+    kjb_image irradiance_out_tex, ray_orig_output_tex, ray_output_tex, rng_output_tex, hit_normal_output_tex, reservoir_out_tex;
+    float gbuffer_tex_size[4];
+} kjb_rtr_restir_temporal_args;
+int kjb_pass_rtr_restir_temporal(kjb_context *ctx, const kjb_rtr_restir_temporal_args *a);
+
+#define KJB_SPATIAL_RESOLVE_OFFSET_COUNT (16 * 4 * 8)
+typedef struct kjb_rtr_resolve_args {                /* "reflection resolve", resolve.hlsl:16-36, rtr.rs:290-316 */
+    kjb_image gbuffer_tex, depth_tex, hit0_tex, hit1_tex, hit2_tex, history_tex, reprojection_tex, half_view_normal_tex, half_depth_tex, ray_len_history_tex,
+              restir_irradiance_tex, restir_ray_tex, restir_reservoir_tex, restir_ray_orig_tex, restir_hit_normal_tex;
+    kjb_image output_tex, ray_len_output_tex;        /* R11G11B10_UFLOAT full-res; RG16F full-res */
+    float output_tex_size[4];
+    const int32_t *spatial_resolve_offsets;          /* int4[512] pushed by the host (rtr.rs:402-915); not read by the shader's active path, may be NULL */
+} kjb_rtr_resolve_args;
+int kjb_pass_rtr_resolve(kjb_context *ctx, const kjb_rtr_resolve_args *a);
+
+typedef struct kjb_rtr_temporal_args {               /* "reflection temporal", temporal_filter.hlsl:23-33, rtr.rs:372-385 */
+    kjb_image input_tex, history_tex, depth_tex, ray_len_tex, reprojection_tex, refl_restir_invalidity_tex, gbuffer_tex, output_tex;
+    float output_tex_size[4];
+} kjb_rtr_temporal_args;
+int kjb_pass_rtr_temporal(kjb_context *ctx, const kjb_rtr_temporal_args *a);
+
+typedef struct kjb_rtr_cleanup_args {                /* "reflection cleanup", spatial_cleanup.hlsl:9-15, rtr.rs:387-396 */
+    kjb_image input_tex, depth_tex, geometric_normal_tex, output_tex;
+    const int32_t *spatial_resolve_offsets;          /* int4[512] HOST pointer (rtr.rs:402-915); copied inside the call */
+} kjb_rtr_cleanup_args;
+int kjb_pass_rtr_cleanup(kjb_context *ctx, const kjb_rtr_cleanup_args *a);
+
 /* ------------------------------------------------------------------ taa (renderers/taa.rs:41-185; shaders under assets/shaders/taa/) */
 typedef struct kjb_taa_reproject_args {              /* "reproject taa", reproject_history.hlsl:8-16, taa.rs:66-79 */
     kjb_image history_tex, reprojection_tex, depth_tex, output_tex, closest_velocity_output;

@@ -75,6 +75,8 @@ int  kjb_world_add_mesh(kjb_world *w, const kjb_mesh_desc *mesh, uint32_t *out_m
 int  kjb_world_add_instance(kjb_world *w, uint32_t mesh_handle, const float transform[12], uint32_t *out_instance_handle);
 /* the 256x256 RGBA8 blue-noise LUT (bindless slot 1; assets/images/bluenoise/256_256/LDR_RGBA_0.png in the reference) */
 int  kjb_world_set_blue_noise(kjb_world *w, const uint8_t *rgba8_256x256);
+/* SPATIAL_RESOLVE_OFFSETS (rtr.rs:402-915): the int4[512] constant table the reflection passes receive; required when enable_rtr */
+int  kjb_world_set_spatial_resolve_offsets(kjb_world *w, const int32_t *int4x512);
 /* one frame of prepare_render_graph_standard's hot-path passes; enqueues, does not sync (unless host_result is set) */
 int  kjb_world_render_frame(kjb_world *w, const kjb_world_frame *frame);
 /* one frame of prepare_render_graph_reference (world_render_passes.rs:294-330): the path tracer accumulating in place */

@@ -128,11 +128,13 @@ KJB_DEV float eval_sh_geometrics(float4 sh, float3 normal) {   // lookup.hlsl:19
 // IrcacheLookupParams::lookup (lookup.hlsl:76-311) with the maybe-allocating lookup it wraps (:19-74,:120-190).
 // PRECISE = IRCACHE_LOOKUP_PRECISE: sum the per-direction reservoirs instead of evaluating the SH (the cache's own tracing passes).
 template <bool PRECISE>
-KJB_DEV float3 ircache_lookup(const Globals& g, const IrcacheBufs& b, float3 query_from_ws, float3 pt_ws, float3 normal_ws, uint32_t query_rank, uint32_t& rng) {
+KJB_DEV float3 ircache_lookup(const Globals& g, const IrcacheBufs& b, float3 query_from_ws, float3 pt_ws, float3 normal_ws, uint32_t query_rank, uint32_t& rng, bool stochastic_interpolation = false) {
     if (!b.bound()) return f3(0.0f);
     const kjb_frame_constants& fc = g.fc;
     bool allocated_by_us = false, just_allocated = false;
-    const IrcacheCoord rc = ws_pos_to_ircache_coord(fc, pt_ws, normal_ws, f3(0.0f));   // stochastic interpolation is off on this path
+    // lookup.hlsl:80-86: the three rng draws sit in the arguments of select(), i.e. they happen whether or not interpolation is on
+    float3 jr; jr.x = rand01(rng); jr.y = rand01(rng); jr.z = rand01(rng);
+    const IrcacheCoord rc = ws_pos_to_ircache_coord(fc, pt_ws, normal_ws, stochastic_interpolation ? jr - 0.5f : f3(0.0f));
     const uint32_t cell_idx = ircache_cell_idx(rc);
     {
         const int32_t* so = fc.ircache_cascades[rc.cascade].voxels_scrolled_this_frame;

@@ -541,7 +541,8 @@ KJB_KERNEL(256) k_rtdgi_restir_spatial(Globals g, Img reservoir_input_tex, Img h
 // ------------------------------------------------------------------ D9 restir_resolve.hlsl:42-205
 KJB_DEV float ggx_ndf_unnorm(float a2, float cos_theta) { const float ds = cos_theta * cos_theta * (a2 - 1.0f) + 1.0f; return a2 / (ds * ds); }
 struct ResolveImgs { Img radiance_tex, reservoir_input_tex, gbuffer_tex, depth_tex, half_view_normal_tex, half_depth_tex, ssao_tex, candidate_radiance_tex, candidate_hit_tex, temporal_reservoir_packed_tex; };
-KJB_KERNEL(256) k_rtdgi_restir_resolve(Globals g, ResolveImgs t, ImgW irradiance_output_tex, float4 gts, float4 ots, Rows kjb_rows) {
+struct PowTable4 { float v[4]; };   // v[i] = pow(float(i), 0.666), host-evaluated
+KJB_KERNEL(256) k_rtdgi_restir_resolve(Globals g, ResolveImgs t, ImgW irradiance_output_tex, float4 gts, float4 ots, PowTable4 pw, Rows kjb_rows) {
     KJB_PX; if (x >= irradiance_output_tex.w || y >= irradiance_output_tex.h) return;
     const kjb_view_constants& vc = g.fc.view_constants;
     const int2 hso = halfres_subsample_offset(g.fc.frame_index);
@@ -563,14 +564,19 @@ KJB_KERNEL(256) k_rtdgi_restir_resolve(Globals g, ResolveImgs t, ImgW irradiance
     const float NEAR_FIELD_FADE_OUT_START = NEAR_FIELD_FADE_OUT_END * 0.5f;
     const float near_field_influence = center_ssao;
 
+    // both tap loops use the same four angles: evaluate their sin/cos once
+    float tap_sn[4], tap_cs[4];
+    for (uint32_t i = 0; i < 4u; ++i) {
+        const float ang = (float(i) + blue.x) * KJB_GOLDEN_ANGLE + (float(px_idx_in_quad) / 4.0f) * KJB_TAU_F;
+        kjb_sincos(ang, &tap_sn[i], &tap_cs[i]);
+    }
     float3 total_irradiance = f3(0.0f);
     bool sharpen_gi_kernel = false;
     {
         float w_sum = 0; float3 weighted_irradiance = f3(0.0f);
         for (uint32_t i = 0; i < 4u; ++i) {
-            const float ang = (float(i) + blue.x) * KJB_GOLDEN_ANGLE + (float(px_idx_in_quad) / 4.0f) * KJB_TAU_F;
-            const float radius = kjb_pow(float(i), 0.666f) * 1.0f + 0.4f;
-            float sn, cs; kjb_sincos(ang, &sn, &cs);
+            const float radius = pw.v[i] * 1.0f + 0.4f;
+            const float sn = tap_sn[i], cs = tap_cs[i];
             const float2 off = f2(cs, sn) * radius;
             const int rx = kjb_cvt_i32(kjb_floor(float(x) * 0.5f + off.x)), ry = kjb_cvt_i32(kjb_floor(float(y) * 0.5f + off.y));
             const float2 rpx_uv = get_uv(rx * 2 + hso.x, ry * 2 + hso.y, s4);
@@ -597,9 +603,8 @@ KJB_KERNEL(256) k_rtdgi_restir_resolve(Globals g, ResolveImgs t, ImgW irradiance
         float w_sum = 0; float3 weighted_irradiance = f3(0.0f);
         const float kernel_scale = sharpen_gi_kernel ? 0.5f : 1.0f;
         for (uint32_t i = 0; i < 4u; ++i) {
-            const float ang = (float(i) + blue.x) * KJB_GOLDEN_ANGLE + (float(px_idx_in_quad) / 4.0f) * KJB_TAU_F;
-            const float radius = kjb_pow(float(i), 0.666f) * 1.0f * kernel_scale + 0.4f * kernel_scale;
-            float sn, cs; kjb_sincos(ang, &sn, &cs);
+            const float radius = pw.v[i] * 1.0f * kernel_scale + 0.4f * kernel_scale;
+            const float sn = tap_sn[i], cs = tap_cs[i];
             const float2 off = f2(cs, sn) * radius;
             const int rx = kjb_cvt_i32(kjb_floor(float(x) * 0.5f + off.x)), ry = kjb_cvt_i32(kjb_floor(float(y) * 0.5f + off.y));
             const Reservoir r = Reservoir::from_raw(ld_rg32u(t.reservoir_input_tex, rx, ry));
@@ -702,7 +707,8 @@ KJB_KERNEL(512) k_rtdgi_temporal(Globals g, Img input_tex, Img history_tex, Img 
 // ------------------------------------------------------------------ D11 spatial_filter.hlsl:33-101
 KJB_DEV float3 crunch(float3 v) { return v * kjb_rcp(max3(v.x, v.y, v.z) + 1.0f); }
 KJB_DEV float3 uncrunch(float3 v) { return v * kjb_rcp(1.0f - max3(v.x, v.y, v.z)); }
-KJB_KERNEL(256) k_rtdgi_spatial(Globals g, Img input_tex, Img depth_tex, Img ssao_tex, Img geometric_normal_tex, ImgW output_tex, Rows kjb_rows) {
+struct PowTable8 { float v[8]; };   // v[i] = pow(float(i), 0.666): compile-time constants in the shader ("must be constant, so the pow can be const-folded"), host-evaluated here
+KJB_KERNEL(256) k_rtdgi_spatial(Globals g, Img input_tex, Img depth_tex, Img ssao_tex, Img geometric_normal_tex, ImgW output_tex, PowTable8 pw, Rows kjb_rows) {
     KJB_PX; if (x >= output_tex.w || y >= output_tex.h) return;
     const float4 cin = ld_rgba16f(input_tex, x, y);
     const float center_validity = cin.w;
@@ -716,15 +722,15 @@ KJB_KERNEL(256) k_rtdgi_spatial(Globals g, Img input_tex, Img depth_tex, Img ssa
     uint32_t sample_count = kjb_cvt_u32(kjb_exp2(4.0f * square(1.0f - center_validity)));
     sample_count = sample_count < 2u ? 2u : (sample_count > 8u ? 8u : sample_count);
     float4 sum = f4(crunch(center_value), 1);
-    const float RADIUS_SAMPLE_MULT = MAX_RADIUS_PX / kjb_pow(float(8 - 1), 0.666f);
-    for (uint32_t i = 1; i < 8u; ++i) {
+    const float RADIUS_SAMPLE_MULT = MAX_RADIUS_PX / pw.v[7];
+    for (uint32_t i = 1; i < sample_count; ++i) {   // the shader walks all 8 taps and masks i >= sample_count: no side effects, skip them
         const float ang = (float(i) + ang_off) * KJB_GOLDEN_ANGLE;
-        const float radius = kjb_pow(float(i), 0.666f) * RADIUS_SAMPLE_MULT;
+        const float radius = pw.v[i] * RADIUS_SAMPLE_MULT;
         float sn, cs; kjb_sincos(ang, &sn, &cs);
         const float2 off = f2(cs, sn) * radius;
         const int sx = kjb_cvt_i32(float(x) + off.x), sy = kjb_cvt_i32(float(y) + off.y);
         const float sample_depth = ld_r32f(depth_tex, sx, sy);
-        if (sample_depth != 0 && i < sample_count) {
+        if (sample_depth != 0) {
             const float3 sample_val = xyz(ld_rgba16f(input_tex, sx, sy));
             const float sample_ssao = ld_r8u(ssao_tex, sx, sy);
             float wt = 1;
@@ -867,7 +873,8 @@ int kjb_pass_rtdgi_restir_resolve(kjb_context* c, const kjb_rtdgi_restir_resolve
     t.half_view_normal_tex = img_ro(a->half_view_normal_tex); t.half_depth_tex = img_ro(a->half_depth_tex); t.ssao_tex = img_ro(a->ssao_tex); t.candidate_radiance_tex = img_ro(a->candidate_radiance_tex);
     t.candidate_hit_tex = img_ro(a->candidate_hit_tex); t.temporal_reservoir_packed_tex = img_ro(a->temporal_reservoir_packed_tex);
     KJB_ROWS(c, H);
-    KJB_LAUNCH(c, k_rtdgi_restir_resolve, KJB_GRID2D(W, H, 32, 8), c->g, t, img_rw(a->irradiance_output_tex), F4A(a->gbuffer_tex_size), F4A(a->output_tex_size));
+    PowTable4 pw; for (int i = 0; i < 4; ++i) pw.v[i] = kjb_pow(float(i), 0.666f);
+    KJB_LAUNCH(c, k_rtdgi_restir_resolve, KJB_GRID2D(W, H, 32, 8), c->g, t, img_rw(a->irradiance_output_tex), F4A(a->gbuffer_tex_size), F4A(a->output_tex_size), pw);
     KJB_PASS_EPILOGUE(c, P);
 }
 int kjb_pass_rtdgi_temporal(kjb_context* c, const kjb_rtdgi_temporal_args* a) {
@@ -888,7 +895,8 @@ int kjb_pass_rtdgi_spatial(kjb_context* c, const kjb_rtdgi_spatial_args* a) {
     CHK(a->output_tex, KJB_FMT_RGBA16_FLOAT, "output_tex"); CHKE(a->input_tex, KJB_FMT_RGBA16_FLOAT, "input_tex", W, H); CHKE(a->depth_tex, KJB_FMT_R32_FLOAT, "depth_tex", W, H);
     CHKE(a->ssao_tex, KJB_FMT_R8_UNORM, "ssao_tex", W, H); CHKE(a->geometric_normal_tex, KJB_FMT_A2R10G10B10_UNORM, "geometric_normal_tex", W, H);
     KJB_ROWS(c, H);
-    KJB_LAUNCH(c, k_rtdgi_spatial, KJB_GRID2D(W, H, 32, 8), c->g, img_ro(a->input_tex), img_ro(a->depth_tex), img_ro(a->ssao_tex), img_ro(a->geometric_normal_tex), img_rw(a->output_tex));
+    PowTable8 pw; for (int i = 0; i < 8; ++i) pw.v[i] = kjb_pow(float(i), 0.666f);
+    KJB_LAUNCH(c, k_rtdgi_spatial, KJB_GRID2D(W, H, 32, 8), c->g, img_ro(a->input_tex), img_ro(a->depth_tex), img_ro(a->ssao_tex), img_ro(a->geometric_normal_tex), img_rw(a->output_tex), pw);
     KJB_PASS_EPILOGUE(c, P);
 }
 

@@ -93,11 +93,14 @@ inline float eval_sh_geometrics(float4 sh, float3 normal) {   // lookup.hlsl:197
 }
 
 // IrcacheLookupParams::lookup (lookup.hlsl:76-311).  `precise` = IRCACHE_LOOKUP_PRECISE (used by the cache's own tracing passes).
-inline float3 ircache_lookup(const Globals& g, const IrcacheBufs& b, float3 query_from_ws, float3 pt_ws, float3 normal_ws, uint query_rank, uint& rng, bool precise) {
+inline float3 ircache_lookup(const Globals& g, const IrcacheBufs& b, float3 query_from_ws, float3 pt_ws, float3 normal_ws, uint query_rank, uint& rng, bool precise, bool stochastic_interpolation = false) {
     if (!b.bound()) return float3(0.0f);
     const kjb_frame_constants& fc = g.fc;
     bool allocated_by_us = false, just_allocated = false;
-    const float3 jitter(0.0f);   // stochastic_interpolation is never enabled by the callers on this path
+    // lookup.hlsl:80-86: `select(stochastic_interpolation, float3(rand, rand, rand) - 0.5, 0)` — select() is a function, its arguments are
+    // evaluated eagerly, so the three hash1_mut(rng) draws happen whether or not interpolation is on
+    float3 jr; jr.x = uint_to_u01_float(hash1_mut(rng)); jr.y = uint_to_u01_float(hash1_mut(rng)); jr.z = uint_to_u01_float(hash1_mut(rng));
+    const float3 jitter = stochastic_interpolation ? jr - 0.5f : float3(0.0f);
     {
         const IrcacheCoord rcoord = ws_pos_to_ircache_coord(fc, pt_ws, normal_ws, jitter);
         const int* so = fc.ircache_cascades[rcoord.cascade].voxels_scrolled_this_frame;

@@ -1,0 +1,26 @@
+"""Aggregate an `ncu --page source --csv --print-source cuda,sass` dump by source line (executed warp instructions + stall samples).
+   python tools/ncu_hot_lines.py dump.csv [top]"""
+import csv, sys, collections
+rows = list(csv.reader(open(sys.argv[1])))
+top = int(sys.argv[2]) if len(sys.argv) > 2 else 25
+cur_file = None; hdr = None
+agg = collections.Counter(); samples = collections.Counter(); text = {}; opc = collections.Counter()
+for r in rows:
+    if not r: continue
+    if r[0] == "File Path": cur_file = r[1]; continue
+    if r[0] == "Line No": hdr = {h: i for i, h in enumerate(r)}; continue
+    if r[0] == "Function Name" or hdr is None: continue
+    try:
+        line = int(r[0])
+    except ValueError:
+        continue
+    ie = r[hdr["Instructions Executed"]]
+    if not ie: continue
+    key = (cur_file.split("/")[-1], line)
+    agg[key] += int(float(ie)); samples[key] += int(float(r[hdr["# Samples"]] or 0))
+    # first "Source" column = CUDA-C text for this row kind, second = SASS
+    src_cols = [i for i, h in enumerate(rows[2]) if h == "Source"] if False else None
+tot = sum(agg.values())
+print("total warp instructions (rows with both views are double counted consistently):", tot)
+for (f, l), n in agg.most_common(top):
+    print(f"{n:>12} {100.0 * n / tot:5.1f}%  samples {samples[(f, l)]:>6}  {f}:{l}")
