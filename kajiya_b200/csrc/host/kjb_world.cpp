@@ -109,6 +109,11 @@ struct kjb_world {
     PingPong temporal_radiance_tex{"rtdgi.radiance"}, temporal_ray_orig_tex{"rtdgi.ray_orig"}, temporal_ray_tex{"rtdgi.ray"},
         temporal_reservoir_tex{"rtdgi.reservoir"}, temporal_candidate_tex{"rtdgi.candidate"}, temporal_invalidity_tex{"rtdgi.invalidity"},
         temporal2_tex{"rtdgi.temporal2"}, temporal2_variance_tex{"rtdgi.temporal2_var"}, temporal_hit_normal_tex{"rtdgi.hit_normal"};
+    // RtrRenderer (rtr.rs:18-34, :55-72)
+    PingPong rtr_temporal_tex{"rtr.temporal"}, rtr_ray_len_tex{"rtr.ray_len"}, rtr_temporal_irradiance_tex{"rtr.irradiance"}, rtr_temporal_ray_orig_tex{"rtr.ray_orig"},
+        rtr_temporal_ray_tex{"rtr.ray"}, rtr_temporal_reservoir_tex{"rtr.reservoir"}, rtr_temporal_rng_tex{"rtr.rng"}, rtr_temporal_hit_normal_tex{"rtr.hit_normal"};
+    bool rtr_reuse_rtdgi_rays = true;
+    std::vector<int32_t> spatial_resolve_offsets;
     PingPong taa_temporal_tex{"taa"}, taa_temporal_velocity_tex{"taa.velocity"}, taa_temporal_smooth_var_tex{"taa.smooth_var"};   // taa.rs:19-27
     uint32_t OW = 0, OH = 0;   // temporal_upscale_extent
 
@@ -200,7 +205,7 @@ int kjb_world_create(kjb_context* ctx, const kjb_world_desc* desc, kjb_world** o
     w->W = desc->render_width; w->H = desc->render_height;
     w->HW = (w->W + 1) / 2; w->HH = (w->H + 1) / 2;   // ImageDesc::half_res = div_up (image.rs:140-142)
     w->OW = desc->temporal_upscale_width ? desc->temporal_upscale_width : w->W; w->OH = desc->temporal_upscale_height ? desc->temporal_upscale_height : w->H;
-    if (desc->tile_count > 1 && desc->enable_ircache) { delete w; return 1; }   // the cache is one global racy structure: it does not shard by rows
+    if (desc->tile_count > 1 && (desc->enable_ircache || desc->enable_rtr)) { delete w; return 1; }   // the cache is one global racy structure (does not shard by rows); rtr tiles: not yet
     if (desc->tile_count > 1) {
         if (w->OW != w->W || w->OH != w->H || (w->H & 1)) { delete w; return 1; }   // tiles + temporal upscaling / odd heights: not supported
         w->tiled = true; w->trank = desc->tile_rank; w->tcount = desc->tile_count;
@@ -295,6 +300,11 @@ int kjb_world_set_blue_noise(kjb_world* w, const uint8_t* rgba) {
 }
 
 uint32_t kjb_world_frame_index(kjb_world* w) { return w->frame_idx; }
+int kjb_world_set_spatial_resolve_offsets(kjb_world* w, const int32_t* t) {
+    if (!t) return 1;
+    w->spatial_resolve_offsets.assign(t, t + 4 * KJB_SPATIAL_RESOLVE_OFFSET_COUNT);
+    return 0;
+}
 int kjb_world_get_image(kjb_world* w, const char* name, kjb_image* out) {
     auto it = w->images.find(name); if (it == w->images.end()) return 1; *out = it->second; return 0;
 }
@@ -713,6 +723,72 @@ static void rtdgi_render(kjb_world* w, kjb_image& reprojected_history_tex, kjb_i
 }
 
 // ---------------------------------------------------------------- TaaRenderer::render (taa.rs:41-185)
+// ---------------------------------------------------------------- RtrRenderer::trace + TracedRtr::filter_temporal (rtr.rs:90-399)
+// `lighting.render_specular` (world_render_passes.rs:190-201), which adds triangle-light specular into the resolved image before the
+// temporal filter, belongs to renderers/lighting.rs and is outside the hot path.
+static kjb_image* rtr_render(kjb_world* w, kjb_image& gbuffer, kjb_image& depth, kjb_image& geometric_normal, kjb_image& reprojection_map, kjb_image& sky_cube,
+                             kjb_image& rtdgi_irradiance, const kjb_ircache_bindings& ircache) {
+    kjb_context* ctx = w->ctx;
+    const uint32_t HW = w->HW, HH = w->HH, W = w->W, H = w->H;
+    float gbuffer_size[4]; size4(gbuffer_size, gbuffer);
+    if (w->spatial_resolve_offsets.empty()) { w->err = 1; return nullptr; }
+    // RtdgiCandidates (rtr.rs:105-109): the diffuse candidate images double as the reflection candidates
+    kjb_image& refl0_tex = w->img("rtdgi.candidate_radiance", HW, HH, KJB_FMT_RGBA16_FLOAT);
+    kjb_image& refl1_tex = w->img("rtdgi.candidate_hit", HW, HH, KJB_FMT_RGBA16_FLOAT);
+    kjb_image& refl2_tex = w->img("rtdgi.candidate_normal", HW, HH, KJB_FMT_RGBA8_SNORM);
+    kjb_image *rng_output_tex, *rng_history_tex; w->get_output_and_history(w->rtr_temporal_rng_tex, HW, HH, KJB_FMT_R32_UINT, rng_output_tex, rng_history_tex);
+    {
+        kjb_rtr_trace_args a{}; a.gbuffer_tex = gbuffer; a.depth_tex = depth; a.rtdgi_tex = rtdgi_irradiance; a.sky_cube_tex = sky_cube; a.ircache = ircache;
+        a.out0_tex = refl0_tex; a.out1_tex = refl1_tex; a.out2_tex = refl2_tex; a.rng_out_tex = *rng_output_tex; memcpy(a.gbuffer_tex_size, gbuffer_size, 16);
+        a.reuse_rtdgi_rays = w->rtr_reuse_rtdgi_rays ? 1u : 0u;
+        RUN("reflection trace", kjb_pass_rtr_trace(ctx, &a));
+    }
+    kjb_image& half_view_normal_tex = w->img("half_view_normal", HW, HH, KJB_FMT_RGBA8_SNORM);   // memoised by rtdgi (mod.rs:54-70)
+    kjb_image& half_depth_tex = w->img("half_depth", HW, HH, KJB_FMT_R32_FLOAT);
+    kjb_image *ray_orig_output_tex, *ray_orig_history_tex; w->get_output_and_history(w->rtr_temporal_ray_orig_tex, HW, HH, KJB_FMT_RGBA32_FLOAT, ray_orig_output_tex, ray_orig_history_tex);
+    kjb_image& refl_restir_invalidity_tex = w->img("rtr.restir_invalidity", HW, HH, KJB_FMT_R8_UNORM);
+    kjb_image *hit_normal_output_tex, *hit_normal_history_tex; w->get_output_and_history(w->rtr_temporal_hit_normal_tex, HW, HH, KJB_FMT_RGBA16_FLOAT, hit_normal_output_tex, hit_normal_history_tex);
+    kjb_image *irradiance_output_tex, *irradiance_history_tex; w->get_output_and_history(w->rtr_temporal_irradiance_tex, HW, HH, KJB_FMT_RGBA16_FLOAT, irradiance_output_tex, irradiance_history_tex);
+    kjb_image *reservoir_output_tex, *reservoir_history_tex; w->get_output_and_history(w->rtr_temporal_reservoir_tex, HW, HH, KJB_FMT_RG32_UINT, reservoir_output_tex, reservoir_history_tex);
+    kjb_image *ray_output_tex, *ray_history_tex; w->get_output_and_history(w->rtr_temporal_ray_tex, HW, HH, KJB_FMT_RGBA16_FLOAT, ray_output_tex, ray_history_tex);
+    {
+        kjb_rtr_validate_args a{}; a.gbuffer_tex = gbuffer; a.depth_tex = depth; a.rtdgi_tex = rtdgi_irradiance; a.sky_cube_tex = sky_cube; a.refl_restir_invalidity_tex = refl_restir_invalidity_tex;
+        a.ircache = ircache; a.ray_orig_history_tex = *ray_orig_history_tex; a.ray_history_tex = *ray_history_tex; a.rng_history_tex = *rng_history_tex;
+        a.irradiance_history_tex = *irradiance_history_tex; a.reservoir_history_tex = *reservoir_history_tex; memcpy(a.gbuffer_tex_size, gbuffer_size, 16);
+        RUN("reflection validate", kjb_pass_rtr_validate(ctx, &a));
+    }
+    {
+        kjb_rtr_restir_temporal_args a{}; a.gbuffer_tex = gbuffer; a.half_view_normal_tex = half_view_normal_tex; a.depth_tex = depth; a.candidate0_tex = refl0_tex; a.candidate1_tex = refl1_tex;
+        a.candidate2_tex = refl2_tex; a.irradiance_history_tex = *irradiance_history_tex; a.ray_orig_history_tex = *ray_orig_history_tex; a.ray_history_tex = *ray_history_tex;
+        a.rng_history_tex = *rng_history_tex; a.reservoir_history_tex = *reservoir_history_tex; a.reprojection_tex = reprojection_map; a.hit_normal_history_tex = *hit_normal_history_tex;
+        a.irradiance_out_tex = *irradiance_output_tex; a.ray_orig_output_tex = *ray_orig_output_tex; a.ray_output_tex = *ray_output_tex; a.rng_output_tex = *rng_output_tex;
+        a.hit_normal_output_tex = *hit_normal_output_tex; a.reservoir_out_tex = *reservoir_output_tex; memcpy(a.gbuffer_tex_size, gbuffer_size, 16);
+        RUN("rtr restir temporal", kjb_pass_rtr_restir_temporal(ctx, &a));
+    }
+    kjb_image& resolved_tex = w->img("rtr.resolved", W, H, KJB_FMT_R11G11B10_UFLOAT);
+    kjb_image *temporal_output_tex, *history_tex; w->get_output_and_history(w->rtr_temporal_tex, W, H, KJB_FMT_RGBA16_FLOAT, temporal_output_tex, history_tex);
+    kjb_image *ray_len_output_tex, *ray_len_history_tex; w->get_output_and_history(w->rtr_ray_len_tex, W, H, KJB_FMT_RG16_FLOAT, ray_len_output_tex, ray_len_history_tex);
+    {
+        kjb_rtr_resolve_args a{}; a.gbuffer_tex = gbuffer; a.depth_tex = depth; a.hit0_tex = refl0_tex; a.hit1_tex = refl1_tex; a.hit2_tex = refl2_tex; a.history_tex = *history_tex;
+        a.reprojection_tex = reprojection_map; a.half_view_normal_tex = half_view_normal_tex; a.half_depth_tex = half_depth_tex; a.ray_len_history_tex = *ray_len_history_tex;
+        a.restir_irradiance_tex = *irradiance_output_tex; a.restir_ray_tex = *ray_output_tex; a.restir_reservoir_tex = *reservoir_output_tex; a.restir_ray_orig_tex = *ray_orig_output_tex;
+        a.restir_hit_normal_tex = *hit_normal_output_tex; a.output_tex = resolved_tex; a.ray_len_output_tex = *ray_len_output_tex; size4(a.output_tex_size, resolved_tex);
+        a.spatial_resolve_offsets = w->spatial_resolve_offsets.data();
+        RUN("reflection resolve", kjb_pass_rtr_resolve(ctx, &a));
+    }
+    {   // filter_temporal (rtr.rs:366-398)
+        kjb_rtr_temporal_args a{}; a.input_tex = resolved_tex; a.history_tex = *history_tex; a.depth_tex = depth; a.ray_len_tex = *ray_len_output_tex; a.reprojection_tex = reprojection_map;
+        a.refl_restir_invalidity_tex = refl_restir_invalidity_tex; a.gbuffer_tex = gbuffer; a.output_tex = *temporal_output_tex; size4(a.output_tex_size, *temporal_output_tex);
+        RUN("reflection temporal", kjb_pass_rtr_temporal(ctx, &a));
+    }
+    {
+        kjb_rtr_cleanup_args a{}; a.input_tex = *temporal_output_tex; a.depth_tex = depth; a.geometric_normal_tex = geometric_normal; a.output_tex = resolved_tex;
+        a.spatial_resolve_offsets = w->spatial_resolve_offsets.data();
+        RUN("reflection cleanup", kjb_pass_rtr_cleanup(ctx, &a));
+    }
+    return &resolved_tex;
+}
+
 static kjb_image* taa_render(kjb_world* w, kjb_image& input_tex, kjb_image& reprojection_map, kjb_image& depth_tex) {
     kjb_context* ctx = w->ctx;
     const uint32_t OW = w->OW, OH = w->OH, IW = input_tex.width, IH = input_tex.height;
@@ -824,6 +900,12 @@ int kjb_world_render_frame(kjb_world* w, const kjb_world_frame* f) {
     if (w->desc.enable_ircache) ircache_sum_up_irradiance(w, ircache_state);   // world_render_passes.rs:138-140
     // rtdgi.render (world_render_passes.rs:146-160): diffuse rays use the convolved sky cube
     rtdgi_render(w, reprojected_history_tex, *temporal_output_tex, gbuffer, depth, geometric_normal, reprojection_map, convolved_sky_cube, ssao_tex, ircache_state.bindings());
+
+    // rtr.trace + filter_temporal (world_render_passes.rs:171-205): reflection rays use the full sky cube
+    if (w->desc.enable_rtr) {
+        kjb_image gi{};
+        if (kjb_world_get_image(w, "rtdgi.spatial_filtered", &gi) == 0) rtr_render(w, gbuffer, depth, geometric_normal, reprojection_map, sky_cube, gi, ircache_state.bindings());
+    }
 
     // taa.render (world_render_passes.rs:253-263).  light_gbuffer (the composite that normally feeds TAA) is outside the hot
     // path: TAA consumes the GI result directly.

@@ -333,6 +333,33 @@ KJB_DEV void st_rgba16s(const ImgW& i, int x, int y, float4 v) {
 KJB_DEV void st_a2r10g10b10(const ImgW& i, int x, int y, float3 v) {
     if (inb(i, x, y)) st_raw<uint32_t>(i, x, y, (enc_unorm(v.x, 1023.0f) << 20) | (enc_unorm(v.y, 1023.0f) << 10) | enc_unorm(v.z, 1023.0f));
 }
+// B10G11R11_UFLOAT: truncating float->ufloat conversion ("GPU will convert ... by trimming", pack_unpack.hlsl:166-177)
+KJB_DEV uint32_t f32_to_uf(float v, int mant_bits) {
+    if (!(v > 0.0f)) return 0u;
+    const uint32_t u = kjb_f2u(v);
+    const int e = int(u >> 23) - 127 + 15;
+    const uint32_t m = (u & 0x7fffffu) >> (23 - mant_bits);
+    if (e >= 31) return (30u << mant_bits) | ((1u << mant_bits) - 1u);
+    if (e <= 0) {
+        if (e < -mant_bits) return 0u;
+        return ((u & 0x7fffffu) | 0x800000u) >> (23 - mant_bits + 1 - e);
+    }
+    return (uint32_t(e) << mant_bits) | m;
+}
+KJB_DEV float uf_to_f32(uint32_t v, int mant_bits) {
+    const uint32_t e = v >> mant_bits, m = v & ((1u << mant_bits) - 1u);
+    if (e == 0) return float(m) * kjb_exp2(float(-14 - mant_bits));
+    if (e == 31) return kjb_u2f(0x7f800000u);
+    return kjb_u2f(((e + 112u) << 23) | (m << (23 - mant_bits)));
+}
+KJB_DEV float3 ld_r11g11b10(const Img& i, int x, int y) {
+    if (!inb(i, x, y)) return f3(0.0f);
+    const uint32_t v = ld_raw<uint32_t>(i, x, y);
+    return f3(uf_to_f32(v & 2047u, 6), uf_to_f32((v >> 11) & 2047u, 6), uf_to_f32(v >> 22, 5));
+}
+KJB_DEV void st_r11g11b10(const ImgW& i, int x, int y, float3 c) { if (inb(i, x, y)) st_raw<uint32_t>(i, x, y, f32_to_uf(c.x, 6) | (f32_to_uf(c.y, 6) << 11) | (f32_to_uf(c.z, 5) << 22)); }
+KJB_DEV uint32_t ld_r32u(const Img& i, int x, int y) { return inb(i, x, y) ? ld_raw<uint32_t>(i, x, y) : 0u; }
+KJB_DEV void st_r32u(const ImgW& i, int x, int y, uint32_t v) { if (inb(i, x, y)) st_raw<uint32_t>(i, x, y, v); }
 KJB_DEV int clampi(int v, int n) { return v < 0 ? 0 : (v >= n ? n - 1 : v); }
 // SampleLevel(sampler_nnc): nearest, clamp to edge
 KJB_DEV int2 nearest_clamp_px(const Img& i, float2 uv) {
@@ -589,8 +616,10 @@ KJB_DEV BrdfSample specular_sample(const SpecularBrdf& b, float3 wo, float2 uran
     res.value = fresnel * g * ggx_ndf(a2, h.z) / (4 * wo.z * wi.z);
     return res;
 }
-struct EnergyPreservation { float3 preintegrated_reflection, preintegrated_reflection_mult, preintegrated_transmission_fraction; };
+struct EnergyPreservation { float3 preintegrated_reflection, preintegrated_reflection_mult, preintegrated_transmission_fraction; float valid_sample_fraction; };
 struct LayeredBrdf { SpecularBrdf specular_brdf; DiffuseBrdf diffuse_brdf; EnergyPreservation ep; };
+struct Globals;
+KJB_DEV EnergyPreservation energy_preservation_from_brdf_ndotv(const Globals& g, const SpecularBrdf& s, float ndotv);
 KJB_DEV LayeredBrdf layered_brdf_from_gbuffer_ndotv(const Globals& g, const GbufferData& gb, float ndotv) {
     SpecularBrdf s; s.albedo = f3(0.04f); s.roughness = gb.roughness;
     DiffuseBrdf d; d.albedo = gb.albedo;
@@ -604,21 +633,26 @@ KJB_DEV LayeredBrdf layered_brdf_from_gbuffer_ndotv(const Globals& g, const Gbuf
         d.albedo = vmin(f3(1.0f), d.albedo * boost);
     }
     LayeredBrdf r;
-    {   // SpecularBrdfEnergyPreservation::from_brdf_ndotv (brdf_lut.hlsl:15-77, `#elif 1` branch)
-        const float2 uv = f2(ndotv, s.roughness) * f2((64.0f - 1.0f) / 64.0f) + f2(0.5f / 64.0f);
-        const float4 fg = bilinear_clamp(64, 64, uv, [&](int x, int y) { return ld_rgba16f(g.brdf_fg_lut, x, y); });
-        const float3 single_scatter = s.albedo * fg.x + fg.y;
-        const float e_ss = fg.x + fg.y;
-        const float3 f_ss = single_scatter / e_ss;
-        const float3 f_ss_tail = vlerp(f_ss, f3(1.0f), 0.4f);
-        const float3 bounce_radiance = (1.0f - e_ss) * f_ss_tail;
-        const float3 mult = 1.0f + bounce_radiance / (1.0f - bounce_radiance);
-        r.ep.preintegrated_reflection = single_scatter * mult;
-        r.ep.preintegrated_reflection_mult = mult;
-        r.ep.preintegrated_transmission_fraction = 1.0f - r.ep.preintegrated_reflection;
-    }
+    r.ep = energy_preservation_from_brdf_ndotv(g, s, ndotv);
     r.specular_brdf = s; r.diffuse_brdf = d;
     return r;
+}
+// SpecularBrdfEnergyPreservation::from_brdf_ndotv (brdf_lut.hlsl:15-77, `#elif 1` branch)
+KJB_DEV EnergyPreservation energy_preservation_from_brdf_ndotv(const Globals& g, const SpecularBrdf& s, float ndotv) {
+    EnergyPreservation ep;
+    const float2 uv = f2(ndotv, s.roughness) * f2((64.0f - 1.0f) / 64.0f) + f2(0.5f / 64.0f);
+    const float4 fg = bilinear_clamp(64, 64, uv, [&](int x, int y) { return ld_rgba16f(g.brdf_fg_lut, x, y); });
+    const float3 single_scatter = s.albedo * fg.x + fg.y;
+    ep.valid_sample_fraction = fg.z;
+    const float e_ss = fg.x + fg.y;
+    const float3 f_ss = single_scatter / e_ss;
+    const float3 f_ss_tail = vlerp(f_ss, f3(1.0f), 0.4f);
+    const float3 bounce_radiance = (1.0f - e_ss) * f_ss_tail;
+    const float3 mult = 1.0f + bounce_radiance / (1.0f - bounce_radiance);
+    ep.preintegrated_reflection = single_scatter * mult;
+    ep.preintegrated_reflection_mult = mult;
+    ep.preintegrated_transmission_fraction = 1.0f - ep.preintegrated_reflection;
+    return ep;
 }
 KJB_DEV float3 layered_evaluate(const LayeredBrdf& b, float3 wo, float3 wi) {
     if (wo.z <= 0 || wi.z <= 0) return f3(0.0f);

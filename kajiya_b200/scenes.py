@@ -15,6 +15,13 @@ def blue_noise():
     return np.fromfile(os.path.join(_ASSETS, "bluenoise_256_rgba8.bin"), np.uint8).reshape(256, 256, 4)
 
 
+def spatial_resolve_offsets():
+    """SPATIAL_RESOLVE_OFFSETS (rtr.rs:402-915) as int32[512, 4]"""
+    xy = np.fromfile(os.path.join(_ASSETS, "spatial_resolve_offsets_i16.bin"), np.int16).reshape(512, 2)
+    out = np.zeros((512, 4), np.int32); out[:, :2] = xy
+    return out
+
+
 def cornell_box():
     j = json.load(open(os.path.join(_ASSETS, "cornell_box.json")))
     mesh = dict(positions=np.array(j["positions"], np.float32), normals=np.array(j["normals"], np.float32),
@@ -121,3 +128,4 @@ def populate(world, scene):
         for t in transforms:
             world.add_instance(h, t)
     world.set_blue_noise(blue_noise())
+    world.set_spatial_resolve_offsets(spatial_resolve_offsets())

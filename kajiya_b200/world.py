@@ -35,6 +35,11 @@ class World:
         if self.ctx:
             self.d.kjb_destroy(self.ctx); self.ctx = None
 
+    def set_spatial_resolve_offsets(self, table):
+        """SPATIAL_RESOLVE_OFFSETS: int32[512, 4] (rtr.rs:402-915); required when enable_rtr"""
+        t = np.ascontiguousarray(table, np.int32).reshape(512, 4)
+        self._check(self.d.kjb_world_set_spatial_resolve_offsets(self.w, t.ctypes.data))
+
     def set_debug_serial(self, on=True):
         """cache-touching passes on one device thread in launch order (deterministic; slow)"""
         self._check(self.d.kjb_set_debug_serial(self.ctx, int(on)))

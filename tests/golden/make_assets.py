@@ -7,7 +7,11 @@
   kajiya_b200/assets/bluenoise_256_rgba8.bin <- /root/reference/assets/images/bluenoise/256_256/LDR_RGBA_0.png
         (the 256x256 RGBA8 blue-noise LUT bound at bindless slot 1, inc/bindless_textures.hlsl:11; raw texels)
 
-No reference SOURCE code is copied: both outputs are data assets, re-encoded.
+  kajiya_b200/assets/spatial_resolve_offsets_i16.bin <- the SPATIAL_RESOLVE_OFFSETS constant table of
+        /root/reference/crates/lib/kajiya/src/renderers/rtr.rs:402-915 (512 integer (x, y) sample offsets that the host pushes to the
+        reflection passes as shader constants; stored as int16[512, 2], the zero z/w lanes are re-added on load)
+
+No reference SOURCE code is copied: all outputs are data assets, re-encoded.
 """
 import json, struct, sys, os
 import numpy as np
@@ -89,6 +93,16 @@ def main():
     assert im.shape == (256, 256, 4)
     im.tofile(f"{OUT}/bluenoise_256_rgba8.bin")
     print("blue noise:", im.shape, im.mean())
+
+    import re
+    src = open(f"{REF}/crates/lib/kajiya/src/renderers/rtr.rs").read()
+    body = src[src.index("pub const SPATIAL_RESOLVE_OFFSETS"):]
+    body = body[body.index("= [") + 3:body.index("];")]
+    tup = re.findall(r"\(\s*(-?\d+)i32,\s*(-?\d+)i32,\s*0,\s*0\)", body)
+    assert len(tup) == 16 * 4 * 8, len(tup)
+    offs = np.array(tup, dtype=np.int16)
+    offs.tofile(f"{OUT}/spatial_resolve_offsets_i16.bin")
+    print("spatial resolve offsets:", offs.shape, offs.min(), offs.max())
 
 
 if __name__ == "__main__":
