@@ -22,10 +22,12 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 WORKLOADS = {
-    # name: (scene fn name, kwargs, width, height, spatial passes)
-    "cornell_1080p_rtdgi_1s1t": ("cornell_box", {}, 1920, 1080, 1),
-    "cornell_256_rtdgi": ("cornell_box", {}, 256, 256, 1),
-    "atrium_1080p_rtdgi": ("atrium", {}, 1920, 1080, 2),
+    # name: (scene fn name, kwargs, width, height, spatial passes, world flags)
+    "cornell_1080p_rtdgi_1s1t": ("cornell_box", {}, 1920, 1080, 1, {}),                       # BASELINE configs[1]: the metric's configuration
+    "cornell_256_rtdgi": ("cornell_box", {}, 256, 256, 1, {}),
+    "atrium_1080p_rtdgi": ("atrium", {}, 1920, 1080, 2, {}),
+    "atrium_1080p_gi_ircache_rtr": ("atrium", {}, 1920, 1080, 2, dict(enable_ircache=True, enable_rtr=True)),                   # configs[2] stand-in (Sponza-class)
+    "atrium_1440p_full_taa": ("atrium", {}, 2560, 1440, 2, dict(enable_ircache=True, enable_rtr=True, enable_taa=True)),       # configs[3] on one GPU
 }
 
 # compulsory bytes per pixel of each pass at its own grid (F = full-res px, Hh = half-res px)
@@ -33,7 +35,14 @@ PASS_BYTES = {
     "rtdgi reproject": ("F", 24), "extract ssao/2": ("Hh", 2), "extract half depth": ("Hh", 8), "extract view normal/2": ("Hh", 20),
     "rtdgi validate": ("Hh", 5), "rtdgi trace": ("Hh", 38), "validity integrate": ("Hh", 21), "restir temporal": ("Hh", 160),
     "restir spatial": ("Hh", 41), "restir resolve": ("F+Hh", (29, 56)), "rtdgi temporal": ("F+Hh", (48, 4)), "rtdgi spatial": ("F", 25),
+    # rtr (44 + 45 + 152 Hh; 36 F + 60 Hh; 52 F + 1 Hh; 20 F)
+    "reflection trace": ("Hh", 44), "reflection validate": ("Hh", 45), "rtr restir temporal": ("Hh", 152), "reflection resolve": ("F+Hh", (36, 60)),
+    "reflection temporal": ("F+Hh", (52, 1)), "reflection cleanup": ("F", 20),
 }
+# DRAM bytes per launch of each kernel, from one `ncu --set full` capture of the default workload (profiles/r01c_full_summary.csv:
+# dram__bytes_read.sum + dram__bytes_write.sum).  Far below the algorithmic bytes: the frame's working set stays in the 126 MB L2.
+NCU_TRAFFIC_1080P = {"rtdgi reproject": 22.97e6, "rtdgi validate": 4.21e6, "rtdgi trace": 15.18e6, "validity integrate": 21.28e6, "restir temporal": 23.39e6,
+                     "restir spatial": 12.01e6, "restir resolve": 33.74e6, "rtdgi temporal": 71.35e6, "rtdgi spatial": 35.46e6}
 
 
 def pass_bytes(label, F, Hh, validation_frame_fraction=1.0 / 3.0):
@@ -64,13 +73,16 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.samples.append([x.strip() for x in line.split(",")])
+            self.samples.append([x.strip() for x in line.split(",")] + [time.perf_counter()])
 
-    def stop(self):
+    def stop(self, t_begin=None, t_end=None):
+        """median SM clock / reasons over the samples taken in [t_begin, t_end] (perf_counter), i.e. while the timed loops ran"""
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
         self.proc.terminate()
+        if t_begin is not None:
+            self.samples = [s for s in self.samples if t_begin <= s[-1] <= t_end + 0.1]
         sm = sorted(int(float(s[0])) for s in self.samples if s and s[0].replace(".", "").isdigit())
         reasons = set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
@@ -95,9 +107,9 @@ def load_peaks():
 def build_world(lib, workload, device=0, tile=None):
     from kajiya_b200 import scenes
     from kajiya_b200.world import World
-    fn, kw, W, H, spatial = WORKLOADS[workload]
+    fn, kw, W, H, spatial, flags = WORKLOADS[workload]
     scene, view = getattr(scenes, fn)(**kw)
-    w = World(lib, W, H, device=device, spatial_reuse_pass_count=spatial, tile=tile)
+    w = World(lib, W, H, device=device, spatial_reuse_pass_count=spatial, tile=tile, **flags)
     scenes.populate(w, scene)
     return w, view, W, H
 
@@ -149,9 +161,10 @@ def run_cuda(args):
             bufs.append(t)
         host_ring.append(bufs)
     w.sync()
-    res_img = w.image_handle("rtdgi.spatial_filtered")
+    res_img = w.image_handle("taa.this_frame_out" if WORKLOADS[workload][5].get("enable_taa") else "rtdgi.spatial_filtered")
     res_bytes = res_img.width * res_img.height * 8
     host_result = pinned_empty(torch, res_bytes)
+    host_results = [host_result, pinned_empty(torch, res_bytes)]   # streaming mode alternates between two result buffers
 
     def barrier():
         if dist is not None:
@@ -161,24 +174,28 @@ def run_cuda(args):
     def step_device(i):
         w.render_frame(replay_slot=(i % nslots) + 1, **view)
 
+    # e2e: every step hands the frame's G-buffer inputs over as pinned HOST buffers and receives the result in a pinned host buffer.
+    # Streaming mode (kjb_world.h): uploads, passes and downloads run on three queues, two frames in flight; a tiled (multi-GPU)
+    # world falls back to the blocking call.
+    streaming = world_size == 1 and not args.no_streaming
     def step_e2e(i):
         b = host_ring[i % nslots]
-        w.render_frame(host_inputs=(b[0].data_ptr(), b[1].data_ptr(), b[2].data_ptr(), b[3].data_ptr()), host_result=host_result.data_ptr(), **view)
+        w.render_frame(host_inputs=(b[0].data_ptr(), b[1].data_ptr(), b[2].data_ptr(), b[3].data_ptr()), host_result=host_results[i & 1].data_ptr(), streaming=streaming, **view)
 
-    # ---- device-resident leg
+    # ---- device-resident leg (the clock sampler is already running when the timed loop starts; nvidia-smi needs ~0.2 s to come up)
+    clocks = ClockSampler(local_rank); clocks.start()
     for i in range(Wm):
         step_device(i)
     w.sync(); w.stats()          # reset ray counters
     launches0 = lib.dll.kjb_launch_count(w.ctx)
-    clocks = ClockSampler(local_rank); clocks.start()
     barrier()
+    t_load_begin = time.perf_counter()
     w.timer_record(1000)
     for i in range(K):
         step_device(Wm + i)
     w.timer_record(1001)
     ms_total = w.timer_elapsed_ms(1000, 1001)
     barrier()
-    clock_info = clocks.stop()
     st = w.stats()
     rays = st["closest_rays"] + st["any_hit_rays"]
     launches = lib.dll.kjb_launch_count(w.ctx) - launches0
@@ -191,18 +208,20 @@ def run_cuda(args):
     w.set_profiling(False)
 
     # ---- e2e leg: host G-buffer in, irradiance out
-    for i in range(max(3, Wm // 2)):
+    for i in range(max(4, Wm // 2)):
         step_e2e(i)
-    w.sync(); w.stats()
+    w.wait(); w.stats()
     barrier()
     t0 = time.perf_counter()
     w.timer_record(1002)
     for i in range(K):
         step_e2e(i)
+    w.wait()                     # the last results have landed in host memory
     w.timer_record(1003)
     ms_e2e = w.timer_elapsed_ms(1002, 1003)
     wall_e2e = (time.perf_counter() - t0) * 1e3
     barrier()
+    clock_info = clocks.stop(t_load_begin, time.perf_counter())   # samples from the device-timed, per-pass and e2e loops (GPU under load throughout)
     st2 = w.stats()
     rays_e2e = st2["closest_rays"] + st2["any_hit_rays"]
     ms_e2e = max(ms_e2e, wall_e2e)   # the call blocks on the download: wall clock is the honest end-to-end figure
@@ -233,14 +252,16 @@ def run_cuda(args):
     out = {
         "metric": "gi_rays_per_sec", "value": rays / (ms_total * 1e-3), "unit": "rays/s", "n_gpus": world_size, "steps": K, "warmup": Wm,
         "ms_per_step": frame_ms, "higher_is_better": True, "scaling": "strong" if world_size > 1 else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload, "scene": WORKLOADS[workload][0], "resolution": [W, H], "spatial_reuse_passes": WORKLOADS[workload][4],
+        "config": {"workload": workload, "scene": WORKLOADS[workload][0], "resolution": [W, H], "spatial_reuse_passes": WORKLOADS[workload][4], "features": WORKLOADS[workload][5],
                    "l2_policy": f"inputs larger than L2: ring of {nslots} distinct jittered G-buffers ({nslots * 32 * F / 1e6:.0f} MB) + ~{frame_bytes / 1e6:.0f} MB/frame of temporal state",
                    "rays_per_frame": rays / K / world_size, "multi_gpu": f"one frame tile-sharded into {world_size} bands of half-res rows, 1 ncclAllGather of band borders per frame; rays include halo recompute" if world_size > 1 else "n/a"},
         "e2e": {"value": rays_e2e / (ms_e2e * 1e-3), "unit": "rays/s", "ms_per_step": ms_e2e / K,
-                "h2d_bytes_per_step": int(32 * F + 1216), "d2h_bytes_per_step": int(res_bytes)},
+                "h2d_bytes_per_step": int(32 * F + 1216), "d2h_bytes_per_step": int(res_bytes),
+                "mode": "streaming: upload/compute/download queues, 2 frames in flight" if streaming else "blocking call per frame"},
         "gpu_launches": int(launches),
         "clocks": clock_info,
-        "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+        "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": NCU_TRAFFIC_1080P.get(dom) if workload == "cornell_1080p_rtdgi_1s1t" and world_size == 1 else None, "traffic_source": "profiles/r01c_full_summary.csv",
                      "peak_source": peak_src, "kernel_ms": per_pass[dom], "kernel_share_of_step": share[dom] / sum(share.values()),
                      "algorithmic_bytes_per_launch": dom_bytes,
                      "frame": {"algorithmic_bytes": frame_bytes, "achieved_gbs": frame_bytes / (frame_ms * 1e-3) / 1e9, "frac": frame_bytes / (frame_ms * 1e-3) / 1e9 / peak},
@@ -302,6 +323,7 @@ def main():
     ap.add_argument("--impl", default="kajiya_b200", choices=["kajiya_b200", "reference"])
     ap.add_argument("--workload", default="cornell_1080p_rtdgi_1s1t", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-streaming", action="store_true", help="e2e leg with the blocking call (upload, passes, download serialised)")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)

@@ -219,6 +219,19 @@ int  kjb_memcpy_d2d(kjb_context *ctx, void *dst, const void *src, uint64_t bytes
 
 /* Tile-sharded frames: restrict the FOLLOWING passes to rows [y0, y1) of their own output grid
  * (each rank of a multi-GPU frame computes its band plus the halo a pass's consumers need).  (0, 0) = whole image. */
+/* Copy queues: besides the compute queue every pass is enqueued on, a context owns an upload and a download queue (CUDA streams on
+ * the copy engines) so that host<->device transfers of neighbouring frames overlap the passes.  Events order work between queues:
+ * record on one queue, make another queue (or the host) wait.  Host memory must be page-locked for the copies to be asynchronous.
+ * (An interop host that shares memory with Vulkan never needs these; the frame driver's streaming mode does, kjb_world.h.) */
+#define KJB_QUEUE_COMPUTE  0u
+#define KJB_QUEUE_UPLOAD   1u
+#define KJB_QUEUE_DOWNLOAD 2u
+#define KJB_MAX_EVENTS 64u
+int  kjb_image_upload_on(kjb_context *ctx, uint32_t queue, const kjb_image *dst, const void *host_src);
+int  kjb_image_download_on(kjb_context *ctx, uint32_t queue, const kjb_image *src, void *host_dst);
+int  kjb_event_record(kjb_context *ctx, uint32_t event, uint32_t queue);
+int  kjb_queue_wait_event(kjb_context *ctx, uint32_t queue, uint32_t event);   /* no-op if the event was never recorded */
+int  kjb_event_synchronize(kjb_context *ctx, uint32_t event);                   /* host wait; no-op if never recorded */
 int  kjb_set_scissor(kjb_context *ctx, uint32_t y0, uint32_t y1);
 /* Determinism aid: while on, every pass that touches the (racy by design) irradiance cache runs on ONE device thread in the launch
  * order of its parallel kernel. Orders of magnitude slower; for reproducing cache states and for bit-exact parity tests. */

@@ -66,6 +66,11 @@ typedef struct kjb_world_frame {
      * G-buffer inputs (after the raster stand-in / upload) in ring slot k; replay_slot = k > 0 binds ring slot k as the
      * frame's G-buffer inputs (no raster pass, no copy). */
     uint32_t capture_slot, replay_slot;
+    /* Streaming mode (host_gbuffer + host_result given, streaming != 0): the call returns as soon as the frame is enqueued.  Uploads,
+     * passes and the result download run on three queues with two frames in flight, so the copies of neighbouring frames overlap the
+     * passes.  The host input buffers of a frame and its host_result must stay untouched until kjb_world_wait() (or until two further
+     * streaming frames have been submitted); consecutive frames must use different host_result buffers. */
+    uint32_t streaming;
 } kjb_world_frame;
 
 int  kjb_world_create(kjb_context *ctx, const kjb_world_desc *desc, kjb_world **out);
@@ -81,6 +86,8 @@ int  kjb_world_set_spatial_resolve_offsets(kjb_world *w, const int32_t *int4x512
 int  kjb_world_render_frame(kjb_world *w, const kjb_world_frame *frame);
 /* one frame of prepare_render_graph_reference (world_render_passes.rs:294-330): the path tracer accumulating in place */
 int  kjb_world_render_reference(kjb_world *w, const kjb_world_frame *frame, uint32_t indirect_only);
+/* block until every streaming frame submitted so far has delivered its host_result */
+int  kjb_world_wait(kjb_world *w);
 uint32_t kjb_world_frame_index(kjb_world *w);
 /* Look up a live image by its reference resource name ("rtdgi.radiance:0", "gbuffer", "rtdgi.irradiance", ...). */
 int  kjb_world_get_image(kjb_world *w, const char *name, kjb_image *out);

@@ -52,7 +52,7 @@ class WorldFrame(C.Structure):
     _fields_ = [("camera_position", C.c_float * 3), ("camera_rotation", C.c_float * 4), ("vertical_fov_deg", C.c_float), ("near_plane", C.c_float),
                 ("sun_direction", C.c_float * 3), ("delta_time_seconds", C.c_float),
                 ("host_gbuffer", C.c_void_p), ("host_depth", C.c_void_p), ("host_geometric_normal", C.c_void_p), ("host_velocity", C.c_void_p),
-                ("host_result", C.c_void_p), ("capture_slot", C.c_uint32), ("replay_slot", C.c_uint32)]
+                ("host_result", C.c_void_p), ("capture_slot", C.c_uint32), ("replay_slot", C.c_uint32), ("streaming", C.c_uint32)]
 
 
 assert C.sizeof(MeshMaterial) == 152
@@ -95,6 +95,7 @@ class KjbLib:
             "kjb_world_render_frame": (C.c_int, [P, C.POINTER(WorldFrame)]),
             "kjb_world_render_reference": (C.c_int, [P, C.POINTER(WorldFrame), C.c_uint32]),
             "kjb_world_frame_index": (C.c_uint32, [P]),
+            "kjb_world_wait": (C.c_int, [P]),
             "kjb_world_get_image": (C.c_int, [P, C.c_char_p, C.POINTER(Image)]),
             "kjb_world_image_names": (C.c_char_p, [P]),
             "kjb_world_last_frame_stats": (C.c_int, [P, C.POINTER(C.c_uint64 * 4)]),

@@ -113,6 +113,7 @@ struct kjb_world {
     PingPong rtr_temporal_tex{"rtr.temporal"}, rtr_ray_len_tex{"rtr.ray_len"}, rtr_temporal_irradiance_tex{"rtr.irradiance"}, rtr_temporal_ray_orig_tex{"rtr.ray_orig"},
         rtr_temporal_ray_tex{"rtr.ray"}, rtr_temporal_reservoir_tex{"rtr.reservoir"}, rtr_temporal_rng_tex{"rtr.rng"}, rtr_temporal_hit_normal_tex{"rtr.hit_normal"};
     bool rtr_reuse_rtdgi_rays = true;
+    uint32_t stream_frames = 0;   // streaming frames submitted (selects the input set / result stage)
     std::vector<int32_t> spatial_resolve_offsets;
     PingPong taa_temporal_tex{"taa"}, taa_temporal_velocity_tex{"taa.velocity"}, taa_temporal_smooth_var_tex{"taa.smooth_var"};   // taa.rs:19-27
     uint32_t OW = 0, OH = 0;   // temporal_upscale_extent
@@ -850,13 +851,24 @@ int kjb_world_render_frame(kjb_world* w, const kjb_world_frame* f) {
     }
 
     // G-buffer + depth + geometric normal + velocity (world_render_passes.rs:40-82)
-    const std::string in_prefix = f->replay_slot ? "slot" + std::to_string(f->replay_slot) + "." : "";
+    // streaming mode: two input sets / two result stages so that the copy queues can run one frame ahead / behind the passes
+    const bool streaming = f->streaming && f->host_gbuffer && f->host_result && !f->replay_slot && !w->tiled;
+    const uint32_t sset = w->stream_frames & 1u;
+    const uint32_t EV_UP = 8 + sset, EV_DONE = 10 + sset, EV_DL = 12 + sset;   // kjb_event slots per set
+    const std::string in_prefix = f->replay_slot ? "slot" + std::to_string(f->replay_slot) + "." : (streaming ? "in" + std::to_string(sset) + "." : "");
     kjb_image& geometric_normal = w->img(in_prefix + "geometric_normal", W, H, KJB_FMT_A2R10G10B10_UNORM);
     kjb_image& gbuffer = w->img(in_prefix + "gbuffer", W, H, KJB_FMT_RGBA32_FLOAT);
     kjb_image& depth = w->img(in_prefix + "depth", W, H, KJB_FMT_R32_FLOAT);
     kjb_image& velocity = w->img(in_prefix + "velocity", W, H, KJB_FMT_RGBA16_FLOAT);
     if (f->replay_slot) {
         // inputs already resident in HBM (captured earlier): nothing to produce
+    } else if (streaming) {
+        // the upload queue may overwrite this input set once the passes of the frame that last used it are done
+        int rc = kjb_queue_wait_event(ctx, KJB_QUEUE_UPLOAD, EV_DONE);
+        rc |= kjb_image_upload_on(ctx, KJB_QUEUE_UPLOAD, &gbuffer, f->host_gbuffer) | kjb_image_upload_on(ctx, KJB_QUEUE_UPLOAD, &depth, f->host_depth)
+            | kjb_image_upload_on(ctx, KJB_QUEUE_UPLOAD, &geometric_normal, f->host_geometric_normal) | kjb_image_upload_on(ctx, KJB_QUEUE_UPLOAD, &velocity, f->host_velocity);
+        rc |= kjb_event_record(ctx, EV_UP, KJB_QUEUE_UPLOAD) | kjb_queue_wait_event(ctx, KJB_QUEUE_COMPUTE, EV_UP);
+        if (rc) return rc;
     } else if (f->host_gbuffer) {
         int rc = kjb_image_upload(ctx, &gbuffer, f->host_gbuffer) | kjb_image_upload(ctx, &depth, f->host_depth)
                | kjb_image_upload(ctx, &geometric_normal, f->host_geometric_normal) | kjb_image_upload(ctx, &velocity, f->host_velocity);
@@ -930,12 +942,27 @@ int kjb_world_render_frame(kjb_world* w, const kjb_world_frame* f) {
         w->pass_end();
         w->rows_all();
     }
-    if (f->host_result && !w->err) {
+    if (streaming && !w->err) {
+        kjb_image result{};
+        if (kjb_world_get_image(w, result_name, &result) == 0) {
+            kjb_image& stage = w->img("result.stage" + std::to_string(sset), result.width, result.height, result.format);
+            int rc = kjb_queue_wait_event(ctx, KJB_QUEUE_COMPUTE, EV_DL);          // the previous download from this stage has drained
+            rc |= kjb_image_copy(ctx, &stage, &result) | kjb_event_record(ctx, EV_DONE, KJB_QUEUE_COMPUTE);
+            rc |= kjb_queue_wait_event(ctx, KJB_QUEUE_DOWNLOAD, EV_DONE) | kjb_image_download_on(ctx, KJB_QUEUE_DOWNLOAD, &stage, f->host_result) | kjb_event_record(ctx, EV_DL, KJB_QUEUE_DOWNLOAD);
+            if (rc) w->err = rc;
+        }
+        w->stream_frames += 1;
+    } else if (f->host_result && !w->err) {
         kjb_image result{};
         if (kjb_world_get_image(w, result_name, &result) == 0) { kjb_image_download(ctx, &result, f->host_result); kjb_sync(ctx); }
     }
     end_frame(w);
     return w->err;
+}
+
+int kjb_world_wait(kjb_world* w) {
+    int rc = kjb_event_synchronize(w->ctx, 12) | kjb_event_synchronize(w->ctx, 13);
+    return rc | kjb_sync(w->ctx);
 }
 
 int kjb_world_render_reference(kjb_world* w, const kjb_world_frame* f, uint32_t indirect_only) {

@@ -41,6 +41,8 @@ void kjb_destroy(kjb_context* c) {
     dev_free(c->d_tex_data); dev_free(c->d_tex_desc); dev_free(c->d_lights); dev_free(c->d_ray_counters);
 #if !defined(KJB_EMU)
     if (c->pinned_staging) cudaFreeHost(c->pinned_staging);
+    for (auto& ev : c->queue_events) if (ev) cudaEventDestroy(ev);
+    for (auto& st : c->copy_streams) if (st) cudaStreamDestroy(st);
     if (c->stream) cudaStreamDestroy(c->stream);
 #endif
     delete c;
@@ -70,6 +72,37 @@ int kjb_image_copy(kjb_context* c, const kjb_image* dst, const kjb_image* src) {
 }
 int kjb_image_upload(kjb_context* c, const kjb_image* dst, const void* src) { return dev_h2d(c, dst->data, src, image_bytes(*dst)); }
 int kjb_image_download(kjb_context* c, const kjb_image* src, void* dst) { return dev_d2h(c, dst, src->data, image_bytes(*src)); }
+#if defined(KJB_EMU)
+int kjb_image_upload_on(kjb_context* c, uint32_t, const kjb_image* dst, const void* src) { return kjb_image_upload(c, dst, src); }
+int kjb_image_download_on(kjb_context* c, uint32_t, const kjb_image* src, void* dst) { return kjb_image_download(c, src, dst); }
+int kjb_event_record(kjb_context*, uint32_t, uint32_t) { return 0; }
+int kjb_queue_wait_event(kjb_context*, uint32_t, uint32_t) { return 0; }
+int kjb_event_synchronize(kjb_context*, uint32_t) { return 0; }
+#else
+int kjb_image_upload_on(kjb_context* c, uint32_t q, const kjb_image* dst, const void* src) {
+    cudaStream_t st = c->queue(q); if (!st) return c->fail("kjb_image_upload_on: bad queue");
+    return cudaMemcpyAsync(dst->data, src, image_bytes(*dst), cudaMemcpyHostToDevice, st) != cudaSuccess ? c->fail("kjb_image_upload_on: copy failed") : 0;
+}
+int kjb_image_download_on(kjb_context* c, uint32_t q, const kjb_image* src, void* dst) {
+    cudaStream_t st = c->queue(q); if (!st) return c->fail("kjb_image_download_on: bad queue");
+    return cudaMemcpyAsync(dst, src->data, image_bytes(*src), cudaMemcpyDeviceToHost, st) != cudaSuccess ? c->fail("kjb_image_download_on: copy failed") : 0;
+}
+int kjb_event_record(kjb_context* c, uint32_t e, uint32_t q) {
+    cudaStream_t st = c->queue(q); if (!st || e >= KJB_MAX_EVENTS) return c->fail("kjb_event_record: bad queue or event");
+    if (!c->queue_events[e] && cudaEventCreateWithFlags(&c->queue_events[e], cudaEventDisableTiming) != cudaSuccess) return c->fail("kjb_event_record: cudaEventCreate failed");
+    return cudaEventRecord(c->queue_events[e], st) != cudaSuccess ? c->fail("kjb_event_record: record failed") : 0;
+}
+int kjb_queue_wait_event(kjb_context* c, uint32_t q, uint32_t e) {
+    cudaStream_t st = c->queue(q); if (!st || e >= KJB_MAX_EVENTS) return c->fail("kjb_queue_wait_event: bad queue or event");
+    if (!c->queue_events[e]) return 0;
+    return cudaStreamWaitEvent(st, c->queue_events[e], 0) != cudaSuccess ? c->fail("kjb_queue_wait_event: wait failed") : 0;
+}
+int kjb_event_synchronize(kjb_context* c, uint32_t e) {
+    if (e >= KJB_MAX_EVENTS) return c->fail("kjb_event_synchronize: bad event");
+    if (!c->queue_events[e]) return 0;
+    return cudaEventSynchronize(c->queue_events[e]) != cudaSuccess ? c->fail("kjb_event_synchronize: failed") : 0;
+}
+#endif
 int kjb_buffer_alloc(kjb_context* c, uint64_t n, kjb_buffer* out) { out->data = dev_alloc(n); out->size_bytes = n; return out->data ? 0 : c->fail("kjb_buffer_alloc: out of device memory"); }
 int kjb_buffer_free(kjb_context*, kjb_buffer* b) { dev_free(b->data); b->data = nullptr; return 0; }
 int kjb_buffer_upload(kjb_context* c, const kjb_buffer* dst, uint64_t off, const void* src, uint64_t n) { return dev_h2d(c, (char*)dst->data + off, src, n); }

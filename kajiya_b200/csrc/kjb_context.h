@@ -36,6 +36,14 @@ struct kjb_context {
     int32_t* d_resolve_offsets = nullptr; std::vector<int32_t> h_resolve_offsets;   // SPATIAL_RESOLVE_OFFSETS as last pushed by the host
 #if !defined(KJB_EMU)
     std::vector<cudaEvent_t> timer_events;
+    cudaStream_t copy_streams[2] = {nullptr, nullptr};        // KJB_QUEUE_UPLOAD, KJB_QUEUE_DOWNLOAD (created on first use)
+    cudaEvent_t queue_events[64] = {};                        // kjb_event_record slots
+    cudaStream_t queue(uint32_t q) {
+        if (q == 0) return stream;
+        if (q > 2) return nullptr;
+        if (!copy_streams[q - 1] && cudaStreamCreateWithFlags(&copy_streams[q - 1], cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+        return copy_streams[q - 1];
+    }
 #endif
 
     kjb::Globals g;   // host copy, passed by value to every kernel

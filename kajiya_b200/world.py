@@ -101,7 +101,7 @@ class World:
         self._check(self.d.kjb_world_set_blue_noise(self.w, a.ctypes.data))
 
     # -- frames ------------------------------------------------------------------------------------------------
-    def _frame(self, camera_position, camera_rotation, sun_direction, vfov=52.0, host_inputs=None, host_result=None, capture_slot=0, replay_slot=0):
+    def _frame(self, camera_position, camera_rotation, sun_direction, vfov=52.0, host_inputs=None, host_result=None, capture_slot=0, replay_slot=0, streaming=False):
         f = WorldFrame()
         f.camera_position[:] = camera_position; f.camera_rotation[:] = camera_rotation
         f.vertical_fov_deg = vfov; f.near_plane = 0.01; f.sun_direction[:] = sun_direction; f.delta_time_seconds = 1.0 / 60.0
@@ -110,6 +110,7 @@ class World:
         if host_result is not None:
             f.host_result = host_result
         f.capture_slot, f.replay_slot = capture_slot, replay_slot
+        f.streaming = int(streaming)
         return f
 
     def render_frame(self, camera_position, camera_rotation, sun_direction, **kw):
@@ -119,6 +120,10 @@ class World:
     def render_reference(self, camera_position, camera_rotation, sun_direction, indirect_only=False, **kw):
         f = self._frame(camera_position, camera_rotation, sun_direction, **kw)
         self._check(self.d.kjb_world_render_reference(self.w, C.byref(f), int(indirect_only)))
+
+    def wait(self):
+        """block until every streaming frame has delivered its host_result"""
+        self._check(self.d.kjb_world_wait(self.w))
 
     def sync(self):
         self._check(self.d.kjb_sync(self.ctx))

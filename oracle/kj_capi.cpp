@@ -72,7 +72,12 @@ int kjb_allgather(kjb_context* c, const void* send, void* recv, uint64_t bytes) 
 }
 int kjb_memcpy_d2d(kjb_context*, void* dst, const void* src, uint64_t bytes) { memmove(dst, src, bytes); return 0; }
 int kjb_set_scissor(kjb_context* c, uint32_t y0, uint32_t y1) { c->scissor_y0 = y0; c->scissor_y1 = y1; return 0; }
-int kjb_set_debug_serial(kjb_context*, uint32_t) { return 0; }   // the oracle's cache passes are always serial
+int kjb_set_debug_serial(kjb_context*, uint32_t) { return 0; }
+int kjb_image_upload_on(kjb_context* c, uint32_t, const kjb_image* dst, const void* src) { return kjb_image_upload(c, dst, src); }
+int kjb_image_download_on(kjb_context* c, uint32_t, const kjb_image* src, void* dst) { return kjb_image_download(c, src, dst); }
+int kjb_event_record(kjb_context*, uint32_t, uint32_t) { return 0; }
+int kjb_queue_wait_event(kjb_context*, uint32_t, uint32_t) { return 0; }
+int kjb_event_synchronize(kjb_context*, uint32_t) { return 0; }   // the oracle's cache passes are always serial
 int kjb_set_luts(kjb_context* c, const kjb_image* fg, const kjb_image* bn) { c->g.brdf_fg_lut = Img(*fg); c->g.blue_noise = Img(*bn); return 0; }
 static std::chrono::steady_clock::time_point g_timer_slots[1024];
 int kjb_timer_record(kjb_context*, uint32_t slot) { if (slot >= 1024) return 1; g_timer_slots[slot] = std::chrono::steady_clock::now(); return 0; }

@@ -140,3 +140,22 @@ def test_rtr_with_ircache_and_taa(oracle_lib, emu_lib):
     _, wb, report = parity.run_lockstep(oracle_lib, emu_lib, _glossy(scene), view, 80, 48, 6, enable_rtr=True, enable_ircache=True, enable_taa=True)
     _clean(report)
     assert wb.image("ircache.meta_buf").ravel()[3] > 50
+
+
+def test_streaming_frames_match_blocking_frames(emu_lib):
+    """kjb_world_frame.streaming (two input sets / result stages, copy queues): same bits as the blocking call."""
+    scene, view = scenes.cornell_box()
+    wa, wb = parity.make_world(emu_lib, scene, 64, 40), parity.make_world(emu_lib, scene, 64, 40)
+    host = []
+    for i in range(5):   # produce 5 frames' worth of host G-buffers with a third world
+        wa.render_frame(**view)
+        host.append([wa.image(n).copy() for n in ("gbuffer", "depth", "geometric_normal", "velocity")])
+    wc = parity.make_world(emu_lib, scene, 64, 40)
+    res_b = [np.zeros((40, 64, 4), np.float16) for _ in range(5)]; res_s = [np.zeros((40, 64, 4), np.float16) for _ in range(5)]
+    for i in range(5):
+        wb.render_frame(host_inputs=tuple(a.ctypes.data for a in host[i]), host_result=res_b[i].ctypes.data, **view)
+        wc.render_frame(host_inputs=tuple(a.ctypes.data for a in host[i]), host_result=res_s[i].ctypes.data, streaming=True, **view)
+    wc.wait()
+    for i in range(5):
+        assert np.array_equal(res_b[i].view(np.uint16), res_s[i].view(np.uint16)), i
+    assert {"in0.gbuffer", "in1.gbuffer", "result.stage0", "result.stage1"} <= set(wc.image_names())
