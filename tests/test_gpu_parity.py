@@ -174,3 +174,25 @@ def test_full_pipeline_serial_schedule_bit_exact(oracle_lib, cuda_lib):
         wa.render_frame(**view); wb.render_frame(**view)
         bad = parity.compare_images(wa, wb)
         assert not bad, (f, bad[:5])
+
+
+def test_streaming_frames_match_blocking_frames(cuda_lib):
+    """Streaming mode (upload / compute / download queues, two frames in flight) delivers the same bits as the blocking call,
+    also when frames are submitted back to back without waiting (1080p so that copies and passes really overlap)."""
+    scene, view = scenes.cornell_box()
+    W, H, N = 1920, 1080, 6
+    wa = parity.make_world(cuda_lib, scene, W, H, spatial_reuse_pass_count=1)
+    host = []
+    for i in range(N):
+        wa.render_frame(**view)
+        host.append([wa.image(n).copy() for n in ("gbuffer", "depth", "geometric_normal", "velocity")])
+    wa.close()
+    wb, wc = parity.make_world(cuda_lib, scene, W, H, spatial_reuse_pass_count=1), parity.make_world(cuda_lib, scene, W, H, spatial_reuse_pass_count=1)
+    res_b = [np.zeros((H, W, 4), np.float16) for _ in range(N)]; res_s = [np.zeros((H, W, 4), np.float16) for _ in range(N)]
+    for i in range(N):
+        wb.render_frame(host_inputs=tuple(a.ctypes.data for a in host[i]), host_result=res_b[i].ctypes.data, **view)
+    for i in range(N):
+        wc.render_frame(host_inputs=tuple(a.ctypes.data for a in host[i]), host_result=res_s[i].ctypes.data, streaming=True, **view)
+    wc.wait()
+    for i in range(N):
+        assert np.array_equal(res_b[i].view(np.uint16), res_s[i].view(np.uint16)), i
