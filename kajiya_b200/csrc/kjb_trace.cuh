@@ -52,6 +52,11 @@ KJB_DEV bool intersect_leaf(const BvhTri* tris, uint32_t first, uint32_t count, 
 template <bool ANY_HIT>
 KJB_DEV HitInfo trace(const SceneView& sc, const Ray& r, bool cull_back) {
     HitInfo best; best.hit = false; best.t = r.tmax; best.u = 0; best.v = 0; best.gid = 0xffffffffu;
+    // A ray with a NaN anywhere can never pass the triangle test (every comparison on t/u/v is false), but the NaN-ignoring min/max of
+    // the slab test would let it visit EVERY node.  Such rays are routine — the validation passes re-trace stored rays, and an empty
+    // reservoir stores a zero-length one (normalize(0) = NaN).  Same result, no traversal.
+    if (!(r.dir.x == r.dir.x && r.dir.y == r.dir.y && r.dir.z == r.dir.z && r.origin.x == r.origin.x && r.origin.y == r.origin.y && r.origin.z == r.origin.z
+          && r.tmin == r.tmin && r.tmax == r.tmax)) return best;
     const float3 inv_dir = f3(1.0f / r.dir.x, 1.0f / r.dir.y, 1.0f / r.dir.z);
     int stack[64]; int sp = 0;
     int cur = sc.root;   // inner node index (>= 0) or an encoded leaf when the whole scene is one leaf

@@ -127,6 +127,9 @@ struct Scene {
         t_out = t; u_out = u; v_out = v;
         return true;
     }
+    static bool ray_has_nan(const Ray& r) {
+        return !(r.dir.x == r.dir.x && r.dir.y == r.dir.y && r.dir.z == r.dir.z && r.origin.x == r.origin.x && r.origin.y == r.origin.y && r.origin.z == r.origin.z && r.tmin == r.tmin && r.tmax == r.tmax);
+    }
     static bool slab(const BvhNode& n, const Ray& r, float3 inv_dir, float tmax) {
         float3 t0 = (n.bmin - r.origin) * inv_dir, t1 = (n.bmax - r.origin) * inv_dir;
         float3 a = min(t0, t1), b = max(t0, t1);
@@ -137,7 +140,7 @@ struct Scene {
     HitInfo closest(const Ray& r, bool cull_back) const {
         n_closest++;
         HitInfo h; h.hit = false; h.t = r.tmax; h.tri = 0xffffffffu; h.u = h.v = 0;
-        if (nodes.empty()) return h;
+        if (nodes.empty() || ray_has_nan(r)) return h;   // a NaN ray cannot pass the triangle test; skip the (NaN-ignoring) slab walk
         float3 inv_dir = 1.0f / r.dir;
         int stack[64]; int sp = 0; stack[sp++] = 0;
         while (sp) {
@@ -163,7 +166,7 @@ struct Scene {
     }
     bool any_hit(const Ray& r) const {
         n_any++;
-        if (nodes.empty()) return false;
+        if (nodes.empty() || ray_has_nan(r)) return false;
         float3 inv_dir = 1.0f / r.dir;
         int stack[64]; int sp = 0; stack[sp++] = 0;
         while (sp) {

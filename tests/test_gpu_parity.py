@@ -196,3 +196,16 @@ def test_streaming_frames_match_blocking_frames(cuda_lib):
     wc.wait()
     for i in range(N):
         assert np.array_equal(res_b[i].view(np.uint16), res_s[i].view(np.uint16)), i
+
+
+def test_atrium_full_pipeline_serial_schedule(oracle_lib, cuda_lib):
+    """Sponza-class procedural scene (many materials, 1x1 placeholder textures, NaN validation rays from empty reservoirs):
+    rtdgi + ircache + rtr, cache passes on the serial schedule, everything bit for bit."""
+    scene, view = scenes.atrium(target_tris=12000)
+    kw = dict(enable_rtr=True, enable_ircache=True, spatial_reuse_pass_count=2)
+    wa, wb = parity.make_world(oracle_lib, scene, 96, 54, **kw), parity.make_world(cuda_lib, scene, 96, 54, **kw)
+    wb.set_debug_serial(True)
+    for f in range(5):
+        wa.render_frame(**view); wb.render_frame(**view)
+        bad = parity.compare_images(wa, wb)
+        assert not bad, (f, bad[:5])
