@@ -103,6 +103,17 @@ KJB_HD float kjb_f16_to_f32(uint32_t h) {
     return kjb_u2f(sign | ((exp + 112u) << 23) | (man << 13));
 }
 
+/* ---- fused multiply-add: the ONLY place contraction happens.  Both sides compile with contraction off, so a*b+c written with
+ * operators is two roundings everywhere; code that wants the fused form says so explicitly and gets it on the device (FFMA) and on
+ * the host (vfmadd / libm fmaf) alike.  Used by dot / matrix-vector / lerp and the polynomial kernels below. ---- */
+KJB_HD float kjb_fma(float a, float b, float c) {
+#if defined(__CUDA_ARCH__)
+    return __fmaf_rn(a, b, c);
+#else
+    return __builtin_fmaf(a, b, c);
+#endif
+}
+
 /* ---- elementary helpers with HLSL semantics ---- */
 /* HLSL/DXIL FMin/FMax = IEEE minNum/maxNum: a NaN operand loses (the shaders rely on it, e.g. `max(0.0, dot(n, NaN_dir))`
  * for neighbours at depth 0 in restir_resolve.hlsl:112-114).  Same as CUDA fminf/fmaxf. */
@@ -118,12 +129,12 @@ KJB_HD float kjb_floor(float x) { return floorf(x); }
 KJB_HD float kjb_ceil(float x) { return ceilf(x); }
 KJB_HD float kjb_trunc(float x) { return truncf(x); }
 KJB_HD float kjb_frac(float x) { return x - floorf(x); }
-KJB_HD float kjb_lerp(float a, float b, float t) { return a + (b - a) * t; }   /* HLSL lerp = a + t*(b-a) */
+KJB_HD float kjb_lerp(float a, float b, float t) { return kjb_fma(b - a, t, a); }   /* HLSL lerp = a + t*(b-a) */
 KJB_HD float kjb_step(float edge, float x) { return x >= edge ? 1.0f : 0.0f; }
 KJB_HD float kjb_sign(float x) { return x > 0.0f ? 1.0f : (x < 0.0f ? -1.0f : 0.0f); }
 KJB_HD float kjb_smoothstep(float a, float b, float x) {
     const float t = kjb_saturate((x - a) / (b - a));
-    return t * t * (3.0f - 2.0f * t);
+    return t * t * kjb_fma(-2.0f, t, 3.0f);
 }
 
 /* float -> int conversions with the saturating semantics GPUs implement (HLSL leaves out-of-range
@@ -161,11 +172,10 @@ KJB_HD void kjb_sincos(float xx, float *s_out, float *c_out) {
     float y = (float)j;
     if (j & 1u) { j += 1u; y += 1.0f; }
     j &= 7u;
-    x = ((x - y * DP1) - y * DP2) - y * DP3;
+    x = kjb_fma(-y, DP3, kjb_fma(-y, DP2, kjb_fma(-y, DP1, x)));
     const float z = x * x;
-    const float ps = ((-1.9515295891e-4f * z + 8.3321608736e-3f) * z - 1.6666654611e-1f) * z * x + x;
-    const float pc = ((2.443315711809948e-5f * z - 1.388731625493765e-3f) * z + 4.166664568298827e-2f) * z * z
-                     - 0.5f * z + 1.0f;
+    const float ps = kjb_fma(kjb_fma(kjb_fma(-1.9515295891e-4f, z, 8.3321608736e-3f), z, -1.6666654611e-1f) * z, x, x);
+    const float pc = kjb_fma(kjb_fma(kjb_fma(2.443315711809948e-5f, z, -1.388731625493765e-3f), z, 4.166664568298827e-2f) * z, z, kjb_fma(-0.5f, z, 1.0f));
     float s, c;
     int ssign = neg, csign = 0;
     if (j > 3u) { ssign = !ssign; csign = !csign; j -= 4u; }
@@ -188,13 +198,13 @@ KJB_HD float kjb_exp2(float x) {
     /* 2^f, minimax-ish Taylor in f*ln2, degree 7 */
     const float t = f * 0.693147180559945f;
     float p = 1.984126984e-4f;
-    p = p * t + 1.388888889e-3f;
-    p = p * t + 8.333333333e-3f;
-    p = p * t + 4.166666667e-2f;
-    p = p * t + 1.666666667e-1f;
-    p = p * t + 0.5f;
-    p = p * t + 1.0f;
-    p = p * t + 1.0f;
+    p = kjb_fma(p, t, 1.388888889e-3f);
+    p = kjb_fma(p, t, 8.333333333e-3f);
+    p = kjb_fma(p, t, 4.166666667e-2f);
+    p = kjb_fma(p, t, 1.666666667e-1f);
+    p = kjb_fma(p, t, 0.5f);
+    p = kjb_fma(p, t, 1.0f);
+    p = kjb_fma(p, t, 1.0f);
     if (n > 127) return p * 2.0f * kjb_u2f((uint32_t)(127 + 127) << 23);
     return p * kjb_u2f((uint32_t)(n + 127) << 23);
 }
@@ -215,13 +225,13 @@ KJB_HD float kjb_log2(float x) {
     const float s = f / (2.0f + f);
     const float z = s * s;
     float p = 0.1818181818f;
-    p = p * z + 0.2222222222f;
-    p = p * z + 0.2857142857f;
-    p = p * z + 0.4f;
-    p = p * z + 0.6666666667f;
-    p = p * z + 2.0f;
+    p = kjb_fma(p, z, 0.2222222222f);
+    p = kjb_fma(p, z, 0.2857142857f);
+    p = kjb_fma(p, z, 0.4f);
+    p = kjb_fma(p, z, 0.6666666667f);
+    p = kjb_fma(p, z, 2.0f);
     const float ln1pf = p * s;
-    return ln1pf * 1.44269504088896f + (float)e;
+    return kjb_fma(ln1pf, 1.44269504088896f, (float)e);
 }
 
 KJB_HD float kjb_pow(float x, float y) { return kjb_exp2(y * kjb_log2(x)); }   /* HLSL pow semantics */
@@ -236,7 +246,7 @@ KJB_HD float kjb_atan(float xx) {
     else if (x > 0.4142135623730950f) { y = 0.7853981633974483f; x = (x - 1.0f) / (x + 1.0f); }
     else y = 0.0f;
     const float z = x * x;
-    y = y + ((((8.05374449538e-2f * z - 1.38776856032e-1f) * z + 1.99777106478e-1f) * z - 3.33329491539e-1f) * z * x + x);
+    y = y + kjb_fma(kjb_fma(kjb_fma(kjb_fma(8.05374449538e-2f, z, -1.38776856032e-1f), z, 1.99777106478e-1f), z, -3.33329491539e-1f) * z, x, x);
     return xx < 0.0f ? -y : y;
 }
 KJB_HD float kjb_atan2(float y, float x) {

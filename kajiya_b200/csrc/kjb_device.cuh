@@ -79,13 +79,14 @@ KJB_DEV float2 vfloor(float2 a) { return f2(kjb_floor(a.x), kjb_floor(a.y)); }
 KJB_DEV float2 vfrac(float2 a) { return f2(kjb_frac(a.x), kjb_frac(a.y)); }
 KJB_DEV float2 vsaturate(float2 a) { return f2(kjb_saturate(a.x), kjb_saturate(a.y)); }
 KJB_DEV float3 vclamp(float3 v, float3 lo, float3 hi) { return vmin(vmax(v, lo), hi); }
-KJB_DEV float3 vlerp(float3 a, float3 b, float t) { return a + (b - a) * t; }
-KJB_DEV float3 vlerp(float3 a, float3 b, float3 t) { return a + (b - a) * t; }
-KJB_DEV float4 vlerp(float4 a, float4 b, float t) { return a + (b - a) * t; }
-KJB_DEV float2 vlerp(float2 a, float2 b, float t) { return a + (b - a) * t; }
-KJB_DEV float dot(float2 a, float2 b) { return a.x * b.x + a.y * b.y; }
-KJB_DEV float dot(float3 a, float3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
-KJB_DEV float dot(float4 a, float4 b) { return a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w; }
+// lerp, dot and matrix-vector products are FMA chains (numeric contract: the fused form is written out, kjb_numeric.h)
+KJB_DEV float3 vlerp(float3 a, float3 b, float t) { return f3(kjb_lerp(a.x, b.x, t), kjb_lerp(a.y, b.y, t), kjb_lerp(a.z, b.z, t)); }
+KJB_DEV float3 vlerp(float3 a, float3 b, float3 t) { return f3(kjb_lerp(a.x, b.x, t.x), kjb_lerp(a.y, b.y, t.y), kjb_lerp(a.z, b.z, t.z)); }
+KJB_DEV float4 vlerp(float4 a, float4 b, float t) { return f4(kjb_lerp(a.x, b.x, t), kjb_lerp(a.y, b.y, t), kjb_lerp(a.z, b.z, t), kjb_lerp(a.w, b.w, t)); }
+KJB_DEV float2 vlerp(float2 a, float2 b, float t) { return f2(kjb_lerp(a.x, b.x, t), kjb_lerp(a.y, b.y, t)); }
+KJB_DEV float dot(float2 a, float2 b) { return kjb_fma(a.y, b.y, a.x * b.x); }
+KJB_DEV float dot(float3 a, float3 b) { return kjb_fma(a.z, b.z, kjb_fma(a.y, b.y, a.x * b.x)); }
+KJB_DEV float dot(float4 a, float4 b) { return kjb_fma(a.w, b.w, kjb_fma(a.z, b.z, kjb_fma(a.y, b.y, a.x * b.x))); }
 KJB_DEV float3 cross(float3 a, float3 b) { return f3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
 KJB_DEV float length(float2 a) { return kjb_sqrt(dot(a, a)); }
 KJB_DEV float length(float3 a) { return kjb_sqrt(dot(a, a)); }
@@ -97,13 +98,13 @@ KJB_DEV float square(float x) { return x * x; }
 // ------------------------------------------------------------------------------------------------ matrices
 KJB_DEV float4 mul(const kjb_mat4& M, float4 v) {   // column-major glam Mat4, HLSL mul(M, v)
     const float* m = M.m;
-    return f4(m[0] * v.x + m[4] * v.y + m[8] * v.z + m[12] * v.w, m[1] * v.x + m[5] * v.y + m[9] * v.z + m[13] * v.w,
-              m[2] * v.x + m[6] * v.y + m[10] * v.z + m[14] * v.w, m[3] * v.x + m[7] * v.y + m[11] * v.z + m[15] * v.w);
+    return f4(kjb_fma(m[12], v.w, kjb_fma(m[8], v.z, kjb_fma(m[4], v.y, m[0] * v.x))), kjb_fma(m[13], v.w, kjb_fma(m[9], v.z, kjb_fma(m[5], v.y, m[1] * v.x))),
+              kjb_fma(m[14], v.w, kjb_fma(m[10], v.z, kjb_fma(m[6], v.y, m[2] * v.x))), kjb_fma(m[15], v.w, kjb_fma(m[11], v.z, kjb_fma(m[7], v.y, m[3] * v.x))));
 }
 struct float3x3 { float3 r0, r1, r2; };
 KJB_DEV float3 mul(const float3x3& M, float3 v) { return f3(dot(M.r0, v), dot(M.r1, v), dot(M.r2, v)); }
 KJB_DEV float3 mul(float3 v, const float3x3& M) {
-    return f3(v.x * M.r0.x + v.y * M.r1.x + v.z * M.r2.x, v.x * M.r0.y + v.y * M.r1.y + v.z * M.r2.y, v.x * M.r0.z + v.y * M.r1.z + v.z * M.r2.z);
+    return f3(kjb_fma(v.z, M.r2.x, kjb_fma(v.y, M.r1.x, v.x * M.r0.x)), kjb_fma(v.z, M.r2.y, kjb_fma(v.y, M.r1.y, v.x * M.r0.y)), kjb_fma(v.z, M.r2.z, kjb_fma(v.y, M.r1.z, v.x * M.r0.z)));
 }
 KJB_DEV float3 xform_point(const float* m, float3 p) {   // row-major 3x4
     return f3(m[0] * p.x + m[1] * p.y + m[2] * p.z + m[3], m[4] * p.x + m[5] * p.y + m[6] * p.z + m[7], m[8] * p.x + m[9] * p.y + m[10] * p.z + m[11]);
@@ -372,8 +373,8 @@ template <typename F> KJB_DEV float4 bilinear_clamp(int w, int h, float2 uv, F f
     const float tx = fx - x0f, ty = fy - y0f;
     const int x0 = clampi(kjb_cvt_i32(x0f), w), x1 = clampi(kjb_cvt_i32(x0f) + 1, w), y0 = clampi(kjb_cvt_i32(y0f), h), y1 = clampi(kjb_cvt_i32(y0f) + 1, h);
     const float4 a = fetch(x0, y0), b = fetch(x1, y0), c = fetch(x0, y1), d = fetch(x1, y1);
-    const float4 top = a + (b - a) * tx, bot = c + (d - c) * tx;
-    return top + (bot - top) * ty;
+    const float4 top = vlerp(a, b, tx), bot = vlerp(c, d, tx);
+    return vlerp(top, bot, ty);
 }
 // TextureCube.SampleLevel(sampler_llr): Vulkan face selection, bilinear inside the face (no seamless edges)
 KJB_DEV float4 sample_cube_rgba16f(const Img& cube, float3 dir) {

@@ -138,8 +138,8 @@ struct Img {
         auto cl = [](int v, int n) { return v < 0 ? 0 : (v >= n ? n - 1 : v); };
         x0 = cl(x0, w()); x1 = cl(x1, w()); y0 = cl(y0, h()); y1 = cl(y1, h());
         float4 a = load(x0, y0, layer), b = load(x1, y0, layer), c = load(x0, y1, layer), dd = load(x1, y1, layer);
-        float4 top = a + (b - a) * tx, bot = c + (dd - c) * tx;
-        return top + (bot - top) * ty;
+        float4 top = lerp(a, b, tx), bot = lerp(c, dd, tx);   // fma(b - a, t, a) per component
+        return lerp(top, bot, ty);
     }
     // TextureCube.SampleLevel(sampler_llr, dir, 0): face select (Vulkan spec table), bilinear inside the face,
     // clamp at face edges (no seamless filtering: documented deviation).

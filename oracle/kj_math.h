@@ -98,16 +98,17 @@ inline float2 frac(float2 a) { return float2(frac(a.x), frac(a.y)); }
 inline float3 exp(float3 a) { return float3(exp(a.x), exp(a.y), exp(a.z)); }
 inline float3 clamp(float3 v, float3 a, float3 b) { return min(max(v, a), b); }
 inline float2 clamp(float2 v, float2 a, float2 b) { return min(max(v, a), b); }
-inline float3 lerp(float3 a, float3 b, float t) { return a + (b - a) * t; }
-inline float3 lerp(float3 a, float3 b, float3 t) { return a + (b - a) * t; }
-inline float4 lerp(float4 a, float4 b, float t) { return a + (b - a) * t; }
-inline float2 lerp(float2 a, float2 b, float t) { return a + (b - a) * t; }
+// lerp = fma(b - a, t, a) per component (numeric contract: explicit FMA, kjb_numeric.h)
+inline float3 lerp(float3 a, float3 b, float t) { return float3(kjb_lerp(a.x, b.x, t), kjb_lerp(a.y, b.y, t), kjb_lerp(a.z, b.z, t)); }
+inline float3 lerp(float3 a, float3 b, float3 t) { return float3(kjb_lerp(a.x, b.x, t.x), kjb_lerp(a.y, b.y, t.y), kjb_lerp(a.z, b.z, t.z)); }
+inline float4 lerp(float4 a, float4 b, float t) { return float4(kjb_lerp(a.x, b.x, t), kjb_lerp(a.y, b.y, t), kjb_lerp(a.z, b.z, t), kjb_lerp(a.w, b.w, t)); }
+inline float2 lerp(float2 a, float2 b, float t) { return float2(kjb_lerp(a.x, b.x, t), kjb_lerp(a.y, b.y, t)); }
 inline float2 saturate(float2 a) { return float2(saturate(a.x), saturate(a.y)); }
 inline float3 saturate(float3 a) { return float3(saturate(a.x), saturate(a.y), saturate(a.z)); }
-// dot products: left-to-right sums (the evaluation order both sides of the parity agree on)
-inline float dot(float2 a, float2 b) { return a.x * b.x + a.y * b.y; }
-inline float dot(float3 a, float3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
-inline float dot(float4 a, float4 b) { return a.x * b.x + a.y * b.y + a.z * b.z + a.w * b.w; }
+// dot products: left-to-right FMA chains (the evaluation order both sides of the parity agree on)
+inline float dot(float2 a, float2 b) { return kjb_fma(a.y, b.y, a.x * b.x); }
+inline float dot(float3 a, float3 b) { return kjb_fma(a.z, b.z, kjb_fma(a.y, b.y, a.x * b.x)); }
+inline float dot(float4 a, float4 b) { return kjb_fma(a.w, b.w, kjb_fma(a.z, b.z, kjb_fma(a.y, b.y, a.x * b.x))); }
 inline float3 cross(float3 a, float3 b) { return float3(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x); }
 inline float length(float2 a) { return sqrt(dot(a, a)); }
 inline float length(float3 a) { return sqrt(dot(a, a)); }
@@ -120,19 +121,19 @@ inline bool any_nonzero(float3 a) { return a.x != 0.0f || a.y != 0.0f || a.z != 
 inline float4 mul(const kjb_mat4& M, float4 v) {
     const float* m = M.m;
     return float4(
-        m[0] * v.x + m[4] * v.y + m[8] * v.z + m[12] * v.w,
-        m[1] * v.x + m[5] * v.y + m[9] * v.z + m[13] * v.w,
-        m[2] * v.x + m[6] * v.y + m[10] * v.z + m[14] * v.w,
-        m[3] * v.x + m[7] * v.y + m[11] * v.z + m[15] * v.w);
+        kjb_fma(m[12], v.w, kjb_fma(m[8], v.z, kjb_fma(m[4], v.y, m[0] * v.x))),
+        kjb_fma(m[13], v.w, kjb_fma(m[9], v.z, kjb_fma(m[5], v.y, m[1] * v.x))),
+        kjb_fma(m[14], v.w, kjb_fma(m[10], v.z, kjb_fma(m[6], v.y, m[2] * v.x))),
+        kjb_fma(m[15], v.w, kjb_fma(m[11], v.z, kjb_fma(m[7], v.y, m[3] * v.x))));
 }
 // float3x3 stored as rows (HLSL float3x3(r0, r1, r2) constructor order)
 struct float3x3 { float3 r0, r1, r2; };
 inline float3 mul(const float3x3& M, float3 v) { return float3(dot(M.r0, v), dot(M.r1, v), dot(M.r2, v)); }
 // mul(v, M): row vector times matrix
 inline float3 mul(float3 v, const float3x3& M) {
-    return float3(v.x * M.r0.x + v.y * M.r1.x + v.z * M.r2.x,
-                  v.x * M.r0.y + v.y * M.r1.y + v.z * M.r2.y,
-                  v.x * M.r0.z + v.y * M.r1.z + v.z * M.r2.z);
+    return float3(kjb_fma(v.z, M.r2.x, kjb_fma(v.y, M.r1.x, v.x * M.r0.x)),
+                  kjb_fma(v.z, M.r2.y, kjb_fma(v.y, M.r1.y, v.x * M.r0.y)),
+                  kjb_fma(v.z, M.r2.z, kjb_fma(v.y, M.r1.z, v.x * M.r0.z)));
 }
 
 // ---------------------------------------------------------------- math_const.hlsl
