@@ -49,6 +49,16 @@ KJB_DEV bool intersect_leaf(const BvhTri* tris, uint32_t first, uint32_t count, 
     return false;
 }
 
+// min/max of the slab test: the result only steers the walk (boxes are conservative and the hit rule does not depend on the
+// topology), so the single-instruction FMNMX forms are used on the device — they differ from kjb_min/kjb_max only in the sign of a
+// zero result, which no comparison below can see.
+#if defined(__CUDA_ARCH__)
+#define KJB_SLAB_MIN fminf
+#define KJB_SLAB_MAX fmaxf
+#else
+#define KJB_SLAB_MIN kjb_min
+#define KJB_SLAB_MAX kjb_max
+#endif
 template <bool ANY_HIT>
 KJB_DEV HitInfo trace(const SceneView& sc, const Ray& r, bool cull_back) {
     HitInfo best; best.hit = false; best.t = r.tmax; best.u = 0; best.v = 0; best.gid = 0xffffffffu;
@@ -74,10 +84,10 @@ KJB_DEV HitInfo trace(const SceneView& sc, const Ray& r, bool cull_back) {
             const float c1loy = (n1.z - r.origin.y) * inv_dir.y, c1hiy = (n1.w - r.origin.y) * inv_dir.y;
             const float c1loz = (n2.z - r.origin.z) * inv_dir.z, c1hiz = (n2.w - r.origin.z) * inv_dir.z;
             const float tmax_cur = ANY_HIT ? r.tmax : best.t;
-            const float t0n = kjb_max(kjb_max(kjb_min(c0lox, c0hix), kjb_min(c0loy, c0hiy)), kjb_max(kjb_min(c0loz, c0hiz), r.tmin));
-            const float t0f = kjb_min(kjb_min(kjb_max(c0lox, c0hix), kjb_max(c0loy, c0hiy)), kjb_min(kjb_max(c0loz, c0hiz), tmax_cur));
-            const float t1n = kjb_max(kjb_max(kjb_min(c1lox, c1hix), kjb_min(c1loy, c1hiy)), kjb_max(kjb_min(c1loz, c1hiz), r.tmin));
-            const float t1f = kjb_min(kjb_min(kjb_max(c1lox, c1hix), kjb_max(c1loy, c1hiy)), kjb_min(kjb_max(c1loz, c1hiz), tmax_cur));
+            const float t0n = KJB_SLAB_MAX(KJB_SLAB_MAX(KJB_SLAB_MIN(c0lox, c0hix), KJB_SLAB_MIN(c0loy, c0hiy)), KJB_SLAB_MAX(KJB_SLAB_MIN(c0loz, c0hiz), r.tmin));
+            const float t0f = KJB_SLAB_MIN(KJB_SLAB_MIN(KJB_SLAB_MAX(c0lox, c0hix), KJB_SLAB_MAX(c0loy, c0hiy)), KJB_SLAB_MIN(KJB_SLAB_MAX(c0loz, c0hiz), tmax_cur));
+            const float t1n = KJB_SLAB_MAX(KJB_SLAB_MAX(KJB_SLAB_MIN(c1lox, c1hix), KJB_SLAB_MIN(c1loy, c1hiy)), KJB_SLAB_MAX(KJB_SLAB_MIN(c1loz, c1hiz), r.tmin));
+            const float t1f = KJB_SLAB_MIN(KJB_SLAB_MIN(KJB_SLAB_MAX(c1lox, c1hix), KJB_SLAB_MAX(c1loy, c1hiy)), KJB_SLAB_MIN(KJB_SLAB_MAX(c1loz, c1hiz), tmax_cur));
             const bool h0 = t0n <= t0f, h1 = t1n <= t1f;
             if (h0 && h1) {
                 const bool near0 = t0n <= t1n;
