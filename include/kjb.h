@@ -368,6 +368,12 @@ typedef struct kjb_rtdgi_restir_spatial_args {       /* "restir spatial", restir
 } kjb_rtdgi_restir_spatial_args;
 int kjb_pass_rtdgi_restir_spatial(kjb_context *ctx, const kjb_rtdgi_restir_spatial_args *a);
 
+typedef struct kjb_rtdgi_restir_check_args {         /* "restir check" (optional: RtdgiRenderer::use_raytraced_reservoir_visibility), restir_check.rgen.hlsl:10-15, rtdgi.rs:478-494 */
+    kjb_image half_depth_tex, temporal_reservoir_packed_tex, reservoir_input_tex;   /* reservoir_input_tex is read-write */
+    float gbuffer_tex_size[4];
+} kjb_rtdgi_restir_check_args;
+int kjb_pass_rtdgi_restir_check(kjb_context *ctx, const kjb_rtdgi_restir_check_args *a);
+
 typedef struct kjb_rtdgi_restir_resolve_args {       /* "restir resolve", restir_resolve.hlsl:16-31, rtdgi.rs:502-523 */
     kjb_image radiance_tex, reservoir_input_tex, gbuffer_tex, depth_tex, half_view_normal_tex, half_depth_tex,
               ssao_tex, candidate_radiance_tex, candidate_hit_tex, temporal_reservoir_packed_tex,

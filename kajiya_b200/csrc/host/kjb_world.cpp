@@ -690,6 +690,12 @@ static void rtdgi_render(kjb_world* w, kjb_image& reprojected_history_tex, kjb_i
         std::swap(reservoir_output_tex0, reservoir_output_tex1);
         reservoir_input_tex = reservoir_output_tex1;
     }
+    if (w->desc.use_raytraced_reservoir_visibility) {   // "restir check" (rtdgi.rs:478-494)
+        kjb_rtdgi_restir_check_args a{}; a.half_depth_tex = half_depth_tex; a.temporal_reservoir_packed_tex = temporal_reservoir_packed_tex; a.reservoir_input_tex = *reservoir_input_tex;
+        memcpy(a.gbuffer_tex_size, gbuffer_size, 16);
+        w->rows(th.spatial_last, 1);
+        RUN("restir check", kjb_pass_rtdgi_restir_check(ctx, &a));
+    }
     kjb_image& irradiance_output_tex = w->img("rtdgi.irradiance", W, H, KJB_FMT_RGBA16_FLOAT);
     {   // "restir resolve" (rtdgi.rs:502-523)
         kjb_rtdgi_restir_resolve_args a{};

@@ -419,6 +419,7 @@ struct ViewRayContext {
     KJB_DEV float3 ray_origin_ws() const { return xyz(ray_origin_ws_h) / ray_origin_ws_h.w; }
     KJB_DEV float3 ray_hit_vs() const { return xyz(ray_hit_vs_h) / ray_hit_vs_h.w; }
     KJB_DEV float3 ray_hit_ws() const { return xyz(ray_hit_ws_h) / ray_hit_ws_h.w; }
+    KJB_DEV float3 biased_secondary_ray_origin_ws() const { return ray_hit_ws() - ray_dir_ws() * (length(ray_hit_vs()) + length(ray_hit_ws())) * 1e-4f; }
     KJB_DEV float3 biased_secondary_ray_origin_ws_with_normal(float3 normal) const {
         const float3 hw = ray_hit_ws();
         const float3 ws_abs = vabs(hw);

@@ -538,6 +538,28 @@ KJB_KERNEL(256) k_rtdgi_restir_spatial(Globals g, Img reservoir_input_tex, Img h
     st_rg32u(reservoir_output_tex, x, y, reservoir.as_raw());
 }
 
+// ------------------------------------------------------------------ D8 restir_check.rgen.hlsl:21-66 (optional)
+KJB_KERNEL(128) k_rtdgi_restir_check(Globals g, Img half_depth_tex, Img temporal_reservoir_packed_tex, ImgW reservoir_input_tex, float4 gts, Rows kjb_rows) {
+    KJB_PX; if (x >= reservoir_input_tex.w || y >= reservoir_input_tex.h) return;
+    const kjb_view_constants& vc = g.fc.view_constants;
+    const int2 hso = halfres_subsample_offset(g.fc.frame_index);
+    const float s4[4] = {gts.x, gts.y, gts.z, gts.w};
+    const float depth = ld_r32f(half_depth_tex, x, y);
+    const ViewRayContext vrc = ViewRayContext::from_uv_and_biased_depth(vc, get_uv(x * 2 + hso.x, y * 2 + hso.y, s4), depth);
+    Reservoir r = Reservoir::from_raw(ld_rg32u(as_ro(reservoir_input_tex), x, y));
+    const int spx_x = int(r.payload & 0xffffu), spx_y = int(r.payload >> 16);
+    const TemporalReservoirOutput spx_packed = tro_from_raw(ld_rgba32u(temporal_reservoir_packed_tex, spx_x, spx_y));
+    const ViewRayContext spx_ctx = ViewRayContext::from_uv_and_depth(vc, get_uv(spx_x * 2 + hso.x, spx_y * 2 + hso.y, s4), spx_packed.depth);
+    const float3 spx_pos_ws = spx_ctx.ray_hit_ws();
+    const float3 hit_ws = spx_packed.ray_hit_offset_ws + spx_pos_ws;
+    const float3 trace_origin_ws = vrc.biased_secondary_ray_origin_ws();
+    const float3 trace_vec = hit_ws - trace_origin_ws;
+    if (rt_is_shadowed(g, trace_origin_ws, normalize(trace_vec), 0.0f, kjb_min(5 * length(spx_pos_ws - trace_origin_ws), length(trace_vec) * 0.999f))) {
+        r.W = 0;
+        st_rg32u(reservoir_input_tex, x, y, r.as_raw());
+    }
+}
+
 // ------------------------------------------------------------------ D9 restir_resolve.hlsl:42-205
 KJB_DEV float ggx_ndf_unnorm(float a2, float cos_theta) { const float ds = cos_theta * cos_theta * (a2 - 1.0f) + 1.0f; return a2 / (ds * ds); }
 struct ResolveImgs { Img radiance_tex, reservoir_input_tex, gbuffer_tex, depth_tex, half_view_normal_tex, half_depth_tex, ssao_tex, candidate_radiance_tex, candidate_hit_tex, temporal_reservoir_packed_tex; };
@@ -860,6 +882,15 @@ int kjb_pass_rtdgi_restir_spatial(kjb_context* c, const kjb_rtdgi_restir_spatial
     KJB_LAUNCH(c, k_rtdgi_restir_spatial, KJB_GRID2D(W, H, 32, 8), c->g, img_ro(a->reservoir_input_tex), img_ro(a->half_view_normal_tex), img_ro(a->half_depth_tex), img_ro(a->half_ssao_tex),
                img_ro(a->temporal_reservoir_packed_tex), img_rw(a->reservoir_output_tex), F4A(a->gbuffer_tex_size), F4A(a->output_tex_size), a->spatial_reuse_pass_idx, a->perform_occlusion_raymarch,
                a->occlusion_raymarch_importance_only);
+    KJB_PASS_EPILOGUE(c, P);
+}
+int kjb_pass_rtdgi_restir_check(kjb_context* c, const kjb_rtdgi_restir_check_args* a) {
+    const char* P = "restir check"; const uint32_t W = a->reservoir_input_tex.width, H = a->reservoir_input_tex.height;
+    CHK(a->reservoir_input_tex, KJB_FMT_RG32_UINT, "reservoir_input_tex"); CHKE(a->half_depth_tex, KJB_FMT_R32_FLOAT, "half_depth_tex", W, H);
+    CHKE(a->temporal_reservoir_packed_tex, KJB_FMT_RGBA32_UINT, "temporal_reservoir_packed_tex", W, H);
+    if (!c->tlas_valid) return c->fail("restir check: no acceleration structure (call kjb_rebuild_tlas)");
+    KJB_ROWS(c, H);
+    KJB_LAUNCH(c, k_rtdgi_restir_check, KJB_GRID2D(W, H, 16, 8), c->g, img_ro(a->half_depth_tex), img_ro(a->temporal_reservoir_packed_tex), img_rw(a->reservoir_input_tex), F4A(a->gbuffer_tex_size));
     KJB_PASS_EPILOGUE(c, P);
 }
 int kjb_pass_rtdgi_restir_resolve(kjb_context* c, const kjb_rtdgi_restir_resolve_args* a) {

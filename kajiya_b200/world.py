@@ -11,14 +11,14 @@ def quat_from_rotation_x(angle):
 
 class World:
     def __init__(self, lib, width, height, device=0, spatial_reuse_pass_count=2, enable_ircache=False, enable_rtr=False, enable_taa=False,
-                 upscale=None, tile=None):
+                 upscale=None, tile=None, use_raytraced_reservoir_visibility=False):
         self.lib = lib
         self.d = lib.dll
         self.ctx = C.c_void_p()
         if self.d.kjb_create(device, C.byref(self.ctx)):
             raise KjbError("kjb_create failed: " + (self.d.kjb_last_error(None) or b"").decode())
         tile_rank, tile_count = tile if tile else (0, 0)
-        desc = WorldDesc(width, height, (upscale or (0, 0))[0], (upscale or (0, 0))[1], spatial_reuse_pass_count, 0,
+        desc = WorldDesc(width, height, (upscale or (0, 0))[0], (upscale or (0, 0))[1], spatial_reuse_pass_count, int(use_raytraced_reservoir_visibility),
                          int(enable_ircache), int(enable_rtr), int(enable_taa), 0, 0, tile_rank, tile_count)
         self.w = C.c_void_p()
         self._check(self.d.kjb_world_create(self.ctx, C.byref(desc), C.byref(self.w)))

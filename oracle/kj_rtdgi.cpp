@@ -674,6 +674,36 @@ int kjb_pass_rtdgi_restir_spatial(kjb_context* ctx, const kjb_rtdgi_restir_spati
     return 0;
 }
 
+// ------------------------------------------------------------------ D8: rtdgi/restir_check.rgen.hlsl:21-66 (optional pass)
+int kjb_pass_rtdgi_restir_check(kjb_context* ctx, const kjb_rtdgi_restir_check_args* a) {
+    const Globals& g = ctx->g; const kjb_view_constants& vc = g.fc.view_constants;
+    Img half_depth_tex(a->half_depth_tex), temporal_reservoir_packed_tex(a->temporal_reservoir_packed_tex), reservoir_input_tex(a->reservoir_input_tex);
+    const float4 gbuffer_tex_size = f4(a->gbuffer_tex_size);
+    const int W = reservoir_input_tex.w(), H = reservoir_input_tex.h();
+    const int2 hi_px_offset = halfres_subsample_offset(g.fc.frame_index);
+    pass_rows(ctx, H, [&](int y) { for (int x = 0; x < W; ++x) {
+        const int2 px(x, y); const int2 hi_px = px * 2 + hi_px_offset;
+        const float depth = half_depth_tex.load(px).x;
+        const float2 uv = get_uv(hi_px, gbuffer_tex_size);
+        const ViewRayContext view_ray_context = ViewRayContext::from_uv_and_biased_depth(vc, uv, depth);
+        uint4 raw = reservoir_input_tex.load_u(px);
+        Reservoir1spp r = Reservoir1spp::from_raw(uint2(raw.x, raw.y));
+        const int2 spx = reservoir_payload_to_px(r.payload);
+        const TemporalReservoirOutput spx_packed = TemporalReservoirOutput::from_raw(temporal_reservoir_packed_tex.load_u(spx));
+        const float2 spx_uv = get_uv(spx * 2 + hi_px_offset, gbuffer_tex_size);
+        const ViewRayContext spx_ray_ctx = ViewRayContext::from_uv_and_depth(vc, spx_uv, spx_packed.depth);
+        const float3 hit_ws = spx_packed.ray_hit_offset_ws + spx_ray_ctx.ray_hit_ws();
+        const float3 spx_pos_ws = spx_ray_ctx.ray_hit_ws();
+        const float3 trace_origin_ws = view_ray_context.biased_secondary_ray_origin_ws();
+        const float3 trace_vec = hit_ws - trace_origin_ws;
+        if (rt_is_shadowed(ctx->scene, trace_origin_ws, normalize(trace_vec), 0.0f, min(5 * length(spx_pos_ws - trace_origin_ws), length(trace_vec) * 0.999f))) {
+            r.W = 0;
+            uint2 rr = r.as_raw(); reservoir_input_tex.store_u(x, y, uint4(rr.x, rr.y, 0, 0));
+        }
+    } }, ctx->num_threads);
+    return 0;
+}
+
 // ------------------------------------------------------------------ D9: rtdgi/restir_resolve.hlsl:42-205
 static float ggx_ndf_unnorm(float a2, float cos_theta) { float ds = cos_theta * cos_theta * (a2 - 1.0f) + 1.0f; return a2 / (ds * ds); }
 

@@ -28,6 +28,7 @@ struct ViewRayContext {
     float3 ray_hit_vs() const { return ray_hit_vs_h.xyz() / ray_hit_vs_h.w; }
     float3 ray_hit_ws() const { return ray_hit_ws_h.xyz() / ray_hit_ws_h.w; }
 
+    float3 biased_secondary_ray_origin_ws() const { return ray_hit_ws() - ray_dir_ws() * (length(ray_hit_vs()) + length(ray_hit_ws())) * 1e-4f; }   // frame_constants.hlsl:133-135
     float3 biased_secondary_ray_origin_ws_with_normal(float3 normal) const {   // frame_constants.hlsl:140-144
         float3 ws_abs = abs(ray_hit_ws());
         float max_comp = max(max(ws_abs.x, ws_abs.y), max(ws_abs.z, -ray_hit_vs().z));

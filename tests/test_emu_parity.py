@@ -159,3 +159,13 @@ def test_streaming_frames_match_blocking_frames(emu_lib):
     for i in range(5):
         assert np.array_equal(res_b[i].view(np.uint16), res_s[i].view(np.uint16)), i
     assert {"in0.gbuffer", "in1.gbuffer", "result.stage0", "result.stage1"} <= set(wc.image_names())
+
+
+def test_restir_check_optional_pass(oracle_lib, emu_lib):
+    """RtdgiRenderer::use_raytraced_reservoir_visibility: the optional "restir check" ray pass + importance-only ray march."""
+    scene, view = scenes.cornell_box()
+    wa, wb, report = parity.run_lockstep(oracle_lib, emu_lib, scene, view, 72, 44, 5, use_raytraced_reservoir_visibility=True)
+    _clean(report)
+    wc = parity.make_world(emu_lib, scene, 72, 44)
+    for _ in range(5): wc.render_frame(**view)
+    assert parity.compare_images(wb, wc, names=["rtdgi.irradiance"])   # the pass does change the result
