@@ -457,6 +457,11 @@ KJB_KERNEL(256) k_rtr_resolve(Globals g, RtrResolveImgs t, float4 ots, float rad
     const float ang_offset = float(g.fc.frame_index * 59u % 128u) * KJB_PLASTIC;
     const float RADIUS_INC_ON_FAIL = 0.25f;
     const int2 hso = halfres_subsample_offset(g.fc.frame_index); (void)hso;
+    // per-pixel invariants of the tap loop
+    const float origin_bias_lerp = kjb_lerp(1.0f, RTR_NEIGHBOR_RAY_ORIGIN_CENTER_BIAS, 0.4f * kjb_min(1.0f, 3 * kjb_sqrt(gbuffer.roughness)));
+    const float pdf_lerp_t = kjb_smoothstep(0.4f, 0.7f, kjb_sqrt(gbuffer.roughness)) * kjb_smoothstep(0.0f, 0.1f, ray_len_avg / eye_to_surf_dist);
+    const float depth_rej_scale = kjb_max(1e-10f, kernel_size_ws), depth_rej_nz = -kjb_max(0.3f, normal_vs.z);
+    const float squished_surf_to_hit = exponential_squish(surf_to_hit_dist, ray_squish_scale);
     float sample_radius_accum = 1;
     for (int sample_i = 1; sample_i <= 8; ++sample_i, sample_radius_accum += RADIUS_INC_ON_FAIL) {
         const bool is_center_sample = sample_i == 8;
@@ -496,7 +501,7 @@ KJB_KERNEL(256) k_rtr_resolve(Globals g, RtrResolveImgs t, float4 ots, float rad
         const float center_to_hit_dist = length(center_to_hit_vs);
         const float sample_to_hit_dist = length(sample_hit_ws - sample_origin_ws);
         {   // RTR_USE_BULLSHIT_TO_FIX_EDGE_HALOS
-            const float wat = length(sample_hit_vs - vlerp(refl_ray_origin_vs, sample_origin_vs, kjb_lerp(1.0f, RTR_NEIGHBOR_RAY_ORIGIN_CENTER_BIAS, 0.4f * kjb_min(1.0f, 3 * kjb_sqrt(gbuffer.roughness)))));
+            const float wat = length(sample_hit_vs - vlerp(refl_ray_origin_vs, sample_origin_vs, origin_bias_lerp));
             pdf0_mult *= kjb_max(1e-5f, kjb_pow(wat / sample_to_hit_dist, 2.0f));
             pdf1_mult *= kjb_max(1.0f, kjb_pow(center_to_hit_dist / sample_to_hit_dist, 2.0f));
         }
@@ -504,8 +509,8 @@ KJB_KERNEL(256) k_rtr_resolve(Globals g, RtrResolveImgs t, float4 ots, float rad
         if (wi.z < 1e-5f) continue;
         rejection_bias *= dot(normal_vs, sample_normal_vs) > 0.7f ? 1.0f : 0.0f;
         {
-            const float depth_diff = kjb_abs(refl_ray_origin_vs.z - sample_origin_vs.z) / kjb_max(1e-10f, kernel_size_ws);
-            rejection_bias *= kjb_exp2(-kjb_max(0.3f, normal_vs.z) * depth_diff * depth_diff);
+            const float depth_diff = kjb_abs(refl_ray_origin_vs.z - sample_origin_vs.z) / depth_rej_scale;
+            rejection_bias *= kjb_exp2(depth_rej_nz * depth_diff * depth_diff);
         }
         const float3 surface_offset = sample_origin_vs - refl_ray_origin_vs;
         if (dot(center_to_hit_vs, normal_vs) * 0.2f / length(center_to_hit_vs) < dot(surface_offset, normal_vs) / length(surface_offset)) rejection_bias *= is_center_sample ? 1.0f : 0.0f;   // USE_APPROXIMATE_SAMPLE_SHADOWING
@@ -517,7 +522,6 @@ KJB_KERNEL(256) k_rtr_resolve(Globals g, RtrResolveImgs t, float4 ots, float rad
             const float bent_cos_theta = kjb_min(sample_cos_theta, cos_theta * 1.25f);
             const float sample_ray_ndf = ggx_ndf(a2, bent_cos_theta), center_ndf = ggx_ndf(a2, cos_theta);
             const float bent_sample_pdf0 = spec.pdf * sample_ray_ndf / center_ndf;
-            const float pdf_lerp_t = kjb_smoothstep(0.4f, 0.7f, kjb_sqrt(gbuffer.roughness)) * kjb_smoothstep(0.0f, 0.1f, ray_len_avg / eye_to_surf_dist);
             const float3 pdfs[2] = {f3(kjb_min(bent_sample_pdf0, RTR_RESTIR_MAX_PDF_CLAMP) * 1.0f, neighbor_sampling_pdf * pdf0_mult, 1 - pdf_lerp_t),
                                     f3(kjb_min(spec.pdf, RTR_RESTIR_MAX_PDF_CLAMP), neighbor_sampling_pdf * pdf1_mult, pdf_lerp_t)};
             for (uint32_t pdf_i = 0; pdf_i < 2u; ++pdf_i) {
@@ -527,7 +531,7 @@ KJB_KERNEL(256) k_rtr_resolve(Globals g, RtrResolveImgs t, float4 ots, float rad
                 contrib_accum += f4(sample_radiance * bent_sample_pdf / nsp * spec.value_over_pdf, 1) * contrib_wt * pdf_influence;
             }
         }
-        ray_len_accum += exponential_squish(surf_to_hit_dist, ray_squish_scale) * contrib_wt;
+        ray_len_accum += squished_surf_to_hit * contrib_wt;
         sample_radius_accum += 1.0f - RADIUS_INC_ON_FAIL;
     }
     const float contrib_norm_factor = kjb_max(1e-14f, contrib_accum.w);

@@ -69,9 +69,13 @@ KJB_DEV HitInfo trace(const SceneView& sc, const Ray& r, bool cull_back) {
           && r.tmin == r.tmin && r.tmax == r.tmax)) return best;
     const float3 inv_dir = f3(1.0f / r.dir.x, 1.0f / r.dir.y, 1.0f / r.dir.z);
     int stack[64]; int sp = 0;
-    int cur = sc.root;   // inner node index (>= 0) or an encoded leaf when the whole scene is one leaf
+    int cur = sc.root;   // inner node index (>= 0) or an encoded leaf (< 0) when the whole scene is one leaf
+    // "while-while" walk: every lane first descends through inner nodes until it holds a leaf (or runs out of work), then the lanes
+    // that hold leaves intersect them together — fewer mixed node/leaf iterations per warp than a single interleaved loop.
+    // The visiting order per ray is unchanged (near child first, far child pushed), hence so is the result.
+    const int DONE = 0x7fffffff;
     for (;;) {
-        if (cur >= 0) {
+        while (cur >= 0 && cur != DONE) {
             const float* np = reinterpret_cast<const float*>(sc.nodes + cur);
             const float4 n0 = ldg4(np), n1 = ldg4(np + 4), n2 = ldg4(np + 8);
             const int2 ch = *reinterpret_cast<const int2*>(np + 12);
@@ -93,15 +97,16 @@ KJB_DEV HitInfo trace(const SceneView& sc, const Ray& r, bool cull_back) {
                 const bool near0 = t0n <= t1n;
                 stack[sp++] = near0 ? ch.y : ch.x;
                 cur = near0 ? ch.x : ch.y;
-                continue;
-            } else if (h0) { cur = ch.x; continue; }
-            else if (h1) { cur = ch.y; continue; }
-        } else {
+            } else if (h0) cur = ch.x;
+            else if (h1) cur = ch.y;
+            else cur = sp ? stack[--sp] : DONE;
+        }
+        if (cur == DONE) break;
+        {
             const uint32_t enc = uint32_t(~cur);
             if (intersect_leaf<ANY_HIT>(sc.tris, enc >> 3, (enc & 7u) + 1u, r, cull_back, best)) { best.hit = true; return best; }
         }
-        if (sp == 0) break;
-        cur = stack[--sp];
+        cur = sp ? stack[--sp] : DONE;
     }
     return best;
 }
