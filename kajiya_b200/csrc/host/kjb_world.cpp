@@ -293,6 +293,12 @@ int kjb_world_add_instance(kjb_world* w, uint32_t mesh, const float transform[12
     return 0;
 }
 
+int kjb_world_set_instance_transform(kjb_world* w, uint32_t handle, const float transform[12]) {
+    if (handle >= w->instances.size()) return 1;
+    memcpy(w->instances[handle].transform, transform, sizeof(float) * 12);
+    return 0;
+}
+
 int kjb_world_set_blue_noise(kjb_world* w, const uint8_t* rgba) {
     kjb_image& bn = w->img("lut.blue_noise", 256, 256, KJB_FMT_RGBA8_UNORM);
     int rc = kjb_image_upload(w->ctx, &bn, rgba);

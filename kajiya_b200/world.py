@@ -96,6 +96,10 @@ class World:
         self._check(self.d.kjb_world_add_instance(self.w, mesh, C.byref(t), C.byref(h)))
         return h.value
 
+    def set_instance_transform(self, handle, transform):
+        t = (C.c_float * 12)(*np.asarray(transform, np.float32).reshape(-1)[:12])
+        self._check(self.d.kjb_world_set_instance_transform(self.w, handle, C.byref(t)))
+
     def set_blue_noise(self, rgba8):
         a = np.ascontiguousarray(rgba8, np.uint8); assert a.size == 256 * 256 * 4
         self._check(self.d.kjb_world_set_blue_noise(self.w, a.ctypes.data))

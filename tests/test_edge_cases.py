@@ -1,0 +1,90 @@
+"""Edge cases of the pass API: empty scene, degenerate extents, error behaviour (same code in the CUDA build — exercised here through
+the CPU builds), instanced + moving geometry."""
+import ctypes as C
+import numpy as np, pytest
+import parity
+from kajiya_b200 import scenes
+from kajiya_b200.world import World
+from kajiya_b200._abi import Image, KjbError, FMT
+
+
+def _empty_world(lib, w, h, **kw):
+    wd = World(lib, w, h, **kw)
+    wd.set_blue_noise(scenes.blue_noise()); wd.set_spatial_resolve_offsets(scenes.spatial_resolve_offsets())
+    return wd
+
+
+def test_empty_scene_is_all_sky(oracle_lib, emu_lib):
+    """No meshes at all: every ray misses, every pass takes its depth == 0 branch; the full path must still run and agree."""
+    _, view = scenes.cornell_box()
+    kw = dict(enable_ircache=True, enable_rtr=True, enable_taa=True)
+    wa, wb = _empty_world(oracle_lib, 40, 24, **kw), _empty_world(emu_lib, 40, 24, **kw)
+    for f in range(4):
+        wa.render_frame(**view); wb.render_frame(**view)
+        assert not parity.compare_images(wa, wb), f
+    assert (wb.image("depth") == 0).all()
+    assert (wb.image("rtdgi.spatial_filtered")[..., :3] == 0).all()
+    assert wb.image("ircache.meta_buf").ravel()[3] == 0          # nothing was allocated
+
+
+@pytest.mark.parametrize("extent", [(1, 1), (2, 2), (3, 5), (17, 2)])
+def test_degenerate_extents(oracle_lib, emu_lib, extent):
+    """1x1 .. ragged tiny frames: half-res = div_up, blocks mostly out of range, stencils all clamp/zero paths."""
+    scene, view = scenes.cornell_box()
+    _, _, report = parity.run_lockstep(oracle_lib, emu_lib, scene, view, extent[0], extent[1], 4, enable_rtr=True, enable_taa=True)
+    assert not [b for fr in report for b in fr]
+
+
+def test_pass_argument_errors_are_reported(emu_lib):
+    """Every entry point validates formats/extents and reports through the return code + kjb_last_error (no exceptions across the ABI)."""
+    d = emu_lib.dll
+    ctx = C.c_void_p(); assert d.kjb_create(0, C.byref(ctx)) == 0
+    img = Image()
+    assert d.kjb_image_alloc(ctx, 8, 8, 1, FMT["RGBA16_FLOAT"], C.byref(img)) == 0
+    assert d.kjb_image_alloc(ctx, 0, 8, 1, FMT["RGBA16_FLOAT"], C.byref(Image())) != 0
+    assert b"bad format or extent" in d.kjb_last_error(ctx)
+
+    class ReprojArgs(C.Structure):   # kjb_rtdgi_reproject_args
+        _fields_ = [("input_tex", Image), ("reprojection_tex", Image), ("output_tex", Image), ("output_tex_size", C.c_float * 4)]
+    a = ReprojArgs(); a.input_tex = img; a.output_tex = img            # reprojection_tex left NULL
+    d.kjb_pass_rtdgi_reproject.restype = C.c_int; d.kjb_pass_rtdgi_reproject.argtypes = [C.c_void_p, C.c_void_p]
+    assert d.kjb_pass_rtdgi_reproject(ctx, C.byref(a)) != 0
+    assert b"rtdgi reproject" in d.kjb_last_error(ctx) and b"null" in d.kjb_last_error(ctx)
+    wrong = Image(); assert d.kjb_image_alloc(ctx, 8, 8, 1, FMT["R32_FLOAT"], C.byref(wrong)) == 0
+    a.reprojection_tex = wrong
+    assert d.kjb_pass_rtdgi_reproject(ctx, C.byref(a)) != 0
+    assert b"format" in d.kjb_last_error(ctx)
+    d.kjb_destroy(ctx)
+
+
+def test_world_refuses_unsupported_combinations(emu_lib):
+    with pytest.raises(KjbError):
+        World(emu_lib, 64, 64, enable_ircache=True, tile=(0, 2))      # the cache does not shard by rows
+    w = World(emu_lib, 32, 32, enable_rtr=True)
+    w.set_blue_noise(scenes.blue_noise())
+    _, view = scenes.cornell_box()
+    with pytest.raises(KjbError):
+        w.render_frame(**view)                                         # rtr needs SPATIAL_RESOLVE_OFFSETS from the host
+
+
+def test_instanced_moving_geometry(oracle_lib, emu_lib):
+    """Two instances of one mesh, one of them moving every frame: "rebuild tlas" re-flattens, velocities are non-zero, histories
+    reproject — all bit for bit."""
+    scene, view = scenes.cornell_box()
+    mesh, transforms = scene[0]
+    worlds = []
+    for lib in (oracle_lib, emu_lib):
+        w = World(lib, 72, 44, enable_rtr=True, enable_taa=True)
+        h = w.add_mesh(mesh)
+        w.add_instance(h, transforms[0])
+        w.set_blue_noise(scenes.blue_noise()); w.set_spatial_resolve_offsets(scenes.spatial_resolve_offsets())
+        worlds.append((w, h))
+    small = np.array([[0.25, 0, 0, 0.1], [0, 0.25, 0, 0.3], [0, 0, 0.25, 0.2]], np.float32)
+    ids = [w.add_instance(h, small) for w, h in worlds]
+    for f in range(5):
+        for (w, h), iid in zip(worlds, ids):
+            if hasattr(w, "set_instance_transform"):
+                t = small.copy(); t[0, 3] += 0.05 * f
+                w.set_instance_transform(iid, t)
+            w.render_frame(**view)
+        assert not parity.compare_images(worlds[0][0], worlds[1][0]), f
