@@ -113,23 +113,37 @@ KJB_KERNEL(32) k_ircache_age_serial(uint32_t* meta, uint32_t* gm, uint32_t* entr
 }
 
 // ------------------------------------------------------------------ I5 prefix_scan/*.hlsl: inclusive scan of <= 64 Ki u32 in one CTA
-// 1024 threads x 64 consecutive elements each (256 KB, L2-resident): per-thread serial sums, one shared-memory scan of the
-// 1024 partials, per-thread serial rescan.  Replaces the reference's 3-pass 1 Mi-element scan (prefix_scan.rs:10-39).
+// Replaces the reference's 3-pass 1 Mi-element scan (prefix_scan.rs:10-39).  The array is walked in chunks of 8192: coalesced load into
+// shared memory, each of the 1024 threads scans 8 consecutive values, a Hillis-Steele scan of the 1024 partials, carry from the
+// previous chunk, coalesced store.
 KJB_KERNEL(1024) k_inclusive_prefix_scan(uint32_t* d, uint32_t n, Rows kjb_rows) {
+    __shared__ uint32_t chunk[8192];
     __shared__ uint32_t partial[1024];
-    const uint32_t t = threadIdx.x, per = (n + 1023u) / 1024u, b0 = t * per, b1 = (b0 + per < n) ? b0 + per : n;
-    uint32_t s = 0;
-    for (uint32_t i = b0; i < b1; ++i) s += d[i];
-    partial[t] = s;
+    __shared__ uint32_t carry_s;
+    const uint32_t t = threadIdx.x;
+    if (t == 0) carry_s = 0;
     __syncthreads();
-    for (uint32_t off = 1; off < 1024u; off <<= 1) {
-        const uint32_t v = t >= off ? partial[t - off] : 0u;
+    for (uint32_t base = 0; base < n; base += 8192u) {
+        for (uint32_t k = 0; k < 8u; ++k) { const uint32_t i = base + k * 1024u + t; chunk[k * 1024u + t] = i < n ? d[i] : 0u; }
         __syncthreads();
-        partial[t] += v;
+        uint32_t s = 0;
+        for (uint32_t k = 0; k < 8u; ++k) { s += chunk[t * 8u + k]; chunk[t * 8u + k] = s; }   // inclusive within the thread's 8 values
+        partial[t] = s;
+        __syncthreads();
+        for (uint32_t off = 1; off < 1024u; off <<= 1) {
+            const uint32_t v = t >= off ? partial[t - off] : 0u;
+            __syncthreads();
+            partial[t] += v;
+            __syncthreads();
+        }
+        const uint32_t before = (t ? partial[t - 1] : 0u) + carry_s;
+        for (uint32_t k = 0; k < 8u; ++k) chunk[t * 8u + k] += before;
+        __syncthreads();
+        for (uint32_t k = 0; k < 8u; ++k) { const uint32_t i = base + k * 1024u + t; if (i < n) d[i] = chunk[k * 1024u + t]; }
+        __syncthreads();
+        if (t == 0) carry_s += partial[1023];
         __syncthreads();
     }
-    uint32_t acc = t ? partial[t - 1] : 0u;
-    for (uint32_t i = b0; i < b1; ++i) { acc += d[i]; d[i] = acc; }
 }
 
 // ------------------------------------------------------------------ I6 ircache_compact_entries.hlsl
