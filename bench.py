@@ -38,6 +38,14 @@ PASS_BYTES = {
     # rtr (44 + 45 + 152 Hh; 36 F + 60 Hh; 52 F + 1 Hh; 20 F)
     "reflection trace": ("Hh", 44), "reflection validate": ("Hh", 45), "rtr restir temporal": ("Hh", 152), "reflection resolve": ("F+Hh", (36, 60)),
     "reflection temporal": ("F+Hh", (52, 1)), "reflection cleanup": ("F", 20),
+    # taa (80 O + 120 I in total; split per pass from the images each kernel binds, O = I without upscaling)
+    "reproject taa": ("F", 32), "taa filter input": ("F", 28), "taa filter history": ("F", 16), "taa input prob": ("F", 40), "taa prob filter": ("F", 4),
+    "taa prob filter2": ("F", 4), "taa": ("F", 76),
+    # irradiance cache (6.3 MB of grid + 1548 B per live entry; the entry count lives on the device, so only the fixed part is
+    # charged here) and the other small passes of the frame
+    "scroll cascades": ("const", 6291456), "age ircache entries": ("const", 0), "_prefix scan": ("const", 524288), "ircache compact": ("const", 0), "_ircache dispatch args": ("const", 0),
+    "ircache reset": ("const", 0), "ircache trace access": ("const", 0), "ircache validate": ("const", 0), "ircache trace": ("const", 0), "ircache sum": ("const", 0),
+    "restir check": ("Hh", 28), "reprojection map": ("F", 28), "copy depth": ("F", 8),
 }
 # DRAM bytes per launch of each kernel, from one `ncu --set full` capture of the default workload (profiles/r01c_full_summary.csv:
 # dram__bytes_read.sum + dram__bytes_write.sum).  Far below the algorithmic bytes: the frame's working set stays in the 126 MB L2.
@@ -49,6 +57,8 @@ def pass_bytes(label, F, Hh, validation_frame_fraction=1.0 / 3.0):
     kind, b = PASS_BYTES[label]
     if label == "rtdgi validate":
         return Hh * (5 + 61 * validation_frame_fraction)
+    if kind == "const":
+        return b
     if kind == "F":
         return F * b
     if kind == "Hh":
