@@ -483,13 +483,16 @@ static int tile_exchange(kjb_world* w, const std::vector<XchgItem>& items) {
         const uint32_t k = std::min(it.border, b1 - b0);
         out[0][0] = b0; out[0][1] = b0 + k; out[1][0] = b1 - k; out[1][1] = b1;
     };
-    // pack
+    // pack (one batched launch)
+    std::vector<kjb_copy_desc> copies;
     for (size_t i = 0; i < items.size(); ++i) {
         const uint64_t row_bytes = uint64_t(items[i].img.width) * kjb_format_texel_bytes(items[i].img.format);
         uint32_t st[2][2]; strips_of(w->trank, items[i], st);
         for (int k = 0; k < (items[i].border ? 2 : 1); ++k)
-            if (kjb_memcpy_d2d(ctx, (char*)w->xchg_send.data + off[i] + strip_bytes[i] * k, (const char*)items[i].img.data + row_bytes * st[k][0], row_bytes * (st[k][1] - st[k][0]))) return 1;
+            copies.push_back({(char*)w->xchg_send.data + off[i] + strip_bytes[i] * k, (const char*)items[i].img.data + row_bytes * st[k][0], row_bytes * (st[k][1] - st[k][0])});
     }
+    if (kjb_memcpy_d2d_batch(ctx, copies.data(), uint32_t(copies.size()))) return 1;
+    copies.clear();
     if (kjb_allgather(ctx, w->xchg_send.data, w->xchg_recv.data, total)) return 1;
     // unpack what this rank reads next frame: its band grown by `border` rows (everything for whole-band items)
     for (uint32_t r = 0; r < n; ++r) {
@@ -511,11 +514,11 @@ static int tile_exchange(kjb_world* w, const std::vector<XchgItem>& items) {
                 uint32_t a = std::max(st[k][0], iv[v][0]), b = std::min(st[k][1], iv[v][1]);
                 if (k == 1 && items[i].border) a = std::max(a, st[0][1]);   // rows already delivered by the top strip (band <= 2*border)
                 if (a >= b) continue;
-                if (kjb_memcpy_d2d(ctx, (char*)items[i].img.data + row_bytes * a, base + off[i] + strip_bytes[i] * k + row_bytes * (a - st[k][0]), row_bytes * (b - a))) return 1;
+                copies.push_back({(char*)items[i].img.data + row_bytes * a, base + off[i] + strip_bytes[i] * k + row_bytes * (a - st[k][0]), row_bytes * (b - a)});
             }
         }
     }
-    return 0;
+    return kjb_memcpy_d2d_batch(ctx, copies.data(), uint32_t(copies.size()));   // unpack (one batched launch per 96 strips)
 }
 
 // ---------------------------------------------------------------- RtdgiRenderer::render (rtdgi.rs:173-554)

@@ -35,6 +35,23 @@ struct NcclApi {
 #endif
 }  // namespace
 
+// ---- batched device-to-device copy: blockIdx.y selects the copy, KJB_COPY_CTAS CTAs stride over it with 16-byte accesses when
+// both ends and the size allow, bytes otherwise
+#define KJB_COPY_BATCH 96u
+#define KJB_COPY_CTAS 24u
+struct CopyBatch { kjb_copy_desc d[KJB_COPY_BATCH]; uint32_t count; };
+KJB_KERNEL(256) k_copy_batch(CopyBatch b, kjb::Rows kjb_rows) {
+    const kjb_copy_desc cd = b.d[blockIdx.y];
+    const uint64_t tid = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x, nthreads = uint64_t(gridDim.x) * blockDim.x;
+    if (((uintptr_t(cd.dst) | uintptr_t(cd.src) | cd.bytes) & 15u) == 0) {
+        const uint4* s = reinterpret_cast<const uint4*>(cd.src); uint4* d = reinterpret_cast<uint4*>(cd.dst);
+        for (uint64_t i = tid; i < cd.bytes / 16; i += nthreads) d[i] = s[i];
+    } else {
+        const uint8_t* s = reinterpret_cast<const uint8_t*>(cd.src); uint8_t* d = reinterpret_cast<uint8_t*>(cd.dst);
+        for (uint64_t i = tid; i < cd.bytes; i += nthreads) d[i] = s[i];
+    }
+}
+
 extern "C" {
 
 int kjb_comm_nccl_unique_id(void* out) {
@@ -73,5 +90,17 @@ int kjb_allgather(kjb_context* c, const void* send, void* recv, uint64_t bytes) 
     return c->ag_fn(c->ag_user, send, recv, bytes);
 }
 int kjb_memcpy_d2d(kjb_context* c, void* dst, const void* src, uint64_t bytes) { return dev_d2d(c, dst, src, bytes); }
+int kjb_memcpy_d2d_batch(kjb_context* c, const kjb_copy_desc* copies, uint32_t count) {
+    const kjb::Rows kjb__rows = {0, 1};
+    for (uint32_t i0 = 0; i0 < count; i0 += KJB_COPY_BATCH) {
+        CopyBatch b; b.count = count - i0 < KJB_COPY_BATCH ? count - i0 : KJB_COPY_BATCH;
+        bool any = false;
+        for (uint32_t i = 0; i < b.count; ++i) { b.d[i] = copies[i0 + i]; any = any || copies[i0 + i].bytes; }
+        if (!any) continue;
+        KJB_LAUNCH(c, k_copy_batch, KJB_DIMS(dim3(KJB_COPY_CTAS, b.count), dim3(256)), b);
+    }
+    const char* e = dev_check(c); if (e) return c->fail(std::string("kjb_memcpy_d2d_batch: ") + e);
+    return 0;
+}
 
 }  // extern "C"
