@@ -185,9 +185,8 @@ def run_cuda(args):
         w.render_frame(replay_slot=(i % nslots) + 1, **view)
 
     # e2e: every step hands the frame's G-buffer inputs over as pinned HOST buffers and receives the result in a pinned host buffer.
-    # Streaming mode (kjb_world.h): uploads, passes and downloads run on three queues, two frames in flight; a tiled (multi-GPU)
-    # world falls back to the blocking call.
-    streaming = world_size == 1 and not args.no_streaming
+    # Streaming mode (kjb_world.h): uploads, passes and downloads run on three queues, two frames in flight.
+    streaming = not args.no_streaming
     def step_e2e(i):
         b = host_ring[i % nslots]
         w.render_frame(host_inputs=(b[0].data_ptr(), b[1].data_ptr(), b[2].data_ptr(), b[3].data_ptr()), host_result=host_results[i & 1].data_ptr(), streaming=streaming, **view)

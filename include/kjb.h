@@ -214,11 +214,13 @@ int  kjb_comm_nccl_unique_id(void *out_128_bytes);
 int  kjb_comm_init_nccl(kjb_context *ctx, const void *unique_id_128_bytes, uint32_t rank, uint32_t nranks);
 int  kjb_comm_set_callback(kjb_context *ctx, kjb_allgather_fn fn, void *user, uint32_t rank, uint32_t nranks);
 int  kjb_comm_rank(kjb_context *ctx, uint32_t *rank, uint32_t *nranks);
-int  kjb_allgather(kjb_context *ctx, const void *send, void *recv, uint64_t bytes_per_rank);     /* enqueued on the stream */
+int  kjb_allgather(kjb_context *ctx, const void *send, void *recv, uint64_t bytes_per_rank);
+int  kjb_allgather_on(kjb_context *ctx, uint32_t queue, const void *send, void *recv, uint64_t bytes_per_rank);   /* same, enqueued on `queue` */     /* enqueued on the stream */
 int  kjb_memcpy_d2d(kjb_context *ctx, void *dst, const void *src, uint64_t bytes);
 /* Many device-to-device copies in ONE launch (the pack / unpack of the tile border exchange is dozens of small row strips). */
 typedef struct kjb_copy_desc { void *dst; const void *src; uint64_t bytes; } kjb_copy_desc;
-int  kjb_memcpy_d2d_batch(kjb_context *ctx, const kjb_copy_desc *copies, uint32_t count);                /* enqueued on the stream */
+int  kjb_memcpy_d2d_batch(kjb_context *ctx, const kjb_copy_desc *copies, uint32_t count);
+int  kjb_memcpy_d2d_batch_on(kjb_context *ctx, uint32_t queue, const kjb_copy_desc *copies, uint32_t count);                /* enqueued on the stream */
 
 /* Tile-sharded frames: restrict the FOLLOWING passes to rows [y0, y1) of their own output grid
  * (each rank of a multi-GPU frame computes its band plus the halo a pass's consumers need).  (0, 0) = whole image. */
@@ -229,6 +231,7 @@ int  kjb_memcpy_d2d_batch(kjb_context *ctx, const kjb_copy_desc *copies, uint32_
 #define KJB_QUEUE_COMPUTE  0u
 #define KJB_QUEUE_UPLOAD   1u
 #define KJB_QUEUE_DOWNLOAD 2u
+#define KJB_QUEUE_COMM     3u   /* collectives of tile-sharded frames, so that they overlap passes that do not depend on them */
 #define KJB_MAX_EVENTS 64u
 int  kjb_image_upload_on(kjb_context *ctx, uint32_t queue, const kjb_image *dst, const void *host_src);
 int  kjb_image_download_on(kjb_context *ctx, uint32_t queue, const kjb_image *src, void *host_dst);

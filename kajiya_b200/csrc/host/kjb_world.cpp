@@ -113,6 +113,7 @@ struct kjb_world {
     PingPong rtr_temporal_tex{"rtr.temporal"}, rtr_ray_len_tex{"rtr.ray_len"}, rtr_temporal_irradiance_tex{"rtr.irradiance"}, rtr_temporal_ray_orig_tex{"rtr.ray_orig"},
         rtr_temporal_ray_tex{"rtr.ray"}, rtr_temporal_reservoir_tex{"rtr.reservoir"}, rtr_temporal_rng_tex{"rtr.rng"}, rtr_temporal_hit_normal_tex{"rtr.hit_normal"};
     bool rtr_reuse_rtdgi_rays = true;
+    bool exchanged_this_frame = false, exchange_pending = false;   // tile exchange bookkeeping (tile_exchange_frame)
     uint32_t stream_frames = 0;   // streaming frames submitted (selects the input set / result stage)
     std::vector<int32_t> spatial_resolve_offsets;
     PingPong taa_temporal_tex{"taa"}, taa_temporal_velocity_tex{"taa.velocity"}, taa_temporal_smooth_var_tex{"taa.smooth_var"};   // taa.rs:19-27
@@ -313,7 +314,10 @@ int kjb_world_set_spatial_resolve_offsets(kjb_world* w, const int32_t* t) {
     return 0;
 }
 int kjb_world_get_image(kjb_world* w, const char* name, kjb_image* out) {
-    auto it = w->images.find(name); if (it == w->images.end()) return 1; *out = it->second; return 0;
+    auto it = w->images.find(name); if (it == w->images.end()) return 1; *out = it->second;
+    // a caller that is about to read the image on the compute queue must see a finished border exchange (event slot 17 = EV_XCHG_DONE)
+    if (w->exchange_pending) kjb_queue_wait_event(w->ctx, KJB_QUEUE_COMPUTE, 17);
+    return 0;
 }
 const char* kjb_world_image_names(kjb_world* w) {
     if (w->names_cache.empty()) for (auto& kv : w->images) { w->names_cache += kv.first; w->names_cache += '\n'; }
@@ -338,7 +342,7 @@ const char* kjb_world_pass_timings(kjb_world* w) {
 // ---------------------------------------------------------------- per-frame constants (world_renderer.rs:1001-1108)
 static int begin_frame(kjb_world* w, const kjb_world_frame* f, kjb_frame_constants& fc, bool jitter) {
     kjb_context* ctx = w->ctx;
-    w->stopped = false; w->stats[3] = 0;
+    w->stopped = false; w->stats[3] = 0; w->exchanged_this_frame = false;
     w->launches_at_frame_start = kjb_launch_count(ctx);
     if (w->geometry_dirty) {
         for (size_t i = 0; i < w->textures.size(); ++i) w->textures[i].texels = w->texture_storage[i].data();
@@ -457,7 +461,7 @@ struct XchgItem { kjb_image img; uint32_t scale; uint32_t border; };   // border
 // ONE all-gather per frame: every rank contributes the top and bottom `border` rows of its band of each temporal image (its
 // whole band for the full-res GI history, which the next frame's rays sample at arbitrary screen positions), and copies the
 // strips it needs from the other ranks' contributions into its own images.  Row strips of row-major images are contiguous.
-static int tile_exchange(kjb_world* w, const std::vector<XchgItem>& items) {
+static int tile_exchange(kjb_world* w, const std::vector<XchgItem>& items, uint32_t queue) {
     kjb_context* ctx = w->ctx;
     const uint32_t n = w->tcount;
     uint32_t band_max = 0;
@@ -491,9 +495,9 @@ static int tile_exchange(kjb_world* w, const std::vector<XchgItem>& items) {
         for (int k = 0; k < (items[i].border ? 2 : 1); ++k)
             copies.push_back({(char*)w->xchg_send.data + off[i] + strip_bytes[i] * k, (const char*)items[i].img.data + row_bytes * st[k][0], row_bytes * (st[k][1] - st[k][0])});
     }
-    if (kjb_memcpy_d2d_batch(ctx, copies.data(), uint32_t(copies.size()))) return 1;
+    if (kjb_memcpy_d2d_batch_on(ctx, queue, copies.data(), uint32_t(copies.size()))) return 1;
     copies.clear();
-    if (kjb_allgather(ctx, w->xchg_send.data, w->xchg_recv.data, total)) return 1;
+    if (kjb_allgather_on(ctx, queue, w->xchg_send.data, w->xchg_recv.data, total)) return 1;
     // unpack what this rank reads next frame: its band grown by `border` rows (everything for whole-band items)
     for (uint32_t r = 0; r < n; ++r) {
         if (r == w->trank) continue;
@@ -518,7 +522,37 @@ static int tile_exchange(kjb_world* w, const std::vector<XchgItem>& items) {
             }
         }
     }
-    return kjb_memcpy_d2d_batch(ctx, copies.data(), uint32_t(copies.size()));   // unpack (one batched launch per 96 strips)
+    return kjb_memcpy_d2d_batch_on(ctx, queue, copies.data(), uint32_t(copies.size()));   // unpack (one batched launch per 96 strips)
+}
+
+// The frame's single collective: borders of every temporal image (what is history next frame) + this rank's band of the GI history.
+// It runs on the COMM queue, fenced by two events, so that it overlaps whatever does not depend on it: the spatial filter of this
+// frame when it is issued right after "rtdgi temporal" (no TAA), and the front of the next frame (reprojection map, extracts) up to
+// "rtdgi reproject", the first consumer of exchanged history.  With per-pass profiling on it stays on the compute queue so that the
+// timers see it.
+static const uint32_t EV_XCHG_BEGIN = 16, EV_XCHG_DONE = 17;
+static void tile_exchange_frame(kjb_world* w) {
+    if (!w->tiled || w->err || w->stopped) return;
+    kjb_context* ctx = w->ctx;
+    const TileHalos th2 = tile_halos(w);
+    std::vector<XchgItem> items;
+    auto add = [&](const PingPong& pp, uint32_t scale, uint32_t border) { auto it = w->images.find(pp.history_key); if (it != w->images.end()) items.push_back({it->second, scale, border}); };
+    add(w->temporal2_tex, 2, 0);
+    add(w->temporal2_variance_tex, 2, 2 * (th2.d10 + 2));
+    add(w->temporal_radiance_tex, 1, th2.border); add(w->temporal_ray_orig_tex, 1, th2.border); add(w->temporal_ray_tex, 1, th2.border);
+    add(w->temporal_reservoir_tex, 1, th2.border); add(w->temporal_candidate_tex, 1, th2.border); add(w->temporal_invalidity_tex, 1, th2.border);
+    add(w->temporal_hit_normal_tex, 1, th2.border);
+    if (w->desc.enable_taa) { add(w->taa_temporal_tex, 2, 16); add(w->taa_temporal_velocity_tex, 2, 16); add(w->taa_temporal_smooth_var_tex, 2, 16); }
+    const uint32_t queue = w->profiling ? KJB_QUEUE_COMPUTE : KJB_QUEUE_COMM;
+    w->pass_begin("tile border all-gather");
+    int rc = 0;
+    if (queue != KJB_QUEUE_COMPUTE) rc |= kjb_event_record(ctx, EV_XCHG_BEGIN, KJB_QUEUE_COMPUTE) | kjb_queue_wait_event(ctx, queue, EV_XCHG_BEGIN);
+    rc |= tile_exchange(w, items, queue);
+    if (queue != KJB_QUEUE_COMPUTE) { rc |= kjb_event_record(ctx, EV_XCHG_DONE, queue); w->exchange_pending = true; }
+    if (rc) w->err = 1;
+    w->pass_end();
+    w->rows_all();
+    w->exchanged_this_frame = true;
 }
 
 // ---------------------------------------------------------------- RtdgiRenderer::render (rtdgi.rs:173-554)
@@ -727,6 +761,7 @@ static void rtdgi_render(kjb_world* w, kjb_image& reprojected_history_tex, kjb_i
         w->rows(th.d10, 2);
         RUN("rtdgi temporal", kjb_pass_rtdgi_temporal(ctx, &a));
     }
+    if (w->tiled && !w->desc.enable_taa) tile_exchange_frame(w);   // everything that travels is final: overlap the collective with the spatial filter
     // RtdgiRenderer::spatial (rtdgi.rs:117-141)
     kjb_image& spatial_filtered_tex = w->img("rtdgi.spatial_filtered", W, H, KJB_FMT_RGBA16_FLOAT);
     {
@@ -867,7 +902,7 @@ int kjb_world_render_frame(kjb_world* w, const kjb_world_frame* f) {
 
     // G-buffer + depth + geometric normal + velocity (world_render_passes.rs:40-82)
     // streaming mode: two input sets / two result stages so that the copy queues can run one frame ahead / behind the passes
-    const bool streaming = f->streaming && f->host_gbuffer && f->host_result && !f->replay_slot && !w->tiled;
+    const bool streaming = f->streaming && f->host_gbuffer && f->host_result && !f->replay_slot;
     const uint32_t sset = w->stream_frames & 1u;
     const uint32_t EV_UP = 8 + sset, EV_DONE = 10 + sset, EV_DL = 12 + sset;   // kjb_event slots per set
     const std::string in_prefix = f->replay_slot ? "slot" + std::to_string(f->replay_slot) + "." : (streaming ? "in" + std::to_string(sset) + "." : "");
@@ -922,6 +957,7 @@ int kjb_world_render_frame(kjb_world* w, const kjb_world_frame* f) {
     {
         kjb_rtdgi_reproject_args a{}; a.input_tex = *history_tex; a.reprojection_tex = reprojection_map; a.output_tex = reprojected_history_tex;
         size4(a.output_tex_size, reprojected_history_tex);
+        if (w->exchange_pending) { if (kjb_queue_wait_event(ctx, KJB_QUEUE_COMPUTE, EV_XCHG_DONE)) w->err = 1; w->exchange_pending = false; }   // first consumer of exchanged history
         RUN("rtdgi reproject", kjb_pass_rtdgi_reproject(ctx, &a));
     }
     if (w->desc.enable_ircache) ircache_sum_up_irradiance(w, ircache_state);   // world_render_passes.rs:138-140
@@ -941,22 +977,7 @@ int kjb_world_render_frame(kjb_world* w, const kjb_world_frame* f) {
         kjb_image gi{};
         if (kjb_world_get_image(w, "rtdgi.spatial_filtered", &gi) == 0) { taa_render(w, gi, reprojection_map, depth); result_name = "taa.this_frame_out"; }
     }
-    if (w->tiled && !w->err && !w->stopped) {
-        // the frame's single collective: borders of every temporal image (what is history next frame) + this band of the GI history
-        const TileHalos th2 = tile_halos(w);
-        std::vector<XchgItem> items;
-        auto add = [&](const PingPong& pp, uint32_t scale, uint32_t border) { auto it = w->images.find(pp.history_key); if (it != w->images.end()) items.push_back({it->second, scale, border}); };
-        add(w->temporal2_tex, 2, 0);
-        add(w->temporal2_variance_tex, 2, 2 * (th2.d10 + 2));
-        add(w->temporal_radiance_tex, 1, th2.border); add(w->temporal_ray_orig_tex, 1, th2.border); add(w->temporal_ray_tex, 1, th2.border);
-        add(w->temporal_reservoir_tex, 1, th2.border); add(w->temporal_candidate_tex, 1, th2.border); add(w->temporal_invalidity_tex, 1, th2.border);
-        add(w->temporal_hit_normal_tex, 1, th2.border);
-        if (w->desc.enable_taa) { add(w->taa_temporal_tex, 2, 16); add(w->taa_temporal_velocity_tex, 2, 16); add(w->taa_temporal_smooth_var_tex, 2, 16); }
-        w->pass_begin("tile border all-gather");
-        if (tile_exchange(w, items)) w->err = 1;
-        w->pass_end();
-        w->rows_all();
-    }
+    if (w->tiled && !w->exchanged_this_frame) tile_exchange_frame(w);   // with TAA its history images travel too: exchange at the end of the frame
     if (streaming && !w->err) {
         kjb_image result{};
         if (kjb_world_get_image(w, result_name, &result) == 0) {

@@ -36,11 +36,11 @@ struct kjb_context {
     int32_t* d_resolve_offsets = nullptr; std::vector<int32_t> h_resolve_offsets;   // SPATIAL_RESOLVE_OFFSETS as last pushed by the host
 #if !defined(KJB_EMU)
     std::vector<cudaEvent_t> timer_events;
-    cudaStream_t copy_streams[2] = {nullptr, nullptr};        // KJB_QUEUE_UPLOAD, KJB_QUEUE_DOWNLOAD (created on first use)
+    cudaStream_t copy_streams[3] = {nullptr, nullptr, nullptr};   // KJB_QUEUE_UPLOAD, _DOWNLOAD, _COMM (created on first use)
     cudaEvent_t queue_events[64] = {};                        // kjb_event_record slots
     cudaStream_t queue(uint32_t q) {
         if (q == 0) return stream;
-        if (q > 2) return nullptr;
+        if (q > 3) return nullptr;
         if (!copy_streams[q - 1] && cudaStreamCreateWithFlags(&copy_streams[q - 1], cudaStreamNonBlocking) != cudaSuccess) return nullptr;
         return copy_streams[q - 1];
     }
@@ -91,7 +91,11 @@ inline int dev_h2d(kjb_context* c, void* d, const void* h, size_t n) { return cu
 inline int dev_d2h(kjb_context* c, void* h, const void* d, size_t n) { return cudaMemcpyAsync(h, d, n, cudaMemcpyDeviceToHost, c->stream) != cudaSuccess; }
 inline int dev_d2d(kjb_context* c, void* d, const void* s, size_t n) { return cudaMemcpyAsync(d, s, n, cudaMemcpyDeviceToDevice, c->stream) != cudaSuccess; }
 inline int dev_memset(kjb_context* c, void* d, int v, size_t n) { return cudaMemsetAsync(d, v, n, c->stream) != cudaSuccess; }
-inline int dev_sync(kjb_context* c) { return cudaStreamSynchronize(c->stream) != cudaSuccess; }
+inline int dev_sync(kjb_context* c) {   // every queue of the context
+    int rc = cudaStreamSynchronize(c->stream) != cudaSuccess;
+    for (cudaStream_t st : c->copy_streams) if (st) rc |= cudaStreamSynchronize(st) != cudaSuccess;
+    return rc;
+}
 inline const char* dev_check(kjb_context*) { cudaError_t e = cudaGetLastError(); return e == cudaSuccess ? nullptr : cudaGetErrorString(e); }
 #endif
 

@@ -77,30 +77,43 @@ int kjb_comm_init_nccl(kjb_context* c, const void* id, uint32_t rank, uint32_t n
 }
 int kjb_comm_set_callback(kjb_context* c, kjb_allgather_fn fn, void* user, uint32_t rank, uint32_t nranks) { c->ag_fn = fn; c->ag_user = user; c->rank = rank; c->nranks = nranks; return 0; }
 int kjb_comm_rank(kjb_context* c, uint32_t* r, uint32_t* n) { *r = c->rank; *n = c->nranks; return 0; }
-int kjb_allgather(kjb_context* c, const void* send, void* recv, uint64_t bytes) {
-    if (c->nranks <= 1) return dev_d2d(c, recv, send, bytes);
+int kjb_allgather_on(kjb_context* c, uint32_t queue, const void* send, void* recv, uint64_t bytes) {
 #if !defined(KJB_EMU)
+    cudaStream_t st = c->queue(queue); if (!st) return c->fail("kjb_allgather: bad queue");
+    if (c->nranks <= 1) return cudaMemcpyAsync(recv, send, bytes, cudaMemcpyDeviceToDevice, st) != cudaSuccess;
     if (c->nccl_comm) {
-        const int rc = g_nccl.AllGather(send, recv, size_t(bytes), /* ncclInt8 */ 0, c->nccl_comm, c->stream);
+        const int rc = g_nccl.AllGather(send, recv, size_t(bytes), /* ncclInt8 */ 0, c->nccl_comm, st);
         return rc == 0 ? 0 : c->fail(std::string("ncclAllGather: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "error"));
     }
+#else
+    if (c->nranks <= 1) return dev_d2d(c, recv, send, bytes);
 #endif
     if (!c->ag_fn) return c->fail("kjb_allgather: no transport registered (kjb_comm_init_nccl / kjb_comm_set_callback)");
     if (dev_sync(c)) return c->fail("kjb_allgather: sync failed");
     return c->ag_fn(c->ag_user, send, recv, bytes);
 }
+int kjb_allgather(kjb_context* c, const void* send, void* recv, uint64_t bytes) { return kjb_allgather_on(c, KJB_QUEUE_COMPUTE, send, recv, bytes); }
 int kjb_memcpy_d2d(kjb_context* c, void* dst, const void* src, uint64_t bytes) { return dev_d2d(c, dst, src, bytes); }
-int kjb_memcpy_d2d_batch(kjb_context* c, const kjb_copy_desc* copies, uint32_t count) {
-    const kjb::Rows kjb__rows = {0, 1};
+int kjb_memcpy_d2d_batch_on(kjb_context* c, uint32_t queue, const kjb_copy_desc* copies, uint32_t count) {
+#if !defined(KJB_EMU)
+    cudaStream_t st = c->queue(queue); if (!st) return c->fail("kjb_memcpy_d2d_batch: bad queue");
+#endif
     for (uint32_t i0 = 0; i0 < count; i0 += KJB_COPY_BATCH) {
         CopyBatch b; b.count = count - i0 < KJB_COPY_BATCH ? count - i0 : KJB_COPY_BATCH;
         bool any = false;
         for (uint32_t i = 0; i < b.count; ++i) { b.d[i] = copies[i0 + i]; any = any || copies[i0 + i].bytes; }
         if (!any) continue;
-        KJB_LAUNCH(c, k_copy_batch, KJB_DIMS(dim3(KJB_COPY_CTAS, b.count), dim3(256)), b);
+        const kjb::Rows rows = {0, 1};
+#if defined(KJB_EMU)
+        kjb_emu::launch(dim3(KJB_COPY_CTAS, b.count), dim3(256), [&]() { k_copy_batch(b, rows); });
+#else
+        k_copy_batch<<<dim3(KJB_COPY_CTAS, b.count), dim3(256), 0, st>>>(b, rows);
+#endif
+        c->launches++;
     }
     const char* e = dev_check(c); if (e) return c->fail(std::string("kjb_memcpy_d2d_batch: ") + e);
     return 0;
 }
+int kjb_memcpy_d2d_batch(kjb_context* c, const kjb_copy_desc* copies, uint32_t count) { return kjb_memcpy_d2d_batch_on(c, KJB_QUEUE_COMPUTE, copies, count); }
 
 }  // extern "C"

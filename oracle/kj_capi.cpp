@@ -70,7 +70,9 @@ int kjb_allgather(kjb_context* c, const void* send, void* recv, uint64_t bytes) 
     if (!c->ag_fn) { c->last_error = "kjb_allgather: no transport registered"; return 1; }
     return c->ag_fn(c->ag_user, send, recv, bytes);
 }
+int kjb_allgather_on(kjb_context* c, uint32_t, const void* send, void* recv, uint64_t bytes) { return kjb_allgather(c, send, recv, bytes); }
 int kjb_memcpy_d2d(kjb_context*, void* dst, const void* src, uint64_t bytes) { memmove(dst, src, bytes); return 0; }
+int kjb_memcpy_d2d_batch_on(kjb_context*, uint32_t, const kjb_copy_desc* c, uint32_t n) { for (uint32_t i = 0; i < n; ++i) if (c[i].bytes) memmove(c[i].dst, c[i].src, c[i].bytes); return 0; }
 int kjb_memcpy_d2d_batch(kjb_context*, const kjb_copy_desc* c, uint32_t n) { for (uint32_t i = 0; i < n; ++i) if (c[i].bytes) memmove(c[i].dst, c[i].src, c[i].bytes); return 0; }
 int kjb_set_scissor(kjb_context* c, uint32_t y0, uint32_t y1) { c->scissor_y0 = y0; c->scissor_y1 = y1; return 0; }
 int kjb_set_debug_serial(kjb_context*, uint32_t) { return 0; }
