@@ -15,7 +15,7 @@ def _free_port():
     s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
 
 
-def _worker(rank, world_size, port, enable_taa, ret):
+def _worker(rank, world_size, port, enable_taa, H, ret):
     sys.path.insert(0, ROOT); sys.path.insert(0, HERE)
     os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
     os.environ["KJB_EMU_THREADS"] = "2"
@@ -57,10 +57,12 @@ def _worker(rank, world_size, port, enable_taa, ret):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("world_size,enable_taa", [(2, False), (3, True)])
-def test_tile_sharded_frames_match_single_process(world_size, enable_taa, emu_lib):
+# (4 ranks, 288 rows): bands of 36 half-res rows — narrower than the halo and than the exchanged border, as on 8 GPUs at 1080p:
+# ranks need rows from beyond their direct neighbours and both border strips of a band coincide.
+@pytest.mark.parametrize("world_size,enable_taa,height", [(2, False, H), (3, True, H), (4, False, 288)])
+def test_tile_sharded_frames_match_single_process(world_size, enable_taa, height, emu_lib):
     ret = mp.Manager().dict()
-    mp.spawn(_worker, args=(world_size, _free_port(), enable_taa, ret), nprocs=world_size, join=True)
+    mp.spawn(_worker, args=(world_size, _free_port(), enable_taa, height, ret), nprocs=world_size, join=True)
     for rank in range(world_size):
         bad, calls = ret[rank]
         assert calls == FRAMES, "exactly one all-gather per frame"
