@@ -245,6 +245,18 @@ def run_cuda(args):
             dist.destroy_process_group()
         return
 
+    rays_traced, rays_e2e_traced = rays, rays_e2e
+    if world_size > 1:
+        # The tiled ranks also trace rays for their halos.  The metric counts the rays of THE FRAME, i.e. what one GPU traces for it:
+        # measure that on rank 0 with an untiled world over the same K-frame pattern (untimed), and use it for `value` and `e2e`.
+        w1, _, _, _ = build_world(lib, workload, device=local_rank, tile=None)
+        for i in range(4):
+            w1.render_frame(**view)
+        w1.sync(); w1.stats()
+        for i in range(K):
+            w1.render_frame(**view)
+        s1 = w1.stats(); w1.close()
+        rays = rays_e2e = s1["closest_rays"] + s1["any_hit_rays"]
     peak, peak_src = load_peaks()
     # dominant kernel = the pass with the largest share of device time
     if "tile border all-gather" in timings:
@@ -263,7 +275,9 @@ def run_cuda(args):
         "ms_per_step": frame_ms, "higher_is_better": True, "scaling": "strong" if world_size > 1 else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload, "scene": WORKLOADS[workload][0], "resolution": [W, H], "spatial_reuse_passes": WORKLOADS[workload][4], "features": WORKLOADS[workload][5],
                    "l2_policy": f"inputs larger than L2: ring of {nslots} distinct jittered G-buffers ({nslots * 32 * F / 1e6:.0f} MB) + ~{frame_bytes / 1e6:.0f} MB/frame of temporal state",
-                   "rays_per_frame": rays / K / world_size, "multi_gpu": f"one frame tile-sharded into {world_size} bands of half-res rows, 1 ncclAllGather of band borders per frame; rays include halo recompute" if world_size > 1 else "n/a"},
+                   "rays_per_frame": rays / K,
+                   "multi_gpu": (f"one frame tile-sharded into {world_size} bands of half-res rows, 1 ncclAllGather of band borders per frame; `value` counts the frame's rays once "
+                                 f"(the ranks actually traced {rays_traced / K:.0f} per frame including halo recompute)") if world_size > 1 else "n/a"},
         "e2e": {"value": rays_e2e / (ms_e2e * 1e-3), "unit": "rays/s", "ms_per_step": ms_e2e / K,
                 "h2d_bytes_per_step": int(32 * F + 1216), "d2h_bytes_per_step": int(res_bytes),
                 "mode": "streaming: upload/compute/download queues, 2 frames in flight" if streaming else "blocking call per frame"},
