@@ -250,11 +250,14 @@ def run_cuda(args):
         # The tiled ranks also trace rays for their halos.  The metric counts the rays of THE FRAME, i.e. what one GPU traces for it:
         # measure that on rank 0 with an untiled world over the same K-frame pattern (untimed), and use it for `value` and `e2e`.
         w1, _, _, _ = build_world(lib, workload, device=local_rank, tile=None)
-        for i in range(4):
-            w1.render_frame(**view)
+        n1 = min(K, 4)
+        for i in range(n1):
+            w1.render_frame(capture_slot=i + 1, **view)       # G-buffers by the raster stand-in (its rays are not GI rays)
+        for i in range(Wm):
+            w1.render_frame(replay_slot=(i % n1) + 1, **view)
         w1.sync(); w1.stats()
         for i in range(K):
-            w1.render_frame(**view)
+            w1.render_frame(replay_slot=((Wm + i) % n1) + 1, **view)
         s1 = w1.stats(); w1.close()
         rays = rays_e2e = s1["closest_rays"] + s1["any_hit_rays"]
     peak, peak_src = load_peaks()
