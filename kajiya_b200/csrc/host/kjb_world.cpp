@@ -461,11 +461,14 @@ struct XchgItem { kjb_image img; uint32_t scale; uint32_t border; };   // border
 // ONE all-gather per frame: every rank contributes the top and bottom `border` rows of its band of each temporal image (its
 // whole band for the full-res GI history, which the next frame's rays sample at arbitrary screen positions), and copies the
 // strips it needs from the other ranks' contributions into its own images.  Row strips of row-major images are contiguous.
-static int tile_exchange(kjb_world* w, const std::vector<XchgItem>& items, uint32_t queue) {
+static int tile_exchange(kjb_world* w, const std::vector<XchgItem>& items_in, uint32_t queue) {
     kjb_context* ctx = w->ctx;
     const uint32_t n = w->tcount;
-    uint32_t band_max = 0;
-    for (uint32_t r = 0; r < n; ++r) { uint32_t b0, b1; w->band(r, w->HH, b0, b1); band_max = std::max(band_max, b1 - b0); }
+    uint32_t band_max = 0, band_min = 0xffffffffu;
+    for (uint32_t r = 0; r < n; ++r) { uint32_t b0, b1; w->band(r, w->HH, b0, b1); band_max = std::max(band_max, b1 - b0); band_min = std::min(band_min, b1 - b0); }
+    // narrow bands (many ranks): when the two border strips of a band touch or overlap, send the band once instead of twice
+    std::vector<XchgItem> items = items_in;
+    for (XchgItem& it : items) if (it.border && 2 * it.border >= band_min * it.scale) it.border = 0;
     // layout of one rank's contribution
     std::vector<uint64_t> off(items.size()), strip_bytes(items.size());
     uint64_t total = 0;
