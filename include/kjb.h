@@ -271,6 +271,24 @@ int kjb_pass_extract_half_res_depth(kjb_context *ctx, const kjb_extract_half_res
 int kjb_pass_extract_half_res_view_normal(kjb_context *ctx, const kjb_extract_half_res_args *a);  /* "extract view normal/2" */
 int kjb_pass_extract_half_res_ssao(kjb_context *ctx, const kjb_extract_half_res_args *a);         /* "extract ssao/2" */
 
+/* ------------------------------------------------------------------ ssao (renderers/ssgi.rs; shaders under assets/shaders/ssgi/, USE_AO_ONLY)
+ * the screen-space occlusion that guides the rtdgi kernels (half_ssao / ssao inputs of D7, D9, D11). */
+typedef struct kjb_ssao_args {                        /* "ssao", ssgi.hlsl:10-21, ssgi.rs:61-73 */
+    kjb_image gbuffer_tex, half_depth_tex, half_view_normal_tex, prev_radiance_tex, reprojection_tex;   /* prev_radiance: unused with USE_AO_ONLY, may be null */
+    kjb_image output_tex;                             /* R16_FLOAT half-res */
+    float input_tex_size[4], output_tex_size[4];
+} kjb_ssao_args;
+int kjb_pass_ssao(kjb_context *ctx, const kjb_ssao_args *a);
+typedef struct kjb_ssao_spatial_args { kjb_image ssgi_tex, depth_tex, normal_tex, output_tex; } kjb_ssao_spatial_args;      /* "ssao spatial", spatial_filter.hlsl:4-7 */
+int kjb_pass_ssao_spatial(kjb_context *ctx, const kjb_ssao_spatial_args *a);
+typedef struct kjb_ssao_upsample_args { kjb_image ssgi_tex, depth_tex, gbuffer_tex, output_tex; } kjb_ssao_upsample_args;   /* "ssao upsample", upsample.hlsl:5-8 */
+int kjb_pass_ssao_upsample(kjb_context *ctx, const kjb_ssao_upsample_args *a);
+typedef struct kjb_ssao_temporal_args {               /* "ssao temporal", temporal_filter.hlsl:3-9 */
+    kjb_image input_tex, history_tex, reprojection_tex, final_output_tex, history_output_tex;        /* final: R8_UNORM; history: R16_FLOAT */
+    float output_tex_size[4];
+} kjb_ssao_temporal_args;
+int kjb_pass_ssao_temporal(kjb_context *ctx, const kjb_ssao_temporal_args *a);
+
 /* ------------------------------------------------------------------ ircache binding block (ircache/bindings.hlsl, ircache.rs:59-78).
  * NULL `meta_buf.data` = irradiance cache not bound: lookups return 0 and allocate nothing. */
 typedef struct kjb_ircache_bindings {

@@ -30,6 +30,7 @@ typedef struct kjb_world_desc {
     /* Tile sharding by rank: with tile_count > 1 this world renders the tile_rank-th of tile_count horizontal bands (balanced
      * split of the half-res rows) and exchanges band borders once per frame through kjb_allgather. Overrides tile_y0/y1. */
     uint32_t tile_rank, tile_count;
+    uint32_t enable_ssao;   /* SsgiRenderer (ssgi.rs): real screen-space occlusion instead of the constant-1 guide */
 } kjb_world_desc;
 
 /* TriangleMesh as the asset pipeline hands it to add_mesh (kajiya-asset/src/mesh.rs:85-98) */

@@ -116,6 +116,8 @@ struct kjb_world {
     bool exchanged_this_frame = false, exchange_pending = false;   // tile exchange bookkeeping (tile_exchange_frame)
     uint32_t stream_frames = 0;   // streaming frames submitted (selects the input set / result stage)
     std::vector<int32_t> spatial_resolve_offsets;
+    PingPong ssgi_tex{"ssgi"};   // SsgiRenderer (ssgi.rs:9-19)
+    uint32_t half_normal_frame = 0xffffffffu, half_depth_frame = 0xffffffffu;   // GbufferDepth memoisation (renderers/mod.rs:54-70)
     PingPong taa_temporal_tex{"taa"}, taa_temporal_velocity_tex{"taa.velocity"}, taa_temporal_smooth_var_tex{"taa.smooth_var"};   // taa.rs:19-27
     uint32_t OW = 0, OH = 0;   // temporal_upscale_extent
 
@@ -660,7 +662,7 @@ static void rtdgi_render(kjb_world* w, kjb_image& reprojected_history_tex, kjb_i
     kjb_image& temporal_reservoir_packed_tex = w->img("rtdgi.temporal_reservoir_packed", HW, HH, KJB_FMT_RGBA32_UINT);
 
     kjb_image& half_depth_tex = w->img("half_depth", HW, HH, KJB_FMT_R32_FLOAT);
-    { kjb_extract_half_res_args a{depth, half_depth_tex}; RUN("extract half depth", kjb_pass_extract_half_res_depth(ctx, &a)); }
+    if (w->half_depth_frame != w->frame_idx) { kjb_extract_half_res_args a{depth, half_depth_tex}; RUN("extract half depth", kjb_pass_extract_half_res_depth(ctx, &a)); w->half_depth_frame = w->frame_idx; }
 
     kjb_image *invalidity_output_tex, *invalidity_history_tex; w->get_output_and_history(w->temporal_invalidity_tex, HW, HH, KJB_FMT_RG16_FLOAT, invalidity_output_tex, invalidity_history_tex);
     kjb_image *radiance_output_tex, *radiance_history_tex; w->get_output_and_history(w->temporal_radiance_tex, HW, HH, KJB_FMT_RGBA16_FLOAT, radiance_output_tex, radiance_history_tex);
@@ -668,7 +670,7 @@ static void rtdgi_render(kjb_world* w, kjb_image& reprojected_history_tex, kjb_i
     kjb_image *ray_output_tex, *ray_history_tex; w->get_output_and_history(w->temporal_ray_tex, HW, HH, KJB_FMT_RGBA16_FLOAT, ray_output_tex, ray_history_tex);
 
     kjb_image& half_view_normal_tex = w->img("half_view_normal", HW, HH, KJB_FMT_RGBA8_SNORM);
-    { kjb_extract_half_res_args a{gbuffer, half_view_normal_tex}; RUN("extract view normal/2", kjb_pass_extract_half_res_view_normal(ctx, &a)); }
+    if (w->half_normal_frame != w->frame_idx) { kjb_extract_half_res_args a{gbuffer, half_view_normal_tex}; RUN("extract view normal/2", kjb_pass_extract_half_res_view_normal(ctx, &a)); w->half_normal_frame = w->frame_idx; }
 
     kjb_image& rt_history_validity_pre_input_tex = w->img("rtdgi.rt_history_validity_pre_input", HW, HH, KJB_FMT_R8_UNORM);
     kjb_image *reservoir_output_tex, *reservoir_history_tex; w->get_output_and_history(w->temporal_reservoir_tex, HW, HH, KJB_FMT_RG32_UINT, reservoir_output_tex, reservoir_history_tex);
@@ -777,6 +779,37 @@ static void rtdgi_render(kjb_world* w, kjb_image& reprojected_history_tex, kjb_i
 }
 
 // ---------------------------------------------------------------- TaaRenderer::render (taa.rs:41-185)
+// ---------------------------------------------------------------- SsgiRenderer::render (ssgi.rs:23-181), USE_AO_ONLY
+// The half-res depth / view-normal images are the memoised ones rtdgi uses (mod.rs:54-70); this renderer runs before rtdgi, so it
+// produces them here (same kernels, same contents).
+static kjb_image& ssgi_render(kjb_world* w, kjb_image& gbuffer, kjb_image& depth, kjb_image& reprojection_map) {
+    kjb_context* ctx = w->ctx;
+    const uint32_t HW = w->HW, HH = w->HH, W = w->W, H = w->H;
+    w->rows_all();   // four small passes: every rank of a tiled frame computes the whole image
+    kjb_image& half_view_normal_tex = w->img("half_view_normal", HW, HH, KJB_FMT_RGBA8_SNORM);
+    if (w->half_normal_frame != w->frame_idx) { kjb_extract_half_res_args a{gbuffer, half_view_normal_tex}; RUN("extract view normal/2", kjb_pass_extract_half_res_view_normal(ctx, &a)); w->half_normal_frame = w->frame_idx; }
+    kjb_image& half_depth_tex = w->img("half_depth", HW, HH, KJB_FMT_R32_FLOAT);
+    if (w->half_depth_frame != w->frame_idx) { kjb_extract_half_res_args a{depth, half_depth_tex}; RUN("extract half depth", kjb_pass_extract_half_res_depth(ctx, &a)); w->half_depth_frame = w->frame_idx; }
+    kjb_image& raw = w->img("ssgi.raw", HW, HH, KJB_FMT_R16_FLOAT);
+    {
+        kjb_ssao_args a{}; a.gbuffer_tex = gbuffer; a.half_depth_tex = half_depth_tex; a.half_view_normal_tex = half_view_normal_tex; a.reprojection_tex = reprojection_map; a.output_tex = raw;
+        size4(a.input_tex_size, gbuffer); size4(a.output_tex_size, raw);
+        RUN("ssao", kjb_pass_ssao(ctx, &a));
+    }
+    kjb_image& spatially_filtered_tex = w->img("ssgi.spatial", HW, HH, KJB_FMT_R16_FLOAT);
+    { kjb_ssao_spatial_args a{raw, half_depth_tex, half_view_normal_tex, spatially_filtered_tex}; RUN("ssao spatial", kjb_pass_ssao_spatial(ctx, &a)); }
+    kjb_image& upsampled_tex = w->img("ssgi.upsampled", W, H, KJB_FMT_R16_FLOAT);
+    { kjb_ssao_upsample_args a{spatially_filtered_tex, depth, gbuffer, upsampled_tex}; RUN("ssao upsample", kjb_pass_ssao_upsample(ctx, &a)); }
+    kjb_image *history_output_tex, *history_tex; w->get_output_and_history(w->ssgi_tex, W, H, KJB_FMT_R16_FLOAT, history_output_tex, history_tex);
+    kjb_image& filtered_output_tex = w->img("ssao", W, H, KJB_FMT_R8_UNORM);
+    {
+        kjb_ssao_temporal_args a{}; a.input_tex = upsampled_tex; a.history_tex = *history_tex; a.reprojection_tex = reprojection_map; a.final_output_tex = filtered_output_tex;
+        a.history_output_tex = *history_output_tex; size4(a.output_tex_size, *history_output_tex);
+        RUN("ssao temporal", kjb_pass_ssao_temporal(ctx, &a));
+    }
+    return filtered_output_tex;
+}
+
 // ---------------------------------------------------------------- RtrRenderer::trace + TracedRtr::filter_temporal (rtr.rs:90-399)
 // `lighting.render_specular` (world_render_passes.rs:190-201), which adds triangle-light specular into the resolved image before the
 // temporal filter, belongs to renderers/lighting.rs and is outside the hot path.
@@ -948,7 +981,8 @@ int kjb_world_render_frame(kjb_world* w, const kjb_world_frame* f) {
     }
     // SSAO guides the rtdgi kernels only; ssgi.rs is outside the hot path: constant 1.0 ("no occlusion"), SURVEY §8d input 2
     kjb_image& ssao_tex = w->img("ssao", W, H, KJB_FMT_R8_UNORM);
-    if (!w->ssao_filled) { kjb_image_fill_u8(ctx, &ssao_tex, 255); w->ssao_filled = true; }
+    if (w->desc.enable_ssao) ssgi_render(w, gbuffer, depth, reprojection_map);   // ssgi.render (world_render_passes.rs:90-96)
+    else if (!w->ssao_filled) { kjb_image_fill_u8(ctx, &ssao_tex, 255); w->ssao_filled = true; }
 
     // ircache.prepare + trace_irradiance (world_render_passes.rs:99-122): cache rays use the convolved sky cube
     IrcacheState ircache_state;

@@ -359,6 +359,8 @@ KJB_DEV float3 ld_r11g11b10(const Img& i, int x, int y) {
     return f3(uf_to_f32(v & 2047u, 6), uf_to_f32((v >> 11) & 2047u, 6), uf_to_f32(v >> 22, 5));
 }
 KJB_DEV void st_r11g11b10(const ImgW& i, int x, int y, float3 c) { if (inb(i, x, y)) st_raw<uint32_t>(i, x, y, f32_to_uf(c.x, 6) | (f32_to_uf(c.y, 6) << 11) | (f32_to_uf(c.z, 5) << 22)); }
+KJB_DEV float ld_r16f(const Img& i, int x, int y) { return inb(i, x, y) ? kjb_f16_to_f32(ld_raw<uint16_t>(i, x, y)) : 0.0f; }
+KJB_DEV void st_r16f(const ImgW& i, int x, int y, float v) { if (inb(i, x, y)) st_raw<uint16_t>(i, x, y, uint16_t(kjb_f32_to_f16(v))); }
 KJB_DEV uint32_t ld_r32u(const Img& i, int x, int y) { return inb(i, x, y) ? ld_raw<uint32_t>(i, x, y) : 0u; }
 KJB_DEV void st_r32u(const ImgW& i, int x, int y, uint32_t v) { if (inb(i, x, y)) st_raw<uint32_t>(i, x, y, v); }
 KJB_DEV int clampi(int v, int n) { return v < 0 ? 0 : (v >= n ? n - 1 : v); }

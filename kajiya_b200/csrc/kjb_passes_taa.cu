@@ -149,7 +149,6 @@ KJB_KERNEL(256) k_taa_input_prob(Globals g, Img filtered_input_tex, Img filtered
     st_raw<uint16_t>(output_tex, x, y, uint16_t(kjb_f32_to_f16(input_prob)));
 }
 
-KJB_DEV float ld_r16f(const Img& i, int x, int y) { return inb(i, x, y) ? kjb_f16_to_f32(ld_raw<uint16_t>(i, x, y)) : 0.0f; }
 // ------------------------------------------------------------------ T5 filter_prob.hlsl / T6 filter_prob2.hlsl
 KJB_KERNEL(256) k_taa_prob_filter(Img input_tex, ImgW output_tex, Rows kjb_rows) {
     KJB_PX; if (x >= output_tex.w || y >= output_tex.h) return;

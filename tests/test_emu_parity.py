@@ -169,3 +169,26 @@ def test_restir_check_optional_pass(oracle_lib, emu_lib):
     wc = parity.make_world(emu_lib, scene, 72, 44)
     for _ in range(5): wc.render_frame(**view)
     assert parity.compare_images(wb, wc, names=["rtdgi.irradiance"])   # the pass does change the result
+
+
+def test_ssao_guide(oracle_lib, emu_lib):
+    """SsgiRenderer: the real screen-space occlusion guide instead of the constant 1 — ssao, spatial, upsample,
+    temporal — feeding the rtdgi kernels, camera in motion (history reprojection)."""
+    scene, view = scenes.cornell_box()
+    kw = dict(enable_ssao=True, enable_rtr=True)
+    wa, wb = parity.make_world(oracle_lib, scene, 96, 60, **kw), parity.make_world(emu_lib, scene, 96, 60, **kw)
+    cp = np.array(view["camera_position"], np.float32)
+    for f in range(6):
+        v = dict(view); v["camera_position"] = tuple(cp + np.array([0.02 * f, 0.0, -0.03 * f], np.float32))
+        wa.render_frame(**v); wb.render_frame(**v)
+        bad = parity.compare_images(wa, wb)
+        assert not bad, (f, bad[:5])
+    ao = wb.image("ssao")[..., 0]; depth = wb.image("depth")[..., 0]
+    assert {"ssgi.raw", "ssgi.spatial", "ssgi.upsampled", "ssgi:0", "ssgi:1"} <= set(wb.image_names())
+    geo = ao[depth != 0]
+    assert geo.min() < 200 and geo.max() > 230          # corners are occluded, open walls are not
+    wc = parity.make_world(emu_lib, scene, 96, 60, enable_rtr=True)
+    for f in range(6):
+        v = dict(view); v["camera_position"] = tuple(cp + np.array([0.02 * f, 0.0, -0.03 * f], np.float32))
+        wc.render_frame(**v)
+    assert parity.compare_images(wb, wc, names=["rtdgi.irradiance"])   # the guide does steer the GI kernels

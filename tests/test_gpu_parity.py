@@ -209,3 +209,16 @@ def test_atrium_full_pipeline_serial_schedule(oracle_lib, cuda_lib):
         wa.render_frame(**view); wb.render_frame(**view)
         bad = parity.compare_images(wa, wb)
         assert not bad, (f, bad[:5])
+
+
+def test_ssao_guide(oracle_lib, cuda_lib):
+    """SsgiRenderer (ssao, spatial, upsample, temporal) feeding rtdgi + rtr, camera in motion: every image bit for bit."""
+    scene, view = scenes.cornell_box()
+    kw = dict(enable_ssao=True, enable_rtr=True)
+    wa, wb = parity.make_world(oracle_lib, scene, 160, 90, **kw), parity.make_world(cuda_lib, scene, 160, 90, **kw)
+    cp = np.array(view["camera_position"], np.float32)
+    for f in range(6):
+        v = dict(view); v["camera_position"] = tuple(cp + np.array([0.02 * f, 0.0, -0.03 * f], np.float32))
+        wa.render_frame(**v); wb.render_frame(**v)
+        bad = parity.compare_images(wa, wb)
+        assert not bad, (f, bad[:5])

@@ -26,7 +26,7 @@ def _worker(rank, world_size, port, enable_taa, H, ret):
     lib = KjbLib(os.path.join(HERE, "emu", "_build", "libkjb_emu.so"))
     scene, view = scenes.cornell_box()
     view = dict(view, camera_position=(0.0, 1.0, 5.0))
-    kw = dict(enable_taa=enable_taa, spatial_reuse_pass_count=2)
+    kw = dict(enable_taa=enable_taa, spatial_reuse_pass_count=2, enable_ssao=(world_size == 2))   # the 2-rank case also runs the SSAO guide (whole image on every rank)
     tiled = parity.make_world(lib, scene, W, H, tile=(rank, world_size), **kw)
     calls = [0]
 
