@@ -474,6 +474,22 @@ typedef struct kjb_rtr_cleanup_args {                /* "reflection cleanup", sp
 } kjb_rtr_cleanup_args;
 int kjb_pass_rtr_cleanup(kjb_context *ctx, const kjb_rtr_cleanup_args *a);
 
+/* ------------------------------------------------------------------ lighting composite
+ * "trace shadow mask" (renderers/shadows.rs:10-35, rt/trace_sun_shadow_mask.rgen.hlsl) and "light gbuffer" (renderers/deferred.rs:8-43,
+ * light_gbuffer.hlsl): direct sun + emissive + rtdgi * albedo + rtr * FG; the sky with the sun disk where depth == 0. */
+typedef struct kjb_trace_sun_shadow_mask_args { kjb_image depth_tex, geometric_normal_tex, output_tex; } kjb_trace_sun_shadow_mask_args;   /* output R8_UNORM */
+int kjb_pass_trace_sun_shadow_mask(kjb_context *ctx, const kjb_trace_sun_shadow_mask_args *a);
+typedef struct kjb_light_gbuffer_args {              /* light_gbuffer.hlsl:27-44 */
+    kjb_image gbuffer_tex, depth_tex, shadow_mask_tex, rtr_tex, rtdgi_tex;   /* rtr_tex: R11G11B10 resolved reflections (a zero image when rtr is off) */
+    kjb_ircache_bindings ircache;                     /* only read by debug_shading_mode 5, which is not supported */
+    kjb_image temporal_output_tex, output_tex;        /* RGBA16F, RGBA16F */
+    kjb_image unconvolved_sky_cube_tex, sky_cube_tex;
+    float output_tex_size[4];
+    uint32_t debug_shading_mode;                      /* 0 default, 2 diffuse GI, 3 reflections, 4 "RTX off"; 1 and 5 are refused */
+    uint32_t debug_show_wrc;                          /* must be 0 (wrc is disabled upstream) */
+} kjb_light_gbuffer_args;
+int kjb_pass_light_gbuffer(kjb_context *ctx, const kjb_light_gbuffer_args *a);
+
 /* ------------------------------------------------------------------ taa (renderers/taa.rs:41-185; shaders under assets/shaders/taa/) */
 typedef struct kjb_taa_reproject_args {              /* "reproject taa", reproject_history.hlsl:8-16, taa.rs:66-79 */
     kjb_image history_tex, reprojection_tex, depth_tex, output_tex, closest_velocity_output;

@@ -39,7 +39,7 @@ class WorldDesc(C.Structure):
     _fields_ = [("render_width", C.c_uint32), ("render_height", C.c_uint32), ("temporal_upscale_width", C.c_uint32), ("temporal_upscale_height", C.c_uint32),
                 ("spatial_reuse_pass_count", C.c_uint32), ("use_raytraced_reservoir_visibility", C.c_uint32),
                 ("enable_ircache", C.c_uint32), ("enable_rtr", C.c_uint32), ("enable_taa", C.c_uint32), ("tile_y0", C.c_uint32), ("tile_y1", C.c_uint32),
-                ("tile_rank", C.c_uint32), ("tile_count", C.c_uint32), ("enable_ssao", C.c_uint32)]
+                ("tile_rank", C.c_uint32), ("tile_count", C.c_uint32), ("enable_ssao", C.c_uint32), ("enable_lighting", C.c_uint32), ("hard_sun", C.c_uint32)]
 
 
 class MeshDesc(C.Structure):

@@ -209,7 +209,7 @@ int kjb_world_create(kjb_context* ctx, const kjb_world_desc* desc, kjb_world** o
     w->W = desc->render_width; w->H = desc->render_height;
     w->HW = (w->W + 1) / 2; w->HH = (w->H + 1) / 2;   // ImageDesc::half_res = div_up (image.rs:140-142)
     w->OW = desc->temporal_upscale_width ? desc->temporal_upscale_width : w->W; w->OH = desc->temporal_upscale_height ? desc->temporal_upscale_height : w->H;
-    if (desc->tile_count > 1 && (desc->enable_ircache || desc->enable_rtr)) { delete w; return 1; }   // the cache is one global racy structure (does not shard by rows); rtr tiles: not yet
+    if (desc->tile_count > 1 && (desc->enable_ircache || desc->enable_rtr || desc->enable_lighting)) { delete w; return 1; }   // the cache is one global racy structure (does not shard by rows); rtr tiles: not yet
     if (desc->tile_count > 1) {
         if (w->OW != w->W || w->OH != w->H || (w->H & 1)) { delete w; return 1; }   // tiles + temporal upscaling / odd heights: not supported
         w->tiled = true; w->trank = desc->tile_rank; w->tcount = desc->tile_count;
@@ -378,7 +378,8 @@ static int begin_frame(kjb_world* w, const kjb_world_frame* f, kjb_frame_constan
     for (int c = 0; c < 3; ++c) fc.sun_direction[c] = f->sun_direction[c] / sl;
     fc.frame_index = w->frame_idx;
     fc.delta_time_seconds = f->delta_time_seconds > 0 ? f->delta_time_seconds : 1.0f / 60.0f;
-    fc.sun_angular_radius_cos = std::cos(1.0f * (0.53f * 3.14159265358979323846f / 180.0f) * 0.5f);
+    // WorldRenderer::sun_size_multiplier (world_renderer.rs:207,508,1078): 1.0 = the sun as seen from Earth; hard_sun = 0
+    fc.sun_angular_radius_cos = std::cos((w->desc.hard_sun ? 0.0f : 1.0f) * (0.53f * 3.14159265358979323846f / 180.0f) * 0.5f);
     for (int c = 0; c < 3; ++c) { fc.sun_color_multiplier[c] = 1.0f; fc.sky_ambient[c] = 0.0f; }
     fc.pre_exposure = fc.pre_exposure_prev = fc.pre_exposure_delta = 1.0f;   // dynamic exposure lives in post (out of scope): EV 0
     fc.render_override_flags = 0; fc.render_override_material_roughness_scale = 1.0f;
@@ -1007,12 +1008,26 @@ int kjb_world_render_frame(kjb_world* w, const kjb_world_frame* f) {
         if (kjb_world_get_image(w, "rtdgi.spatial_filtered", &gi) == 0) rtr_render(w, gbuffer, depth, geometric_normal, reprojection_map, sky_cube, gi, ircache_state.bindings());
     }
 
-    // taa.render (world_render_passes.rs:253-263).  light_gbuffer (the composite that normally feeds TAA) is outside the hot
-    // path: TAA consumes the GI result directly.
+    // light_gbuffer + taa.render (world_render_passes.rs:215-263)
     const char* result_name = "rtdgi.spatial_filtered";
+    if (w->desc.enable_lighting && !w->err && !w->stopped) {
+        // "trace shadow mask" + "light gbuffer" (world_render_passes.rs:124-128,215-232); the shadow denoiser is not built, see kjb_world.h
+        w->rows_all();
+        kjb_image& sun_shadow_mask = w->img("sun_shadow_mask", W, H, KJB_FMT_R8_UNORM);
+        { kjb_trace_sun_shadow_mask_args a{depth, geometric_normal, sun_shadow_mask}; RUN("trace shadow mask", kjb_pass_trace_sun_shadow_mask(ctx, &a)); }
+        kjb_image gi{}; kjb_world_get_image(w, "rtdgi.spatial_filtered", &gi);
+        kjb_image& rtr = w->img("rtr.resolved", W, H, KJB_FMT_R11G11B10_UFLOAT);   // zero image when rtr is off (create_dummy_output, rtr.rs:327-362)
+        kjb_image& accum_img = w->img("accum", W, H, KJB_FMT_RGBA16_FLOAT);
+        kjb_image& debug_out_tex = w->img("debug_out", W, H, KJB_FMT_RGBA16_FLOAT);
+        kjb_light_gbuffer_args a{}; a.gbuffer_tex = gbuffer; a.depth_tex = depth; a.shadow_mask_tex = sun_shadow_mask; a.rtr_tex = rtr; a.rtdgi_tex = gi;
+        a.temporal_output_tex = accum_img; a.output_tex = debug_out_tex; a.unconvolved_sky_cube_tex = sky_cube; a.sky_cube_tex = convolved_sky_cube; size4(a.output_tex_size, gbuffer);
+        RUN("light gbuffer", kjb_pass_light_gbuffer(ctx, &a));
+        result_name = "debug_out";
+    }
     if (w->desc.enable_taa) {
-        kjb_image gi{};
-        if (kjb_world_get_image(w, "rtdgi.spatial_filtered", &gi) == 0) { taa_render(w, gi, reprojection_map, depth); result_name = "taa.this_frame_out"; }
+        // taa consumes the lit image when the lighting composite runs (world_render_passes.rs:253-263), else the GI result directly
+        kjb_image taa_in{};
+        if (kjb_world_get_image(w, result_name, &taa_in) == 0) { taa_render(w, taa_in, reprojection_map, depth); result_name = "taa.this_frame_out"; }
     }
     if (w->tiled && !w->exchanged_this_frame) tile_exchange_frame(w);   // with TAA its history images travel too: exchange at the end of the frame
     if (streaming && !w->err) {

@@ -11,7 +11,7 @@ def quat_from_rotation_x(angle):
 
 class World:
     def __init__(self, lib, width, height, device=0, spatial_reuse_pass_count=2, enable_ircache=False, enable_rtr=False, enable_taa=False,
-                 upscale=None, tile=None, use_raytraced_reservoir_visibility=False, enable_ssao=False):
+                 upscale=None, tile=None, use_raytraced_reservoir_visibility=False, enable_ssao=False, enable_lighting=False, hard_sun=False):
         self.lib = lib
         self.d = lib.dll
         self.ctx = C.c_void_p()
@@ -19,7 +19,7 @@ class World:
             raise KjbError("kjb_create failed: " + (self.d.kjb_last_error(None) or b"").decode())
         tile_rank, tile_count = tile if tile else (0, 0)
         desc = WorldDesc(width, height, (upscale or (0, 0))[0], (upscale or (0, 0))[1], spatial_reuse_pass_count, int(use_raytraced_reservoir_visibility),
-                         int(enable_ircache), int(enable_rtr), int(enable_taa), 0, 0, tile_rank, tile_count, int(enable_ssao))
+                         int(enable_ircache), int(enable_rtr), int(enable_taa), 0, 0, tile_rank, tile_count, int(enable_ssao), int(enable_lighting), int(hard_sun))
         self.w = C.c_void_p()
         self._check(self.d.kjb_world_create(self.ctx, C.byref(desc), C.byref(self.w)))
         self.width, self.height = width, height

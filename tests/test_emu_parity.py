@@ -192,3 +192,21 @@ def test_ssao_guide(oracle_lib, emu_lib):
         v = dict(view); v["camera_position"] = tuple(cp + np.array([0.02 * f, 0.0, -0.03 * f], np.float32))
         wc.render_frame(**v)
     assert parity.compare_images(wb, wc, names=["rtdgi.irradiance"])   # the guide does steer the GI kernels
+
+
+def test_lighting_composite_feeds_taa(oracle_lib, emu_lib):
+    """sun shadow mask trace + light_gbuffer (direct sun, emissive, rtdgi * albedo, rtr * FG, sky with the sun disk),
+    whose output is what TAA then consumes; full path around it."""
+    scene, view = scenes.cornell_box()
+    kw = dict(enable_lighting=True, enable_rtr=True, enable_ircache=True, enable_taa=True, enable_ssao=True)
+    wa, wb, report = parity.run_lockstep(oracle_lib, emu_lib, _glossy(scene), view, 96, 60, 5, **kw)
+    _clean(report)
+    out = wb.image("debug_out").astype(np.float32); gi = wb.image("rtdgi.spatial_filtered").astype(np.float32)
+    depth = wb.image("depth")[..., 0]
+    assert {"sun_shadow_mask", "accum", "debug_out", "taa.this_frame_out"} <= set(wb.image_names())
+    assert np.isfinite(out[depth != 0]).all() and out[depth != 0][:, :3].mean() > 0.01
+    m = wb.image("sun_shadow_mask")[..., 0]
+    assert set(np.unique(m)) <= {0, 255}                  # 1 spp: lit or shadowed
+    # hard sun: the configuration in which upstream skips its shadow denoiser too
+    _, wc, report = parity.run_lockstep(oracle_lib, emu_lib, scene, view, 64, 40, 3, enable_lighting=True, hard_sun=True)
+    _clean(report)
