@@ -248,7 +248,10 @@ typedef struct kjb_raster_gbuffer_args {   /* replaces "raster simple" (raster_s
     kjb_image geometric_normal_out;        /* A2R10G10B10_UNORM, view-space normal *0.5+0.5 */
     kjb_image gbuffer_out;                 /* RGBA32_FLOAT (packed GbufferData) */
     kjb_image depth_out;                   /* R32_FLOAT reverse-Z, 0 = sky */
-    kjb_image velocity_out;                /* RGBA16_FLOAT view-space motion (0 for static scenes) */
+    kjb_image velocity_out;                /* RGBA16_FLOAT view-space motion: prev_view(prev_world_pos) - view(world_pos), raster_simple_vs.hlsl */
+    /* last frame's instance list (HOST pointer, same order as the list given to kjb_rebuild_tlas) for the motion of moving objects;
+     * NULL / 0 = objects are static (camera motion only) */
+    const kjb_instance *prev_instances; uint32_t prev_instance_count;
 } kjb_raster_gbuffer_args;
 int kjb_pass_raster_gbuffer(kjb_context *ctx, const kjb_raster_gbuffer_args *a);
 

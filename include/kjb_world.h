@@ -84,7 +84,7 @@ void kjb_world_destroy(kjb_world *w);
 int  kjb_world_add_mesh(kjb_world *w, const kjb_mesh_desc *mesh, uint32_t *out_mesh_handle);
 int  kjb_world_add_instance(kjb_world *w, uint32_t mesh_handle, const float transform[12], uint32_t *out_instance_handle);
 /* WorldRenderer::set_instance_transform (world_renderer.rs:815-818). The next frame re-flattens the acceleration structure.
- * (The primary-visibility stand-in that produces the G-buffer when the host supplies none derives velocities from camera motion only.) */
+ * (The primary-visibility stand-in that produces the G-buffer when the host supplies none uses last frame's transform for the velocity.) */
 int  kjb_world_set_instance_transform(kjb_world *w, uint32_t instance_handle, const float transform[12]);
 /* the 256x256 RGBA8 blue-noise LUT (bindless slot 1; assets/images/bluenoise/256_256/LDR_RGBA_0.png in the reference) */
 int  kjb_world_set_blue_noise(kjb_world *w, const uint8_t *rgba8_256x256);

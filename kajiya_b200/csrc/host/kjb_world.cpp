@@ -92,7 +92,7 @@ struct kjb_world {
     std::vector<kjb_gpu_mesh> meshes;
     std::vector<uint32_t> mesh_index_counts;
     std::vector<std::vector<kjb_triangle_light>> mesh_lights;
-    std::vector<kjb_instance> instances;
+    std::vector<kjb_instance> instances, prev_instances;   // prev = transforms of the last rendered frame (retire_frame, world_renderer.rs:1110-1113)
     std::vector<std::vector<uint8_t>> texture_storage;
     std::vector<kjb_texture_desc> textures;
     bool geometry_dirty = true;
@@ -437,6 +437,7 @@ static int begin_frame(kjb_world* w, const kjb_world_frame* f, kjb_frame_constan
 static void end_frame(kjb_world* w) {
     w->stats[0] = kjb_launch_count(w->ctx) - w->launches_at_frame_start;
     if (w->profiling) w->flush_timers();
+    w->prev_instances = w->instances;
     w->frame_idx += 1;   // retire_frame (world_renderer.rs:1110-1113)
 }
 
@@ -961,7 +962,8 @@ int kjb_world_render_frame(kjb_world* w, const kjb_world_frame* f) {
                | kjb_image_upload(ctx, &geometric_normal, f->host_geometric_normal) | kjb_image_upload(ctx, &velocity, f->host_velocity);
         if (rc) return rc;
     } else {
-        kjb_raster_gbuffer_args a{geometric_normal, gbuffer, depth, velocity};
+        kjb_raster_gbuffer_args a{geometric_normal, gbuffer, depth, velocity, nullptr, 0};
+        if (w->prev_instances.size() == w->instances.size()) { a.prev_instances = w->prev_instances.data(); a.prev_instance_count = uint32_t(w->prev_instances.size()); }
         RUN("raster simple", kjb_pass_raster_gbuffer(ctx, &a));
     }
     if (f->capture_slot && !f->replay_slot) {

@@ -38,7 +38,7 @@ void kjb_destroy(kjb_context* c) {
     if (!c) return;
     dev_sync(c);
     dev_free(c->d_vertices); dev_free(c->d_meshes); dev_free(c->d_instances); dev_free(c->d_nodes); dev_free(c->d_tris); dev_free(c->d_tri_info);
-    dev_free(c->d_tex_data); dev_free(c->d_tex_desc); dev_free(c->d_lights); dev_free(c->d_ray_counters);
+    dev_free(c->d_tex_data); dev_free(c->d_tex_desc); dev_free(c->d_lights); dev_free(c->d_ray_counters); dev_free(c->d_prev_instances); dev_free(c->d_resolve_offsets);
 #if !defined(KJB_EMU)
     if (c->pinned_staging) cudaFreeHost(c->pinned_staging);
     for (auto& ev : c->queue_events) if (ev) cudaEventDestroy(ev);

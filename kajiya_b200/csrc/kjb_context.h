@@ -33,6 +33,7 @@ struct kjb_context {
     kjb_triangle_light* d_lights = nullptr; uint32_t lights_capacity = 0;
     unsigned long long* d_ray_counters = nullptr;
     void* pinned_staging = nullptr; size_t pinned_bytes = 0;
+    kjb_instance* d_prev_instances = nullptr; uint32_t prev_instances_capacity = 0; std::vector<kjb_instance> h_prev_instances;   // raster stand-in: last frame's transforms
     int32_t* d_resolve_offsets = nullptr; std::vector<int32_t> h_resolve_offsets;   // SPATIAL_RESOLVE_OFFSETS as last pushed by the host
 #if !defined(KJB_EMU)
     std::vector<cudaEvent_t> timer_events;

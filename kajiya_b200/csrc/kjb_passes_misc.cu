@@ -6,7 +6,7 @@ using namespace kjb;
 
 // ------------------------------------------------------------------ primary-visibility G-buffer by ray casting
 // (stand-in for raster_simple_ps.hlsl:39-140; hit shading = rt/gbuffer.rchit.hlsl)
-KJB_KERNEL(128) k_raster_gbuffer(Globals g, ImgW gn, ImgW gb, ImgW dp, ImgW vel, Rows kjb_rows) {
+KJB_KERNEL(128) k_raster_gbuffer(Globals g, ImgW gn, ImgW gb, ImgW dp, ImgW vel, const kjb_instance* prev_instances, uint32_t prev_instance_count, Rows kjb_rows) {
     KJB_PX; if (x >= gb.w || y >= gb.h) return;
     const kjb_view_constants& vc = g.fc.view_constants;
     const float size[4] = {float(gb.w), float(gb.h), 1.0f / float(gb.w), 1.0f / float(gb.h)};
@@ -25,24 +25,27 @@ KJB_KERNEL(128) k_raster_gbuffer(Globals g, ImgW gn, ImgW gb, ImgW dp, ImgW vel,
     const float3 pos_ws = r.origin + r.dir * h.t;
     const float3 pos_cs = position_world_to_clip(vc, pos_ws);
     // geometric normal from the world-space triangle the contract intersected
-    float3 e1, e2;
+    float3 e1, e2, prev_pos_ws = pos_ws;
     {   // find the leaf record again through the global id: tri_info -> instance/prim -> vertices (cheap: once per pixel)
         const TriInfo ti = g.scene.tri_info[h.gid];
         const kjb_instance& inst = g.scene.instances[ti.instance];
         const kjb_gpu_mesh mesh = g.scene.meshes[inst.mesh_index];
-        float3 p[3];
+        float3 p[3], po[3];
         for (int k = 0; k < 3; ++k) {
             const uint32_t idx = vb_u32(g.scene, mesh.index_offset + (ti.prim * 3 + k) * 4);
             const float4 v = *reinterpret_cast<const float4*>(g.scene.vertices + mesh.vertex_core_offset + idx * 16);
-            p[k] = xform_point(inst.transform, f3(v.x, v.y, v.z));
+            po[k] = f3(v.x, v.y, v.z);
+            p[k] = xform_point(inst.transform, po[k]);
         }
         e1 = p[1] - p[0]; e2 = p[2] - p[0];
+        if (prev_instances && ti.instance < prev_instance_count)   // object motion: the same surface point under last frame's transform
+            prev_pos_ws = xform_point(prev_instances[ti.instance].transform, po[0] * (1.0f - h.u - h.v) + po[1] * h.u + po[2] * h.v);
     }
     float3 gnorm_ws = normalize(cross(e1, e2));
     if (dot(gnorm_ws, r.dir) > 0) gnorm_ws = -gnorm_ws;
     const float3 gnorm_vs = normalize(direction_world_to_view(vc, gnorm_ws));
     const float3 vs_pos = xyz(mul(vc.world_to_view, f4(pos_ws, 1)));
-    const float3 prev_vs_pos = xyz(mul(vc.prev_world_to_prev_view, f4(pos_ws, 1)));
+    const float3 prev_vs_pos = xyz(mul(vc.prev_world_to_prev_view, f4(prev_pos_ws, 1)));
     st_a2r10g10b10(gn, x, y, gnorm_vs * 0.5f + 0.5f);
     st_rgba32u(gb, x, y, packed);
     st_r32f(dp, x, y, pos_cs.z);
@@ -188,8 +191,19 @@ int kjb_pass_raster_gbuffer(kjb_context* c, const kjb_raster_gbuffer_args* a) {
     const uint32_t W = a->gbuffer_out.width, H = a->gbuffer_out.height;
     if (!check_img(c, a->gbuffer_out, KJB_FMT_RGBA32_FLOAT, P, "gbuffer_out") || !check_img(c, a->geometric_normal_out, KJB_FMT_A2R10G10B10_UNORM, P, "geometric_normal_out", W, H)
         || !check_img(c, a->depth_out, KJB_FMT_R32_FLOAT, P, "depth_out", W, H) || !check_img(c, a->velocity_out, KJB_FMT_RGBA16_FLOAT, P, "velocity_out", W, H)) return 1;
+    const kjb_instance* d_prev = nullptr;
+    if (a->prev_instances && a->prev_instance_count) {
+        if (c->prev_instances_capacity < a->prev_instance_count) {
+            dev_free(c->d_prev_instances); c->d_prev_instances = (kjb_instance*)dev_alloc(sizeof(kjb_instance) * a->prev_instance_count);
+            if (!c->d_prev_instances) return c->fail("raster simple: out of memory");
+            c->prev_instances_capacity = a->prev_instance_count;
+        }
+        c->h_prev_instances.assign(a->prev_instances, a->prev_instances + a->prev_instance_count);   // stable host copy for the async upload
+        if (dev_h2d(c, c->d_prev_instances, c->h_prev_instances.data(), sizeof(kjb_instance) * a->prev_instance_count)) return c->fail("raster simple: upload failed");
+        d_prev = c->d_prev_instances;
+    }
     KJB_ROWS(c, H);
-    KJB_LAUNCH(c, k_raster_gbuffer, KJB_GRID2D(W, H, 16, 8), c->g, img_rw(a->geometric_normal_out), img_rw(a->gbuffer_out), img_rw(a->depth_out), img_rw(a->velocity_out));
+    KJB_LAUNCH(c, k_raster_gbuffer, KJB_GRID2D(W, H, 16, 8), c->g, img_rw(a->geometric_normal_out), img_rw(a->gbuffer_out), img_rw(a->depth_out), img_rw(a->velocity_out), d_prev, d_prev ? a->prev_instance_count : 0u);
     KJB_PASS_EPILOGUE(c, P);
 }
 int kjb_pass_reprojection_map(kjb_context* c, const kjb_reprojection_map_args* a) {

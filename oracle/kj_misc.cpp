@@ -32,7 +32,16 @@ int kjb_pass_raster_gbuffer(kjb_context* ctx, const kjb_raster_gbuffer_args* a) 
         if (dot(gnorm_ws, r.dir) > 0) gnorm_ws = -gnorm_ws;
         const float3 gnorm_vs = normalize(direction_world_to_view(vc, gnorm_ws));
         const float3 vs_pos = mul(vc.world_to_view, float4(pos_ws, 1)).xyz();
-        const float3 prev_vs_pos = mul(vc.prev_world_to_prev_view, float4(pos_ws, 1)).xyz();
+        float3 prev_pos_ws = pos_ws;
+        if (a->prev_instances && wt.instance < a->prev_instance_count) {   // object motion: the same surface point under last frame's transform
+            const kjb_instance& inst = ctx->scene.instances[wt.instance];
+            const kjb_gpu_mesh& mesh = ctx->scene.meshes[inst.mesh_index];
+            float3 p[3];
+            for (int k = 0; k < 3; ++k) p[k] = ctx->scene.load_f3(mesh.vertex_core_offset + ctx->scene.load_u32(mesh.index_offset + (wt.prim * 3 + k) * 4) * 16);
+            const float3 p_obj = p[0] * (1.0f - h.u - h.v) + p[1] * h.u + p[2] * h.v;
+            prev_pos_ws = Scene::xform_point(a->prev_instances[wt.instance].transform, p_obj);
+        }
+        const float3 prev_vs_pos = mul(vc.prev_world_to_prev_view, float4(prev_pos_ws, 1)).xyz();
         gn.store(x, y, float4(gnorm_vs * 0.5f + 0.5f, 0));
         gb.store_u(x, y, packed);
         dp.store(x, y, float4(pos_cs.z));

@@ -88,3 +88,7 @@ def test_instanced_moving_geometry(oracle_lib, emu_lib):
                 w.set_instance_transform(iid, t)
             w.render_frame(**view)
         assert not parity.compare_images(worlds[0][0], worlds[1][0]), f
+    # the moving instance has object motion in its velocity (last frame's transform), the static one only camera motion (none here)
+    vel = worlds[1][0].image("velocity").astype(np.float32)
+    assert np.abs(vel[..., 0]).max() > 0.01
+    assert (np.abs(vel[..., :3]).sum(-1) == 0).mean() > 0.5
