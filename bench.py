@@ -28,6 +28,8 @@ WORKLOADS = {
     "atrium_1080p_rtdgi": ("atrium", {}, 1920, 1080, 2, {}),
     "atrium_1080p_gi_ircache_rtr": ("atrium", {}, 1920, 1080, 2, dict(enable_ircache=True, enable_rtr=True)),                   # configs[2] stand-in (Sponza-class)
     "atrium_1440p_full_taa": ("atrium", {}, 2560, 1440, 2, dict(enable_ircache=True, enable_rtr=True, enable_taa=True)),       # configs[3] on one GPU
+    # configs[4] on one GPU: 2 M-triangle ruins, rendered at 1080p and temporally upsampled to 4K by the TAA pass, full GI + SSAO guide + lit composite
+    "ruins_4k_upsampled_full": ("ruins", {}, 1920, 1080, 2, dict(enable_ircache=True, enable_rtr=True, enable_taa=True, enable_ssao=True, enable_lighting=True, upscale=(3840, 2160))),
 }
 
 # compulsory bytes per pixel of each pass at its own grid (F = full-res px, Hh = half-res px)
