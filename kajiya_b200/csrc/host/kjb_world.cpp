@@ -220,7 +220,10 @@ int kjb_world_create(kjb_context* ctx, const kjb_world_desc* desc, kjb_world** o
 }
 void kjb_world_destroy(kjb_world* w) {
     if (!w) return;
+    kjb_sync(w->ctx);   // every queue: nothing of this world is in flight any more
     for (auto& kv : w->images) kjb_image_free(w->ctx, &kv.second);
+    if (w->xchg_send.data) kjb_buffer_free(w->ctx, &w->xchg_send);
+    if (w->xchg_recv.data) kjb_buffer_free(w->ctx, &w->xchg_recv);
     delete w;
 }
 
