@@ -238,6 +238,15 @@ int  kjb_image_download_on(kjb_context *ctx, uint32_t queue, const kjb_image *sr
 int  kjb_event_record(kjb_context *ctx, uint32_t event, uint32_t queue);
 int  kjb_queue_wait_event(kjb_context *ctx, uint32_t queue, uint32_t event);   /* no-op if the event was never recorded */
 int  kjb_event_synchronize(kjb_context *ctx, uint32_t event);                   /* host wait; no-op if never recorded */
+/* Options (off unless set).
+ * KJB_OPTION_HALF_RES_POSITION_CACHE: "restir spatial" and "restir resolve" unproject the same half-res pixels over and over (16 and 8
+ * times per pixel); with this option the library keeps two scratch images of world positions — one from `half_depth_tex`, one from the
+ * depth channel of `temporal_reservoir_packed_tex` — refreshes them when their sources change and lets the two passes load instead of
+ * recompute (same values bit for bit).  The library sees every change made through its own entry points ("extract half depth",
+ * "restir temporal", kjb_image_upload/clear/copy/fill, kjb_set_frame_constants); a host that writes those two images by other means
+ * (interop) must leave the option off. */
+#define KJB_OPTION_HALF_RES_POSITION_CACHE 1u
+int  kjb_set_option(kjb_context *ctx, uint32_t option, uint32_t value);
 int  kjb_set_scissor(kjb_context *ctx, uint32_t y0, uint32_t y1);
 /* Determinism aid: while on, every pass that touches the (racy by design) irradiance cache runs on ONE device thread in the launch
  * order of its parallel kernel. Orders of magnitude slower; for reproducing cache states and for bit-exact parity tests. */

@@ -205,6 +205,7 @@ extern "C" {
 int kjb_world_create(kjb_context* ctx, const kjb_world_desc* desc, kjb_world** out) {
     kjb_world* w = new kjb_world();
     w->ctx = ctx; w->desc = *desc;
+    kjb_set_option(ctx, KJB_OPTION_HALF_RES_POSITION_CACHE, 1);   // this driver only writes half_depth / the packed reservoirs through the passes the option tracks
     if (w->desc.spatial_reuse_pass_count == 0) w->desc.spatial_reuse_pass_count = 2;
     w->W = desc->render_width; w->H = desc->render_height;
     w->HW = (w->W + 1) / 2; w->HH = (w->H + 1) / 2;   // ImageDesc::half_res = div_up (image.rs:140-142)

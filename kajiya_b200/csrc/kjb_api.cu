@@ -64,13 +64,13 @@ int kjb_image_alloc(kjb_context* c, uint32_t w, uint32_t h, uint32_t layers, uin
     return out->data ? 0 : c->fail("kjb_image_alloc: out of device memory");
 }
 int kjb_image_free(kjb_context*, kjb_image* img) { dev_free(img->data); img->data = nullptr; return 0; }
-int kjb_image_clear(kjb_context* c, const kjb_image* img) { return dev_memset(c, img->data, 0, image_bytes(*img)); }
-int kjb_image_fill_u8(kjb_context* c, const kjb_image* img, uint32_t v) { return dev_memset(c, img->data, int(v), image_bytes(*img)); }
-int kjb_image_copy(kjb_context* c, const kjb_image* dst, const kjb_image* src) {
+int kjb_image_clear(kjb_context* c, const kjb_image* img) { c->invalidate_positions(); return dev_memset(c, img->data, 0, image_bytes(*img)); }
+int kjb_image_fill_u8(kjb_context* c, const kjb_image* img, uint32_t v) { c->invalidate_positions(); return dev_memset(c, img->data, int(v), image_bytes(*img)); }
+int kjb_image_copy(kjb_context* c, const kjb_image* dst, const kjb_image* src) { c->invalidate_positions();
     if (image_bytes(*dst) != image_bytes(*src) || dst->format != src->format) return c->fail("kjb_image_copy: extent/format mismatch");
     return dev_d2d(c, dst->data, src->data, image_bytes(*dst));
 }
-int kjb_image_upload(kjb_context* c, const kjb_image* dst, const void* src) { return dev_h2d(c, dst->data, src, image_bytes(*dst)); }
+int kjb_image_upload(kjb_context* c, const kjb_image* dst, const void* src) { c->invalidate_positions(); return dev_h2d(c, dst->data, src, image_bytes(*dst)); }
 int kjb_image_download(kjb_context* c, const kjb_image* src, void* dst) { return dev_d2h(c, dst, src->data, image_bytes(*src)); }
 #if defined(KJB_EMU)
 int kjb_image_upload_on(kjb_context* c, uint32_t, const kjb_image* dst, const void* src) { return kjb_image_upload(c, dst, src); }
@@ -80,6 +80,7 @@ int kjb_queue_wait_event(kjb_context*, uint32_t, uint32_t) { return 0; }
 int kjb_event_synchronize(kjb_context*, uint32_t) { return 0; }
 #else
 int kjb_image_upload_on(kjb_context* c, uint32_t q, const kjb_image* dst, const void* src) {
+    c->invalidate_positions();
     cudaStream_t st = c->queue(q); if (!st) return c->fail("kjb_image_upload_on: bad queue");
     return cudaMemcpyAsync(dst->data, src, image_bytes(*dst), cudaMemcpyHostToDevice, st) != cudaSuccess ? c->fail("kjb_image_upload_on: copy failed") : 0;
 }
@@ -182,7 +183,7 @@ int kjb_rebuild_tlas(kjb_context* c, const kjb_instance* inst, uint32_t n) {
 
 int kjb_set_frame_constants(kjb_context* c, const kjb_frame_constants* fc, const kjb_triangle_light* lights, uint32_t n) {
     if (fc->triangle_light_count != n) return c->fail("kjb_set_frame_constants: triangle_light_count mismatch");
-    c->g.fc = *fc;
+    c->g.fc = *fc; c->invalidate_positions();
     // SUN_COLOR is a pure function of the frame constants (sun.hlsl:21-29): evaluate once here with the contract's math
     const float3 sc = sun_color_in_direction(*fc, sun_direction(*fc));
     c->g.sun_color[0] = sc.x; c->g.sun_color[1] = sc.y; c->g.sun_color[2] = sc.z; c->g.sun_color[3] = 0;
@@ -196,6 +197,10 @@ int kjb_set_frame_constants(kjb_context* c, const kjb_frame_constants* fc, const
 }
 int kjb_set_scissor(kjb_context* c, uint32_t y0, uint32_t y1) { c->scissor_y0 = y0; c->scissor_y1 = y1; return 0; }
 int kjb_set_debug_serial(kjb_context* c, uint32_t on) { c->debug_serial = on != 0; return 0; }
+int kjb_set_option(kjb_context* c, uint32_t option, uint32_t value) {
+    if (option == KJB_OPTION_HALF_RES_POSITION_CACHE) { c->opt_position_cache = value != 0; c->invalidate_positions(); return 0; }
+    return c->fail("kjb_set_option: unknown option");
+}
 int kjb_set_luts(kjb_context* c, const kjb_image* fg, const kjb_image* bn) {
     if (!check_img(c, *fg, KJB_FMT_RGBA16_FLOAT, "kjb_set_luts", "brdf_fg_lut", 64, 64)) return 1;
     if (!check_img(c, *bn, KJB_FMT_RGBA8_UNORM, "kjb_set_luts", "blue_noise", 256, 256)) return 1;

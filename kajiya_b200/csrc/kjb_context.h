@@ -55,6 +55,10 @@ struct kjb_context {
     // Row scissor for tile-sharded frames: the next pass only computes rows [scissor_y0, scissor_y1) of ITS output
     // grid (0,0 = whole image).  Set by kjb_set_scissor, consumed (and kept) by every kjb_pass_* launch.
     uint32_t scissor_y0 = 0, scissor_y1 = 0;
+    // KJB_OPTION_HALF_RES_POSITION_CACHE: world positions of the half-res pixels, from half_depth (a) and from the packed reservoirs (b)
+    struct PosCache { float4* d = nullptr; size_t cap = 0; const void* src = nullptr; uint32_t w = 0, h = 0; float gts[4] = {0, 0, 0, 0}; uint64_t epoch = ~0ull; };
+    PosCache pos_a, pos_b; uint64_t epoch_a = 0, epoch_b = 0; bool opt_position_cache = false;
+    void invalidate_positions() { epoch_a++; epoch_b++; }
     bool debug_serial = false;   // kjb_set_debug_serial: cache-touching passes run on one GPU thread in launch order
     kjb::Rows rows_for(uint32_t H) const {
         kjb::Rows r; r.y0 = 0; r.y1 = int(H);

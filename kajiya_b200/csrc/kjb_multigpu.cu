@@ -93,8 +93,9 @@ int kjb_allgather_on(kjb_context* c, uint32_t queue, const void* send, void* rec
     return c->ag_fn(c->ag_user, send, recv, bytes);
 }
 int kjb_allgather(kjb_context* c, const void* send, void* recv, uint64_t bytes) { return kjb_allgather_on(c, KJB_QUEUE_COMPUTE, send, recv, bytes); }
-int kjb_memcpy_d2d(kjb_context* c, void* dst, const void* src, uint64_t bytes) { return dev_d2d(c, dst, src, bytes); }
+int kjb_memcpy_d2d(kjb_context* c, void* dst, const void* src, uint64_t bytes) { c->invalidate_positions(); return dev_d2d(c, dst, src, bytes); }
 int kjb_memcpy_d2d_batch_on(kjb_context* c, uint32_t queue, const kjb_copy_desc* copies, uint32_t count) {
+    c->invalidate_positions();   // raw device writes may land in an image the position cache was built from
 #if !defined(KJB_EMU)
     cudaStream_t st = c->queue(queue); if (!st) return c->fail("kjb_memcpy_d2d_batch: bad queue");
 #endif

@@ -237,6 +237,7 @@ int kjb_pass_brdf_fg_lut(kjb_context* c, const kjb_brdf_fg_lut_args* a) {
     KJB_PASS_EPILOGUE(c, "brdf fg lut");
 }
 int kjb_pass_extract_half_res_depth(kjb_context* c, const kjb_extract_half_res_args* a) {
+    c->epoch_a++;   // half_depth changes: the position cache built from it is stale
     if (!check_img(c, a->input_tex, KJB_FMT_R32_FLOAT, "extract half depth", "input_tex") || !check_img(c, a->output_tex, KJB_FMT_R32_FLOAT, "extract half depth", "output_tex")) return 1;
     KJB_ROWS(c, a->output_tex.height);
     KJB_LAUNCH(c, k_extract_half_depth, KJB_GRID2D(a->output_tex.width, a->output_tex.height, 32, 8), img_ro(a->input_tex), img_rw(a->output_tex), halfres_subsample_offset(c->g.fc.frame_index));

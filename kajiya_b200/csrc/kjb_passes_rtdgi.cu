@@ -420,10 +420,41 @@ KJB_KERNEL(256) k_rtdgi_restir_temporal(Globals g, RestirTemporalImgs t, float4 
                                                          pack_normal_11_10_11(xyz(hit_normal_ws_dot))));
 }
 
+// ------------------------------------------------------------------ half-res world positions (KJB_OPTION_HALF_RES_POSITION_CACHE)
+// D7 and D9 evaluate hit_ws_from_uv_depth(get_uv(p * 2 + hso), depth(p)) for 16 / 8 neighbours p of every pixel, with depth(p) taken from
+// half_depth_tex or from the depth word of temporal_reservoir_packed_tex.  One small kernel evaluates it once per half-res pixel and
+// source; the passes then load the 16-byte result (L2 hits) — the very same function of the very same inputs, hence the same bits.
+struct PosView { const float4* p; int w, h; };
+KJB_DEV float3 cached_or_hit_ws(const PosView& pv, const kjb_view_constants& vc, int px, int py, float2 uv, float depth) {
+    if (pv.p && (unsigned)px < (unsigned)pv.w && (unsigned)py < (unsigned)pv.h) return xyz(pv.p[py * pv.w + px]);
+    return hit_ws_from_uv_depth(vc, uv, depth);
+}
+KJB_KERNEL(256) k_half_res_positions(Globals g, Img src, int packed, float4* out, float4 gts, Rows kjb_rows) {
+    KJB_PX; if (x >= src.w || y >= src.h) return;
+    const int2 hso = halfres_subsample_offset(g.fc.frame_index);
+    const float s4[4] = {gts.x, gts.y, gts.z, gts.w};
+    const float depth = packed ? kjb_u2f(ld_rgba32u(src, x, y).x) : ld_r32f(src, x, y);
+    out[y * src.w + x] = f4(hit_ws_from_uv_depth(g.fc.view_constants, get_uv(x * 2 + hso.x, y * 2 + hso.y, s4), depth), 0.0f);
+}
+static PosView ensure_positions(kjb_context* c, kjb_context::PosCache& pc, uint64_t epoch, const kjb_image& src, bool packed, const float* gts) {
+    PosView none; none.p = nullptr; none.w = 0; none.h = 0;
+    if (!c->opt_position_cache) return none;
+    const bool fresh = pc.epoch == epoch && pc.src == src.data && pc.w == src.width && pc.h == src.height && memcmp(pc.gts, gts, 16) == 0;
+    if (!fresh) {
+        const size_t need = size_t(src.width) * src.height * sizeof(float4);
+        if (pc.cap < need) { dev_sync(c); dev_free(pc.d); pc.d = (float4*)dev_alloc(need); pc.cap = pc.d ? need : 0; if (!pc.d) return none; }
+        const kjb::Rows kjb__rows = {0, int(src.height)};
+        KJB_LAUNCH(c, k_half_res_positions, KJB_GRID2D(src.width, src.height, 32, 8), c->g, img_ro(src), packed ? 1 : 0, pc.d, f4(gts[0], gts[1], gts[2], gts[3]));
+        pc.epoch = epoch; pc.src = src.data; pc.w = src.width; pc.h = src.height; memcpy(pc.gts, gts, 16);
+    }
+    PosView v; v.p = pc.d; v.w = int(src.width); v.h = int(src.height);
+    return v;
+}
+
 // ------------------------------------------------------------------ D7 restir_spatial.hlsl:48-372 + occlusion_raymarch.hlsl:69-146
 KJB_DEV float normal_influence_nonlinearity(float x, float b) { return x < -b ? 0.0f : (x + b) * (x + b) / (4 * b); }
 KJB_KERNEL(256) k_rtdgi_restir_spatial(Globals g, Img reservoir_input_tex, Img half_view_normal_tex, Img half_depth_tex, Img half_ssao_tex, Img temporal_reservoir_packed_tex,
-                                       ImgW reservoir_output_tex, float4 gts, float4 ots, uint32_t pass_idx, uint32_t perform_occlusion_raymarch, uint32_t importance_only, Rows kjb_rows) {
+                                       ImgW reservoir_output_tex, float4 gts, float4 ots, uint32_t pass_idx, uint32_t perform_occlusion_raymarch, uint32_t importance_only, PosView pos_a, PosView pos_b, Rows kjb_rows) {
     KJB_PX; if (x >= reservoir_output_tex.w || y >= reservoir_output_tex.h) return;
     const kjb_view_constants& vc = g.fc.view_constants;
     const int2 hso = halfres_subsample_offset(g.fc.frame_index);
@@ -477,9 +508,9 @@ KJB_KERNEL(256) k_rtdgi_restir_spatial(Globals g, Img reservoir_input_tex, Img h
         const float2 rpx_uv = get_uv(rx * 2 + hso.x, ry * 2 + hso.y, s4);
         const float rpx_depth = ld_r32f(half_depth_tex, rx, ry);
         if (rpx_depth == 0.0f) continue;
-        const float3 rpx_hit_ws = hit_ws_from_uv_depth(vc, rpx_uv, rpx_depth);
+        const float3 rpx_hit_ws = cached_or_hit_ws(pos_a, vc, rx, ry, rpx_uv, rpx_depth);
         const float2 spx_uv = get_uv(spx_x * 2 + hso.x, spx_y * 2 + hso.y, s4);
-        const float3 sample_hit_ws = spx_packed.ray_hit_offset_ws + hit_ws_from_uv_depth(vc, spx_uv, spx_packed.depth);
+        const float3 sample_hit_ws = spx_packed.ray_hit_offset_ws + cached_or_hit_ws(pos_b, vc, spx_x, spx_y, spx_uv, spx_packed.depth);
         const float3 reused_dir_unnorm = sample_hit_ws - rpx_hit_ws;
         const float reused_dist = length(reused_dir_unnorm);
         const float3 reused_dir_to_sample_hit_ws = reused_dir_unnorm / reused_dist;
@@ -564,7 +595,7 @@ KJB_KERNEL(128) k_rtdgi_restir_check(Globals g, Img half_depth_tex, Img temporal
 KJB_DEV float ggx_ndf_unnorm(float a2, float cos_theta) { const float ds = cos_theta * cos_theta * (a2 - 1.0f) + 1.0f; return a2 / (ds * ds); }
 struct ResolveImgs { Img radiance_tex, reservoir_input_tex, gbuffer_tex, depth_tex, half_view_normal_tex, half_depth_tex, ssao_tex, candidate_radiance_tex, candidate_hit_tex, temporal_reservoir_packed_tex; };
 struct PowTable4 { float v[4]; };   // v[i] = pow(float(i), 0.666), host-evaluated
-KJB_KERNEL(256) k_rtdgi_restir_resolve(Globals g, ResolveImgs t, ImgW irradiance_output_tex, float4 gts, float4 ots, PowTable4 pw, Rows kjb_rows) {
+KJB_KERNEL(256) k_rtdgi_restir_resolve(Globals g, ResolveImgs t, ImgW irradiance_output_tex, float4 gts, float4 ots, PowTable4 pw, PosView pos_a, PosView pos_b, Rows kjb_rows) {
     KJB_PX; if (x >= irradiance_output_tex.w || y >= irradiance_output_tex.h) return;
     const kjb_view_constants& vc = g.fc.view_constants;
     const int2 hso = halfres_subsample_offset(g.fc.frame_index);
@@ -603,7 +634,7 @@ KJB_KERNEL(256) k_rtdgi_restir_resolve(Globals g, ResolveImgs t, ImgW irradiance
             const int rx = kjb_cvt_i32(kjb_floor(float(x) * 0.5f + off.x)), ry = kjb_cvt_i32(kjb_floor(float(y) * 0.5f + off.y));
             const float2 rpx_uv = get_uv(rx * 2 + hso.x, ry * 2 + hso.y, s4);
             const float rpx_depth = ld_r32f(t.half_depth_tex, rx, ry);
-            const float3 hit_ws = xyz(ld_rgba16f(t.candidate_hit_tex, rx, ry)) + hit_ws_from_uv_depth(vc, rpx_uv, rpx_depth);
+            const float3 hit_ws = xyz(ld_rgba16f(t.candidate_hit_tex, rx, ry)) + cached_or_hit_ws(pos_a, vc, rx, ry, rpx_uv, rpx_depth);
             const float3 sample_offset = hit_ws - center_hit_ws;
             const float sample_dist = length(sample_offset);
             const float3 sample_dir = sample_offset / sample_dist;
@@ -634,7 +665,7 @@ KJB_KERNEL(256) k_rtdgi_restir_resolve(Globals g, ResolveImgs t, ImgW irradiance
             const TemporalReservoirOutput spx_packed = tro_from_raw(ld_rgba32u(t.temporal_reservoir_packed_tex, spx_x, spx_y));
             const float2 spx_uv = get_uv(spx_x * 2 + hso.x, spx_y * 2 + hso.y, s4);
             const float rpx_depth = ld_r32f(t.half_depth_tex, rx, ry);
-            const float3 hit_ws = spx_packed.ray_hit_offset_ws + hit_ws_from_uv_depth(vc, spx_uv, spx_packed.depth);
+            const float3 hit_ws = spx_packed.ray_hit_offset_ws + cached_or_hit_ws(pos_b, vc, spx_x, spx_y, spx_uv, spx_packed.depth);
             const float3 sample_offset = hit_ws - center_hit_ws;
             const float sample_dist = length(sample_offset);
             const float3 sample_dir = sample_offset / sample_dist;
@@ -848,6 +879,7 @@ int kjb_pass_rtdgi_validity_integrate(kjb_context* c, const kjb_rtdgi_validity_i
     KJB_PASS_EPILOGUE(c, P);
 }
 int kjb_pass_rtdgi_restir_temporal(kjb_context* c, const kjb_rtdgi_restir_temporal_args* a) {
+    c->epoch_b++;   // temporal_reservoir_packed_tex changes: the position cache built from it is stale
     const char* P = "restir temporal"; const uint32_t W = a->radiance_out_tex.width, H = a->radiance_out_tex.height;
     CHK(a->radiance_out_tex, KJB_FMT_RGBA16_FLOAT, "radiance_out_tex");
     CHKE(a->half_view_normal_tex, KJB_FMT_RGBA8_SNORM, "half_view_normal_tex", W, H); CHK(a->depth_tex, KJB_FMT_R32_FLOAT, "depth_tex");
@@ -878,10 +910,12 @@ int kjb_pass_rtdgi_restir_spatial(kjb_context* c, const kjb_rtdgi_restir_spatial
     CHKE(a->half_view_normal_tex, KJB_FMT_RGBA8_SNORM, "half_view_normal_tex", W, H); CHKE(a->half_depth_tex, KJB_FMT_R32_FLOAT, "half_depth_tex", W, H);
     CHKE(a->half_ssao_tex, KJB_FMT_R8_SNORM, "half_ssao_tex", W, H); CHKE(a->temporal_reservoir_packed_tex, KJB_FMT_RGBA32_UINT, "temporal_reservoir_packed_tex", W, H);
     if (a->reservoir_input_tex.data == a->reservoir_output_tex.data) return c->fail("restir spatial: input and output reservoirs must differ");
+    const PosView pos_a = ensure_positions(c, c->pos_a, c->epoch_a, a->half_depth_tex, false, a->gbuffer_tex_size);
+    const PosView pos_b = ensure_positions(c, c->pos_b, c->epoch_b, a->temporal_reservoir_packed_tex, true, a->gbuffer_tex_size);
     KJB_ROWS(c, H);
     KJB_LAUNCH(c, k_rtdgi_restir_spatial, KJB_GRID2D(W, H, 32, 8), c->g, img_ro(a->reservoir_input_tex), img_ro(a->half_view_normal_tex), img_ro(a->half_depth_tex), img_ro(a->half_ssao_tex),
                img_ro(a->temporal_reservoir_packed_tex), img_rw(a->reservoir_output_tex), F4A(a->gbuffer_tex_size), F4A(a->output_tex_size), a->spatial_reuse_pass_idx, a->perform_occlusion_raymarch,
-               a->occlusion_raymarch_importance_only);
+               a->occlusion_raymarch_importance_only, pos_a, pos_b);
     KJB_PASS_EPILOGUE(c, P);
 }
 int kjb_pass_rtdgi_restir_check(kjb_context* c, const kjb_rtdgi_restir_check_args* a) {
@@ -903,9 +937,11 @@ int kjb_pass_rtdgi_restir_resolve(kjb_context* c, const kjb_rtdgi_restir_resolve
     t.radiance_tex = img_ro(a->radiance_tex); t.reservoir_input_tex = img_ro(a->reservoir_input_tex); t.gbuffer_tex = img_ro(a->gbuffer_tex); t.depth_tex = img_ro(a->depth_tex);
     t.half_view_normal_tex = img_ro(a->half_view_normal_tex); t.half_depth_tex = img_ro(a->half_depth_tex); t.ssao_tex = img_ro(a->ssao_tex); t.candidate_radiance_tex = img_ro(a->candidate_radiance_tex);
     t.candidate_hit_tex = img_ro(a->candidate_hit_tex); t.temporal_reservoir_packed_tex = img_ro(a->temporal_reservoir_packed_tex);
+    const PosView pos_a = ensure_positions(c, c->pos_a, c->epoch_a, a->half_depth_tex, false, a->gbuffer_tex_size);
+    const PosView pos_b = ensure_positions(c, c->pos_b, c->epoch_b, a->temporal_reservoir_packed_tex, true, a->gbuffer_tex_size);
     KJB_ROWS(c, H);
     PowTable4 pw; for (int i = 0; i < 4; ++i) pw.v[i] = kjb_pow(float(i), 0.666f);
-    KJB_LAUNCH(c, k_rtdgi_restir_resolve, KJB_GRID2D(W, H, 32, 8), c->g, t, img_rw(a->irradiance_output_tex), F4A(a->gbuffer_tex_size), F4A(a->output_tex_size), pw);
+    KJB_LAUNCH(c, k_rtdgi_restir_resolve, KJB_GRID2D(W, H, 32, 8), c->g, t, img_rw(a->irradiance_output_tex), F4A(a->gbuffer_tex_size), F4A(a->output_tex_size), pw, pos_a, pos_b);
     KJB_PASS_EPILOGUE(c, P);
 }
 int kjb_pass_rtdgi_temporal(kjb_context* c, const kjb_rtdgi_temporal_args* a) {

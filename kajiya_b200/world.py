@@ -44,6 +44,10 @@ class World:
         """cache-touching passes on one device thread in launch order (deterministic; slow)"""
         self._check(self.d.kjb_set_debug_serial(self.ctx, int(on)))
 
+    def set_option(self, option, value):
+        """kjb_set_option: 1 = KJB_OPTION_HALF_RES_POSITION_CACHE (the frame driver switches it on)"""
+        self._check(self.d.kjb_set_option(self.ctx, int(option), int(value)))
+
     # -- multi-GPU transport (tile = (rank, count)) ------------------------------------------------------------
     def comm_init_nccl(self, unique_id_bytes, rank, nranks):
         buf = C.create_string_buffer(bytes(unique_id_bytes), 128)

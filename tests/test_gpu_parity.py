@@ -222,3 +222,13 @@ def test_ssao_guide(oracle_lib, cuda_lib):
         wa.render_frame(**v); wb.render_frame(**v)
         bad = parity.compare_images(wa, wb)
         assert not bad, (f, bad[:5])
+
+
+@pytest.mark.gpu
+def test_position_cache_is_invisible_on_gpu(cuda_lib):
+    scene, view = scenes.cornell_box()
+    wa, wb = parity.make_world(cuda_lib, scene, 320, 180), parity.make_world(cuda_lib, scene, 320, 180)
+    wb.set_option(1, 0)
+    for f in range(4):
+        wa.render_frame(**view); wb.render_frame(**view)
+        assert not parity.compare_images(wa, wb), f
