@@ -94,6 +94,13 @@ class World:
         self._check(self.d.kjb_world_add_mesh(self.w, C.byref(md), C.byref(h)))
         return h.value
 
+    def add_mesh_desc(self, desc, use_lights=False):
+        """add_mesh with a ready kjb_mesh_desc, e.g. `asset.GltfScene(path).desc` (the asset must outlive this call only)"""
+        desc.use_lights = int(use_lights)
+        h = C.c_uint32()
+        self._check(self.d.kjb_world_add_mesh(self.w, C.byref(desc), C.byref(h)))
+        return h.value
+
     def add_instance(self, mesh, transform3x4):
         t = (C.c_float * 12)(*np.asarray(transform3x4, np.float32).reshape(12))
         h = C.c_uint32()
