@@ -129,6 +129,17 @@ KJB_HD float kjb_floor(float x) { return floorf(x); }
 KJB_HD float kjb_ceil(float x) { return ceilf(x); }
 KJB_HD float kjb_trunc(float x) { return truncf(x); }
 KJB_HD float kjb_frac(float x) { return x - floorf(x); }
+/* x / d for an INTEGER-valued x (|x| < 2^24) and a positive constant d: reciprocal multiply plus one exact-residual correction
+ * (q = x*(1/d); q + (x - d*q)*(1/d), both steps fused).  With 1/d correctly rounded this is the correctly rounded quotient — the same
+ * bits as the IEEE division the oracle writes — in 3 instructions instead of the ~9 of a full-range division; tests/test_numeric.py
+ * checks every numerator of every call site (texel decode: d = 127, 255, 1023, 2047, 32767, 65535) exhaustively. */
+KJB_HD float kjb_div_int_const(float x, float d, float rcp_d) { const float q = x * rcp_d; return kjb_fma(kjb_fma(-d, q, x), rcp_d, q); }
+#if defined(KJB_NO_DIV_INT_CONST)   /* A/B switch for tools/variant_bench.py */
+#define KJB_DIV_INT_CONST(x, d) ((x) / (d))
+#else
+#define KJB_DIV_INT_CONST(x, d) kjb_div_int_const((x), (d), 1.0f / (d))
+#endif
+
 KJB_HD float kjb_lerp(float a, float b, float t) { return kjb_fma(b - a, t, a); }   /* HLSL lerp = a + t*(b-a) */
 KJB_HD float kjb_step(float edge, float x) { return x >= edge ? 1.0f : 0.0f; }
 KJB_HD float kjb_sign(float x) { return x > 0.0f ? 1.0f : (x < 0.0f ? -1.0f : 0.0f); }

@@ -130,6 +130,7 @@ inline bool check_img(kjb_context* c, const kjb_image& i, uint32_t fmt, const ch
 // ---- kernel launch: <<<>>> in the product; a serial block/thread loop under the test emulator
 #if defined(KJB_EMU)
 #define KJB_KERNEL(bounds) static void
+#define KJB_KERNEL_OCC(bounds, min_blocks) static void
 #define KJB_LAUNCH(ctx, kernel, dims, ...) do { if (kjb__rows.y1 > kjb__rows.y0) { kjb_emu::launch(dims, [&]() { kernel(__VA_ARGS__, kjb__rows); }); (ctx)->launches++; } } while (0)
 #define KJB_LAUNCH_SYNC(ctx, kernel, dims, ...) do { if (kjb__rows.y1 > kjb__rows.y0) { kjb_emu::launch_sync(dims, [&]() { kernel(__VA_ARGS__, kjb__rows); }); (ctx)->launches++; } } while (0)
 // kernels that touch the (racy by design) irradiance cache: the emulator runs their blocks one after another in launch order, which
@@ -137,6 +138,8 @@ inline bool check_img(kjb_context* c, const kjb_image& i, uint32_t fmt, const ch
 #define KJB_LAUNCH_ORDERED(ctx, kernel, dims, ...) do { if (kjb__rows.y1 > kjb__rows.y0) { kjb_emu::g_serial++; kjb_emu::launch(dims, [&]() { kernel(__VA_ARGS__, kjb__rows); }); kjb_emu::g_serial--; (ctx)->launches++; } } while (0)
 #else
 #define KJB_KERNEL(bounds) __global__ void __launch_bounds__(bounds)
+// same, with a resident-blocks-per-SM target that caps the register allocation (occupancy tuning of the instruction-issue-bound filters)
+#define KJB_KERNEL_OCC(bounds, min_blocks) __global__ void __launch_bounds__(bounds, min_blocks)
 #define KJB_LAUNCH(ctx, kernel, dims, ...) do { if (kjb__rows.y1 > kjb__rows.y0) { kernel<<<dims, 0, (ctx)->stream>>>(__VA_ARGS__, kjb__rows); (ctx)->launches++; } } while (0)
 #define KJB_LAUNCH_SYNC KJB_LAUNCH   /* kernels that use __syncthreads(): only the test emulator needs to know */
 #define KJB_LAUNCH_ORDERED KJB_LAUNCH

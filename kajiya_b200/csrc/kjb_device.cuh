@@ -181,7 +181,7 @@ KJB_DEV float2 cs_to_uv(float2 cs) { return cs * f2(0.5f, -0.5f) + f2(0.5f, 0.5f
 KJB_DEV float2 uv_to_cs(float2 uv) { return (uv - f2(0.5f)) * f2(2.0f, -2.0f); }
 
 // ------------------------------------------------------------------------------------------------ packing
-KJB_DEV float unpack_unorm(uint32_t p, uint32_t bits) { const uint32_t mx = (1u << bits) - 1u; return float(p & mx) / float(mx); }
+KJB_DEV float unpack_unorm(uint32_t p, uint32_t bits) { const uint32_t mx = (1u << bits) - 1u; return KJB_DIV_INT_CONST(float(p & mx), float(mx)); }   // == float(p & mx) / float(mx)
 KJB_DEV uint32_t pack_unorm(float v, uint32_t bits) { const uint32_t mx = (1u << bits) - 1u; return uint32_t(kjb_clamp(v, 0.0f, 1.0f) * float(mx) + 0.5f); }
 KJB_DEV uint32_t pack_normal_11_10_11(float3 n) {
     return pack_unorm(n.x * 0.5f + 0.5f, 11) + (pack_unorm(n.y * 0.5f + 0.5f, 10) << 11) + (pack_unorm(n.z * 0.5f + 0.5f, 11) << 21);
@@ -279,8 +279,8 @@ template <typename T> KJB_DEV void st_raw(const ImgW& i, int x, int y, T v, int 
 }
 KJB_DEV float4 half4_to_float4(uint2 v) { return f4(kjb_f16_to_f32(v.x & 0xffffu), kjb_f16_to_f32(v.x >> 16), kjb_f16_to_f32(v.y & 0xffffu), kjb_f16_to_f32(v.y >> 16)); }
 KJB_DEV uint2 float4_to_half4(float4 v) { return u2(pack_2x16f(v.x, v.y), pack_2x16f(v.z, v.w)); }
-KJB_DEV float snorm8(uint32_t b) { return kjb_max(float(int(int8_t(b & 0xffu))) / 127.0f, -1.0f); }
-KJB_DEV float snorm16(uint32_t b) { return kjb_max(float(int(int16_t(b & 0xffffu))) / 32767.0f, -1.0f); }
+KJB_DEV float snorm8(uint32_t b) { return kjb_max(KJB_DIV_INT_CONST(float(int(int8_t(b & 0xffu))), 127.0f), -1.0f); }
+KJB_DEV float snorm16(uint32_t b) { return kjb_max(KJB_DIV_INT_CONST(float(int(int16_t(b & 0xffffu))), 32767.0f), -1.0f); }
 KJB_DEV uint32_t enc_unorm(float v, float scale) { return uint32_t(kjb_clamp(v, 0.0f, 1.0f) * scale + 0.5f); }
 KJB_DEV int enc_snorm(float v, float scale) { v = kjb_clamp(v, -1.0f, 1.0f) * scale; return v >= 0.0f ? int(v + 0.5f) : -int(-v + 0.5f); }
 
@@ -293,14 +293,14 @@ KJB_DEV float2 ld_rg16f(const Img& i, int x, int y) { return inb(i, x, y) ? unpa
 KJB_DEV float4 ld_rgba8u(const Img& i, int x, int y) {
     if (!inb(i, x, y)) return f4(0.0f);
     const uint32_t v = ld_raw<uint32_t>(i, x, y);
-    return f4(float(v & 255u) / 255.0f, float((v >> 8) & 255u) / 255.0f, float((v >> 16) & 255u) / 255.0f, float(v >> 24) / 255.0f);
+    return f4(KJB_DIV_INT_CONST(float(v & 255u), 255.0f), KJB_DIV_INT_CONST(float((v >> 8) & 255u), 255.0f), KJB_DIV_INT_CONST(float((v >> 16) & 255u), 255.0f), KJB_DIV_INT_CONST(float(v >> 24), 255.0f));
 }
 KJB_DEV float4 ld_rgba8s(const Img& i, int x, int y) {
     if (!inb(i, x, y)) return f4(0.0f);
     const uint32_t v = ld_raw<uint32_t>(i, x, y);
     return f4(snorm8(v), snorm8(v >> 8), snorm8(v >> 16), snorm8(v >> 24));
 }
-KJB_DEV float ld_r8u(const Img& i, int x, int y) { return inb(i, x, y) ? float(ld_raw<uint8_t>(i, x, y)) / 255.0f : 0.0f; }
+KJB_DEV float ld_r8u(const Img& i, int x, int y) { return inb(i, x, y) ? KJB_DIV_INT_CONST(float(ld_raw<uint8_t>(i, x, y)), 255.0f) : 0.0f; }
 KJB_DEV float ld_r8s(const Img& i, int x, int y) { return inb(i, x, y) ? snorm8(ld_raw<uint8_t>(i, x, y)) : 0.0f; }
 KJB_DEV float4 ld_rgba16s(const Img& i, int x, int y) {
     if (!inb(i, x, y)) return f4(0.0f);
@@ -310,7 +310,7 @@ KJB_DEV float4 ld_rgba16s(const Img& i, int x, int y) {
 KJB_DEV float3 ld_a2r10g10b10(const Img& i, int x, int y) {
     if (!inb(i, x, y)) return f3(0.0f);
     const uint32_t v = ld_raw<uint32_t>(i, x, y);
-    return f3(float((v >> 20) & 1023u) / 1023.0f, float((v >> 10) & 1023u) / 1023.0f, float(v & 1023u) / 1023.0f);
+    return f3(KJB_DIV_INT_CONST(float((v >> 20) & 1023u), 1023.0f), KJB_DIV_INT_CONST(float((v >> 10) & 1023u), 1023.0f), KJB_DIV_INT_CONST(float(v & 1023u), 1023.0f));
 }
 KJB_DEV void st_r32f(const ImgW& i, int x, int y, float v) { if (inb(i, x, y)) st_raw<float>(i, x, y, v); }
 KJB_DEV void st_rgba32f(const ImgW& i, int x, int y, float4 v) { if (inb(i, x, y)) st_raw<float4>(i, x, y, v); }

@@ -231,7 +231,10 @@ KJB_DEV void rtdgi_trace_px(const Globals& g, const Img& half_view_normal_tex, c
     const int rx = kjb_cvt_i32(kjb_floor(float(x) + gts.x * reproj.x / 2 + 0.5f)), ry = kjb_cvt_i32(kjb_floor(float(y) + gts.y * reproj.y / 2 + 0.5f));
     st_r8u(inv_out, x, y, ld_r8u(inv_in, rx, ry));
 }
-KJB_KERNEL(128) k_rtdgi_trace(Globals g, Img half_view_normal_tex, Img depth_tex, Img reprojected_gi_tex, Img reprojection_tex, Img sky_cube_tex,
+#ifndef KJB_OCC_TRACE
+#define KJB_OCC_TRACE 1
+#endif
+KJB_KERNEL_OCC(128, KJB_OCC_TRACE) k_rtdgi_trace(Globals g, Img half_view_normal_tex, Img depth_tex, Img reprojected_gi_tex, Img reprojection_tex, Img sky_cube_tex,
                               ImgW cand_irr, ImgW cand_normal, ImgW cand_hit, Img inv_in, ImgW inv_out, float4 gts, IrcacheBufs ircache, Rows kjb_rows) {
     KJB_PX; if (x >= cand_irr.w || y >= cand_irr.h) return;
     rtdgi_trace_px(g, half_view_normal_tex, depth_tex, reprojected_gi_tex, reprojection_tex, sky_cube_tex, cand_irr, cand_normal, cand_hit, inv_in, inv_out, gts, ircache, x, y);
@@ -306,7 +309,10 @@ struct RestirTemporalImgs {
         reservoir_history_tex, reprojection_tex, hit_normal_history_tex, candidate_history_tex, rt_invalidity_tex;
     ImgW radiance_out_tex, ray_orig_output_tex, ray_output_tex, hit_normal_output_tex, reservoir_out_tex, candidate_out_tex, temporal_reservoir_packed_tex;
 };
-KJB_KERNEL(256) k_rtdgi_restir_temporal(Globals g, RestirTemporalImgs t, float4 gts, Rows kjb_rows) {
+#ifndef KJB_OCC_RESTIR_TEMPORAL
+#define KJB_OCC_RESTIR_TEMPORAL 1
+#endif
+KJB_KERNEL_OCC(256, KJB_OCC_RESTIR_TEMPORAL) k_rtdgi_restir_temporal(Globals g, RestirTemporalImgs t, float4 gts, Rows kjb_rows) {
     KJB_PX; if (x >= t.radiance_out_tex.w || y >= t.radiance_out_tex.h) return;
     const kjb_view_constants& vc = g.fc.view_constants;
     const uint32_t frame_index = g.fc.frame_index;
@@ -453,7 +459,10 @@ static PosView ensure_positions(kjb_context* c, kjb_context::PosCache& pc, uint6
 
 // ------------------------------------------------------------------ D7 restir_spatial.hlsl:48-372 + occlusion_raymarch.hlsl:69-146
 KJB_DEV float normal_influence_nonlinearity(float x, float b) { return x < -b ? 0.0f : (x + b) * (x + b) / (4 * b); }
-KJB_KERNEL(256) k_rtdgi_restir_spatial(Globals g, Img reservoir_input_tex, Img half_view_normal_tex, Img half_depth_tex, Img half_ssao_tex, Img temporal_reservoir_packed_tex,
+#ifndef KJB_OCC_RESTIR_SPATIAL
+#define KJB_OCC_RESTIR_SPATIAL 1
+#endif
+KJB_KERNEL_OCC(256, KJB_OCC_RESTIR_SPATIAL) k_rtdgi_restir_spatial(Globals g, Img reservoir_input_tex, Img half_view_normal_tex, Img half_depth_tex, Img half_ssao_tex, Img temporal_reservoir_packed_tex,
                                        ImgW reservoir_output_tex, float4 gts, float4 ots, uint32_t pass_idx, uint32_t perform_occlusion_raymarch, uint32_t importance_only, PosView pos_a, PosView pos_b, Rows kjb_rows) {
     KJB_PX; if (x >= reservoir_output_tex.w || y >= reservoir_output_tex.h) return;
     const kjb_view_constants& vc = g.fc.view_constants;
@@ -595,7 +604,10 @@ KJB_KERNEL(128) k_rtdgi_restir_check(Globals g, Img half_depth_tex, Img temporal
 KJB_DEV float ggx_ndf_unnorm(float a2, float cos_theta) { const float ds = cos_theta * cos_theta * (a2 - 1.0f) + 1.0f; return a2 / (ds * ds); }
 struct ResolveImgs { Img radiance_tex, reservoir_input_tex, gbuffer_tex, depth_tex, half_view_normal_tex, half_depth_tex, ssao_tex, candidate_radiance_tex, candidate_hit_tex, temporal_reservoir_packed_tex; };
 struct PowTable4 { float v[4]; };   // v[i] = pow(float(i), 0.666), host-evaluated
-KJB_KERNEL(256) k_rtdgi_restir_resolve(Globals g, ResolveImgs t, ImgW irradiance_output_tex, float4 gts, float4 ots, PowTable4 pw, PosView pos_a, PosView pos_b, Rows kjb_rows) {
+#ifndef KJB_OCC_RESTIR_RESOLVE
+#define KJB_OCC_RESTIR_RESOLVE 1
+#endif
+KJB_KERNEL_OCC(256, KJB_OCC_RESTIR_RESOLVE) k_rtdgi_restir_resolve(Globals g, ResolveImgs t, ImgW irradiance_output_tex, float4 gts, float4 ots, PowTable4 pw, PosView pos_a, PosView pos_b, Rows kjb_rows) {
     KJB_PX; if (x >= irradiance_output_tex.w || y >= irradiance_output_tex.h) return;
     const kjb_view_constants& vc = g.fc.view_constants;
     const int2 hso = halfres_subsample_offset(g.fc.frame_index);

@@ -7,6 +7,11 @@ SRC = r'''
 #define E(name, expr) void name(const float* a, const float* b, float* o, int n) { for (int i = 0; i < n; ++i) o[i] = expr; }
 E(t_sin, kjb_sin(a[i])) E(t_cos, kjb_cos(a[i])) E(t_exp2, kjb_exp2(a[i])) E(t_log2, kjb_log2(a[i])) E(t_pow, kjb_pow(a[i], b[i]))
 E(t_atan, kjb_atan(a[i])) E(t_atan2, kjb_atan2(a[i], b[i])) E(t_acos, kjb_acos(a[i])) E(t_min, kjb_min(a[i], b[i])) E(t_max, kjb_max(a[i], b[i]))
+int t_div_int_const(void) {   /* number of (numerator, divisor) pairs where the 3-instruction form differs from IEEE division: must be 0 */
+    const float ds[] = {127.0f, 255.0f, 1023.0f, 2047.0f, 32767.0f, 65535.0f}; int bad = 0;
+    for (int k = 0; k < 6; ++k) for (int i = -70000; i <= 70000; ++i) { const float x = (float)i; const float a = kjb_div_int_const(x, ds[k], 1.0f / ds[k]), b = x / ds[k]; bad += kjb_f2u(a) != kjb_f2u(b); }
+    return bad;
+}
 void t_f2h(const float* a, unsigned* o, int n) { for (int i = 0; i < n; ++i) o[i] = kjb_f32_to_f16(a[i]); }
 void t_h2f(const unsigned* a, float* o, int n) { for (int i = 0; i < n; ++i) o[i] = kjb_f16_to_f32(a[i]); }
 void t_cvt(const float* a, int* o, unsigned* u, int n) { for (int i = 0; i < n; ++i) { o[i] = kjb_cvt_i32(a[i]); u[i] = kjb_cvt_u32(a[i]); } }
@@ -76,3 +81,8 @@ def test_saturating_conversions(num):
     num.t_cvt(x.ctypes.data_as(C.c_void_p), i.ctypes.data_as(C.c_void_p), u.ctypes.data_as(C.c_void_p), C.c_int(x.size))
     assert i.tolist() == [0, 0, 1, -1, 2147483647, -2147483648, 2147483647, 0, 2147483520]
     assert u.tolist() == [0, 0, 1, 0, 3000000000, 0, 4294967295, 0, 2147483520]
+
+
+def test_integer_over_constant_division_is_ieee_exact(num):
+    """kjb_div_int_const (texel decode on the device) == the `/` the oracle writes, for every numerator any texel format can produce"""
+    assert num.t_div_int_const() == 0
