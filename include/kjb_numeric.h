@@ -129,7 +129,7 @@ KJB_HD float kjb_floor(float x) { return floorf(x); }
 KJB_HD float kjb_ceil(float x) { return ceilf(x); }
 KJB_HD float kjb_trunc(float x) { return truncf(x); }
 KJB_HD float kjb_frac(float x) { return x - floorf(x); }
-/* x / d for an INTEGER-valued x (|x| < 2^24) and a positive constant d: reciprocal multiply plus one exact-residual correction
+/* x / d for a non-negative-or-integer x and a positive divisor d whose reciprocal is at hand (both well inside the normal range): reciprocal multiply plus one exact-residual correction
  * (q = x*(1/d); q + (x - d*q)*(1/d), both steps fused).  With 1/d correctly rounded this is the correctly rounded quotient — the same
  * bits as the IEEE division the oracle writes — in 3 instructions instead of the ~9 of a full-range division; tests/test_numeric.py
  * checks every numerator of every call site (texel decode: d = 127, 255, 1023, 2047, 32767, 65535) exhaustively. */

@@ -232,7 +232,7 @@ KJB_DEV void rtdgi_trace_px(const Globals& g, const Img& half_view_normal_tex, c
     st_r8u(inv_out, x, y, ld_r8u(inv_in, rx, ry));
 }
 #ifndef KJB_OCC_TRACE
-#define KJB_OCC_TRACE 1
+#define KJB_OCC_TRACE 6   /* 78 registers, no spills: 78 -> 68 us */
 #endif
 KJB_KERNEL_OCC(128, KJB_OCC_TRACE) k_rtdgi_trace(Globals g, Img half_view_normal_tex, Img depth_tex, Img reprojected_gi_tex, Img reprojection_tex, Img sky_cube_tex,
                               ImgW cand_irr, ImgW cand_normal, ImgW cand_hit, Img inv_in, ImgW inv_out, float4 gts, IrcacheBufs ircache, Rows kjb_rows) {
@@ -310,7 +310,7 @@ struct RestirTemporalImgs {
     ImgW radiance_out_tex, ray_orig_output_tex, ray_output_tex, hit_normal_output_tex, reservoir_out_tex, candidate_out_tex, temporal_reservoir_packed_tex;
 };
 #ifndef KJB_OCC_RESTIR_TEMPORAL
-#define KJB_OCC_RESTIR_TEMPORAL 1
+#define KJB_OCC_RESTIR_TEMPORAL 4   /* 64 registers: 45 -> 36 us */
 #endif
 KJB_KERNEL_OCC(256, KJB_OCC_RESTIR_TEMPORAL) k_rtdgi_restir_temporal(Globals g, RestirTemporalImgs t, float4 gts, Rows kjb_rows) {
     KJB_PX; if (x >= t.radiance_out_tex.w || y >= t.radiance_out_tex.h) return;
@@ -460,7 +460,7 @@ static PosView ensure_positions(kjb_context* c, kjb_context::PosCache& pc, uint6
 // ------------------------------------------------------------------ D7 restir_spatial.hlsl:48-372 + occlusion_raymarch.hlsl:69-146
 KJB_DEV float normal_influence_nonlinearity(float x, float b) { return x < -b ? 0.0f : (x + b) * (x + b) / (4 * b); }
 #ifndef KJB_OCC_RESTIR_SPATIAL
-#define KJB_OCC_RESTIR_SPATIAL 1
+#define KJB_OCC_RESTIR_SPATIAL 1   /* 74 registers; capping at 64 / 48 costs 5 % / 13 % */
 #endif
 KJB_KERNEL_OCC(256, KJB_OCC_RESTIR_SPATIAL) k_rtdgi_restir_spatial(Globals g, Img reservoir_input_tex, Img half_view_normal_tex, Img half_depth_tex, Img half_ssao_tex, Img temporal_reservoir_packed_tex,
                                        ImgW reservoir_output_tex, float4 gts, float4 ots, uint32_t pass_idx, uint32_t perform_occlusion_raymarch, uint32_t importance_only, PosView pos_a, PosView pos_b, Rows kjb_rows) {
@@ -541,6 +541,7 @@ KJB_KERNEL_OCC(256, KJB_OCC_RESTIR_SPATIAL) k_rtdgi_restir_spatial(Globals g, Im
             if (k_count > 6) k_count = 6;
             const float depth_step_per_z = (raymarch_end_cs.z - raymarch_start_cs.z) / length(xy(raymarch_end_cs) - xy(raymarch_start_cs));
             const float t_step = 1.0f / float(k_count);
+            const float rcp_gts_x = 1.0f / gts.x, rcp_gts_y = 1.0f / gts.y;
             float tt = 0.5f * t_step;
             for (int k = 0; k < k_count; ++k) {
                 const float3 interp_pos_cs = vlerp(raymarch_start_cs, raymarch_end_cs, tt);
@@ -548,7 +549,8 @@ KJB_KERNEL_OCC(256, KJB_OCC_RESTIR_SPATIAL) k_rtdgi_restir_spatial(Globals g, Im
                 const uint32_t pix = (kjb_cvt_u32(kjb_floor(uv_at_interp.x * gts.x - float(hso.x))) & ~1u) + uint32_t(hso.x);
                 const uint32_t piy = (kjb_cvt_u32(kjb_floor(uv_at_interp.y * gts.y - float(hso.y))) & ~1u) + uint32_t(hso.y);
                 const float depth_at_interp = ld_r32f(half_depth_tex, int(pix >> 1u), int(piy >> 1u));
-                const float2 quantized_cs = uv_to_cs((f2(float(pix), float(piy)) + 0.5f) / f2(gts.x, gts.y));
+                // (texel centre) / (texture size): positive finite numerators over a per-thread constant divisor, see kjb_div_int_const
+                const float2 quantized_cs = uv_to_cs(f2(kjb_div_int_const(float(pix) + 0.5f, gts.x, rcp_gts_x), kjb_div_int_const(float(piy) + 0.5f, gts.y, rcp_gts_y)));
                 const float biased_interp_z = raymarch_start_cs.z + depth_step_per_z * length(quantized_cs - xy(raymarch_start_cs));
                 if (depth_at_interp > biased_interp_z) {
                     const float depth_diff = inverse_depth_relative_diff(interp_pos_cs.z, depth_at_interp);
@@ -605,7 +607,7 @@ KJB_DEV float ggx_ndf_unnorm(float a2, float cos_theta) { const float ds = cos_t
 struct ResolveImgs { Img radiance_tex, reservoir_input_tex, gbuffer_tex, depth_tex, half_view_normal_tex, half_depth_tex, ssao_tex, candidate_radiance_tex, candidate_hit_tex, temporal_reservoir_packed_tex; };
 struct PowTable4 { float v[4]; };   // v[i] = pow(float(i), 0.666), host-evaluated
 #ifndef KJB_OCC_RESTIR_RESOLVE
-#define KJB_OCC_RESTIR_RESOLVE 1
+#define KJB_OCC_RESTIR_RESOLVE 5   /* 48 registers, 5 blocks/SM: 117 -> 112 us at 1080p (profiles/r01r_variants.txt) */
 #endif
 KJB_KERNEL_OCC(256, KJB_OCC_RESTIR_RESOLVE) k_rtdgi_restir_resolve(Globals g, ResolveImgs t, ImgW irradiance_output_tex, float4 gts, float4 ots, PowTable4 pw, PosView pos_a, PosView pos_b, Rows kjb_rows) {
     KJB_PX; if (x >= irradiance_output_tex.w || y >= irradiance_output_tex.h) return;
