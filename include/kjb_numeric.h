@@ -120,7 +120,13 @@ KJB_HD float kjb_fma(float a, float b, float c) {
 KJB_HD float kjb_min(float a, float b) { return (a < b || b != b) ? a : b; }
 KJB_HD float kjb_max(float a, float b) { return (a > b || b != b) ? a : b; }
 KJB_HD float kjb_clamp(float x, float lo, float hi) { return kjb_min(kjb_max(x, lo), hi); }
-KJB_HD float kjb_saturate(float x) { return kjb_clamp(x, 0.0f, 1.0f); }
+KJB_HD float kjb_saturate(float x) {
+#if defined(__CUDA_ARCH__)
+    return __saturatef(x);   /* one instruction; documented as clamp to [+0.0, 1.0] with NaN -> +0: exactly the expression below (-0 -> +0 too) */
+#else
+    return kjb_clamp(x, 0.0f, 1.0f);
+#endif
+}
 KJB_HD float kjb_abs(float x) { return kjb_u2f(kjb_f2u(x) & 0x7fffffffu); }
 KJB_HD float kjb_rcp(float x) { return 1.0f / x; }
 KJB_HD float kjb_sqrt(float x) { return sqrtf(x); }                /* IEEE correctly rounded on both sides */

@@ -83,6 +83,11 @@ KJB_DEV float3 vclamp(float3 v, float3 lo, float3 hi) { return vmin(vmax(v, lo),
 KJB_DEV float3 vlerp(float3 a, float3 b, float t) { return f3(kjb_lerp(a.x, b.x, t), kjb_lerp(a.y, b.y, t), kjb_lerp(a.z, b.z, t)); }
 KJB_DEV float3 vlerp(float3 a, float3 b, float3 t) { return f3(kjb_lerp(a.x, b.x, t.x), kjb_lerp(a.y, b.y, t.y), kjb_lerp(a.z, b.z, t.z)); }
 KJB_DEV float4 vlerp(float4 a, float4 b, float t) { return f4(kjb_lerp(a.x, b.x, t), kjb_lerp(a.y, b.y, t), kjb_lerp(a.z, b.z, t), kjb_lerp(a.w, b.w, t)); }
+// HLSL mad(): a * s + c with ONE rounding per component — the weighted-sum taps of the filters (explicit, like every fused op of the contract)
+KJB_DEV float  mad(float a, float s, float c) { return kjb_fma(a, s, c); }
+KJB_DEV float2 mad(float2 a, float s, float2 c) { return f2(kjb_fma(a.x, s, c.x), kjb_fma(a.y, s, c.y)); }
+KJB_DEV float3 mad(float3 a, float s, float3 c) { return f3(kjb_fma(a.x, s, c.x), kjb_fma(a.y, s, c.y), kjb_fma(a.z, s, c.z)); }
+KJB_DEV float4 mad(float4 a, float s, float4 c) { return f4(kjb_fma(a.x, s, c.x), kjb_fma(a.y, s, c.y), kjb_fma(a.z, s, c.z), kjb_fma(a.w, s, c.w)); }
 KJB_DEV float2 vlerp(float2 a, float2 b, float t) { return f2(kjb_lerp(a.x, b.x, t), kjb_lerp(a.y, b.y, t)); }
 KJB_DEV float dot(float2 a, float2 b) { return kjb_fma(a.y, b.y, a.x * b.x); }
 KJB_DEV float dot(float3 a, float3 b) { return kjb_fma(a.z, b.z, kjb_fma(a.y, b.y, a.x * b.x)); }
@@ -271,12 +276,13 @@ KJB_DEV ImgW img_rw(const kjb_image& i) { ImgW r; r.p = (uint8_t*)i.data; r.w = 
 KJB_DEV Img as_ro(const ImgW& i) { Img r; r.p = i.p; r.w = i.w; r.h = i.h; return r; }
 KJB_DEV bool inb(const Img& i, int x, int y) { return (unsigned)x < (unsigned)i.w && (unsigned)y < (unsigned)i.h; }
 KJB_DEV bool inb(const ImgW& i, int x, int y) { return (unsigned)x < (unsigned)i.w && (unsigned)y < (unsigned)i.h; }
-template <typename T> KJB_DEV T ld_raw(const Img& i, int x, int y, int layer = 0) {
-    return *(const T*)(i.p + ((size_t)layer * i.h * i.w + (size_t)y * i.w + x) * sizeof(T));
+// texel index inside one layer in 32 bits (an image layer holds < 2^32 texels: one IMAD + one widening IMAD per access instead of 64-bit products)
+KJB_DEV size_t texel_offset(int w, int h, int x, int y, int layer, size_t texel_bytes) {
+    const uint32_t in_layer = uint32_t(y) * uint32_t(w) + uint32_t(x);
+    return (layer == 0 ? size_t(in_layer) : size_t(layer) * size_t(uint32_t(h) * uint32_t(w)) + in_layer) * texel_bytes;
 }
-template <typename T> KJB_DEV void st_raw(const ImgW& i, int x, int y, T v, int layer = 0) {
-    *(T*)(i.p + ((size_t)layer * i.h * i.w + (size_t)y * i.w + x) * sizeof(T)) = v;
-}
+template <typename T> KJB_DEV T ld_raw(const Img& i, int x, int y, int layer = 0) { return *(const T*)(i.p + texel_offset(i.w, i.h, x, y, layer, sizeof(T))); }
+template <typename T> KJB_DEV void st_raw(const ImgW& i, int x, int y, T v, int layer = 0) { *(T*)(i.p + texel_offset(i.w, i.h, x, y, layer, sizeof(T))) = v; }
 KJB_DEV float4 half4_to_float4(uint2 v) { return f4(kjb_f16_to_f32(v.x & 0xffffu), kjb_f16_to_f32(v.x >> 16), kjb_f16_to_f32(v.y & 0xffffu), kjb_f16_to_f32(v.y >> 16)); }
 KJB_DEV uint2 float4_to_half4(float4 v) { return u2(pack_2x16f(v.x, v.y), pack_2x16f(v.z, v.w)); }
 KJB_DEV float snorm8(uint32_t b) { return kjb_max(KJB_DIV_INT_CONST(float(int(int8_t(b & 0xffu))), 127.0f), -1.0f); }

@@ -275,7 +275,7 @@ KJB_KERNEL(256) k_rtdgi_validity_integrate(Globals g, Img input_tex, Img history
     __syncthreads();
     {
         float acc = 0.0f;
-        for (int yy = 0; yy < 5; ++yy) for (int xx = 0; xx < 5; ++xx) acc += in_tile[ty + yy][tx + xx] * wt.w[yy * 5 + xx];
+        for (int yy = 0; yy < 5; ++yy) for (int xx = 0; xx < 5; ++xx) acc = mad(in_tile[ty + yy][tx + xx], wt.w[yy * 5 + xx], acc);
         blur_s[ty][tx] = acc / wt.w_sum;
         edge_s[ty][tx] = d5_edge(reprojection_tex, half_depth_tex, x, y);
     }
@@ -661,7 +661,7 @@ KJB_KERNEL_OCC(256, KJB_OCC_RESTIR_RESOLVE) k_rtdgi_restir_resolve(Globals g, Re
             float w = 1;
             w *= ggx_ndf_unnorm(0.01f, kjb_saturate(dot(center_normal_vs, sample_normal_vs)));
             w *= kjb_exp2(-200.0f * kjb_abs(center_normal_vs.z * (center_depth / rpx_depth - 1.0f)));
-            weighted_irradiance += contribution * w;
+            weighted_irradiance = mad(contribution, w, weighted_irradiance);
             w_sum += w;
         }
         total_irradiance += weighted_irradiance / kjb_max(1e-20f, w_sum);
@@ -694,7 +694,7 @@ KJB_KERNEL_OCC(256, KJB_OCC_RESTIR_RESOLVE) k_rtdgi_restir_resolve(Globals g, Re
             w *= ggx_ndf_unnorm(0.01f, kjb_saturate(dot(center_normal_vs, sample_normal_vs)));
             w *= kjb_exp2(-200.0f * kjb_abs(center_normal_vs.z * (center_depth / rpx_depth - 1.0f)));
             w *= kjb_exp2(-20.0f * kjb_abs(center_ssao - sample_ssao));
-            weighted_irradiance += contribution * w;
+            weighted_irradiance = mad(contribution, w, weighted_irradiance);
             w_sum += w;
         }
         total_irradiance += weighted_irradiance / kjb_max(1e-20f, w_sum);
@@ -707,7 +707,7 @@ KJB_KERNEL_OCC(256, KJB_OCC_RESTIR_RESOLVE) k_rtdgi_restir_resolve(Globals g, Re
 // converted to the crunched luma-chroma working space (sRGB->YCbCr, sqrt, divide), so the conversion runs once per texel
 // instead of once per tap (25x fewer), and the 50 taps per pixel become LDS instead of L1 requests.  The 25 Gaussian
 // weights exp(-3 r^2 / 9) are evaluated once on the host with the contract's kjb_exp and arrive as a kernel parameter.
-struct Weights25 { float w[25]; };
+struct Weights25 { float w[25]; float w_sum; };   // w_sum: the float sum of w[] in tap order (what the shader's `wsum += w` arrives at), host-evaluated
 #define D10_BX 32
 #define D10_BY 16
 #define D10_TW (D10_BX + 4)
@@ -734,14 +734,14 @@ KJB_KERNEL(512) k_rtdgi_temporal(Globals g, Img input_tex, Img history_tex, Img 
     const float4 center = s_in[tcy * D10_TW + tcx];
     const float4 reproj = ld_rgba16s(reprojection_tex, x, y);
     const float4 history = linear_to_working(ld_rgba16f(history_tex, x, y) * history_mult);
-    float4 vsum = f4(0.0f), vsum2 = f4(0.0f); float wsum = 0, hist_vsum = 0, hist_vsum2 = 0;
+    float4 vsum = f4(0.0f), vsum2 = f4(0.0f); const float wsum = wt.w_sum; float hist_vsum = 0, hist_vsum2 = 0;
     for (int yy = -2; yy <= 2; ++yy) for (int xx = -2; xx <= 2; ++xx) {
         const int ti = (tcy + yy) * D10_TW + (tcx + xx);
         const float4 neigh = s_in[ti];
         const float hist_luma = s_hist_luma[ti];
         const float w = wt.w[(yy + 2) * 5 + (xx + 2)];
-        vsum += neigh * w; vsum2 += neigh * neigh * w; wsum += w;
-        hist_vsum += hist_luma * w; hist_vsum2 += hist_luma * hist_luma * w;
+        vsum = mad(neigh, w, vsum); vsum2 = mad(neigh * neigh, w, vsum2);
+        hist_vsum = mad(hist_luma, w, hist_vsum); hist_vsum2 = mad(hist_luma * hist_luma, w, hist_vsum2);
     }
     const float4 ex = vsum / wsum, ex2 = vsum2 / wsum;
     const float4 dev = vsqrt(vmax(f4(0.0f), ex2 - ex * ex));
@@ -803,7 +803,7 @@ KJB_KERNEL(256) k_rtdgi_spatial(Globals g, Img input_tex, Img depth_tex, Img ssa
             float wt = 1;
             wt *= kjb_exp2(-100.0f * kjb_abs(center_normal_vs.z * (center_depth / sample_depth - 1.0f)));
             wt *= kjb_exp2(-20.0f * kjb_abs(sample_ssao - center_ssao));
-            sum += f4(crunch(sample_val), 1.0f) * wt;
+            sum = mad(f4(crunch(sample_val), 1.0f), wt, sum);
         }
     }
     const float norm_factor = 1.0f / kjb_max(1e-5f, sum.w);
@@ -966,6 +966,7 @@ int kjb_pass_rtdgi_temporal(kjb_context* c, const kjb_rtdgi_temporal_args* a) {
     CHKE(a->variance_history_output_tex, KJB_FMT_RG16_FLOAT, "variance_history_output_tex", W, H);
     Weights25 wt;
     for (int yy = -2; yy <= 2; ++yy) for (int xx = -2; xx <= 2; ++xx) wt.w[(yy + 2) * 5 + (xx + 2)] = kjb_exp(-3.0f * float(xx * xx + yy * yy) / float((2 + 1.) * (2 + 1.)));
+    wt.w_sum = 0; for (int i = 0; i < 25; ++i) wt.w_sum += wt.w[i];
     KJB_ROWS(c, H);
     KJB_LAUNCH_SYNC(c, k_rtdgi_temporal, KJB_GRID2D(W, H, D10_BX, D10_BY), c->g, img_ro(a->input_tex), img_ro(a->history_tex), img_ro(a->variance_history_tex), img_ro(a->reprojection_tex), img_ro(a->rt_history_invalidity_tex),
                img_rw(a->output_tex), img_rw(a->history_output_tex), img_rw(a->variance_history_output_tex), F4A(a->output_tex_size), wt);

@@ -106,6 +106,11 @@ inline float2 lerp(float2 a, float2 b, float t) { return float2(kjb_lerp(a.x, b.
 inline float2 saturate(float2 a) { return float2(saturate(a.x), saturate(a.y)); }
 inline float3 saturate(float3 a) { return float3(saturate(a.x), saturate(a.y), saturate(a.z)); }
 // dot products: left-to-right FMA chains (the evaluation order both sides of the parity agree on)
+// HLSL mad(): a * s + c with one rounding per component (the filters' weighted-sum taps; mirrors kjb_device.cuh)
+inline float  mad(float a, float s, float c) { return kjb_fma(a, s, c); }
+inline float2 mad(float2 a, float s, float2 c) { return float2(kjb_fma(a.x, s, c.x), kjb_fma(a.y, s, c.y)); }
+inline float3 mad(float3 a, float s, float3 c) { return float3(kjb_fma(a.x, s, c.x), kjb_fma(a.y, s, c.y), kjb_fma(a.z, s, c.z)); }
+inline float4 mad(float4 a, float s, float4 c) { return float4(kjb_fma(a.x, s, c.x), kjb_fma(a.y, s, c.y), kjb_fma(a.z, s, c.z), kjb_fma(a.w, s, c.w)); }
 inline float dot(float2 a, float2 b) { return kjb_fma(a.y, b.y, a.x * b.x); }
 inline float dot(float3 a, float3 b) { return kjb_fma(a.z, b.z, kjb_fma(a.y, b.y, a.x * b.x)); }
 inline float dot(float4 a, float4 b) { return kjb_fma(a.w, b.w, kjb_fma(a.z, b.z, kjb_fma(a.y, b.y, a.x * b.x))); }

@@ -304,7 +304,7 @@ int kjb_pass_rtdgi_validity_integrate(kjb_context* ctx, const kjb_rtdgi_validity
         const int k = 2;
         for (int yy = -k; yy <= k; ++yy) for (int xx = -k; xx <= k; ++xx) {
             float w = exp2(-0.1f * float(xx * xx + yy * yy));
-            invalid_blurred += float2(input_tex.load(x + xx, y + yy).x, 1) * w;
+            invalid_blurred = mad(float2(input_tex.load(x + xx, y + yy).x, 1), w, invalid_blurred);
         }
         invalid_blurred = invalid_blurred / invalid_blurred.y;
         A[size_t(y) * PW + x] = invalid_blurred.x;
@@ -759,7 +759,7 @@ int kjb_pass_rtdgi_restir_resolve(kjb_context* ctx, const kjb_rtdgi_restir_resol
                     float w = 1;
                     w *= ggx_ndf_unnorm(0.01f, saturate(dot(center_normal_vs, sample_normal_vs)));
                     w *= exp2(-200.0f * abs(center_normal_vs.z * (center_depth / rpx_depth - 1.0f)));
-                    weighted_irradiance += contribution * w;
+                    weighted_irradiance = mad(contribution, w, weighted_irradiance);
                     w_sum += w;
                 }
             }
@@ -798,7 +798,7 @@ int kjb_pass_rtdgi_restir_resolve(kjb_context* ctx, const kjb_rtdgi_restir_resol
                     w *= ggx_ndf_unnorm(0.01f, saturate(dot(center_normal_vs, sample_normal_vs)));
                     w *= exp2(-200.0f * abs(center_normal_vs.z * (center_depth / rpx_depth - 1.0f)));
                     w *= exp2(-20.0f * abs(center_ssao - sample_ssao));
-                    weighted_irradiance += contribution * w;
+                    weighted_irradiance = mad(contribution, w, weighted_irradiance);
                     w_sum += w;
                 }
             }
@@ -832,12 +832,12 @@ int kjb_pass_rtdgi_temporal(kjb_context* ctx, const kjb_rtdgi_temporal_args* a) 
             float4 hist_neigh = linear_rgb_to_crunched_luma_chroma(history_tex.load(x + xx, y + yy) * history_mult);
             float neigh_luma = neigh.x, hist_luma = hist_neigh.x;
             float w = exp(-3.0f * float(xx * xx + yy * yy) / float((k + 1.) * (k + 1.)));
-            vsum += neigh * w;
-            vsum2 += neigh * neigh * w;
+            vsum = mad(neigh, w, vsum);
+            vsum2 = mad(neigh * neigh, w, vsum2);
             wsum += w;
             hist_diff += abs(neigh_luma - hist_luma) / max(1e-5f, neigh_luma + hist_luma) * w;
-            hist_vsum += hist_luma * w;
-            hist_vsum2 += hist_luma * hist_luma * w;
+            hist_vsum = mad(hist_luma, w, hist_vsum);
+            hist_vsum2 = mad(hist_luma * hist_luma, w, hist_vsum2);
         }
         float4 ex = vsum / wsum, ex2 = vsum2 / wsum;
         float4 dev = sqrt(max(float4(0.0f), ex2 - ex * ex));
@@ -909,7 +909,7 @@ int kjb_pass_rtdgi_spatial(kjb_context* ctx, const kjb_rtdgi_spatial_args* a) {
                 float wt = 1;
                 wt *= exp2(-100.0f * abs(center_normal_vs.z * (center_depth / sample_depth - 1.0f)));
                 wt *= exp2(-20.0f * abs(sample_ssao - center_ssao));
-                sum += float4(crunch(sample_val), 1.0f) * wt;
+                sum = mad(float4(crunch(sample_val), 1.0f), wt, sum);
             }
         }
         float norm_factor = 1.0f / max(1e-5f, sum.w);
