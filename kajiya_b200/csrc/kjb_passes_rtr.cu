@@ -617,7 +617,7 @@ KJB_KERNEL(256) k_rtr_temporal(Globals g, RtrTemporalImgs t, float4 ots, Rows kj
         const float4 neigh = linear_to_working(inb(t.input_tex, x + xx, y + yy) ? f4(ld_r11g11b10(t.input_tex, x + xx, y + yy), 1) : f4(0.0f));
         float w = 1;
         w *= kjb_exp2(-200.0f * kjb_abs(center_depth / sample_depth - 1.0f));
-        vsum += neigh * w; vsum2 += neigh * neigh * w; wsum += w;
+        vsum = mad(neigh, w, vsum); vsum2 = mad(neigh * neigh, w, vsum2); wsum += w;
     }
     const float4 ex = vsum / wsum, ex2 = vsum2 / wsum;
     const float4 dev = vsqrt(vmax(f4(0.0f), ex2 - ex * ex));
@@ -676,7 +676,7 @@ KJB_KERNEL(256) k_rtr_cleanup(Globals g, Img input_tex, Img depth_tex, Img geome
         w *= kjb_exp2(-50.0f * kjb_abs(center_normal_vs.z * (center_depth / sample_depth - 1.0f)));
         const float dp = kjb_saturate(dot(center_normal_vs, sample_normal_vs));
         w *= dp * dp * dp;
-        vsum += neigh * w; wsum += w;
+        vsum = mad(neigh, w, vsum); wsum += w;
     }
     const float3 v = vsum / wsum;
     st_r11g11b10(output_tex, x, y, v * v);   // crunched_rgb_to_linear_rgb

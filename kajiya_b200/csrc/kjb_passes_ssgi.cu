@@ -120,7 +120,7 @@ KJB_KERNEL(256) k_ssao_spatial(Img ssgi_tex, Img depth_tex, Img normal_tex, ImgW
                 float normal_factor = kjb_max(0.0f, dot(xyz(ld_rgba8s(normal_tex, x + xx, y + yy)), center_normal));
                 normal_factor *= normal_factor; normal_factor *= normal_factor;
                 float w = 1; w *= depth_factor; w *= normal_factor;
-                w_sum += w; result += ld_r16f(ssgi_tex, x + xx, y + yy) * w;
+                w_sum += w; result = mad(ld_r16f(ssgi_tex, x + xx, y + yy), w, result);
             }
         }
     }
@@ -140,7 +140,7 @@ KJB_KERNEL(256) k_ssao_upsample(Img ssgi_tex, Img depth_tex, ImgW output_tex, W9
             if (depth != 0.0f) {
                 float w = 1; w *= kjb_exp2(-200.0f * kjb_abs(1.0f - (center_depth / depth)));
                 w *= gw.w[(yy + 1) * 3 + (xx + 1)];
-                w_sum += w; result += ld_r16f(ssgi_tex, spx, spy) * w;
+                w_sum += w; result = mad(ld_r16f(ssgi_tex, spx, spy), w, result);
             }
         }
     }
@@ -160,7 +160,7 @@ KJB_KERNEL(256) k_ssao_temporal(Img input_tex, Img history_tex, Img reprojection
     for (int yy = -2; yy <= 2; ++yy) for (int xx = -2; xx <= 2; ++xx) {
         const float neigh = ld_r16f(input_tex, x + xx * 2, y + yy * 2);
         const float w = gw.w[(yy + 2) * 5 + (xx + 2)];
-        vsum += neigh * w; vsum2 += neigh * neigh * w; wsum += w;
+        vsum = mad(neigh, w, vsum); vsum2 = mad(neigh * neigh, w, vsum2); wsum += w;
     }
     const float ex = vsum / wsum, ex2 = vsum2 / wsum;
     const float dev = kjb_sqrt(kjb_max(0.0f, ex2 - ex * ex));

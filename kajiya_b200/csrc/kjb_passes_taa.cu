@@ -82,7 +82,7 @@ KJB_DEV FilteredInput t2_inner(const Img& input_tex, const Img& depth_tex, int p
         w *= kjb_exp2(-kjb_min(16.0f, depth_scale * inverse_depth_relative_diff(center_depth, depth)));
         w *= dw[(y + 1) * 3 + (x + 1)];
         w *= kjb_pow(kjb_saturate(luma_cutoff / s.x), 8.0f);
-        clamped_iwsum += w; clamped_iex += s * w;
+        clamped_iwsum += w; clamped_iex = mad(s, w, clamped_iex);
         iwsum += 1; iex += s; iex2 += s * s;
     }
     FilteredInput r; r.clamped_ex = clamped_iex / clamped_iwsum;
@@ -108,7 +108,7 @@ KJB_DEV float3 t3_filter(const Img& input_tex, float2 uv, float4 its, float luma
         float w = 1;
         w *= dw[(y + 2) * 5 + (x + 2)];
         w *= kjb_pow(kjb_saturate(luma_cutoff / s.x), 8.0f);
-        iwsum += w; iex += s * w;
+        iwsum += w; iex = mad(s, w, iex);
     }
     return iex / iwsum;
 }
@@ -183,8 +183,8 @@ KJB_DEV Unjittered sample_image_unjitter_taa(const Img& img, int ox, int oy, flo
         const float dist2 = dot(sco, sco);
         const float dev_wt = kjb_exp2(-dist2 * irs.x);
         const float wt = kjb_exp2(-10 * dist2 * irs.x);
-        res += col * wt; wt_sum += wt;
-        ex += xyz(col) * dev_wt; ex2 += xyz(col) * xyz(col) * dev_wt; dev_wt_sum += dev_wt;
+        res = mad(col, wt, res); wt_sum += wt;
+        ex = mad(xyz(col), dev_wt, ex); ex2 = mad(xyz(col) * xyz(col), dev_wt, ex2); dev_wt_sum += dev_wt;
     }
     Unjittered u; u.color = res; u.coverage = wt_sum; u.ex = ex / dev_wt_sum; u.ex2 = ex2 / dev_wt_sum;
     return u;
@@ -207,7 +207,7 @@ KJB_KERNEL(256) k_taa(Globals g, TaaImgs t, float4 its, float4 ots, W25t bw, Row
         float4 csum = f4(0.0f); float wsum = 0;
         for (int yy = -2; yy <= 2; ++yy) for (int xx = -2; xx <= 2; ++xx) {
             const float w = bw.w[(yy + 2) * 5 + (xx + 2)];
-            csum += ld_rgba16f(t.history_tex, x + xx, y + yy) * w; wsum += w;
+            csum = mad(ld_rgba16f(t.history_tex, x + xx, y + yy), w, csum); wsum += w;
         }
         bhistory_packed = csum / wsum;
     }

@@ -663,7 +663,7 @@ int kjb_pass_rtr_temporal(kjb_context* ctx, const kjb_rtr_temporal_args* a) {
             const float4 neigh = linear_rgb_to_crunched_luma_chroma(input_tex.load(sample_px));
             float w = 1;
             w *= exp2(-200.0f * abs(center_depth / sample_depth - 1.0f));
-            vsum += neigh * w; vsum2 += neigh * neigh * w; wsum += w;
+            vsum = mad(neigh, w, vsum); vsum2 = mad(neigh * neigh, w, vsum2); wsum += w;
         }
         const float4 ex = vsum / wsum, ex2 = vsum2 / wsum;
         const float4 dev = sqrt(max(float4(0.0f), ex2 - ex * ex));
@@ -736,7 +736,7 @@ int kjb_pass_rtr_cleanup(kjb_context* ctx, const kjb_rtr_cleanup_args* a) {
             w *= exp2(-50.0f * abs(center_normal_vs.z * (center_depth / sample_depth - 1.0f)));
             const float dp = saturate(dot(center_normal_vs, sample_normal_vs));
             w *= dp * dp * dp;
-            vsum += neigh * w; wsum += w;
+            vsum = mad(neigh, w, vsum); wsum += w;
         }
         const float3 v = vsum / wsum;
         output_tex.store(px, float4(v * v, 1));   // crunched_rgb_to_linear_rgb

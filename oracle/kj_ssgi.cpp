@@ -145,7 +145,7 @@ int kjb_pass_ssao_spatial(kjb_context* ctx, const kjb_ssao_spatial_args* a) {
                     float normal_factor = max(0.0f, dot(normal, center_normal));
                     normal_factor *= normal_factor; normal_factor *= normal_factor;
                     float w = 1; w *= depth_factor; w *= normal_factor;
-                    w_sum += w; result += ssgi * w;
+                    w_sum += w; result = mad(ssgi, w, result);
                 }
             }
         }
@@ -172,7 +172,7 @@ int kjb_pass_ssao_upsample(kjb_context* ctx, const kjb_ssao_upsample_args* a) {
                     const float depth_factor = exp2(-200.0f * abs(depth_diff));
                     float w = 1; w *= depth_factor;
                     w *= exp(-dot(float2(float(xx), float(yy)), float2(float(xx), float(yy))));
-                    w_sum += w; result += ssgi * w;
+                    w_sum += w; result = mad(ssgi, w, result);
                 }
             }
         }
@@ -198,7 +198,7 @@ int kjb_pass_ssao_temporal(kjb_context* ctx, const kjb_ssao_temporal_args* a) {
         for (int yy = -k; yy <= k; ++yy) for (int xx = -k; xx <= k; ++xx) {
             const float4 neigh = input_tex.load(x + xx * 2, y + yy * 2);
             const float w = exp(-3.0f * float(xx * xx + yy * yy) / float((k + 1.) * (k + 1.)));
-            vsum += neigh * w; vsum2 += neigh * neigh * w; wsum += w;
+            vsum = mad(neigh, w, vsum); vsum2 = mad(neigh * neigh, w, vsum2); wsum += w;
         }
         const float4 ex = vsum / wsum, ex2 = vsum2 / wsum;
         const float4 dev = sqrt(max(float4(0.0f), ex2 - ex * ex));

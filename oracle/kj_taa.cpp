@@ -56,8 +56,8 @@ UnjitteredSampleInfo sample_image_unjitter_taa(const Img& img, int2 output_px, f
         float dist2 = dot(sco, sco);
         float dev_wt = exp2(-dist2 * irs.x);
         float wt = exp2(-10 * dist2 * irs.x);
-        res += col * wt; wt_sum += wt;
-        ex += col.xyz() * dev_wt; ex2 += col.xyz() * col.xyz() * dev_wt; dev_wt_sum += dev_wt;
+        res = mad(col, wt, res); wt_sum += wt;
+        ex = mad(col.xyz(), dev_wt, ex); ex2 = mad(col.xyz() * col.xyz(), dev_wt, ex2); dev_wt_sum += dev_wt;
     }
     UnjitteredSampleInfo info; info.color = res; info.coverage = wt_sum; info.ex = ex / dev_wt_sum; info.ex2 = ex2 / dev_wt_sum;
     return info;
@@ -121,7 +121,7 @@ int kjb_pass_taa_filter_input(kjb_context* ctx, const kjb_taa_filter_input_args*
             w *= exp2(-min(16.0f, depth_scale * inverse_depth_relative_diff(center_depth, depth)));
             w *= distance_w;
             w *= pow(saturate(luma_cutoff / s.x), 8.0f);
-            clamped_iwsum += w; clamped_iex += s * w;
+            clamped_iwsum += w; clamped_iex = mad(s, w, clamped_iex);
             iwsum += 1; iex += s; iex2 += s * s;
         }
         clamped_iex = clamped_iex / clamped_iwsum;
@@ -153,7 +153,7 @@ int kjb_pass_taa_filter_history(kjb_context* ctx, const kjb_taa_filter_history_a
             float w = 1;
             w *= distance_w;
             w *= pow(saturate(luma_cutoff / s.x), 8.0f);
-            iwsum += w; iex += s * w;
+            iwsum += w; iex = mad(s, w, iex);
         }
         return iex / iwsum;
     };
@@ -247,7 +247,7 @@ int kjb_pass_taa(kjb_context* ctx, const kjb_taa_args* a) {
                 float4 c = history_tex.load(x + xx, y + yy);
                 float2 offset = float2(float(xx), float(yy)) * 1.0f;
                 float w = exp(-dot(offset, offset));
-                csum += c * w; wsum += w;
+                csum = mad(c, w, csum); wsum += w;
             }
             bhistory_packed = csum / wsum;
         }
