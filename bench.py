@@ -52,7 +52,7 @@ PASS_BYTES = {
 # DRAM bytes per launch of each kernel, from one `ncu --set full` capture of the default workload (profiles/r01c_full_summary.csv:
 # dram__bytes_read.sum + dram__bytes_write.sum).  Far below the algorithmic bytes: the frame's working set stays in the 126 MB L2.
 NCU_TRAFFIC_1080P = {"rtdgi reproject": 22.97e6, "rtdgi validate": 4.21e6, "rtdgi trace": 15.18e6, "validity integrate": 21.28e6, "restir temporal": 23.39e6,
-                     "restir spatial": 12.01e6, "restir resolve": 33.74e6, "rtdgi temporal": 71.35e6, "rtdgi spatial": 35.46e6}
+                     "restir spatial": 18.27e6, "restir resolve": 41.21e6, "rtdgi temporal": 72.08e6, "rtdgi spatial": 35.46e6}   # the three heaviest: profiles/r01s_top3_summary.csv
 
 
 def pass_bytes(label, F, Hh, validation_frame_fraction=1.0 / 3.0):
@@ -269,7 +269,8 @@ def run_cuda(args):
     per_pass = {k: v[1] / max(v[0], 1) for k, v in timings.items() if k in PASS_BYTES}
     calls = {k: v[0] for k, v in timings.items()}
     share = {k: timings[k][1] for k in per_pass}
-    dom = max(share, key=share.get)
+    # the dominant KERNEL: the exchange entry is a wait on the communication queue (pack + ncclAllGather + unpack, overlapped with compute), not one of our kernels
+    dom = max((k for k in share if k != "tile border all-gather"), key=share.get)
     dom_bytes = pass_bytes(dom, F, Hh)
     achieved = dom_bytes / (per_pass[dom] * 1e-3) / 1e9
     frame_bytes = sum(pass_bytes(k, F, Hh) * (calls[k] / K) for k in per_pass)
@@ -289,7 +290,7 @@ def run_cuda(args):
         "gpu_launches": int(launches),
         "clocks": clock_info,
         "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": NCU_TRAFFIC_1080P.get(dom) if workload == "cornell_1080p_rtdgi_1s1t" and world_size == 1 else None, "traffic_source": "profiles/r01c_full_summary.csv",
+                     "traffic": NCU_TRAFFIC_1080P.get(dom) if workload == "cornell_1080p_rtdgi_1s1t" and world_size == 1 else None, "traffic_source": "profiles/r01s_top3_summary.csv, profiles/r01c_full_summary.csv",
                      "peak_source": peak_src, "kernel_ms": per_pass[dom], "kernel_share_of_step": share[dom] / sum(share.values()),
                      "algorithmic_bytes_per_launch": dom_bytes,
                      "frame": {"algorithmic_bytes": frame_bytes, "achieved_gbs": frame_bytes / (frame_ms * 1e-3) / 1e9, "frac": frame_bytes / (frame_ms * 1e-3) / 1e9 / peak},
