@@ -116,9 +116,31 @@ KJB_HD float kjb_fma(float a, float b, float c) {
 
 /* ---- elementary helpers with HLSL semantics ---- */
 /* HLSL/DXIL FMin/FMax = IEEE minNum/maxNum: a NaN operand loses (the shaders rely on it, e.g. `max(0.0, dot(n, NaN_dir))`
- * for neighbours at depth 0 in restir_resolve.hlsl:112-114).  Same as CUDA fminf/fmaxf. */
-KJB_HD float kjb_min(float a, float b) { return (a < b || b != b) ? a : b; }
-KJB_HD float kjb_max(float a, float b) { return (a > b || b != b) ? a : b; }
+ * for neighbours at depth 0 in restir_resolve.hlsl:112-114).  Signed zeros are ordered -0 < +0 and two NaNs give the canonical
+ * 0x7fffffff (IEEE 754-2019 minimumNumber / maximumNumber): exactly what the single FMNMX instruction behind fminf/fmaxf returns on
+ * sm_100a (probed: tools/probe_minmax.cu, profiles/r01u_probe_minmax.txt), spelled out for the host. */
+KJB_HD float kjb_min(float a, float b) {
+#if defined(__CUDA_ARCH__)
+    return fminf(a, b);
+#else
+    if (a != a) return b == b ? b : kjb_u2f(0x7fffffffu);
+    if (b != b) return a;
+    if (a < b) return a;
+    if (b < a) return b;
+    return kjb_u2f(kjb_f2u(a) | kjb_f2u(b));   /* equal: identical bits, or +-0 where the sign bit (the smaller one) wins */
+#endif
+}
+KJB_HD float kjb_max(float a, float b) {
+#if defined(__CUDA_ARCH__)
+    return fmaxf(a, b);
+#else
+    if (a != a) return b == b ? b : kjb_u2f(0x7fffffffu);
+    if (b != b) return a;
+    if (a > b) return a;
+    if (b > a) return b;
+    return kjb_u2f(kjb_f2u(a) & kjb_f2u(b));   /* equal: identical bits, or +-0 where +0 (the larger one) wins */
+#endif
+}
 KJB_HD float kjb_clamp(float x, float lo, float hi) { return kjb_min(kjb_max(x, lo), hi); }
 KJB_HD float kjb_saturate(float x) {
 #if defined(__CUDA_ARCH__)

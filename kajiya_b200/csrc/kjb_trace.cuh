@@ -49,16 +49,9 @@ KJB_DEV bool intersect_leaf(const BvhTri* tris, uint32_t first, uint32_t count, 
     return false;
 }
 
-// min/max of the slab test: the result only steers the walk (boxes are conservative and the hit rule does not depend on the
-// topology), so the single-instruction FMNMX forms are used on the device — they differ from kjb_min/kjb_max only in the sign of a
-// zero result, which no comparison below can see.
-#if defined(__CUDA_ARCH__)
-#define KJB_SLAB_MIN fminf
-#define KJB_SLAB_MAX fmaxf
-#else
+// the slab test's min/max are kjb_min / kjb_max: one FMNMX each on the device (include/kjb_numeric.h)
 #define KJB_SLAB_MIN kjb_min
 #define KJB_SLAB_MAX kjb_max
-#endif
 template <bool ANY_HIT>
 KJB_DEV HitInfo trace(const SceneView& sc, const Ray& r, bool cull_back) {
     HitInfo best; best.hit = false; best.t = r.tmax; best.u = 0; best.v = 0; best.gid = 0xffffffffu;
