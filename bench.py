@@ -34,7 +34,7 @@ WORKLOADS = {
 
 # compulsory bytes per pixel of each pass at its own grid (F = full-res px, Hh = half-res px)
 PASS_BYTES = {
-    "rtdgi reproject": ("F", 24), "extract ssao/2": ("Hh", 2), "extract half depth": ("Hh", 8), "extract view normal/2": ("Hh", 20),
+    "rtdgi reproject": ("F", 24), "extract ssao/2": ("Hh", 2), "extract half-res inputs": ("Hh", 30), "extract half depth": ("Hh", 8), "extract view normal/2": ("Hh", 20),
     "rtdgi validate": ("Hh", 5), "rtdgi trace": ("Hh", 38), "validity integrate": ("Hh", 21), "restir temporal": ("Hh", 160),
     "restir spatial": ("Hh", 41), "restir resolve": ("F+Hh", (29, 56)), "rtdgi temporal": ("F+Hh", (48, 4)), "rtdgi spatial": ("F", 25),
     # rtr (44 + 45 + 152 Hh; 36 F + 60 Hh; 52 F + 1 Hh; 20 F)

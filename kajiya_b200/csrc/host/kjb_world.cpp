@@ -658,7 +658,13 @@ static void rtdgi_render(kjb_world* w, kjb_image& reprojected_history_tex, kjb_i
     w->rows_all();   // the half-res extracts are cheap and read at arbitrary screen positions (ray march): whole image
 
     kjb_image& half_ssao_tex = w->img("rtdgi.half_ssao", HW, HH, KJB_FMT_R8_SNORM);
-    { kjb_extract_half_res_args a{ssao_tex, half_ssao_tex}; RUN("extract ssao/2", kjb_pass_extract_half_res_ssao(ctx, &a)); }
+    kjb_image& half_depth_tex = w->img("half_depth", HW, HH, KJB_FMT_R32_FLOAT);
+    kjb_image& half_view_normal_tex = w->img("half_view_normal", HW, HH, KJB_FMT_RGBA8_SNORM);
+    if (w->half_depth_frame != w->frame_idx && w->half_normal_frame != w->frame_idx) {   // nothing extracted yet this frame: the three reference passes in one launch
+        kjb_extract_half_res_fused_args a{gbuffer, depth, ssao_tex, half_view_normal_tex, half_depth_tex, half_ssao_tex};
+        RUN("extract half-res inputs", kjb_pass_extract_half_res_fused(ctx, &a));
+        w->half_depth_frame = w->half_normal_frame = w->frame_idx;
+    } else { kjb_extract_half_res_args a{ssao_tex, half_ssao_tex}; RUN("extract ssao/2", kjb_pass_extract_half_res_ssao(ctx, &a)); }
 
     kjb_image *hit_normal_output_tex, *hit_normal_history_tex; w->get_output_and_history(w->temporal_hit_normal_tex, HW, HH, KJB_FMT_RGBA8_UNORM, hit_normal_output_tex, hit_normal_history_tex);
     kjb_image *candidate_output_tex, *candidate_history_tex; w->get_output_and_history(w->temporal_candidate_tex, HW, HH, KJB_FMT_RGBA16_FLOAT, candidate_output_tex, candidate_history_tex);
@@ -667,7 +673,6 @@ static void rtdgi_render(kjb_world* w, kjb_image& reprojected_history_tex, kjb_i
     kjb_image& candidate_hit_tex = w->img("rtdgi.candidate_hit", HW, HH, KJB_FMT_RGBA16_FLOAT);
     kjb_image& temporal_reservoir_packed_tex = w->img("rtdgi.temporal_reservoir_packed", HW, HH, KJB_FMT_RGBA32_UINT);
 
-    kjb_image& half_depth_tex = w->img("half_depth", HW, HH, KJB_FMT_R32_FLOAT);
     if (w->half_depth_frame != w->frame_idx) { kjb_extract_half_res_args a{depth, half_depth_tex}; RUN("extract half depth", kjb_pass_extract_half_res_depth(ctx, &a)); w->half_depth_frame = w->frame_idx; }
 
     kjb_image *invalidity_output_tex, *invalidity_history_tex; w->get_output_and_history(w->temporal_invalidity_tex, HW, HH, KJB_FMT_RG16_FLOAT, invalidity_output_tex, invalidity_history_tex);
@@ -675,7 +680,6 @@ static void rtdgi_render(kjb_world* w, kjb_image& reprojected_history_tex, kjb_i
     kjb_image *ray_orig_output_tex, *ray_orig_history_tex; w->get_output_and_history(w->temporal_ray_orig_tex, HW, HH, KJB_FMT_RGBA32_FLOAT, ray_orig_output_tex, ray_orig_history_tex);
     kjb_image *ray_output_tex, *ray_history_tex; w->get_output_and_history(w->temporal_ray_tex, HW, HH, KJB_FMT_RGBA16_FLOAT, ray_output_tex, ray_history_tex);
 
-    kjb_image& half_view_normal_tex = w->img("half_view_normal", HW, HH, KJB_FMT_RGBA8_SNORM);
     if (w->half_normal_frame != w->frame_idx) { kjb_extract_half_res_args a{gbuffer, half_view_normal_tex}; RUN("extract view normal/2", kjb_pass_extract_half_res_view_normal(ctx, &a)); w->half_normal_frame = w->frame_idx; }
 
     kjb_image& rt_history_validity_pre_input_tex = w->img("rtdgi.rt_history_validity_pre_input", HW, HH, KJB_FMT_R8_UNORM);
@@ -793,8 +797,13 @@ static kjb_image& ssgi_render(kjb_world* w, kjb_image& gbuffer, kjb_image& depth
     const uint32_t HW = w->HW, HH = w->HH, W = w->W, H = w->H;
     w->rows_all();   // four small passes: every rank of a tiled frame computes the whole image
     kjb_image& half_view_normal_tex = w->img("half_view_normal", HW, HH, KJB_FMT_RGBA8_SNORM);
-    if (w->half_normal_frame != w->frame_idx) { kjb_extract_half_res_args a{gbuffer, half_view_normal_tex}; RUN("extract view normal/2", kjb_pass_extract_half_res_view_normal(ctx, &a)); w->half_normal_frame = w->frame_idx; }
     kjb_image& half_depth_tex = w->img("half_depth", HW, HH, KJB_FMT_R32_FLOAT);
+    if (w->half_depth_frame != w->frame_idx && w->half_normal_frame != w->frame_idx) {
+        kjb_extract_half_res_fused_args a{gbuffer, depth, kjb_image{}, half_view_normal_tex, half_depth_tex, kjb_image{}};
+        RUN("extract half-res inputs", kjb_pass_extract_half_res_fused(ctx, &a));
+        w->half_depth_frame = w->half_normal_frame = w->frame_idx;
+    }
+    if (w->half_normal_frame != w->frame_idx) { kjb_extract_half_res_args a{gbuffer, half_view_normal_tex}; RUN("extract view normal/2", kjb_pass_extract_half_res_view_normal(ctx, &a)); w->half_normal_frame = w->frame_idx; }
     if (w->half_depth_frame != w->frame_idx) { kjb_extract_half_res_args a{depth, half_depth_tex}; RUN("extract half depth", kjb_pass_extract_half_res_depth(ctx, &a)); w->half_depth_frame = w->frame_idx; }
     kjb_image& raw = w->img("ssgi.raw", HW, HH, KJB_FMT_R16_FLOAT);
     {

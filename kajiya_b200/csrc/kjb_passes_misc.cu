@@ -183,6 +183,16 @@ KJB_KERNEL(256) k_extract_half_view_normal(Globals g, Img in, ImgW out, int2 off
     const float3 normal_vs = normalize(xyz(mul(g.fc.view_constants.world_to_view, f4(normal_ws, 0))));
     st_rgba8s(out, x, y, f4(normal_vs, 1));
 }
+KJB_KERNEL(256) k_extract_half_fused(Globals g, Img gbuffer, Img depth, Img ssao, ImgW out_normal, ImgW out_depth, ImgW out_ssao, int with_ssao, int2 off, Rows kjb_rows) {
+    KJB_PX; if (x >= out_depth.w || y >= out_depth.h) return;
+    const int sx = x * 2 + off.x, sy = y * 2 + off.y;
+    st_r32f(out_depth, x, y, ld_r32f(depth, sx, sy));
+    const uint4 gbt = ld_rgba32u(gbuffer, sx, sy);
+    const float3 normal_ws = unpack_normal_11_10_11_no_normalize(gbt.y);
+    const float3 normal_vs = normalize(xyz(mul(g.fc.view_constants.world_to_view, f4(normal_ws, 0))));
+    st_rgba8s(out_normal, x, y, f4(normal_vs, 1));
+    if (with_ssao) st_r8s(out_ssao, x, y, ld_r8u(ssao, sx, sy));
+}
 
 extern "C" {
 
@@ -242,6 +252,19 @@ int kjb_pass_extract_half_res_depth(kjb_context* c, const kjb_extract_half_res_a
     KJB_ROWS(c, a->output_tex.height);
     KJB_LAUNCH(c, k_extract_half_depth, KJB_GRID2D(a->output_tex.width, a->output_tex.height, 32, 8), img_ro(a->input_tex), img_rw(a->output_tex), halfres_subsample_offset(c->g.fc.frame_index));
     KJB_PASS_EPILOGUE(c, "extract half depth");
+}
+int kjb_pass_extract_half_res_fused(kjb_context* c, const kjb_extract_half_res_fused_args* a) {
+    const char* P = "extract half-res inputs";
+    c->epoch_a++;   // half_depth changes: the position cache built from it is stale
+    const uint32_t W = a->half_depth_out.width, H = a->half_depth_out.height;
+    const bool with_ssao = a->ssao_tex.data != nullptr && a->half_ssao_out.data != nullptr;
+    if (!check_img(c, a->gbuffer_tex, KJB_FMT_RGBA32_FLOAT, P, "gbuffer_tex") || !check_img(c, a->depth_tex, KJB_FMT_R32_FLOAT, P, "depth_tex") ||
+        !check_img(c, a->half_depth_out, KJB_FMT_R32_FLOAT, P, "half_depth_out") || !check_img(c, a->half_view_normal_out, KJB_FMT_RGBA8_SNORM, P, "half_view_normal_out", W, H)) return 1;
+    if (with_ssao && (!check_img(c, a->ssao_tex, KJB_FMT_R8_UNORM, P, "ssao_tex") || !check_img(c, a->half_ssao_out, KJB_FMT_R8_SNORM, P, "half_ssao_out", W, H))) return 1;
+    KJB_ROWS(c, H);
+    KJB_LAUNCH(c, k_extract_half_fused, KJB_GRID2D(W, H, 32, 8), c->g, img_ro(a->gbuffer_tex), img_ro(a->depth_tex), img_ro(with_ssao ? a->ssao_tex : a->depth_tex), img_rw(a->half_view_normal_out),
+               img_rw(a->half_depth_out), img_rw(with_ssao ? a->half_ssao_out : a->half_depth_out), with_ssao ? 1 : 0, halfres_subsample_offset(c->g.fc.frame_index));
+    KJB_PASS_EPILOGUE(c, P);
 }
 int kjb_pass_extract_half_res_ssao(kjb_context* c, const kjb_extract_half_res_args* a) {
     if (!check_img(c, a->input_tex, KJB_FMT_R8_UNORM, "extract ssao/2", "input_tex") || !check_img(c, a->output_tex, KJB_FMT_R8_SNORM, "extract ssao/2", "output_tex")) return 1;

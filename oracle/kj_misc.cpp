@@ -190,6 +190,12 @@ int kjb_pass_extract_half_res_depth(kjb_context* ctx, const kjb_extract_half_res
 int kjb_pass_extract_half_res_ssao(kjb_context* ctx, const kjb_extract_half_res_args* a) {
     return kjb_pass_extract_half_res_depth(ctx, a);
 }
+int kjb_pass_extract_half_res_fused(kjb_context* ctx, const kjb_extract_half_res_fused_args* a) {   // the product's one-launch fusion = the reference's three passes
+    kjb_extract_half_res_args d{a->depth_tex, a->half_depth_out}, n{a->gbuffer_tex, a->half_view_normal_out}, s{a->ssao_tex, a->half_ssao_out};
+    int rc = kjb_pass_extract_half_res_depth(ctx, &d) | kjb_pass_extract_half_res_view_normal(ctx, &n);
+    if (a->ssao_tex.data && a->half_ssao_out.data) rc |= kjb_pass_extract_half_res_ssao(ctx, &s);
+    return rc;
+}
 int kjb_pass_extract_half_res_view_normal(kjb_context* ctx, const kjb_extract_half_res_args* a) {   // extract_half_res_gbuffer_view_normal_rgba8.hlsl:15-53 ("tired" branch)
     Img in(a->input_tex), out(a->output_tex); const int2 o = halfres_subsample_offset(ctx->g.fc.frame_index);
     const kjb_view_constants& vc = ctx->g.fc.view_constants;
