@@ -183,10 +183,15 @@ KJB_KERNEL(256) k_extract_half_view_normal(Globals g, Img in, ImgW out, int2 off
     const float3 normal_vs = normalize(xyz(mul(g.fc.view_constants.world_to_view, f4(normal_ws, 0))));
     st_rgba8s(out, x, y, f4(normal_vs, 1));
 }
-KJB_KERNEL(256) k_extract_half_fused(Globals g, Img gbuffer, Img depth, Img ssao, ImgW out_normal, ImgW out_depth, ImgW out_ssao, int with_ssao, int2 off, Rows kjb_rows) {
+KJB_KERNEL(256) k_extract_half_fused(Globals g, Img gbuffer, Img depth, Img ssao, ImgW out_normal, ImgW out_depth, ImgW out_ssao, int with_ssao, int2 off, float4* positions, float4 gts, Rows kjb_rows) {
     KJB_PX; if (x >= out_depth.w || y >= out_depth.h) return;
     const int sx = x * 2 + off.x, sy = y * 2 + off.y;
-    st_r32f(out_depth, x, y, ld_r32f(depth, sx, sy));
+    const float d = ld_r32f(depth, sx, sy);
+    st_r32f(out_depth, x, y, d);
+    if (positions) {   // KJB_OPTION_HALF_RES_POSITION_CACHE: the same expression k_half_res_positions evaluates (kjb_passes_rtdgi.cu)
+        const float s4[4] = {gts.x, gts.y, gts.z, gts.w};
+        positions[y * out_depth.w + x] = f4(hit_ws_from_uv_depth(g.fc.view_constants, get_uv(sx, sy, s4), d), 0.0f);
+    }
     const uint4 gbt = ld_rgba32u(gbuffer, sx, sy);
     const float3 normal_ws = unpack_normal_11_10_11_no_normalize(gbt.y);
     const float3 normal_vs = normalize(xyz(mul(g.fc.view_constants.world_to_view, f4(normal_ws, 0))));
@@ -262,8 +267,18 @@ int kjb_pass_extract_half_res_fused(kjb_context* c, const kjb_extract_half_res_f
         !check_img(c, a->half_depth_out, KJB_FMT_R32_FLOAT, P, "half_depth_out") || !check_img(c, a->half_view_normal_out, KJB_FMT_RGBA8_SNORM, P, "half_view_normal_out", W, H)) return 1;
     if (with_ssao && (!check_img(c, a->ssao_tex, KJB_FMT_R8_UNORM, P, "ssao_tex") || !check_img(c, a->half_ssao_out, KJB_FMT_R8_SNORM, P, "half_ssao_out", W, H))) return 1;
     KJB_ROWS(c, H);
+    // the half-res world positions D7/D9 want (kjb_set_option) come for free here when the launch covers the whole image
+    kjb_context::PosCache& pc = c->pos_a;
+    const float gts[4] = {float(a->gbuffer_tex.width), float(a->gbuffer_tex.height), 1.0f / float(a->gbuffer_tex.width), 1.0f / float(a->gbuffer_tex.height)};
+    float4* positions = nullptr;
+    if (c->opt_position_cache && kjb__rows.y0 == 0 && kjb__rows.y1 == int(H)) {
+        const size_t need = size_t(W) * H * sizeof(float4);
+        if (pc.cap < need) { dev_sync(c); dev_free(pc.d); pc.d = (float4*)dev_alloc(need); pc.cap = pc.d ? need : 0; }
+        positions = pc.d;
+    }
     KJB_LAUNCH(c, k_extract_half_fused, KJB_GRID2D(W, H, 32, 8), c->g, img_ro(a->gbuffer_tex), img_ro(a->depth_tex), img_ro(with_ssao ? a->ssao_tex : a->depth_tex), img_rw(a->half_view_normal_out),
-               img_rw(a->half_depth_out), img_rw(with_ssao ? a->half_ssao_out : a->half_depth_out), with_ssao ? 1 : 0, halfres_subsample_offset(c->g.fc.frame_index));
+               img_rw(a->half_depth_out), img_rw(with_ssao ? a->half_ssao_out : a->half_depth_out), with_ssao ? 1 : 0, halfres_subsample_offset(c->g.fc.frame_index), positions, f4(gts[0], gts[1], gts[2], gts[3]));
+    if (positions) { pc.epoch = c->epoch_a; pc.src = a->half_depth_out.data; pc.w = W; pc.h = H; memcpy(pc.gts, gts, 16); }
     KJB_PASS_EPILOGUE(c, P);
 }
 int kjb_pass_extract_half_res_ssao(kjb_context* c, const kjb_extract_half_res_args* a) {
