@@ -312,19 +312,23 @@ struct RestirTemporalImgs {
 #ifndef KJB_OCC_RESTIR_TEMPORAL
 #define KJB_OCC_RESTIR_TEMPORAL 4   /* 64 registers: 45 -> 36 us */
 #endif
-KJB_KERNEL_OCC(256, KJB_OCC_RESTIR_TEMPORAL) k_rtdgi_restir_temporal(Globals g, RestirTemporalImgs t, float4 gts, Rows kjb_rows) {
+KJB_KERNEL_OCC(256, KJB_OCC_RESTIR_TEMPORAL) k_rtdgi_restir_temporal(Globals g, RestirTemporalImgs t, float4 gts, float4* positions, Rows kjb_rows) {
     KJB_PX; if (x >= t.radiance_out_tex.w || y >= t.radiance_out_tex.h) return;
     const kjb_view_constants& vc = g.fc.view_constants;
     const uint32_t frame_index = g.fc.frame_index;
     const int2 hso = halfres_subsample_offset(frame_index);
     const int hx = x * 2 + hso.x, hy = y * 2 + hso.y;
     const float depth = ld_r32f(t.depth_tex, hx, hy);
-    if (0.0f == depth) {
-        st_rgba16f(t.radiance_out_tex, x, y, f4(0, 0, 0, -SKY_DIST)); st_rgba8u(t.hit_normal_output_tex, x, y, f4(0.0f)); st_rg32u(t.reservoir_out_tex, x, y, u2(0, 0));
-        return;
-    }
     const float s4[4] = {gts.x, gts.y, gts.z, gts.w};
     const float2 uv = get_uv(hx, hy, s4);
+    if (0.0f == depth) {
+        st_rgba16f(t.radiance_out_tex, x, y, f4(0, 0, 0, -SKY_DIST)); st_rgba8u(t.hit_normal_output_tex, x, y, f4(0.0f)); st_rg32u(t.reservoir_out_tex, x, y, u2(0, 0));
+        // temporal_reservoir_packed_tex keeps its old texel here (as in the shader): the cached position is that of the old depth word
+        if (positions) positions[y * t.radiance_out_tex.w + x] = f4(hit_ws_from_uv_depth(vc, uv, kjb_u2f(ld_rgba32u(as_ro(t.temporal_reservoir_packed_tex), x, y).x)), 0.0f);
+        return;
+    }
+    // KJB_OPTION_HALF_RES_POSITION_CACHE: what k_half_res_positions would compute from the depth word written below
+    if (positions) positions[y * t.radiance_out_tex.w + x] = f4(hit_ws_from_uv_depth(vc, uv, depth), 0.0f);
     const ViewRayContext vrc = ViewRayContext::from_uv_and_biased_depth(vc, uv, depth);
     const float3 normal_vs = xyz(ld_rgba8s(t.half_view_normal_tex, x, y));
     const float3 normal_ws = direction_view_to_world(vc, normal_vs);
@@ -915,7 +919,16 @@ int kjb_pass_rtdgi_restir_temporal(kjb_context* c, const kjb_rtdgi_restir_tempor
     t.ray_output_tex = img_rw(a->ray_output_tex); t.hit_normal_output_tex = img_rw(a->hit_normal_output_tex); t.reservoir_out_tex = img_rw(a->reservoir_out_tex);
     t.candidate_out_tex = img_rw(a->candidate_out_tex); t.temporal_reservoir_packed_tex = img_rw(a->temporal_reservoir_packed_tex);
     KJB_ROWS(c, H);
-    KJB_LAUNCH(c, k_rtdgi_restir_temporal, KJB_GRID2D(W, H, 32, 8), c->g, t, F4A(a->gbuffer_tex_size));
+    // the positions of the packed reservoirs' depth words (D7/D9 read them 8-16 times per pixel) ride along when the launch covers the whole image
+    kjb_context::PosCache& pc = c->pos_b;
+    float4* positions = nullptr;
+    if (c->opt_position_cache && kjb__rows.y0 == 0 && kjb__rows.y1 == int(H)) {
+        const size_t need = size_t(W) * H * sizeof(float4);
+        if (pc.cap < need) { dev_sync(c); dev_free(pc.d); pc.d = (float4*)dev_alloc(need); pc.cap = pc.d ? need : 0; }
+        positions = pc.d;
+    }
+    KJB_LAUNCH(c, k_rtdgi_restir_temporal, KJB_GRID2D(W, H, 32, 8), c->g, t, F4A(a->gbuffer_tex_size), positions);
+    if (positions) { pc.epoch = c->epoch_b; pc.src = a->temporal_reservoir_packed_tex.data; pc.w = W; pc.h = H; memcpy(pc.gts, a->gbuffer_tex_size, 16); }
     KJB_PASS_EPILOGUE(c, P);
 }
 int kjb_pass_rtdgi_restir_spatial(kjb_context* c, const kjb_rtdgi_restir_spatial_args* a) {

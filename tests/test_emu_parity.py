@@ -14,7 +14,7 @@ def test_cornell_lockstep(oracle_lib, emu_lib):
     scene, view = scenes.cornell_box()
     wa, wb, report = parity.run_lockstep(oracle_lib, emu_lib, scene, view, 96, 64, 7)
     _clean(report)
-    assert wb.stats()["launches"] == 14 and len(wb.image_names()) >= 40
+    assert wb.stats()["launches"] == 13 and len(wb.image_names()) >= 40
 
 
 def test_cornell_odd_extent_single_spatial_pass(oracle_lib, emu_lib):
@@ -63,7 +63,7 @@ def test_taa_native_and_upscaled(oracle_lib, emu_lib):
     for kw in (dict(enable_taa=True), dict(enable_taa=True, upscale=(150, 96))):
         wa, wb, report = parity.run_lockstep(oracle_lib, emu_lib, scene, view, 100, 64, 5, **kw)
         _clean(report)
-        assert "taa.this_frame_out" in wb.image_names() and wb.stats()["launches"] == 21
+        assert "taa.this_frame_out" in wb.image_names() and wb.stats()["launches"] == 20
 
 
 def _moving_views(view, frames):
@@ -213,11 +213,11 @@ def test_lighting_composite_feeds_taa(oracle_lib, emu_lib):
 
 
 def test_position_cache_is_invisible(emu_lib):
-    """KJB_OPTION_HALF_RES_POSITION_CACHE hoists hit_ws_from_uv_depth out of the D7/D9 neighbour loops: same bits, one more launch"""
+    """KJB_OPTION_HALF_RES_POSITION_CACHE hoists hit_ws_from_uv_depth out of the D7/D9 neighbour loops: same bits, no extra launch when the producers cover the whole image"""
     scene, view = scenes.cornell_box()
     wa, wb = parity.make_world(emu_lib, scene, 70, 46), parity.make_world(emu_lib, scene, 70, 46)
     wb.set_option(1, 0)
     for f in range(4):
         wa.render_frame(**view); wb.render_frame(**view)
         assert not parity.compare_images(wa, wb), f
-    assert wa.stats()["launches"] == wb.stats()["launches"] + 1   # the packed-reservoir positions; the half_depth ones ride in the fused extract
+    assert wa.stats()["launches"] == wb.stats()["launches"]   # both position sets ride in kernels that run anyway (fused extract, restir temporal)
