@@ -49,10 +49,12 @@ PASS_BYTES = {
     "ircache reset": ("const", 0), "ircache trace access": ("const", 0), "ircache validate": ("const", 0), "ircache trace": ("const", 0), "ircache sum": ("const", 0),
     "restir check": ("Hh", 28), "reprojection map": ("F", 28), "copy depth": ("F", 8),
 }
-# DRAM bytes per launch of each kernel, from one `ncu --set full` capture of the default workload (profiles/r01c_full_summary.csv:
-# dram__bytes_read.sum + dram__bytes_write.sum).  Far below the algorithmic bytes: the frame's working set stays in the 126 MB L2.
-NCU_TRAFFIC_1080P = {"rtdgi reproject": 22.97e6, "rtdgi validate": 4.21e6, "rtdgi trace": 15.18e6, "validity integrate": 21.28e6, "restir temporal": 23.39e6,
-                     "restir spatial": 18.27e6, "restir resolve": 41.21e6, "rtdgi temporal": 72.08e6, "rtdgi spatial": 35.46e6}   # the three heaviest: profiles/r01s_top3_summary.csv
+# DRAM bytes per launch of each kernel, from one `ncu --set full` capture of the default workload (profiles/r01v_full_summary.csv:
+# dram__bytes_read.sum + dram__bytes_write.sum; the captured frame is a validation frame).  Far below the algorithmic bytes: the frame's
+# working set stays in the 126 MB L2.
+NCU_TRAFFIC_1080P = {"rtdgi reproject": 22.97e6, "rtdgi validate": 17.73e6, "rtdgi trace": 9.48e6, "validity integrate": 21.28e6, "restir temporal": 24.92e6,
+                     "restir spatial": 18.26e6, "restir resolve": 40.75e6, "rtdgi temporal": 69.74e6, "rtdgi spatial": 35.59e6, "reprojection map": 20.99e6,
+                     "extract half-res inputs": 21.78e6}
 
 
 def pass_bytes(label, F, Hh, validation_frame_fraction=1.0 / 3.0):
@@ -290,7 +292,7 @@ def run_cuda(args):
         "gpu_launches": int(launches),
         "clocks": clock_info,
         "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": NCU_TRAFFIC_1080P.get(dom) if workload == "cornell_1080p_rtdgi_1s1t" and world_size == 1 else None, "traffic_source": "profiles/r01s_top3_summary.csv, profiles/r01c_full_summary.csv",
+                     "traffic": NCU_TRAFFIC_1080P.get(dom) if workload == "cornell_1080p_rtdgi_1s1t" and world_size == 1 else None, "traffic_source": "profiles/r01v_full_summary.csv",
                      "peak_source": peak_src, "kernel_ms": per_pass[dom], "kernel_share_of_step": share[dom] / sum(share.values()),
                      "algorithmic_bytes_per_launch": dom_bytes,
                      "frame": {"algorithmic_bytes": frame_bytes, "achieved_gbs": frame_bytes / (frame_ms * 1e-3) / 1e9, "frac": frame_bytes / (frame_ms * 1e-3) / 1e9 / peak},
