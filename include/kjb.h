@@ -242,7 +242,8 @@ int  kjb_event_synchronize(kjb_context *ctx, uint32_t event);                   
  * KJB_OPTION_HALF_RES_POSITION_CACHE: "restir spatial" and "restir resolve" unproject the same half-res pixels over and over (16 and 8
  * times per pixel); with this option the library keeps two scratch images of world positions — one from `half_depth_tex`, one from the
  * depth channel of `temporal_reservoir_packed_tex` — refreshes them when their sources change and lets the two passes load instead of
- * recompute (same values bit for bit).  The library sees every change made through its own entry points ("extract half depth",
+ * recompute (same values bit for bit).  "extract half-res inputs" and "restir temporal" write them as a by-product when they cover the whole
+ * image; otherwise a small kernel refreshes them on demand.  The library sees every change made through its own entry points ("extract half depth",
  * "restir temporal", kjb_image_upload/clear/copy/fill, kjb_set_frame_constants); a host that writes those two images by other means
  * (interop) must leave the option off. */
 #define KJB_OPTION_HALF_RES_POSITION_CACHE 1u
