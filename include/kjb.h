@@ -500,8 +500,29 @@ int kjb_pass_rtr_cleanup(kjb_context *ctx, const kjb_rtr_cleanup_args *a);
  * light_gbuffer.hlsl): direct sun + emissive + rtdgi * albedo + rtr * FG; the sky with the sun disk where depth == 0. */
 typedef struct kjb_trace_sun_shadow_mask_args { kjb_image depth_tex, geometric_normal_tex, output_tex; } kjb_trace_sun_shadow_mask_args;   /* output R8_UNORM */
 int kjb_pass_trace_sun_shadow_mask(kjb_context *ctx, const kjb_trace_sun_shadow_mask_args *a);
+/* ------------------------------------------------------------------ shadow denoiser (renderers/shadow_denoise.rs:19-149; shaders under
+ * assets/shaders/shadow_denoise/, the FidelityFX shadow denoiser as kajiya adapted it).  Runs between "trace shadow mask" and "light gbuffer"
+ * whenever the sun is an area light (WorldRenderer::sun_size_multiplier > 0, world_render_passes.rs:124-137). */
+typedef struct kjb_shadow_bitpack_args {              /* "shadow bitpack", bitpack_shadow_mask.hlsl:1-30 */
+    kjb_image input_tex;                              /* R8_UNORM ray-traced mask */
+    kjb_image output_tex;                             /* R32_UINT, one texel per 8x4 pixel tile: bit (y%4)*8 + x%8 = lit */
+    float input_tex_size[4]; uint32_t bitpacked_shadow_mask_extent[2];
+} kjb_shadow_bitpack_args;
+int kjb_pass_shadow_bitpack(kjb_context *ctx, const kjb_shadow_bitpack_args *a);
+typedef struct kjb_shadow_temporal_args {             /* "shadow temporal", megakernel.hlsl:6-150 + ffx_denoiser_shadows_tileclassification.hlsl */
+    kjb_image shadow_mask_tex, bitpacked_shadow_mask_tex, prev_moments_tex /* RGBA16F */, prev_accum_tex /* RG16F */, reprojection_tex;
+    kjb_image output_moments_tex /* RGBA16F */, temporal_output_tex /* RG16F: shadow, variance */, meta_output_tex /* R32_UINT per 8x8 group */;
+    float input_tex_size[4]; uint32_t bitpacked_shadow_mask_extent[2];
+} kjb_shadow_temporal_args;
+int kjb_pass_shadow_temporal(kjb_context *ctx, const kjb_shadow_temporal_args *a);
+typedef struct kjb_shadow_spatial_args {              /* "shadow spatial", spatial_filter.hlsl:3-78 + ffx_denoiser_shadows_filter.hlsl; run with step 1, 2, 4 */
+    kjb_image input_tex /* RG16F */, meta_tex, geometric_normal_tex, depth_tex, output_tex /* RG16F */;
+    float input_tex_size[4]; uint32_t bitpacked_shadow_mask_extent[2]; uint32_t step_size;
+} kjb_shadow_spatial_args;
+int kjb_pass_shadow_spatial(kjb_context *ctx, const kjb_shadow_spatial_args *a);
+
 typedef struct kjb_light_gbuffer_args {              /* light_gbuffer.hlsl:27-44 */
-    kjb_image gbuffer_tex, depth_tex, shadow_mask_tex, rtr_tex, rtdgi_tex;   /* rtr_tex: R11G11B10 resolved reflections (a zero image when rtr is off) */
+    kjb_image gbuffer_tex, depth_tex, shadow_mask_tex, rtr_tex, rtdgi_tex;   /* shadow_mask_tex: R8_UNORM raw mask or RG16F denoiser output (.x); rtr_tex: R11G11B10 resolved reflections (a zero image when rtr is off) */
     kjb_ircache_bindings ircache;                     /* only read by debug_shading_mode 5, which is not supported */
     kjb_image temporal_output_tex, output_tex;        /* RGBA16F, RGBA16F */
     kjb_image unconvolved_sky_cube_tex, sky_cube_tex;

@@ -31,9 +31,8 @@ typedef struct kjb_world_desc {
      * split of the half-res rows) and exchanges band borders once per frame through kjb_allgather. Overrides tile_y0/y1. */
     uint32_t tile_rank, tile_count;
     uint32_t enable_ssao;   /* SsgiRenderer (ssgi.rs): real screen-space occlusion instead of the constant-1 guide */
-    /* "trace shadow mask" + "light gbuffer" (world_render_passes.rs:124-128,215-232): the lit image ("debug_out"), which then is what
-     * TAA consumes.  The shadow denoiser (shadow_denoise.rs) is not part of this build: with the default sun the mask is the raw 1-spp
-     * trace; with hard_sun (WorldRenderer::sun_size_multiplier = 0) upstream skips the denoiser too and the frames correspond exactly. */
+    /* "trace shadow mask" + shadow denoiser + "light gbuffer" (world_render_passes.rs:124-137,215-232): the lit image ("debug_out"), which then is
+     * what TAA consumes.  hard_sun = WorldRenderer::sun_size_multiplier 0: a point sun, for which upstream skips the denoiser (and so do we). */
     uint32_t enable_lighting, hard_sun;
 } kjb_world_desc;
 

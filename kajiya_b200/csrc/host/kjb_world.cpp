@@ -118,6 +118,7 @@ struct kjb_world {
     std::vector<int32_t> spatial_resolve_offsets;
     PingPong ssgi_tex{"ssgi"};   // SsgiRenderer (ssgi.rs:9-19)
     uint32_t half_normal_frame = 0xffffffffu, half_depth_frame = 0xffffffffu;   // GbufferDepth memoisation (renderers/mod.rs:54-70)
+    PingPong shadow_denoise_accum{"shadow_denoise_accum"}, shadow_denoise_moments{"shadow_denoise_moments"};   // shadow_denoise.rs:5-17
     PingPong taa_temporal_tex{"taa"}, taa_temporal_velocity_tex{"taa.velocity"}, taa_temporal_smooth_var_tex{"taa.smooth_var"};   // taa.rs:19-27
     uint32_t OW = 0, OH = 0;   // temporal_upscale_extent
 
@@ -1026,7 +1027,7 @@ int kjb_world_render_frame(kjb_world* w, const kjb_world_frame* f) {
     // light_gbuffer + taa.render (world_render_passes.rs:215-263)
     const char* result_name = "rtdgi.spatial_filtered";
     if (w->desc.enable_lighting && !w->err && !w->stopped) {
-        // "trace shadow mask" + "light gbuffer" (world_render_passes.rs:124-128,215-232); the shadow denoiser is not built, see kjb_world.h
+        // "trace shadow mask" (+ the shadow denoiser under a soft sun) + "light gbuffer" (world_render_passes.rs:124-137,215-232)
         w->rows_all();
         kjb_image& sun_shadow_mask = w->img("sun_shadow_mask", W, H, KJB_FMT_R8_UNORM);
         { kjb_trace_sun_shadow_mask_args a{depth, geometric_normal, sun_shadow_mask}; RUN("trace shadow mask", kjb_pass_trace_sun_shadow_mask(ctx, &a)); }
@@ -1034,7 +1035,31 @@ int kjb_world_render_frame(kjb_world* w, const kjb_world_frame* f) {
         kjb_image& rtr = w->img("rtr.resolved", W, H, KJB_FMT_R11G11B10_UFLOAT);   // zero image when rtr is off (create_dummy_output, rtr.rs:327-362)
         kjb_image& accum_img = w->img("accum", W, H, KJB_FMT_RGBA16_FLOAT);
         kjb_image& debug_out_tex = w->img("debug_out", W, H, KJB_FMT_RGBA16_FLOAT);
-        kjb_light_gbuffer_args a{}; a.gbuffer_tex = gbuffer; a.depth_tex = depth; a.shadow_mask_tex = sun_shadow_mask; a.rtr_tex = rtr; a.rtdgi_tex = gi;
+        // ShadowDenoiseRenderer::render (shadow_denoise.rs:19-120) whenever the sun is an area light (world_render_passes.rs:130-137)
+        kjb_image* shadow_for_lighting = &sun_shadow_mask;
+        if (!w->desc.hard_sun) {
+            uint32_t ext[2] = {(W + 7) / 8, (H + 3) / 4};
+            float size[4]; size4(size, gbuffer);
+            kjb_image& bitpacked = w->img("shadow_denoise.bitpacked", ext[0], ext[1], KJB_FMT_R32_UINT);
+            { kjb_shadow_bitpack_args b{sun_shadow_mask, bitpacked, {size[0], size[1], size[2], size[3]}, {ext[0], ext[1]}}; RUN("shadow bitpack", kjb_pass_shadow_bitpack(ctx, &b)); }
+            kjb_image *moments_image, *prev_moments_image; w->get_output_and_history(w->shadow_denoise_moments, W, H, KJB_FMT_RGBA16_FLOAT, moments_image, prev_moments_image);
+            kjb_image *accum_image, *prev_accum_image; w->get_output_and_history(w->shadow_denoise_accum, W, H, KJB_FMT_RG16_FLOAT, accum_image, prev_accum_image);
+            kjb_image& spatial_input_image = w->img("shadow_denoise.spatial_input", W, H, KJB_FMT_RG16_FLOAT);
+            kjb_image& metadata_image = w->img("shadow_denoise.metadata", ext[0], ext[1], KJB_FMT_R32_UINT);
+            { kjb_shadow_temporal_args b{sun_shadow_mask, bitpacked, *prev_moments_image, *prev_accum_image, reprojection_map, *moments_image, spatial_input_image, metadata_image,
+                                         {size[0], size[1], size[2], size[3]}, {ext[0], ext[1]}};
+              RUN("shadow temporal", kjb_pass_shadow_temporal(ctx, &b)); }
+            kjb_image& temp = w->img("shadow_denoise.temp", W, H, KJB_FMT_RG16_FLOAT);
+            auto filter_spatial = [&](uint32_t step, kjb_image& in, kjb_image& out) {
+                kjb_shadow_spatial_args b{in, metadata_image, geometric_normal, depth, out, {size[0], size[1], size[2], size[3]}, {ext[0], ext[1]}, step};
+                RUN("shadow spatial", kjb_pass_shadow_spatial(ctx, &b));
+            };
+            filter_spatial(1, spatial_input_image, *accum_image);
+            filter_spatial(2, *accum_image, temp);
+            filter_spatial(4, temp, spatial_input_image);
+            shadow_for_lighting = &spatial_input_image;
+        }
+        kjb_light_gbuffer_args a{}; a.gbuffer_tex = gbuffer; a.depth_tex = depth; a.shadow_mask_tex = *shadow_for_lighting; a.rtr_tex = rtr; a.rtdgi_tex = gi;
         a.temporal_output_tex = accum_img; a.output_tex = debug_out_tex; a.unconvolved_sky_cube_tex = sky_cube; a.sky_cube_tex = convolved_sky_cube; size4(a.output_tex_size, gbuffer);
         RUN("light gbuffer", kjb_pass_light_gbuffer(ctx, &a));
         result_name = "debug_out";

@@ -212,6 +212,38 @@ def test_lighting_composite_feeds_taa(oracle_lib, emu_lib):
     _clean(report)
 
 
+def _orbit(view, f):
+    import math
+    v = dict(view); px, py, pz = view["camera_position"]
+    v["camera_position"] = (px + 0.25 * math.sin(0.7 * f), py + 0.05 * f, pz - 0.1 * f)
+    return v
+
+
+def test_shadow_denoiser(oracle_lib, emu_lib):
+    """ShadowDenoiseRenderer (shadow_denoise.rs): bitpack, temporal (tile classification, moments, history clamp under a moving camera:
+    disocclusions and the Catmull-Rom history fetch), three a-trous passes; every image bit for bit, odd extents included"""
+    scene, view = scenes.cornell_box()
+    for (w, h) in ((96, 60), (77, 45)):
+        wa, wb = parity.make_world(oracle_lib, scene, w, h, enable_lighting=True), parity.make_world(emu_lib, scene, w, h, enable_lighting=True)
+        for f in range(5):
+            v = _orbit(view, f)
+            wa.render_frame(**v); wb.render_frame(**v)
+            assert not parity.compare_images(wa, wb), (w, h, f)
+        names = set(wb.image_names())
+        assert {"shadow_denoise.bitpacked", "shadow_denoise.metadata", "shadow_denoise.spatial_input", "shadow_denoise.temp", "shadow_denoise_accum:0", "shadow_denoise_moments:0"} <= names
+        raw = wb.image("sun_shadow_mask")[..., 0].astype(np.float32) / 255.0
+        den = wb.image("shadow_denoise.spatial_input")[..., 0].astype(np.float32)
+        meta = wb.image("shadow_denoise.metadata")[: (h + 7) // 8, :, 0]
+        bits = wb.image("shadow_denoise.bitpacked")[..., 0]
+        assert ((meta & 1) == 0).any() and ((meta & 1) == 1).any()           # penumbra tiles are filtered, uniform ones are cleared
+        geo = wb.image("depth")[..., 0] != 0                                   # sky texels are not shadow receivers: 0 in filtered tiles, 1 in all-lit ones
+        assert ((den[geo] > 0.02) & (den[geo] < 0.98)).mean() > 0.01          # the 1-bit mask became a soft one ...
+        assert abs(den[geo].mean() - raw[geo].mean()) < 0.05 and np.isfinite(den).all() and den.min() >= 0 and den.max() <= 1.25   # ... with the same amount of light (the Catmull-Rom history fetch may overshoot 1 a little, as upstream)
+        # the bit masks are the mask: bit (y%4)*8 + x%8 of tile (x/8, y/4)
+        yy, xx = np.mgrid[0:h, 0:w]
+        assert np.array_equal(((bits[yy // 4, xx // 8] >> ((yy % 4) * 8 + (xx % 8))) & 1).astype(bool), raw > 0.5)
+
+
 def test_position_cache_is_invisible(emu_lib):
     """KJB_OPTION_HALF_RES_POSITION_CACHE hoists hit_ws_from_uv_depth out of the D7/D9 neighbour loops: same bits, no extra launch when the producers cover the whole image"""
     scene, view = scenes.cornell_box()

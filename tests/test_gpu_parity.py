@@ -232,3 +232,17 @@ def test_position_cache_is_invisible_on_gpu(cuda_lib):
     for f in range(4):
         wa.render_frame(**view); wb.render_frame(**view)
         assert not parity.compare_images(wa, wb), f
+
+
+@pytest.mark.gpu
+def test_shadow_denoiser_on_gpu(oracle_lib, cuda_lib):
+    """soft sun: trace shadow mask -> bitpack -> temporal -> 3 x spatial -> light gbuffer, camera in motion; every image bit for bit"""
+    import math
+    scene, view = scenes.cornell_box()
+    wa, wb = parity.make_world(oracle_lib, scene, 200, 120, enable_lighting=True, enable_taa=True), parity.make_world(cuda_lib, scene, 200, 120, enable_lighting=True, enable_taa=True)
+    for f in range(5):
+        v = dict(view); px, py, pz = view["camera_position"]; v["camera_position"] = (px + 0.25 * math.sin(0.7 * f), py + 0.05 * f, pz - 0.1 * f)
+        wa.render_frame(**v); wb.render_frame(**v)
+        assert not parity.compare_images(wa, wb), f
+    den = wb.image("shadow_denoise.spatial_input")[..., 0].astype(np.float32); geo = wb.image("depth")[..., 0] != 0
+    assert ((den[geo] > 0.02) & (den[geo] < 0.98)).mean() > 0.01
