@@ -90,3 +90,35 @@ def test_lit_image_vs_reference_path_tracer_oracle(oracle_lib):
 @pytest.mark.gpu
 def test_lit_image_vs_reference_path_tracer_cuda(cuda_lib):
     _check_lit(cuda_lib)
+
+
+def _check_lit_soft_sun(lib):
+    """The default area sun: 1-spp shadow mask -> shadow denoiser -> light_gbuffer, against the path tracer sampling the same sun disk.
+    Measured on the oracle: mean ratio 0.93, relative per-pixel L2 0.116; gate: mean within 12 %, L2 <= 0.15."""
+    scene, view = scenes.cornell_box()
+    wp = parity.make_world(lib, scene, W, H)
+    for _ in range(192):
+        wp.render_reference(**view)
+    pt = wp.image("refpt.accum")[..., :3].astype(np.float64)
+    w = parity.make_world(lib, scene, W, H, enable_lighting=True, enable_ircache=True, enable_rtr=True)
+    acc = np.zeros((H, W, 3)); n = 0
+    for f in range(52):
+        w.render_frame(**view)
+        if f >= 32:
+            acc += w.image("debug_out")[..., :3].astype(np.float64); n += 1
+    lit = acc / n; depth = w.image("depth")[..., 0]
+    m = (depth > 0) & (pt.max(-1) < 5.0)
+    r = lit[m].mean() / pt[m].mean()
+    err = np.sqrt(((lit[m] - pt[m]) ** 2).mean()) / np.sqrt((pt[m] ** 2).mean())
+    assert 0.88 < r < 1.12, r
+    assert err <= 0.15, err
+    assert "shadow_denoise.spatial_input" in w.image_names()
+
+
+def test_soft_sun_lit_image_vs_reference_path_tracer_oracle(oracle_lib):
+    _check_lit_soft_sun(oracle_lib)
+
+
+@pytest.mark.gpu
+def test_soft_sun_lit_image_vs_reference_path_tracer_cuda(cuda_lib):
+    _check_lit_soft_sun(cuda_lib)
