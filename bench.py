@@ -48,6 +48,10 @@ PASS_BYTES = {
     "scroll cascades": ("const", 6291456), "age ircache entries": ("const", 0), "_prefix scan": ("const", 524288), "ircache compact": ("const", 0), "_ircache dispatch args": ("const", 0),
     "ircache reset": ("const", 0), "ircache trace access": ("const", 0), "ircache validate": ("const", 0), "ircache trace": ("const", 0), "ircache sum": ("const", 0),
     "restir check": ("Hh", 28), "reprojection map": ("F", 28), "copy depth": ("F", 8),
+    # lit composite (N4): bound texels of trace_sun_shadow_mask.rgen / the three shadow_denoise shaders / light_gbuffer.hlsl, once each
+    "trace shadow mask": ("F", 9), "shadow bitpack": ("F", 1.125), "shadow temporal": ("F", 33.25), "shadow spatial": ("F", 16), "light gbuffer": ("F", 52),
+    # SSAO guide (N3): ssgi.hlsl + spatial + upsample + temporal (ssgi.rs:41-243)
+    "ssao": ("Hh", 30), "ssao spatial": ("Hh", 12), "ssao upsample": ("F+Hh", (10, 10)), "ssao temporal": ("F", 14),
 }
 # DRAM bytes per launch of each kernel, from one `ncu --set full` capture of the default workload (profiles/r01v_full_summary.csv:
 # dram__bytes_read.sum + dram__bytes_write.sum; the captured frame is a validation frame).  Far below the algorithmic bytes: the frame's
