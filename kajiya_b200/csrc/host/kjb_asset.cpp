@@ -12,6 +12,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <stdexcept>
 #include <string>
 #include <vector>
 
@@ -170,6 +171,10 @@ bool read_accessor(const Doc& d, int64_t index, bool as_uint, AccessorData& out,
     const int cb = component_bytes(out.ctype);
     if (!cb || !out.comps) { set_error(std::string(what) + ": bad accessor componentType/type"); return false; }
     const size_t n = out.count * size_t(out.comps);
+    const Json& views = d.list("bufferViews");
+    View v;   // validate the extent BEFORE sizing the output: a hostile count must not drive a multi-gigabyte allocation
+    if (acc.has("bufferView")) { if (!view_of(d, views, acc.i("bufferView", -1), size_t(acc.i("byteOffset", 0)), size_t(cb) * out.comps, out.count, v, what)) return false; }
+    else if (out.count > (size_t(1) << 28)) { set_error(std::string(what) + ": accessor without a buffer view is implausibly large"); return false; }
     if (as_uint) out.u.assign(n, 0); else out.f.assign(n, 0.0f);
     auto store = [&](size_t row, const uint8_t* p) {
         for (int c = 0; c < out.comps; ++c) {
@@ -178,11 +183,7 @@ bool read_accessor(const Doc& d, int64_t index, bool as_uint, AccessorData& out,
             else out.f[row * out.comps + c] = float(load_component(q, out.ctype));
         }
     };
-    const Json& views = d.list("bufferViews");
-    if (acc.has("bufferView")) {
-        View v; if (!view_of(d, views, acc.i("bufferView", -1), size_t(acc.i("byteOffset", 0)), size_t(cb) * out.comps, out.count, v, what)) return false;
-        for (size_t i = 0; i < out.count; ++i) store(i, v.p + i * v.stride);
-    }
+    if (acc.has("bufferView")) for (size_t i = 0; i < out.count; ++i) store(i, v.p + i * v.stride);
     if (const Json* sp = acc.get("sparse")) {
         const size_t sc = size_t(sp->i("count", 0));
         const Json* ji = sp->get("indices"); const Json* jv = sp->get("values");
@@ -480,7 +481,10 @@ int kjb_asset_load_gltf(const char* path, float scale, const float rotation_xyzw
     if (out) *out = nullptr;
     if (!path || !out) { set_error("kjb_asset_load_gltf: null argument"); return 1; }
     Importer imp; imp.out = new kjb_asset();
-    if (!imp.run(path, scale, rotation_xyzw)) { delete imp.out; return 1; }
+    bool ok = false;
+    try { ok = imp.run(path, scale, rotation_xyzw); }   // errors are values at this boundary: nothing may unwind into the caller
+    catch (const std::exception& e) { set_error(std::string("kjb_asset_load_gltf: ") + e.what()); }
+    if (!ok) { delete imp.out; return 1; }
     *out = imp.out;
     return 0;
 }
@@ -504,7 +508,8 @@ int kjb_asset_stats(const kjb_asset* a, uint32_t out[4]) { if (!a || !out) retur
 int kjb_asset_decode_image(const uint8_t* bytes, uint64_t byte_count, uint8_t** out_rgba8, uint32_t* out_width, uint32_t* out_height) {
     if (!bytes || !out_rgba8 || !out_width || !out_height) { set_error("kjb_asset_decode_image: null argument"); return 1; }
     std::vector<uint8_t> rgba; uint32_t w = 0, h = 0;
-    if (!decode_image(bytes, size_t(byte_count), rgba, w, h)) return 1;
+    try { if (!decode_image(bytes, size_t(byte_count), rgba, w, h)) return 1; }
+    catch (const std::exception& e) { set_error(std::string("kjb_asset_decode_image: ") + e.what()); return 1; }
     uint8_t* p = static_cast<uint8_t*>(malloc(rgba.size() ? rgba.size() : 1));
     if (!p) { set_error("out of memory"); return 1; }
     memcpy(p, rgba.data(), rgba.size());
@@ -515,7 +520,8 @@ int kjb_asset_build_mips(const uint8_t* rgba8, uint32_t width, uint32_t height, 
                          uint8_t** out_texels, uint64_t* out_bytes, uint32_t* out_width, uint32_t* out_height, uint32_t* out_mip_count) {
     if (!rgba8 || !width || !height || !out_texels || !out_bytes || !out_width || !out_height || !out_mip_count) { set_error("kjb_asset_build_mips: bad argument"); return 1; }
     std::vector<uint8_t> texels; uint32_t w, h, levels;
-    build_mips(rgba8, width, height, use_mips != 0, channel_swizzle, texels, w, h, levels);
+    try { build_mips(rgba8, width, height, use_mips != 0, channel_swizzle, texels, w, h, levels); }
+    catch (const std::exception& e) { set_error(std::string("kjb_asset_build_mips: ") + e.what()); return 1; }
     uint8_t* p = static_cast<uint8_t*>(malloc(texels.size()));
     if (!p) { set_error("out of memory"); return 1; }
     memcpy(p, texels.data(), texels.size());

@@ -200,6 +200,8 @@ bool decode_png(const uint8_t* p, size_t n, std::vector<uint8_t>& rgba, uint32_t
         const uint32_t pw = (W > ps.x0) ? (W - ps.x0 + ps.dx - 1) / ps.dx : 0, ph = (H > ps.y0) ? (H - ps.y0 + ps.dy - 1) / ps.dy : 0;
         if (pw && ph) raw_size += size_t(ph) * (1 + row_bytes(pw));
     }
+    // deflate cannot expand by more than 1032:1, so a header that promises more than the IDAT stream could hold is corrupt (and must not drive the allocations below)
+    if (raw_size > idat.size() * 1032 + 1024) { set_error("png: image data stream too short for the header's dimensions"); return false; }
     std::vector<uint8_t> raw;
     if (!zlib_decompress(idat.data(), idat.size(), raw, raw_size) || raw.size() < raw_size) { set_error("png: corrupt image data stream"); return false; }
 

@@ -328,3 +328,61 @@ def test_imported_scene_renders_identically_on_gpu(oracle_lib, cuda_lib):
     for f in range(3):
         wa.render_frame(**COURTYARD_VIEW); wb.render_frame(**COURTYARD_VIEW)
         assert not parity.compare_images(wa, wb), f
+
+
+# ------------------------------------------------------------------ robustness: malformed inputs are errors, never crashes
+_FUZZ = r'''
+import sys, os, glob, random, struct, zlib, json, shutil
+sys.path.insert(0, sys.argv[1])
+from kajiya_b200 import asset
+fix, tmp = sys.argv[2], sys.argv[3]
+random.seed(1234)
+def refix(d):   # recompute chunk CRCs so that mutations reach the inflater and the unfilter / expand code
+    out = bytearray(d[:8]); off = 8
+    while off + 12 <= len(d):
+        ln = struct.unpack(">I", d[off:off + 4])[0]; typ = d[off + 4:off + 8]; body = d[off + 8:off + 8 + ln]
+        if off + 12 + ln > len(d): out += d[off:]; break
+        out += d[off:off + 8] + body + struct.pack(">I", zlib.crc32(typ + body) & 0xffffffff); off += 12 + ln
+    return bytes(out)
+images = sorted(glob.glob(os.path.join(fix, "png", "*.png")))[::5] + sorted(glob.glob(os.path.join(fix, "jpg", "*.jpg")))
+decoded = rejected = 0
+for it in range(700):
+    f = random.choice(images); d = bytearray(open(f, "rb").read()); r = random.random()
+    if r < 0.6:
+        for _ in range(random.randint(1, 5)): d[random.randrange(8, len(d))] = random.randrange(256)
+    elif r < 0.8: d = d[:random.randrange(1, len(d))]
+    else: i = random.randrange(len(d)); d[i:i] = bytes(random.randrange(256) for _ in range(random.randint(1, 30)))
+    data = refix(bytes(d)) if f.endswith(".png") and random.random() < 0.7 else bytes(d)
+    try: asset.decode_image(data); decoded += 1
+    except asset.AssetError: rejected += 1
+for f in ("courtyard.bin", "albedo tex.png", "spec.png"): shutil.copy(os.path.join(fix, f), tmp)
+doc = json.load(open(os.path.join(fix, "courtyard.gltf")))
+def mutate(o):
+    if isinstance(o, dict):
+        k = random.choice(list(o.keys()))
+        if random.random() < 0.15: o.pop(k); return
+        if isinstance(o[k], (dict, list)) and o[k]: mutate(o[k])
+        else: o[k] = random.choice([-1, 0, 1, 2 ** 31, 10 ** 9, 3.5, "x", None, [], {}, True, 65536, 5126, 5121])
+    elif isinstance(o, list):
+        i = random.randrange(len(o))
+        if isinstance(o[i], (dict, list)) and o[i]: mutate(o[i])
+        else: o[i] = random.choice([-1, 0, 1, 2 ** 31, 10 ** 9, 3.5, "x", None, [], {}, 99999])
+loaded = refused = 0
+for it in range(500):
+    d = json.loads(json.dumps(doc))
+    for _ in range(random.randint(1, 3)): mutate(d)
+    open(os.path.join(tmp, "m.gltf"), "w").write(json.dumps(d))
+    try: s = asset.GltfScene(os.path.join(tmp, "m.gltf")); s.arrays(); s.close(); loaded += 1
+    except asset.AssetError: refused += 1
+print("FUZZ", decoded, rejected, loaded, refused)
+'''
+
+
+def test_malformed_inputs_never_crash_the_importer(tmp_path):
+    """700 mutated PNG/JPEG streams (chunk CRCs repaired so the damage reaches the decoders) and 500 mutated glTF documents, in a child
+    process so that an abort or a segfault would be seen: every input either decodes or is refused with an error"""
+    import subprocess
+    r = subprocess.run([sys.executable, "-c", _FUZZ, conftest.ROOT, FIX, str(tmp_path)], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=600)
+    assert r.returncode == 0, (r.returncode, r.stderr[-500:])
+    tag, decoded, rejected, loaded, refused = r.stdout.split()[-5:]
+    assert tag == "FUZZ" and int(decoded) + int(rejected) == 700 and int(loaded) + int(refused) == 500 and int(rejected) > 100 and int(refused) > 100
