@@ -211,7 +211,10 @@ int kjb_world_create(kjb_context* ctx, const kjb_world_desc* desc, kjb_world** o
     w->W = desc->render_width; w->H = desc->render_height;
     w->HW = (w->W + 1) / 2; w->HH = (w->H + 1) / 2;   // ImageDesc::half_res = div_up (image.rs:140-142)
     w->OW = desc->temporal_upscale_width ? desc->temporal_upscale_width : w->W; w->OH = desc->temporal_upscale_height ? desc->temporal_upscale_height : w->H;
-    if (desc->tile_count > 1 && (desc->enable_ircache || desc->enable_rtr || desc->enable_lighting)) { delete w; return 1; }   // the cache is one global racy structure (does not shard by rows); rtr tiles: not yet
+    // Tiles + irradiance cache: every rank keeps its OWN replica of the cache, fed by the rays of its band and halos (SURVEY §8e "replicas
+    // only" fall-back: the cache is one global racy structure and does not shard by rows; results stay statistically equivalent, which is all
+    // the cache promises on one GPU too).  Tiles + reflections / lit composite: not yet (rtr samples this frame's GI anywhere on screen).
+    if (desc->tile_count > 1 && (desc->enable_rtr || desc->enable_lighting)) { delete w; return 1; }
     if (desc->tile_count > 1) {
         if (w->OW != w->W || w->OH != w->H || (w->H & 1)) { delete w; return 1; }   // tiles + temporal upscaling / odd heights: not supported
         w->tiled = true; w->trank = desc->tile_rank; w->tcount = desc->tile_count;

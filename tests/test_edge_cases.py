@@ -59,7 +59,7 @@ def test_pass_argument_errors_are_reported(emu_lib):
 
 def test_world_refuses_unsupported_combinations(emu_lib):
     with pytest.raises(KjbError):
-        World(emu_lib, 64, 64, enable_ircache=True, tile=(0, 2))      # the cache does not shard by rows
+        World(emu_lib, 64, 64, enable_rtr=True, tile=(0, 2))          # reflections sample this frame's GI anywhere on screen: no tiles yet
     w = World(emu_lib, 32, 32, enable_rtr=True)
     w.set_blue_noise(scenes.blue_noise())
     _, view = scenes.cornell_box()
