@@ -45,7 +45,7 @@ PASS_BYTES = {
     "taa prob filter2": ("F", 4), "taa": ("F", 76),
     # irradiance cache (6.3 MB of grid + 1548 B per live entry; the entry count lives on the device, so only the fixed part is
     # charged here) and the other small passes of the frame
-    "scroll cascades": ("const", 6291456), "age ircache entries": ("const", 0), "_prefix scan": ("const", 524288), "ircache compact": ("const", 0), "_ircache dispatch args": ("const", 0),
+    "clear ircache pool": ("const", 0), "scroll cascades": ("const", 6291456), "age ircache entries": ("const", 0), "_prefix scan": ("const", 524288), "ircache compact": ("const", 0), "_ircache dispatch args": ("const", 0),
     "ircache reset": ("const", 0), "ircache trace access": ("const", 0), "ircache validate": ("const", 0), "ircache trace": ("const", 0), "ircache sum": ("const", 0),
     "restir check": ("Hh", 28), "reprojection map": ("F", 28), "copy depth": ("F", 8),
     # lit composite (N4): bound texels of trace_sun_shadow_mask.rgen / the three shadow_denoise shaders / light_gbuffer.hlsl, once each
@@ -59,6 +59,22 @@ PASS_BYTES = {
 NCU_TRAFFIC_1080P = {"rtdgi reproject": 22.97e6, "rtdgi validate": 17.73e6, "rtdgi trace": 9.48e6, "validity integrate": 21.28e6, "restir temporal": 24.92e6,
                      "restir spatial": 18.26e6, "restir resolve": 40.75e6, "rtdgi temporal": 69.74e6, "rtdgi spatial": 35.59e6, "reprojection map": 20.99e6,
                      "extract half-res inputs": 21.78e6}
+# warp instructions per launch from the same capture (smsp__inst_executed.sum): these kernels are bound by instruction issue, not by DRAM, so
+# the line also reports the dominant kernel against the issue-slot ceiling of the chip (148 SMs x 4 schedulers x 1 warp instruction per clock).
+NCU_WARP_INST_1080P = {"rtdgi reproject": 26.04e6, "rtdgi validate": 44.03e6, "rtdgi trace": 18.36e6, "validity integrate": 17.19e6, "restir temporal": 21.11e6,
+                       "restir spatial": 88.55e6, "restir resolve": 73.66e6, "rtdgi temporal": 87.08e6, "rtdgi spatial": 65.29e6, "reprojection map": 24.14e6,
+                       "extract half-res inputs": 5.75e6}
+
+
+def issue_slot_roofline(kernel, kernel_ms, clock_info):
+    """the dominant kernel against the chip's instruction-issue ceiling (148 SMs x 4 schedulers x 1 warp instruction per clock)"""
+    if kernel not in NCU_WARP_INST_1080P or not kernel_ms:
+        return None
+    sm_mhz = (clock_info or {}).get("sm_mhz") or (clock_info or {}).get("sm_max_mhz") or 1965
+    peak_ginst = 148 * 4 * float(sm_mhz) * 1e6 / 1e9
+    ach = NCU_WARP_INST_1080P[kernel] / (kernel_ms * 1e-3) / 1e9
+    return {"kernel": kernel, "warp_inst_per_launch": NCU_WARP_INST_1080P[kernel], "achieved_ginst_s": ach, "peak_ginst_s": peak_ginst, "frac": ach / peak_ginst,
+            "source": "profiles/r01v_full_summary.csv (smsp__inst_executed.sum) / live kernel time; peak = 148 SMs x 4 schedulers x SM clock"}
 
 
 def pass_bytes(label, F, Hh, validation_frame_fraction=1.0 / 3.0):
@@ -280,6 +296,10 @@ def run_cuda(args):
     dom_bytes = pass_bytes(dom, F, Hh)
     achieved = dom_bytes / (per_pass[dom] * 1e-3) / 1e9
     frame_bytes = sum(pass_bytes(k, F, Hh) * (calls[k] / K) for k in per_pass)
+    try:
+        issue = issue_slot_roofline(dom, per_pass[dom], clock_info) if workload == "cornell_1080p_rtdgi_1s1t" and world_size == 1 else None
+    except Exception:   # an explanatory extra must never cost the bench line
+        issue = None
     frame_ms = ms_total / K
 
     out = {
@@ -300,7 +320,8 @@ def run_cuda(args):
                      "peak_source": peak_src, "kernel_ms": per_pass[dom], "kernel_share_of_step": share[dom] / sum(share.values()),
                      "algorithmic_bytes_per_launch": dom_bytes,
                      "frame": {"algorithmic_bytes": frame_bytes, "achieved_gbs": frame_bytes / (frame_ms * 1e-3) / 1e9, "frac": frame_bytes / (frame_ms * 1e-3) / 1e9 / peak},
-                     "per_pass_ms": {k: round(v, 5) for k, v in sorted(per_pass.items(), key=lambda kv: -share[kv[0]])}},
+                     "per_pass_ms": {k: round(v, 5) for k, v in sorted(per_pass.items(), key=lambda kv: -share[kv[0]])},
+                     "issue_slots": issue},
     }
     if world_size == 1 and not args.no_cpu_baseline:
         out["cpu_baseline"] = cpu_baseline(workload, seconds=args.cpu_seconds)
