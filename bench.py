@@ -49,7 +49,7 @@ PASS_BYTES = {
     "ircache reset": ("const", 0), "ircache trace access": ("const", 0), "ircache validate": ("const", 0), "ircache trace": ("const", 0), "ircache sum": ("const", 0),
     "restir check": ("Hh", 28), "reprojection map": ("F", 28), "copy depth": ("F", 8),
     # lit composite (N4): bound texels of trace_sun_shadow_mask.rgen / the three shadow_denoise shaders / light_gbuffer.hlsl, once each
-    "trace shadow mask": ("F", 9), "shadow bitpack": ("F", 1.125), "shadow temporal": ("F", 33.25), "shadow spatial": ("F", 16), "light gbuffer": ("F", 52),
+    "trace shadow mask": ("F", 9), "shadow bitpack": ("F", 1.125), "shadow temporal": ("F", 33.25), "shadow spatial": ("F", 16), "light gbuffer": ("F", 52), "sample lights": ("Hh", 32), "spatial reuse lights": ("F+Hh", (28, 36)),
     # SSAO guide (N3): ssgi.hlsl + spatial + upsample + temporal (ssgi.rs:41-243)
     "ssao": ("Hh", 30), "ssao spatial": ("Hh", 12), "ssao upsample": ("F+Hh", (10, 10)), "ssao temporal": ("F", 14),
 }

@@ -521,6 +521,23 @@ typedef struct kjb_shadow_spatial_args {              /* "shadow spatial", spati
 } kjb_shadow_spatial_args;
 int kjb_pass_shadow_spatial(kjb_context *ctx, const kjb_shadow_spatial_args *a);
 
+/* ------------------------------------------------------------------ LightingRenderer::render_specular (renderers/lighting.rs:23-87): specular light of the
+ * emissive-triangle lights, rendered INTO the resolved reflections before their temporal filter (world_render_passes.rs:190-201); only when
+ * the scene has triangle lights (kjb_mesh_desc.use_lights). */
+typedef struct kjb_sample_lights_args {               /* "sample lights", lighting/sample_lights.rgen.hlsl:10-63 */
+    kjb_image depth_tex;
+    kjb_image out0_tex, out1_tex, out2_tex;           /* half-res: RGBA16F radiance (w = 1 for a valid sample), RGBA32F view-space hit + area pdf, RGBA8_SNORM light normal */
+    float gbuffer_tex_size[4];
+} kjb_sample_lights_args;
+int kjb_pass_sample_lights(kjb_context *ctx, const kjb_sample_lights_args *a);
+typedef struct kjb_spatial_reuse_lights_args {        /* "spatial reuse lights", lighting/spatial_reuse_lights.hlsl:11-168 */
+    kjb_image gbuffer_tex, depth_tex, hit0_tex, hit1_tex, hit2_tex, half_view_normal_tex, half_depth_tex;
+    kjb_image output_tex;                             /* R11G11B10 resolved reflections: read, the light's specular is added, written back */
+    float output_tex_size[4];
+    const int32_t *spatial_resolve_offsets;           /* int4[512] HOST pointer (rtr.rs:402-915); copied inside the call */
+} kjb_spatial_reuse_lights_args;
+int kjb_pass_spatial_reuse_lights(kjb_context *ctx, const kjb_spatial_reuse_lights_args *a);
+
 typedef struct kjb_light_gbuffer_args {              /* light_gbuffer.hlsl:27-44 */
     kjb_image gbuffer_tex, depth_tex, shadow_mask_tex, rtr_tex, rtdgi_tex;   /* shadow_mask_tex: R8_UNORM raw mask or RG16F denoiser output (.x); rtr_tex: R11G11B10 resolved reflections (a zero image when rtr is off) */
     kjb_ircache_bindings ircache;                     /* only read by debug_shading_mode 5, which is not supported */

@@ -92,6 +92,7 @@ struct kjb_world {
     std::vector<kjb_gpu_mesh> meshes;
     std::vector<uint32_t> mesh_index_counts;
     std::vector<std::vector<kjb_triangle_light>> mesh_lights;
+    uint32_t frame_light_count = 0;   // triangle lights of the frame being rendered
     std::vector<kjb_instance> instances, prev_instances;   // prev = transforms of the last rendered frame (retire_frame, world_renderer.rs:1110-1113)
     std::vector<std::vector<uint8_t>> texture_storage;
     std::vector<kjb_texture_desc> textures;
@@ -427,6 +428,7 @@ static int begin_frame(kjb_world* w, const kjb_world_frame* f, kjb_frame_constan
         lights.push_back(l);
     }
     fc.triangle_light_count = uint32_t(lights.size());
+    w->frame_light_count = fc.triangle_light_count;
     if (kjb_set_frame_constants(ctx, &fc, lights.data(), fc.triangle_light_count)) return 1;
     w->prev_camera = cam; w->have_prev_camera = true;
 
@@ -881,6 +883,15 @@ static kjb_image* rtr_render(kjb_world* w, kjb_image& gbuffer, kjb_image& depth,
         a.restir_hit_normal_tex = *hit_normal_output_tex; a.output_tex = resolved_tex; a.ray_len_output_tex = *ray_len_output_tex; size4(a.output_tex_size, resolved_tex);
         a.spatial_resolve_offsets = w->spatial_resolve_offsets.data();
         RUN("reflection resolve", kjb_pass_rtr_resolve(ctx, &a));
+    }
+    if (w->frame_light_count > 0) {   // lighting.render_specular (world_render_passes.rs:190-201, lighting.rs:23-87): the triangle lights' specular, into the resolved reflections
+        kjb_image& l0 = w->img("lighting.refl0", HW, HH, KJB_FMT_RGBA16_FLOAT);
+        kjb_image& l1 = w->img("lighting.refl1", HW, HH, KJB_FMT_RGBA32_FLOAT);
+        kjb_image& l2 = w->img("lighting.refl2", HW, HH, KJB_FMT_RGBA8_SNORM);
+        { kjb_sample_lights_args a{}; a.depth_tex = depth; a.out0_tex = l0; a.out1_tex = l1; a.out2_tex = l2; size4(a.gbuffer_tex_size, gbuffer); RUN("sample lights", kjb_pass_sample_lights(ctx, &a)); }
+        { kjb_spatial_reuse_lights_args a{}; a.gbuffer_tex = gbuffer; a.depth_tex = depth; a.hit0_tex = l0; a.hit1_tex = l1; a.hit2_tex = l2; a.half_view_normal_tex = half_view_normal_tex;
+          a.half_depth_tex = half_depth_tex; a.output_tex = resolved_tex; size4(a.output_tex_size, resolved_tex); a.spatial_resolve_offsets = w->spatial_resolve_offsets.data();
+          RUN("spatial reuse lights", kjb_pass_spatial_reuse_lights(ctx, &a)); }
     }
     {   // filter_temporal (rtr.rs:366-398)
         kjb_rtr_temporal_args a{}; a.input_tex = resolved_tex; a.history_tex = *history_tex; a.depth_tex = depth; a.ray_len_tex = *ray_len_output_tex; a.reprojection_tex = reprojection_map;

@@ -272,6 +272,92 @@ KJB_KERNEL(64) k_shadow_spatial(ShadowSpatialImgs t, float4 its, uint32_t ext_x,
     if (in_rows) st_rg16f(t.output_tex, x, y, kjb_max(0.0f, shadow_sum.x / weight_sum), kjb_max(0.0f, shadow_sum.y / (weight_sum * weight_sum)));
 }
 
+// ------------------------------------------------------------------ LightingRenderer::render_specular (renderers/lighting.rs:23-87)
+// "sample lights" (lighting/sample_lights.rgen.hlsl:18-63): one light sample + shadow ray per half-res pixel
+KJB_KERNEL(128) k_sample_lights(Globals g, Img depth_tex, ImgW out0_tex, ImgW out1_tex, ImgW out2_tex, float4 gts, Rows kjb_rows) {
+    KJB_PX; if (x >= out0_tex.w || y >= out0_tex.h) return;
+    const kjb_view_constants& vc = g.fc.view_constants;
+    const int2 hso = halfres_subsample_offset(g.fc.frame_index);
+    const int hx = x * 2 + hso.x, hy = y * 2 + hso.y;
+    const float depth = ld_r32f(depth_tex, hx, hy);
+    if (0.0f == depth) { st_rgba16f(out0_tex, x, y, f4(0.0f)); return; }
+    const float s4[4] = {gts.x, gts.y, gts.z, gts.w};
+    const float2 uv = get_uv(hx, hy, s4);
+    const ViewRayContext vrc = ViewRayContext::from_uv_and_depth(vc, uv, depth);
+    const float3 shadow_ray_origin = vrc.biased_secondary_ray_origin_ws();
+    const float4 urand4 = blue_noise_for_pixel(g, uint32_t(x), uint32_t(y), g.fc.frame_index);
+    const uint32_t light_count = g.fc.triangle_light_count;
+    const uint32_t light_idx = kjb_cvt_u32(urand4.z * float(light_count)) % light_count;
+    const float light_choice_pmf = 1.0f / float(light_count);
+    const kjb_triangle_light tl = g.lights[light_idx];
+    const LightSample ls = sample_triangle_light(tl, f2(urand4.x, urand4.y));
+    const float3 to_light_ws = ls.pos - shadow_ray_origin;
+    const float dist_to_light = length(to_light_ws);
+    const bool is_shadowed = rt_is_shadowed(g, shadow_ray_origin, to_light_ws / kjb_max(1e-8f, dist_to_light), 0.0f, dist_to_light - 1e-4f);
+    st_rgba16f(out0_tex, x, y, f4(is_shadowed ? f3(0.0f) : f3(tl.radiance[0], tl.radiance[1], tl.radiance[2]), 1.0f));
+    st_rgba32f(out1_tex, x, y, f4(vrc.ray_hit_vs() + direction_world_to_view(vc, to_light_ws), ls.pdf * light_choice_pmf));
+    st_rgba8s(out2_tex, x, y, f4(direction_world_to_view(vc, ls.normal), 0.0f));
+}
+
+// "spatial reuse lights" (lighting/spatial_reuse_lights.hlsl:33-168): 8 borrowed half-res samples per pixel, added into the resolved reflections
+struct ReuseLightsImgs { Img gbuffer_tex, depth_tex, hit0_tex, hit1_tex, hit2_tex, half_view_normal_tex, half_depth_tex; ImgW output_tex; };
+KJB_KERNEL(256) k_spatial_reuse_lights(Globals g, ReuseLightsImgs t, float4 ots, const int32_t* offs, Rows kjb_rows) {
+    KJB_PX; if (x >= t.output_tex.w || y >= t.output_tex.h) return;
+    const kjb_view_constants& vc = g.fc.view_constants;
+    const float s4[4] = {ots.x, ots.y, ots.z, ots.w};
+    const float2 uv = get_uv(x, y, s4);
+    const float depth = ld_r32f(t.depth_tex, x, y);
+    if (0.0f == depth) return;
+    const int2 hso = halfres_subsample_offset(g.fc.frame_index);
+    const ViewRayContext vrc = ViewRayContext::from_uv_and_depth(vc, uv, depth);
+    GbufferData gbuffer = gbuffer_unpack(ld_rgba32u(t.gbuffer_tex, x, y));
+    gbuffer.roughness = kjb_max(gbuffer.roughness, 3e-4f);
+    const float3x3 tangent_to_world = build_orthonormal_basis(gbuffer.normal);
+    float3 wo = mul(-normalize(vrc.ray_dir_ws()), tangent_to_world);
+    if (wo.z < 0.0f) { wo.z *= -0.25f; wo = normalize(wo); }
+    const LayeredBrdf layered_brdf = layered_brdf_from_gbuffer_ndotv(g, gbuffer, wo.z);
+    const SpecularBrdf specular_brdf = layered_brdf.specular_brdf;
+    const float3 energy_preservation_mult = layered_brdf.ep.preintegrated_reflection_mult;
+    const uint32_t px_idx_in_quad = (((uint32_t(x) & 1u) | (uint32_t(y) & 1u) * 2u) + g.fc.frame_index) & 3u;
+    float4 contrib_accum = f4(0.0f);
+    const float3 normal_vs = direction_world_to_view(vc, gbuffer.normal);
+    const float3 center_hit_vs = vrc.ray_hit_vs();
+    for (uint32_t sample_i = 0; sample_i < 8u; ++sample_i) {
+        const int32_t* o = offs + 4 * ((px_idx_in_quad * 16u + sample_i) + 64u * 3u);
+        const int spx = x / 2 + o[0], spy = y / 2 + o[1];
+        const float sample_depth = ld_r32f(t.half_depth_tex, spx, spy);
+        const float4 packed0 = ld_rgba16f(t.hit0_tex, spx, spy);
+        if (packed0.w != 0.0f && sample_depth != 0.0f) {
+            const float2 sample_uv = get_uv(spx * 2 + hso.x, spy * 2 + hso.y, s4);
+            const ViewRayContext sample_ray_ctx = ViewRayContext::from_uv_and_depth(vc, sample_uv, sample_depth);
+            const float3 sample_origin_vs = sample_ray_ctx.ray_hit_vs();
+            const float4 packed1 = ld_rgba32f(t.hit1_tex, spx, spy);
+            float neighbor_sampling_pdf = packed1.w;
+            const float3 sample_hit_normal_vs = xyz(ld_rgba8s(t.hit2_tex, spx, spy));
+            const float3 center_to_hit_vs = xyz(packed1) - vlerp(center_hit_vs, sample_origin_vs, 0.5f);
+            const float3 wi = normalize(mul(direction_view_to_world(vc, center_to_hit_vs), tangent_to_world));
+            const float3 sample_normal_vs = xyz(ld_rgba8s(t.half_view_normal_tex, spx, spy));
+            float rejection_bias = 1;
+            rejection_bias *= kjb_saturate((dot(normal_vs, sample_normal_vs) - 0.9f) / (0.999f - 0.9f));
+            rejection_bias *= kjb_exp2(-10.0f * kjb_abs(depth / sample_depth - 1.0f));
+            {
+                const float3 surface_offset = sample_origin_vs - center_hit_vs;
+                const float fraction_of_normal_direction_as_offset = dot(surface_offset, normal_vs) / length(surface_offset);
+                if (wi.z > 0.0f && wi.z * 0.2f < fraction_of_normal_direction_as_offset) rejection_bias *= sample_i == 0u ? 1.0f : 0.0f;
+            }
+            const BrdfValue spec = specular_evaluate(specular_brdf, wo, wi);
+            const float center_to_hit_dist2 = dot(center_to_hit_vs, center_to_hit_vs);
+            const float to_psa_metric = kjb_max(0.0f, wi.z) * kjb_max(0.0f, dot(sample_hit_normal_vs, -normalize(center_to_hit_vs))) / center_to_hit_dist2;
+            neighbor_sampling_pdf /= to_psa_metric;
+            const float3 contrib_rgb = xyz(packed0) * spec.value * energy_preservation_mult * kjb_step(0.0f, wi.z) * (neighbor_sampling_pdf > 0.0f ? (1 / neighbor_sampling_pdf) : 0.0f);
+            contrib_accum = contrib_accum + f4(contrib_rgb, 1) * rejection_bias;
+        }
+    }
+    const float contrib_norm_factor = kjb_max(1e-8f, contrib_accum.w);
+    const float3 out_color = xyz(contrib_accum) / contrib_norm_factor;
+    st_r11g11b10(t.output_tex, x, y, ld_r11g11b10(as_ro(t.output_tex), x, y) + out_color);   // RENDER_INTO_RTR: output_tex[px].rgb += out_color
+}
+
 #define F4A(a) f4((a)[0], (a)[1], (a)[2], (a)[3])
 #define CHK(img, fmt, name) if (!check_img(c, (img), (fmt), P, name)) return 1
 #define CHKE(img, fmt, name, w, h) if (!check_img(c, (img), (fmt), P, name, (w), (h))) return 1
@@ -346,6 +432,34 @@ int kjb_pass_shadow_spatial(kjb_context* c, const kjb_shadow_spatial_args* a) {
     KJB_ROWS(c, H);
     if (kjb__rows.y0 % 8) return c->fail("shadow spatial: the scissor must start on a multiple of 8 rows (8x8 denoiser tiles)");
     KJB_LAUNCH_SYNC(c, k_shadow_spatial, KJB_DIMS(dim3((W + 7) / 8, (uint32_t(kjb__rows.y1 - kjb__rows.y0) + 7) / 8), dim3(8, 8)), t, F4A(a->input_tex_size), a->bitpacked_shadow_mask_extent[0], int(a->step_size));
+    KJB_PASS_EPILOGUE(c, P);
+}
+
+int kjb_pass_sample_lights(kjb_context* c, const kjb_sample_lights_args* a) {
+    const char* P = "sample lights"; const uint32_t W = a->out0_tex.width, H = a->out0_tex.height;
+    CHK(a->depth_tex, KJB_FMT_R32_FLOAT, "depth_tex"); CHK(a->out0_tex, KJB_FMT_RGBA16_FLOAT, "out0_tex"); CHKE(a->out1_tex, KJB_FMT_RGBA32_FLOAT, "out1_tex", W, H); CHKE(a->out2_tex, KJB_FMT_RGBA8_SNORM, "out2_tex", W, H);
+    if (c->g.fc.triangle_light_count == 0) return c->fail("sample lights: the scene has no triangle lights");
+    if (!c->tlas_valid) return c->fail("sample lights: no acceleration structure (call kjb_rebuild_tlas)");
+    KJB_ROWS(c, H);
+    KJB_LAUNCH(c, k_sample_lights, KJB_GRID2D(W, H, 16, 8), c->g, img_ro(a->depth_tex), img_rw(a->out0_tex), img_rw(a->out1_tex), img_rw(a->out2_tex), F4A(a->gbuffer_tex_size));
+    KJB_PASS_EPILOGUE(c, P);
+}
+int kjb_pass_spatial_reuse_lights(kjb_context* c, const kjb_spatial_reuse_lights_args* a) {
+    const char* P = "spatial reuse lights"; const uint32_t W = a->output_tex.width, H = a->output_tex.height;
+    CHK(a->output_tex, KJB_FMT_R11G11B10_UFLOAT, "output_tex"); CHKE(a->gbuffer_tex, KJB_FMT_RGBA32_FLOAT, "gbuffer_tex", W, H); CHKE(a->depth_tex, KJB_FMT_R32_FLOAT, "depth_tex", W, H);
+    const uint32_t HW = a->hit0_tex.width, HH = a->hit0_tex.height;
+    CHK(a->hit0_tex, KJB_FMT_RGBA16_FLOAT, "hit0_tex"); CHKE(a->hit1_tex, KJB_FMT_RGBA32_FLOAT, "hit1_tex", HW, HH); CHKE(a->hit2_tex, KJB_FMT_RGBA8_SNORM, "hit2_tex", HW, HH);
+    CHKE(a->half_view_normal_tex, KJB_FMT_RGBA8_SNORM, "half_view_normal_tex", HW, HH); CHKE(a->half_depth_tex, KJB_FMT_R32_FLOAT, "half_depth_tex", HW, HH);
+    if (!a->spatial_resolve_offsets) return c->fail("spatial reuse lights: spatial_resolve_offsets is null");
+    const size_t bytes = sizeof(int32_t) * 4 * KJB_SPATIAL_RESOLVE_OFFSET_COUNT;
+    if (!c->d_resolve_offsets) { c->d_resolve_offsets = (int32_t*)dev_alloc(bytes); if (!c->d_resolve_offsets) return c->fail("spatial reuse lights: out of device memory"); c->h_resolve_offsets.clear(); }
+    if (c->h_resolve_offsets.size() != 4 * KJB_SPATIAL_RESOLVE_OFFSET_COUNT || memcmp(c->h_resolve_offsets.data(), a->spatial_resolve_offsets, bytes) != 0) {
+        c->h_resolve_offsets.assign(a->spatial_resolve_offsets, a->spatial_resolve_offsets + 4 * KJB_SPATIAL_RESOLVE_OFFSET_COUNT);
+        if (dev_h2d(c, c->d_resolve_offsets, c->h_resolve_offsets.data(), bytes)) return c->fail("spatial reuse lights: upload failed");
+    }
+    ReuseLightsImgs t{img_ro(a->gbuffer_tex), img_ro(a->depth_tex), img_ro(a->hit0_tex), img_ro(a->hit1_tex), img_ro(a->hit2_tex), img_ro(a->half_view_normal_tex), img_ro(a->half_depth_tex), img_rw(a->output_tex)};
+    KJB_ROWS(c, H);
+    KJB_LAUNCH(c, k_spatial_reuse_lights, KJB_GRID2D(W, H, 32, 8), c->g, t, F4A(a->output_tex_size), (const int32_t*)c->d_resolve_offsets);
     KJB_PASS_EPILOGUE(c, P);
 }
 

@@ -244,6 +244,38 @@ def test_shadow_denoiser(oracle_lib, emu_lib):
         assert np.array_equal(((bits[yy // 4, xx // 8] >> ((yy % 4) * 8 + (xx % 8))) & 1).astype(bool), raw > 0.5)
 
 
+def _cornell_with_ceiling_light(lib, w, h, **kw):
+    """the bundled Cornell box has no emitter: add a small emissive quad under the ceiling, registered as triangle lights (AddMeshOptions::use_lights)"""
+    from kajiya_b200.world import World
+    scene, view = scenes.cornell_box()
+    world = World(lib, w, h, **kw)
+    mesh, transforms = _glossy(scene)[0]
+    hm = world.add_mesh(mesh)
+    for t in transforms: world.add_instance(hm, t)
+    P = np.array([[-0.3, 1.9, -0.3], [0.3, 1.9, -0.3], [0.3, 1.9, 0.3], [-0.3, 1.9, 0.3]], np.float32)
+    light = dict(positions=P, normals=np.tile(np.array([0, -1, 0], np.float32), (4, 1)), indices=np.array([0, 1, 2, 0, 2, 3], np.uint32), material_ids=np.zeros(4, np.uint32),
+                 materials=[dict(base_color=[0, 0, 0, 1], roughness=1.0, metallic=0.0, emissive=[17.0, 12.0, 4.0])])
+    hl = world.add_mesh(light, use_lights=True)
+    world.add_instance(hl, np.array([[1, 0, 0, 0], [0, 1, 0, 0], [0, 0, 1, 0]], np.float32))
+    world.set_blue_noise(scenes.blue_noise()); world.set_spatial_resolve_offsets(scenes.spatial_resolve_offsets())
+    return world, view
+
+
+def test_triangle_light_specular(oracle_lib, emu_lib):
+    """LightingRenderer::render_specular (lighting.rs): "sample lights" + "spatial reuse lights" add the emissive triangles' specular into the
+    resolved reflections before their temporal filter; whole reflection path around it, every image bit for bit"""
+    kw = dict(enable_rtr=True, enable_lighting=True, enable_taa=True)
+    wa, view = _cornell_with_ceiling_light(oracle_lib, 88, 56, **kw); wb, _ = _cornell_with_ceiling_light(emu_lib, 88, 56, **kw)
+    for f in range(4):
+        v = _orbit(view, f)
+        wa.render_frame(**v); wb.render_frame(**v)
+        assert not parity.compare_images(wa, wb), f
+    assert {"lighting.refl0", "lighting.refl1", "lighting.refl2"} <= set(wb.image_names())
+    r0 = wb.image("lighting.refl0").astype(np.float32)
+    assert (r0[..., 3] == 1).mean() > 0.3 and (r0[..., :3].max(-1) > 0).mean() > 0.1      # valid samples, a good part of them unshadowed
+    assert wb.image("rtr.resolved").astype(np.float32).mean() > 0
+
+
 def test_position_cache_is_invisible(emu_lib):
     """KJB_OPTION_HALF_RES_POSITION_CACHE hoists hit_ws_from_uv_depth out of the D7/D9 neighbour loops: same bits, no extra launch when the producers cover the whole image"""
     scene, view = scenes.cornell_box()
