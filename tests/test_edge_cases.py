@@ -92,3 +92,20 @@ def test_instanced_moving_geometry(oracle_lib, emu_lib):
     vel = worlds[1][0].image("velocity").astype(np.float32)
     assert np.abs(vel[..., 0]).max() > 0.01
     assert (np.abs(vel[..., :3]).sum(-1) == 0).mean() > 0.5
+
+
+def test_every_pass_entry_rejects_a_zeroed_argument_block(emu_lib):
+    """all `kjb_pass_*` entries of include/kjb.h called with null images / buffers: an error code and a message naming the pass and the
+    resource, never a crash (the closures upstream return Err and the graph panics with the pass name, graph.rs:989-993)"""
+    import ctypes as C, re, os, conftest
+    d = emu_lib.dll
+    ctx = C.c_void_p(); assert d.kjb_create(-1, C.byref(ctx)) == 0
+    names = sorted(set(re.findall(r"\b(kjb_pass_[a-z0-9_]+)\s*\(", open(os.path.join(conftest.ROOT, "include", "kjb.h")).read())))
+    assert len(names) >= 56
+    zero = (C.c_uint8 * 8192)()
+    for n in names:
+        f = getattr(d, n); f.restype = C.c_int; f.argtypes = [C.c_void_p, C.c_void_p]
+        assert f(ctx, C.cast(zero, C.c_void_p)) != 0, n
+        msg = d.kjb_last_error(ctx) or b""
+        assert len(msg) > 8 and b":" in msg, (n, msg)
+    d.kjb_destroy(ctx)
