@@ -276,6 +276,34 @@ def test_triangle_light_specular(oracle_lib, emu_lib):
     assert wb.image("rtr.resolved").astype(np.float32).mean() > 0
 
 
+def test_everything_at_once(oracle_lib, emu_lib):
+    """every feature of the frame driver in one configuration — 2 spatial passes with ray-traced reservoir visibility, irradiance cache,
+    reflections + triangle-light specular, SSAO guide, soft sun through the shadow denoiser, lit composite, TAA upsampling 1.5x — on the
+    imported glTF fixture (textured, emissive-mapped lights) under camera motion: bit for bit, frame after frame"""
+    from kajiya_b200 import asset
+    from kajiya_b200.world import World
+    import os, conftest
+    path = os.path.join(conftest.ROOT, "tests", "golden", "gltf", "courtyard.gltf")
+    view = dict(camera_position=(0.5, 2.5, 7.0), camera_rotation=(float(np.sin(-0.15)), 0.0, 0.0, float(np.cos(-0.15))), sun_direction=(0.35, 0.8, 0.45))
+    kw = dict(spatial_reuse_pass_count=2, use_raytraced_reservoir_visibility=True, enable_ircache=True, enable_rtr=True, enable_ssao=True, enable_lighting=True, enable_taa=True, upscale=(108, 72))
+    worlds = []
+    for lib in (oracle_lib, emu_lib):
+        sc = asset.GltfScene(path)
+        w = World(lib, 72, 48, **kw)
+        w.add_instance(w.add_mesh_desc(sc.desc, use_lights=True), np.array([[1, 0, 0, 0], [0, 1, 0, 0], [0, 0, 1, 0]], np.float32))
+        w.set_blue_noise(scenes.blue_noise()); w.set_spatial_resolve_offsets(scenes.spatial_resolve_offsets())
+        sc.close(); worlds.append(w)
+    wa, wb = worlds
+    for f in range(5):
+        v = _orbit(view, f)
+        wa.render_frame(**v); wb.render_frame(**v)
+        assert not parity.compare_images(wa, wb), f
+    names = set(wb.image_names())
+    assert {"lighting.refl0", "shadow_denoise.spatial_input", "ssao", "rtr.resolved", "ircache.meta_buf", "taa.this_frame_out", "debug_out"} <= names
+    assert wb.image("taa.this_frame_out").shape[:2] == (72, 108) and int(wb.image("ircache.meta_buf").ravel()[3]) > 20
+    assert wb.stats()["passes"] >= 50        # render-graph passes of one frame
+
+
 def test_position_cache_is_invisible(emu_lib):
     """KJB_OPTION_HALF_RES_POSITION_CACHE hoists hit_ws_from_uv_depth out of the D7/D9 neighbour loops: same bits, no extra launch when the producers cover the whole image"""
     scene, view = scenes.cornell_box()
