@@ -5,8 +5,9 @@
  * `CreateGpuImage::process_rgba8` (src/image.rs:130-283: 2048 clamp, Lanczos3 mip chain, channel swizzle).
  * It is host-only code (the reference's is too: an offline bake step) in its own library, libkjb_asset.so; the TriangleMesh it
  * returns is laid out as the `kjb_mesh_desc` that kjb_world_add_mesh (WorldRenderer::add_mesh) consumes, so the two calls chain
- * without a copy.  Not mirrored: BC5/BC7 block compression (intel_tex_2 ISPC encoders; textures stay RGBA8, which is what the
- * hit shader's SampleLevel sees after hardware decode up to the encoder's loss), DDS containers, mikktspace tangent generation
+ * without a copy.  DDS images (`process_dds`, image.rs:285-335: DX10-header BC1_SRGB / BC3 / BC5 files with their own mips) are decoded
+ * block by block into the same RGBA8 chains.  Not mirrored: BC5/BC7 block COMPRESSION (intel_tex_2 ISPC encoders; textures stay RGBA8, which is
+ * what the hit shader's SampleLevel sees after hardware decode up to the encoder's loss), mikktspace tangent generation
  * (tangents only feed the raster normal-map path; the ray-traced hit shader has normal mapping compiled out, gbuffer.rchit.hlsl:124-167).
  */
 #ifndef KJB_ASSET_H
@@ -35,7 +36,7 @@ const float *kjb_asset_tangents(const kjb_asset *a);
 /* counts for reports: [0] nodes visited, [1] primitives appended, [2] primitives skipped (no POSITION/NORMAL), [3] images decoded */
 int  kjb_asset_stats(const kjb_asset *a, uint32_t out[4]);
 
-/* LoadImage (image.rs:62-98): PNG (all colour types / bit depths, Adam7) and baseline + progressive JPEG -> tightly packed RGBA8.
+/* LoadImage (image.rs:62-98): PNG (all colour types / bit depths, Adam7), baseline + progressive JPEG, DX10 DDS (top level) -> tightly packed RGBA8.
  * The caller frees *out_rgba8 with kjb_asset_free_buffer. */
 int  kjb_asset_decode_image(const uint8_t *bytes, uint64_t byte_count, uint8_t **out_rgba8, uint32_t *out_width, uint32_t *out_height);
 /* CreateGpuImage::process_rgba8 with TexCompressionMode::None (image.rs:130-283): clamp to 2048 with Lanczos3, full mip chain by

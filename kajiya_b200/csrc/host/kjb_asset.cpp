@@ -20,6 +20,7 @@ namespace kjb_asset_detail {
 static thread_local std::string g_error;
 void set_error(const std::string& m) { g_error = m; }
 bool decode_image(const uint8_t* bytes, size_t n, std::vector<uint8_t>& rgba, uint32_t& w, uint32_t& h);
+bool decode_dds(const uint8_t* p, size_t n, std::vector<uint8_t>& texels, uint32_t& W, uint32_t& H, uint32_t& mips, uint32_t& srgb);
 void build_mips(const uint8_t* rgba8, uint32_t width, uint32_t height, bool use_mips, const uint32_t* swizzle, std::vector<uint8_t>& out, uint32_t& ow, uint32_t& oh, uint32_t& levels);
 }  // namespace kjb_asset_detail
 using namespace kjb_asset_detail;
@@ -226,7 +227,7 @@ struct kjb_asset {
 };
 
 namespace {
-struct ImageSource { bool loaded = false, ok = false; std::vector<uint8_t> rgba; uint32_t w = 0, h = 0; std::string where; };
+struct ImageSource { bool loaded = false, ok = false, is_dds = false; std::vector<uint8_t> rgba; uint32_t w = 0, h = 0, dds_mips = 0, dds_srgb = 0; std::string where; };   // DDS: rgba holds the whole decoded chain
 
 struct Importer {
     Doc d; kjb_asset* out = nullptr;
@@ -289,7 +290,10 @@ struct Importer {
             if (bi < 0 || size_t(bi) >= d.buffers.size() || off + len > d.buffers[size_t(bi)].size()) { im.where = "gltf: image buffer view out of range"; set_error(im.where); return nullptr; }
             bytes.assign(d.buffers[size_t(bi)].begin() + off, d.buffers[size_t(bi)].begin() + off + len);
         } else { im.where = "gltf: image has neither uri nor bufferView"; set_error(im.where); return nullptr; }
-        if (!decode_image(bytes.data(), bytes.size(), im.rgba, im.w, im.h)) { im.where = g_error; return nullptr; }
+        if (bytes.size() >= 4 && !memcmp(bytes.data(), "DDS ", 4)) {   // RawImage::Dds (image.rs:70-84): the file's own format and mips win over TexParams
+            im.is_dds = true;
+            if (!decode_dds(bytes.data(), bytes.size(), im.rgba, im.w, im.h, im.dds_mips, im.dds_srgb)) { im.where = g_error; return nullptr; }
+        } else if (!decode_image(bytes.data(), bytes.size(), im.rgba, im.w, im.h)) { im.where = g_error; return nullptr; }
         im.ok = true; out->stats[3]++;
         return &im;
     }
@@ -315,6 +319,7 @@ struct Importer {
         if (!tex.is(Json::Object) || !tex.has("source")) { set_error("gltf: texture without an image source"); return false; }
         const ImageSource* im = image(size_t(tex.i("source", -1)));
         if (!im) return false;
+        if (im->is_dds) { t.texels = im->rgba; t.w = im->w; t.h = im->h; t.mips = im->dds_mips; t.srgb = im->dds_srgb; return true; }   // process_dds (image.rs:285-335)
         build_mips(im->rgba.data(), im->w, im->h, true, swizzle, t.texels, t.w, t.h, t.mips);
         t.srgb = srgb ? 1 : 0;
         return true;

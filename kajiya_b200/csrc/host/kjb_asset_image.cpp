@@ -9,6 +9,7 @@
 #include "../../../include/kjb_asset.h"
 #include <algorithm>
 #include <cmath>
+#include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <string>
@@ -646,11 +647,82 @@ void resize_lanczos3(const uint8_t* src, uint32_t sw, uint32_t sh, uint32_t dw, 
 }
 }  // namespace
 
+
+// ------------------------------------------------------------------------------------------------ DDS (image.rs:70-84,285-335 process_dds)
+// Upstream hands block-compressed DDS mips to the GPU as they are; this build's textures are RGBA8, so the blocks are decoded here with the
+// D3D11 functional-spec arithmetic.  Accepted, like upstream: DX10-header files in BC1_UNORM_SRGB, BC3_UNORM[_SRGB], BC5_UNORM / BC5_SNORM.
+namespace {
+inline void rgb565(uint32_t c, int out[3]) { const int r = (c >> 11) & 31, g = (c >> 5) & 63, b = c & 31; out[0] = (r << 3) | (r >> 2); out[1] = (g << 2) | (g >> 4); out[2] = (b << 3) | (b >> 2); }
+void decode_bc1_colors(const uint8_t* blk, bool opaque_only, uint8_t out[16][4]) {   // 8 bytes: two RGB565 endpoints, 16 x 2-bit indices
+    const uint32_t c0 = blk[0] | (blk[1] << 8), c1 = blk[2] | (blk[3] << 8);
+    int e0[3], e1[3]; rgb565(c0, e0); rgb565(c1, e1);
+    int pal[4][4];
+    for (int k = 0; k < 3; ++k) { pal[0][k] = e0[k]; pal[1][k] = e1[k]; }
+    pal[0][3] = pal[1][3] = pal[2][3] = pal[3][3] = 255;
+    if (c0 > c1 || opaque_only) for (int k = 0; k < 3; ++k) { pal[2][k] = (2 * e0[k] + e1[k] + 1) / 3; pal[3][k] = (e0[k] + 2 * e1[k] + 1) / 3; }
+    else { for (int k = 0; k < 3; ++k) { pal[2][k] = (e0[k] + e1[k]) / 2; pal[3][k] = 0; } pal[3][3] = 0; }
+    const uint32_t idx = blk[4] | (blk[5] << 8) | (blk[6] << 16) | (uint32_t(blk[7]) << 24);
+    for (int t = 0; t < 16; ++t) { const int* c = pal[(idx >> (2 * t)) & 3]; for (int k = 0; k < 4; ++k) out[t][k] = uint8_t(c[k]); }
+}
+void decode_bc4(const uint8_t* blk, bool snorm, uint8_t out[16]) {   // 8 bytes: two endpoints, 16 x 3-bit indices; SNORM results are mapped to UNORM8 texels
+    float a[8];
+    if (snorm) { const int s0 = int8_t(blk[0]), s1 = int8_t(blk[1]); a[0] = std::max(s0 / 127.0f, -1.0f); a[1] = std::max(s1 / 127.0f, -1.0f);
+        if (s0 > s1) for (int i = 1; i < 7; ++i) a[i + 1] = ((7 - i) * a[0] + i * a[1]) / 7.0f; else { for (int i = 1; i < 5; ++i) a[i + 1] = ((5 - i) * a[0] + i * a[1]) / 5.0f; a[6] = -1.0f; a[7] = 1.0f; } }
+    else { const int u0 = blk[0], u1 = blk[1]; a[0] = u0 / 255.0f; a[1] = u1 / 255.0f;
+        if (u0 > u1) for (int i = 1; i < 7; ++i) a[i + 1] = ((7 - i) * a[0] + i * a[1]) / 7.0f; else { for (int i = 1; i < 5; ++i) a[i + 1] = ((5 - i) * a[0] + i * a[1]) / 5.0f; a[6] = 0.0f; a[7] = 1.0f; } }
+    uint64_t bits = 0; for (int i = 0; i < 6; ++i) bits |= uint64_t(blk[2 + i]) << (8 * i);
+    for (int t = 0; t < 16; ++t) { const float v = a[(bits >> (3 * t)) & 7]; const float u = snorm ? v * 0.5f + 0.5f : v; out[t] = uint8_t(std::floor(std::min(std::max(u, 0.0f), 1.0f) * 255.0f + 0.5f)); }
+}
+}  // namespace
+
+bool decode_dds(const uint8_t* p, size_t n, std::vector<uint8_t>& texels, uint32_t& W, uint32_t& H, uint32_t& mips, uint32_t& srgb) {
+    auto u32 = [&](size_t off) { return uint32_t(p[off]) | (uint32_t(p[off + 1]) << 8) | (uint32_t(p[off + 2]) << 16) | (uint32_t(p[off + 3]) << 24); };
+    if (n < 128 || memcmp(p, "DDS ", 4) != 0 || u32(4) != 124) { set_error("dds: bad header"); return false; }
+    H = u32(12); W = u32(16); mips = std::max(1u, u32(28));
+    const uint32_t pf_flags = u32(80), fourcc = u32(84);
+    if (!(pf_flags & 4u) || fourcc != 0x30315844u /* "DX10" */ || n < 148) { set_error("dds: only DX10-header files are accepted (as upstream: it matches on the DXGI format)"); return false; }
+    const uint32_t dxgi = u32(128);
+    enum { BC1, BC3, BC5U, BC5S } kind;
+    switch (dxgi) {
+        case 72: kind = BC1; srgb = 1; break;      // BC1_UNORM_SRGB
+        case 77: kind = BC3; srgb = 0; break;      // BC3_UNORM
+        case 78: kind = BC3; srgb = 1; break;      // BC3_UNORM_SRGB
+        case 83: kind = BC5U; srgb = 0; break;     // BC5_UNORM
+        case 84: kind = BC5S; srgb = 0; break;     // BC5_SNORM
+        default: { char m[96]; snprintf(m, sizeof m, "dds: DXGI format %u not supported yet", dxgi); set_error(m); return false; }
+    }
+    if (!W || !H || W > 16384 || H > 16384 || mips > 15) { set_error("dds: implausible dimensions"); return false; }
+    const size_t block_bytes = kind == BC1 ? 8 : 16;
+    size_t off = 148; texels.clear();
+    for (uint32_t l = 0; l < mips; ++l) {
+        const uint32_t w = std::max(1u, W >> l), h = std::max(1u, H >> l);
+        const uint32_t bw = (std::max(w, 4u) + 3) / 4, bh = (std::max(h, 4u) + 3) / 4;     // process_dds: (dim >> mip).max(pitch_height)
+        if (off + size_t(bw) * bh * block_bytes > n) { set_error("dds: mip data reaches past the end of the file"); return false; }
+        const size_t base = texels.size(); texels.resize(base + size_t(w) * h * 4);
+        for (uint32_t by = 0; by < bh; ++by) for (uint32_t bx = 0; bx < bw; ++bx) {
+            const uint8_t* blk = p + off + (size_t(by) * bw + bx) * block_bytes;
+            uint8_t px[16][4];
+            if (kind == BC1) decode_bc1_colors(blk, false, px);
+            else if (kind == BC3) { uint8_t al[16]; decode_bc4(blk, false, al); decode_bc1_colors(blk + 8, true, px); for (int t = 0; t < 16; ++t) px[t][3] = al[t]; }
+            else { uint8_t r[16], g[16]; decode_bc4(blk, kind == BC5S, r); decode_bc4(blk + 8, kind == BC5S, g); for (int t = 0; t < 16; ++t) { px[t][0] = r[t]; px[t][1] = g[t]; px[t][2] = 0; px[t][3] = 255; } }
+            for (int t = 0; t < 16; ++t) { const uint32_t x = bx * 4 + (t & 3), y = by * 4 + (t >> 2); if (x < w && y < h) memcpy(&texels[base + (size_t(y) * w + x) * 4], px[t], 4); }
+        }
+        off += size_t(bw) * bh * block_bytes;
+    }
+    return true;
+}
+
 bool decode_image(const uint8_t* bytes, size_t n, std::vector<uint8_t>& rgba, uint32_t& w, uint32_t& h) {
     static const uint8_t PNG_SIG[8] = {0x89, 'P', 'N', 'G', 0x0d, 0x0a, 0x1a, 0x0a};
     if (n >= 8 && !memcmp(bytes, PNG_SIG, 8)) return decode_png(bytes, n, rgba, w, h);
     if (n >= 3 && bytes[0] == 0xff && bytes[1] == 0xd8 && bytes[2] == 0xff) { JpegDecoder d; d.p = bytes; d.n = n; return d.run(rgba, w, h); }
-    set_error("image: unrecognised container (PNG and JPEG are supported)");
+    if (n >= 4 && !memcmp(bytes, "DDS ", 4)) {   // top level of the chain
+        std::vector<uint8_t> chain; uint32_t mips, srgb;
+        if (!decode_dds(bytes, n, chain, w, h, mips, srgb)) return false;
+        rgba.assign(chain.begin(), chain.begin() + size_t(w) * h * 4);
+        return true;
+    }
+    set_error("image: unrecognised container (PNG, JPEG and DX10 DDS are supported)");
     return false;
 }
 

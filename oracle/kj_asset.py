@@ -278,7 +278,7 @@ class _Images:
             else:
                 bv = self.doc["bufferViews"][ji["bufferView"]]
                 data = self.buffers[bv["buffer"]][bv.get("byteOffset", 0):bv.get("byteOffset", 0) + bv["byteLength"]]
-            self.cache[index] = decode_image(data)
+            self.cache[index] = ("dds",) + decode_dds(bytes(data)) if bytes(data[:4]) == b"DDS " else decode_image(data)
         return self.cache[index]
 
 
@@ -296,7 +296,10 @@ def load_gltf_material(doc, mat, images):
         if not info:
             return dict(levels=[np.array(placeholder, np.uint8).reshape(1, 1, 4)], srgb=0)
         src = doc["textures"][info["index"]]["source"]
-        return dict(levels=process_rgba8(images.get(src), True, swizzle), srgb=int(srgb))
+        img = images.get(src)
+        if isinstance(img, tuple) and img[0] == "dds":   # RawImage::Dds: the file's mips and format, TexParams ignored (image.rs:285-335)
+            return dict(levels=img[1], srgb=img[2])
+        return dict(levels=process_rgba8(img, True, swizzle), srgb=int(srgb))
 
     maps = [make(normal, [127, 127, 255, 255], False, None), make(spec, [255, 255, 127, 255], False, [1, 2, 0, 3]),
             make(albedo, [255, 255, 255, 255], True, None), make(emissive, [255, 255, 255, 255], True, None)]
@@ -372,3 +375,70 @@ def load_gltf_scene(path, scale=1.0, rotation=(0.0, 0.0, 0.0, 1.0)):
     return dict(positions=cat("positions", (0, 3), F), normals=cat("normals", (0, 3), F), colors=cat("colors", (0, 4), F), uvs=cat("uvs", (0, 2), F),
                 tangents=cat("tangents", (0, 4), F), material_ids=cat("material_ids", (0,), np.uint32), indices=cat("indices", (0,), np.uint32),
                 materials=res["materials"], maps=res["maps"])
+
+
+# ------------------------------------------------------------------ DDS (image.rs:70-84, 285-335): DX10 header, BC1_SRGB / BC3 / BC5 -> RGBA8 mip chain
+def _bc1_palette(c0, c1, force_four):
+    def expand(c):
+        r, g, b = (c >> 11) & 31, (c >> 5) & 63, c & 31
+        return np.stack([(r << 3) | (r >> 2), (g << 2) | (g >> 4), (b << 3) | (b >> 2)], -1).astype(np.int32)
+    e0, e1 = expand(c0.astype(np.int32)), expand(c1.astype(np.int32))
+    four = (c0 > c1) | force_four
+    p2 = np.where(four[:, None], (2 * e0 + e1 + 1) // 3, (e0 + e1) // 2)
+    p3 = np.where(four[:, None], (e0 + 2 * e1 + 1) // 3, 0)
+    a3 = np.where(four, 255, 0)
+    pal = np.zeros((len(c0), 4, 4), np.int32)
+    pal[:, 0, :3], pal[:, 1, :3], pal[:, 2, :3], pal[:, 3, :3] = e0, e1, p2, p3
+    pal[:, :3, 3] = 255; pal[:, 3, 3] = a3
+    return pal
+
+
+def _bc4_values(b0, b1, snorm):
+    if snorm:
+        s0, s1 = b0.astype(np.int8).astype(np.int32), b1.astype(np.int8).astype(np.int32)
+        a0, a1 = np.maximum(s0.astype(F) / F(127), F(-1)), np.maximum(s1.astype(F) / F(127), F(-1)); six = s0 > s1; lo, hi = F(-1), F(1)
+    else:
+        a0, a1 = b0.astype(F) / F(255), b1.astype(F) / F(255); six = b0 > b1; lo, hi = F(0), F(1)
+    vals = np.zeros((len(b0), 8), F); vals[:, 0], vals[:, 1] = a0, a1
+    for i in range(1, 7):
+        v6 = ((F(7 - i) * a0 + F(i) * a1) / F(7)).astype(F)
+        v4 = ((F(5 - i) * a0 + F(i) * a1) / F(5)).astype(F) if i < 5 else (np.full(len(b0), lo if i == 5 else hi, F))
+        vals[:, i + 1] = np.where(six, v6, v4)
+    u = (vals * F(0.5) + F(0.5)).astype(F) if snorm else vals
+    return np.floor(np.clip(u, F(0), F(1)) * F(255) + F(0.5)).astype(np.uint8)
+
+
+def decode_dds(data):
+    """-> (list of uint8[h, w, 4] levels, srgb)"""
+    assert data[:4] == b"DDS " and struct.unpack_from("<I", data, 4)[0] == 124
+    H, W = struct.unpack_from("<II", data, 12); mips = max(1, struct.unpack_from("<I", data, 28)[0])
+    assert struct.unpack_from("<I", data, 84)[0] == 0x30315844, "only DX10-header files"
+    dxgi = struct.unpack_from("<I", data, 128)[0]
+    kind, srgb = {72: ("bc1", 1), 77: ("bc3", 0), 78: ("bc3", 1), 83: ("bc5u", 0), 84: ("bc5s", 0)}[dxgi]
+    bb = 8 if kind == "bc1" else 16
+    off, levels = 148, []
+    for l in range(mips):
+        w, h = max(1, W >> l), max(1, H >> l); bw, bh = (max(w, 4) + 3) // 4, (max(h, 4) + 3) // 4
+        blocks = np.frombuffer(data, np.uint8, bw * bh * bb, off).reshape(bw * bh, bb); off += bw * bh * bb
+        out = np.zeros((bw * bh, 16, 4), np.uint8)
+
+        def colours(cb, force_four):
+            c0 = cb[:, 0].astype(np.uint32) | (cb[:, 1].astype(np.uint32) << 8); c1 = cb[:, 2].astype(np.uint32) | (cb[:, 3].astype(np.uint32) << 8)
+            pal = _bc1_palette(c0, c1, force_four)
+            idx = cb[:, 4].astype(np.uint32) | (cb[:, 5].astype(np.uint32) << 8) | (cb[:, 6].astype(np.uint32) << 16) | (cb[:, 7].astype(np.uint32) << 24)
+            sel = (idx[:, None] >> (2 * np.arange(16, dtype=np.uint32))[None, :]) & 3
+            return np.take_along_axis(pal, sel[:, :, None].astype(np.int64).repeat(4, 2), 1).astype(np.uint8)
+
+        def alphas(ab, snorm):
+            vals = _bc4_values(ab[:, 0], ab[:, 1], snorm)
+            bits = np.zeros(len(ab), np.uint64)
+            for i in range(6): bits |= ab[:, 2 + i].astype(np.uint64) << np.uint64(8 * i)
+            sel = (bits[:, None] >> (np.uint64(3) * np.arange(16, dtype=np.uint64))[None, :]) & np.uint64(7)
+            return np.take_along_axis(vals, sel.astype(np.int64), 1)
+        if kind == "bc1": out[:] = colours(blocks, False)
+        elif kind == "bc3": out[:] = colours(blocks[:, 8:], True); out[:, :, 3] = alphas(blocks[:, :8], False)
+        else:
+            out[:, :, 0] = alphas(blocks[:, :8], kind == "bc5s"); out[:, :, 1] = alphas(blocks[:, 8:], kind == "bc5s"); out[:, :, 2] = 0; out[:, :, 3] = 255
+        img = out.reshape(bh, bw, 4, 4, 4).transpose(0, 2, 1, 3, 4).reshape(bh * 4, bw * 4, 4)[:h, :w]
+        levels.append(np.ascontiguousarray(img))
+    return levels, srgb

@@ -111,6 +111,64 @@ def test_jpeg_errors_are_reported():
         asset.decode_image(b"\xff\xd8\xff\xd9")
 
 
+# ------------------------------------------------------------------ DDS
+def _dds(dxgi, w, h, mips, seed):
+    import struct
+    rng = np.random.default_rng(seed)
+    bb = 8 if dxgi == 72 else 16
+    body = b""
+    for l in range(mips):
+        lw, lh = max(1, w >> l), max(1, h >> l)
+        body += rng.integers(0, 256, ((max(lw, 4) + 3) // 4) * ((max(lh, 4) + 3) // 4) * bb, dtype=np.uint8).tobytes()   # any bytes are valid BC blocks
+    hdr = struct.pack("<4sIIIIIII44x", b"DDS ", 124, 0x1007 | 0x20000, h, w, 0, 0, mips) + struct.pack("<II4sIIIII", 32, 4, b"DX10", 0, 0, 0, 0, 0) + struct.pack("<IIIII", 0x1000 | 0x400000, 0, 0, 0, 0)
+    return hdr + struct.pack("<IIIII", dxgi, 3, 0, 1, 0) + body
+
+
+@pytest.mark.parametrize("dxgi,w,h,mips", [(72, 16, 12, 5), (77, 20, 20, 3), (78, 8, 8, 4), (83, 13, 7, 1), (84, 32, 4, 6)])
+def test_dds_block_decoding_matches_the_restatement(dxgi, w, h, mips):
+    """process_dds accepts BC1_SRGB / BC3 / BC3_SRGB / BC5 / BC5_SNORM with their own mip chains; random blocks, odd extents, sub-block mips"""
+    data = _dds(dxgi, w, h, mips, dxgi * 100 + w)
+    want, srgb = oracle.decode_dds(data)
+    top = asset.decode_image(data)
+    assert top.shape == want[0].shape and np.array_equal(top, want[0])
+    assert len(want) == mips and [l.shape[:2] for l in want] == [(max(1, h >> l), max(1, w >> l)) for l in range(mips)] and srgb == (1 if dxgi in (72, 78) else 0)
+
+
+def test_dds_hand_decoded_blocks():
+    import struct
+    def file(dxgi, block):
+        hdr = struct.pack("<4sIIIIIII44x", b"DDS ", 124, 0x1007, 4, 4, 0, 0, 1) + struct.pack("<II4sIIIII", 32, 4, b"DX10", 0, 0, 0, 0, 0) + struct.pack("<IIIII", 0x1000, 0, 0, 0, 0)
+        return hdr + struct.pack("<IIIII", dxgi, 3, 0, 1, 0) + block
+    # BC1: c0 = pure red (0xF800) > c1 = pure blue (0x001F): four-colour mode; indices 0,1,2,3 repeating
+    img = asset.decode_image(file(72, struct.pack("<HHI", 0xF800, 0x001F, 0xE4E4E4E4)))
+    assert [tuple(int(v) for v in img[0, x]) for x in range(4)] == [(255, 0, 0, 255), (0, 0, 255, 255), (170, 0, 85, 255), (85, 0, 170, 255)]
+    # c0 <= c1: three colours + transparent black
+    img = asset.decode_image(file(72, struct.pack("<HHI", 0x001F, 0xF800, 0xE4E4E4E4)))
+    assert tuple(int(v) for v in img[0, 2]) == (127, 0, 127, 255) and tuple(int(v) for v in img[0, 3]) == (0, 0, 0, 0)
+    # BC5_UNORM: red ramp 255 > 0 (six interpolants), green 0 < 255 (four interpolants + 0 and 1)
+    red = bytes([255, 0]) + (0o76543210 | (0o76543210 << 24)).to_bytes(6, "little"); green = bytes([0, 255]) + (0o76543210 | (0o76543210 << 24)).to_bytes(6, "little")
+    img = asset.decode_image(file(83, red + green))
+    assert [int(v) for v in img.reshape(-1, 4)[:8, 0]] == [255, 0, 219, 182, 146, 109, 73, 36]
+    assert [int(v) for v in img.reshape(-1, 4)[:8, 1]] == [0, 255, 51, 102, 153, 204, 0, 255]
+    for bad, msg in ((b"DDS " + bytes(200), "bad header"), (file(71, bytes(8)), "not supported"), (file(72, bytes(4)), "past the end")):
+        with pytest.raises(asset.AssetError, match=msg):
+            asset.decode_image(bad)
+
+
+def test_gltf_with_dds_textures_uses_the_files_own_mips(tmp_path):
+    import shutil
+    doc = json.load(open(os.path.join(FIX, "courtyard.gltf")))
+    for f in ("courtyard.bin", "spec.png"):
+        shutil.copy(os.path.join(FIX, f), tmp_path)
+    (tmp_path / "albedo.dds").write_bytes(_dds(72, 16, 8, 5, 7))
+    doc["images"][0] = {"uri": "albedo.dds"}
+    (tmp_path / "dds.gltf").write_text(json.dumps(doc))
+    sc = asset.GltfScene(str(tmp_path / "dds.gltf")); a = sc.arrays()
+    assert_same_mesh(a, oracle.load_gltf_scene(str(tmp_path / "dds.gltf")))
+    m = a["maps"][2]
+    assert (m["width"], m["height"], m["mips"], m["srgb"]) == (16, 8, 5, 1)     # the file's chain and its sRGB format, not TexParams / Lanczos
+
+
 # ------------------------------------------------------------------ mip chains
 @pytest.mark.parametrize("w,h", [(37, 21), (64, 64), (1, 9), (5, 1), (130, 7)])
 def test_mip_chain_matches_the_restatement(w, h):
