@@ -85,6 +85,10 @@ int  kjb_world_add_instance(kjb_world *w, uint32_t mesh_handle, const float tran
 /* WorldRenderer::set_instance_transform (world_renderer.rs:815-818). The next frame re-flattens the acceleration structure.
  * (The primary-visibility stand-in that produces the G-buffer when the host supplies none uses last frame's transform for the velocity.) */
 int  kjb_world_set_instance_transform(kjb_world *w, uint32_t instance_handle, const float transform[12]);
+/* WorldRenderer::remove_instance (world_renderer.rs:800-813): swap_remove — the LAST instance moves into the freed slot (InstanceID order, hence ray tie-breaks, follow upstream) */
+int  kjb_world_remove_instance(kjb_world *w, uint32_t instance_handle);
+/* InstanceDynamicParameters::emissive_multiplier (world_renderer.rs:96-105,828-834): scales the instance's emissive in hit shading and its triangle lights */
+int  kjb_world_set_instance_emissive_multiplier(kjb_world *w, uint32_t instance_handle, float emissive_multiplier);
 /* the 256x256 RGBA8 blue-noise LUT (bindless slot 1; assets/images/bluenoise/256_256/LDR_RGBA_0.png in the reference) */
 int  kjb_world_set_blue_noise(kjb_world *w, const uint8_t *rgba8_256x256);
 /* SPATIAL_RESOLVE_OFFSETS (rtr.rs:402-915): the int4[512] constant table the reflection passes receive; required when enable_rtr */

@@ -91,6 +91,8 @@ class KjbLib:
             "kjb_world_add_mesh": (C.c_int, [P, C.POINTER(MeshDesc), C.POINTER(C.c_uint32)]),
             "kjb_world_add_instance": (C.c_int, [P, C.c_uint32, C.POINTER(C.c_float * 12), C.POINTER(C.c_uint32)]),
             "kjb_world_set_instance_transform": (C.c_int, [P, C.c_uint32, C.POINTER(C.c_float * 12)]),
+            "kjb_world_remove_instance": (C.c_int, [P, C.c_uint32]),
+            "kjb_world_set_instance_emissive_multiplier": (C.c_int, [P, C.c_uint32, C.c_float]),
             "kjb_world_set_blue_noise": (C.c_int, [P, P]),
             "kjb_world_set_spatial_resolve_offsets": (C.c_int, [P, P]),
             "kjb_world_render_frame": (C.c_int, [P, C.POINTER(WorldFrame)]),

@@ -93,6 +93,7 @@ struct kjb_world {
     std::vector<uint32_t> mesh_index_counts;
     std::vector<std::vector<kjb_triangle_light>> mesh_lights;
     uint32_t frame_light_count = 0;   // triangle lights of the frame being rendered
+    std::vector<uint32_t> instance_handles; std::map<uint32_t, uint32_t> instance_handle_to_index; uint32_t next_instance_handle = 0;   // world_renderer.rs:150-152
     std::vector<kjb_instance> instances, prev_instances;   // prev = transforms of the last rendered frame (retire_frame, world_renderer.rs:1110-1113)
     std::vector<std::vector<uint8_t>> texture_storage;
     std::vector<kjb_texture_desc> textures;
@@ -300,14 +301,37 @@ int kjb_world_add_mesh(kjb_world* w, const kjb_mesh_desc* mesh, uint32_t* out_ha
 int kjb_world_add_instance(kjb_world* w, uint32_t mesh, const float transform[12], uint32_t* out_handle) {
     if (mesh >= w->meshes.size()) return 1;
     kjb_instance i{}; memcpy(i.transform, transform, sizeof(i.transform)); i.mesh_index = mesh; i.emissive_multiplier = 1.0f;
-    w->instances.push_back(i);
-    if (out_handle) *out_handle = uint32_t(w->instances.size() - 1);
+    const uint32_t handle = w->next_instance_handle++;
+    w->instance_handle_to_index[handle] = uint32_t(w->instances.size());
+    w->instances.push_back(i); w->instance_handles.push_back(handle);
+    if (out_handle) *out_handle = handle;
+    return 0;
+}
+
+// WorldRenderer::remove_instance (world_renderer.rs:800-813): swap_remove, so the last instance takes the freed slot (and its InstanceID)
+int kjb_world_remove_instance(kjb_world* w, uint32_t handle) {
+    auto it = w->instance_handle_to_index.find(handle);
+    if (it == w->instance_handle_to_index.end()) return 1;   // upstream: expect("no such instance")
+    const uint32_t index = it->second;
+    w->instance_handle_to_index.erase(it);
+    w->instances[index] = w->instances.back(); w->instances.pop_back();
+    w->instance_handles[index] = w->instance_handles.back(); w->instance_handles.pop_back();
+    if (index < w->instance_handles.size()) w->instance_handle_to_index[w->instance_handles[index]] = index;
     return 0;
 }
 
 int kjb_world_set_instance_transform(kjb_world* w, uint32_t handle, const float transform[12]) {
-    if (handle >= w->instances.size()) return 1;
-    memcpy(w->instances[handle].transform, transform, sizeof(float) * 12);
+    auto it = w->instance_handle_to_index.find(handle);
+    if (it == w->instance_handle_to_index.end()) return 1;
+    memcpy(w->instances[it->second].transform, transform, sizeof(float) * 12);
+    return 0;
+}
+
+// get_instance_dynamic_parameters_mut(inst).emissive_multiplier (world_renderer.rs:828-834, InstanceDynamicParameters :96-105)
+int kjb_world_set_instance_emissive_multiplier(kjb_world* w, uint32_t handle, float emissive_multiplier) {
+    auto it = w->instance_handle_to_index.find(handle);
+    if (it == w->instance_handle_to_index.end()) return 1;
+    w->instances[it->second].emissive_multiplier = emissive_multiplier;
     return 0;
 }
 

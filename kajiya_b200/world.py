@@ -111,6 +111,13 @@ class World:
         t = (C.c_float * 12)(*np.asarray(transform, np.float32).reshape(-1)[:12])
         self._check(self.d.kjb_world_set_instance_transform(self.w, handle, C.byref(t)))
 
+    def remove_instance(self, handle):
+        """WorldRenderer::remove_instance (swap_remove: the last instance takes the freed slot)"""
+        self._check(self.d.kjb_world_remove_instance(self.w, handle))
+
+    def set_instance_emissive_multiplier(self, handle, value):
+        self._check(self.d.kjb_world_set_instance_emissive_multiplier(self.w, handle, float(value)))
+
     def set_blue_noise(self, rgba8):
         a = np.ascontiguousarray(rgba8, np.uint8); assert a.size == 256 * 256 * 4
         self._check(self.d.kjb_world_set_blue_noise(self.w, a.ctypes.data))

@@ -109,3 +109,46 @@ def test_every_pass_entry_rejects_a_zeroed_argument_block(emu_lib):
         msg = d.kjb_last_error(ctx) or b""
         assert len(msg) > 8 and b":" in msg, (n, msg)
     d.kjb_destroy(ctx)
+
+
+def test_remove_instance_and_emissive_multiplier(oracle_lib, emu_lib):
+    """WorldRenderer::remove_instance is a swap_remove (the last instance takes the freed slot); InstanceDynamicParameters::emissive_multiplier
+    scales emissive hits and the instance's triangle lights.  Frames before and after the edits: bit for bit on oracle and emulator."""
+    import parity
+    scene, view = scenes.cornell_box()
+    mesh, transforms = scene[0]
+    P = np.array([[-0.3, 1.9, -0.3], [0.3, 1.9, -0.3], [0.3, 1.9, 0.3], [-0.3, 1.9, 0.3]], np.float32)
+    light = dict(positions=P, normals=np.tile(np.array([0, -1, 0], np.float32), (4, 1)), indices=np.array([0, 1, 2, 0, 2, 3], np.uint32), material_ids=np.zeros(4, np.uint32),
+                 materials=[dict(base_color=[0, 0, 0, 1], roughness=1.0, metallic=0.0, emissive=[6.0, 5.0, 3.0])])
+    ident = np.array([[1, 0, 0, 0], [0, 1, 0, 0], [0, 0, 1, 0]], np.float32)
+    worlds = []
+    for lib in (oracle_lib, emu_lib):
+        w = World(lib, 64, 40)
+        hm = w.add_mesh(mesh); hl = w.add_mesh(light, use_lights=True)
+        a = w.add_instance(hm, transforms[0])
+        b = w.add_instance(hm, np.array([[2, 0, 0, 4.5], [0, 2, 0, -1], [0, 0, 2, 0]], np.float32))   # a second box to the right
+        c = w.add_instance(hl, ident)
+        assert (a, b, c) == (0, 1, 2)
+        w.set_blue_noise(scenes.blue_noise()); worlds.append((w, a, b, c))
+    def frame():
+        for w, *_ in worlds: w.render_frame(**view)
+        assert not parity.compare_images(worlds[0][0], worlds[1][0])
+    frame(); frame()
+    lit = worlds[1][0].image("rtdgi.spatial_filtered").astype(np.float32).mean()
+    for w, a, b, c in worlds: w.set_instance_emissive_multiplier(c, 0.0)
+    for _ in range(6): frame()
+    assert worlds[1][0].image("rtdgi.spatial_filtered").astype(np.float32).mean() < lit          # the light went dark
+    for w, a, b, c in worlds: w.remove_instance(a)                                                # the light (last) moves into slot 0
+    frame(); frame()
+    depth = worlds[1][0].image("depth")[..., 0]
+    ref = World(emu_lib, 64, 40); hm = ref.add_mesh(mesh); hl = ref.add_mesh(light, use_lights=True)
+    ref.add_instance(hl, ident); ref.add_instance(hm, np.array([[2, 0, 0, 4.5], [0, 2, 0, -1], [0, 0, 2, 0]], np.float32))   # the order swap_remove leaves
+    ref.set_blue_noise(scenes.blue_noise())
+    ref.render_frame(**view); ref.render_frame(**view); ref.render_frame(**view)
+    # same jitter sequence position? frame indices differ, so compare coverage rather than bits: the first box is gone, the second and the light stay
+    assert abs((depth > 0).mean() - (ref.image("depth")[..., 0] > 0).mean()) < 0.02
+    for w, a, b, c in worlds:
+        with pytest.raises(KjbError):
+            w.remove_instance(a)                                                                  # "no such instance"
+        w.set_instance_transform(b, ident[None][0] * 1.0)                                         # handles of the survivors stay valid
+    frame()
