@@ -89,6 +89,9 @@ int  kjb_world_set_instance_transform(kjb_world *w, uint32_t instance_handle, co
 int  kjb_world_remove_instance(kjb_world *w, uint32_t instance_handle);
 /* InstanceDynamicParameters::emissive_multiplier (world_renderer.rs:96-105,828-834): scales the instance's emissive in hit shading and its triangle lights */
 int  kjb_world_set_instance_emissive_multiplier(kjb_world *w, uint32_t instance_handle, float emissive_multiplier);
+/* WorldRenderer::sun_size_multiplier (world_renderer.rs:207,1078): angular radius of the sun disk in units of the real one; 0 = point sun (no shadow
+ * denoiser, world_render_passes.rs:130).  kjb_world_desc.hard_sun only picks the initial value (0 or 1). */
+int  kjb_world_set_sun_size_multiplier(kjb_world *w, float multiplier);
 /* the 256x256 RGBA8 blue-noise LUT (bindless slot 1; assets/images/bluenoise/256_256/LDR_RGBA_0.png in the reference) */
 int  kjb_world_set_blue_noise(kjb_world *w, const uint8_t *rgba8_256x256);
 /* SPATIAL_RESOLVE_OFFSETS (rtr.rs:402-915): the int4[512] constant table the reflection passes receive; required when enable_rtr */

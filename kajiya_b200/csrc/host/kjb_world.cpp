@@ -93,6 +93,7 @@ struct kjb_world {
     std::vector<uint32_t> mesh_index_counts;
     std::vector<std::vector<kjb_triangle_light>> mesh_lights;
     uint32_t frame_light_count = 0;   // triangle lights of the frame being rendered
+    float sun_size_multiplier = 1.0f;  // WorldRenderer::sun_size_multiplier (world_renderer.rs:207,508): 1 = the sun as seen from Earth, 0 = point sun
     std::vector<uint32_t> instance_handles; std::map<uint32_t, uint32_t> instance_handle_to_index; uint32_t next_instance_handle = 0;   // world_renderer.rs:150-152
     std::vector<kjb_instance> instances, prev_instances;   // prev = transforms of the last rendered frame (retire_frame, world_renderer.rs:1110-1113)
     std::vector<std::vector<uint8_t>> texture_storage;
@@ -208,6 +209,7 @@ extern "C" {
 int kjb_world_create(kjb_context* ctx, const kjb_world_desc* desc, kjb_world** out) {
     kjb_world* w = new kjb_world();
     w->ctx = ctx; w->desc = *desc;
+    w->sun_size_multiplier = desc->hard_sun ? 0.0f : 1.0f;
     kjb_set_option(ctx, KJB_OPTION_HALF_RES_POSITION_CACHE, 1);   // this driver only writes half_depth / the packed reservoirs through the passes the option tracks
     if (w->desc.spatial_reuse_pass_count == 0) w->desc.spatial_reuse_pass_count = 2;
     w->W = desc->render_width; w->H = desc->render_height;
@@ -335,6 +337,8 @@ int kjb_world_set_instance_emissive_multiplier(kjb_world* w, uint32_t handle, fl
     return 0;
 }
 
+int kjb_world_set_sun_size_multiplier(kjb_world* w, float m) { if (!(m >= 0.0f)) return 1; w->sun_size_multiplier = m; return 0; }
+
 int kjb_world_set_blue_noise(kjb_world* w, const uint8_t* rgba) {
     kjb_image& bn = w->img("lut.blue_noise", 256, 256, KJB_FMT_RGBA8_UNORM);
     int rc = kjb_image_upload(w->ctx, &bn, rgba);
@@ -412,7 +416,7 @@ static int begin_frame(kjb_world* w, const kjb_world_frame* f, kjb_frame_constan
     fc.frame_index = w->frame_idx;
     fc.delta_time_seconds = f->delta_time_seconds > 0 ? f->delta_time_seconds : 1.0f / 60.0f;
     // WorldRenderer::sun_size_multiplier (world_renderer.rs:207,508,1078): 1.0 = the sun as seen from Earth; hard_sun = 0
-    fc.sun_angular_radius_cos = std::cos((w->desc.hard_sun ? 0.0f : 1.0f) * (0.53f * 3.14159265358979323846f / 180.0f) * 0.5f);
+    fc.sun_angular_radius_cos = std::cos(w->sun_size_multiplier * ((0.53f * 3.14159265358979323846f / 180.0f) * 0.5f));
     for (int c = 0; c < 3; ++c) { fc.sun_color_multiplier[c] = 1.0f; fc.sky_ambient[c] = 0.0f; }
     fc.pre_exposure = fc.pre_exposure_prev = fc.pre_exposure_delta = 1.0f;   // dynamic exposure lives in post (out of scope): EV 0
     fc.render_override_flags = 0; fc.render_override_material_roughness_scale = 1.0f;
@@ -1075,7 +1079,7 @@ int kjb_world_render_frame(kjb_world* w, const kjb_world_frame* f) {
         kjb_image& debug_out_tex = w->img("debug_out", W, H, KJB_FMT_RGBA16_FLOAT);
         // ShadowDenoiseRenderer::render (shadow_denoise.rs:19-120) whenever the sun is an area light (world_render_passes.rs:130-137)
         kjb_image* shadow_for_lighting = &sun_shadow_mask;
-        if (!w->desc.hard_sun) {
+        if (w->sun_size_multiplier > 0.0f) {   // world_render_passes.rs:130
             uint32_t ext[2] = {(W + 7) / 8, (H + 3) / 4};
             float size[4]; size4(size, gbuffer);
             kjb_image& bitpacked = w->img("shadow_denoise.bitpacked", ext[0], ext[1], KJB_FMT_R32_UINT);

@@ -111,6 +111,10 @@ class World:
         t = (C.c_float * 12)(*np.asarray(transform, np.float32).reshape(-1)[:12])
         self._check(self.d.kjb_world_set_instance_transform(self.w, handle, C.byref(t)))
 
+    def set_sun_size_multiplier(self, m):
+        """WorldRenderer::sun_size_multiplier: 1 = the real sun disk, 0 = point sun (skips the shadow denoiser)"""
+        self._check(self.d.kjb_world_set_sun_size_multiplier(self.w, float(m)))
+
     def remove_instance(self, handle):
         """WorldRenderer::remove_instance (swap_remove: the last instance takes the freed slot)"""
         self._check(self.d.kjb_world_remove_instance(self.w, handle))

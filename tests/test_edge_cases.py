@@ -152,3 +152,27 @@ def test_remove_instance_and_emissive_multiplier(oracle_lib, emu_lib):
             w.remove_instance(a)                                                                  # "no such instance"
         w.set_instance_transform(b, ident[None][0] * 1.0)                                         # handles of the survivors stay valid
     frame()
+
+
+def test_sun_size_multiplier_at_run_time(oracle_lib, emu_lib):
+    """WorldRenderer::sun_size_multiplier: a larger disk softens the shadows (denoiser on), 0 is the point sun (denoiser off, world_render_passes.rs:130)"""
+    import parity
+    scene, view = scenes.cornell_box()
+    wa, wb = parity.make_world(oracle_lib, scene, 72, 44, enable_lighting=True), parity.make_world(emu_lib, scene, 72, 44, enable_lighting=True)
+    def frames(n):
+        for _ in range(n):
+            wa.render_frame(**view); wb.render_frame(**view)
+            assert not parity.compare_images(wa, wb)
+    frames(2)
+    raw1 = wb.image("sun_shadow_mask")[..., 0].astype(np.float32).copy(); launches_soft = wb.stats()["launches"]
+    for w in (wa, wb): w.set_sun_size_multiplier(8.0)
+    frames(3)
+    geo = wb.image("depth")[..., 0] != 0
+    # a disk 8x wider: more texels differ between two 1-spp masks of consecutive frames (wider penumbrae)
+    m_a = wb.image("sun_shadow_mask")[..., 0].astype(np.float32).copy(); frames(1); m_b = wb.image("sun_shadow_mask")[..., 0].astype(np.float32)
+    assert (m_a[geo] != m_b[geo]).mean() > 0.005
+    for w in (wa, wb): w.set_sun_size_multiplier(0.0)
+    frames(2)
+    assert wb.stats()["launches"] == launches_soft - 5                   # bitpack + temporal + 3 spatial are gone
+    with pytest.raises(KjbError):
+        wb.set_sun_size_multiplier(-1.0)
