@@ -89,6 +89,13 @@ int  kjb_world_set_instance_transform(kjb_world *w, uint32_t instance_handle, co
 int  kjb_world_remove_instance(kjb_world *w, uint32_t instance_handle);
 /* InstanceDynamicParameters::emissive_multiplier (world_renderer.rs:96-105,828-834): scales the instance's emissive in hit shading and its triangle lights */
 int  kjb_world_set_instance_emissive_multiplier(kjb_world *w, uint32_t instance_handle, float emissive_multiplier);
+/* WorldRenderer's public knobs that reach FrameConstants (world_renderer.rs:200-211,1066-1108): sun colour multiplier and sky ambient (baked into
+ * the sky cubes, which are recomputed), RenderOverrides (KJB_OVERRIDE_* flags + material roughness scale, consumed by the closest-hit shader),
+ * debug_shading_mode of the lit composite (0 default, 2 diffuse GI, 3 reflections, 4 "RTX off"). */
+int  kjb_world_set_sun_color_multiplier(kjb_world *w, const float rgb[3]);
+int  kjb_world_set_sky_ambient(kjb_world *w, const float rgb[3]);
+int  kjb_world_set_render_overrides(kjb_world *w, uint32_t flags, float material_roughness_scale);
+int  kjb_world_set_debug_shading_mode(kjb_world *w, uint32_t mode);
 /* WorldRenderer::sun_size_multiplier (world_renderer.rs:207,1078): angular radius of the sun disk in units of the real one; 0 = point sun (no shadow
  * denoiser, world_render_passes.rs:130).  kjb_world_desc.hard_sun only picks the initial value (0 or 1). */
 int  kjb_world_set_sun_size_multiplier(kjb_world *w, float multiplier);

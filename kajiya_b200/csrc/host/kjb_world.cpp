@@ -93,6 +93,9 @@ struct kjb_world {
     std::vector<uint32_t> mesh_index_counts;
     std::vector<std::vector<kjb_triangle_light>> mesh_lights;
     uint32_t frame_light_count = 0;   // triangle lights of the frame being rendered
+    float sun_color_multiplier[3] = {1, 1, 1}, sky_ambient[3] = {0, 0, 0};   // world_renderer.rs:208-209,511-512
+    uint32_t render_override_flags = 0; float render_override_material_roughness_scale = 1.0f;   // RenderOverrides (rust-shaders-shared frame_constants.rs)
+    uint32_t debug_shading_mode = 0;   // world_renderer.rs:201 (light_gbuffer.hlsl modes 0, 2, 3, 4)
     float sun_size_multiplier = 1.0f;  // WorldRenderer::sun_size_multiplier (world_renderer.rs:207,508): 1 = the sun as seen from Earth, 0 = point sun
     std::vector<uint32_t> instance_handles; std::map<uint32_t, uint32_t> instance_handle_to_index; uint32_t next_instance_handle = 0;   // world_renderer.rs:150-152
     std::vector<kjb_instance> instances, prev_instances;   // prev = transforms of the last rendered frame (retire_frame, world_renderer.rs:1110-1113)
@@ -337,6 +340,13 @@ int kjb_world_set_instance_emissive_multiplier(kjb_world* w, uint32_t handle, fl
     return 0;
 }
 
+int kjb_world_set_sun_color_multiplier(kjb_world* w, const float rgb[3]) { memcpy(w->sun_color_multiplier, rgb, 12); w->sky_valid = false; return 0; }   // the sky cube bakes it in
+int kjb_world_set_sky_ambient(kjb_world* w, const float rgb[3]) { memcpy(w->sky_ambient, rgb, 12); w->sky_valid = false; return 0; }
+int kjb_world_set_render_overrides(kjb_world* w, uint32_t flags, float material_roughness_scale) {
+    if (flags & ~15u) return 1;
+    w->render_override_flags = flags; w->render_override_material_roughness_scale = material_roughness_scale; return 0;
+}
+int kjb_world_set_debug_shading_mode(kjb_world* w, uint32_t mode) { if (mode == 1 || mode > 4) return 1; w->debug_shading_mode = mode; return 0; }
 int kjb_world_set_sun_size_multiplier(kjb_world* w, float m) { if (!(m >= 0.0f)) return 1; w->sun_size_multiplier = m; return 0; }
 
 int kjb_world_set_blue_noise(kjb_world* w, const uint8_t* rgba) {
@@ -417,9 +427,9 @@ static int begin_frame(kjb_world* w, const kjb_world_frame* f, kjb_frame_constan
     fc.delta_time_seconds = f->delta_time_seconds > 0 ? f->delta_time_seconds : 1.0f / 60.0f;
     // WorldRenderer::sun_size_multiplier (world_renderer.rs:207,508,1078): 1.0 = the sun as seen from Earth; hard_sun = 0
     fc.sun_angular_radius_cos = std::cos(w->sun_size_multiplier * ((0.53f * 3.14159265358979323846f / 180.0f) * 0.5f));
-    for (int c = 0; c < 3; ++c) { fc.sun_color_multiplier[c] = 1.0f; fc.sky_ambient[c] = 0.0f; }
+    for (int c = 0; c < 3; ++c) { fc.sun_color_multiplier[c] = w->sun_color_multiplier[c]; fc.sky_ambient[c] = w->sky_ambient[c]; }
     fc.pre_exposure = fc.pre_exposure_prev = fc.pre_exposure_delta = 1.0f;   // dynamic exposure lives in post (out of scope): EV 0
-    fc.render_override_flags = 0; fc.render_override_material_roughness_scale = 1.0f;
+    fc.render_override_flags = w->render_override_flags; fc.render_override_material_roughness_scale = w->render_override_material_roughness_scale;
 
     if (w->desc.enable_ircache) {
         // IrcacheRenderer::update_eye_position + constants (ircache.rs:125-157, world_renderer.rs:1060-1092)
@@ -1102,7 +1112,7 @@ int kjb_world_render_frame(kjb_world* w, const kjb_world_frame* f) {
             shadow_for_lighting = &spatial_input_image;
         }
         kjb_light_gbuffer_args a{}; a.gbuffer_tex = gbuffer; a.depth_tex = depth; a.shadow_mask_tex = *shadow_for_lighting; a.rtr_tex = rtr; a.rtdgi_tex = gi;
-        a.temporal_output_tex = accum_img; a.output_tex = debug_out_tex; a.unconvolved_sky_cube_tex = sky_cube; a.sky_cube_tex = convolved_sky_cube; size4(a.output_tex_size, gbuffer);
+        a.temporal_output_tex = accum_img; a.output_tex = debug_out_tex; a.unconvolved_sky_cube_tex = sky_cube; a.sky_cube_tex = convolved_sky_cube; size4(a.output_tex_size, gbuffer); a.debug_shading_mode = w->debug_shading_mode;
         RUN("light gbuffer", kjb_pass_light_gbuffer(ctx, &a));
         result_name = "debug_out";
     }

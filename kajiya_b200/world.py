@@ -111,6 +111,19 @@ class World:
         t = (C.c_float * 12)(*np.asarray(transform, np.float32).reshape(-1)[:12])
         self._check(self.d.kjb_world_set_instance_transform(self.w, handle, C.byref(t)))
 
+    def set_sun_color_multiplier(self, rgb):
+        self._check(self.d.kjb_world_set_sun_color_multiplier(self.w, C.byref((C.c_float * 3)(*rgb))))
+
+    def set_sky_ambient(self, rgb):
+        self._check(self.d.kjb_world_set_sky_ambient(self.w, C.byref((C.c_float * 3)(*rgb))))
+
+    def set_render_overrides(self, flags=0, material_roughness_scale=1.0):
+        """RenderOverrides: 1 FORCE_FACE_NORMALS, 2 NO_NORMAL_MAPS, 4 FLIP_NORMAL_MAP_YZ, 8 NO_METAL; roughness scale as in the view app's GUI"""
+        self._check(self.d.kjb_world_set_render_overrides(self.w, int(flags), float(material_roughness_scale)))
+
+    def set_debug_shading_mode(self, mode):
+        self._check(self.d.kjb_world_set_debug_shading_mode(self.w, int(mode)))
+
     def set_sun_size_multiplier(self, m):
         """WorldRenderer::sun_size_multiplier: 1 = the real sun disk, 0 = point sun (skips the shadow denoiser)"""
         self._check(self.d.kjb_world_set_sun_size_multiplier(self.w, float(m)))
