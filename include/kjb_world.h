@@ -107,6 +107,8 @@ int  kjb_world_set_spatial_resolve_offsets(kjb_world *w, const int32_t *int4x512
 int  kjb_world_render_frame(kjb_world *w, const kjb_world_frame *frame);
 /* one frame of prepare_render_graph_reference (world_render_passes.rs:294-330): the path tracer accumulating in place */
 int  kjb_world_render_reference(kjb_world *w, const kjb_world_frame *frame, uint32_t indirect_only);
+/* WorldRenderer::reset_reference_accumulation (world_renderer.rs:183): the next reference frame starts from a cleared accumulator (camera moved, scene edited) */
+int  kjb_world_reset_reference_accumulation(kjb_world *w);
 /* block until every streaming frame submitted so far has delivered its host_result */
 int  kjb_world_wait(kjb_world *w);
 uint32_t kjb_world_frame_index(kjb_world *w);

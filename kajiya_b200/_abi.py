@@ -97,6 +97,7 @@ class KjbLib:
             "kjb_world_set_sky_ambient": (C.c_int, [P, C.POINTER(C.c_float * 3)]),
             "kjb_world_set_render_overrides": (C.c_int, [P, C.c_uint32, C.c_float]),
             "kjb_world_set_debug_shading_mode": (C.c_int, [P, C.c_uint32]),
+            "kjb_world_reset_reference_accumulation": (C.c_int, [P]),
             "kjb_world_set_instance_emissive_multiplier": (C.c_int, [P, C.c_uint32, C.c_float]),
             "kjb_world_set_blue_noise": (C.c_int, [P, P]),
             "kjb_world_set_spatial_resolve_offsets": (C.c_int, [P, P]),

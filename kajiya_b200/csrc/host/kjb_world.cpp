@@ -95,6 +95,7 @@ struct kjb_world {
     uint32_t frame_light_count = 0;   // triangle lights of the frame being rendered
     float sun_color_multiplier[3] = {1, 1, 1}, sky_ambient[3] = {0, 0, 0};   // world_renderer.rs:208-209,511-512
     uint32_t render_override_flags = 0; float render_override_material_roughness_scale = 1.0f;   // RenderOverrides (rust-shaders-shared frame_constants.rs)
+    bool reset_reference_accumulation = false;   // world_renderer.rs:183
     uint32_t debug_shading_mode = 0;   // world_renderer.rs:201 (light_gbuffer.hlsl modes 0, 2, 3, 4)
     float sun_size_multiplier = 1.0f;  // WorldRenderer::sun_size_multiplier (world_renderer.rs:207,508): 1 = the sun as seen from Earth, 0 = point sun
     std::vector<uint32_t> instance_handles; std::map<uint32_t, uint32_t> instance_handle_to_index; uint32_t next_instance_handle = 0;   // world_renderer.rs:150-152
@@ -346,6 +347,7 @@ int kjb_world_set_render_overrides(kjb_world* w, uint32_t flags, float material_
     if (flags & ~15u) return 1;
     w->render_override_flags = flags; w->render_override_material_roughness_scale = material_roughness_scale; return 0;
 }
+int kjb_world_reset_reference_accumulation(kjb_world* w) { w->reset_reference_accumulation = true; return 0; }
 int kjb_world_set_debug_shading_mode(kjb_world* w, uint32_t mode) { if (mode == 1 || mode > 4) return 1; w->debug_shading_mode = mode; return 0; }
 int kjb_world_set_sun_size_multiplier(kjb_world* w, float m) { if (!(m >= 0.0f)) return 1; w->sun_size_multiplier = m; return 0; }
 
@@ -1149,6 +1151,7 @@ int kjb_world_render_reference(kjb_world* w, const kjb_world_frame* f, uint32_t 
     kjb_frame_constants fc;
     if (begin_frame(w, f, fc, false)) return 1;
     kjb_image& accum = w->img("refpt.accum", w->W, w->H, KJB_FMT_RGBA32_FLOAT);
+    if (w->reset_reference_accumulation) { w->reset_reference_accumulation = false; if (kjb_image_clear(w->ctx, &accum)) w->err = 1; }   // world_render_passes.rs:311-314
     kjb_reference_pt_args a{accum, indirect_only};
     RUN("reference pt", kjb_pass_reference_path_trace(w->ctx, &a));
     if (f->host_result && !w->err) { kjb_image_download(w->ctx, &accum, f->host_result); kjb_sync(w->ctx); }

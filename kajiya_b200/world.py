@@ -121,6 +121,9 @@ class World:
         """RenderOverrides: 1 FORCE_FACE_NORMALS, 2 NO_NORMAL_MAPS, 4 FLIP_NORMAL_MAP_YZ, 8 NO_METAL; roughness scale as in the view app's GUI"""
         self._check(self.d.kjb_world_set_render_overrides(self.w, int(flags), float(material_roughness_scale)))
 
+    def reset_reference_accumulation(self):
+        self._check(self.d.kjb_world_reset_reference_accumulation(self.w))
+
     def set_debug_shading_mode(self, mode):
         self._check(self.d.kjb_world_set_debug_shading_mode(self.w, int(mode)))
 

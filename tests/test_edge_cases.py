@@ -215,3 +215,18 @@ def test_world_renderer_knobs(oracle_lib, emu_lib):
     for bad in (lambda: wb.set_debug_shading_mode(1), lambda: wb.set_debug_shading_mode(5), lambda: wb.set_render_overrides(16, 1.0)):
         with pytest.raises(KjbError):
             bad()
+
+
+def test_reference_accumulation_reset(oracle_lib, emu_lib):
+    """reset_reference_accumulation: the path tracer's running mean (accum.w = sample count) restarts from a cleared image"""
+    import parity
+    scene, view = scenes.cornell_box()
+    wa, wb = parity.make_world(oracle_lib, scene, 40, 28), parity.make_world(emu_lib, scene, 40, 28)
+    for _ in range(3):
+        wa.render_reference(**view); wb.render_reference(**view)
+    assert float(wb.image("refpt.accum")[..., 3].max()) == 3.0
+    for w in (wa, wb): w.reset_reference_accumulation()
+    moved = dict(view, camera_position=(0.5, 1.2, 6.0))
+    wa.render_reference(**moved); wb.render_reference(**moved)
+    a, b = wa.image("refpt.accum"), wb.image("refpt.accum")
+    assert np.array_equal(a.view(np.uint32), b.view(np.uint32)) and float(b[..., 3].max()) == 1.0
