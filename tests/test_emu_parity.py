@@ -313,3 +313,27 @@ def test_position_cache_is_invisible(emu_lib):
         wa.render_frame(**view); wb.render_frame(**view)
         assert not parity.compare_images(wa, wb), f
     assert wa.stats()["launches"] == wb.stats()["launches"]   # both position sets ride in kernels that run anyway (fused extract, restir temporal)
+
+
+def test_shadow_denoiser_neighbourhood_against_a_plain_convolution(oracle_lib):
+    """Independent pin of the denoiser's bit-mask arithmetic (three 8x4 tiles -> 17 horizontal taps, group-shared vertical pass): for tiles that
+    are filtered, moments.w must equal the separable 17x17 FFX kernel applied to the binary mask with zero padding (fp16 storage tolerance)"""
+    scene, view = scenes.cornell_box()
+    w_, h_ = 90, 58
+    w = parity.make_world(oracle_lib, scene, w_, h_, enable_lighting=True)
+    w.render_frame(**view)
+    mask = (w.image("sun_shadow_mask")[..., 0] > 127).astype(np.float64)
+    k = np.exp(-3.0 * np.arange(9) ** 2 / 81.0); k = k / (k[0] + 2 * k[1:].sum())
+    kern = np.concatenate([k[:0:-1], k])
+    pad = np.pad(mask, 8)
+    hor = sum(kern[i] * pad[8:-8, i:i + w_] for i in range(17))
+    padv = np.pad(hor, ((8, 8), (0, 0)))
+    want = sum(kern[i] * padv[i:i + h_] for i in range(17))
+    got = w.image("shadow_denoise_moments:0")[..., 3].astype(np.float64)
+    meta = w.image("shadow_denoise.metadata")[: (h_ + 7) // 8, : (w_ + 7) // 8, 0]
+    filtered = np.kron((meta & 1) == 0, np.ones((8, 8), bool))[:h_, :w_]
+    assert filtered.mean() > 0.05
+    assert np.abs(got - want)[filtered].max() < 2e-3, np.abs(got - want)[filtered].max()
+    # cleared tiles carry the uniform value instead
+    cleared_lit = np.kron(meta == 3, np.ones((8, 8), bool))[:h_, :w_]
+    assert (got[cleared_lit] == 1.0).all()
