@@ -6,7 +6,7 @@ import numpy as np
 from ._abi import MeshDesc, MeshMaterial, TextureDesc
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-ASSET_SO = os.path.join(_HERE, "csrc", "libkjb_asset.so")
+ASSET_SO = os.environ.get("KJB_ASSET_SO") or os.path.join(_HERE, "csrc", "libkjb_asset.so")   # KJB_ASSET_SO: the sanitizer build tests/test_asset.py makes of the same sources
 _dll = None
 
 

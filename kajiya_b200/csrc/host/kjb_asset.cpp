@@ -143,14 +143,24 @@ int type_components(const std::string& t) { return t == "SCALAR" ? 1 : t == "VEC
 
 struct View { const uint8_t* p = nullptr; size_t stride = 0, count = 0; int64_t ctype = 0; int comps = 0; bool normalized = false; };
 bool view_of(const Doc& d, const Json& bv_list, int64_t bv_index, size_t byte_offset, size_t elem_bytes, size_t count, View& v, const char* what) {
+    if (bv_index < 0) { set_error(std::string(what) + ": bad bufferView index"); return false; }
     const Json& bv = bv_list[size_t(bv_index)];
-    if (bv_index < 0 || !bv.is(Json::Object)) { set_error(std::string(what) + ": bad bufferView index"); return false; }
+    if (!bv.is(Json::Object)) { set_error(std::string(what) + ": bad bufferView index"); return false; }
     const int64_t bi = bv.i("buffer", -1);
     if (bi < 0 || size_t(bi) >= d.buffers.size()) { set_error(std::string(what) + ": bad buffer index"); return false; }
-    const size_t off = size_t(bv.i("byteOffset", 0)) + byte_offset, len = size_t(bv.i("byteLength", 0));
-    const size_t stride = bv.has("byteStride") ? size_t(bv.i("byteStride", 0)) : elem_bytes;
-    if (count && (byte_offset + (count - 1) * stride + elem_bytes > len || off + (count - 1) * stride + elem_bytes > d.buffers[size_t(bi)].size())) { set_error(std::string(what) + ": accessor reaches past its buffer view"); return false; }
-    v.p = d.buffers[size_t(bi)].data() + off; v.stride = stride;
+    bool ok = true;
+    const size_t bv_off = bv.size("byteOffset", 0, ok), len = bv.size("byteLength", 0, ok);
+    const size_t stride = bv.has("byteStride") ? bv.size("byteStride", 0, ok) : elem_bytes;
+    if (!ok) { set_error(std::string(what) + ": bufferView byteOffset / byteLength / byteStride is not a non-negative integer"); return false; }
+    const size_t buf_size = d.buffers[size_t(bi)].size();
+    // every comparison is written so that nothing can wrap: the view lies inside its buffer, the accessor inside its view
+    if (bv_off > buf_size || len > buf_size - bv_off) { set_error(std::string(what) + ": buffer view reaches past its buffer"); return false; }
+    if (count) {
+        if (elem_bytes > len || byte_offset > len - elem_bytes) { set_error(std::string(what) + ": accessor reaches past its buffer view"); return false; }
+        const size_t room = len - byte_offset - elem_bytes;   // bytes available for the (count - 1) strides
+        if (count - 1 != 0 && (stride == 0 ? false : (count - 1) > room / stride)) { set_error(std::string(what) + ": accessor reaches past its buffer view"); return false; }
+    }
+    v.p = d.buffers[size_t(bi)].data() + bv_off + byte_offset; v.stride = stride;
     return true;
 }
 double load_component(const uint8_t* p, int64_t ct) {
@@ -168,13 +178,16 @@ struct AccessorData { std::vector<float> f; std::vector<uint32_t> u; int64_t cty
 bool read_accessor(const Doc& d, int64_t index, bool as_uint, AccessorData& out, const char* what) {
     const Json& acc = d.list("accessors")[size_t(index)];
     if (index < 0 || !acc.is(Json::Object)) { set_error(std::string(what) + ": bad accessor index"); return false; }
-    out.ctype = acc.i("componentType", 0); out.comps = type_components(acc.s("type")); out.count = size_t(acc.i("count", 0));
+    bool fields_ok = true;
+    out.ctype = acc.i("componentType", 0); out.comps = type_components(acc.s("type")); out.count = acc.size("count", 0, fields_ok);
+    const size_t acc_off = acc.size("byteOffset", 0, fields_ok);
     const int cb = component_bytes(out.ctype);
     if (!cb || !out.comps) { set_error(std::string(what) + ": bad accessor componentType/type"); return false; }
-    const size_t n = out.count * size_t(out.comps);
+    if (!fields_ok || out.count > (size_t(1) << 31)) { set_error(std::string(what) + ": accessor count / byteOffset is not a plausible non-negative integer"); return false; }
+    const size_t n = out.count * size_t(out.comps);   // <= 2^31 * 16: cannot wrap
     const Json& views = d.list("bufferViews");
     View v;   // validate the extent BEFORE sizing the output: a hostile count must not drive a multi-gigabyte allocation
-    if (acc.has("bufferView")) { if (!view_of(d, views, acc.i("bufferView", -1), size_t(acc.i("byteOffset", 0)), size_t(cb) * out.comps, out.count, v, what)) return false; }
+    if (acc.has("bufferView")) { if (!view_of(d, views, acc.i("bufferView", -1), acc_off, size_t(cb) * out.comps, out.count, v, what)) return false; }
     else if (out.count > (size_t(1) << 28)) { set_error(std::string(what) + ": accessor without a buffer view is implausibly large"); return false; }
     if (as_uint) out.u.assign(n, 0); else out.f.assign(n, 0.0f);
     auto store = [&](size_t row, const uint8_t* p) {
@@ -186,14 +199,17 @@ bool read_accessor(const Doc& d, int64_t index, bool as_uint, AccessorData& out,
     };
     if (acc.has("bufferView")) for (size_t i = 0; i < out.count; ++i) store(i, v.p + i * v.stride);
     if (const Json* sp = acc.get("sparse")) {
-        const size_t sc = size_t(sp->i("count", 0));
+        bool sp_ok = true;
+        const size_t sc = sp->size("count", 0, sp_ok);
         const Json* ji = sp->get("indices"); const Json* jv = sp->get("values");
-        if (!ji || !jv) { set_error(std::string(what) + ": malformed sparse accessor"); return false; }
+        if (!ji || !jv || !sp_ok || sc > out.count) { set_error(std::string(what) + ": malformed sparse accessor"); return false; }
+        const size_t ji_off = ji->size("byteOffset", 0, sp_ok), jv_off = jv->size("byteOffset", 0, sp_ok);
+        if (!sp_ok) { set_error(std::string(what) + ": malformed sparse accessor"); return false; }
         const int64_t ict = ji->i("componentType", 0); const int icb = component_bytes(ict);
         if (!icb) { set_error(std::string(what) + ": bad sparse index type"); return false; }
         View vi, vv;
-        if (!view_of(d, views, ji->i("bufferView", -1), size_t(ji->i("byteOffset", 0)), size_t(icb), sc, vi, what)) return false;
-        if (!view_of(d, views, jv->i("bufferView", -1), size_t(jv->i("byteOffset", 0)), size_t(cb) * out.comps, sc, vv, what)) return false;
+        if (!view_of(d, views, ji->i("bufferView", -1), ji_off, size_t(icb), sc, vi, what)) return false;
+        if (!view_of(d, views, jv->i("bufferView", -1), jv_off, size_t(cb) * out.comps, sc, vv, what)) return false;
         for (size_t k = 0; k < sc; ++k) {
             const size_t row = size_t(load_component(vi.p + k * vi.stride, ict));
             if (row >= out.count) { set_error(std::string(what) + ": sparse index out of range"); return false; }
@@ -263,7 +279,9 @@ struct Importer {
             std::vector<uint8_t> data;
             if (bufs[i].has("uri")) { if (!read_uri(d.base, bufs[i].s("uri"), data)) return false; }
             else { if (!have_blob) { set_error("gltf: buffer without uri but no GLB BIN chunk"); return false; } data.swap(blob); have_blob = false; }
-            const size_t want = size_t(bufs[i].i("byteLength", 0));
+            bool bl_ok = true;
+            const size_t want = bufs[i].size("byteLength", 0, bl_ok);
+            if (!bl_ok) { set_error("gltf: buffer byteLength is not a non-negative integer"); return false; }
             if (data.size() < want) { char m[160]; snprintf(m, sizeof m, "gltf: buffer %zu is %zu bytes, document says %zu", i, data.size(), want); set_error(m); return false; }
             while (data.size() % 4) data.push_back(0);
             d.buffers.push_back(std::move(data));
@@ -284,10 +302,13 @@ struct Importer {
             const std::string uri = percent_decode(ji.s("uri"));
             if (!read_uri(d.base, uri, bytes)) { im.where = g_error; return nullptr; }
         } else if (ji.has("bufferView")) {
-            const Json& bv = d.list("bufferViews")[size_t(ji.i("bufferView", -1))];
+            const int64_t bvi = ji.i("bufferView", -1);
+            static const Json no_view;
+            const Json& bv = bvi >= 0 ? d.list("bufferViews")[size_t(bvi)] : no_view;
             const int64_t bi = bv.i("buffer", -1);
-            const size_t off = size_t(bv.i("byteOffset", 0)), len = size_t(bv.i("byteLength", 0));
-            if (bi < 0 || size_t(bi) >= d.buffers.size() || off + len > d.buffers[size_t(bi)].size()) { im.where = "gltf: image buffer view out of range"; set_error(im.where); return nullptr; }
+            bool bv_ok = true;
+            const size_t off = bv.size("byteOffset", 0, bv_ok), len = bv.size("byteLength", 0, bv_ok);
+            if (!bv_ok || bi < 0 || size_t(bi) >= d.buffers.size() || off > d.buffers[size_t(bi)].size() || len > d.buffers[size_t(bi)].size() - off) { im.where = "gltf: image buffer view out of range"; set_error(im.where); return nullptr; }
             bytes.assign(d.buffers[size_t(bi)].begin() + off, d.buffers[size_t(bi)].begin() + off + len);
         } else { im.where = "gltf: image has neither uri nor bufferView"; set_error(im.where); return nullptr; }
         if (bytes.size() >= 4 && !memcmp(bytes.data(), "DDS ", 4)) {   // RawImage::Dds (image.rs:70-84): the file's own format and mips win over TexParams

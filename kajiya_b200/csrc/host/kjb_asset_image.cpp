@@ -302,10 +302,13 @@ const uint8_t ZIGZAG[64] = {0, 1, 8, 16, 9, 2, 3, 10, 17, 24, 32, 25, 18, 11, 4,
 // integer IDCT of stb_image (which jpeg-decoder 0.1's idct.rs follows): 12-bit fixed point constants, rows then columns
 inline int f2f(double x) { return int(x * 4096.0 + 0.5); }
 inline uint8_t clamp_u8(int x) { return uint8_t(x < 0 ? 0 : x > 255 ? 255 : x); }
+// dequantised coefficient, clamped to +-2^15: legitimate 8-bit JPEG coefficients stay below 2^12, so real files are untouched
+inline int64_t jdeq(int16_t c, uint16_t q) { const int64_t v = int64_t(c) * int64_t(q); return v < -32768 ? -32768 : v > 32768 ? 32768 : v; }
+inline uint8_t clamp_u8(int64_t x) { return uint8_t(x < 0 ? 0 : x > 255 ? 255 : x); }
 void idct_block(const int16_t* in, const uint16_t* q, uint8_t* out, size_t out_stride) {
-    int val[64];
+    int64_t val[64];
 #define KJB_IDCT_1D(s0, s1, s2, s3, s4, s5, s6, s7)                                                             \
-    int t0, t1, t2, t3, p1, p2, p3, p4, p5, x0, x1, x2, x3;                                                     \
+    int64_t t0, t1, t2, t3, p1, p2, p3, p4, p5, x0, x1, x2, x3;   /* 64-bit: hostile 16-bit DQT tables must not overflow (same values as int on real files) */ \
     p2 = s2; p3 = s6; p1 = (p2 + p3) * f2f(0.5411961); t2 = p1 + p3 * f2f(-1.847759065); t3 = p1 + p2 * f2f(0.765366865); \
     p2 = s0; p3 = s4; t0 = (p2 + p3) * 4096; t1 = (p2 - p3) * 4096;                                             \
     x0 = t0 + t3; x3 = t0 - t3; x1 = t1 + t2; x2 = t1 - t2;                                                     \
@@ -315,19 +318,19 @@ void idct_block(const int16_t* in, const uint16_t* q, uint8_t* out, size_t out_s
     p1 = p5 + p1 * f2f(-0.899976223); p2 = p5 + p2 * f2f(-2.562915447); p3 = p3 * f2f(-1.961570560); p4 = p4 * f2f(-0.390180644); \
     t3 += p1 + p4; t2 += p2 + p3; t1 += p2 + p4; t0 += p1 + p3;
     for (int i = 0; i < 8; ++i) {
-        const int16_t* d = in + i; const uint16_t* qq = q + i; int* v = val + i;
+        const int16_t* d = in + i; const uint16_t* qq = q + i; int64_t* v = val + i;
         if (d[8] == 0 && d[16] == 0 && d[24] == 0 && d[32] == 0 && d[40] == 0 && d[48] == 0 && d[56] == 0) {
-            const int dc = int(d[0]) * qq[0] * 4;
+            const int64_t dc = jdeq(d[0], qq[0]) * 4;
             v[0] = v[8] = v[16] = v[24] = v[32] = v[40] = v[48] = v[56] = dc;
         } else {
-            KJB_IDCT_1D(int(d[0]) * qq[0], int(d[8]) * qq[8], int(d[16]) * qq[16], int(d[24]) * qq[24], int(d[32]) * qq[32], int(d[40]) * qq[40], int(d[48]) * qq[48], int(d[56]) * qq[56])
+            KJB_IDCT_1D(jdeq(d[0], qq[0]), jdeq(d[8], qq[8]), jdeq(d[16], qq[16]), jdeq(d[24], qq[24]), jdeq(d[32], qq[32]), jdeq(d[40], qq[40]), jdeq(d[48], qq[48]), jdeq(d[56], qq[56]))
             x0 += 512; x1 += 512; x2 += 512; x3 += 512;
             v[0] = (x0 + t3) >> 10; v[56] = (x0 - t3) >> 10; v[8] = (x1 + t2) >> 10; v[48] = (x1 - t2) >> 10;
             v[16] = (x2 + t1) >> 10; v[40] = (x2 - t1) >> 10; v[24] = (x3 + t0) >> 10; v[32] = (x3 - t0) >> 10;
         }
     }
     for (int i = 0; i < 8; ++i) {
-        const int* v = val + i * 8; uint8_t* o = out + size_t(i) * out_stride;
+        const int64_t* v = val + i * 8; uint8_t* o = out + size_t(i) * out_stride;
         KJB_IDCT_1D(v[0], v[1], v[2], v[3], v[4], v[5], v[6], v[7])
         x0 += 65536 + (128 << 17); x1 += 65536 + (128 << 17); x2 += 65536 + (128 << 17); x3 += 65536 + (128 << 17);
         o[0] = clamp_u8((x0 + t3) >> 17); o[7] = clamp_u8((x0 - t3) >> 17); o[1] = clamp_u8((x1 + t2) >> 17); o[6] = clamp_u8((x1 - t2) >> 17);
@@ -501,6 +504,11 @@ struct JpegDecoder {
                 if (nc == 1) { comps[0].h = comps[0].v = 1; }
                 hmax = vmax = 1; for (auto& c : comps) { hmax = std::max(hmax, c.h); vmax = std::max(vmax, c.v); }
                 mcux = (width + 8 * hmax - 1) / (8 * hmax); mcuy = (height + 8 * vmax - 1) / (8 * vmax);
+                {   // plausibility before sizing the coefficient planes: every 8x8 block costs at least one entropy-coded bit, so a frame
+                    // cannot hold more blocks than 8x the bytes that are left (plus a hard cap); a tiny file with a 65535^2 SOF is refused here
+                    size_t blocks = 0; for (auto& c : comps) blocks += size_t(mcux) * c.h * size_t(mcuy) * c.v;
+                    if (blocks > (n - pos) * 8 + 64 || blocks > (size_t(1) << 24)) return fail("frame size is implausible for the amount of data");
+                }
                 for (auto& c : comps) { c.bw = mcux * c.h; c.bh = mcuy * c.v; c.coef.assign(size_t(c.bw) * c.bh * 64, 0); }
                 have_frame = true;
             } else if (m >= 0xc3 && m <= 0xcf && m != 0xc4 && m != 0xc8 && m != 0xcc) {
@@ -512,6 +520,7 @@ struct JpegDecoder {
                 if (dl >= 12 && !memcmp(d, "Adobe", 5)) adobe_transform = d[11];
             } else if (m == 0xda) {
                 if (!have_frame) return fail("scan before frame header");
+                if (dl < 1) return fail("bad SOS");
                 const int ns = d[0]; if (ns < 1 || ns > int(comps.size()) || dl < size_t(4 + 2 * ns)) return fail("bad SOS");
                 std::vector<int> order;
                 for (int i = 0; i < ns; ++i) {

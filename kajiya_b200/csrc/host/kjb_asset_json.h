@@ -30,7 +30,23 @@ struct Json {
     double number_or(double d) const { return kind == Number ? num : d; }
     // typed field readers with glTF defaults
     double f(const char* key, double d) const { const Json* j = get(key); return j && j->kind == Number ? j->num : d; }
-    int64_t i(const char* key, int64_t d) const { const Json* j = get(key); return j && j->kind == Number ? (int64_t)j->num : d; }
+    // integer field: NaN / out-of-range doubles would make the cast undefined; they saturate (callers range-check the result)
+    int64_t i(const char* key, int64_t d) const {
+        const Json* j = get(key); if (!j || j->kind != Number) return d;
+        const double v = j->num;
+        if (!(v == v)) return -1;
+        if (v >= 9007199254740992.0) return INT64_C(9007199254740992);
+        if (v <= -9007199254740992.0) return -INT64_C(9007199254740992);
+        return (int64_t)v;
+    }
+    // a size / offset / count: non-negative, integral, below 2^53 — anything else is reported through `ok`
+    size_t size(const char* key, size_t d, bool& ok) const {
+        const Json* j = get(key); if (!j) return d;
+        if (j->kind != Number) { ok = false; return 0; }
+        const double v = j->num;
+        if (!(v >= 0.0) || v >= 9007199254740992.0 || v != (double)(uint64_t)v) { ok = false; return 0; }
+        return (size_t)v;
+    }
     bool has(const char* key) const { return get(key) != nullptr; }
     std::string s(const char* key, const char* d = "") const { const Json* j = get(key); return j && j->kind == String ? j->str : std::string(d); }
 };

@@ -211,6 +211,8 @@ static void size4(float out[4], const kjb_image& i) { out[0] = float(i.width); o
 extern "C" {
 
 int kjb_world_create(kjb_context* ctx, const kjb_world_desc* desc, kjb_world** out) {
+    if (!ctx || !desc || !out || desc->render_width == 0 || desc->render_height == 0) return 1;
+    if (desc->tile_count > 1 && desc->tile_rank >= desc->tile_count) return 1;
     kjb_world* w = new kjb_world();
     w->ctx = ctx; w->desc = *desc;
     w->sun_size_multiplier = desc->hard_sun ? 0.0f : 1.0f;
@@ -241,6 +243,15 @@ void kjb_world_destroy(kjb_world* w) {
 }
 
 int kjb_world_add_mesh(kjb_world* w, const kjb_mesh_desc* mesh, uint32_t* out_handle) {
+    // a malformed description is an error code, never an out-of-bounds access on the host or the device
+    if (!w || !mesh || !mesh->positions || !mesh->normals || !mesh->indices || !mesh->material_ids || !mesh->materials) return 1;
+    if (mesh->index_count % 3u != 0 || mesh->material_count == 0) return 1;
+    for (uint32_t i = 0; i < mesh->index_count; ++i) if (mesh->indices[i] >= mesh->vertex_count) return 1;
+    for (uint32_t i = 0; i < mesh->vertex_count; ++i) if (mesh->material_ids[i] >= mesh->material_count) return 1;
+    if (mesh->map_count && !mesh->maps) return 1;
+    for (uint32_t i = 0; i < mesh->map_count; ++i) if (!mesh->maps[i].texels || !mesh->maps[i].width || !mesh->maps[i].height || !mesh->maps[i].mip_count) return 1;
+    // map ids index this mesh's own map list; a mesh without maps reads "no texture" (white) rather than whatever another mesh uploads later
+    for (uint32_t i = 0; i < mesh->material_count; ++i) for (int k = 0; k < 4; ++k) if (mesh->map_count && mesh->materials[i].maps[k] >= mesh->map_count) return 1;
     const uint32_t mesh_idx = uint32_t(w->meshes.size());
     // bindless textures: one id per map of this mesh (add_mesh dedups identical assets; ids are per-upload here)
     const uint32_t tex_base = uint32_t(w->textures.size());
@@ -252,7 +263,7 @@ int kjb_world_add_mesh(kjb_world* w, const kjb_mesh_desc* mesh, uint32_t* out_ha
     }
     std::vector<kjb_mesh_material> materials(mesh->materials, mesh->materials + mesh->material_count);
     for (auto& mat : materials) {
-        for (int k = 0; k < 4; ++k) mat.maps[k] = tex_base + mat.maps[k];
+        for (int k = 0; k < 4; ++k) mat.maps[k] = mesh->map_count ? tex_base + mat.maps[k] : 0xffffffffu;
         if (mesh->use_lights) mat.flags |= 1u;   // MESH_MATERIAL_FLAG_EMISSIVE_USED_AS_LIGHT (world_renderer.rs:649-654)
     }
     // BufferBuilder::append order (world_renderer.rs:657-672): indices, verts, uvs, material ids, colors, tangents, materials
@@ -310,6 +321,7 @@ int kjb_world_add_instance(kjb_world* w, uint32_t mesh, const float transform[12
     const uint32_t handle = w->next_instance_handle++;
     w->instance_handle_to_index[handle] = uint32_t(w->instances.size());
     w->instances.push_back(i); w->instance_handles.push_back(handle);
+    w->prev_instances.push_back(i);   // a new instance starts with prev_transform = transform (world_renderer.rs:785-797)
     if (out_handle) *out_handle = handle;
     return 0;
 }
@@ -321,6 +333,7 @@ int kjb_world_remove_instance(kjb_world* w, uint32_t handle) {
     const uint32_t index = it->second;
     w->instance_handle_to_index.erase(it);
     w->instances[index] = w->instances.back(); w->instances.pop_back();
+    w->prev_instances[index] = w->prev_instances.back(); w->prev_instances.pop_back();   // prev_transform lives in the MeshInstance upstream: it moves with the swap_remove
     w->instance_handles[index] = w->instance_handles.back(); w->instance_handles.pop_back();
     if (index < w->instance_handles.size()) w->instance_handle_to_index[w->instance_handles[index]] = index;
     return 0;
@@ -1031,7 +1044,7 @@ int kjb_world_render_frame(kjb_world* w, const kjb_world_frame* f) {
         if (rc) return rc;
     } else {
         kjb_raster_gbuffer_args a{geometric_normal, gbuffer, depth, velocity, nullptr, 0};
-        if (w->prev_instances.size() == w->instances.size()) { a.prev_instances = w->prev_instances.data(); a.prev_instance_count = uint32_t(w->prev_instances.size()); }
+        a.prev_instances = w->prev_instances.data(); a.prev_instance_count = uint32_t(w->prev_instances.size());   // slot-aligned with `instances` by construction
         RUN("raster simple", kjb_pass_raster_gbuffer(ctx, &a));
     }
     if (f->capture_slot && !f->replay_slot) {

@@ -444,3 +444,84 @@ def test_malformed_inputs_never_crash_the_importer(tmp_path):
     assert r.returncode == 0, (r.returncode, r.stderr[-500:])
     tag, decoded, rejected, loaded, refused = r.stdout.split()[-5:]
     assert tag == "FUZZ" and int(decoded) + int(rejected) == 700 and int(loaded) + int(refused) == 500 and int(rejected) > 100 and int(refused) > 100
+
+
+# ------------------------------------------------------------------ structured hostile inputs, against an ASan + UBSan build of the importer
+_HOSTILE = r'''
+import sys, os, json, struct, shutil
+sys.path.insert(0, sys.argv[1])
+from kajiya_b200 import asset
+fix, tmp = sys.argv[2], sys.argv[3]
+for f in ("courtyard.bin", "albedo tex.png", "spec.png"): shutil.copy(os.path.join(fix, f), tmp)
+doc = json.load(open(os.path.join(fix, "courtyard.gltf")))
+def with_(path, value):
+    d = json.loads(json.dumps(doc)); o = d
+    for k in path[:-1]: o = o[k]
+    o[path[-1]] = value
+    return d
+acc_with_view = next(i for i, a in enumerate(doc["accessors"]) if "bufferView" in a)
+bv = doc["accessors"][acc_with_view]["bufferView"]
+cases = []
+for v in (4611686018427387904, 2 ** 63, 2 ** 64, 1e300, -1, -16, 2.5, 2 ** 53, 2 ** 40):
+    cases.append(with_(["accessors", acc_with_view, "count"], v))
+    cases.append(with_(["accessors", acc_with_view, "byteOffset"], v))
+    cases.append(with_(["bufferViews", bv, "byteOffset"], v))
+    cases.append(with_(["bufferViews", bv, "byteLength"], v))
+    cases.append(with_(["bufferViews", bv, "byteStride"], v))
+    cases.append(with_(["buffers", 0, "byteLength"], v))
+d = with_(["accessors", acc_with_view, "count"], 4611686018427387904); d["accessors"][acc_with_view]["type"] = "VEC4"; d["bufferViews"][bv]["byteStride"] = 16; cases.append(d)
+for v in (4611686018427387904, -1, 2 ** 32, 10 ** 6):
+    d = json.loads(json.dumps(doc)); a = d["accessors"][acc_with_view]
+    a["sparse"] = {"count": v, "indices": {"bufferView": bv, "componentType": 5125, "byteOffset": 0}, "values": {"bufferView": bv, "byteOffset": 0}}; cases.append(d)
+    d = json.loads(json.dumps(doc)); a = d["accessors"][acc_with_view]
+    a["sparse"] = {"count": 1, "indices": {"bufferView": bv, "componentType": 5125, "byteOffset": v}, "values": {"bufferView": bv, "byteOffset": v}}; cases.append(d)
+if doc.get("images"):
+    for v in (-16, 2 ** 63, 2 ** 64 - 8):
+        d = json.loads(json.dumps(doc)); d["images"][0] = {"bufferView": bv, "mimeType": "image/png"}; d["bufferViews"][bv]["byteOffset"] = v; cases.append(d)
+        d = json.loads(json.dumps(doc)); d["images"][0] = {"bufferView": -1, "mimeType": "image/png"}; cases.append(d)
+loaded = refused = 0
+for d in cases:
+    open(os.path.join(tmp, "h.gltf"), "w").write(json.dumps(d))
+    try: s = asset.GltfScene(os.path.join(tmp, "h.gltf")); s.arrays(); s.close(); loaded += 1
+    except asset.AssetError: refused += 1
+good = open(os.path.join(fix, "jpg", "baseline_420.jpg"), "rb").read()
+sos = good.index(b"\xff\xda")
+jpegs = [good[:sos] + b"\xff\xda\x00\x02", good[:sos] + b"\xff\xda\x00\x03\x03", b"\xff\xd8\xff\xda\x00\x02"]
+sof = good.index(b"\xff\xc0")
+big = bytearray(good); big[sof + 5:sof + 9] = b"\xff\xff\xff\xff"; jpegs.append(bytes(big[:sos + 40]))
+dqt = good.index(b"\xff\xdb")
+q16 = bytearray(good[:dqt]) + b"\xff\xdb" + struct.pack(">H", 2 + 129) + bytes([0x10]) + b"\xff\xff" * 64 + good[dqt:]   # a 16-bit table 0 of 65535s ahead of the real ones ...
+jpegs.append(bytes(q16))
+ln = struct.unpack(">H", good[dqt + 2:dqt + 4])[0]
+q16b = bytearray(good[:dqt + 2 + ln]) + b"\xff\xdb" + struct.pack(">H", 2 + 129) + bytes([0x10]) + b"\xff\xff" * 64 + good[dqt + 2 + ln:]   # ... and one that replaces table 0 before the scan
+jpegs.append(bytes(q16b))
+dec = rej = 0
+for j in jpegs:
+    try: asset.decode_image(j); dec += 1
+    except asset.AssetError: rej += 1
+print("HOSTILE", len(cases), loaded, refused, len(jpegs), dec, rej)
+'''
+
+
+def test_structured_hostile_inputs_under_sanitizers(tmp_path):
+    """Numeric-field overflows (count / byteOffset / byteStride / byteLength at 2^62, 2^64, negative, fractional; sparse views; image buffer
+    views), a SOS cut after its length word, a 65535^2 SOF on a tiny file and 16-bit quantisation tables of 65535 — against the importer
+    built with AddressSanitizer + UBSan, in a child process: every case is refused or decodes, and the sanitizers stay silent"""
+    import shutil, subprocess
+    if not shutil.which("g++"):
+        pytest.skip("no host compiler")
+    host = os.path.join(conftest.ROOT, "kajiya_b200", "csrc", "host")
+    out = os.path.join(conftest.ROOT, "tests", "emu", "_build_san", "libkjb_asset_san.so")
+    os.makedirs(os.path.dirname(out), exist_ok=True)
+    srcs = [os.path.join(host, f) for f in ("kjb_asset.cpp", "kjb_asset_image.cpp")]
+    deps = srcs + [os.path.join(host, "kjb_asset_json.h")]
+    if not os.path.exists(out) or any(os.path.getmtime(d) > os.path.getmtime(out) for d in deps):
+        subprocess.run(["g++", "-O1", "-g", "-std=c++17", "-fPIC", "-shared", "-ffp-contract=off", "-fno-omit-frame-pointer", "-fsanitize=address,undefined",
+                        "-fno-sanitize=vptr", "-fno-sanitize-recover=undefined", "-I", os.path.join(conftest.ROOT, "include")] + srcs + ["-o", out], check=True)
+    rt = subprocess.run(["gcc", "-print-file-name=libasan.so"], stdout=subprocess.PIPE, text=True).stdout.strip()
+    env = dict(os.environ, KJB_ASSET_SO=out, LD_PRELOAD=rt, ASAN_OPTIONS="detect_leaks=0:halt_on_error=1:abort_on_error=1", UBSAN_OPTIONS="halt_on_error=1:print_stacktrace=1")
+    r = subprocess.run([sys.executable, "-c", _HOSTILE, conftest.ROOT, FIX, str(tmp_path)], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=600, env=env)
+    assert r.returncode == 0, (r.returncode, r.stderr[-1500:])
+    assert "ERROR: AddressSanitizer" not in r.stderr and "runtime error" not in r.stderr, r.stderr[-1500:]
+    tag, ncases, loaded, refused, njpeg, dec, rej = r.stdout.split()[-7:]
+    assert tag == "HOSTILE" and int(loaded) + int(refused) == int(ncases) and int(refused) >= int(ncases) - 12 and int(dec) + int(rej) == int(njpeg) and int(rej) >= 4
