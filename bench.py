@@ -1,38 +1,53 @@
 #!/usr/bin/env python
-"""bench.py — headline benchmark of the B200-native kajiya ReSTIR-GI hot path.
+"""bench.py — benchmark of the B200-native kajiya ReSTIR-GI hot path (rtdgi + irradiance cache + rtr + taa).
 
     python bench.py --gpus N --steps K --warmup W            # this implementation (CUDA, sm_100a)
-    python bench.py --impl reference --gpus N --steps K ...  # the CPU restatement of the reference's path, host cores
+    python bench.py --impl reference --gpus N --steps K ...  # the CPU restatement of the reference's path, all host threads
 
-A "step" is one frame of the hot path (rtdgi reproject -> validate/trace -> ReSTIR temporal/spatial -> resolve ->
-temporal+spatial filter, 15 kernels) over one synthetic batch of G-buffer inputs.  Workload at N=1: BASELINE.json configs[1],
-"Cornell box, 1080p, ReSTIR GI 1 spatial + 1 temporal pass".  Metric: GI rays/s (closest-hit + any-hit rays actually
-traced, counted on the device) with ms/frame as `ms_per_step`.
+A "step" is one frame of the hot path over one synthetic batch of G-buffer inputs.  The headline workload is the WHOLE path on the
+Sponza-class atrium at 1080p (BASELINE.json configs[2] — rtdgi with two spatial passes + irradiance cache + ray-traced reflections —
+plus the TAA passes): ~40 kernels per frame.  The line also carries `configs`: one entry per BASELINE.json configuration
+(configs[0] Cornell 256^2 reference path tracer, configs[1] Cornell 1080p rtdgi 1 spatial + 1 temporal, configs[2] the headline,
+configs[3] atrium 1440p full path + TAA, configs[4] 2 M-triangle ruins rendered at 2560x1440 and temporally upsampled to 4K), each with
+its own `roofline`, `e2e` and `cpu_baseline`.  Metric: GI rays/s (closest-hit + any-hit rays actually traced, counted on the device)
+with ms/frame as `ms_per_step`.
 
-`value`    : inputs (the frame's G-buffer/depth/normal/velocity) already resident in HBM (device ring, captured untimed).
-`e2e`      : the same frames through the public host-buffer call (kjb_world_render_frame with pinned HOST G-buffer inputs
-             uploaded and the result irradiance image downloaded inside the timed region).
-`roofline` : achieved HBM GB/s of the dominant kernel = algorithmic bytes of that pass (SURVEY.md §8a per-pixel figures x
-             pixels) / its mean launch duration (CUDA events on the launch stream, profiling pass over the same K frames).
-`cpu_baseline`: the oracle (CPU port of the reference shaders) on the host cores over a bounded sample of the same workload.
+`value`    : inputs (the frame's G-buffer/depth/normal/velocity) already resident in HBM (a ring of distinct jittered G-buffers larger
+             than L2, captured untimed).
+`e2e`      : the same frames through the public host-buffer call (kjb_world_render_frame with pinned HOST G-buffer inputs uploaded and
+             the result image downloaded inside the timed region).
+`roofline` : achieved HBM GB/s of the dominant kernel = algorithmic bytes of that pass (SURVEY.md §8a per-pixel figures x pixels) / its
+             mean launch duration (CUDA events on the launch stream, a profiling pass over the same K frames); `traffic` = ncu DRAM
+             bytes per launch of that kernel, read from the table named in `traffic_source` (profiles/, made by tools/ncu_table.py).
+`cpu_baseline`: the oracle (CPU port of the reference shaders, every host thread, cache passes on the parallel schedule) on a bounded
+             sample of the same workload — replayed G-buffers, i.e. exactly the passes the GPU arm times.
+At N > 1 ONE frame is tile-sharded over the ranks (strong scaling); `parity` compares every rank's band with an untiled render of the
+same frames on that rank.
 """
-import argparse, ctypes as C, json, os, subprocess, sys, threading, time
+import argparse, ctypes as C, hashlib, json, os, subprocess, sys, threading, time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+FULL = dict(enable_ircache=True, enable_rtr=True, enable_taa=True)
 WORKLOADS = {
-    # name: (scene fn name, kwargs, width, height, spatial passes, world flags)
-    "cornell_1080p_rtdgi_1s1t": ("cornell_box", {}, 1920, 1080, 1, {}),                       # BASELINE configs[1]: the metric's configuration
+    # name: (scene fn name, kwargs, render width, render height, spatial passes, world flags)
+    "cornell_256_reference_pt": ("cornell_box", {}, 256, 256, 1, {}),                         # BASELINE configs[0]: the reference path tracer (paths/s)
+    "cornell_1080p_rtdgi_1s1t": ("cornell_box", {}, 1920, 1080, 1, {}),                       # BASELINE configs[1]
     "cornell_256_rtdgi": ("cornell_box", {}, 256, 256, 1, {}),
     "atrium_1080p_rtdgi": ("atrium", {}, 1920, 1080, 2, {}),
-    "atrium_1080p_gi_ircache_rtr": ("atrium", {}, 1920, 1080, 2, dict(enable_ircache=True, enable_rtr=True)),                   # configs[2] stand-in (Sponza-class)
-    "atrium_1440p_full_taa": ("atrium", {}, 2560, 1440, 2, dict(enable_ircache=True, enable_rtr=True, enable_taa=True)),       # configs[3] on one GPU
-    # configs[4] on one GPU: 2 M-triangle ruins, rendered at 1080p and temporally upsampled to 4K by the TAA pass, full GI + SSAO guide + lit composite
-    "ruins_4k_upsampled_full": ("ruins", {}, 1920, 1080, 2, dict(enable_ircache=True, enable_rtr=True, enable_taa=True, enable_ssao=True, enable_lighting=True, upscale=(3840, 2160))),
+    "atrium_1080p_gi_ircache_rtr": ("atrium", {}, 1920, 1080, 2, dict(enable_ircache=True, enable_rtr=True)),
+    "atrium_1080p_full": ("atrium", {}, 1920, 1080, 2, dict(FULL)),                           # BASELINE configs[2] (Sponza-class) + TAA: the whole hot path — HEADLINE
+    "atrium_1440p_full_taa": ("atrium", {}, 2560, 1440, 2, dict(FULL)),                       # BASELINE configs[3] (the driver's 2/4/8-GPU runs shard the headline; this is its 1-GPU number)
+    # BASELINE configs[4]: 2 M-triangle ruins, `--temporal-upsampling 1.5` at 4K = rendered at 2560x1440 and upsampled to 3840x2160 by the TAA
+    # pass (crates/lib/kajiya-simple/src/main_loop.rs:222-233), full GI + SSAO guide + lit composite
+    "ruins_4k_upsampled_full": ("ruins", {}, 2560, 1440, 2, dict(FULL, enable_ssao=True, enable_lighting=True, upscale=(3840, 2160))),
 }
+BASELINE_CONFIG = {"cornell_256_reference_pt": 0, "cornell_1080p_rtdgi_1s1t": 1, "atrium_1080p_full": 2, "atrium_1440p_full_taa": 3, "ruins_4k_upsampled_full": 4}
+HEADLINE = "atrium_1080p_full"
+CONFIG_SET = ["cornell_256_reference_pt", "cornell_1080p_rtdgi_1s1t", "atrium_1080p_full", "atrium_1440p_full_taa", "ruins_4k_upsampled_full"]
 
-# compulsory bytes per pixel of each pass at its own grid (F = full-res px, Hh = half-res px)
+# compulsory bytes per pixel of each pass at its own grid (F = render-res px, Hh = half-res px, O = TAA output px)
 PASS_BYTES = {
     "rtdgi reproject": ("F", 24), "extract ssao/2": ("Hh", 2), "extract half-res inputs": ("Hh", 30), "extract half depth": ("Hh", 8), "extract view normal/2": ("Hh", 20),
     "rtdgi validate": ("Hh", 5), "rtdgi trace": ("Hh", 38), "validity integrate": ("Hh", 21), "restir temporal": ("Hh", 160),
@@ -40,9 +55,9 @@ PASS_BYTES = {
     # rtr (44 + 45 + 152 Hh; 36 F + 60 Hh; 52 F + 1 Hh; 20 F)
     "reflection trace": ("Hh", 44), "reflection validate": ("Hh", 45), "rtr restir temporal": ("Hh", 152), "reflection resolve": ("F+Hh", (36, 60)),
     "reflection temporal": ("F+Hh", (52, 1)), "reflection cleanup": ("F", 20),
-    # taa (80 O + 120 I in total; split per pass from the images each kernel binds, O = I without upscaling)
-    "reproject taa": ("F", 32), "taa filter input": ("F", 28), "taa filter history": ("F", 16), "taa input prob": ("F", 40), "taa prob filter": ("F", 4),
-    "taa prob filter2": ("F", 4), "taa": ("F", 76),
+    # taa (80 O + 120 I in total; split per pass from the images each kernel binds)
+    "reproject taa": ("O+F", (20, 12)), "taa filter input": ("F", 28), "taa filter history": ("O+F", (8, 8)), "taa input prob": ("F", 46), "taa prob filter": ("F", 4),
+    "taa prob filter2": ("F", 4), "taa": ("O+F", (52, 18)),
     # irradiance cache (6.3 MB of grid + 1548 B per live entry; the entry count lives on the device, so only the fixed part is
     # charged here) and the other small passes of the frame
     "clear ircache pool": ("const", 0), "scroll cascades": ("const", 6291456), "age ircache entries": ("const", 0), "_prefix scan": ("const", 524288), "ircache compact": ("const", 0), "_ircache dispatch args": ("const", 0),
@@ -52,32 +67,21 @@ PASS_BYTES = {
     "trace shadow mask": ("F", 9), "shadow bitpack": ("F", 1.125), "shadow temporal": ("F", 33.25), "shadow spatial": ("F", 16), "light gbuffer": ("F", 52), "sample lights": ("Hh", 32), "spatial reuse lights": ("F+Hh", (28, 36)),
     # SSAO guide (N3): ssgi.hlsl + spatial + upsample + temporal (ssgi.rs:41-243)
     "ssao": ("Hh", 30), "ssao spatial": ("Hh", 12), "ssao upsample": ("F+Hh", (10, 10)), "ssao temporal": ("F", 14),
+    "tile border all-gather": ("const", 0), "tile gi all-gather": ("const", 0),
 }
-# DRAM bytes per launch of each kernel, from one `ncu --set full` capture of the default workload (profiles/r01v_full_summary.csv:
-# dram__bytes_read.sum + dram__bytes_write.sum; the captured frame is a validation frame).  Far below the algorithmic bytes: the frame's
-# working set stays in the 126 MB L2.
-NCU_TRAFFIC_1080P = {"rtdgi reproject": 22.97e6, "rtdgi validate": 17.73e6, "rtdgi trace": 9.48e6, "validity integrate": 21.28e6, "restir temporal": 24.92e6,
-                     "restir spatial": 18.26e6, "restir resolve": 40.75e6, "rtdgi temporal": 69.74e6, "rtdgi spatial": 35.59e6, "reprojection map": 20.99e6,
-                     "extract half-res inputs": 21.78e6}
-# warp instructions per launch from the same capture (smsp__inst_executed.sum): these kernels are bound by instruction issue, not by DRAM, so
-# the line also reports the dominant kernel against the issue-slot ceiling of the chip (148 SMs x 4 schedulers x 1 warp instruction per clock).
-NCU_WARP_INST_1080P = {"rtdgi reproject": 26.04e6, "rtdgi validate": 44.03e6, "rtdgi trace": 18.36e6, "validity integrate": 17.19e6, "restir temporal": 21.11e6,
-                       "restir spatial": 88.55e6, "restir resolve": 73.66e6, "rtdgi temporal": 87.08e6, "rtdgi spatial": 65.29e6, "reprojection map": 24.14e6,
-                       "extract half-res inputs": 5.75e6}
+NCU_TABLE = os.path.join("profiles", "ncu_kernel_table.json")   # {workload: {pass label: {"dram_bytes": .., "warp_inst": .., "source": "profiles/<csv>"}}}, made by tools/ncu_table.py
 
 
-def issue_slot_roofline(kernel, kernel_ms, clock_info):
-    """the dominant kernel against the chip's instruction-issue ceiling (148 SMs x 4 schedulers x 1 warp instruction per clock)"""
-    if kernel not in NCU_WARP_INST_1080P or not kernel_ms:
-        return None
-    sm_mhz = (clock_info or {}).get("sm_mhz") or (clock_info or {}).get("sm_max_mhz") or 1965
-    peak_ginst = 148 * 4 * float(sm_mhz) * 1e6 / 1e9
-    ach = NCU_WARP_INST_1080P[kernel] / (kernel_ms * 1e-3) / 1e9
-    return {"kernel": kernel, "warp_inst_per_launch": NCU_WARP_INST_1080P[kernel], "achieved_ginst_s": ach, "peak_ginst_s": peak_ginst, "frac": ach / peak_ginst,
-            "source": "profiles/r01v_full_summary.csv (smsp__inst_executed.sum) / live kernel time; peak = 148 SMs x 4 schedulers x SM clock"}
+def load_ncu_table():
+    p = os.path.join(ROOT, NCU_TABLE)
+    try:
+        return json.load(open(p))
+    except Exception:
+        return {}
 
 
-def pass_bytes(label, F, Hh, validation_frame_fraction=1.0 / 3.0):
+def pass_bytes(label, F, Hh, O=None, validation_frame_fraction=1.0 / 3.0):
+    O = F if O is None else O
     kind, b = PASS_BYTES[label]
     if label == "rtdgi validate":
         return Hh * (5 + 61 * validation_frame_fraction)
@@ -87,6 +91,8 @@ def pass_bytes(label, F, Hh, validation_frame_fraction=1.0 / 3.0):
         return F * b
     if kind == "Hh":
         return Hh * b
+    if kind == "O+F":
+        return O * b[0] + F * b[1]
     return F * b[0] + Hh * b[1]
 
 
@@ -109,18 +115,19 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.samples.append([x.strip() for x in line.split(",")] + [time.perf_counter()])
 
-    def stop(self, t_begin=None, t_end=None):
-        """median SM clock / reasons over the samples taken in [t_begin, t_end] (perf_counter), i.e. while the timed loops ran"""
+    def stop(self, windows=None):
+        """median SM clock / reasons over the samples taken inside the [begin, end] perf_counter windows, i.e. while timed loops ran"""
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
         self.proc.terminate()
-        if t_begin is not None:
-            self.samples = [s for s in self.samples if t_begin <= s[-1] <= t_end + 0.1]
-        sm = sorted(int(float(s[0])) for s in self.samples if s and s[0].replace(".", "").isdigit())
+        smp = self.samples
+        if windows:
+            smp = [s for s in smp if any(a <= s[-1] <= b + 0.1 for a, b in windows)]
+        sm = sorted(int(float(s[0])) for s in smp if s and s[0].replace(".", "").isdigit())
         reasons = set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for s in self.samples:
+        for s in smp:
             for i, n in enumerate(names):
                 if len(s) > 3 + i and s[3 + i].lower().startswith("active"):
                     reasons.add(n)
@@ -148,24 +155,27 @@ def build_world(lib, workload, device=0, tile=None):
     return w, view, W, H
 
 
+def config_of(workload):
+    """The workload description both arms print (identical keys and values for `--impl reference`, independent of N)."""
+    fn, kw, W, H, spatial, flags = WORKLOADS[workload]
+    out = flags.get("upscale") or (W, H)
+    return {"workload": workload, "baseline_config": BASELINE_CONFIG.get(workload), "scene": fn, "resolution": [W, H], "output_resolution": list(out),
+            "spatial_reuse_passes": spatial, "features": sorted(k for k, v in flags.items() if v and k != "upscale"),
+            "inputs": "a ring of distinct jittered G-buffers larger than L2 (126 MB), replayed; e2e uploads them from pinned host memory"}
+
+
 def pinned_empty(torch, nbytes):
     return torch.empty(nbytes, dtype=torch.uint8).pin_memory()
 
 
-def run_cuda(args):
-    import numpy as np, torch
-    import kajiya_b200
-    rank = int(os.environ.get("RANK", "0")); world_size = int(os.environ.get("WORLD_SIZE", "1")); local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    dist = None
-    if world_size > 1:
-        import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    torch.cuda.set_device(local_rank)
-    lib = kajiya_b200.lib()   # raises without the CUDA extension: no fallback
-    workload = args.workload
-    # Multi-GPU: ONE frame is tile-sharded across the ranks: rank r renders its band of half-res rows plus the
-    # halo each pass needs, and the frame's single collective is an ncclAllGather of band borders on the context stream.
-    # Total work is fixed as N grows => "strong" scaling.
+def result_image_name(workload):
+    flags = WORKLOADS[workload][5]
+    return "taa.this_frame_out" if flags.get("enable_taa") else ("debug_out" if flags.get("enable_lighting") else "rtdgi.spatial_filtered")
+
+
+# ---------------------------------------------------------------------------------------------------------------- GPU arm
+def measure_frames(lib, torch, dist, workload, K, Wm, rank, world_size, local_rank, nslots, streaming=True):
+    """device-resident, per-pass and end-to-end legs of one frame workload; returns a dict on every rank (reduced over ranks)"""
     w, view, W, H = build_world(lib, workload, device=local_rank, tile=(rank, world_size) if world_size > 1 else None)
     if world_size > 1:
         uid = [None]
@@ -175,30 +185,28 @@ def run_cuda(args):
             uid[0] = buf.raw
         dist.broadcast_object_list(uid, src=0)
         w.comm_init_nccl(uid[0], rank, world_size)
-    F, Hh = W * H, ((W + 1) // 2) * ((H + 1) // 2)
-    K, Wm = args.steps, args.warmup
-    nslots = min(K, 16)   # ring of distinct jittered G-buffers (each 32 B/px): inputs 16 x 66 MB = 1 GB > L2 (126 MB)
+    flags = WORKLOADS[workload][5]
+    OW, OH = flags.get("upscale") or (W, H)
+    F, Hh, O = W * H, ((W + 1) // 2) * ((H + 1) // 2), OW * OH
+    nslots = max(2, min(K, nslots))
 
     # ---- untimed: produce the G-buffer ring on the device (the raster stand-in is an input producer, not the hot path)
     for i in range(nslots):
         w.render_frame(capture_slot=i + 1, **view)
     w.sync()
-    # host copies of the ring for the e2e leg (pinned)
     host_ring = []
     for i in range(nslots):
         bufs = []
         for name in ("gbuffer", "depth", "geometric_normal", "velocity"):
             img = w.image_handle(f"slot{i + 1}.{name}")
-            nbytes = img.width * img.height * lib.dll.kjb_format_texel_bytes(img.format)
-            t = pinned_empty(torch, nbytes)
+            t = pinned_empty(torch, img.width * img.height * lib.dll.kjb_format_texel_bytes(img.format))
             w._check(lib.dll.kjb_image_download(w.ctx, C.byref(img), t.data_ptr()))
             bufs.append(t)
         host_ring.append(bufs)
     w.sync()
-    res_img = w.image_handle("taa.this_frame_out" if WORKLOADS[workload][5].get("enable_taa") else "rtdgi.spatial_filtered")
-    res_bytes = res_img.width * res_img.height * 8
-    host_result = pinned_empty(torch, res_bytes)
-    host_results = [host_result, pinned_empty(torch, res_bytes)]   # streaming mode alternates between two result buffers
+    res_img = w.image_handle(result_image_name(workload))
+    res_bytes = res_img.width * res_img.height * lib.dll.kjb_format_texel_bytes(res_img.format)
+    host_results = [pinned_empty(torch, res_bytes), pinned_empty(torch, res_bytes)]   # streaming mode alternates between two result buffers
 
     def barrier():
         if dist is not None:
@@ -208,21 +216,17 @@ def run_cuda(args):
     def step_device(i):
         w.render_frame(replay_slot=(i % nslots) + 1, **view)
 
-    # e2e: every step hands the frame's G-buffer inputs over as pinned HOST buffers and receives the result in a pinned host buffer.
-    # Streaming mode (kjb_world.h): uploads, passes and downloads run on three queues, two frames in flight.
-    streaming = not args.no_streaming
     def step_e2e(i):
         b = host_ring[i % nslots]
         w.render_frame(host_inputs=(b[0].data_ptr(), b[1].data_ptr(), b[2].data_ptr(), b[3].data_ptr()), host_result=host_results[i & 1].data_ptr(), streaming=streaming, **view)
 
-    # ---- device-resident leg (the clock sampler is already running when the timed loop starts; nvidia-smi needs ~0.2 s to come up)
-    clocks = ClockSampler(local_rank); clocks.start()
+    # ---- device-resident leg
     for i in range(Wm):
         step_device(i)
     w.sync(); w.stats()          # reset ray counters
     launches0 = lib.dll.kjb_launch_count(w.ctx)
     barrier()
-    t_load_begin = time.perf_counter()
+    t_begin = time.perf_counter()
     w.timer_record(1000)
     for i in range(K):
         step_device(Wm + i)
@@ -240,7 +244,7 @@ def run_cuda(args):
     timings = w.pass_timings()
     w.set_profiling(False)
 
-    # ---- e2e leg: host G-buffer in, irradiance out
+    # ---- e2e leg: host G-buffer in, result out
     for i in range(max(4, Wm // 2)):
         step_e2e(i)
     w.wait(); w.stats()
@@ -254,119 +258,305 @@ def run_cuda(args):
     ms_e2e = w.timer_elapsed_ms(1002, 1003)
     wall_e2e = (time.perf_counter() - t0) * 1e3
     barrier()
-    clock_info = clocks.stop(t_load_begin, time.perf_counter())   # samples from the device-timed, per-pass and e2e loops (GPU under load throughout)
+    windows = [(t_begin, time.perf_counter())]
     st2 = w.stats()
     rays_e2e = st2["closest_rays"] + st2["any_hit_rays"]
     ms_e2e = max(ms_e2e, wall_e2e)   # the call blocks on the download: wall clock is the honest end-to-end figure
+    h2d = sum(int(t.numel()) for t in host_ring[0]) + 1216
+    w.close()
+    del host_ring, host_results
 
     # ---- reduce over ranks: max time, summed rays
+    rays_traced = rays
+    per_pass = {k: v[1] / max(v[0], 1) for k, v in timings.items() if k in PASS_BYTES}
+    calls = {k: v[0] for k, v in timings.items() if k in PASS_BYTES}
     if dist is not None:
         t = torch.tensor([ms_total, ms_e2e], device="cuda", dtype=torch.float64); dist.all_reduce(t, op=dist.ReduceOp.MAX)
         r = torch.tensor([rays, rays_e2e, launches], device="cuda", dtype=torch.float64); dist.all_reduce(r, op=dist.ReduceOp.SUM)
-        ms_total, ms_e2e = t.tolist(); rays, rays_e2e, launches = r.tolist()
+        ms_total, ms_e2e = t.tolist(); rays_traced, _, launches = r.tolist()
+        labels = sorted(per_pass)   # every rank runs the same pass list
+        pm = torch.tensor([per_pass[k] for k in labels], device="cuda", dtype=torch.float64); dist.all_reduce(pm, op=dist.ReduceOp.MAX)
+        per_pass = dict(zip(labels, pm.tolist()))   # slowest rank per pass
+    return dict(workload=workload, W=W, H=H, F=F, Hh=Hh, O=O, K=K, ms_total=ms_total, ms_e2e=ms_e2e, rays=rays, rays_e2e=rays_e2e, rays_traced=rays_traced, launches=launches,
+                per_pass=per_pass, calls=calls, h2d=h2d, d2h=res_bytes, nslots=nslots, windows=windows, view=view, streaming=streaming)
+
+
+def frame_rays_untiled(lib, workload, K, Wm, local_rank, nslots):
+    """rays one GPU traces for the same K frames: at N > 1 the metric counts the frame's rays once (the tiles also trace rays for their halos)"""
+    w1, view, _, _ = build_world(lib, workload, device=local_rank, tile=None)
+    n1 = max(2, min(K, nslots, 4))
+    for i in range(n1):
+        w1.render_frame(capture_slot=i + 1, **view)
+    for i in range(Wm):
+        w1.render_frame(replay_slot=(i % n1) + 1, **view)
+    w1.sync(); w1.stats()
+    for i in range(K):
+        w1.render_frame(replay_slot=((Wm + i) % n1) + 1, **view)
+    s1 = w1.stats(); w1.close()
+    return s1["closest_rays"] + s1["any_hit_rays"]
+
+
+def band_compare(a, b, H, rank, world_size, statistical):
+    """compare this rank's band (rows of the result image) of an untiled render `a` and a tiled render `b` (numpy arrays, storage dtype)"""
+    import numpy as np
+    HH = (H + 1) // 2
+    y0, y1 = 2 * (HH * rank // world_size), 2 * (HH * (rank + 1) // world_size)
+    scale = max(1, a.shape[0] // H)
+    ba, bb = a[y0 * scale:y1 * scale], b[y0 * scale:y1 * scale]
+    exact = bool(np.array_equal(ba, bb))
+    if ba.dtype == np.uint16:   # RGBA16F storage
+        fa, fb = ba.view(np.float16).astype(np.float32)[..., :3], bb.view(np.float16).astype(np.float32)[..., :3]
+    else:
+        fa, fb = ba.astype(np.float32)[..., :3], bb.astype(np.float32)[..., :3]
+    mean_a, mean_b = float(fa.mean()), float(fb.mean())
+    rel_mean = abs(mean_b / max(mean_a, 1e-12) - 1.0)
+    rel_rms = float(np.sqrt(((fa - fb) ** 2).mean())) / max(mean_a, 1e-12)
+    ok = exact if not statistical else (rel_mean < 0.05 and rel_rms < 0.25)
+    return ok, exact, rel_mean, rel_rms, hashlib.sha256(bb.tobytes()).hexdigest()[:16]
+
+
+def parity_check(lib, torch, dist, workload, rank, world_size, local_rank, frames=6):
+    """every rank renders `frames` frames tiled (its band, NCCL exchange) AND untiled on its own GPU and compares its band of the result.
+    Without the irradiance cache the band must be bit-identical; with it (racy by design, per-rank replicas) the comparison is
+    statistical: band mean within 5 %, RMS difference below 25 % of the mean."""
+    wt, view, W, H = build_world(lib, workload, device=local_rank, tile=(rank, world_size))
+    uid = [None]
+    if rank == 0:
+        buf = C.create_string_buffer(128); assert lib.dll.kjb_comm_nccl_unique_id(buf) == 0; uid[0] = buf.raw
+    dist.broadcast_object_list(uid, src=0)
+    wt.comm_init_nccl(uid[0], rank, world_size)
+    wu, _, _, _ = build_world(lib, workload, device=local_rank, tile=None)
+    for _ in range(frames):
+        wt.render_frame(**view); wu.render_frame(**view)
+    name = result_image_name(workload)
+    statistical = bool(WORKLOADS[workload][5].get("enable_ircache"))
+    ok, exact, rel_mean, rel_rms, sha = band_compare(wu.image(name), wt.image(name), H, rank, world_size, statistical)
+    wt.close(); wu.close()
+    v = torch.tensor([1.0 if ok else 0.0, 1.0 if exact else 0.0, rel_mean, rel_rms], device="cuda", dtype=torch.float64)
+    lo = v.clone(); dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+    hi = v.clone(); dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+    return {"ok": bool(lo[0].item() > 0.5), "mode": "statistical (irradiance cache: per-rank replicas, racy by design)" if statistical else "bit-exact (every rank's band of the tiled frame == the untiled frame)",
+            "bands_bit_identical": bool(lo[1].item() > 0.5), "worst_band_mean_rel_diff": hi[2].item(), "worst_band_rel_rms": hi[3].item(), "frames": frames,
+            "band_sha256_rank0": sha, "image": name}
+
+
+def summarize(m, world_size, peak, ncu_table):
+    """bench-line fields of one measured frame workload"""
+    F, Hh, O, K = m["F"], m["Hh"], m["O"], m["K"]
+    per_pass, calls = m["per_pass"], m["calls"]
+    share = {k: per_pass[k] * calls.get(k, K) for k in per_pass}
+    kernels = [k for k in share if not k.startswith("tile ")]   # the exchange entries are waits on the communication queue, not one of our kernels
+    dom = max(kernels, key=share.get)
+    dom_bytes = pass_bytes(dom, F, Hh, O)
+    # at N > 1 the frame's algorithmic bytes are counted ONCE (halo recompute is not credited) against N x the per-GPU peak
+    achieved = dom_bytes / (per_pass[dom] * 1e-3) / 1e9
+    frame_bytes = sum(pass_bytes(k, F, Hh, O) * (calls.get(k, K) / K) for k in per_pass)
+    frame_ms = m["ms_total"] / K
+    tab = (ncu_table.get(m["workload"]) or {}).get(dom) if world_size == 1 else None
+    roof = {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak * world_size, "unit": "GB/s", "frac": achieved / (peak * world_size),
+            "traffic": tab.get("dram_bytes") if tab else None, "traffic_source": (tab.get("source") if tab else None),
+            "kernel_ms": per_pass[dom], "kernel_share_of_step": share[dom] / sum(share.values()), "algorithmic_bytes_per_launch": dom_bytes,
+            "frame": {"algorithmic_bytes": frame_bytes, "achieved_gbs": frame_bytes / (frame_ms * 1e-3) / 1e9, "frac": frame_bytes / (frame_ms * 1e-3) / 1e9 / (peak * world_size)},
+            "per_pass_ms": {k: round(v, 5) for k, v in sorted(per_pass.items(), key=lambda kv: -share[kv[0]])}}
+    if tab and tab.get("warp_inst"):
+        # these kernels are bound by instruction issue, not DRAM: also report the dominant kernel against 148 SMs x 4 schedulers x SM clock
+        sm_mhz = 1965.0
+        ach = tab["warp_inst"] / (per_pass[dom] * 1e-3) / 1e9
+        roof["issue_slots"] = {"warp_inst_per_launch": tab["warp_inst"], "achieved_ginst_s": ach, "peak_ginst_s": 148 * 4 * sm_mhz * 1e-3, "frac": ach / (148 * 4 * sm_mhz * 1e-3), "source": tab.get("source")}
+    return {"ms_per_step": frame_ms, "value": m["rays"] / (m["ms_total"] * 1e-3), "unit": "rays/s", "rays_per_frame": m["rays"] / K,
+            "e2e": {"value": m["rays_e2e"] / (m["ms_e2e"] * 1e-3), "unit": "rays/s", "ms_per_step": m["ms_e2e"] / K, "h2d_bytes_per_step": int(m["h2d"]), "d2h_bytes_per_step": int(m["d2h"]),
+                    "mode": "streaming: upload/compute/download queues, 2 frames in flight" if m["streaming"] else "blocking call per frame"},
+            "gpu_launches": int(m["launches"]), "roofline": roof}
+
+
+def measure_reference_pt(lib, torch, workload, K, Wm, local_rank):
+    """BASELINE configs[0]: the reference path tracer (rt/reference_path_trace.rgen.hlsl), 1 path per pixel per frame, on the GPU"""
+    w, view, W, H = build_world(lib, workload, device=local_rank)
+    for _ in range(Wm):
+        w.render_reference(**view)
+    w.sync(); w.stats()
+    l0 = lib.dll.kjb_launch_count(w.ctx)
+    torch.cuda.synchronize()
+    w.timer_record(1000)
+    for _ in range(K):
+        w.render_reference(**view)
+    w.timer_record(1001)
+    ms = w.timer_elapsed_ms(1000, 1001)
+    st = w.stats()
+    launches = lib.dll.kjb_launch_count(w.ctx) - l0
+    res = pinned_empty(torch, W * H * 16)   # e2e: each frame downloads the accumulated image
+    t0 = time.perf_counter()
+    for _ in range(K):
+        w.render_reference(host_result=res.data_ptr(), **view)
+    w.sync()
+    ms_e2e = (time.perf_counter() - t0) * 1e3
+    st2 = w.stats(); w.close()
+    rays = st["closest_rays"] + st["any_hit_rays"]
+    return {"ms_per_step": ms / K, "value": rays / (ms * 1e-3), "unit": "rays/s", "paths_per_sec": W * H * K / (ms * 1e-3), "rays_per_frame": rays / K,
+            "e2e": {"value": (st2["closest_rays"] + st2["any_hit_rays"]) / (ms_e2e * 1e-3), "unit": "rays/s", "ms_per_step": ms_e2e / K, "h2d_bytes_per_step": 1216, "d2h_bytes_per_step": W * H * 16, "mode": "blocking call per frame"},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "kernel": "reference pt", "achieved": None, "peak": None, "unit": "GB/s", "frac": None, "traffic": None,
+                         "note": "BVH traversal of a 32-triangle scene: L1-resident, no HBM roofline applies (SURVEY.md §8d: ray traversal is reported as rays/s)"}}
+
+
+def run_cuda(args):
+    import torch
+    import kajiya_b200
+    rank = int(os.environ.get("RANK", "0")); world_size = int(os.environ.get("WORLD_SIZE", "1")); local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world_size > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    torch.cuda.set_device(local_rank)
+    lib = kajiya_b200.lib()   # raises without the CUDA extension: no fallback
+    K, Wm = args.steps, args.warmup
+    peak, peak_src = load_peaks()
+    ncu_table = load_ncu_table()
+    headline = args.workload
+    if args.configs == "all":
+        names = [headline] + [c for c in CONFIG_SET if c != headline]
+    elif args.configs == "auto":   # N = 1: every BASELINE configuration; N > 1: the headline and configs[1]
+        names = [headline] + ([c for c in CONFIG_SET if c != headline] if world_size == 1 else [c for c in ("cornell_1080p_rtdgi_1s1t",) if c != headline])
+    else:
+        names = [headline]
+    clocks = ClockSampler(local_rank); clocks.start()
+    windows, entries, head = [], [], None
+    for name in names:
+        Kc = K if name == headline else max(4, min(K, 16))   # secondary configurations: a shorter timed region keeps the default run within minutes
+        Wc = Wm if name == headline else max(3, min(Wm, 4))
+        if name == "cornell_256_reference_pt":
+            if rank == 0:
+                e = measure_reference_pt(lib, torch, name, Kc, Wc, local_rank)
+                e.update(config=config_of(name), steps=Kc, warmup=Wc)
+                e["metric_note"] = "paths/s = pixels x frames / time (1 path per pixel per frame, up to 16 bounces)"
+                if not args.no_cpu_baseline:
+                    e["cpu_baseline"] = cpu_baseline_pt(name, seconds=min(args.cpu_seconds, 4.0))
+                entries.append(e)
+            if dist is not None:
+                dist.barrier()
+            continue
+        m = measure_frames(lib, torch, dist, name, Kc, Wc, rank, world_size, local_rank, nslots=16 if name == headline else 6, streaming=not args.no_streaming)
+        windows += m["windows"]
+        par = None
+        if world_size > 1:
+            m["rays_traced_all_ranks"] = m["rays_traced"]
+            if rank == 0:
+                m["rays"] = m["rays_e2e"] = frame_rays_untiled(lib, name, Kc, Wc, local_rank, 4)
+            par = parity_check(lib, torch, dist, name, rank, world_size, local_rank)
+        if rank == 0:
+            e = summarize(m, world_size, peak, ncu_table)
+            e.update(config=config_of(name), steps=Kc, warmup=Wc)
+            e["roofline"]["peak_source"] = peak_src + (f" x {world_size} GPUs; the frame's algorithmic bytes counted once, slowest rank's kernel time" if world_size > 1 else "")
+            if world_size > 1:
+                e["multi_gpu"] = (f"one frame tile-sharded into {world_size} bands of half-res rows, NCCL all-gather of band borders per frame; `value` counts the frame's rays once "
+                                  f"(the ranks actually traced {m['rays_traced_all_ranks'] / Kc:.0f} per frame including halo recompute)")
+                e["parity"] = par
+            if world_size == 1 and not args.no_cpu_baseline:
+                e["cpu_baseline"] = cpu_baseline(name, seconds=args.cpu_seconds if name == headline else min(args.cpu_seconds, 4.0), reduced=name != headline)
+            entries.append(e)
+            if name == headline:
+                head = e
+    clock_info = clocks.stop(windows)
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
         return
-
-    rays_traced, rays_e2e_traced = rays, rays_e2e
-    if world_size > 1:
-        # The tiled ranks also trace rays for their halos.  The metric counts the rays of THE FRAME, i.e. what one GPU traces for it:
-        # measure that on rank 0 with an untiled world over the same K-frame pattern (untimed), and use it for `value` and `e2e`.
-        w1, _, _, _ = build_world(lib, workload, device=local_rank, tile=None)
-        n1 = min(K, 4)
-        for i in range(n1):
-            w1.render_frame(capture_slot=i + 1, **view)       # G-buffers by the raster stand-in (its rays are not GI rays)
-        for i in range(Wm):
-            w1.render_frame(replay_slot=(i % n1) + 1, **view)
-        w1.sync(); w1.stats()
-        for i in range(K):
-            w1.render_frame(replay_slot=((Wm + i) % n1) + 1, **view)
-        s1 = w1.stats(); w1.close()
-        rays = rays_e2e = s1["closest_rays"] + s1["any_hit_rays"]
-    peak, peak_src = load_peaks()
-    # dominant kernel = the pass with the largest share of device time
-    if "tile border all-gather" in timings:
-        PASS_BYTES.setdefault("tile border all-gather", ("F", 0))
-    per_pass = {k: v[1] / max(v[0], 1) for k, v in timings.items() if k in PASS_BYTES}
-    calls = {k: v[0] for k, v in timings.items()}
-    share = {k: timings[k][1] for k in per_pass}
-    # the dominant KERNEL: the exchange entry is a wait on the communication queue (pack + ncclAllGather + unpack, overlapped with compute), not one of our kernels
-    dom = max((k for k in share if k != "tile border all-gather"), key=share.get)
-    dom_bytes = pass_bytes(dom, F, Hh)
-    achieved = dom_bytes / (per_pass[dom] * 1e-3) / 1e9
-    frame_bytes = sum(pass_bytes(k, F, Hh) * (calls[k] / K) for k in per_pass)
-    try:
-        issue = issue_slot_roofline(dom, per_pass[dom], clock_info) if workload == "cornell_1080p_rtdgi_1s1t" and world_size == 1 else None
-    except Exception:   # an explanatory extra must never cost the bench line
-        issue = None
-    frame_ms = ms_total / K
-
-    out = {
-        "metric": "gi_rays_per_sec", "value": rays / (ms_total * 1e-3), "unit": "rays/s", "n_gpus": world_size, "steps": K, "warmup": Wm,
-        "ms_per_step": frame_ms, "higher_is_better": True, "scaling": "strong" if world_size > 1 else "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload, "scene": WORKLOADS[workload][0], "resolution": [W, H], "spatial_reuse_passes": WORKLOADS[workload][4], "features": WORKLOADS[workload][5],
-                   "l2_policy": f"inputs larger than L2: ring of {nslots} distinct jittered G-buffers ({nslots * 32 * F / 1e6:.0f} MB) + ~{frame_bytes / 1e6:.0f} MB/frame of temporal state",
-                   "rays_per_frame": rays / K,
-                   "multi_gpu": (f"one frame tile-sharded into {world_size} bands of half-res rows, 1 ncclAllGather of band borders per frame; `value` counts the frame's rays once "
-                                 f"(the ranks actually traced {rays_traced / K:.0f} per frame including halo recompute)") if world_size > 1 else "n/a"},
-        "e2e": {"value": rays_e2e / (ms_e2e * 1e-3), "unit": "rays/s", "ms_per_step": ms_e2e / K,
-                "h2d_bytes_per_step": int(32 * F + 1216), "d2h_bytes_per_step": int(res_bytes),
-                "mode": "streaming: upload/compute/download queues, 2 frames in flight" if streaming else "blocking call per frame"},
-        "gpu_launches": int(launches),
-        "clocks": clock_info,
-        "roofline": {"bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": NCU_TRAFFIC_1080P.get(dom) if workload == "cornell_1080p_rtdgi_1s1t" and world_size == 1 else None, "traffic_source": "profiles/r01v_full_summary.csv",
-                     "peak_source": peak_src, "kernel_ms": per_pass[dom], "kernel_share_of_step": share[dom] / sum(share.values()),
-                     "algorithmic_bytes_per_launch": dom_bytes,
-                     "frame": {"algorithmic_bytes": frame_bytes, "achieved_gbs": frame_bytes / (frame_ms * 1e-3) / 1e9, "frac": frame_bytes / (frame_ms * 1e-3) / 1e9 / peak},
-                     "per_pass_ms": {k: round(v, 5) for k, v in sorted(per_pass.items(), key=lambda kv: -share[kv[0]])},
-                     "issue_slots": issue},
-    }
-    if world_size == 1 and not args.no_cpu_baseline:
-        out["cpu_baseline"] = cpu_baseline(workload, seconds=args.cpu_seconds)
+    out = {"metric": "gi_rays_per_sec", "value": head["value"], "unit": "rays/s", "n_gpus": world_size, "steps": K, "warmup": Wm, "ms_per_step": head["ms_per_step"],
+           "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": head["config"],
+           "e2e": head["e2e"], "gpu_launches": head["gpu_launches"], "clocks": clock_info, "roofline": head["roofline"]}
+    for k in ("cpu_baseline", "parity", "multi_gpu"):
+        if k in head:
+            out[k] = head[k]
+    out["configs"] = entries
     print(json.dumps(out))
     if dist is not None:
         dist.destroy_process_group()
 
 
-def cpu_baseline(workload, seconds=15.0, steps=None, warmup=1):
-    """The oracle (CPU port of the reference shaders, all host threads) on a bounded sample of the same workload:
-    the same scene, resolution and pass list, as many frames as fit in ~`seconds`."""
+# ---------------------------------------------------------------------------------------------------------------- CPU arms
+def oracle_lib():
     from kajiya_b200._abi import KjbLib
-    so = os.path.join(ROOT, "oracle", "_build", "libkj_oracle.so")
-    lib = KjbLib(so)
-    w, view, W, H = build_world(lib, workload)
-    for _ in range(warmup):
-        w.render_frame(**view)
+    return KjbLib(os.path.join(ROOT, "oracle", "_build", "libkj_oracle.so"))
+
+
+def cpu_frames(workload, steps=None, seconds=None, warmup=1, reduced=False):
+    """The oracle (CPU port of the reference shaders) on the host cores: the same scene and pass list over replayed G-buffers (the raster
+    stand-in is outside the timed region on both arms), cache passes on the parallel schedule so every host thread is used.
+    `reduced`: secondary configurations run at 1/4 of the width and height (scene-complexity-matched sample)."""
+    from kajiya_b200 import scenes
+    from kajiya_b200.world import World
+    lib = oracle_lib()
+    fn, kw, W, H, spatial, flags = WORKLOADS[workload]
+    fl = dict(flags)
+    if reduced:
+        W, H = max(64, W // 4) & ~1, max(64, H // 4) & ~1
+        if fl.get("upscale"):
+            fl["upscale"] = ((fl["upscale"][0] // 4) & ~1, (fl["upscale"][1] // 4) & ~1)
+    scene, view = getattr(scenes, fn)(**kw)
+    w = World(lib, W, H, spatial_reuse_pass_count=spatial, **fl)
+    scenes.populate(w, scene)
+    w.set_debug_serial(False)   # oracle: cache-touching passes on all threads (racy, like the reference's GPU dispatch)
+    nslots = 2
+    for i in range(nslots):
+        w.render_frame(capture_slot=i + 1, **view)
+    for i in range(warmup):
+        w.render_frame(replay_slot=(i % nslots) + 1, **view)
     w.stats()
-    t0 = time.perf_counter(); n = 0
+    per_frame, n, t0 = [], 0, time.perf_counter()
     while True:
-        w.render_frame(**view); n += 1
+        t1 = time.perf_counter()
+        w.render_frame(replay_slot=((warmup + n) % nslots) + 1, **view); n += 1
+        per_frame.append(time.perf_counter() - t1)
         el = time.perf_counter() - t0
-        if (steps is not None and n >= steps) or (steps is None and (el > seconds or n >= 64)):
+        if (steps is not None and n >= steps) or (steps is None and ((el > seconds and n >= 3) or n >= 64)):
             break
-    st = w.stats()
+    st = w.stats(); w.close()
     rays = st["closest_rays"] + st["any_hit_rays"]
+    pf = sorted(per_frame)
     return {"value": rays / el, "unit": "rays/s", "cores": os.cpu_count(), "kind": "port", "ms_per_step": el / n * 1e3,
-            "sample": f"{n} full frames of {workload} ({W}x{H}) after {warmup} warm-up, all {os.cpu_count()} host threads; includes the CPU raster stand-in"}
+            "spread_ms": {"min": pf[0] * 1e3, "median": pf[len(pf) // 2] * 1e3, "max": pf[-1] * 1e3, "frames": n},
+            "sample": f"{n} replayed frames of {workload} at {W}x{H}" + (" (1/4 of the configuration's width and height)" if reduced else "") +
+                      f" after {warmup} warm-up, {os.cpu_count()} host threads, G-buffers captured beforehand (the same passes the GPU arm times)"}
+
+
+def cpu_baseline(workload, seconds=12.0, reduced=False):
+    return cpu_frames(workload, seconds=seconds, reduced=reduced)
+
+
+def cpu_baseline_pt(workload, seconds=4.0):
+    from kajiya_b200 import scenes
+    from kajiya_b200.world import World
+    lib = oracle_lib()
+    fn, kw, W, H, spatial, flags = WORKLOADS[workload]
+    scene, view = getattr(scenes, fn)(**kw)
+    w = World(lib, W, H, spatial_reuse_pass_count=spatial, **flags)
+    scenes.populate(w, scene)
+    w.render_reference(**view); w.stats()
+    n, t0 = 0, time.perf_counter()
+    while True:
+        w.render_reference(**view); n += 1
+        el = time.perf_counter() - t0
+        if el > seconds or n >= 256:
+            break
+    st = w.stats(); w.close()
+    rays = st["closest_rays"] + st["any_hit_rays"]
+    return {"value": rays / el, "unit": "rays/s", "paths_per_sec": W * H * n / el, "cores": os.cpu_count(), "kind": "port", "ms_per_step": el / n * 1e3,
+            "sample": f"{n} frames of the reference path tracer at {W}x{H} (1 path per pixel per frame), {os.cpu_count()} host threads"}
 
 
 def run_reference(args):
     """--impl reference: the reference's own implementation of the path cannot run here (Rust + Vulkan RT, SURVEY.md §8c);
-    its CPU restatement (oracle port) is timed on the host cores on the same config/metric/unit."""
+    its CPU restatement (oracle port) is timed on the host cores on the same config/metric/unit: W warm-up and EXACTLY K timed steps,
+    each step one replayed frame of the headline workload."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     world_size = int(os.environ.get("WORLD_SIZE", "1"))
     K, Wm = args.steps, args.warmup
-    steps = max(1, min(K, 8))   # bounded sample: a 1080p oracle frame takes ~2 s on 8 threads
-    cb = cpu_baseline(args.workload, steps=steps, warmup=min(Wm, 1))
-    W, H = WORKLOADS[args.workload][2:4]
+    cb = cpu_frames(args.workload, steps=K, warmup=Wm)
     out = {"impl": "reference", "metric": "gi_rays_per_sec", "value": cb["value"], "unit": "rays/s", "n_gpus": world_size, "steps": K, "warmup": Wm,
-           "ms_per_step": cb["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-           "config": {"workload": args.workload, "scene": WORKLOADS[args.workload][0], "resolution": [W, H], "spatial_reuse_passes": WORKLOADS[args.workload][4],
-                      "timed_steps": steps},
+           "ms_per_step": cb["ms_per_step"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+           "config": config_of(args.workload),
            "cpu_baseline": cb, "e2e": {"value": cb["value"], "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     print(json.dumps(out))
 
@@ -374,13 +564,14 @@ def run_reference(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=64)
-    ap.add_argument("--warmup", type=int, default=8)
+    ap.add_argument("--steps", type=int, default=32)
+    ap.add_argument("--warmup", type=int, default=6)
     ap.add_argument("--impl", default="kajiya_b200", choices=["kajiya_b200", "reference"])
-    ap.add_argument("--workload", default="cornell_1080p_rtdgi_1s1t", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default=HEADLINE, choices=sorted(WORKLOADS), help="the headline workload of the line")
+    ap.add_argument("--configs", default="auto", choices=["auto", "all", "headline"], help="which BASELINE configurations ride along in `configs`")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-streaming", action="store_true", help="e2e leg with the blocking call (upload, passes, download serialised)")
-    ap.add_argument("--cpu-seconds", type=float, default=15.0)
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":

@@ -313,8 +313,10 @@ int kjb_pass_ssao_temporal(kjb_context *ctx, const kjb_ssao_temporal_args *a);
 /* ------------------------------------------------------------------ ircache binding block (ircache/bindings.hlsl, ircache.rs:59-78).
  * NULL `meta_buf.data` = irradiance cache not bound: lookups return 0 and allocate nothing. */
 typedef struct kjb_ircache_bindings {
-    kjb_buffer meta_buf, grid_meta_buf, entry_cell_buf, spatial_buf, irradiance_buf, aux_buf,
-               life_buf, pool_buf, reposition_proposal_buf, reposition_proposal_count_buf;
+    /* IrcacheRenderState::bind_mut call order = DEFINE_IRCACHE_BINDINGS(b0..b8) (ircache.rs:67-75, ircache/bindings.hlsl:6-15).  The
+     * per-entry reservoirs (`aux`) are NOT part of the block: only the cache's own passes bind them (IRCACHE_LOOKUP_PRECISE). */
+    kjb_buffer meta_buf, pool_buf, reposition_proposal_buf, reposition_proposal_count_buf, grid_meta_buf, entry_cell_buf,
+               spatial_buf, irradiance_buf, life_buf;
 } kjb_ircache_bindings;
 
 /* ------------------------------------------------------------------ ircache (renderers/ircache.rs, shaders under assets/shaders/ircache/)
@@ -350,8 +352,7 @@ int kjb_pass_ircache_trace_access(kjb_context *ctx, const kjb_ircache_trace_acce
 typedef struct kjb_ircache_trace_args {               /* "ircache validate" / "ircache trace", trace_irradiance.rgen.hlsl:21-33 */
     kjb_buffer spatial_buf; kjb_image sky_cube_tex;
     kjb_buffer grid_meta_buf, life_buf, reposition_proposal_buf, reposition_proposal_count_buf, meta_buf, aux_buf, pool_buf,
-               entry_indirection_buf, entry_cell_buf;
-    kjb_buffer irradiance_buf;                        /* lookup.hlsl reads it through DEFINE_IRCACHE_BINDINGS-equivalent globals */
+               entry_indirection_buf, entry_cell_buf;   /* bindings 0-11 minus the (disabled) wrc block; IRCACHE_LOOKUP_PRECISE reads `aux`, never the SH */
 } kjb_ircache_trace_args;
 int kjb_pass_ircache_validate(kjb_context *ctx, const kjb_ircache_trace_args *a);
 int kjb_pass_ircache_trace(kjb_context *ctx, const kjb_ircache_trace_args *a);

@@ -48,7 +48,8 @@ CameraMatrices camera_matrices(const kjb_world_frame& f, float aspect) {   // ca
     const float qc[4] = {-q[0], -q[1], -q[2], q[3]};
     c.view_to_world = m4_mul(m4_translation(f.camera_position[0], f.camera_position[1], f.camera_position[2]), m4_from_quat(q));
     c.world_to_view = m4_mul(m4_from_quat(qc), m4_translation(-f.camera_position[0], -f.camera_position[1], -f.camera_position[2]));
-    const float fov = (f.vertical_fov_deg > 0 ? f.vertical_fov_deg : 52.0f) * 3.14159265358979323846f / 180.0f;
+    const float RADS_PER_DEG = 3.14159265358979323846f / 180.0f;   // f32::to_radians: self * (PI / 180), the constant folded in f32 (camera.rs:89)
+    const float fov = (f.vertical_fov_deg > 0 ? f.vertical_fov_deg : 52.0f) * RADS_PER_DEG;
     const float znear = f.near_plane > 0 ? f.near_plane : 0.01f;
     const float h = std::cos(0.5f * fov) / std::sin(0.5f * fov);
     const float w = h / aspect;
@@ -635,7 +636,7 @@ struct IrcacheState {
         kjb_ircache_bindings b{};
         if (!bound) return b;
         b.meta_buf = meta_buf; b.grid_meta_buf = grid_meta_buf; b.entry_cell_buf = entry_cell_buf; b.spatial_buf = spatial_buf; b.irradiance_buf = irradiance_buf;
-        b.aux_buf = aux_buf; b.life_buf = life_buf; b.pool_buf = pool_buf; b.reposition_proposal_buf = reposition_proposal_buf;
+        b.life_buf = life_buf; b.pool_buf = pool_buf; b.reposition_proposal_buf = reposition_proposal_buf;
         b.reposition_proposal_count_buf = reposition_proposal_count_buf;
         return b;
     }
@@ -697,7 +698,7 @@ static void ircache_trace_irradiance(kjb_world* w, IrcacheState& st, kjb_image& 
     kjb_ircache_trace_args t{};
     t.spatial_buf = st.spatial_buf; t.sky_cube_tex = sky_cube; t.grid_meta_buf = st.grid_meta_buf; t.life_buf = st.life_buf; t.reposition_proposal_buf = st.reposition_proposal_buf;
     t.reposition_proposal_count_buf = st.reposition_proposal_count_buf; t.meta_buf = st.meta_buf; t.aux_buf = st.aux_buf; t.pool_buf = st.pool_buf;
-    t.entry_indirection_buf = st.entry_indirection_buf; t.entry_cell_buf = st.entry_cell_buf; t.irradiance_buf = st.irradiance_buf;
+    t.entry_indirection_buf = st.entry_indirection_buf; t.entry_cell_buf = st.entry_cell_buf;
     RUN("ircache validate", kjb_pass_ircache_validate(ctx, &t));
     RUN("ircache trace", kjb_pass_ircache_trace(ctx, &t));
 }

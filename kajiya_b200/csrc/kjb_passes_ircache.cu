@@ -431,11 +431,11 @@ static int check_trace_args(kjb_context* c, const char* P, const kjb_ircache_tra
     BUF(a->spatial_buf, float4, MAX_ENTRIES, "spatial_buf"); BUF(a->grid_meta_buf, uint2, KJB_IRCACHE_GRID_CELLS, "grid_meta_buf"); BUF(a->life_buf, uint32_t, MAX_ENTRIES, "life_buf");
     BUF(a->reposition_proposal_buf, float4, MAX_ENTRIES, "reposition_proposal_buf"); BUF(a->reposition_proposal_count_buf, uint32_t, MAX_ENTRIES, "reposition_proposal_count_buf");
     BUF(a->meta_buf, uint32_t, 8, "meta_buf"); BUF(a->aux_buf, float4, 64 * MAX_ENTRIES, "aux_buf"); BUF(a->pool_buf, uint32_t, MAX_ENTRIES, "pool_buf");
-    BUF(a->entry_indirection_buf, uint32_t, MAX_ENTRIES + 1, "entry_indirection_buf"); BUF(a->entry_cell_buf, uint32_t, MAX_ENTRIES, "entry_cell_buf"); BUF(a->irradiance_buf, float4, 3 * MAX_ENTRIES, "irradiance_buf");
+    BUF(a->entry_indirection_buf, uint32_t, MAX_ENTRIES + 1, "entry_indirection_buf"); BUF(a->entry_cell_buf, uint32_t, MAX_ENTRIES, "entry_cell_buf");
     if (!check_img(c, a->sky_cube_tex, KJB_FMT_RGBA16_FLOAT, P, "sky_cube_tex")) return 1;
     if (!c->tlas_valid) return c->fail(std::string(P) + ": no acceleration structure (call kjb_rebuild_tlas)");
     b.meta = U32P(a->meta_buf); b.pool = U32P(a->pool_buf); b.reposition_count = U32P(a->reposition_proposal_count_buf); b.grid_meta = U32P(a->grid_meta_buf); b.entry_cell = U32P(a->entry_cell_buf);
-    b.life = U32P(a->life_buf); b.reposition_proposal = F4P(a->reposition_proposal_buf); b.spatial = F4P(a->spatial_buf); b.irradiance = F4P(a->irradiance_buf); b.aux = F4P(a->aux_buf);
+    b.life = U32P(a->life_buf); b.reposition_proposal = F4P(a->reposition_proposal_buf); b.spatial = F4P(a->spatial_buf); b.irradiance = nullptr; b.aux = F4P(a->aux_buf);   // precise lookups read the per-entry reservoirs, not the SH
     return 0;
 }
 int kjb_pass_ircache_validate(kjb_context* c, const kjb_ircache_trace_args* a) {

@@ -10,6 +10,10 @@ struct kjb_context {
     kjo::Globals g;
     std::string last_error;
     int num_threads = 0;
+    // Cache-touching passes: serial in launch order by default (the deterministic schedule every parity test compares against).
+    // kjb_set_debug_serial(ctx, 0) lets them run on all host threads — racy by design like the reference's GPU dispatch (the lookups use
+    // the same atomics), used ONLY by bench.py's CPU-baseline / `--impl reference` legs so that the CPU arm really has every core.
+    bool cache_passes_parallel = false;
     kjb_allgather_fn ag_fn = nullptr; void* ag_user = nullptr; uint32_t rank = 0, nranks = 1;
     uint32_t scissor_y0 = 0, scissor_y1 = 0;   // kjb_set_scissor: rows [y0, y1) of the pass's output grid (0,0 = all)
 };
@@ -46,10 +50,16 @@ inline void pass_rows(const kjb_context* ctx, int H, const std::function<void(in
 // Passes that touch the irradiance cache run on ONE thread in the order a serialised GPU launch would execute them: 16x8 pixel
 // blocks, row-major over blocks, row-major inside a block (the product's launch shape for the two rtdgi ray passes).
 inline void pass_pixels(const kjb_context* ctx, int W, int H, bool serial_tiles, const std::function<void(int, int)>& px_fn) {
-    if (!serial_tiles) { pass_rows(ctx, H, [&](int y) { for (int x = 0; x < W; ++x) px_fn(x, y); }, ctx->num_threads); return; }
+    if (!serial_tiles || ctx->cache_passes_parallel) { pass_rows(ctx, H, [&](int y) { for (int x = 0; x < W; ++x) px_fn(x, y); }, ctx->num_threads); return; }
     int y0, y1; scissor_rows(ctx, H, y0, y1);
     for (int by = y0; by < y1; by += 8) for (int bx = 0; bx < W; bx += 16)
         for (int y = by; y < by + 8 && y < y1; ++y) for (int x = bx; x < bx + 16 && x < W; ++x) px_fn(x, y);
+}
+
+// 1-D cache passes (one item per entry sample): serial index order, or chunks of 64 items over the host threads in the parallel schedule
+inline void pass_items(const kjb_context* ctx, uint32_t n, const std::function<void(uint32_t)>& fn) {
+    if (!ctx->cache_passes_parallel) { for (uint32_t i = 0; i < n; ++i) fn(i); return; }
+    parallel_rows(int((n + 63) / 64), [&](int c) { const uint32_t e = uint32_t(c) * 64 + 64 < n ? uint32_t(c) * 64 + 64 : n; for (uint32_t i = uint32_t(c) * 64; i < e; ++i) fn(i); }, ctx->num_threads);
 }
 
 inline float4 f4(const float* p) { return float4(p[0], p[1], p[2], p[3]); }

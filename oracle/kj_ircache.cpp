@@ -71,7 +71,7 @@ IrcacheTraceResult ircache_trace(const kjb_context& ctx, const IrcacheBufs& b, c
 IrcacheBufs bufs_of(const kjb_ircache_trace_args* a) {
     IrcacheBufs b{}; b.meta = (uint32_t*)a->meta_buf.data; b.pool = (uint32_t*)a->pool_buf.data; b.reposition_proposal = (float4*)a->reposition_proposal_buf.data;
     b.reposition_count = (uint32_t*)a->reposition_proposal_count_buf.data; b.grid_meta = (uint32_t*)a->grid_meta_buf.data; b.entry_cell = (uint32_t*)a->entry_cell_buf.data;
-    b.spatial = (const float4*)a->spatial_buf.data; b.irradiance = (const float4*)a->irradiance_buf.data; b.life = (uint32_t*)a->life_buf.data; b.aux = (float4*)a->aux_buf.data;
+    b.spatial = (const float4*)a->spatial_buf.data; b.irradiance = nullptr; b.life = (uint32_t*)a->life_buf.data; b.aux = (float4*)a->aux_buf.data;
     return b;
 }
 }  // namespace
@@ -197,10 +197,10 @@ int kjb_pass_ircache_trace_access(kjb_context* ctx, const kjb_ircache_trace_acce
     const uint32_t *meta = (const uint32_t*)a->meta_buf.data, *ind = (const uint32_t*)a->entry_indirection_buf.data, *life = (const uint32_t*)a->life_buf.data;
     const float4* spatial = (const float4*)a->spatial_buf.data; float4* aux = (float4*)a->aux_buf.data;
     const uint alloc_count = meta[IRCACHE_META_TRACING_ALLOC_COUNT];
-    for (uint di = 0; di < alloc_count * IRCACHE_OCTA_DIMS2; ++di) {
-        if (slot_is_stale_duplicate(ind, alloc_count, di / IRCACHE_OCTA_DIMS2)) continue;
+    pass_items(ctx, alloc_count * IRCACHE_OCTA_DIMS2, [&](uint di) {
+        if (slot_is_stale_duplicate(ind, alloc_count, di / IRCACHE_OCTA_DIMS2)) return;
         const uint entry_idx = ind[di / IRCACHE_OCTA_DIMS2], octa_idx = di % IRCACHE_OCTA_DIMS2;
-        if (!is_ircache_entry_life_valid(life[entry_idx])) continue;
+        if (!is_ircache_entry_life_valid(life[entry_idx])) return;
         const Vertex entry = unpack_vertex(spatial[entry_idx]);
         const uint output_idx = entry_idx * IRCACHE_AUX_STRIDE + octa_idx;
         Reservoir1spp r = Reservoir1spp::from_raw(uint2(asuint(aux[output_idx].x), asuint(aux[output_idx].y)));
@@ -209,7 +209,7 @@ int kjb_pass_ircache_trace_access(kjb_context* ctx, const kjb_ircache_trace_acce
             r.M *= 0.8f;
             uint2 raw = r.as_raw(); aux[output_idx].x = asfloat(raw.x); aux[output_idx].y = asfloat(raw.y);
         }
-    }
+    });
     return 0;
 }
 
@@ -218,8 +218,8 @@ int kjb_pass_ircache_validate(kjb_context* ctx, const kjb_ircache_trace_args* a)
     const uint32_t* ind = (const uint32_t*)a->entry_indirection_buf.data; float4* aux = b.aux;
     const uint alloc_count = b.meta[IRCACHE_META_TRACING_ALLOC_COUNT];
     const float ped = ctx->g.fc.pre_exposure_delta;
-    for (uint di = 0; di < alloc_count * IRCACHE_VALIDATION_SAMPLES_PER_FRAME; ++di) {
-        if (slot_is_stale_duplicate(ind, alloc_count, di / 4)) continue;
+    pass_items(ctx, alloc_count * IRCACHE_VALIDATION_SAMPLES_PER_FRAME, [&](uint di) {
+        if (slot_is_stale_duplicate(ind, alloc_count, di / 4)) return;
         const uint entry_idx = ind[di / 4], sample_idx = di % 4;
         const uint life = b.life[entry_idx];
         const SampleParams sample_params = SampleParams::from_spf_entry_sample_frame(4, entry_idx, sample_idx, ctx->g.fc.frame_index);
@@ -240,7 +240,7 @@ int kjb_pass_ircache_validate(kjb_context* ctx, const kjb_ircache_trace_args* a)
             uint2 raw = r.as_raw(); aux[output_idx].x = asfloat(raw.x); aux[output_idx].y = asfloat(raw.y);
             aux[output_idx + IRCACHE_OCTA_DIMS2] = prev_value_and_count;
         }
-    }
+    });
     return 0;
 }
 
@@ -249,8 +249,8 @@ int kjb_pass_ircache_trace(kjb_context* ctx, const kjb_ircache_trace_args* a) { 
     const uint32_t* ind = (const uint32_t*)a->entry_indirection_buf.data; float4* aux = b.aux;
     const uint alloc_count = b.meta[IRCACHE_META_TRACING_ALLOC_COUNT];
     const float ped = ctx->g.fc.pre_exposure_delta;
-    for (uint di = 0; di < alloc_count * IRCACHE_SAMPLES_PER_FRAME; ++di) {
-        if (slot_is_stale_duplicate(ind, alloc_count, di / 4)) continue;
+    pass_items(ctx, alloc_count * IRCACHE_SAMPLES_PER_FRAME, [&](uint di) {
+        if (slot_is_stale_duplicate(ind, alloc_count, di / 4)) return;
         const uint entry_idx = ind[di / 4], sample_idx = di % 4;
         const uint life = b.life[entry_idx];
         const float4 packed_entry = b.spatial[entry_idx];
@@ -277,7 +277,7 @@ int kjb_pass_ircache_trace(kjb_context* ctx, const kjb_ircache_trace_args* a) { 
         uint2 raw = reservoir.as_raw(); aux[output_idx].x = asfloat(raw.x); aux[output_idx].y = asfloat(raw.y);
         aux[output_idx + IRCACHE_OCTA_DIMS2] = float4(val_sel, reservoir.W);
         if (selected_new) aux[output_idx + IRCACHE_OCTA_DIMS2 * 2] = packed_entry;
-    }
+    });
     return 0;
 }
 

@@ -26,7 +26,7 @@ struct IrcacheBufs {   // DEFINE_IRCACHE_BINDINGS (ircache/bindings.hlsl) + aux 
     static IrcacheBufs from(const kjb_ircache_bindings& b) {
         IrcacheBufs r{}; r.meta = (uint32_t*)b.meta_buf.data; r.pool = (uint32_t*)b.pool_buf.data; r.reposition_proposal = (float4*)b.reposition_proposal_buf.data;
         r.reposition_count = (uint32_t*)b.reposition_proposal_count_buf.data; r.grid_meta = (uint32_t*)b.grid_meta_buf.data; r.entry_cell = (uint32_t*)b.entry_cell_buf.data;
-        r.spatial = (const float4*)b.spatial_buf.data; r.irradiance = (const float4*)b.irradiance_buf.data; r.life = (uint32_t*)b.life_buf.data; r.aux = (float4*)b.aux_buf.data;
+        r.spatial = (const float4*)b.spatial_buf.data; r.irradiance = (const float4*)b.irradiance_buf.data; r.life = (uint32_t*)b.life_buf.data; r.aux = nullptr;   /* not in the binding block (ircache/bindings.hlsl): only the cache's own passes are IRCACHE_LOOKUP_PRECISE */
         return r;
     }
 };
