@@ -195,6 +195,8 @@ int  kjb_scene_set_geometry(kjb_context *ctx, const void *vertex_buffer, uint64_
 int  kjb_scene_set_textures(kjb_context *ctx, const kjb_texture_desc *textures, uint32_t texture_count);
 /* "rebuild tlas" (world_renderer.rs:865-911): instance transforms -> TLAS, every frame in the reference. */
 int  kjb_rebuild_tlas(kjb_context *ctx, const kjb_instance *instances, uint32_t instance_count);
+/* how "rebuild tlas" was served so far: [0] full rebuilds (instances or meshes changed), [1] device refits (only transforms changed: the per-frame case) */
+int  kjb_tlas_stats(kjb_context *ctx, uint64_t out_rebuilds_refits[2]);
 /* set 2 of every pass (renderer.rs:45-78): FrameConstants + triangle lights. */
 int  kjb_set_frame_constants(kjb_context *ctx, const kjb_frame_constants *fc,
                              const kjb_triangle_light *lights, uint32_t light_count);
@@ -248,6 +250,13 @@ int  kjb_event_synchronize(kjb_context *ctx, uint32_t event);                   
  * (interop) must leave the option off. */
 #define KJB_OPTION_HALF_RES_POSITION_CACHE 1u
 int  kjb_set_option(kjb_context *ctx, uint32_t option, uint32_t value);
+/* CUDA Graph replay of a frame's passes (the reference records one command buffer per frame, graph.rs:865-867; ~40 kernel launches here):
+ * every pass enqueued on the compute queue between the two calls is RECORDED instead of launched; kjb_graph_end turns the recording into
+ * an executable graph on first use, afterwards only updates the kernel-node parameters of the instance it keeps (same pass list => same
+ * topology), and submits the whole frame with ONE launch.  Calls that touch other queues or wait on the host must stay outside the pair. */
+int  kjb_graph_begin(kjb_context *ctx);
+int  kjb_graph_end(kjb_context *ctx);
+int  kjb_graph_stats(kjb_context *ctx, uint64_t out_launches_instantiations[2]);
 int  kjb_set_scissor(kjb_context *ctx, uint32_t y0, uint32_t y1);
 /* Determinism aid: while on, every pass that touches the (racy by design) irradiance cache runs on ONE device thread in the launch
  * order of its parallel kernel. Orders of magnitude slower; for reproducing cache states and for bit-exact parity tests. */

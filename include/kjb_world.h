@@ -122,6 +122,10 @@ int  kjb_world_last_frame_stats(kjb_world *w, uint64_t out[4]);   /* launches, c
 int  kjb_world_set_stop_after(kjb_world *w, const char *pass_label);
 /* Per-pass device timing: when on, every pass is bracketed by kjb_timer_record and accumulated per rg label. */
 int  kjb_world_set_profiling(kjb_world *w, uint32_t on);
+/* Submit each frame's passes as ONE CUDA graph launch (kjb_graph_begin / kjb_graph_end around the pass list).  On by default; it applies from the fifth
+ * frame on (every lazily created resource exists by then), never while per-pass profiling is on or the frame is tile-sharded (its exchange lives on
+ * another queue).  The environment variable KJB_NO_GRAPH=1 switches the default off (A/B timing). */
+int  kjb_world_set_cuda_graph(kjb_world *w, uint32_t on);
 /* "label\tcalls\ttotal_ms\n" per pass since profiling was switched on (synchronises). */
 const char *kjb_world_pass_timings(kjb_world *w);
 

@@ -115,6 +115,9 @@ class KjbLib:
             "kjb_comm_set_callback": (C.c_int, [P, P, P, C.c_uint32, C.c_uint32]),
             "kjb_world_pass_timings": (C.c_char_p, [P]),
             "kjb_set_debug_serial": (C.c_int, [P, C.c_uint32]),
+            "kjb_tlas_stats": (C.c_int, [P, C.POINTER(C.c_uint64 * 2)]),
+            "kjb_graph_stats": (C.c_int, [P, C.POINTER(C.c_uint64 * 2)]),
+            "kjb_world_set_cuda_graph": (C.c_int, [P, C.c_uint32]),
             "kjb_set_option": (C.c_int, [P, C.c_uint32, C.c_uint32]),
             "kjb_timer_record": (C.c_int, [P, C.c_uint32]),
             "kjb_timer_elapsed_ms": (C.c_int, [P, C.c_uint32, C.c_uint32, C.POINTER(C.c_float)]),

@@ -10,6 +10,7 @@
 #include <cmath>
 #include <algorithm>
 #include <cstring>
+#include <cstdlib>
 #include <map>
 #include <string>
 #include <vector>
@@ -137,7 +138,7 @@ struct kjb_world {
     int err = 0;
     // ---- tile sharding: this world owns half-res rows [ty0, ty1) of every frame
     bool tiled = false; uint32_t trank = 0, tcount = 1, ty0 = 0, ty1 = 0;
-    kjb_buffer xchg_send{}, xchg_recv{}; uint64_t xchg_bytes_per_rank = 0;
+    kjb_buffer xchg_send[2]{}, xchg_recv[2]{}; uint64_t xchg_bytes_per_rank[2] = {0, 0};   // [0] end-of-frame history borders, [1] mid-frame GI bands (reflections on)
     void band(uint32_t r, uint32_t rows, uint32_t& b0, uint32_t& b1) const { b0 = uint32_t(uint64_t(rows) * r / tcount); b1 = uint32_t(uint64_t(rows) * (r + 1) / tcount); }
     // restrict the next pass to the owned band grown by `e` half-res rows; `scale` = 2 for full-res passes
     uint32_t cur_row0 = 0;   // first row of the scissor last set by rows()
@@ -153,6 +154,7 @@ struct kjb_world {
         const uint32_t a = ty0 * 2 > e_full ? ty0 * 2 - e_full : 0, b = ty1 * 2 + e_full;
         kjb_set_scissor(ctx, a, b);
     }
+    bool use_graph = true, graph_open = false;   // kjb_world_set_cuda_graph
     bool profiling = false; uint32_t timer_next = 0;
     std::vector<std::pair<std::string, std::pair<uint32_t, uint32_t>>> timer_pending;   // label -> (slot_begin, slot_end) of this frame
     std::map<std::string, std::pair<uint32_t, double>> pass_ms;                          // label -> (calls, total ms)
@@ -217,6 +219,7 @@ int kjb_world_create(kjb_context* ctx, const kjb_world_desc* desc, kjb_world** o
     kjb_world* w = new kjb_world();
     w->ctx = ctx; w->desc = *desc;
     w->sun_size_multiplier = desc->hard_sun ? 0.0f : 1.0f;
+    { const char* e = getenv("KJB_NO_GRAPH"); if (e && e[0] == '1') w->use_graph = false; }
     kjb_set_option(ctx, KJB_OPTION_HALF_RES_POSITION_CACHE, 1);   // this driver only writes half_depth / the packed reservoirs through the passes the option tracks
     if (w->desc.spatial_reuse_pass_count == 0) w->desc.spatial_reuse_pass_count = 2;
     w->W = desc->render_width; w->H = desc->render_height;
@@ -225,7 +228,7 @@ int kjb_world_create(kjb_context* ctx, const kjb_world_desc* desc, kjb_world** o
     // Tiles + irradiance cache: every rank keeps its OWN replica of the cache, fed by the rays of its band and halos (SURVEY §8e "replicas
     // only" fall-back: the cache is one global racy structure and does not shard by rows; results stay statistically equivalent, which is all
     // the cache promises on one GPU too).  Tiles + reflections / lit composite: not yet (rtr samples this frame's GI anywhere on screen).
-    if (desc->tile_count > 1 && (desc->enable_rtr || desc->enable_lighting)) { delete w; return 1; }
+    if (desc->tile_count > 1 && desc->enable_lighting) { delete w; return 1; }   // the lit composite (shadow denoiser history) does not shard yet
     if (desc->tile_count > 1) {
         if (w->OW != w->W || w->OH != w->H || (w->H & 1)) { delete w; return 1; }   // tiles + temporal upscaling / odd heights: not supported
         w->tiled = true; w->trank = desc->tile_rank; w->tcount = desc->tile_count;
@@ -238,8 +241,7 @@ void kjb_world_destroy(kjb_world* w) {
     if (!w) return;
     kjb_sync(w->ctx);   // every queue: nothing of this world is in flight any more
     for (auto& kv : w->images) kjb_image_free(w->ctx, &kv.second);
-    if (w->xchg_send.data) kjb_buffer_free(w->ctx, &w->xchg_send);
-    if (w->xchg_recv.data) kjb_buffer_free(w->ctx, &w->xchg_recv);
+    for (int k = 0; k < 2; ++k) { if (w->xchg_send[k].data) kjb_buffer_free(w->ctx, &w->xchg_send[k]); if (w->xchg_recv[k].data) kjb_buffer_free(w->ctx, &w->xchg_recv[k]); }
     delete w;
 }
 
@@ -396,6 +398,7 @@ int kjb_world_last_frame_stats(kjb_world* w, uint64_t out[4]) {
     memcpy(out, w->stats, sizeof(w->stats)); return 0;
 }
 int kjb_world_set_stop_after(kjb_world* w, const char* label) { w->stop_after = label ? label : ""; return 0; }
+int kjb_world_set_cuda_graph(kjb_world* w, uint32_t on) { w->use_graph = on != 0; return 0; }
 int kjb_world_set_profiling(kjb_world* w, uint32_t on) { w->flush_timers(); w->profiling = on != 0; if (on) w->pass_ms.clear(); return 0; }
 const char* kjb_world_pass_timings(kjb_world* w) {
     w->flush_timers();
@@ -510,14 +513,20 @@ static void end_frame(kjb_world* w) {
 // Half-res rows a pass must compute beyond the owned band so that every later pass of the SAME frame finds valid inputs
 // (derived from the shaders' stencils: restir_spatial.hlsl:89-92 radii 32/16/8, payload indirection `spx`, resolve ~3,
 // temporal filter 5x5, spatial filter <=16 px, taa 3x3..5x5).  History older than this frame comes from the exchange.
-struct TileHalos { uint32_t d11, d10, d9, spatial_last, d6, d5, d4, halo, border; };
+// Reflections (rtr.rs): the spatial cleanup reaches SPATIAL_RESOLVE_OFFSETS (|offset| <= 12, x2 at low sample counts) = 12 half-res rows, its
+// temporal filter 3x3, the resolve's world-space footprint is clamped to 0.1 of the screen height (resolve.hlsl:201-207) = H/40 half-res
+// rows (+ 8 % for the outermost tap + 2), the reservoir history is searched within 14 half-res px of the reprojected pixel
+// (rtr_restir_temporal.hlsl rpx_offset_radius) and validated in 2x2 quads.
+struct TileHalos { uint32_t d11, d10, d9, spatial_last, d6, d5, d4, halo, border; uint32_t r_cleanup, r_temporal, r_resolve, r_rt, r_validate, r_border; };
 static TileHalos tile_halos(const kjb_world* w) {
     TileHalos h{};
     const uint32_t x = w->desc.enable_taa ? 6u : 0u;
+    h.r_cleanup = x; h.r_temporal = x + 13; h.r_resolve = h.r_temporal + 1; h.r_rt = h.r_resolve + w->H / 36 + 4; h.r_validate = h.r_rt + 18; h.r_border = h.r_validate + 4;
     uint32_t sum_r = 0;
     for (uint32_t i = 0; i < w->desc.spatial_reuse_pass_count; ++i) sum_r += i == 0 ? 32u : (i == 1 ? 16u : 8u);
     h.d11 = x; h.d10 = x + 8; h.d9 = x + 9; h.spatial_last = x + 12;
     h.d6 = x + 12 + sum_r; h.d5 = h.d6; h.d4 = h.d6 + 4; h.halo = h.d6 + 8; h.border = h.halo + 4;
+    if (w->desc.enable_rtr) h.d4 = std::max(h.d4, h.r_rt + 2);   // the diffuse candidates double as reflection candidates (rtr.rs:105-109)
     return h;
 }
 static uint32_t spatial_radius(uint32_t pass_idx) { return pass_idx == 0 ? 32u : (pass_idx == 1 ? 16u : 8u); }
@@ -529,7 +538,7 @@ struct XchgItem { kjb_image img; uint32_t scale; uint32_t border; };   // border
 // ONE all-gather per frame: every rank contributes the top and bottom `border` rows of its band of each temporal image (its
 // whole band for the full-res GI history, which the next frame's rays sample at arbitrary screen positions), and copies the
 // strips it needs from the other ranks' contributions into its own images.  Row strips of row-major images are contiguous.
-static int tile_exchange(kjb_world* w, const std::vector<XchgItem>& items_in, uint32_t queue) {
+static int tile_exchange(kjb_world* w, const std::vector<XchgItem>& items_in, uint32_t queue, int set = 0) {
     kjb_context* ctx = w->ctx;
     const uint32_t n = w->tcount;
     uint32_t band_max = 0, band_min = 0xffffffffu;
@@ -547,10 +556,10 @@ static int tile_exchange(kjb_world* w, const std::vector<XchgItem>& items_in, ui
         off[i] = total; total += strip_bytes[i] * (items[i].border ? 2 : 1);
     }
     total = (total + 255) / 256 * 256;
-    if (w->xchg_bytes_per_rank != total) {
-        if (w->xchg_send.data) { kjb_sync(ctx); kjb_buffer_free(ctx, &w->xchg_send); kjb_buffer_free(ctx, &w->xchg_recv); }
-        if (kjb_buffer_alloc(ctx, total, &w->xchg_send) || kjb_buffer_alloc(ctx, total * n, &w->xchg_recv)) return 1;
-        w->xchg_bytes_per_rank = total;
+    if (w->xchg_bytes_per_rank[set] != total) {
+        if (w->xchg_send[set].data) { kjb_sync(ctx); kjb_buffer_free(ctx, &w->xchg_send[set]); kjb_buffer_free(ctx, &w->xchg_recv[set]); }
+        if (kjb_buffer_alloc(ctx, total, &w->xchg_send[set]) || kjb_buffer_alloc(ctx, total * n, &w->xchg_recv[set])) return 1;
+        w->xchg_bytes_per_rank[set] = total;
     }
     auto strips_of = [&](uint32_t r, const XchgItem& it, uint32_t out[2][2]) {   // [strip][row0,row1) in image rows
         uint32_t b0, b1; w->band(r, w->HH, b0, b1); b0 *= it.scale; b1 *= it.scale;
@@ -564,15 +573,15 @@ static int tile_exchange(kjb_world* w, const std::vector<XchgItem>& items_in, ui
         const uint64_t row_bytes = uint64_t(items[i].img.width) * kjb_format_texel_bytes(items[i].img.format);
         uint32_t st[2][2]; strips_of(w->trank, items[i], st);
         for (int k = 0; k < (items[i].border ? 2 : 1); ++k)
-            copies.push_back({(char*)w->xchg_send.data + off[i] + strip_bytes[i] * k, (const char*)items[i].img.data + row_bytes * st[k][0], row_bytes * (st[k][1] - st[k][0])});
+            copies.push_back({(char*)w->xchg_send[set].data + off[i] + strip_bytes[i] * k, (const char*)items[i].img.data + row_bytes * st[k][0], row_bytes * (st[k][1] - st[k][0])});
     }
     if (kjb_memcpy_d2d_batch_on(ctx, queue, copies.data(), uint32_t(copies.size()))) return 1;
     copies.clear();
-    if (kjb_allgather_on(ctx, queue, w->xchg_send.data, w->xchg_recv.data, total)) return 1;
+    if (kjb_allgather_on(ctx, queue, w->xchg_send[set].data, w->xchg_recv[set].data, total)) return 1;
     // unpack what this rank reads next frame: its band grown by `border` rows (everything for whole-band items)
     for (uint32_t r = 0; r < n; ++r) {
         if (r == w->trank) continue;
-        const char* base = (const char*)w->xchg_recv.data + total * r;
+        const char* base = (const char*)w->xchg_recv[set].data + total * r;
         for (size_t i = 0; i < items.size(); ++i) {
             const uint64_t row_bytes = uint64_t(items[i].img.width) * kjb_format_texel_bytes(items[i].img.format);
             uint32_t mine[2][2]; strips_of(w->trank, items[i], mine);
@@ -614,6 +623,11 @@ static void tile_exchange_frame(kjb_world* w) {
     add(w->temporal_reservoir_tex, 1, th2.border); add(w->temporal_candidate_tex, 1, th2.border); add(w->temporal_invalidity_tex, 1, th2.border);
     add(w->temporal_hit_normal_tex, 1, th2.border);
     if (w->desc.enable_taa) { add(w->taa_temporal_tex, 2, 16); add(w->taa_temporal_velocity_tex, 2, 16); add(w->taa_temporal_smooth_var_tex, 2, 16); }
+    if (w->desc.enable_rtr) {   // what RtrRenderer reads as history next frame
+        add(w->rtr_temporal_irradiance_tex, 1, th2.r_border); add(w->rtr_temporal_ray_orig_tex, 1, th2.r_border); add(w->rtr_temporal_ray_tex, 1, th2.r_border);
+        add(w->rtr_temporal_reservoir_tex, 1, th2.r_border); add(w->rtr_temporal_rng_tex, 1, th2.r_border); add(w->rtr_temporal_hit_normal_tex, 1, th2.r_border);
+        add(w->rtr_temporal_tex, 2, 2 * (th2.r_resolve + 4)); add(w->rtr_ray_len_tex, 2, 2 * (th2.r_resolve + 4));
+    }
     const uint32_t queue = w->profiling ? KJB_QUEUE_COMPUTE : KJB_QUEUE_COMM;
     w->pass_begin("tile border all-gather");
     int rc = 0;
@@ -836,7 +850,7 @@ static void rtdgi_render(kjb_world* w, kjb_image& reprojected_history_tex, kjb_i
         w->rows(th.d10, 2);
         RUN("rtdgi temporal", kjb_pass_rtdgi_temporal(ctx, &a));
     }
-    if (w->tiled && !w->desc.enable_taa) tile_exchange_frame(w);   // everything that travels is final: overlap the collective with the spatial filter
+    if (w->tiled && !w->desc.enable_taa && !w->desc.enable_rtr) tile_exchange_frame(w);   // everything that travels is final: overlap the collective with the spatial filter
     // RtdgiRenderer::spatial (rtdgi.rs:117-141)
     kjb_image& spatial_filtered_tex = w->img("rtdgi.spatial_filtered", W, H, KJB_FMT_RGBA16_FLOAT);
     {
@@ -894,6 +908,15 @@ static kjb_image* rtr_render(kjb_world* w, kjb_image& gbuffer, kjb_image& depth,
     const uint32_t HW = w->HW, HH = w->HH, W = w->W, H = w->H;
     float gbuffer_size[4]; size4(gbuffer_size, gbuffer);
     if (w->spatial_resolve_offsets.empty()) { w->err = 1; return nullptr; }
+    const TileHalos th = tile_halos(w);
+    if (w->tiled && !w->err && !w->stopped) {
+        // Reflection rays land anywhere on screen and read THIS frame's GI there (reflection_trace_common.inc.hlsl, USE_SCREEN_GI_REPROJECTION):
+        // every rank contributes its band of the filtered GI and receives the others' — the frame's second (and last) collective.
+        std::vector<XchgItem> gi; gi.push_back({rtdgi_irradiance, 2, 0});
+        w->pass_begin("tile gi all-gather");
+        if (tile_exchange(w, gi, KJB_QUEUE_COMPUTE, 1)) w->err = 1;
+        w->pass_end();
+    }
     // RtdgiCandidates (rtr.rs:105-109): the diffuse candidate images double as the reflection candidates
     kjb_image& refl0_tex = w->img("rtdgi.candidate_radiance", HW, HH, KJB_FMT_RGBA16_FLOAT);
     kjb_image& refl1_tex = w->img("rtdgi.candidate_hit", HW, HH, KJB_FMT_RGBA16_FLOAT);
@@ -903,6 +926,7 @@ static kjb_image* rtr_render(kjb_world* w, kjb_image& gbuffer, kjb_image& depth,
         kjb_rtr_trace_args a{}; a.gbuffer_tex = gbuffer; a.depth_tex = depth; a.rtdgi_tex = rtdgi_irradiance; a.sky_cube_tex = sky_cube; a.ircache = ircache;
         a.out0_tex = refl0_tex; a.out1_tex = refl1_tex; a.out2_tex = refl2_tex; a.rng_out_tex = *rng_output_tex; memcpy(a.gbuffer_tex_size, gbuffer_size, 16);
         a.reuse_rtdgi_rays = w->rtr_reuse_rtdgi_rays ? 1u : 0u;
+        w->rows(th.r_rt + 1, 1);
         RUN("reflection trace", kjb_pass_rtr_trace(ctx, &a));
     }
     kjb_image& half_view_normal_tex = w->img("half_view_normal", HW, HH, KJB_FMT_RGBA8_SNORM);   // memoised by rtdgi (mod.rs:54-70)
@@ -917,7 +941,9 @@ static kjb_image* rtr_render(kjb_world* w, kjb_image& gbuffer, kjb_image& depth,
         kjb_rtr_validate_args a{}; a.gbuffer_tex = gbuffer; a.depth_tex = depth; a.rtdgi_tex = rtdgi_irradiance; a.sky_cube_tex = sky_cube; a.refl_restir_invalidity_tex = refl_restir_invalidity_tex;
         a.ircache = ircache; a.ray_orig_history_tex = *ray_orig_history_tex; a.ray_history_tex = *ray_history_tex; a.rng_history_tex = *rng_history_tex;
         a.irradiance_history_tex = *irradiance_history_tex; a.reservoir_history_tex = *reservoir_history_tex; memcpy(a.gbuffer_tex_size, gbuffer_size, 16);
+        w->rows((th.r_validate + 1) & ~1u, 1);
         RUN("reflection validate", kjb_pass_rtr_validate(ctx, &a));
+        RUN_TOP("reflection validate", kjb_pass_rtr_validate(ctx, &a), 4);   // pixel (0,0): empty reservoirs (payload 0) dereference it from anywhere
     }
     {
         kjb_rtr_restir_temporal_args a{}; a.gbuffer_tex = gbuffer; a.half_view_normal_tex = half_view_normal_tex; a.depth_tex = depth; a.candidate0_tex = refl0_tex; a.candidate1_tex = refl1_tex;
@@ -925,6 +951,7 @@ static kjb_image* rtr_render(kjb_world* w, kjb_image& gbuffer, kjb_image& depth,
         a.rng_history_tex = *rng_history_tex; a.reservoir_history_tex = *reservoir_history_tex; a.reprojection_tex = reprojection_map; a.hit_normal_history_tex = *hit_normal_history_tex;
         a.irradiance_out_tex = *irradiance_output_tex; a.ray_orig_output_tex = *ray_orig_output_tex; a.ray_output_tex = *ray_output_tex; a.rng_output_tex = *rng_output_tex;
         a.hit_normal_output_tex = *hit_normal_output_tex; a.reservoir_out_tex = *reservoir_output_tex; memcpy(a.gbuffer_tex_size, gbuffer_size, 16);
+        w->rows(th.r_rt, 1);
         RUN("rtr restir temporal", kjb_pass_rtr_restir_temporal(ctx, &a));
     }
     kjb_image& resolved_tex = w->img("rtr.resolved", W, H, KJB_FMT_R11G11B10_UFLOAT);
@@ -936,6 +963,7 @@ static kjb_image* rtr_render(kjb_world* w, kjb_image& gbuffer, kjb_image& depth,
         a.restir_irradiance_tex = *irradiance_output_tex; a.restir_ray_tex = *ray_output_tex; a.restir_reservoir_tex = *reservoir_output_tex; a.restir_ray_orig_tex = *ray_orig_output_tex;
         a.restir_hit_normal_tex = *hit_normal_output_tex; a.output_tex = resolved_tex; a.ray_len_output_tex = *ray_len_output_tex; size4(a.output_tex_size, resolved_tex);
         a.spatial_resolve_offsets = w->spatial_resolve_offsets.data();
+        w->rows(th.r_resolve, 2);
         RUN("reflection resolve", kjb_pass_rtr_resolve(ctx, &a));
     }
     if (w->frame_light_count > 0) {   // lighting.render_specular (world_render_passes.rs:190-201, lighting.rs:23-87): the triangle lights' specular, into the resolved reflections
@@ -950,11 +978,13 @@ static kjb_image* rtr_render(kjb_world* w, kjb_image& gbuffer, kjb_image& depth,
     {   // filter_temporal (rtr.rs:366-398)
         kjb_rtr_temporal_args a{}; a.input_tex = resolved_tex; a.history_tex = *history_tex; a.depth_tex = depth; a.ray_len_tex = *ray_len_output_tex; a.reprojection_tex = reprojection_map;
         a.refl_restir_invalidity_tex = refl_restir_invalidity_tex; a.gbuffer_tex = gbuffer; a.output_tex = *temporal_output_tex; size4(a.output_tex_size, *temporal_output_tex);
+        w->rows(th.r_temporal, 2);
         RUN("reflection temporal", kjb_pass_rtr_temporal(ctx, &a));
     }
     {
         kjb_rtr_cleanup_args a{}; a.input_tex = *temporal_output_tex; a.depth_tex = depth; a.geometric_normal_tex = geometric_normal; a.output_tex = resolved_tex;
         a.spatial_resolve_offsets = w->spatial_resolve_offsets.data();
+        w->rows(th.r_cleanup, 2);
         RUN("reflection cleanup", kjb_pass_rtr_cleanup(ctx, &a));
     }
     return &resolved_tex;
@@ -1055,6 +1085,9 @@ int kjb_world_render_frame(kjb_world* w, const kjb_world_frame* f) {
         kjb_image_copy(ctx, &w->img(sp + "depth", W, H, KJB_FMT_R32_FLOAT), &depth);
         kjb_image_copy(ctx, &w->img(sp + "velocity", W, H, KJB_FMT_RGBA16_FLOAT), &velocity);
     }
+    // From here to the end of the pass list everything runs on the compute queue: record it and submit the frame as one CUDA graph launch
+    // (the inputs above may have come through the upload queue; the result download below goes through the download queue).
+    if (w->use_graph && !w->profiling && !w->tiled && w->frame_idx >= 4 && w->stop_after.empty() && !w->err) { if (kjb_graph_begin(ctx) == 0) w->graph_open = true; }
     // reprojection map + copy depth (renderers/reprojection.rs:6-52)
     kjb_image& reprojection_map = w->img("reprojection_map", W, H, KJB_FMT_RGBA16_SNORM);
     kjb_image& prev_depth = w->img("reprojection.prev_depth", W, H, KJB_FMT_R32_FLOAT);
@@ -1137,6 +1170,7 @@ int kjb_world_render_frame(kjb_world* w, const kjb_world_frame* f) {
         kjb_image taa_in{};
         if (kjb_world_get_image(w, result_name, &taa_in) == 0) { taa_render(w, taa_in, reprojection_map, depth); result_name = "taa.this_frame_out"; }
     }
+    if (w->graph_open) { w->graph_open = false; if (kjb_graph_end(ctx)) w->err = 1; }
     if (w->tiled && !w->exchanged_this_frame) tile_exchange_frame(w);   // with TAA its history images travel too: exchange at the end of the frame
     if (streaming && !w->err) {
         kjb_image result{};

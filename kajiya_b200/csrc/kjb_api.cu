@@ -1,7 +1,126 @@
 // C-ABI entry points: context, memory, scene upload, "rebuild tlas", frame constants (include/kjb.h).
 #include "kjb_context.h"
+#include "kjb_ircache.cuh"
 
 using namespace kjb;
+
+// ---- TMA tensor maps (kjb_tile.cuh).  The image is described as a 2-D tensor of 32-bit words (4-, 8- and 16-byte texels; the x
+// coordinate of a copy is scaled by words-per-texel) or of its own 1- / 2-byte elements; the box is the tile, rows padded to 16 bytes.
+namespace kjb {
+#if defined(KJB_EMU)
+TileSource tile_source(kjb_context*, const kjb_image&, uint32_t, uint32_t) { TileSource t; t.use_tma = 0; return t; }
+#else
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn() {
+    static EncodeTiledFn fn = [] {
+        void* p = nullptr; cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) p = nullptr;
+        const char* off = getenv("KJB_NO_TMA");   // A/B switch for tools/variant_bench.py: stage every tile with guarded loads
+        if (off && off[0] == '1') p = nullptr;
+        return (EncodeTiledFn)p;
+    }();
+    return fn;
+}
+TileSource tile_source(kjb_context* c, const kjb_image& img, uint32_t box_w, uint32_t box_h) {
+    const auto key = std::make_tuple((const void*)img.data, img.width, img.height, img.format, box_w, box_h);
+    auto it = c->tile_sources.find(key);
+    if (it != c->tile_sources.end()) return it->second;
+    TileSource t; memset(&t, 0, sizeof(t));
+    const uint32_t tb = texel_bytes(img.format);
+    const uint64_t row_bytes = uint64_t(img.width) * tb;
+    EncodeTiledFn enc = encode_tiled_fn();
+    const uint32_t pitch_texels = ((box_w * tb + 15) / 16 * 16) / tb;   // == tile_pitch<tb>(box_w)
+    const uint32_t words = tb >= 4 ? tb / 4 : 1;
+    if (enc && tb && (row_bytes % 16 == 0) && (uintptr_t(img.data) % 16 == 0) && pitch_texels * words <= 256 && box_h <= 256 && (img.layers <= 1)) {
+        const CUtensorMapDataType dt = tb >= 4 ? CU_TENSOR_MAP_DATA_TYPE_UINT32 : (tb == 2 ? CU_TENSOR_MAP_DATA_TYPE_UINT16 : CU_TENSOR_MAP_DATA_TYPE_UINT8);
+        const cuuint64_t dims[2] = {cuuint64_t(img.width) * words, img.height};
+        const cuuint64_t strides[1] = {row_bytes};
+        const cuuint32_t box[2] = {pitch_texels * words, box_h};
+        const cuuint32_t estr[2] = {1, 1};
+        if (enc(&t.map, dt, 2, img.data, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS)
+            t.use_tma = 1;
+    }
+    c->tile_sources[key] = t;
+    return t;
+}
+#endif
+}  // namespace kjb
+
+// ---- "rebuild tlas" on the device.  The reference rebuilds its TLAS every frame (world_renderer.rs:865-911, ray_tracing.rs:455-520); here the
+// acceleration structure is ONE flattened world-space BVH, so a transform change means new world-space triangles and new boxes.  When only
+// transforms changed (same instances, same meshes) the topology is kept and two kernels redo the rest: (1) every leaf-order triangle record
+// is re-derived from the unified vertex buffer and its instance's 3x4 matrix — the same float operations as the host flatten, so the records
+// are bit-identical to a full rebuild's; (2) boxes are refitted bottom-up (one thread per inner node fills its leaf slots, the second arriver
+// at a node carries the union to the parent).  Hits do not depend on the topology (DESIGN.md "ray/triangle contract"), so a refitted
+// structure returns exactly what a rebuilt one would.
+KJB_DEV void box_of_tri(const float3 a, const float3 b, const float3 c, float* out6) {
+    out6[0] = kjb_min(a.x, kjb_min(b.x, c.x)); out6[1] = kjb_min(a.y, kjb_min(b.y, c.y)); out6[2] = kjb_min(a.z, kjb_min(b.z, c.z));
+    out6[3] = kjb_max(a.x, kjb_max(b.x, c.x)); out6[4] = kjb_max(a.y, kjb_max(b.y, c.y)); out6[5] = kjb_max(a.z, kjb_max(b.z, c.z));
+}
+KJB_KERNEL(256) k_refit_tris(SceneView sc, BvhTri* tris, float* tri_box, uint32_t slot_count, Rows kjb_rows) {
+    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= slot_count) return;
+    const uint32_t gid = tris[s].gid;
+    if (gid >= sc.tri_count) return;
+    const TriInfo ti = sc.tri_info[gid];
+    const kjb_instance& inst = sc.instances[ti.instance];
+    const kjb_gpu_mesh mesh = sc.meshes[inst.mesh_index];
+    float3 wv[3];
+    for (int k = 0; k < 3; ++k) {
+        const uint32_t idx = vb_u32(sc, mesh.index_offset + (ti.prim * 3 + k) * 4);
+        const float* v = reinterpret_cast<const float*>(sc.vertices + mesh.vertex_core_offset + size_t(idx) * 16);
+        wv[k] = xform_point(inst.transform, f3(v[0], v[1], v[2]));
+    }
+    BvhTri t = tris[s];
+    t.v0[0] = wv[0].x; t.v0[1] = wv[0].y; t.v0[2] = wv[0].z;
+    t.e1[0] = wv[1].x - wv[0].x; t.e1[1] = wv[1].y - wv[0].y; t.e1[2] = wv[1].z - wv[0].z;
+    t.e2[0] = wv[2].x - wv[0].x; t.e2[1] = wv[2].y - wv[0].y; t.e2[2] = wv[2].z - wv[0].z;
+    tris[s] = t;
+    box_of_tri(wv[0], wv[1], wv[2], tri_box + size_t(s) * 6);
+}
+KJB_DEV void write_padded_slot(BvhNode& nd, int k, const float* b) {   // Builder::padded (kjb_bvh.cpp): the slab test only culls, pad against its rounding
+    float lo[3], hi[3];
+    for (int a = 0; a < 3; ++a) {
+        const float pad = (b[3 + a] - b[a]) * 1e-5f + 1e-6f + 1e-6f * kjb_max(kjb_abs(b[a]), kjb_abs(b[3 + a]));
+        lo[a] = b[a] - pad; hi[a] = b[3 + a] + pad;
+    }
+    float* nxy = k == 0 ? nd.n0 : nd.n1;
+    nxy[0] = lo[0]; nxy[1] = hi[0]; nxy[2] = lo[1]; nxy[3] = hi[1];
+    nd.n2[k * 2 + 0] = lo[2]; nd.n2[k * 2 + 1] = hi[2];
+}
+KJB_KERNEL(256) k_refit_nodes(BvhNode* nodes, const int32_t* parent, uint32_t* count, float* slot_box, const float* tri_box, uint32_t node_count, Rows kjb_rows) {
+    uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= node_count) return;
+    uint32_t leaves = 0;
+    for (int k = 0; k < 2; ++k) {
+        const int32_t ch = nodes[i].child[k];
+        if (ch >= 0) continue;
+        const uint32_t enc = uint32_t(~ch), first = enc >> 3, n = (enc & 7u) + 1u;
+        float b[6] = {3.4e38f, 3.4e38f, 3.4e38f, -3.4e38f, -3.4e38f, -3.4e38f};
+        for (uint32_t t = 0; t < n; ++t) for (int a = 0; a < 3; ++a) { b[a] = kjb_min(b[a], tri_box[size_t(first + t) * 6 + a]); b[3 + a] = kjb_max(b[3 + a], tri_box[size_t(first + t) * 6 + 3 + a]); }
+        for (int a = 0; a < 6; ++a) slot_box[(size_t(i) * 2 + k) * 6 + a] = b[a];
+        write_padded_slot(nodes[i], k, b);
+        ++leaves;
+    }
+    if (leaves == 0) return;
+    // climb: a node is complete once both of its slots hold this frame's boxes; the arrival that completes it carries the union upwards
+    for (;;) {
+#if defined(__CUDA_ARCH__)
+        __threadfence();
+#endif
+        if (atom_add(&count[i], leaves) + leaves < 2u) return;
+        const int32_t p = parent[i];
+        if (p < 0) return;
+        float u[6];
+        for (int a = 0; a < 3; ++a) { u[a] = kjb_min(slot_box[(size_t(i) * 2) * 6 + a], slot_box[(size_t(i) * 2 + 1) * 6 + a]); u[3 + a] = kjb_max(slot_box[(size_t(i) * 2) * 6 + 3 + a], slot_box[(size_t(i) * 2 + 1) * 6 + 3 + a]); }
+        const uint32_t pi = uint32_t(p >> 1); const int pk = p & 1;
+        for (int a = 0; a < 6; ++a) slot_box[(size_t(pi) * 2 + pk) * 6 + a] = u[a];
+        write_padded_slot(nodes[pi], pk, u);
+        i = pi; leaves = 1;
+    }
+}
 
 extern "C" {
 
@@ -38,9 +157,11 @@ void kjb_destroy(kjb_context* c) {
     if (!c) return;
     dev_sync(c);
     dev_free(c->d_vertices); dev_free(c->d_meshes); dev_free(c->d_instances); dev_free(c->d_nodes); dev_free(c->d_tris); dev_free(c->d_tri_info);
+    dev_free(c->d_node_parent); dev_free(c->d_refit_count); dev_free(c->d_slot_box); dev_free(c->d_tri_box);
     dev_free(c->d_tex_data); dev_free(c->d_tex_desc); dev_free(c->d_lights); dev_free(c->d_ray_counters); dev_free(c->d_prev_instances); dev_free(c->d_resolve_offsets);
 #if !defined(KJB_EMU)
     if (c->pinned_staging) cudaFreeHost(c->pinned_staging);
+    if (c->graph_exec) cudaGraphExecDestroy(c->graph_exec);
     for (auto& ev : c->queue_events) if (ev) cudaEventDestroy(ev);
     for (auto& st : c->copy_streams) if (st) cudaStreamDestroy(st);
     if (c->stream) cudaStreamDestroy(c->stream);
@@ -63,7 +184,10 @@ int kjb_image_alloc(kjb_context* c, uint32_t w, uint32_t h, uint32_t layers, uin
     out->data = dev_alloc(image_bytes(*out));   // zero-filled
     return out->data ? 0 : c->fail("kjb_image_alloc: out of device memory");
 }
-int kjb_image_free(kjb_context*, kjb_image* img) { dev_free(img->data); img->data = nullptr; return 0; }
+int kjb_image_free(kjb_context* c, kjb_image* img) {
+    for (auto it = c->tile_sources.begin(); it != c->tile_sources.end();) { if (std::get<0>(it->first) == img->data) it = c->tile_sources.erase(it); else ++it; }   // the address may be reused
+    dev_free(img->data); img->data = nullptr; return 0;
+}
 int kjb_image_clear(kjb_context* c, const kjb_image* img) { c->invalidate_positions(); return dev_memset(c, img->data, 0, image_bytes(*img)); }
 int kjb_image_fill_u8(kjb_context* c, const kjb_image* img, uint32_t v) { c->invalidate_positions(); return dev_memset(c, img->data, int(v), image_bytes(*img)); }
 int kjb_image_copy(kjb_context* c, const kjb_image* dst, const kjb_image* src) { c->invalidate_positions();
@@ -146,9 +270,37 @@ int kjb_scene_set_textures(kjb_context* c, const kjb_texture_desc* t, uint32_t n
 // list is bit-identical to the previous call (static scenes), which is the steady state of every benchmark config.
 int kjb_rebuild_tlas(kjb_context* c, const kjb_instance* inst, uint32_t n) {
     if (c->tlas_valid && c->h_instances.size() == n && (n == 0 || memcmp(c->h_instances.data(), inst, n * sizeof(kjb_instance)) == 0)) return 0;
+    {   // same instances, same meshes, other transforms (the per-frame case of a moving scene): refit on the device, no host work, no sync
+        bool same_topology = c->tlas_valid && c->h_instances.size() == n && n > 0 && c->node_count > 0 && c->d_node_parent;
+        for (uint32_t i = 0; same_topology && i < n; ++i) same_topology = c->h_instances[i].mesh_index == inst[i].mesh_index;
+        if (same_topology) {
+            // the instance array the kernels read is double-buffered through a pinned staging copy so that the caller's array may change at once
+            if (c->pinned_bytes < n * sizeof(kjb_instance)) {
+#if !defined(KJB_EMU)
+                dev_sync(c); if (c->pinned_staging) cudaFreeHost(c->pinned_staging);
+                if (cudaMallocHost(&c->pinned_staging, n * sizeof(kjb_instance) * 4) != cudaSuccess) { c->pinned_staging = nullptr; c->pinned_bytes = 0; return c->fail("kjb_rebuild_tlas: pinned staging allocation failed"); }
+#else
+                free(c->pinned_staging); c->pinned_staging = malloc(n * sizeof(kjb_instance) * 4);
+#endif
+                c->pinned_bytes = n * sizeof(kjb_instance);
+            }
+            kjb_instance* stage = (kjb_instance*)c->pinned_staging + size_t(c->tlas_refits & 3u) * n;
+            memcpy(stage, inst, n * sizeof(kjb_instance));
+            c->h_instances.assign(inst, inst + n);
+            if (dev_h2d(c, c->d_instances, stage, n * sizeof(kjb_instance))) return c->fail("kjb_rebuild_tlas: instance upload failed");
+            dev_memset(c, c->d_refit_count, 0, c->node_count * sizeof(uint32_t));
+            const kjb::Rows kjb__rows = {0, 1};
+            KJB_LAUNCH(c, k_refit_tris, KJB_DIMS(dim3((c->slot_count + 255) / 256), dim3(256)), c->g.scene, c->d_tris, c->d_tri_box, c->slot_count);
+            KJB_LAUNCH(c, k_refit_nodes, KJB_DIMS(dim3((c->node_count + 255) / 256), dim3(256)), c->d_nodes, (const int32_t*)c->d_node_parent, c->d_refit_count, c->d_slot_box, (const float*)c->d_tri_box, c->node_count);
+            c->tlas_refits++;
+            KJB_PASS_EPILOGUE(c, "rebuild tlas (refit)");
+        }
+    }
     dev_sync(c);
+    c->tlas_rebuilds++;
     c->h_instances.assign(inst, inst + n);
     std::vector<float> wt; std::vector<TriInfo> info;
+    { size_t total = 0; for (uint32_t i = 0; i < n; ++i) if (inst[i].mesh_index < c->h_meshes.size()) total += c->h_index_counts[inst[i].mesh_index] / 3; wt.reserve(total * 9); info.reserve(total); }
     for (uint32_t i = 0; i < n; ++i) {
         if (inst[i].mesh_index >= c->h_meshes.size()) return c->fail("kjb_rebuild_tlas: instance references an unknown mesh");
         const kjb_gpu_mesh& m = c->h_meshes[inst[i].mesh_index];
@@ -167,6 +319,13 @@ int kjb_rebuild_tlas(kjb_context* c, const kjb_instance* inst, uint32_t n) {
     HostBvh bvh;
     build_bvh(wt.data(), info.data(), uint32_t(info.size()), bvh);
     dev_free(c->d_nodes); dev_free(c->d_tris); dev_free(c->d_tri_info); dev_free(c->d_instances);
+    dev_free(c->d_node_parent); dev_free(c->d_refit_count); dev_free(c->d_slot_box); dev_free(c->d_tri_box);
+    c->node_count = uint32_t(bvh.nodes.size()); c->slot_count = uint32_t(bvh.tris.size());
+    c->d_node_parent = c->node_count ? (int32_t*)dev_alloc(c->node_count * sizeof(int32_t)) : nullptr;
+    c->d_refit_count = c->node_count ? (uint32_t*)dev_alloc(c->node_count * sizeof(uint32_t)) : nullptr;
+    c->d_slot_box = c->node_count ? (float*)dev_alloc(size_t(c->node_count) * 12 * sizeof(float)) : nullptr;
+    c->d_tri_box = (float*)dev_alloc(size_t(c->slot_count) * 6 * sizeof(float));
+    if (c->d_node_parent) dev_h2d(c, c->d_node_parent, bvh.parent.data(), c->node_count * sizeof(int32_t));
     c->d_nodes = bvh.nodes.empty() ? nullptr : (BvhNode*)dev_alloc(bvh.nodes.size() * sizeof(BvhNode));
     c->d_tris = (BvhTri*)dev_alloc(bvh.tris.size() * sizeof(BvhTri));
     c->d_tri_info = (TriInfo*)dev_alloc((bvh.info.size() + 1) * sizeof(TriInfo));
@@ -181,6 +340,39 @@ int kjb_rebuild_tlas(kjb_context* c, const kjb_instance* inst, uint32_t n) {
     return dev_sync(c);
 }
 
+#if defined(KJB_EMU)
+int kjb_graph_begin(kjb_context*) { return 0; }
+int kjb_graph_end(kjb_context*) { return 0; }
+#else
+int kjb_graph_begin(kjb_context* c) {
+    if (c->graph_capturing) return c->fail("kjb_graph_begin: already recording");
+    if (cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeRelaxed) != cudaSuccess) { cudaGetLastError(); return c->fail("kjb_graph_begin: cudaStreamBeginCapture failed"); }
+    c->graph_capturing = true;
+    return 0;
+}
+int kjb_graph_end(kjb_context* c) {
+    if (!c->graph_capturing) return c->fail("kjb_graph_end: not recording");
+    cudaGraph_t g = nullptr;
+    const cudaError_t e = cudaStreamEndCapture(c->stream, &g);
+    c->graph_capturing = false;
+    if (e != cudaSuccess || !g) { cudaGetLastError(); return c->fail(std::string("kjb_graph_end: the recording was invalidated (") + cudaGetErrorString(e) + "): a pass inside the pair synchronised or touched another queue"); }
+    if (c->graph_exec) {
+        cudaGraphExecUpdateResultInfo info;
+        if (cudaGraphExecUpdate(c->graph_exec, g, &info) != cudaSuccess) { cudaGetLastError(); cudaGraphExecDestroy(c->graph_exec); c->graph_exec = nullptr; }   // other pass list: new instance
+    }
+    if (!c->graph_exec) {
+        if (cudaGraphInstantiate(&c->graph_exec, g, 0) != cudaSuccess) { cudaGetLastError(); cudaGraphDestroy(g); c->graph_exec = nullptr; return c->fail("kjb_graph_end: cudaGraphInstantiate failed"); }
+        c->graph_instantiations++;
+    }
+    const cudaError_t le = cudaGraphLaunch(c->graph_exec, c->stream);
+    cudaGraphDestroy(g);
+    if (le != cudaSuccess) return c->fail(std::string("kjb_graph_end: cudaGraphLaunch failed: ") + cudaGetErrorString(le));
+    c->graph_launches++;
+    return 0;
+}
+#endif
+int kjb_graph_stats(kjb_context* c, uint64_t out[2]) { out[0] = c->graph_launches; out[1] = c->graph_instantiations; return 0; }
+int kjb_tlas_stats(kjb_context* c, uint64_t out[2]) { out[0] = c->tlas_rebuilds; out[1] = c->tlas_refits; return 0; }
 int kjb_set_frame_constants(kjb_context* c, const kjb_frame_constants* fc, const kjb_triangle_light* lights, uint32_t n) {
     if (fc->triangle_light_count != n) return c->fail("kjb_set_frame_constants: triangle_light_count mismatch");
     c->g.fc = *fc; c->invalidate_positions();

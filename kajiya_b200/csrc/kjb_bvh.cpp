@@ -102,7 +102,7 @@ struct Builder {
 }  // namespace
 
 void build_bvh(const float* world_tris, const TriInfo* info, uint32_t tri_count, HostBvh& out) {
-    out.nodes.clear(); out.tris.clear(); out.info.assign(info, info + tri_count);
+    out.nodes.clear(); out.tris.clear(); out.parent.clear(); out.info.assign(info, info + tri_count);
     out.root_child = 0;
     if (tri_count == 0) { out.root_child = ~int32_t(0); out.tris.emplace_back(); /* one degenerate (all-zero) triangle never hits */ return; }
     Builder b; b.tris = world_tris; b.n = tri_count; b.out = &out;
@@ -119,6 +119,8 @@ void build_bvh(const float* world_tris, const TriInfo* info, uint32_t tri_count,
     out.nodes.reserve(tri_count);
     out.tris.reserve(tri_count);
     out.root_child = b.build(0, tri_count, all, call);
+    out.parent.assign(out.nodes.size(), -1);
+    for (size_t i = 0; i < out.nodes.size(); ++i) for (int k = 0; k < 2; ++k) if (out.nodes[i].child[k] >= 0) out.parent[size_t(out.nodes[i].child[k])] = int32_t(i << 1) | k;
 }
 
 }  // namespace kjb

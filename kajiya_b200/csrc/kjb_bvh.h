@@ -24,6 +24,7 @@ struct HostBvh {
     std::vector<BvhTri> tris;        // leaf order
     std::vector<TriInfo> info;       // by gid
     int32_t root_child = 0;          // encoded like a child reference (a 1-leaf scene has no inner node)
+    std::vector<int32_t> parent;     // per inner node: (parent node << 1) | child slot, -1 for the root — what the device refit walks upwards
 };
 
 // world_tris: gid-ordered (instance-major) triangles as (v0, v1, v2) float[9].  Binned-SAH build, leaves of <= 4 triangles.

@@ -4,6 +4,9 @@
 // never loaded by kajiya_b200, and reports itself as "emu-cpu".
 #pragma once
 #include "kjb_trace.cuh"
+#include "kjb_tile.cuh"
+#include <map>
+#include <tuple>
 #include <string>
 #include <vector>
 #include <cstdio>
@@ -29,6 +32,9 @@ struct kjb_context {
     std::vector<uint8_t> h_vertices; std::vector<kjb_gpu_mesh> h_meshes; std::vector<uint32_t> h_index_counts;
     kjb_instance* d_instances = nullptr; std::vector<kjb_instance> h_instances; bool tlas_valid = false;
     kjb::BvhNode* d_nodes = nullptr; kjb::BvhTri* d_tris = nullptr; kjb::TriInfo* d_tri_info = nullptr;
+    // device refit of the acceleration structure when only instance transforms change ("rebuild tlas" every frame, kjb_api.cu)
+    int32_t* d_node_parent = nullptr; uint32_t* d_refit_count = nullptr; float* d_slot_box = nullptr; float* d_tri_box = nullptr; uint32_t node_count = 0, slot_count = 0;
+    uint64_t tlas_refits = 0, tlas_rebuilds = 0;
     uint8_t* d_tex_data = nullptr; uint4* d_tex_desc = nullptr; uint32_t tex_count = 0;
     kjb_triangle_light* d_lights = nullptr; uint32_t lights_capacity = 0;
     unsigned long long* d_ray_counters = nullptr;
@@ -47,7 +53,14 @@ struct kjb_context {
     }
 #endif
 
+#if !defined(KJB_EMU)
+    // CUDA Graph replay of a frame (kjb_graph_begin / kjb_graph_end): the instance kept between frames, updated in place while the topology holds
+    cudaGraphExec_t graph_exec = nullptr; bool graph_capturing = false;
+#endif
+    uint64_t graph_launches = 0, graph_instantiations = 0;
     kjb::Globals g;   // host copy, passed by value to every kernel
+    // tensor maps of the images the tiled kernels stage through TMA, one per (image, box): built on first use, dropped when the image is freed
+    std::map<std::tuple<const void*, uint32_t, uint32_t, uint32_t, uint32_t, uint32_t>, kjb::TileSource> tile_sources;
 
     // multi-GPU transport (tile-sharded frames)
     kjb_allgather_fn ag_fn = nullptr; void* ag_user = nullptr; uint32_t rank = 0, nranks = 1; void* nccl_comm = nullptr;
@@ -87,8 +100,11 @@ inline const char* dev_check(kjb_context*) { return nullptr; }
 inline void* dev_alloc(size_t n) {
     void* p = nullptr;
     if (cudaMalloc(&p, n ? n : 1) != cudaSuccess) return nullptr;
-    cudaMemset(p, 0, n ? n : 1);
-    cudaDeviceSynchronize();
+    // zero-fill on a stream of its own and wait for THAT stream only: allocation also happens lazily inside a frame that is being captured into
+    // a CUDA graph (relaxed capture mode), where touching the legacy stream or synchronising the device would invalidate the capture
+    static thread_local cudaStream_t setup = nullptr;
+    if (!setup && cudaStreamCreateWithFlags(&setup, cudaStreamNonBlocking) != cudaSuccess) { setup = nullptr; cudaFree(p); return nullptr; }
+    if (cudaMemsetAsync(p, 0, n ? n : 1, setup) != cudaSuccess || cudaStreamSynchronize(setup) != cudaSuccess) { cudaFree(p); return nullptr; }
     return p;
 }
 inline void dev_free(void* p) { if (p) cudaFree(p); }
@@ -103,6 +119,11 @@ inline int dev_sync(kjb_context* c) {   // every queue of the context
 }
 inline const char* dev_check(kjb_context*) { cudaError_t e = cudaGetLastError(); return e == cudaSuccess ? nullptr : cudaGetErrorString(e); }
 #endif
+
+inline uint32_t texel_bytes(uint32_t f);
+// TileSource of `img` for tiles of box_w x box_h texels (kjb_tile.cuh).  use_tma = 0 when the image cannot be described to the copy engine
+// (row pitch or base not 16-byte aligned, driver entry point missing): the kernels then stage the same tile with guarded loads.
+kjb::TileSource tile_source(kjb_context* c, const kjb_image& img, uint32_t box_w, uint32_t box_h);
 
 inline uint32_t texel_bytes(uint32_t f) {
     switch (f) {
@@ -145,6 +166,11 @@ inline bool check_img(kjb_context* c, const kjb_image& i, uint32_t fmt, const ch
 #define KJB_LAUNCH_ORDERED KJB_LAUNCH
 #endif
 #define KJB_DIMS(...) __VA_ARGS__
+// Ray-tracing passes: 8 x 16 pixel blocks, so that a warp (32 consecutive threads) is an 8 x 4 pixel patch — compact footprints keep the
+// lanes of a warp on neighbouring BVH nodes and make hit / miss shading branch together more often than 32 x 1 or 16 x 2 strips.  The
+// serial twins (and the oracle's serial schedule, oracle/kj_ctx.h) walk the pixels in the same block order.
+#define KJB_RAY_BX 8
+#define KJB_RAY_BY 16
 // every kernel's last parameter is `Rows kjb_rows`: the row range of its grid this launch covers (tile sharding)
 #define KJB_ROWS(ctx, H) const kjb::Rows kjb__rows = (ctx)->rows_for(H)
 #define KJB_GRID2D(W, H, BX, BY) dim3(((W) + (BX) - 1) / (BX), (unsigned(kjb__rows.y1 - kjb__rows.y0) + (BY) - 1) / (BY), 1), dim3((BX), (BY), 1)

@@ -369,7 +369,7 @@ int kjb_pass_trace_sun_shadow_mask(kjb_context* c, const kjb_trace_sun_shadow_ma
     CHK(a->output_tex, KJB_FMT_R8_UNORM, "output_tex"); CHKE(a->depth_tex, KJB_FMT_R32_FLOAT, "depth_tex", W, H); CHKE(a->geometric_normal_tex, KJB_FMT_A2R10G10B10_UNORM, "geometric_normal_tex", W, H);
     if (!c->tlas_valid) return c->fail("trace shadow mask: no acceleration structure (call kjb_rebuild_tlas)");
     KJB_ROWS(c, H);
-    KJB_LAUNCH(c, k_trace_sun_shadow_mask, KJB_GRID2D(W, H, 16, 8), c->g, img_ro(a->depth_tex), img_ro(a->geometric_normal_tex), img_rw(a->output_tex));
+    KJB_LAUNCH(c, k_trace_sun_shadow_mask, KJB_GRID2D(W, H, KJB_RAY_BX, KJB_RAY_BY), c->g, img_ro(a->depth_tex), img_ro(a->geometric_normal_tex), img_rw(a->output_tex));
     KJB_PASS_EPILOGUE(c, P);
 }
 int kjb_pass_light_gbuffer(kjb_context* c, const kjb_light_gbuffer_args* a) {
@@ -441,7 +441,7 @@ int kjb_pass_sample_lights(kjb_context* c, const kjb_sample_lights_args* a) {
     if (c->g.fc.triangle_light_count == 0) return c->fail("sample lights: the scene has no triangle lights");
     if (!c->tlas_valid) return c->fail("sample lights: no acceleration structure (call kjb_rebuild_tlas)");
     KJB_ROWS(c, H);
-    KJB_LAUNCH(c, k_sample_lights, KJB_GRID2D(W, H, 16, 8), c->g, img_ro(a->depth_tex), img_rw(a->out0_tex), img_rw(a->out1_tex), img_rw(a->out2_tex), F4A(a->gbuffer_tex_size));
+    KJB_LAUNCH(c, k_sample_lights, KJB_GRID2D(W, H, KJB_RAY_BX, KJB_RAY_BY), c->g, img_ro(a->depth_tex), img_rw(a->out0_tex), img_rw(a->out1_tex), img_rw(a->out2_tex), F4A(a->gbuffer_tex_size));
     KJB_PASS_EPILOGUE(c, P);
 }
 int kjb_pass_spatial_reuse_lights(kjb_context* c, const kjb_spatial_reuse_lights_args* a) {

@@ -218,7 +218,7 @@ int kjb_pass_raster_gbuffer(kjb_context* c, const kjb_raster_gbuffer_args* a) {
         d_prev = c->d_prev_instances;
     }
     KJB_ROWS(c, H);
-    KJB_LAUNCH(c, k_raster_gbuffer, KJB_GRID2D(W, H, 16, 8), c->g, img_rw(a->geometric_normal_out), img_rw(a->gbuffer_out), img_rw(a->depth_out), img_rw(a->velocity_out), d_prev, d_prev ? a->prev_instance_count : 0u);
+    KJB_LAUNCH(c, k_raster_gbuffer, KJB_GRID2D(W, H, KJB_RAY_BX, KJB_RAY_BY), c->g, img_rw(a->geometric_normal_out), img_rw(a->gbuffer_out), img_rw(a->depth_out), img_rw(a->velocity_out), d_prev, d_prev ? a->prev_instance_count : 0u);
     KJB_PASS_EPILOGUE(c, P);
 }
 int kjb_pass_reprojection_map(kjb_context* c, const kjb_reprojection_map_args* a) {

@@ -186,10 +186,10 @@ KJB_KERNEL(128) k_rtdgi_validate(Globals g, Img half_view_normal_tex, Img depth_
     rtdgi_validate_px(g, half_view_normal_tex, depth_tex, reprojected_gi_tex, reservoir_tex, reservoir_ray_history_tex, sky_cube_tex, irradiance_history_tex, ray_orig_history_tex, out_tex, gts, ircache, x, y);
 }
 // `_serial` twins (kjb_set_debug_serial, see kjb_passes_ircache.cu): one thread walks the pixels in the launch order of the
-// parallel kernel — 16x8 blocks row-major, pixels row-major inside a block
+// parallel kernel — 8x16 blocks row-major, pixels row-major inside a block
 #define KJB_SERIAL_TILES(W, H, ...) do { if (blockIdx.x | blockIdx.y | threadIdx.x | threadIdx.y) return; \
-        for (int by = kjb_rows.y0; by < kjb_rows.y1; by += 8) for (int bx = 0; bx < (W); bx += 16) \
-            for (int y = by; y < by + 8 && y < kjb_rows.y1 && y < (H); ++y) for (int x = bx; x < bx + 16 && x < (W); ++x) { __VA_ARGS__; } } while (0)
+        for (int by = kjb_rows.y0; by < kjb_rows.y1; by += KJB_RAY_BY) for (int bx = 0; bx < (W); bx += KJB_RAY_BX) \
+            for (int y = by; y < by + KJB_RAY_BY && y < kjb_rows.y1 && y < (H); ++y) for (int x = bx; x < bx + KJB_RAY_BX && x < (W); ++x) { __VA_ARGS__; } } while (0)
 KJB_KERNEL(32) k_rtdgi_validate_serial(Globals g, Img half_view_normal_tex, Img depth_tex, Img reprojected_gi_tex, ImgW reservoir_tex, Img reservoir_ray_history_tex,
                                        Img sky_cube_tex, ImgW irradiance_history_tex, Img ray_orig_history_tex, ImgW out_tex, float4 gts, IrcacheBufs ircache, Rows kjb_rows) {
     KJB_SERIAL_TILES(out_tex.w, out_tex.h, rtdgi_validate_px(g, half_view_normal_tex, depth_tex, reprojected_gi_tex, reservoir_tex, reservoir_ray_history_tex, sky_cube_tex, irradiance_history_tex,
@@ -246,10 +246,10 @@ KJB_KERNEL(32) k_rtdgi_trace_serial(Globals g, Img half_view_normal_tex, Img dep
 
 // ------------------------------------------------------------------ D5 temporal_validity_integrate.hlsl:21-119
 // The shader exchanges values between lanes of its 8x8 group (WaveReadLaneAt ^2, ^16, ^1, ^8; lane = x + 8*y in 32-wide waves):
-// partners are pixels (x^2,y), (x,y^2), (x^1,y), (x,y^1).  A 32x8 block whose origin is a multiple of 4 rows holds every partner,
-// so each thread computes ITS pre-exchange blur / edge value once (threads past the image edge included, like the shader's
-// out-of-range lanes), parks it in shared memory, and the exchange is two shared-memory reads.  The 5x5 blur reads the R8 input
-// from a (32+4)x(8+4) tile decoded once per texel.
+// partners are pixels (x^2,y), (x,y^2), (x^1,y), (x,y^1).  Blocks are 8 x 32 threads whose rows start at a multiple of 4, so a warp is
+// exactly the shader's wave — an 8x4 pixel patch with lane = x + 8*(y & 3) — and the four exchanges are warp shuffles (SHFL.BFLY 2, 16,
+// 1, 8 and their combinations); every thread computes ITS pre-exchange blur / edge value first (threads past the image edge included,
+// like the shader's out-of-range lanes).  The 5x5 blur reads the R8 input from a (8+4)x(32+4) tile decoded once per texel.
 struct Weights25v { float w[25]; float w_sum; };   // w[(yy+2)*5+(xx+2)] = exp2(-0.1 r^2) and their float sum in tap order, host-evaluated
 KJB_DEV float d5_edge(const Img& reprojection_tex, const Img& half_depth_tex, int x, int y) {
     const float center_depth = ld_r32f(half_depth_tex, x, y);
@@ -262,31 +262,33 @@ KJB_DEV float d5_edge(const Img& reprojection_tex, const Img& half_depth_tex, in
     }
     return edge;
 }
+#define D5_BX 8
+#define D5_BY 32
 KJB_KERNEL(256) k_rtdgi_validity_integrate(Globals g, Img input_tex, Img history_tex, Img reprojection_tex, Img half_depth_tex, ImgW output_tex, float4 gts, Weights25v wt, Rows kjb_rows) {
-    __shared__ float in_tile[12][36];
-    __shared__ float blur_s[8][32], edge_s[8][32];
+    __shared__ float in_tile[D5_BY + 4][D5_BX + 4];
     const int tx = int(threadIdx.x), ty = int(threadIdx.y);
-    const int bx0 = int(blockIdx.x) * 32, by0 = (kjb_rows.y0 & ~3) + int(blockIdx.y) * 8;
+    const int bx0 = int(blockIdx.x) * D5_BX, by0 = (kjb_rows.y0 & ~3) + int(blockIdx.y) * D5_BY;
     const int x = bx0 + tx, y = by0 + ty;
-    for (int i = ty * 32 + tx; i < 12 * 36; i += 256) {
-        const int lx = i % 36, ly = i / 36;
+    for (int i = ty * D5_BX + tx; i < (D5_BY + 4) * (D5_BX + 4); i += D5_BX * D5_BY) {
+        const int lx = i % (D5_BX + 4), ly = i / (D5_BX + 4);
         in_tile[ly][lx] = ld_r8u(input_tex, bx0 + lx - 2, by0 + ly - 2);
     }
     __syncthreads();
+    float blur, edge;
     {
         float acc = 0.0f;
         for (int yy = 0; yy < 5; ++yy) for (int xx = 0; xx < 5; ++xx) acc = mad(in_tile[ty + yy][tx + xx], wt.w[yy * 5 + xx], acc);
-        blur_s[ty][tx] = acc / wt.w_sum;
-        edge_s[ty][tx] = d5_edge(reprojection_tex, half_depth_tex, x, y);
+        blur = acc / wt.w_sum;
+        edge = d5_edge(reprojection_tex, half_depth_tex, x, y);
     }
-    __syncthreads();
+    // lane = tx + 8 * (ty & 3): x^2 -> lane^2, y^2 -> lane^16, x^1 -> lane^1, y^1 -> lane^8
+    const float b0 = kjb_lerp(blur, warp_xor(blur, 2), 0.5f);
+    const float b1 = kjb_lerp(warp_xor(blur, 16), warp_xor(blur, 18), 0.5f);
+    const float e0 = kjb_max(edge, warp_xor(edge, 1));
+    const float e1 = kjb_max(warp_xor(edge, 8), warp_xor(edge, 9));
     if (x >= output_tex.w || y >= output_tex.h || y < kjb_rows.y0 || y >= kjb_rows.y1) return;
-    const float b0 = kjb_lerp(blur_s[ty][tx], blur_s[ty][tx ^ 2], 0.5f);
-    const float b1 = kjb_lerp(blur_s[ty ^ 2][tx], blur_s[ty ^ 2][tx ^ 2], 0.5f);
     float inv = kjb_lerp(b0, b1, 0.5f);
     inv = kjb_smoothstep(0.0f, 1.0f, inv);
-    const float e0 = kjb_max(edge_s[ty][tx], edge_s[ty][tx ^ 1]);
-    const float e1 = kjb_max(edge_s[ty ^ 1][tx], edge_s[ty ^ 1][tx ^ 1]);
     inv += kjb_max(e0, e1);
     inv = kjb_saturate(inv);
     const float4 reproj = ld_rgba16s(reprojection_tex, x * 2, y * 2);
@@ -468,7 +470,26 @@ KJB_DEV float normal_influence_nonlinearity(float x, float b) { return x < -b ? 
 #endif
 KJB_KERNEL_OCC(256, KJB_OCC_RESTIR_SPATIAL) k_rtdgi_restir_spatial(Globals g, Img reservoir_input_tex, Img half_view_normal_tex, Img half_depth_tex, Img half_ssao_tex, Img temporal_reservoir_packed_tex,
                                        ImgW reservoir_output_tex, float4 gts, float4 ots, uint32_t pass_idx, uint32_t perform_occlusion_raymarch, uint32_t importance_only, PosView pos_a, PosView pos_b, Rows kjb_rows) {
+    // The tap angles `(sample_i + ang_offset) * GOLDEN_ANGLE` depend on the pixel only through its 8x8 (pass 0) / 4x4 (later passes) screen tile
+    // (ang_offset = hash of the tile): a 32x8 block covers at most 4x2 / 8x3 such tiles, so the block evaluates each tile's 8 / 5 sin-cos pairs
+    // once into shared memory (<= 120 kjb_sincos per block instead of 8 / 5 per pixel) and every pixel reads its tile's row.
+    __shared__ float s_sn[24 * 8], s_cs[24 * 8];
+    const uint32_t sample_count = pass_idx == 0 ? 8u : 5u;
+    const int tshift = pass_idx == 0 ? 3 : 2;
+    const int bx0 = int(blockIdx.x * blockDim.x), by0 = kjb_rows.y0 + int(blockIdx.y * blockDim.y);
+    const int tiles_x = int(blockDim.x) >> tshift, tile_y0 = by0 >> tshift;
+    {
+        const int tiles_y = ((by0 + int(blockDim.y) - 1) >> tshift) - tile_y0 + 1;
+        for (int i = int(threadIdx.y * blockDim.x + threadIdx.x); i < tiles_x * tiles_y * int(sample_count); i += int(blockDim.x * blockDim.y)) {
+            const int sample_i = i % int(sample_count), tile = i / int(sample_count);
+            const uint32_t tsx = uint32_t((bx0 >> tshift) + tile % tiles_x), tsy = uint32_t(tile_y0 + tile / tiles_x);
+            const float ang_offset_t = u01(hash3(tsx, tsy, g.fc.frame_index * 2u + pass_idx)) * KJB_PI_F * 2;
+            kjb_sincos((float(sample_i) + ang_offset_t) * KJB_GOLDEN_ANGLE, &s_sn[tile * 8 + sample_i], &s_cs[tile * 8 + sample_i]);
+        }
+        __syncthreads();
+    }
     KJB_PX; if (x >= reservoir_output_tex.w || y >= reservoir_output_tex.h) return;
+    const int my_tile = ((y >> tshift) - tile_y0) * tiles_x + ((x >> tshift) - (bx0 >> tshift));
     const kjb_view_constants& vc = g.fc.view_constants;
     const int2 hso = halfres_subsample_offset(g.fc.frame_index);
     const float s4[4] = {gts.x, gts.y, gts.z, gts.w};
@@ -494,14 +515,10 @@ KJB_KERNEL_OCC(256, KJB_OCC_RESTIR_SPATIAL) k_rtdgi_restir_spatial(Globals g, Im
     const float2 dist_to_edge_xy = vmin(f2(float(x), float(y)), f2(ots.x, ots.y) - f2(float(x), float(y)));
     const float allow_edge_overstep = center_r.M < 10 ? 100.0f : 1.25f;
     const float2 kernel_radius = vmin(f2(max_kernel_radius), dist_to_edge_xy * allow_edge_overstep);
-    const uint32_t sample_count = pass_idx == 0 ? 8u : 5u;
-    const uint32_t sx = pass_idx == 0 ? (uint32_t(x) >> 3) : (uint32_t(x) >> 2), sy = pass_idx == 0 ? (uint32_t(y) >> 3) : (uint32_t(y) >> 2);
-    const float ang_offset = u01(hash3(sx, sy, g.fc.frame_index * 2u + pass_idx)) * KJB_PI_F * 2;
 
     for (uint32_t sample_i = 0; sample_i < sample_count; ++sample_i) {
-        const float ang = (float(sample_i) + ang_offset) * KJB_GOLDEN_ANGLE;
         const float2 radius = 0 == sample_i ? f2(0.0f) : (kjb_pow((float(sample_i) + sample_radius_offset) / float(sample_count), 0.5f) * kernel_radius);
-        float sn, cs; kjb_sincos(ang, &sn, &cs);
+        const float sn = s_sn[my_tile * 8 + int(sample_i)], cs = s_cs[my_tile * 8 + int(sample_i)];
         const float2 off_f = f2(cs, sn) * radius;
         const int rx = x + kjb_cvt_i32(off_f.x), ry = y + kjb_cvt_i32(off_f.y);
         const bool is_center_sample = sample_i == 0;
@@ -854,10 +871,10 @@ int kjb_pass_rtdgi_validate(kjb_context* c, const kjb_rtdgi_validate_args* a) {
         KJB_LAUNCH(c, k_rtdgi_validate_serial, KJB_DIMS(dim3(1), dim3(32)), c->g, img_ro(a->half_view_normal_tex), img_ro(a->depth_tex), img_ro(a->reprojected_gi_tex), img_rw(a->reservoir_tex),
                img_ro(a->reservoir_ray_history_tex), img_ro(a->sky_cube_tex), img_rw(a->irradiance_history_tex), img_ro(a->ray_orig_history_tex), img_rw(a->rt_history_invalidity_out_tex), F4A(a->gbuffer_tex_size), ircache);
     else if (ircache.bound())
-        KJB_LAUNCH_ORDERED(c, k_rtdgi_validate, KJB_GRID2D(W, H, 16, 8), c->g, img_ro(a->half_view_normal_tex), img_ro(a->depth_tex), img_ro(a->reprojected_gi_tex), img_rw(a->reservoir_tex),
+        KJB_LAUNCH_ORDERED(c, k_rtdgi_validate, KJB_GRID2D(W, H, KJB_RAY_BX, KJB_RAY_BY), c->g, img_ro(a->half_view_normal_tex), img_ro(a->depth_tex), img_ro(a->reprojected_gi_tex), img_rw(a->reservoir_tex),
                img_ro(a->reservoir_ray_history_tex), img_ro(a->sky_cube_tex), img_rw(a->irradiance_history_tex), img_ro(a->ray_orig_history_tex), img_rw(a->rt_history_invalidity_out_tex), F4A(a->gbuffer_tex_size), ircache);
     else
-        KJB_LAUNCH(c, k_rtdgi_validate, KJB_GRID2D(W, H, 16, 8), c->g, img_ro(a->half_view_normal_tex), img_ro(a->depth_tex), img_ro(a->reprojected_gi_tex), img_rw(a->reservoir_tex),
+        KJB_LAUNCH(c, k_rtdgi_validate, KJB_GRID2D(W, H, KJB_RAY_BX, KJB_RAY_BY), c->g, img_ro(a->half_view_normal_tex), img_ro(a->depth_tex), img_ro(a->reprojected_gi_tex), img_rw(a->reservoir_tex),
                img_ro(a->reservoir_ray_history_tex), img_ro(a->sky_cube_tex), img_rw(a->irradiance_history_tex), img_ro(a->ray_orig_history_tex), img_rw(a->rt_history_invalidity_out_tex), F4A(a->gbuffer_tex_size), ircache);
     KJB_PASS_EPILOGUE(c, P);
 }
@@ -875,11 +892,11 @@ int kjb_pass_rtdgi_trace(kjb_context* c, const kjb_rtdgi_trace_args* a) {
                img_rw(a->candidate_irradiance_out_tex), img_rw(a->candidate_normal_out_tex), img_rw(a->candidate_hit_out_tex), img_ro(a->rt_history_invalidity_in_tex), img_rw(a->rt_history_invalidity_out_tex),
                F4A(a->gbuffer_tex_size), ircache);
     else if (ircache.bound())
-        KJB_LAUNCH_ORDERED(c, k_rtdgi_trace, KJB_GRID2D(W, H, 16, 8), c->g, img_ro(a->half_view_normal_tex), img_ro(a->depth_tex), img_ro(a->reprojected_gi_tex), img_ro(a->reprojection_tex), img_ro(a->sky_cube_tex),
+        KJB_LAUNCH_ORDERED(c, k_rtdgi_trace, KJB_GRID2D(W, H, KJB_RAY_BX, KJB_RAY_BY), c->g, img_ro(a->half_view_normal_tex), img_ro(a->depth_tex), img_ro(a->reprojected_gi_tex), img_ro(a->reprojection_tex), img_ro(a->sky_cube_tex),
                img_rw(a->candidate_irradiance_out_tex), img_rw(a->candidate_normal_out_tex), img_rw(a->candidate_hit_out_tex), img_ro(a->rt_history_invalidity_in_tex), img_rw(a->rt_history_invalidity_out_tex),
                F4A(a->gbuffer_tex_size), ircache);
     else
-        KJB_LAUNCH(c, k_rtdgi_trace, KJB_GRID2D(W, H, 16, 8), c->g, img_ro(a->half_view_normal_tex), img_ro(a->depth_tex), img_ro(a->reprojected_gi_tex), img_ro(a->reprojection_tex), img_ro(a->sky_cube_tex),
+        KJB_LAUNCH(c, k_rtdgi_trace, KJB_GRID2D(W, H, KJB_RAY_BX, KJB_RAY_BY), c->g, img_ro(a->half_view_normal_tex), img_ro(a->depth_tex), img_ro(a->reprojected_gi_tex), img_ro(a->reprojection_tex), img_ro(a->sky_cube_tex),
                img_rw(a->candidate_irradiance_out_tex), img_rw(a->candidate_normal_out_tex), img_rw(a->candidate_hit_out_tex), img_ro(a->rt_history_invalidity_in_tex), img_rw(a->rt_history_invalidity_out_tex),
                F4A(a->gbuffer_tex_size), ircache);
     KJB_PASS_EPILOGUE(c, P);
@@ -892,7 +909,7 @@ int kjb_pass_rtdgi_validity_integrate(kjb_context* c, const kjb_rtdgi_validity_i
     for (int yy = -2; yy <= 2; ++yy) for (int xx = -2; xx <= 2; ++xx) { const float w = kjb_exp2(-0.1f * float(xx * xx + yy * yy)); wt.w[(yy + 2) * 5 + (xx + 2)] = w; wt.w_sum += w; }
     KJB_ROWS(c, H);
     // block rows start at a multiple of 4 so that the (y^1, y^2) exchange partners share the block
-    KJB_LAUNCH_SYNC(c, k_rtdgi_validity_integrate, KJB_DIMS(dim3((W + 31) / 32, unsigned(kjb__rows.y1 - (kjb__rows.y0 & ~3) + 7) / 8, 1), dim3(32, 8, 1)), c->g, img_ro(a->input_tex), img_ro(a->history_tex), img_ro(a->reprojection_tex), img_ro(a->half_depth_tex), img_rw(a->output_tex),
+    KJB_LAUNCH_SYNC(c, k_rtdgi_validity_integrate, KJB_DIMS(dim3((W + D5_BX - 1) / D5_BX, unsigned(kjb__rows.y1 - (kjb__rows.y0 & ~3) + D5_BY - 1) / D5_BY, 1), dim3(D5_BX, D5_BY, 1)), c->g, img_ro(a->input_tex), img_ro(a->history_tex), img_ro(a->reprojection_tex), img_ro(a->half_depth_tex), img_rw(a->output_tex),
                F4A(a->gbuffer_tex_size), wt);
     KJB_PASS_EPILOGUE(c, P);
 }
@@ -940,7 +957,7 @@ int kjb_pass_rtdgi_restir_spatial(kjb_context* c, const kjb_rtdgi_restir_spatial
     const PosView pos_a = ensure_positions(c, c->pos_a, c->epoch_a, a->half_depth_tex, false, a->gbuffer_tex_size);
     const PosView pos_b = ensure_positions(c, c->pos_b, c->epoch_b, a->temporal_reservoir_packed_tex, true, a->gbuffer_tex_size);
     KJB_ROWS(c, H);
-    KJB_LAUNCH(c, k_rtdgi_restir_spatial, KJB_GRID2D(W, H, 32, 8), c->g, img_ro(a->reservoir_input_tex), img_ro(a->half_view_normal_tex), img_ro(a->half_depth_tex), img_ro(a->half_ssao_tex),
+    KJB_LAUNCH_SYNC(c, k_rtdgi_restir_spatial, KJB_GRID2D(W, H, 32, 8), c->g, img_ro(a->reservoir_input_tex), img_ro(a->half_view_normal_tex), img_ro(a->half_depth_tex), img_ro(a->half_ssao_tex),
                img_ro(a->temporal_reservoir_packed_tex), img_rw(a->reservoir_output_tex), F4A(a->gbuffer_tex_size), F4A(a->output_tex_size), a->spatial_reuse_pass_idx, a->perform_occlusion_raymarch,
                a->occlusion_raymarch_importance_only, pos_a, pos_b);
     KJB_PASS_EPILOGUE(c, P);
@@ -951,7 +968,7 @@ int kjb_pass_rtdgi_restir_check(kjb_context* c, const kjb_rtdgi_restir_check_arg
     CHKE(a->temporal_reservoir_packed_tex, KJB_FMT_RGBA32_UINT, "temporal_reservoir_packed_tex", W, H);
     if (!c->tlas_valid) return c->fail("restir check: no acceleration structure (call kjb_rebuild_tlas)");
     KJB_ROWS(c, H);
-    KJB_LAUNCH(c, k_rtdgi_restir_check, KJB_GRID2D(W, H, 16, 8), c->g, img_ro(a->half_depth_tex), img_ro(a->temporal_reservoir_packed_tex), img_rw(a->reservoir_input_tex), F4A(a->gbuffer_tex_size));
+    KJB_LAUNCH(c, k_rtdgi_restir_check, KJB_GRID2D(W, H, KJB_RAY_BX, KJB_RAY_BY), c->g, img_ro(a->half_depth_tex), img_ro(a->temporal_reservoir_packed_tex), img_rw(a->reservoir_input_tex), F4A(a->gbuffer_tex_size));
     KJB_PASS_EPILOGUE(c, P);
 }
 int kjb_pass_rtdgi_restir_resolve(kjb_context* c, const kjb_rtdgi_restir_resolve_args* a) {

@@ -1,6 +1,6 @@
 // Ray-traced specular reflections (rtr) as sm_100a kernels — one kernel per render-graph pass of
 // crates/lib/kajiya/src/renderers/rtr.rs, shader sources under /root/reference/assets/shaders/rtr/ (settings frozen to rtr_settings.hlsl).
-// Thread mapping as in kjb_passes_rtdgi.cu: 32x8 blocks on the pass's pixel grid, 16x8 for the two ray-tracing passes.
+// Thread mapping as in kjb_passes_rtdgi.cu: 32x8 blocks on the pass's pixel grid, 8x16 for the two ray-tracing passes (a warp = an 8x4 pixel patch).
 #include "kjb_context.h"
 #include "kjb_ircache.cuh"
 
@@ -171,8 +171,8 @@ KJB_KERNEL(128) k_rtr_trace(Globals g, RtrTraceImgs t, BlueNoiseSamplerTables bn
     rtr_trace_px(g, t, bn, gts, reuse_rtdgi_rays, ircache, x, y);
 }
 #define KJB_SERIAL_TILES(W, H, ...) do { if (blockIdx.x | blockIdx.y | threadIdx.x | threadIdx.y) return; \
-        for (int by = kjb_rows.y0; by < kjb_rows.y1; by += 8) for (int bx = 0; bx < (W); bx += 16) \
-            for (int y = by; y < by + 8 && y < kjb_rows.y1 && y < (H); ++y) for (int x = bx; x < bx + 16 && x < (W); ++x) { __VA_ARGS__; } } while (0)
+        for (int by = kjb_rows.y0; by < kjb_rows.y1; by += KJB_RAY_BY) for (int bx = 0; bx < (W); bx += KJB_RAY_BX) \
+            for (int y = by; y < by + KJB_RAY_BY && y < kjb_rows.y1 && y < (H); ++y) for (int x = bx; x < bx + KJB_RAY_BX && x < (W); ++x) { __VA_ARGS__; } } while (0)
 KJB_KERNEL(32) k_rtr_trace_serial(Globals g, RtrTraceImgs t, BlueNoiseSamplerTables bn, float4 gts, uint32_t reuse_rtdgi_rays, IrcacheBufs ircache, Rows kjb_rows) {
     KJB_SERIAL_TILES(t.out0_tex.w, t.out0_tex.h, rtr_trace_px(g, t, bn, gts, reuse_rtdgi_rays, ircache, x, y));
 }
@@ -263,7 +263,10 @@ KJB_DEV void find_best_reprojection_in_neighborhood(const Globals& g, const RtrR
         if (d < best_dist) { best_dist = d; best_px = i2(sx, sy); }
     }
 }
-KJB_KERNEL(256) k_rtr_restir_temporal(Globals g, RtrRestirTemporalImgs t, float4 gts, Rows kjb_rows) {
+#ifndef KJB_OCC_RTR_RESTIR_TEMPORAL
+#define KJB_OCC_RTR_RESTIR_TEMPORAL 1
+#endif
+KJB_KERNEL_OCC(256, KJB_OCC_RTR_RESTIR_TEMPORAL) k_rtr_restir_temporal(Globals g, RtrRestirTemporalImgs t, float4 gts, Rows kjb_rows) {
     KJB_PX; if (x >= t.irradiance_out_tex.w || y >= t.irradiance_out_tex.h) return;
     const kjb_view_constants& vc = g.fc.view_constants;
     const int2 hso = halfres_subsample_offset(g.fc.frame_index);
@@ -400,7 +403,13 @@ KJB_KERNEL(256) k_rtr_restir_temporal(Globals g, RtrRestirTemporalImgs t, float4
 
 // ------------------------------------------------------------------ R4 resolve.hlsl:78-663 (USE_RESTIR, BORROW_SAMPLES, CUT_CORNERS_IN_MATH)
 struct RtrResolveImgs { Img gbuffer_tex, depth_tex, hit1_tex, reprojection_tex, half_view_normal_tex, ray_len_history_tex, restir_irradiance_tex, restir_ray_tex, restir_reservoir_tex, restir_ray_orig_tex; ImgW output_tex, ray_len_output_tex; };
-KJB_KERNEL(256) k_rtr_resolve(Globals g, RtrResolveImgs t, float4 ots, float radius_sample_mult, Rows kjb_rows) {
+#ifndef KJB_OCC_RTR_RESOLVE
+#define KJB_OCC_RTR_RESOLVE 2
+#endif
+// sin / cos of the tap angles `(sample_i + ang_offset) * GOLDEN_ANGLE + (px_idx_in_quad / 4) * TAU`: 4 quad slots x 8 taps = 32 distinct angles per FRAME
+// (ang_offset depends on the frame index only), so the host evaluates them once with the contract's kjb_sincos and every pixel looks its eight up
+struct ResolveTapAngles { float sn[32], cs[32]; };
+KJB_KERNEL_OCC(256, KJB_OCC_RTR_RESOLVE) k_rtr_resolve(Globals g, RtrResolveImgs t, float4 ots, float radius_sample_mult, ResolveTapAngles ta, Rows kjb_rows) {
     KJB_PX; if (x >= t.output_tex.w || y >= t.output_tex.h) return;
     const kjb_view_constants& vc = g.fc.view_constants;
     const int hpx = x / 2, hpy = y / 2;
@@ -454,7 +463,6 @@ KJB_KERNEL(256) k_rtr_resolve(Globals g, RtrResolveImgs t, float4 ots, float rad
     }
     const float4 blue = blue_noise_for_pixel(g, uint32_t(hpx) + 16u, uint32_t(hpy) + 16u, g.fc.frame_index);
     const float KERNEL_SHARPNESS = 0.666f;
-    const float ang_offset = float(g.fc.frame_index * 59u % 128u) * KJB_PLASTIC;
     const float RADIUS_INC_ON_FAIL = 0.25f;
     const int2 hso = halfres_subsample_offset(g.fc.frame_index); (void)hso;
     // per-pixel invariants of the tap loop
@@ -467,12 +475,11 @@ KJB_KERNEL(256) k_rtr_resolve(Globals g, RtrResolveImgs t, float4 ots, float rad
         const bool is_center_sample = sample_i == 8;
         int spx0, spy0;
         {
-            const float ang = (float(sample_i) + ang_offset) * KJB_GOLDEN_ANGLE + (float(px_idx_in_quad) / 4.0f) * KJB_TAU_F;
             float sample_i_with_jitter = sample_radius_accum;
             if (is_center_sample) sample_i_with_jitter = contrib_accum.w > 1e-8f ? blue.y : 0.0f;
             else sample_i_with_jitter += blue.y;
             const float radius = kjb_pow(sample_i_with_jitter, KERNEL_SHARPNESS) * radius_sample_mult;
-            float sn, cs; kjb_sincos(ang, &sn, &cs);
+            const float sn = ta.sn[px_idx_in_quad * 8u + uint32_t(sample_i - 1)], cs = ta.cs[px_idx_in_quad * 8u + uint32_t(sample_i - 1)];
             const float3 offset_ws = (cs * kernel_t1 + sn * kernel_t2) * radius;
             const float3 sample_cs = position_world_to_sample(vc, refl_ray_origin_ws + offset_ws);
             const float2 sample_uv = cs_to_uv(xy(sample_cs));
@@ -547,7 +554,10 @@ KJB_KERNEL(256) k_rtr_resolve(Globals g, RtrResolveImgs t, float4 ots, float rad
 
 // ------------------------------------------------------------------ R5 temporal_filter.hlsl:36-259
 struct RtrTemporalImgs { Img input_tex, history_tex, depth_tex, ray_len_tex, reprojection_tex, invalidity_tex, gbuffer_tex; ImgW output_tex; };
-KJB_KERNEL(256) k_rtr_temporal(Globals g, RtrTemporalImgs t, float4 ots, Rows kjb_rows) {
+#ifndef KJB_OCC_RTR_TEMPORAL
+#define KJB_OCC_RTR_TEMPORAL 4
+#endif
+KJB_KERNEL_OCC(256, KJB_OCC_RTR_TEMPORAL) k_rtr_temporal(Globals g, RtrTemporalImgs t, float4 ots, Rows kjb_rows) {
     KJB_PX; if (x >= t.output_tex.w || y >= t.output_tex.h) return;
     const kjb_view_constants& vc = g.fc.view_constants;
     const float ped = g.fc.pre_exposure_delta;
@@ -716,8 +726,8 @@ int kjb_pass_rtr_trace(kjb_context* c, const kjb_rtr_trace_args* a) {
     RtrTraceImgs t{img_ro(a->gbuffer_tex), img_ro(a->depth_tex), img_ro(a->rtdgi_tex), img_ro(a->sky_cube_tex), img_rw(a->out0_tex), img_rw(a->out1_tex), img_rw(a->out2_tex), img_rw(a->rng_out_tex)};
     KJB_ROWS(c, H);
     if (ircache.bound() && c->debug_serial) KJB_LAUNCH(c, k_rtr_trace_serial, KJB_DIMS(dim3(1), dim3(32)), c->g, t, bn, F4A(a->gbuffer_tex_size), a->reuse_rtdgi_rays, ircache);
-    else if (ircache.bound()) KJB_LAUNCH_ORDERED(c, k_rtr_trace, KJB_GRID2D(W, H, 16, 8), c->g, t, bn, F4A(a->gbuffer_tex_size), a->reuse_rtdgi_rays, ircache);
-    else KJB_LAUNCH(c, k_rtr_trace, KJB_GRID2D(W, H, 16, 8), c->g, t, bn, F4A(a->gbuffer_tex_size), a->reuse_rtdgi_rays, ircache);
+    else if (ircache.bound()) KJB_LAUNCH_ORDERED(c, k_rtr_trace, KJB_GRID2D(W, H, KJB_RAY_BX, KJB_RAY_BY), c->g, t, bn, F4A(a->gbuffer_tex_size), a->reuse_rtdgi_rays, ircache);
+    else KJB_LAUNCH(c, k_rtr_trace, KJB_GRID2D(W, H, KJB_RAY_BX, KJB_RAY_BY), c->g, t, bn, F4A(a->gbuffer_tex_size), a->reuse_rtdgi_rays, ircache);
     KJB_PASS_EPILOGUE(c, P);
 }
 int kjb_pass_rtr_validate(kjb_context* c, const kjb_rtr_validate_args* a) {
@@ -733,8 +743,8 @@ int kjb_pass_rtr_validate(kjb_context* c, const kjb_rtr_validate_args* a) {
     const int QW = int((W + 1) / 2), QH = int((H + 1) / 2);   // dispatched over half_res() of the half-res image (rtr.rs:229)
     kjb::Rows kjb__rows = c->rows_for(H); kjb__rows.y0 = kjb__rows.y0 / 2; kjb__rows.y1 = (kjb__rows.y1 + 1) / 2;   // scissor (half-res rows) -> quad rows
     if (ircache.bound() && c->debug_serial) KJB_LAUNCH(c, k_rtr_validate_serial, KJB_DIMS(dim3(1), dim3(32)), c->g, t, F4A(a->gbuffer_tex_size), ircache, QW, QH);
-    else if (ircache.bound()) KJB_LAUNCH_ORDERED(c, k_rtr_validate, KJB_GRID2D(QW, QH, 16, 8), c->g, t, F4A(a->gbuffer_tex_size), ircache, QW, QH);
-    else KJB_LAUNCH(c, k_rtr_validate, KJB_GRID2D(QW, QH, 16, 8), c->g, t, F4A(a->gbuffer_tex_size), ircache, QW, QH);
+    else if (ircache.bound()) KJB_LAUNCH_ORDERED(c, k_rtr_validate, KJB_GRID2D(QW, QH, KJB_RAY_BX, KJB_RAY_BY), c->g, t, F4A(a->gbuffer_tex_size), ircache, QW, QH);
+    else KJB_LAUNCH(c, k_rtr_validate, KJB_GRID2D(QW, QH, KJB_RAY_BX, KJB_RAY_BY), c->g, t, F4A(a->gbuffer_tex_size), ircache, QW, QH);
     KJB_PASS_EPILOGUE(c, P);
 }
 int kjb_pass_rtr_restir_temporal(kjb_context* c, const kjb_rtr_restir_temporal_args* a) {
@@ -763,7 +773,15 @@ int kjb_pass_rtr_resolve(kjb_context* c, const kjb_rtr_resolve_args* a) {
                      img_ro(a->restir_ray_tex), img_ro(a->restir_reservoir_tex), img_ro(a->restir_ray_orig_tex), img_rw(a->output_tex), img_rw(a->ray_len_output_tex)};
     const float radius_sample_mult = 1.0f / kjb_pow(8.0f, 0.666f);   // RADIUS_SAMPLE_MULT: const-folded in the shader
     KJB_ROWS(c, H);
-    KJB_LAUNCH(c, k_rtr_resolve, KJB_GRID2D(W, H, 32, 8), c->g, t, F4A(a->output_tex_size), radius_sample_mult);
+    ResolveTapAngles ta;
+    {
+        const float ang_offset = float(c->g.fc.frame_index * 59u % 128u) * KJB_PLASTIC;
+        for (uint32_t q = 0; q < 4u; ++q) for (int sample_i = 1; sample_i <= 8; ++sample_i) {
+            const float ang = (float(sample_i) + ang_offset) * KJB_GOLDEN_ANGLE + (float(q) / 4.0f) * KJB_TAU_F;
+            kjb_sincos(ang, &ta.sn[q * 8u + uint32_t(sample_i - 1)], &ta.cs[q * 8u + uint32_t(sample_i - 1)]);
+        }
+    }
+    KJB_LAUNCH(c, k_rtr_resolve, KJB_GRID2D(W, H, 32, 8), c->g, t, F4A(a->output_tex_size), radius_sample_mult, ta);
     KJB_PASS_EPILOGUE(c, P);
 }
 int kjb_pass_rtr_temporal(kjb_context* c, const kjb_rtr_temporal_args* a) {

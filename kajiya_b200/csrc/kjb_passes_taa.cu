@@ -23,17 +23,24 @@ KJB_DEV bool t1_should_dilate0(const Img& reprojection_tex, int x, int y, float2
     const float2 d = vel_max - vel_min, thr = 0.1f * vmax(f2(its.z, its.w), vabs(vel_max + vel_min));
     return d.x > thr.x || d.y > thr.y;
 }
+// 8 x 32-thread blocks whose rows start at a multiple of 4: a warp is the shader's wave, an 8x4 pixel patch with lane = x + 8*(y & 3), and the
+// WaveReadLaneAt(^2) / (^16) exchange of the dilation flag (reproject_history.hlsl:80-82) is two warp shuffles
+#define T1_BX 8
+#define T1_BY 32
 KJB_KERNEL(256) k_taa_reproject(Globals g, Img history_tex, Img reprojection_tex, Img depth_tex, ImgW output_tex, ImgW closest_velocity_output, float4 its, float4 ots, Rows kjb_rows) {
-    KJB_PX; const int W = output_tex.w, H = output_tex.h; if (x >= W || y >= H) return;
-    const float ped = g.fc.pre_exposure_delta;
+    const int x = int(blockIdx.x) * T1_BX + int(threadIdx.x), y = (kjb_rows.y0 & ~3) + int(blockIdx.y) * T1_BY + int(threadIdx.y);
+    const int W = output_tex.w, H = output_tex.h;
     const float2 irs = f2(its.x, its.y) / f2(ots.x, ots.y);
+    float dilate = t1_should_dilate0(reprojection_tex, x, y, irs, its) ? 1.0f : 0.0f;   // every lane, also those past the image edge (like the shader's)
+    dilate = kjb_max(dilate, warp_xor(dilate, 2));     // (x^2, y)
+    dilate = kjb_max(dilate, warp_xor(dilate, 16));    // (x, y^2) and, transitively, (x^2, y^2)
+    if (x >= W || y >= H || y < kjb_rows.y0 || y >= kjb_rows.y1) return;
+    const float ped = g.fc.pre_exposure_delta;
     const int rx = int(kjb_cvt_u32((float(x) + 0.5f) * irs.x)), ry = int(kjb_cvt_u32((float(y) + 0.5f) * irs.y));
     const float s4[4] = {ots.x, ots.y, ots.z, ots.w};
     const float2 uv = get_uv(x, y, s4);
     int cx = rx, cy = ry;
-    // lane^2 / lane^16 exchange of the 8x8 group == pixels (x^2,y), (x,y^2) and transitively (x^2,y^2)
-    const bool should_dilate = t1_should_dilate0(reprojection_tex, x, y, irs, its) || t1_should_dilate0(reprojection_tex, x ^ 2, y, irs, its)
-                            || t1_should_dilate0(reprojection_tex, x, y ^ 2, irs, its) || t1_should_dilate0(reprojection_tex, x ^ 2, y ^ 2, irs, its);
+    const bool should_dilate = dilate != 0.0f;
     if (should_dilate) {
         float reproj_depth = ld_r32f(depth_tex, rx, ry);
         for (int yy = -1; yy <= 1; ++yy) for (int xx = -1; xx <= 1; ++xx) {
@@ -72,31 +79,64 @@ KJB_KERNEL(256) k_taa_reproject(Globals g, Img history_tex, Img reprojection_tex
 }
 
 // ------------------------------------------------------------------ T2 filter_input.hlsl:32-89
-struct FilteredInput { float3 clamped_ex, var; };
-KJB_DEV FilteredInput t2_inner(const Img& input_tex, const Img& depth_tex, int px, int py, float center_depth, float luma_cutoff, float depth_scale, const float* dw) {
-    float3 iex = f3(0.0f), iex2 = f3(0.0f), clamped_iex = f3(0.0f); float iwsum = 0, clamped_iwsum = 0;
-    for (int y = -1; y <= 1; ++y) for (int x = -1; x <= 1; ++x) {
-        const float3 s = taa_input_remap(ld_rgba16f(input_tex, px + x, py + y));
-        const float depth = ld_r32f(depth_tex, px + x, py + y);
-        float w = 1;
-        w *= kjb_exp2(-kjb_min(16.0f, depth_scale * inverse_depth_relative_diff(center_depth, depth)));
-        w *= dw[(y + 1) * 3 + (x + 1)];
-        w *= kjb_pow(kjb_saturate(luma_cutoff / s.x), 8.0f);
-        clamped_iwsum += w; clamped_iex = mad(s, w, clamped_iex);
-        iwsum += 1; iex += s; iex2 += s * s;
+// Tiled: the block's (32+2)x(8+2) footprint of input_tex and depth_tex arrives in shared memory through one TMA group; the per-texel
+// decode (taa_input_remap: sqrt, three divisions, RGB->YCbCr) then runs once per texel instead of 18 times (two 3x3 passes), and the part
+// of a tap's weight that does not depend on the luma cutoff (depth term x spatial weight) is evaluated once for both passes.  `pow(t, 8)`
+// of t == 1 is exactly 1 under the numeric contract (kjb_log2(1) = 0, kjb_exp2(0) = 1), which is every tap of the first pass
+// (cutoff 1e10): those skip the exp2/log2 pair.  Same operations in the same order per output value => the same bits as t2_inner.
+#define T2_TW 34
+#define T2_TH 10
+KJB_DEVONLY float t2_pow8_sat(float luma_cutoff, float luma) { const float t = kjb_saturate(luma_cutoff / luma); return t == 1.0f ? 1.0f : kjb_pow(t, 8.0f); }
+KJB_KERNEL(256) k_taa_filter_input_tiled(const __grid_constant__ TileSource ts_input, const __grid_constant__ TileSource ts_depth, int use_tma, Img input_tex, Img depth_tex,
+                                         ImgW output_tex, ImgW dev_output_tex, W9 dw, Rows kjb_rows) {
+    constexpr int P8 = tile_pitch<8>(T2_TW), P4 = tile_pitch<4>(T2_TW);
+    __shared__ __align__(128) uint2 s_raw[P8 * T2_TH];
+    __shared__ __align__(128) float s_depth[P4 * T2_TH];
+    __shared__ float s_y[T2_TW * T2_TH], s_cb[T2_TW * T2_TH], s_cr[T2_TW * T2_TH];
+    __shared__ __align__(8) uint64_t bar;
+    const int tid = int(threadIdx.y) * 32 + int(threadIdx.x);
+    const int bx0 = int(blockIdx.x) * 32 - 1, by0 = kjb_rows.y0 + int(blockIdx.y) * 8 - 1;
+    tile_group_begin(&bar, 0, use_tma, tile_bytes<uint2, T2_TW, T2_TH>() + tile_bytes<float, T2_TW, T2_TH>(), tid);
+    tile_issue<uint2, T2_TW, T2_TH>(s_raw, ts_input, input_tex, bx0, by0, &bar, use_tma, tid, 256);
+    tile_issue<float, T2_TW, T2_TH>(s_depth, ts_depth, depth_tex, bx0, by0, &bar, use_tma, tid, 256);
+    tile_group_wait(&bar, 0, use_tma);
+    for (int i = tid; i < T2_TW * T2_TH; i += 256) {
+        const int lx = i % T2_TW, ly = i / T2_TW;
+        const float3 c = taa_input_remap(half4_to_float4(s_raw[ly * P8 + lx]));
+        s_y[i] = c.x; s_cb[i] = c.y; s_cr[i] = c.z;
     }
-    FilteredInput r; r.clamped_ex = clamped_iex / clamped_iwsum;
+    __syncthreads();
+    const int x = int(blockIdx.x) * 32 + int(threadIdx.x), y = kjb_rows.y0 + int(blockIdx.y) * 8 + int(threadIdx.y);
+    if (x >= output_tex.w || y >= output_tex.h || y >= kjb_rows.y1) return;
+    const int tx = int(threadIdx.x) + 1, ty = int(threadIdx.y) + 1;
+    const float center_depth = s_depth[ty * P4 + tx];
+    float wd[9];
+    float3 iex = f3(0.0f), iex2 = f3(0.0f), clamped_iex = f3(0.0f); float iwsum = 0, clamped_iwsum = 0;
+    for (int yy = -1; yy <= 1; ++yy) for (int xx = -1; xx <= 1; ++xx) {
+        const int k = (yy + 1) * 3 + (xx + 1), ti = (ty + yy) * T2_TW + (tx + xx);
+        const float3 sv = f3(s_y[ti], s_cb[ti], s_cr[ti]);
+        const float depth = s_depth[(ty + yy) * P4 + (tx + xx)];
+        float w = 1;
+        w *= kjb_exp2(-kjb_min(16.0f, 200.0f * inverse_depth_relative_diff(center_depth, depth)));
+        w *= dw.w[k];
+        wd[k] = w;
+        w *= t2_pow8_sat(1e10f, sv.x);
+        clamped_iwsum += w; clamped_iex = mad(sv, w, clamped_iex);
+        iwsum += 1; iex += sv; iex2 += sv * sv;
+    }
+    const float3 fi_clamped_ex = clamped_iex / clamped_iwsum;
     iex = iex / iwsum; iex2 = iex2 / iwsum;
-    r.var = vmax(f3(0.0f), iex2 - iex * iex);
-    return r;
-}
-KJB_KERNEL(256) k_taa_filter_input(Img input_tex, Img depth_tex, ImgW output_tex, ImgW dev_output_tex, W9 dw, Rows kjb_rows) {
-    KJB_PX; if (x >= output_tex.w || y >= output_tex.h) return;
-    const float center_depth = ld_r32f(depth_tex, x, y);
-    const FilteredInput fi = t2_inner(input_tex, depth_tex, x, y, center_depth, 1e10f, 200.0f, dw.w);
-    const FilteredInput cfi = t2_inner(input_tex, depth_tex, x, y, center_depth, fi.clamped_ex.x * 1.001f, 200.0f, dw.w);
-    st_rgba16f(output_tex, x, y, f4(cfi.clamped_ex, 0));
-    st_rgba16f(dev_output_tex, x, y, f4(vsqrt(fi.var), 0));
+    const float3 fi_var = vmax(f3(0.0f), iex2 - iex * iex);
+    const float luma_cutoff = fi_clamped_ex.x * 1.001f;
+    clamped_iex = f3(0.0f); clamped_iwsum = 0;
+    for (int yy = -1; yy <= 1; ++yy) for (int xx = -1; xx <= 1; ++xx) {
+        const int k = (yy + 1) * 3 + (xx + 1), ti = (ty + yy) * T2_TW + (tx + xx);
+        const float3 sv = f3(s_y[ti], s_cb[ti], s_cr[ti]);
+        const float w = wd[k] * t2_pow8_sat(luma_cutoff, sv.x);
+        clamped_iwsum += w; clamped_iex = mad(sv, w, clamped_iex);
+    }
+    st_rgba16f(output_tex, x, y, f4(clamped_iex / clamped_iwsum, 0));
+    st_rgba16f(dev_output_tex, x, y, f4(vsqrt(fi_var), 0));
 }
 
 // ------------------------------------------------------------------ T3 filter_history.hlsl:15-62
@@ -118,6 +158,52 @@ KJB_KERNEL(256) k_taa_filter_history(Img input_tex, ImgW output_tex, float4 its,
     const float2 uv = get_uv(x, y, s4);
     const float filtered_luma = t3_filter(input_tex, uv, its, 1e10f, k, dw.w).x;
     st_rgba16f(output_tex, x, y, f4(t3_filter(input_tex, uv, its, filtered_luma * 1.001f, k, dw.w), 0));
+}
+
+// Tiled variant for the native-resolution case (input extent == output extent, k == 1: every tap lies in the block's 34x10 footprint):
+// RGB->YCbCr once per texel, pow(1, 8) shortcut in the first pass as in T2.
+KJB_KERNEL(256) k_taa_filter_history_tiled(const __grid_constant__ TileSource ts_input, int use_tma, Img input_tex, ImgW output_tex, float4 its, float4 ots, W25t dw, Rows kjb_rows) {
+    constexpr int P8 = tile_pitch<8>(T2_TW);
+    __shared__ __align__(128) uint2 s_raw[P8 * T2_TH];
+    __shared__ float s_y[T2_TW * T2_TH], s_cb[T2_TW * T2_TH], s_cr[T2_TW * T2_TH];
+    __shared__ __align__(8) uint64_t bar;
+    const int tid = int(threadIdx.y) * 32 + int(threadIdx.x);
+    const int bx0 = int(blockIdx.x) * 32 - 1, by0 = kjb_rows.y0 + int(blockIdx.y) * 8 - 1;
+    tile_group_begin(&bar, 0, use_tma, tile_bytes<uint2, T2_TW, T2_TH>(), tid);
+    tile_issue<uint2, T2_TW, T2_TH>(s_raw, ts_input, input_tex, bx0, by0, &bar, use_tma, tid, 256);
+    tile_group_wait(&bar, 0, use_tma);
+    for (int i = tid; i < T2_TW * T2_TH; i += 256) {
+        const int lx = i % T2_TW, ly = i / T2_TW;
+        const float3 c = rgb_to_ycbcr(xyz(half4_to_float4(s_raw[ly * P8 + lx])));
+        s_y[i] = c.x; s_cb[i] = c.y; s_cr[i] = c.z;
+    }
+    __syncthreads();
+    const int x = int(blockIdx.x) * 32 + int(threadIdx.x), y = kjb_rows.y0 + int(blockIdx.y) * 8 + int(threadIdx.y);
+    if (x >= output_tex.w || y >= output_tex.h || y >= kjb_rows.y1) return;
+    const float s4[4] = {ots.x, ots.y, ots.z, ots.w};
+    const float2 uv = get_uv(x, y, s4);
+    const int sx = kjb_cvt_i32(kjb_floor(uv.x * its.x + 1e-3f)), sy = kjb_cvt_i32(kjb_floor(uv.y * its.y + 1e-3f));
+    const int tx = sx - bx0, ty = sy - by0;   // == threadIdx + 1 whenever the two extents are equal; a texel the tile does not hold falls back to global loads
+    const bool in_tile = tx >= 1 && tx <= T2_TW - 2 && ty >= 1 && ty <= T2_TH - 2;
+    float3 iex = f3(0.0f); float iwsum = 0; float3 taps[9];
+    for (int yy = -1; yy <= 1; ++yy) for (int xx = -1; xx <= 1; ++xx) {
+        const int k = (yy + 1) * 3 + (xx + 1);
+        taps[k] = in_tile ? f3(s_y[(ty + yy) * T2_TW + tx + xx], s_cb[(ty + yy) * T2_TW + tx + xx], s_cr[(ty + yy) * T2_TW + tx + xx]) : rgb_to_ycbcr(xyz(ld_rgba16f(input_tex, sx + xx, sy + yy)));
+        float w = 1;
+        w *= dw.w[(yy + 2) * 5 + (xx + 2)];
+        w *= t2_pow8_sat(1e10f, taps[k].x);
+        iwsum += w; iex = mad(taps[k], w, iex);
+    }
+    const float luma_cutoff = (iex / iwsum).x * 1.001f;
+    iex = f3(0.0f); iwsum = 0;
+    for (int yy = -1; yy <= 1; ++yy) for (int xx = -1; xx <= 1; ++xx) {
+        const int k = (yy + 1) * 3 + (xx + 1);
+        float w = 1;
+        w *= dw.w[(yy + 2) * 5 + (xx + 2)];
+        w *= t2_pow8_sat(luma_cutoff, taps[k].x);
+        iwsum += w; iex = mad(taps[k], w, iex);
+    }
+    st_rgba16f(output_tex, x, y, f4(iex / iwsum, 0));
 }
 
 // ------------------------------------------------------------------ T4 input_prob.hlsl:47-109
@@ -169,37 +255,50 @@ KJB_KERNEL(256) k_taa_prob_filter2(Img input_tex, ImgW output_tex, Rows kjb_rows
 
 // ------------------------------------------------------------------ T7 taa.hlsl:94-338 (+ inc/unjitter_taa.hlsl:58-125)
 struct Unjittered { float4 color; float coverage; float3 ex, ex2; };
-KJB_DEV Unjittered sample_image_unjitter_taa(const Img& img, int ox, int oy, float2 output_tex_size, float2 sample_offset_pixels, float kernel_scale) {
-    const float2 irs = f2(float(img.w), float(img.h)) / output_tex_size;
+// sample_image_unjitter_taa for kernel_scale 1 (`u`: colour, coverage, moments) and 0.333 (`b`: colour and coverage, all taa.hlsl uses of it)
+// in ONE walk over the 3x3 taps: the decoded tap colour is shared, every accumulator keeps its own tap order.  `fetch(x, y)` returns
+// taa_input_remap of the input texel (bx + x, by + y).
+template <typename F>
+KJB_DEV void sample_image_unjitter_taa2(int img_w, int img_h, int ox, int oy, float2 output_tex_size, float2 sample_offset_pixels, F fetch, Unjittered& u, float4& b_color, float& b_coverage) {
+    const float2 irs = f2(float(img_w), float(img_h)) / output_tex_size;
     const int bx = kjb_cvt_i32((float(ox) + 0.5f) * irs.x), by = kjb_cvt_i32((float(oy) + 0.5f) * irs.y);
     const float2 dst_sample_loc = f2(float(ox), float(oy)) + 0.5f;
     const float2 base_src_sample_loc = (f2(float(bx), float(by)) + 0.5f + sample_offset_pixels * f2(1, -1)) / irs;
-    float4 res = f4(0.0f); float3 ex = f3(0.0f), ex2 = f3(0.0f); float dev_wt_sum = 0.0f, wt_sum = 0.0f;
-    const float kdm = 1.0f * kernel_scale;
+    float4 res = f4(0.0f), bres = f4(0.0f); float3 ex = f3(0.0f), ex2 = f3(0.0f); float dev_wt_sum = 0.0f, wt_sum = 0.0f, bwt_sum = 0.0f;
+    const float kdm = 1.0f * 1.0f, bkdm = 1.0f * 0.333f;
     for (int y = -1; y <= 1; ++y) for (int x = -1; x <= 1; ++x) {
         const float2 src_sample_loc = base_src_sample_loc + f2(float(x), float(y)) / irs;
-        const float4 col = f4(taa_input_remap(ld_rgba16f(img, bx + x, by + y)), 1);
-        const float2 sco = (src_sample_loc - dst_sample_loc) * kdm;
-        const float dist2 = dot(sco, sco);
-        const float dev_wt = kjb_exp2(-dist2 * irs.x);
-        const float wt = kjb_exp2(-10 * dist2 * irs.x);
-        res = mad(col, wt, res); wt_sum += wt;
-        ex = mad(xyz(col), dev_wt, ex); ex2 = mad(xyz(col) * xyz(col), dev_wt, ex2); dev_wt_sum += dev_wt;
+        const float4 col = f4(fetch(bx, by, x, y), 1);
+        {
+            const float2 sco = (src_sample_loc - dst_sample_loc) * kdm;
+            const float dist2 = dot(sco, sco);
+            const float dev_wt = kjb_exp2(-dist2 * irs.x);
+            const float wt = kjb_exp2(-10 * dist2 * irs.x);
+            res = mad(col, wt, res); wt_sum += wt;
+            ex = mad(xyz(col), dev_wt, ex); ex2 = mad(xyz(col) * xyz(col), dev_wt, ex2); dev_wt_sum += dev_wt;
+        }
+        {
+            const float2 sco = (src_sample_loc - dst_sample_loc) * bkdm;
+            const float dist2 = dot(sco, sco);
+            const float wt = kjb_exp2(-10 * dist2 * irs.x);
+            bres = mad(col, wt, bres); bwt_sum += wt;
+        }
     }
-    Unjittered u; u.color = res; u.coverage = wt_sum; u.ex = ex / dev_wt_sum; u.ex2 = ex2 / dev_wt_sum;
-    return u;
+    u.color = res; u.coverage = wt_sum; u.ex = ex / dev_wt_sum; u.ex2 = ex2 / dev_wt_sum;
+    b_color = bres; b_coverage = bwt_sum;
 }
 struct TaaImgs { Img input_tex, history_tex, reprojection_tex, closest_velocity_tex, velocity_history_tex, smooth_var_history_tex, input_prob_tex;
                  ImgW temporal_output_tex, output_tex, smooth_var_output_tex, velocity_output_tex; };
-KJB_KERNEL(256) k_taa(Globals g, TaaImgs t, float4 its, float4 ots, W25t bw, Rows kjb_rows) {
-    KJB_PX; if (x >= t.temporal_output_tex.w || y >= t.temporal_output_tex.h) return;
+// one output pixel of taa.hlsl:94-338; `hist(xx, yy)` = history texel (x + xx, y + yy) as float4, `inp(bx, by, dx, dy)` = taa_input_remap of input texel (bx + dx, by + dy)
+template <typename FH, typename FI>
+KJB_DEV void taa_px(const Globals& g, const TaaImgs& t, float4 its, float4 ots, const W25t& bw, int x, int y, FH hist, FI inp) {
     const float2 sop = f2(g.fc.view_constants.sample_offset_pixels[0], g.fc.view_constants.sample_offset_pixels[1]);
     const float dt = g.fc.delta_time_seconds;
     const float2 irf = f2(its.x, its.y) / f2(ots.x, ots.y);
     const int rx = int(kjb_cvt_u32((float(x) + 0.5f) * irf.x)), ry = int(kjb_cvt_u32((float(y) + 0.5f) * irf.y));
     const float s4[4] = {ots.x, ots.y, ots.z, ots.w};
     const float2 uv = get_uv(x, y, s4);
-    const float4 history_packed = ld_rgba16f(t.history_tex, x, y);
+    const float4 history_packed = hist(0, 0);
     float3 history = xyz(history_packed);
     float history_coverage = kjb_max(0.0f, history_packed.w);
     float4 bhistory_packed;
@@ -207,7 +306,7 @@ KJB_KERNEL(256) k_taa(Globals g, TaaImgs t, float4 its, float4 ots, W25t bw, Row
         float4 csum = f4(0.0f); float wsum = 0;
         for (int yy = -2; yy <= 2; ++yy) for (int xx = -2; xx <= 2; ++xx) {
             const float w = bw.w[(yy + 2) * 5 + (xx + 2)];
-            csum = mad(ld_rgba16f(t.history_tex, x + xx, y + yy), w, csum); wsum += w;
+            csum = mad(hist(xx, yy), w, csum); wsum += w;
         }
         bhistory_packed = csum / wsum;
     }
@@ -217,11 +316,11 @@ KJB_KERNEL(256) k_taa(Globals g, TaaImgs t, float4 its, float4 ots, W25t bw, Row
     const float4 reproj = ld_rgba16s(t.reprojection_tex, rx, ry);
     const float2 cvel = ld_rg16f(t.closest_velocity_tex, x, y);
     const float2 reproj_xy = cvel;
-    const Unjittered center_sample = sample_image_unjitter_taa(t.input_tex, x, y, f2(ots.x, ots.y), sop, 1.0f);
-    const Unjittered bcenter_sample = sample_image_unjitter_taa(t.input_tex, x, y, f2(ots.x, ots.y), sop, 0.333f);
+    Unjittered center_sample; float4 bcenter_color; float bcenter_coverage;
+    sample_image_unjitter_taa2(t.input_tex.w, t.input_tex.h, x, y, f2(ots.x, ots.y), sop, inp, center_sample, bcenter_color, bcenter_coverage);
     float coverage = center_sample.coverage;
     float3 center = xyz(center_sample.color);
-    const float3 bcenter = xyz(bcenter_sample.color) / bcenter_sample.coverage;
+    const float3 bcenter = xyz(bcenter_color) / bcenter_coverage;
     history = vlerp(history, bcenter, kjb_saturate(1.0f - history_coverage));
     bhistory = vlerp(bhistory, bcenter, f3(kjb_saturate(1.0f - bhistory_coverage.x), kjb_saturate(1.0f - bhistory_coverage.y), kjb_saturate(1.0f - bhistory_coverage.z)));
     const float input_prob = ld_r16f(t.input_prob_tex, rx, ry);
@@ -282,6 +381,41 @@ KJB_KERNEL(256) k_taa(Globals g, TaaImgs t, float4 its, float4 ots, W25t bw, Row
     const float2 vo = cvel / dt;
     st_rg16f(t.velocity_output_tex, x, y, vo.x, vo.y);
 }
+KJB_KERNEL(256) k_taa(Globals g, TaaImgs t, float4 its, float4 ots, W25t bw, Rows kjb_rows) {
+    KJB_PX; if (x >= t.temporal_output_tex.w || y >= t.temporal_output_tex.h) return;
+    taa_px(g, t, its, ots, bw, x, y, [&](int xx, int yy) { return ld_rgba16f(t.history_tex, x + xx, y + yy); },
+           [&](int bx, int by, int dx, int dy) { return taa_input_remap(ld_rgba16f(t.input_tex, bx + dx, by + dy)); });
+}
+// Tiled variant for the native-resolution case (input extent == output extent, so the input tap (bx + dx, by + dy) is (x + dx, y + dy)):
+// history (32+4)x(8+4) and input (32+2)x(8+2) footprints through one TMA group; f16 -> f32 of the history and taa_input_remap of the
+// input run once per texel instead of once per tap (25 and 18 taps per pixel).
+#define T7_HW 36
+#define T7_HH 12
+KJB_KERNEL(256) k_taa_tiled(const __grid_constant__ TileSource ts_history, const __grid_constant__ TileSource ts_input, int use_tma, Globals g, TaaImgs t, float4 its, float4 ots, W25t bw, Rows kjb_rows) {
+    constexpr int PH = tile_pitch<8>(T7_HW), PI = tile_pitch<8>(T2_TW);
+    __shared__ __align__(128) uint2 s_hraw[PH * T7_HH];
+    __shared__ __align__(128) uint2 s_iraw[PI * T2_TH];
+    __shared__ float4 s_hist[T7_HW * T7_HH];
+    __shared__ float s_y[T2_TW * T2_TH], s_cb[T2_TW * T2_TH], s_cr[T2_TW * T2_TH];
+    __shared__ __align__(8) uint64_t bar;
+    const int tid = int(threadIdx.y) * 32 + int(threadIdx.x);
+    const int bx0 = int(blockIdx.x) * 32, by0 = kjb_rows.y0 + int(blockIdx.y) * 8;
+    tile_group_begin(&bar, 0, use_tma, tile_bytes<uint2, T7_HW, T7_HH>() + tile_bytes<uint2, T2_TW, T2_TH>(), tid);
+    tile_issue<uint2, T7_HW, T7_HH>(s_hraw, ts_history, t.history_tex, bx0 - 2, by0 - 2, &bar, use_tma, tid, 256);
+    tile_issue<uint2, T2_TW, T2_TH>(s_iraw, ts_input, t.input_tex, bx0 - 1, by0 - 1, &bar, use_tma, tid, 256);
+    tile_group_wait(&bar, 0, use_tma);
+    for (int i = tid; i < T7_HW * T7_HH; i += 256) s_hist[i] = half4_to_float4(s_hraw[(i / T7_HW) * PH + (i % T7_HW)]);
+    for (int i = tid; i < T2_TW * T2_TH; i += 256) {
+        const float3 c = taa_input_remap(half4_to_float4(s_iraw[(i / T2_TW) * PI + (i % T2_TW)]));
+        s_y[i] = c.x; s_cb[i] = c.y; s_cr[i] = c.z;
+    }
+    __syncthreads();
+    const int x = bx0 + int(threadIdx.x), y = by0 + int(threadIdx.y);
+    if (x >= t.temporal_output_tex.w || y >= t.temporal_output_tex.h || y >= kjb_rows.y1) return;
+    const int tx = int(threadIdx.x), ty = int(threadIdx.y);
+    taa_px(g, t, its, ots, bw, x, y, [&](int xx, int yy) { return s_hist[(ty + 2 + yy) * T7_HW + (tx + 2 + xx)]; },
+           [&](int bx, int by, int dx, int dy) { const int ti = (by - by0 + 1 + dy) * T2_TW + (bx - bx0 + 1 + dx); return f3(s_y[ti], s_cb[ti], s_cr[ti]); });
+}
 
 #define F4A(a) f4((a)[0], (a)[1], (a)[2], (a)[3])
 #define CHK(img, fmt, name) if (!check_img(c, (img), (fmt), P, name)) return 1
@@ -294,7 +428,7 @@ int kjb_pass_taa_reproject(kjb_context* c, const kjb_taa_reproject_args* a) {
     CHK(a->output_tex, KJB_FMT_RGBA16_FLOAT, "output_tex"); CHKE(a->history_tex, KJB_FMT_RGBA16_FLOAT, "history_tex", W, H); CHK(a->reprojection_tex, KJB_FMT_RGBA16_SNORM, "reprojection_tex");
     CHK(a->depth_tex, KJB_FMT_R32_FLOAT, "depth_tex"); CHKE(a->closest_velocity_output, KJB_FMT_RG16_FLOAT, "closest_velocity_output", W, H);
     KJB_ROWS(c, H);
-    KJB_LAUNCH(c, k_taa_reproject, KJB_GRID2D(W, H, 32, 8), c->g, img_ro(a->history_tex), img_ro(a->reprojection_tex), img_ro(a->depth_tex), img_rw(a->output_tex), img_rw(a->closest_velocity_output),
+    KJB_LAUNCH_SYNC(c, k_taa_reproject, KJB_DIMS(dim3((W + T1_BX - 1) / T1_BX, unsigned(kjb__rows.y1 - (kjb__rows.y0 & ~3) + T1_BY - 1) / T1_BY, 1), dim3(T1_BX, T1_BY, 1)), c->g, img_ro(a->history_tex), img_ro(a->reprojection_tex), img_ro(a->depth_tex), img_rw(a->output_tex), img_rw(a->closest_velocity_output),
                F4A(a->input_tex_size), F4A(a->output_tex_size));
     KJB_PASS_EPILOGUE(c, P);
 }
@@ -304,7 +438,8 @@ int kjb_pass_taa_filter_input(kjb_context* c, const kjb_taa_filter_input_args* a
     CHKE(a->dev_output_tex, KJB_FMT_RGBA16_FLOAT, "dev_output_tex", W, H);
     W9 dw; for (int y = -1; y <= 1; ++y) for (int x = -1; x <= 1; ++x) dw.w[(y + 1) * 3 + (x + 1)] = kjb_exp(-(0.8f / float(1 * 1)) * float(x * x + y * y));
     KJB_ROWS(c, H);
-    KJB_LAUNCH(c, k_taa_filter_input, KJB_GRID2D(W, H, 32, 8), img_ro(a->input_tex), img_ro(a->depth_tex), img_rw(a->output_tex), img_rw(a->dev_output_tex), dw);
+    const TileSource ts_in = tile_source(c, a->input_tex, T2_TW, T2_TH), ts_depth = tile_source(c, a->depth_tex, T2_TW, T2_TH);
+    KJB_LAUNCH_SYNC(c, k_taa_filter_input_tiled, KJB_GRID2D(W, H, 32, 8), ts_in, ts_depth, ts_in.use_tma & ts_depth.use_tma, img_ro(a->input_tex), img_ro(a->depth_tex), img_rw(a->output_tex), img_rw(a->dev_output_tex), dw);
     KJB_PASS_EPILOGUE(c, P);
 }
 int kjb_pass_taa_filter_history(kjb_context* c, const kjb_taa_filter_history_args* a) {
@@ -313,7 +448,11 @@ int kjb_pass_taa_filter_history(kjb_context* c, const kjb_taa_filter_history_arg
     const int k = (a->input_tex_size[0] / a->output_tex_size[0] > 1.75f) ? 2 : 1;
     W25t dw; for (int y = -2; y <= 2; ++y) for (int x = -2; x <= 2; ++x) dw.w[(y + 2) * 5 + (x + 2)] = kjb_exp(-(0.8f / float(k * k)) * float(x * x + y * y));
     KJB_ROWS(c, H);
-    KJB_LAUNCH(c, k_taa_filter_history, KJB_GRID2D(W, H, 32, 8), img_ro(a->input_tex), img_rw(a->output_tex), F4A(a->input_tex_size), F4A(a->output_tex_size), k, dw);
+    if (k == 1 && a->input_tex.width == W && a->input_tex.height == H) {
+        const TileSource ts_in = tile_source(c, a->input_tex, T2_TW, T2_TH);
+        KJB_LAUNCH_SYNC(c, k_taa_filter_history_tiled, KJB_GRID2D(W, H, 32, 8), ts_in, ts_in.use_tma, img_ro(a->input_tex), img_rw(a->output_tex), F4A(a->input_tex_size), F4A(a->output_tex_size), dw);
+    } else
+        KJB_LAUNCH(c, k_taa_filter_history, KJB_GRID2D(W, H, 32, 8), img_ro(a->input_tex), img_rw(a->output_tex), F4A(a->input_tex_size), F4A(a->output_tex_size), k, dw);
     KJB_PASS_EPILOGUE(c, P);
 }
 int kjb_pass_taa_input_prob(kjb_context* c, const kjb_taa_input_prob_args* a) {
@@ -353,7 +492,11 @@ int kjb_pass_taa(kjb_context* c, const kjb_taa_args* a) {
     t.temporal_output_tex = img_rw(a->temporal_output_tex); t.output_tex = img_rw(a->output_tex); t.smooth_var_output_tex = img_rw(a->smooth_var_output_tex); t.velocity_output_tex = img_rw(a->velocity_output_tex);
     W25t bw; for (int y = -2; y <= 2; ++y) for (int x = -2; x <= 2; ++x) { const float ox = float(x) * 1.0f, oy = float(y) * 1.0f; bw.w[(y + 2) * 5 + (x + 2)] = kjb_exp(-(ox * ox + oy * oy)); }
     KJB_ROWS(c, H);
-    KJB_LAUNCH(c, k_taa, KJB_GRID2D(W, H, 32, 8), c->g, t, F4A(a->input_tex_size), F4A(a->output_tex_size), bw);
+    if (a->input_tex.width == W && a->input_tex.height == H) {
+        const TileSource ts_h = tile_source(c, a->history_tex, T7_HW, T7_HH), ts_i = tile_source(c, a->input_tex, T2_TW, T2_TH);
+        KJB_LAUNCH_SYNC(c, k_taa_tiled, KJB_GRID2D(W, H, 32, 8), ts_h, ts_i, ts_h.use_tma & ts_i.use_tma, c->g, t, F4A(a->input_tex_size), F4A(a->output_tex_size), bw);
+    } else
+        KJB_LAUNCH(c, k_taa, KJB_GRID2D(W, H, 32, 8), c->g, t, F4A(a->input_tex_size), F4A(a->output_tex_size), bw);
     KJB_PASS_EPILOGUE(c, P);
 }
 

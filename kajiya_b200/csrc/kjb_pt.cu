@@ -101,6 +101,6 @@ KJB_KERNEL(128) k_reference_pt(Globals g, ImgW output_tex, uint32_t indirect_onl
 extern "C" int kjb_pass_reference_path_trace(kjb_context* c, const kjb_reference_pt_args* a) {
     if (!check_img(c, a->output_tex, KJB_FMT_RGBA32_FLOAT, "reference pt", "output_tex")) return 1;
     KJB_ROWS(c, a->output_tex.height);
-    KJB_LAUNCH(c, k_reference_pt, KJB_GRID2D(a->output_tex.width, a->output_tex.height, 16, 8), c->g, img_rw(a->output_tex), a->indirect_only);
+    KJB_LAUNCH(c, k_reference_pt, KJB_GRID2D(a->output_tex.width, a->output_tex.height, KJB_RAY_BX, KJB_RAY_BY), c->g, img_rw(a->output_tex), a->indirect_only);
     KJB_PASS_EPILOGUE(c, "reference pt");
 }

@@ -201,6 +201,21 @@ class World:
         self.d.kjb_world_last_frame_stats(self.w, C.byref(s))
         return dict(launches=s[0], closest_rays=s[1], any_hit_rays=s[2], passes=s[3])
 
+    def set_cuda_graph(self, on):
+        """one CUDA graph launch per frame instead of ~40 kernel launches (default on; applies from the fifth frame)"""
+        self._check(self.d.kjb_world_set_cuda_graph(self.w, int(on)))
+
+    def graph_stats(self):
+        s = (C.c_uint64 * 2)()
+        self._check(self.d.kjb_graph_stats(self.ctx, C.byref(s)))
+        return dict(launches=s[0], instantiations=s[1])
+
+    def tlas_stats(self):
+        """how "rebuild tlas" was served: full rebuilds vs device refits (transform-only changes)"""
+        s = (C.c_uint64 * 2)()
+        self._check(self.d.kjb_tlas_stats(self.ctx, C.byref(s)))
+        return dict(rebuilds=s[0], refits=s[1])
+
     # -- images ------------------------------------------------------------------------------------------------
     def image_names(self):
         return [n for n in self.d.kjb_world_image_names(self.w).decode().split("\n") if n]

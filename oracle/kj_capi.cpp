@@ -75,6 +75,10 @@ int kjb_memcpy_d2d(kjb_context*, void* dst, const void* src, uint64_t bytes) { m
 int kjb_memcpy_d2d_batch_on(kjb_context*, uint32_t, const kjb_copy_desc* c, uint32_t n) { for (uint32_t i = 0; i < n; ++i) if (c[i].bytes) memmove(c[i].dst, c[i].src, c[i].bytes); return 0; }
 int kjb_memcpy_d2d_batch(kjb_context*, const kjb_copy_desc* c, uint32_t n) { for (uint32_t i = 0; i < n; ++i) if (c[i].bytes) memmove(c[i].dst, c[i].src, c[i].bytes); return 0; }
 int kjb_set_scissor(kjb_context* c, uint32_t y0, uint32_t y1) { c->scissor_y0 = y0; c->scissor_y1 = y1; return 0; }
+int kjb_graph_begin(kjb_context*) { return 0; }
+int kjb_graph_end(kjb_context*) { return 0; }
+int kjb_graph_stats(kjb_context*, uint64_t out[2]) { out[0] = out[1] = 0; return 0; }
+int kjb_tlas_stats(kjb_context*, uint64_t out[2]) { out[0] = out[1] = 0; return 0; }   // the oracle rebuilds its median-split BVH whenever a transform changes
 int kjb_set_debug_serial(kjb_context* c, uint32_t on) { c->cache_passes_parallel = on == 0; return 0; }   // default (never called): serial
 int kjb_set_option(kjb_context*, uint32_t, uint32_t) { return 0; }   // performance options do not exist here
 int kjb_image_upload_on(kjb_context* c, uint32_t, const kjb_image* dst, const void* src) { return kjb_image_upload(c, dst, src); }

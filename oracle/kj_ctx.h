@@ -47,13 +47,13 @@ inline void pass_rows(const kjb_context* ctx, int H, const std::function<void(in
     parallel_rows_range(y0, y1, row_fn, nthreads);
 }
 
-// Passes that touch the irradiance cache run on ONE thread in the order a serialised GPU launch would execute them: 16x8 pixel
+// Passes that touch the irradiance cache run on ONE thread in the order a serialised GPU launch would execute them: 8x16 pixel
 // blocks, row-major over blocks, row-major inside a block (the product's launch shape for the two rtdgi ray passes).
 inline void pass_pixels(const kjb_context* ctx, int W, int H, bool serial_tiles, const std::function<void(int, int)>& px_fn) {
     if (!serial_tiles || ctx->cache_passes_parallel) { pass_rows(ctx, H, [&](int y) { for (int x = 0; x < W; ++x) px_fn(x, y); }, ctx->num_threads); return; }
     int y0, y1; scissor_rows(ctx, H, y0, y1);
-    for (int by = y0; by < y1; by += 8) for (int bx = 0; bx < W; bx += 16)
-        for (int y = by; y < by + 8 && y < y1; ++y) for (int x = bx; x < bx + 16 && x < W; ++x) px_fn(x, y);
+    for (int by = y0; by < y1; by += 16) for (int bx = 0; bx < W; bx += 8)
+        for (int y = by; y < by + 16 && y < y1; ++y) for (int x = bx; x < bx + 8 && x < W; ++x) px_fn(x, y);
 }
 
 // 1-D cache passes (one item per entry sample): serial index order, or chunks of 64 items over the host threads in the parallel schedule

@@ -20,6 +20,8 @@
 #define __forceinline__ inline
 #define __launch_bounds__(...)
 #define __restrict__
+#define __grid_constant__
+#define __align__(n) __attribute__((aligned(n)))
 #define __shared__ static thread_local
 
 struct float2 { float x, y; };

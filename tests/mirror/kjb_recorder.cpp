@@ -53,6 +53,10 @@ int kjb_timer_elapsed_ms(kjb_context*, uint32_t, uint32_t, float* o) { *o = 0; r
 int kjb_scene_set_geometry(kjb_context*, const void*, uint64_t, const kjb_gpu_mesh*, const uint32_t*, uint32_t) { return 0; }
 int kjb_scene_set_textures(kjb_context*, const kjb_texture_desc*, uint32_t) { return 0; }
 int kjb_rebuild_tlas(kjb_context*, const kjb_instance* inst, uint32_t n) { rec("kjb_rebuild_tlas", inst, n * sizeof(kjb_instance)); return 0; }
+int kjb_graph_begin(kjb_context*) { return 0; }
+int kjb_graph_end(kjb_context*) { return 0; }
+int kjb_graph_stats(kjb_context*, uint64_t out[2]) { out[0] = out[1] = 0; return 0; }
+int kjb_tlas_stats(kjb_context*, uint64_t out[2]) { out[0] = out[1] = 0; return 0; }
 int kjb_set_frame_constants(kjb_context*, const kjb_frame_constants* fc, const kjb_triangle_light*, uint32_t) { rec("kjb_set_frame_constants", fc, sizeof(*fc)); return 0; }
 int kjb_set_luts(kjb_context*, const kjb_image*, const kjb_image*) { return 0; }
 int kjb_ray_counters(kjb_context*, uint64_t out[2], int) { out[0] = out[1] = 0; return 0; }

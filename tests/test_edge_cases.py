@@ -59,7 +59,10 @@ def test_pass_argument_errors_are_reported(emu_lib):
 
 def test_world_refuses_unsupported_combinations(emu_lib):
     with pytest.raises(KjbError):
-        World(emu_lib, 64, 64, enable_rtr=True, tile=(0, 2))          # reflections sample this frame's GI anywhere on screen: no tiles yet
+        World(emu_lib, 64, 64, enable_lighting=True, tile=(0, 2))     # the lit composite (shadow-denoiser history) does not shard yet
+    with pytest.raises(KjbError):
+        World(emu_lib, 64, 64, tile=(2, 2))                            # tile_rank must be < tile_count
+    World(emu_lib, 64, 64, enable_rtr=True, tile=(0, 2)).close()      # reflections shard since round 2 (second all-gather carries this frame's GI)
     w = World(emu_lib, 32, 32, enable_rtr=True)
     w.set_blue_noise(scenes.blue_noise())
     _, view = scenes.cornell_box()
@@ -88,6 +91,9 @@ def test_instanced_moving_geometry(oracle_lib, emu_lib):
                 w.set_instance_transform(iid, t)
             w.render_frame(**view)
         assert not parity.compare_images(worlds[0][0], worlds[1][0]), f
+    # "rebuild tlas" every frame as upstream: the first frame builds the structure, every later transform-only change is a device refit
+    ts = worlds[1][0].tlas_stats()
+    assert ts["rebuilds"] == 1 and ts["refits"] == 4, ts
     # the moving instance has object motion in its velocity (last frame's transform), the static one only camera motion (none here)
     vel = worlds[1][0].image("velocity").astype(np.float32)
     assert np.abs(vel[..., 0]).max() > 0.01

@@ -246,3 +246,80 @@ def test_shadow_denoiser_on_gpu(oracle_lib, cuda_lib):
         assert not parity.compare_images(wa, wb), f
     den = wb.image("shadow_denoise.spatial_input")[..., 0].astype(np.float32); geo = wb.image("depth")[..., 0] != 0
     assert ((den[geo] > 0.02) & (den[geo] < 0.98)).mean() > 0.01
+
+
+# ------------------------------------------------------------------ BASELINE sizes (1080p): the oracle on the box's host threads takes a few seconds per frame
+def test_cornell_1080p_lockstep_config2(oracle_lib, cuda_lib):
+    """BASELINE configs[1] at its real size: Cornell 1920x1080, 1 spatial + 1 temporal pass, 4 frames, EVERY image bit for bit (the
+    production kernels with their TMA tile staging — the small lockstep tests never have 16-byte aligned rows everywhere)."""
+    scene, view = scenes.cornell_box()
+    _, wb, report = parity.run_lockstep(oracle_lib, cuda_lib, scene, view, 1920, 1080, 4, spatial_reuse_pass_count=1)
+    _assert_clean(report)
+    assert wb.stats()["closest_rays"] > 100000
+
+
+def test_atrium_1080p_rtdgi_rtr_taa_lockstep(oracle_lib, cuda_lib):
+    """BASELINE configs[2]'s scene and size without the (racy) cache: the 260 k-triangle atrium at 1920x1080, rtdgi with two spatial passes +
+    reflections + TAA, camera in motion — the parallel production kernels of every pass but the cache's, every image bit for bit."""
+    scene, view = scenes.atrium()
+    kw = dict(enable_rtr=True, enable_taa=True, spatial_reuse_pass_count=2)
+    wa, wb = parity.make_world(oracle_lib, scene, 1920, 1080, **kw), parity.make_world(cuda_lib, scene, 1920, 1080, **kw)
+    cp = np.array(view["camera_position"], np.float32)
+    for f in range(3):
+        v = dict(view); v["camera_position"] = tuple(cp + np.array([0.05 * f, 0.01 * f, 0.02 * f], np.float32))
+        wa.render_frame(**v); wb.render_frame(**v)
+        bad = parity.compare_images(wa, wb)
+        assert not bad, (f, bad[:5])
+
+
+def test_atrium_full_path_serial_schedule_480x270(oracle_lib, cuda_lib):
+    """the whole path (rtdgi + ircache + rtr + taa) on the full atrium with the cache passes on the serial schedule: bit for bit.  (One GPU thread
+    walking 1080p would take minutes per pass; 480x270 exercises the same code on the same scene.)"""
+    scene, view = scenes.atrium()
+    kw = dict(enable_rtr=True, enable_ircache=True, enable_taa=True, spatial_reuse_pass_count=2)
+    wa, wb = parity.make_world(oracle_lib, scene, 480, 270, **kw), parity.make_world(cuda_lib, scene, 480, 270, **kw)
+    wb.set_debug_serial(True)
+    for f in range(3):
+        wa.render_frame(**view); wb.render_frame(**view)
+        bad = parity.compare_images(wa, wb)
+        assert not bad, (f, bad[:5])
+
+
+def test_atrium_1080p_full_path_parallel_statistical(oracle_lib, cuda_lib):
+    """BASELINE configs[2] exactly as bench.py times it — atrium 1080p, rtdgi + ircache + rtr + taa, the PARALLEL (racy) cache kernels — against the
+    oracle's serial schedule.  Statistical by necessity (which thread wins an allocation differs): live cache entries within 5 %, mean L0
+    irradiance of the live entries within 12 %, mean of the GI / reflection / final images within 4 %, and per-image RMS difference below
+    20 % of the image mean (two racy GPU runs differ from each other by about half of that)."""
+    scene, view = scenes.atrium()
+    kw = dict(enable_rtr=True, enable_ircache=True, enable_taa=True, spatial_reuse_pass_count=2)
+    wa, wb = parity.make_world(oracle_lib, scene, 1920, 1080, **kw), parity.make_world(cuda_lib, scene, 1920, 1080, **kw)
+    for f in range(5):
+        wa.render_frame(**view); wb.render_frame(**view)
+    a, b = _cache_summary(wa), _cache_summary(wb)
+    assert abs(a["alloc"] - b["alloc"]) <= 0.05 * a["alloc"] + 2, (a["alloc"], b["alloc"])
+    ma, mb = float(a["r0"].mean()), float(b["r0"].mean())
+    assert abs(ma - mb) <= 0.12 * abs(ma), (ma, mb)
+    for name in ("rtdgi.spatial_filtered", "taa.this_frame_out"):
+        ia, ib = wa.image(name).astype(np.float64)[..., :3], wb.image(name).astype(np.float64)[..., :3]
+        assert np.isfinite(ib).all(), name
+        assert abs(ia.mean() - ib.mean()) <= 0.04 * ia.mean(), (name, ia.mean(), ib.mean())
+        assert np.sqrt(((ia - ib) ** 2).mean()) <= 0.20 * ia.mean(), (name, np.sqrt(((ia - ib) ** 2).mean()), ia.mean())
+    # images that never see the cache are still exact: the G-buffer side and the reprojection map
+    assert not parity.compare_images(wa, wb, names=["depth", "gbuffer", "reprojection_map", "half_depth", "half_view_normal"])
+
+
+def test_cuda_graph_frames_match_directly_launched_frames(cuda_lib):
+    """From the fifth frame on a frame's ~40 passes are recorded and submitted as ONE CUDA graph launch whose kernel-node parameters are updated
+    in place every frame (ping-pong halves, frame constants).  Same bits as launching the kernels one by one — full path, camera in motion,
+    and also through the streaming host-buffer call."""
+    scene, view = scenes.cornell_box()
+    kw = dict(enable_rtr=True, enable_ircache=False, enable_taa=True)
+    wa, wb = parity.make_world(cuda_lib, _glossy(scene), 320, 180, **kw), parity.make_world(cuda_lib, _glossy(scene), 320, 180, **kw)
+    wb.set_cuda_graph(False)
+    cp = np.array(view["camera_position"], np.float32)
+    for f in range(12):
+        v = dict(view); v["camera_position"] = tuple(cp + np.array([0.02 * f, 0.0, -0.03 * f], np.float32))
+        wa.render_frame(**v); wb.render_frame(**v)
+        assert not parity.compare_images(wa, wb), f
+    ga, gb = wa.graph_stats(), wb.graph_stats()
+    assert ga["launches"] == 8 and ga["instantiations"] <= 2 and gb["launches"] == 0, (ga, gb)   # frames 4..11; one instance, updated in place

@@ -15,7 +15,7 @@ def _free_port():
     s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
 
 
-def _worker(rank, world_size, port, enable_taa, H, ret):
+def _worker(rank, world_size, port, enable_taa, H, ret, enable_rtr=False):
     sys.path.insert(0, ROOT); sys.path.insert(0, HERE)
     os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
     os.environ["KJB_EMU_THREADS"] = "2"
@@ -26,7 +26,12 @@ def _worker(rank, world_size, port, enable_taa, H, ret):
     lib = KjbLib(os.path.join(HERE, "emu", "_build", "libkjb_emu.so"))
     scene, view = scenes.cornell_box()
     view = dict(view, camera_position=(0.0, 1.0, 5.0))
-    kw = dict(enable_taa=enable_taa, spatial_reuse_pass_count=2, enable_ssao=(world_size == 2))   # the 2-rank case also runs the SSAO guide (whole image on every rank)
+    kw = dict(enable_taa=enable_taa, spatial_reuse_pass_count=2, enable_ssao=(world_size == 2), enable_rtr=enable_rtr)   # the 2-rank case also runs the SSAO guide (whole image on every rank)
+    if enable_rtr:   # glossy walls so that the reflection passes really trace (roughness <= 0.6)
+        import copy
+        scene = copy.deepcopy(scene)
+        for i, m in enumerate(scene[0][0]["materials"]):
+            m["roughness"] = [0.05, 0.2, 0.35, 0.5, 0.8][i % 5]; m["metallic"] = [1.0, 0.0, 0.5][i % 3]
     tiled = parity.make_world(lib, scene, W, H, tile=(rank, world_size), **kw)
     calls = [0]
 
@@ -47,6 +52,8 @@ def _worker(rank, world_size, port, enable_taa, H, ret):
     names = ["rtdgi.spatial_filtered", "rtdgi.temporal_filtered", "rtdgi.irradiance"] + [n for n in full.image_names() if n.endswith(":0") or n.endswith(":1")]
     if enable_taa:
         names += ["taa.this_frame_out"]
+    if enable_rtr:
+        names += ["rtr.resolved"]
     for n in names:
         a, b = tiled.image(n), full.image(n)
         s = a.shape[0] // hh            # 1 for half-res images, 2 for full-res
@@ -112,3 +119,15 @@ def test_tile_sharded_frames_with_replicated_irradiance_cache(emu_lib):
         assert abs(ma - mb) <= 0.10 * mb, (rank, ma, mb)
         assert rms <= 0.25 * mb, (rank, rms, mb)
         assert 0.3 * lb <= la <= 1.1 * lb, (rank, la, lb)
+
+
+def test_tile_sharded_reflections_match_single_process(emu_lib):
+    """rtdgi + reflections + taa on 2 ranks: the reflection passes run on the band plus their halos (resolve footprint, cleanup offsets, history
+    search radius), this frame's GI travels in a second all-gather (reflection rays read it anywhere on screen) and every rtr history image
+    joins the end-of-frame border exchange — each rank's band must still equal the single-process frame bit for bit."""
+    ret = mp.Manager().dict()
+    mp.spawn(_worker, args=(2, _free_port(), True, H, ret, True), nprocs=2, join=True)
+    for rank in range(2):
+        bad, calls = ret[rank]
+        assert calls == 2 * FRAMES, "two all-gathers per frame: this frame's GI for the reflection rays, then the history borders"
+        assert not bad, f"rank {rank}: band differs from the single-process frame: {bad}"

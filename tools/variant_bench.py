@@ -30,17 +30,23 @@ def build(specs):
         print("built", name, flags)
 
 
-def run(frames, spatial, rounds=3):
+def run(frames, spatial, rounds=3, workload=None):
     import numpy as np
     import kajiya_b200
     from kajiya_b200._abi import KjbLib
     from kajiya_b200.world import World
     from kajiya_b200 import scenes
     libs = [("shipping", os.path.join(ROOT, "kajiya_b200", "csrc", "libkjb.so"))] + [(os.path.basename(p)[7:-3], p) for p in sorted(glob.glob(os.path.join(VAR, "libkjb_*.so")))]
+    import bench
     scene, view = scenes.cornell_box()
     worlds = []
     for name, path in libs:
-        w = World(KjbLib(path), 1920, 1080, spatial_reuse_pass_count=spatial); scenes.populate(w, scene)
+        if workload:   # a bench.py workload (e.g. atrium_1080p_full): replayed G-buffers, like the bench
+            w, view, _, _ = bench.build_world(KjbLib(path), workload)
+            for i in range(4): w.render_frame(capture_slot=i + 1, **view)
+            view = dict(view, replay_slot=1)
+        else:
+            w = World(KjbLib(path), 1920, 1080, spatial_reuse_pass_count=spatial); scenes.populate(w, scene)
         for _ in range(8): w.render_frame(**view)
         w.sync(); worlds.append((name, w))
     acc = {name: {} for name, _ in worlds}
@@ -68,5 +74,5 @@ if __name__ == "__main__":
         build(sys.argv[2:])
     else:
         import argparse
-        ap = argparse.ArgumentParser(); ap.add_argument("cmd"); ap.add_argument("--frames", type=int, default=48); ap.add_argument("--spatial", type=int, default=1)
-        a = ap.parse_args(); run(a.frames, a.spatial)
+        ap = argparse.ArgumentParser(); ap.add_argument("cmd"); ap.add_argument("--frames", type=int, default=48); ap.add_argument("--spatial", type=int, default=1); ap.add_argument("--workload", default=None)
+        a = ap.parse_args(); run(a.frames, a.spatial, workload=a.workload)
