@@ -67,7 +67,7 @@ PASS_BYTES = {
     "trace shadow mask": ("F", 9), "shadow bitpack": ("F", 1.125), "shadow temporal": ("F", 33.25), "shadow spatial": ("F", 16), "light gbuffer": ("F", 52), "sample lights": ("Hh", 32), "spatial reuse lights": ("F+Hh", (28, 36)),
     # SSAO guide (N3): ssgi.hlsl + spatial + upsample + temporal (ssgi.rs:41-243)
     "ssao": ("Hh", 30), "ssao spatial": ("Hh", 12), "ssao upsample": ("F+Hh", (10, 10)), "ssao temporal": ("F", 14),
-    "tile border all-gather": ("const", 0), "tile gi all-gather": ("const", 0),
+    "tile border all-gather": ("const", 0), "tile gi all-gather": ("const", 0), "tile input all-gather": ("const", 0),
 }
 NCU_TABLE = os.path.join("profiles", "ncu_kernel_table.json")   # {workload: {pass label: {"dram_bytes": .., "warp_inst": .., "source": "profiles/<csv>"}}}, made by tools/ncu_table.py
 
@@ -262,7 +262,8 @@ def measure_frames(lib, torch, dist, workload, K, Wm, rank, world_size, local_ra
     st2 = w.stats()
     rays_e2e = st2["closest_rays"] + st2["any_hit_rays"]
     ms_e2e = max(ms_e2e, wall_e2e)   # the call blocks on the download: wall clock is the honest end-to-end figure
-    h2d = sum(int(t.numel()) for t in host_ring[0]) + 1216
+    h2d = sum(int(t.numel()) for t in host_ring[0]) // world_size + 1216    # a rank of a tile-sharded frame uploads its band only (the bands travel over NVLink)
+    res_bytes = res_bytes // world_size
     w.close()
     del host_ring, host_results
 
@@ -369,6 +370,32 @@ def summarize(m, world_size, peak, ncu_table):
             "gpu_launches": int(m["launches"]), "roofline": roof}
 
 
+def measure_fast_math(torch, workload, K, Wm, local_rank, nslots=8):
+    """the same frames through libkjb_fast.so (-DKJB_FAST -use_fast_math: MUFU transcendentals, approximate division / sqrt, FMA contraction) — NOT parity-valid
+    (tests/test_gpu_fast.py states how close it stays), reported next to the exact build so that the cost of the numeric contract is a measured number"""
+    import kajiya_b200
+    try:
+        lib = kajiya_b200.lib_fast()
+    except Exception as e:
+        return {"unavailable": str(e)[:120]}
+    w, view, W, H = build_world(lib, workload, device=local_rank)
+    n = max(2, min(K, nslots))
+    for i in range(n):
+        w.render_frame(capture_slot=i + 1, **view)
+    for i in range(Wm):
+        w.render_frame(replay_slot=(i % n) + 1, **view)
+    w.sync(); w.stats()
+    torch.cuda.synchronize()
+    w.timer_record(1000)
+    for i in range(K):
+        w.render_frame(replay_slot=((Wm + i) % n) + 1, **view)
+    w.timer_record(1001)
+    ms = w.timer_elapsed_ms(1000, 1001)
+    st = w.stats(); w.close()
+    return {"ms_per_step": ms / K, "value": (st["closest_rays"] + st["any_hit_rays"]) / (ms * 1e-3), "unit": "rays/s", "steps": K,
+            "build": "libkjb_fast.so: same sources, -DKJB_FAST -use_fast_math", "parity": "not bit-compatible with the oracle; tolerances in tests/test_gpu_fast.py"}
+
+
 def measure_reference_pt(lib, torch, workload, K, Wm, local_rank):
     """BASELINE configs[0]: the reference path tracer (rt/reference_path_trace.rgen.hlsl), 1 path per pixel per frame, on the GPU"""
     w, view, W, H = build_world(lib, workload, device=local_rank)
@@ -451,6 +478,10 @@ def run_cuda(args):
                 e["multi_gpu"] = (f"one frame tile-sharded into {world_size} bands of half-res rows, NCCL all-gather of band borders per frame; `value` counts the frame's rays once "
                                   f"(the ranks actually traced {m['rays_traced_all_ranks'] / Kc:.0f} per frame including halo recompute)")
                 e["parity"] = par
+            if world_size == 1 and name in (headline, "cornell_1080p_rtdgi_1s1t") and not args.no_fast_math:
+                e["fast_math"] = measure_fast_math(torch, name, max(4, min(Kc, 16)), Wc, local_rank)
+                if "ms_per_step" in e["fast_math"]:
+                    e["fast_math"]["exact_over_fast"] = e["ms_per_step"] / e["fast_math"]["ms_per_step"]
             if world_size == 1 and not args.no_cpu_baseline:
                 e["cpu_baseline"] = cpu_baseline(name, seconds=args.cpu_seconds if name == headline else min(args.cpu_seconds, 4.0), reduced=name != headline)
             entries.append(e)
@@ -464,7 +495,7 @@ def run_cuda(args):
     out = {"metric": "gi_rays_per_sec", "value": head["value"], "unit": "rays/s", "n_gpus": world_size, "steps": K, "warmup": Wm, "ms_per_step": head["ms_per_step"],
            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": head["config"],
            "e2e": head["e2e"], "gpu_launches": head["gpu_launches"], "clocks": clock_info, "roofline": head["roofline"]}
-    for k in ("cpu_baseline", "parity", "multi_gpu"):
+    for k in ("cpu_baseline", "parity", "multi_gpu", "fast_math"):
         if k in head:
             out[k] = head[k]
     out["configs"] = entries
@@ -570,6 +601,7 @@ def main():
     ap.add_argument("--workload", default=HEADLINE, choices=sorted(WORKLOADS), help="the headline workload of the line")
     ap.add_argument("--configs", default="auto", choices=["auto", "all", "headline"], help="which BASELINE configurations ride along in `configs`")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-fast-math", action="store_true", help="skip the libkjb_fast.so leg (the price of the exact numeric contract)")
     ap.add_argument("--no-streaming", action="store_true", help="e2e leg with the blocking call (upload, passes, download serialised)")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     args = ap.parse_args()

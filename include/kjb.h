@@ -237,6 +237,9 @@ int  kjb_memcpy_d2d_batch_on(kjb_context *ctx, uint32_t queue, const kjb_copy_de
 #define KJB_MAX_EVENTS 64u
 int  kjb_image_upload_on(kjb_context *ctx, uint32_t queue, const kjb_image *dst, const void *host_src);
 int  kjb_image_download_on(kjb_context *ctx, uint32_t queue, const kjb_image *src, void *host_dst);
+/* the same for rows [row0, row0 + row_count) only; host pointers address the WHOLE image (tile-sharded frames move their band only) */
+int  kjb_image_upload_rows_on(kjb_context *ctx, uint32_t queue, const kjb_image *dst, const void *host_src, uint32_t row0, uint32_t row_count);
+int  kjb_image_download_rows_on(kjb_context *ctx, uint32_t queue, const kjb_image *src, void *host_dst, uint32_t row0, uint32_t row_count);
 int  kjb_event_record(kjb_context *ctx, uint32_t event, uint32_t queue);
 int  kjb_queue_wait_event(kjb_context *ctx, uint32_t queue, uint32_t event);   /* no-op if the event was never recorded */
 int  kjb_event_synchronize(kjb_context *ctx, uint32_t event);                   /* host wait; no-op if never recorded */

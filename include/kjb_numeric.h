@@ -300,4 +300,33 @@ KJB_HD float kjb_acos(float x) {
     return kjb_atan2(sqrtf((1.0f - x) * (1.0f + x)), x);
 }
 
+/* ---- KJB_FAST: the price tag of the contract.  libkjb_fast.so is the SAME source compiled with -DKJB_FAST -use_fast_math: the
+ * transcendentals below become the GPU's special-function-unit instructions (MUFU.SIN / COS / EX2 / LG2 / RCP / RSQ), division and square
+ * root their approximate forms, and a*b+c contracts to FFMA — i.e. what a shader compiler makes of the reference's HLSL.  Results are then
+ * close to, not equal to, the oracle's (tests/test_gpu_fast.py states how close); the product default stays the exact build. ---- */
+#if defined(KJB_FAST) && defined(__CUDA_ARCH__)
+#define kjb_sincos kjb_sincos_fast
+#define kjb_sin kjb_sin_fast
+#define kjb_cos kjb_cos_fast
+#define kjb_exp2 kjb_exp2_fast
+#define kjb_log2 kjb_log2_fast
+#define kjb_pow kjb_pow_fast
+#define kjb_exp kjb_exp_fast
+#define kjb_log kjb_log_fast
+#define kjb_atan kjb_atan_fast
+#define kjb_atan2 kjb_atan2_fast
+#define kjb_acos kjb_acos_fast
+KJB_HD void kjb_sincos_fast(float x, float *s, float *c) { __sincosf(x, s, c); }
+KJB_HD float kjb_sin_fast(float x) { return __sinf(x); }
+KJB_HD float kjb_cos_fast(float x) { return __cosf(x); }
+KJB_HD float kjb_exp2_fast(float x) { return exp2f(x); }
+KJB_HD float kjb_log2_fast(float x) { return __log2f(x); }
+KJB_HD float kjb_pow_fast(float x, float y) { return exp2f(y * __log2f(x)); }
+KJB_HD float kjb_exp_fast(float x) { return __expf(x); }
+KJB_HD float kjb_log_fast(float x) { return __logf(x); }
+KJB_HD float kjb_atan_fast(float x) { return atanf(x); }
+KJB_HD float kjb_atan2_fast(float y, float x) { return atan2f(y, x); }
+KJB_HD float kjb_acos_fast(float x) { return acosf(fminf(fmaxf(x, -1.0f), 1.0f)); }
+#endif
+
 #endif /* KJB_NUMERIC_H */

@@ -26,3 +26,21 @@ def lib():
         if _lib.backend != "cuda-sm100a":
             raise KjbError(f"unexpected backend {_lib.backend!r} behind {LIB_PATH}")
     return _lib
+
+
+FAST_LIB_PATH = os.path.join(_HERE, "csrc", "libkjb_fast.so")
+_fast = None
+
+
+def lib_fast():
+    """The same kernels compiled with -DKJB_FAST -use_fast_math (MUFU transcendentals, approximate division / sqrt, FMA contraction): NOT
+    bit-compatible with the oracle, never returned by lib().  Exists so that the cost of the exact numeric contract is a measured number
+    (bench.py `fast_math`, tests/test_gpu_fast.py)."""
+    global _fast
+    if _fast is None:
+        if not os.path.exists(FAST_LIB_PATH):
+            raise KjbError(f"fast-math build missing: {FAST_LIB_PATH}")
+        _fast = KjbLib(FAST_LIB_PATH)
+        if _fast.backend != "cuda-sm100a-fast":
+            raise KjbError(f"unexpected backend {_fast.backend!r} behind {FAST_LIB_PATH}")
+    return _fast

@@ -138,7 +138,7 @@ struct kjb_world {
     int err = 0;
     // ---- tile sharding: this world owns half-res rows [ty0, ty1) of every frame
     bool tiled = false; uint32_t trank = 0, tcount = 1, ty0 = 0, ty1 = 0;
-    kjb_buffer xchg_send[2]{}, xchg_recv[2]{}; uint64_t xchg_bytes_per_rank[2] = {0, 0};   // [0] end-of-frame history borders, [1] mid-frame GI bands (reflections on)
+    kjb_buffer xchg_send[3]{}, xchg_recv[3]{}; uint64_t xchg_bytes_per_rank[3] = {0, 0, 0};   // [0] end-of-frame history borders, [1] mid-frame GI bands (reflections on), [2] host-supplied inputs
     void band(uint32_t r, uint32_t rows, uint32_t& b0, uint32_t& b1) const { b0 = uint32_t(uint64_t(rows) * r / tcount); b1 = uint32_t(uint64_t(rows) * (r + 1) / tcount); }
     // restrict the next pass to the owned band grown by `e` half-res rows; `scale` = 2 for full-res passes
     uint32_t cur_row0 = 0;   // first row of the scissor last set by rows()
@@ -241,7 +241,7 @@ void kjb_world_destroy(kjb_world* w) {
     if (!w) return;
     kjb_sync(w->ctx);   // every queue: nothing of this world is in flight any more
     for (auto& kv : w->images) kjb_image_free(w->ctx, &kv.second);
-    for (int k = 0; k < 2; ++k) { if (w->xchg_send[k].data) kjb_buffer_free(w->ctx, &w->xchg_send[k]); if (w->xchg_recv[k].data) kjb_buffer_free(w->ctx, &w->xchg_recv[k]); }
+    for (int k = 0; k < 3; ++k) { if (w->xchg_send[k].data) kjb_buffer_free(w->ctx, &w->xchg_send[k]); if (w->xchg_recv[k].data) kjb_buffer_free(w->ctx, &w->xchg_recv[k]); }
     delete w;
 }
 
@@ -1062,6 +1062,20 @@ int kjb_world_render_frame(kjb_world* w, const kjb_world_frame* f) {
     kjb_image& velocity = w->img(in_prefix + "velocity", W, H, KJB_FMT_RGBA16_FLOAT);
     if (f->replay_slot) {
         // inputs already resident in HBM (captured earlier): nothing to produce
+    } else if (f->host_gbuffer && w->tiled) {
+        // Tile-sharded frame with host inputs: every rank needs the WHOLE G-buffer (rays land anywhere on screen), but pushing 32 B/px through every
+        // rank's PCIe link multiplies the host traffic by N.  Each rank uploads its band only and the bands travel between the GPUs over NVLink
+        // (one all-gather, ~17x the bandwidth of a PCIe link): N-fold less host traffic per frame.
+        const uint32_t q = streaming ? KJB_QUEUE_UPLOAD : KJB_QUEUE_COMPUTE, r0 = w->ty0 * 2, rn = (w->ty1 - w->ty0) * 2;
+        int rc = streaming ? kjb_queue_wait_event(ctx, KJB_QUEUE_UPLOAD, EV_DONE) : 0;
+        rc |= kjb_image_upload_rows_on(ctx, q, &gbuffer, f->host_gbuffer, r0, rn) | kjb_image_upload_rows_on(ctx, q, &depth, f->host_depth, r0, rn)
+            | kjb_image_upload_rows_on(ctx, q, &geometric_normal, f->host_geometric_normal, r0, rn) | kjb_image_upload_rows_on(ctx, q, &velocity, f->host_velocity, r0, rn);
+        if (streaming) rc |= kjb_event_record(ctx, EV_UP, KJB_QUEUE_UPLOAD) | kjb_queue_wait_event(ctx, KJB_QUEUE_COMPUTE, EV_UP);
+        if (rc) return rc;
+        std::vector<XchgItem> in; in.push_back({gbuffer, 2, 0}); in.push_back({depth, 2, 0}); in.push_back({geometric_normal, 2, 0}); in.push_back({velocity, 2, 0});
+        w->pass_begin("tile input all-gather");
+        if (tile_exchange(w, in, KJB_QUEUE_COMPUTE, 2)) w->err = 1;
+        w->pass_end();
     } else if (streaming) {
         // the upload queue may overwrite this input set once the passes of the frame that last used it are done
         int rc = kjb_queue_wait_event(ctx, KJB_QUEUE_UPLOAD, EV_DONE);
@@ -1178,13 +1192,20 @@ int kjb_world_render_frame(kjb_world* w, const kjb_world_frame* f) {
             kjb_image& stage = w->img("result.stage" + std::to_string(sset), result.width, result.height, result.format);
             int rc = kjb_queue_wait_event(ctx, KJB_QUEUE_COMPUTE, EV_DL);          // the previous download from this stage has drained
             rc |= kjb_image_copy(ctx, &stage, &result) | kjb_event_record(ctx, EV_DONE, KJB_QUEUE_COMPUTE);
-            rc |= kjb_queue_wait_event(ctx, KJB_QUEUE_DOWNLOAD, EV_DONE) | kjb_image_download_on(ctx, KJB_QUEUE_DOWNLOAD, &stage, f->host_result) | kjb_event_record(ctx, EV_DL, KJB_QUEUE_DOWNLOAD);
+            rc |= kjb_queue_wait_event(ctx, KJB_QUEUE_DOWNLOAD, EV_DONE);
+            rc |= w->tiled ? kjb_image_download_rows_on(ctx, KJB_QUEUE_DOWNLOAD, &stage, f->host_result, w->ty0 * 2, (w->ty1 - w->ty0) * 2)   // a rank delivers its band of the frame
+                           : kjb_image_download_on(ctx, KJB_QUEUE_DOWNLOAD, &stage, f->host_result);
+            rc |= kjb_event_record(ctx, EV_DL, KJB_QUEUE_DOWNLOAD);
             if (rc) w->err = rc;
         }
         w->stream_frames += 1;
     } else if (f->host_result && !w->err) {
         kjb_image result{};
-        if (kjb_world_get_image(w, result_name, &result) == 0) { kjb_image_download(ctx, &result, f->host_result); kjb_sync(ctx); }
+        if (kjb_world_get_image(w, result_name, &result) == 0) {
+            if (w->tiled) kjb_image_download_rows_on(ctx, KJB_QUEUE_COMPUTE, &result, f->host_result, w->ty0 * 2, (w->ty1 - w->ty0) * 2);
+            else kjb_image_download(ctx, &result, f->host_result);
+            kjb_sync(ctx);
+        }
     }
     end_frame(w);
     return w->err;

@@ -8,7 +8,8 @@ using namespace kjb;
 // coordinate of a copy is scaled by words-per-texel) or of its own 1- / 2-byte elements; the box is the tile, rows padded to 16 bytes.
 namespace kjb {
 #if defined(KJB_EMU)
-TileSource tile_source(kjb_context*, const kjb_image&, uint32_t, uint32_t) { TileSource t; t.use_tma = 0; return t; }
+TileSource tile_source(kjb_context*, const kjb_image&, uint32_t, uint32_t) { TileSource t; t.tensor_ok = 0; t.rows_ok = 0; return t; }
+int tile_mode(std::initializer_list<const TileSource*>) { return KJB_TILE_LOADS; }
 #else
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
                                   CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -16,8 +17,6 @@ static EncodeTiledFn encode_tiled_fn() {
     static EncodeTiledFn fn = [] {
         void* p = nullptr; cudaDriverEntryPointQueryResult q;
         if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) p = nullptr;
-        const char* off = getenv("KJB_NO_TMA");   // A/B switch for tools/variant_bench.py: stage every tile with guarded loads
-        if (off && off[0] == '1') p = nullptr;
         return (EncodeTiledFn)p;
     }();
     return fn;
@@ -32,7 +31,8 @@ TileSource tile_source(kjb_context* c, const kjb_image& img, uint32_t box_w, uin
     EncodeTiledFn enc = encode_tiled_fn();
     const uint32_t pitch_texels = ((box_w * tb + 15) / 16 * 16) / tb;   // == tile_pitch<tb>(box_w)
     const uint32_t words = tb >= 4 ? tb / 4 : 1;
-    if (enc && tb && (row_bytes % 16 == 0) && (uintptr_t(img.data) % 16 == 0) && pitch_texels * words <= 256 && box_h <= 256 && (img.layers <= 1)) {
+    t.rows_ok = tb && (row_bytes % 16 == 0) && (uintptr_t(img.data) % 16 == 0) && img.layers <= 1;
+    if (enc && t.rows_ok && pitch_texels * words <= 256 && box_h <= 256) {
         const CUtensorMapDataType dt = tb >= 4 ? CU_TENSOR_MAP_DATA_TYPE_UINT32 : (tb == 2 ? CU_TENSOR_MAP_DATA_TYPE_UINT16 : CU_TENSOR_MAP_DATA_TYPE_UINT8);
         const cuuint64_t dims[2] = {cuuint64_t(img.width) * words, img.height};
         const cuuint64_t strides[1] = {row_bytes};
@@ -40,10 +40,27 @@ TileSource tile_source(kjb_context* c, const kjb_image& img, uint32_t box_w, uin
         const cuuint32_t estr[2] = {1, 1};
         if (enc(&t.map, dt, 2, img.data, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                 CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS)
-            t.use_tma = 1;
+            t.tensor_ok = 1;
     }
     c->tile_sources[key] = t;
     return t;
+}
+int tile_mode(std::initializer_list<const TileSource*> sources) {
+    // Preference: per-row bulk copies (UBLKCP) by default.  The tensor-map form (UTMALDG) is complete but opt-in: on the B200 boxes of this
+    // pool every cp.async.bulk.tensor — ours, and NVIDIA's own libcu++ wrapper in tools/tma_probe.cu — raises "illegal instruction" while
+    // cp.async.bulk works (profiles/r02_tma_probe.txt), so it cannot be the default here.  KJB_TILE_MODE=loads is the A/B switch.
+    static const int pref = [] {
+        const char* e = getenv("KJB_TILE_MODE"); const char* off = getenv("KJB_NO_TMA");
+        if (off && off[0] == '1') return KJB_TILE_LOADS;
+        if (e && !strcmp(e, "loads")) return KJB_TILE_LOADS;
+        if (e && !strcmp(e, "tensor")) return KJB_TILE_TMA_TENSOR;
+        return KJB_TILE_TMA_ROWS;
+    }();
+    bool tensor = true, rows = true;
+    for (const TileSource* t : sources) { tensor = tensor && t->tensor_ok; rows = rows && t->rows_ok; }
+    if (pref == KJB_TILE_TMA_TENSOR && tensor) return KJB_TILE_TMA_TENSOR;
+    if (pref != KJB_TILE_LOADS && rows) return KJB_TILE_TMA_ROWS;
+    return KJB_TILE_LOADS;
 }
 #endif
 }  // namespace kjb
@@ -128,7 +145,11 @@ int kjb_abi_version(void) { return KJB_ABI_VERSION; }
 #if defined(KJB_EMU)
 const char* kjb_backend_name(void) { return "emu-cpu"; }
 #else
+#if defined(KJB_FAST)
+const char* kjb_backend_name(void) { return "cuda-sm100a-fast"; }   // approximate-math build (include/kjb_numeric.h, KJB_FAST): never the default
+#else
 const char* kjb_backend_name(void) { return "cuda-sm100a"; }
+#endif
 #endif
 
 static thread_local std::string g_create_error;
@@ -199,6 +220,12 @@ int kjb_image_download(kjb_context* c, const kjb_image* src, void* dst) { return
 #if defined(KJB_EMU)
 int kjb_image_upload_on(kjb_context* c, uint32_t, const kjb_image* dst, const void* src) { return kjb_image_upload(c, dst, src); }
 int kjb_image_download_on(kjb_context* c, uint32_t, const kjb_image* src, void* dst) { return kjb_image_download(c, src, dst); }
+int kjb_image_upload_rows_on(kjb_context* c, uint32_t, const kjb_image* dst, const void* src, uint32_t r0, uint32_t n) {
+    if (r0 + n > dst->height) return c->fail("kjb_image_upload_rows_on: rows out of range");
+    const size_t rb = size_t(dst->width) * texel_bytes(dst->format); c->invalidate_positions(); memcpy((char*)dst->data + rb * r0, (const char*)src + rb * r0, rb * n); return 0; }
+int kjb_image_download_rows_on(kjb_context* c, uint32_t, const kjb_image* src, void* dst, uint32_t r0, uint32_t n) {
+    if (r0 + n > src->height) return c->fail("kjb_image_download_rows_on: rows out of range");
+    const size_t rb = size_t(src->width) * texel_bytes(src->format); memcpy((char*)dst + rb * r0, (const char*)src->data + rb * r0, rb * n); return 0; }
 int kjb_event_record(kjb_context*, uint32_t, uint32_t) { return 0; }
 int kjb_queue_wait_event(kjb_context*, uint32_t, uint32_t) { return 0; }
 int kjb_event_synchronize(kjb_context*, uint32_t) { return 0; }
@@ -207,6 +234,19 @@ int kjb_image_upload_on(kjb_context* c, uint32_t q, const kjb_image* dst, const 
     c->invalidate_positions();
     cudaStream_t st = c->queue(q); if (!st) return c->fail("kjb_image_upload_on: bad queue");
     return cudaMemcpyAsync(dst->data, src, image_bytes(*dst), cudaMemcpyHostToDevice, st) != cudaSuccess ? c->fail("kjb_image_upload_on: copy failed") : 0;
+}
+int kjb_image_upload_rows_on(kjb_context* c, uint32_t q, const kjb_image* dst, const void* src, uint32_t r0, uint32_t n) {
+    if (r0 + n > dst->height || (dst->layers > 1)) return c->fail("kjb_image_upload_rows_on: rows out of range");
+    c->invalidate_positions();
+    cudaStream_t st = c->queue(q); if (!st) return c->fail("kjb_image_upload_rows_on: bad queue");
+    const size_t rb = size_t(dst->width) * texel_bytes(dst->format);
+    return cudaMemcpyAsync((char*)dst->data + rb * r0, (const char*)src + rb * r0, rb * n, cudaMemcpyHostToDevice, st) != cudaSuccess ? c->fail("kjb_image_upload_rows_on: copy failed") : 0;
+}
+int kjb_image_download_rows_on(kjb_context* c, uint32_t q, const kjb_image* src, void* dst, uint32_t r0, uint32_t n) {
+    if (r0 + n > src->height || (src->layers > 1)) return c->fail("kjb_image_download_rows_on: rows out of range");
+    cudaStream_t st = c->queue(q); if (!st) return c->fail("kjb_image_download_rows_on: bad queue");
+    const size_t rb = size_t(src->width) * texel_bytes(src->format);
+    return cudaMemcpyAsync((char*)dst + rb * r0, (const char*)src->data + rb * r0, rb * n, cudaMemcpyDeviceToHost, st) != cudaSuccess ? c->fail("kjb_image_download_rows_on: copy failed") : 0;
 }
 int kjb_image_download_on(kjb_context* c, uint32_t q, const kjb_image* src, void* dst) {
     cudaStream_t st = c->queue(q); if (!st) return c->fail("kjb_image_download_on: bad queue");

@@ -7,6 +7,7 @@
 #include "kjb_tile.cuh"
 #include <map>
 #include <tuple>
+#include <initializer_list>
 #include <string>
 #include <vector>
 #include <cstdio>
@@ -124,6 +125,8 @@ inline uint32_t texel_bytes(uint32_t f);
 // TileSource of `img` for tiles of box_w x box_h texels (kjb_tile.cuh).  use_tma = 0 when the image cannot be described to the copy engine
 // (row pitch or base not 16-byte aligned, driver entry point missing): the kernels then stage the same tile with guarded loads.
 kjb::TileSource tile_source(kjb_context* c, const kjb_image& img, uint32_t box_w, uint32_t box_h);
+// staging mode of one launch (KJB_TILE_*): what every source of the launch supports, under the process-wide preference KJB_TILE_MODE = rows | tensor | loads
+int tile_mode(std::initializer_list<const kjb::TileSource*> sources);
 
 inline uint32_t texel_bytes(uint32_t f) {
     switch (f) {

@@ -113,37 +113,36 @@ KJB_KERNEL(32) k_ircache_age_serial(uint32_t* meta, uint32_t* gm, uint32_t* entr
 }
 
 // ------------------------------------------------------------------ I5 prefix_scan/*.hlsl: inclusive scan of <= 64 Ki u32 in one CTA
-// Replaces the reference's 3-pass 1 Mi-element scan (prefix_scan.rs:10-39).  The array is walked in chunks of 8192: coalesced load into
-// shared memory, each of the 1024 threads scans 8 consecutive values, a Hillis-Steele scan of the 1024 partials, carry from the
-// previous chunk, coalesced store.
+// Replaces the reference's 3-pass 1 Mi-element scan (prefix_scan.rs:10-39).  Each of the 1024 threads owns n / 1024 CONSECUTIVE values: it sums
+// them, the 1024 thread totals are scanned with warp shuffles (SHFL.UP inside each warp, then once more over the 32 warp totals), and the
+// thread rewrites its values with the running sum — two barriers instead of the twenty-odd of a shared-memory Hillis-Steele scan per chunk.
 KJB_KERNEL(1024) k_inclusive_prefix_scan(uint32_t* d, uint32_t n, Rows kjb_rows) {
-    __shared__ uint32_t chunk[8192];
-    __shared__ uint32_t partial[1024];
-    __shared__ uint32_t carry_s;
-    const uint32_t t = threadIdx.x;
-    if (t == 0) carry_s = 0;
+    __shared__ uint32_t warp_tot[32];
+    const uint32_t t = threadIdx.x, per = (n + 1023u) / 1024u;
+    const uint32_t b = t * per < n ? t * per : n, e = b + per < n ? b + per : n;
+    uint32_t s = 0;
+    for (uint32_t i = b; i < e; ++i) s += d[i];
+#if !defined(KJB_EMU)
+    const uint32_t lane = t & 31u, warp = t >> 5;
+    uint32_t inc = s;
+    for (uint32_t off = 1; off < 32u; off <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, inc, off); if (lane >= off) inc += v; }
+    if (lane == 31u) warp_tot[warp] = inc;
     __syncthreads();
-    for (uint32_t base = 0; base < n; base += 8192u) {
-        for (uint32_t k = 0; k < 8u; ++k) { const uint32_t i = base + k * 1024u + t; chunk[k * 1024u + t] = i < n ? d[i] : 0u; }
-        __syncthreads();
-        uint32_t s = 0;
-        for (uint32_t k = 0; k < 8u; ++k) { s += chunk[t * 8u + k]; chunk[t * 8u + k] = s; }   // inclusive within the thread's 8 values
-        partial[t] = s;
-        __syncthreads();
-        for (uint32_t off = 1; off < 1024u; off <<= 1) {
-            const uint32_t v = t >= off ? partial[t - off] : 0u;
-            __syncthreads();
-            partial[t] += v;
-            __syncthreads();
-        }
-        const uint32_t before = (t ? partial[t - 1] : 0u) + carry_s;
-        for (uint32_t k = 0; k < 8u; ++k) chunk[t * 8u + k] += before;
-        __syncthreads();
-        for (uint32_t k = 0; k < 8u; ++k) { const uint32_t i = base + k * 1024u + t; if (i < n) d[i] = chunk[k * 1024u + t]; }
-        __syncthreads();
-        if (t == 0) carry_s += partial[1023];
-        __syncthreads();
+    if (warp == 0) {
+        uint32_t w = warp_tot[lane];
+        for (uint32_t off = 1; off < 32u; off <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, w, off); if (lane >= off) w += v; }
+        warp_tot[lane] = w;
     }
+    __syncthreads();
+    uint32_t acc = (inc - s) + (warp ? warp_tot[warp - 1] : 0u);
+#else
+    static thread_local uint32_t tot[1024];
+    (void)warp_tot;
+    tot[t] = s; __syncthreads();
+    uint32_t acc = 0; for (uint32_t k = 0; k < t; ++k) acc += tot[k];
+    __syncthreads();
+#endif
+    for (uint32_t i = b; i < e; ++i) { acc += d[i]; d[i] = acc; }
 }
 
 // ------------------------------------------------------------------ I6 ircache_compact_entries.hlsl

@@ -84,38 +84,43 @@ KJB_KERNEL(256) k_taa_reproject(Globals g, Img history_tex, Img reprojection_tex
 // of a tap's weight that does not depend on the luma cutoff (depth term x spatial weight) is evaluated once for both passes.  `pow(t, 8)`
 // of t == 1 is exactly 1 under the numeric contract (kjb_log2(1) = 0, kjb_exp2(0) = 1), which is every tap of the first pass
 // (cutoff 1e10): those skip the exp2/log2 pair.  Same operations in the same order per output value => the same bits as t2_inner.
-#define T2_TW 34
+// tile origins are 16-byte aligned in their image (row-wise bulk copies need it): 2 texels of left apron for the 8-byte RGBA16F texels, 4 for R32F depth
+#define T2_TW 36
+#define T2_AX 2
+#define T2_DW 40
+#define T2_DX 4
+#define T2_LW 34   /* the logical (32+2)-wide footprint the decoded arrays hold */
 #define T2_TH 10
 KJB_DEVONLY float t2_pow8_sat(float luma_cutoff, float luma) { const float t = kjb_saturate(luma_cutoff / luma); return t == 1.0f ? 1.0f : kjb_pow(t, 8.0f); }
 KJB_KERNEL(256) k_taa_filter_input_tiled(const __grid_constant__ TileSource ts_input, const __grid_constant__ TileSource ts_depth, int use_tma, Img input_tex, Img depth_tex,
                                          ImgW output_tex, ImgW dev_output_tex, W9 dw, Rows kjb_rows) {
-    constexpr int P8 = tile_pitch<8>(T2_TW), P4 = tile_pitch<4>(T2_TW);
+    constexpr int P8 = tile_pitch<8>(T2_TW), P4 = tile_pitch<4>(T2_DW);
     __shared__ __align__(128) uint2 s_raw[P8 * T2_TH];
     __shared__ __align__(128) float s_depth[P4 * T2_TH];
-    __shared__ float s_y[T2_TW * T2_TH], s_cb[T2_TW * T2_TH], s_cr[T2_TW * T2_TH];
+    __shared__ float s_y[T2_LW * T2_TH], s_cb[T2_LW * T2_TH], s_cr[T2_LW * T2_TH];
     __shared__ __align__(8) uint64_t bar;
     const int tid = int(threadIdx.y) * 32 + int(threadIdx.x);
-    const int bx0 = int(blockIdx.x) * 32 - 1, by0 = kjb_rows.y0 + int(blockIdx.y) * 8 - 1;
-    tile_group_begin(&bar, 0, use_tma, tile_bytes<uint2, T2_TW, T2_TH>() + tile_bytes<float, T2_TW, T2_TH>(), tid);
-    tile_issue<uint2, T2_TW, T2_TH>(s_raw, ts_input, input_tex, bx0, by0, &bar, use_tma, tid, 256);
-    tile_issue<float, T2_TW, T2_TH>(s_depth, ts_depth, depth_tex, bx0, by0, &bar, use_tma, tid, 256);
-    tile_group_wait(&bar, 0, use_tma);
-    for (int i = tid; i < T2_TW * T2_TH; i += 256) {
-        const int lx = i % T2_TW, ly = i / T2_TW;
-        const float3 c = taa_input_remap(half4_to_float4(s_raw[ly * P8 + lx]));
+    const int bx0 = int(blockIdx.x) * 32, by0 = kjb_rows.y0 + int(blockIdx.y) * 8 - 1;
+    tile_group_begin(&bar, 0, use_tma, tid);
+    uint32_t staged = tile_issue<uint2, T2_TW, T2_TH>(s_raw, ts_input, input_tex, bx0 - T2_AX, by0, &bar, use_tma, tid, 256);
+    staged += tile_issue<float, T2_DW, T2_TH>(s_depth, ts_depth, depth_tex, bx0 - T2_DX, by0, &bar, use_tma, tid, 256);
+    tile_group_wait(&bar, 0, use_tma, staged, tid);
+    for (int i = tid; i < T2_LW * T2_TH; i += 256) {
+        const int lx = i % T2_LW, ly = i / T2_LW;
+        const float3 c = taa_input_remap(half4_to_float4(s_raw[ly * P8 + lx + (T2_AX - 1)]));
         s_y[i] = c.x; s_cb[i] = c.y; s_cr[i] = c.z;
     }
     __syncthreads();
     const int x = int(blockIdx.x) * 32 + int(threadIdx.x), y = kjb_rows.y0 + int(blockIdx.y) * 8 + int(threadIdx.y);
     if (x >= output_tex.w || y >= output_tex.h || y >= kjb_rows.y1) return;
     const int tx = int(threadIdx.x) + 1, ty = int(threadIdx.y) + 1;
-    const float center_depth = s_depth[ty * P4 + tx];
+    const float center_depth = s_depth[ty * P4 + tx + (T2_DX - 1)];
     float wd[9];
     float3 iex = f3(0.0f), iex2 = f3(0.0f), clamped_iex = f3(0.0f); float iwsum = 0, clamped_iwsum = 0;
     for (int yy = -1; yy <= 1; ++yy) for (int xx = -1; xx <= 1; ++xx) {
-        const int k = (yy + 1) * 3 + (xx + 1), ti = (ty + yy) * T2_TW + (tx + xx);
+        const int k = (yy + 1) * 3 + (xx + 1), ti = (ty + yy) * T2_LW + (tx + xx);
         const float3 sv = f3(s_y[ti], s_cb[ti], s_cr[ti]);
-        const float depth = s_depth[(ty + yy) * P4 + (tx + xx)];
+        const float depth = s_depth[(ty + yy) * P4 + (tx + xx) + (T2_DX - 1)];
         float w = 1;
         w *= kjb_exp2(-kjb_min(16.0f, 200.0f * inverse_depth_relative_diff(center_depth, depth)));
         w *= dw.w[k];
@@ -130,7 +135,7 @@ KJB_KERNEL(256) k_taa_filter_input_tiled(const __grid_constant__ TileSource ts_i
     const float luma_cutoff = fi_clamped_ex.x * 1.001f;
     clamped_iex = f3(0.0f); clamped_iwsum = 0;
     for (int yy = -1; yy <= 1; ++yy) for (int xx = -1; xx <= 1; ++xx) {
-        const int k = (yy + 1) * 3 + (xx + 1), ti = (ty + yy) * T2_TW + (tx + xx);
+        const int k = (yy + 1) * 3 + (xx + 1), ti = (ty + yy) * T2_LW + (tx + xx);
         const float3 sv = f3(s_y[ti], s_cb[ti], s_cr[ti]);
         const float w = wd[k] * t2_pow8_sat(luma_cutoff, sv.x);
         clamped_iwsum += w; clamped_iex = mad(sv, w, clamped_iex);
@@ -165,16 +170,16 @@ KJB_KERNEL(256) k_taa_filter_history(Img input_tex, ImgW output_tex, float4 its,
 KJB_KERNEL(256) k_taa_filter_history_tiled(const __grid_constant__ TileSource ts_input, int use_tma, Img input_tex, ImgW output_tex, float4 its, float4 ots, W25t dw, Rows kjb_rows) {
     constexpr int P8 = tile_pitch<8>(T2_TW);
     __shared__ __align__(128) uint2 s_raw[P8 * T2_TH];
-    __shared__ float s_y[T2_TW * T2_TH], s_cb[T2_TW * T2_TH], s_cr[T2_TW * T2_TH];
+    __shared__ float s_y[T2_LW * T2_TH], s_cb[T2_LW * T2_TH], s_cr[T2_LW * T2_TH];
     __shared__ __align__(8) uint64_t bar;
     const int tid = int(threadIdx.y) * 32 + int(threadIdx.x);
-    const int bx0 = int(blockIdx.x) * 32 - 1, by0 = kjb_rows.y0 + int(blockIdx.y) * 8 - 1;
-    tile_group_begin(&bar, 0, use_tma, tile_bytes<uint2, T2_TW, T2_TH>(), tid);
-    tile_issue<uint2, T2_TW, T2_TH>(s_raw, ts_input, input_tex, bx0, by0, &bar, use_tma, tid, 256);
-    tile_group_wait(&bar, 0, use_tma);
-    for (int i = tid; i < T2_TW * T2_TH; i += 256) {
-        const int lx = i % T2_TW, ly = i / T2_TW;
-        const float3 c = rgb_to_ycbcr(xyz(half4_to_float4(s_raw[ly * P8 + lx])));
+    const int bx0 = int(blockIdx.x) * 32 - 1, by0 = kjb_rows.y0 + int(blockIdx.y) * 8 - 1;   // logical footprint origin
+    tile_group_begin(&bar, 0, use_tma, tid);
+    const uint32_t staged = tile_issue<uint2, T2_TW, T2_TH>(s_raw, ts_input, input_tex, bx0 + 1 - T2_AX, by0, &bar, use_tma, tid, 256);
+    tile_group_wait(&bar, 0, use_tma, staged, tid);
+    for (int i = tid; i < T2_LW * T2_TH; i += 256) {
+        const int lx = i % T2_LW, ly = i / T2_LW;
+        const float3 c = rgb_to_ycbcr(xyz(half4_to_float4(s_raw[ly * P8 + lx + (T2_AX - 1)])));
         s_y[i] = c.x; s_cb[i] = c.y; s_cr[i] = c.z;
     }
     __syncthreads();
@@ -184,11 +189,11 @@ KJB_KERNEL(256) k_taa_filter_history_tiled(const __grid_constant__ TileSource ts
     const float2 uv = get_uv(x, y, s4);
     const int sx = kjb_cvt_i32(kjb_floor(uv.x * its.x + 1e-3f)), sy = kjb_cvt_i32(kjb_floor(uv.y * its.y + 1e-3f));
     const int tx = sx - bx0, ty = sy - by0;   // == threadIdx + 1 whenever the two extents are equal; a texel the tile does not hold falls back to global loads
-    const bool in_tile = tx >= 1 && tx <= T2_TW - 2 && ty >= 1 && ty <= T2_TH - 2;
+    const bool in_tile = tx >= 1 && tx <= T2_LW - 2 && ty >= 1 && ty <= T2_TH - 2;
     float3 iex = f3(0.0f); float iwsum = 0; float3 taps[9];
     for (int yy = -1; yy <= 1; ++yy) for (int xx = -1; xx <= 1; ++xx) {
         const int k = (yy + 1) * 3 + (xx + 1);
-        taps[k] = in_tile ? f3(s_y[(ty + yy) * T2_TW + tx + xx], s_cb[(ty + yy) * T2_TW + tx + xx], s_cr[(ty + yy) * T2_TW + tx + xx]) : rgb_to_ycbcr(xyz(ld_rgba16f(input_tex, sx + xx, sy + yy)));
+        taps[k] = in_tile ? f3(s_y[(ty + yy) * T2_LW + tx + xx], s_cb[(ty + yy) * T2_LW + tx + xx], s_cr[(ty + yy) * T2_LW + tx + xx]) : rgb_to_ycbcr(xyz(ld_rgba16f(input_tex, sx + xx, sy + yy)));
         float w = 1;
         w *= dw.w[(yy + 2) * 5 + (xx + 2)];
         w *= t2_pow8_sat(1e10f, taps[k].x);
@@ -396,17 +401,17 @@ KJB_KERNEL(256) k_taa_tiled(const __grid_constant__ TileSource ts_history, const
     __shared__ __align__(128) uint2 s_hraw[PH * T7_HH];
     __shared__ __align__(128) uint2 s_iraw[PI * T2_TH];
     __shared__ float4 s_hist[T7_HW * T7_HH];
-    __shared__ float s_y[T2_TW * T2_TH], s_cb[T2_TW * T2_TH], s_cr[T2_TW * T2_TH];
+    __shared__ float s_y[T2_LW * T2_TH], s_cb[T2_LW * T2_TH], s_cr[T2_LW * T2_TH];
     __shared__ __align__(8) uint64_t bar;
     const int tid = int(threadIdx.y) * 32 + int(threadIdx.x);
     const int bx0 = int(blockIdx.x) * 32, by0 = kjb_rows.y0 + int(blockIdx.y) * 8;
-    tile_group_begin(&bar, 0, use_tma, tile_bytes<uint2, T7_HW, T7_HH>() + tile_bytes<uint2, T2_TW, T2_TH>(), tid);
-    tile_issue<uint2, T7_HW, T7_HH>(s_hraw, ts_history, t.history_tex, bx0 - 2, by0 - 2, &bar, use_tma, tid, 256);
-    tile_issue<uint2, T2_TW, T2_TH>(s_iraw, ts_input, t.input_tex, bx0 - 1, by0 - 1, &bar, use_tma, tid, 256);
-    tile_group_wait(&bar, 0, use_tma);
+    tile_group_begin(&bar, 0, use_tma, tid);
+    uint32_t staged = tile_issue<uint2, T7_HW, T7_HH>(s_hraw, ts_history, t.history_tex, bx0 - 2, by0 - 2, &bar, use_tma, tid, 256);
+    staged += tile_issue<uint2, T2_TW, T2_TH>(s_iraw, ts_input, t.input_tex, bx0 - T2_AX, by0 - 1, &bar, use_tma, tid, 256);
+    tile_group_wait(&bar, 0, use_tma, staged, tid);
     for (int i = tid; i < T7_HW * T7_HH; i += 256) s_hist[i] = half4_to_float4(s_hraw[(i / T7_HW) * PH + (i % T7_HW)]);
-    for (int i = tid; i < T2_TW * T2_TH; i += 256) {
-        const float3 c = taa_input_remap(half4_to_float4(s_iraw[(i / T2_TW) * PI + (i % T2_TW)]));
+    for (int i = tid; i < T2_LW * T2_TH; i += 256) {
+        const float3 c = taa_input_remap(half4_to_float4(s_iraw[(i / T2_LW) * PI + (i % T2_LW) + (T2_AX - 1)]));
         s_y[i] = c.x; s_cb[i] = c.y; s_cr[i] = c.z;
     }
     __syncthreads();
@@ -414,7 +419,7 @@ KJB_KERNEL(256) k_taa_tiled(const __grid_constant__ TileSource ts_history, const
     if (x >= t.temporal_output_tex.w || y >= t.temporal_output_tex.h || y >= kjb_rows.y1) return;
     const int tx = int(threadIdx.x), ty = int(threadIdx.y);
     taa_px(g, t, its, ots, bw, x, y, [&](int xx, int yy) { return s_hist[(ty + 2 + yy) * T7_HW + (tx + 2 + xx)]; },
-           [&](int bx, int by, int dx, int dy) { const int ti = (by - by0 + 1 + dy) * T2_TW + (bx - bx0 + 1 + dx); return f3(s_y[ti], s_cb[ti], s_cr[ti]); });
+           [&](int bx, int by, int dx, int dy) { const int ti = (by - by0 + 1 + dy) * T2_LW + (bx - bx0 + 1 + dx); return f3(s_y[ti], s_cb[ti], s_cr[ti]); });
 }
 
 #define F4A(a) f4((a)[0], (a)[1], (a)[2], (a)[3])
@@ -438,8 +443,8 @@ int kjb_pass_taa_filter_input(kjb_context* c, const kjb_taa_filter_input_args* a
     CHKE(a->dev_output_tex, KJB_FMT_RGBA16_FLOAT, "dev_output_tex", W, H);
     W9 dw; for (int y = -1; y <= 1; ++y) for (int x = -1; x <= 1; ++x) dw.w[(y + 1) * 3 + (x + 1)] = kjb_exp(-(0.8f / float(1 * 1)) * float(x * x + y * y));
     KJB_ROWS(c, H);
-    const TileSource ts_in = tile_source(c, a->input_tex, T2_TW, T2_TH), ts_depth = tile_source(c, a->depth_tex, T2_TW, T2_TH);
-    KJB_LAUNCH_SYNC(c, k_taa_filter_input_tiled, KJB_GRID2D(W, H, 32, 8), ts_in, ts_depth, ts_in.use_tma & ts_depth.use_tma, img_ro(a->input_tex), img_ro(a->depth_tex), img_rw(a->output_tex), img_rw(a->dev_output_tex), dw);
+    const TileSource ts_in = tile_source(c, a->input_tex, T2_TW, T2_TH), ts_depth = tile_source(c, a->depth_tex, T2_DW, T2_TH);
+    KJB_LAUNCH_SYNC(c, k_taa_filter_input_tiled, KJB_GRID2D(W, H, 32, 8), ts_in, ts_depth, tile_mode({&ts_in, &ts_depth}), img_ro(a->input_tex), img_ro(a->depth_tex), img_rw(a->output_tex), img_rw(a->dev_output_tex), dw);
     KJB_PASS_EPILOGUE(c, P);
 }
 int kjb_pass_taa_filter_history(kjb_context* c, const kjb_taa_filter_history_args* a) {
@@ -450,7 +455,7 @@ int kjb_pass_taa_filter_history(kjb_context* c, const kjb_taa_filter_history_arg
     KJB_ROWS(c, H);
     if (k == 1 && a->input_tex.width == W && a->input_tex.height == H) {
         const TileSource ts_in = tile_source(c, a->input_tex, T2_TW, T2_TH);
-        KJB_LAUNCH_SYNC(c, k_taa_filter_history_tiled, KJB_GRID2D(W, H, 32, 8), ts_in, ts_in.use_tma, img_ro(a->input_tex), img_rw(a->output_tex), F4A(a->input_tex_size), F4A(a->output_tex_size), dw);
+        KJB_LAUNCH_SYNC(c, k_taa_filter_history_tiled, KJB_GRID2D(W, H, 32, 8), ts_in, tile_mode({&ts_in}), img_ro(a->input_tex), img_rw(a->output_tex), F4A(a->input_tex_size), F4A(a->output_tex_size), dw);
     } else
         KJB_LAUNCH(c, k_taa_filter_history, KJB_GRID2D(W, H, 32, 8), img_ro(a->input_tex), img_rw(a->output_tex), F4A(a->input_tex_size), F4A(a->output_tex_size), k, dw);
     KJB_PASS_EPILOGUE(c, P);
@@ -494,7 +499,7 @@ int kjb_pass_taa(kjb_context* c, const kjb_taa_args* a) {
     KJB_ROWS(c, H);
     if (a->input_tex.width == W && a->input_tex.height == H) {
         const TileSource ts_h = tile_source(c, a->history_tex, T7_HW, T7_HH), ts_i = tile_source(c, a->input_tex, T2_TW, T2_TH);
-        KJB_LAUNCH_SYNC(c, k_taa_tiled, KJB_GRID2D(W, H, 32, 8), ts_h, ts_i, ts_h.use_tma & ts_i.use_tma, c->g, t, F4A(a->input_tex_size), F4A(a->output_tex_size), bw);
+        KJB_LAUNCH_SYNC(c, k_taa_tiled, KJB_GRID2D(W, H, 32, 8), ts_h, ts_i, tile_mode({&ts_h, &ts_i}), c->g, t, F4A(a->input_tex_size), F4A(a->output_tex_size), bw);
     } else
         KJB_LAUNCH(c, k_taa, KJB_GRID2D(W, H, 32, 8), c->g, t, F4A(a->input_tex_size), F4A(a->output_tex_size), bw);
     KJB_PASS_EPILOGUE(c, P);

@@ -83,6 +83,12 @@ int kjb_set_debug_serial(kjb_context* c, uint32_t on) { c->cache_passes_parallel
 int kjb_set_option(kjb_context*, uint32_t, uint32_t) { return 0; }   // performance options do not exist here
 int kjb_image_upload_on(kjb_context* c, uint32_t, const kjb_image* dst, const void* src) { return kjb_image_upload(c, dst, src); }
 int kjb_image_download_on(kjb_context* c, uint32_t, const kjb_image* src, void* dst) { return kjb_image_download(c, src, dst); }
+int kjb_image_upload_rows_on(kjb_context*, uint32_t, const kjb_image* dst, const void* src, uint32_t r0, uint32_t n) {
+    if (r0 + n > dst->height) return 1;
+    const size_t rb = size_t(dst->width) * kjb_format_texel_bytes(dst->format); memcpy((char*)dst->data + rb * r0, (const char*)src + rb * r0, rb * n); return 0; }
+int kjb_image_download_rows_on(kjb_context*, uint32_t, const kjb_image* src, void* dst, uint32_t r0, uint32_t n) {
+    if (r0 + n > src->height) return 1;
+    const size_t rb = size_t(src->width) * kjb_format_texel_bytes(src->format); memcpy((char*)dst + rb * r0, (const char*)src->data + rb * r0, rb * n); return 0; }
 int kjb_event_record(kjb_context*, uint32_t, uint32_t) { return 0; }
 int kjb_queue_wait_event(kjb_context*, uint32_t, uint32_t) { return 0; }
 int kjb_event_synchronize(kjb_context*, uint32_t) { return 0; }   // the oracle's cache passes are always serial

@@ -71,6 +71,8 @@ int kjb_memcpy_d2d_batch(kjb_context*, const kjb_copy_desc*, uint32_t) { return 
 int kjb_memcpy_d2d_batch_on(kjb_context*, uint32_t, const kjb_copy_desc*, uint32_t) { return 0; }
 int kjb_image_upload_on(kjb_context*, uint32_t, const kjb_image*, const void*) { return 0; }
 int kjb_image_download_on(kjb_context*, uint32_t, const kjb_image*, void*) { return 0; }
+int kjb_image_upload_rows_on(kjb_context*, uint32_t, const kjb_image*, const void*, uint32_t, uint32_t) { return 0; }
+int kjb_image_download_rows_on(kjb_context*, uint32_t, const kjb_image*, void*, uint32_t, uint32_t) { return 0; }
 int kjb_event_record(kjb_context*, uint32_t, uint32_t) { return 0; }
 int kjb_queue_wait_event(kjb_context*, uint32_t, uint32_t) { return 0; }
 int kjb_event_synchronize(kjb_context*, uint32_t) { return 0; }

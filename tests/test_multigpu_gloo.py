@@ -15,7 +15,7 @@ def _free_port():
     s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
 
 
-def _worker(rank, world_size, port, enable_taa, H, ret, enable_rtr=False):
+def _worker(rank, world_size, port, enable_taa, H, ret, enable_rtr=False, host_inputs=False):
     sys.path.insert(0, ROOT); sys.path.insert(0, HERE)
     os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
     os.environ["KJB_EMU_THREADS"] = "2"
@@ -44,9 +44,16 @@ def _worker(rank, world_size, port, enable_taa, H, ret, enable_rtr=False):
 
     tiled.comm_set_callback(allgather, rank, world_size)
     full = parity.make_world(lib, scene, W, H, **kw)
-    for _ in range(FRAMES):
-        tiled.render_frame(**view); full.render_frame(**view)
     hh = (H + 1) // 2
+    band_result = None
+    for _ in range(FRAMES):
+        full.render_frame(**view)
+        if host_inputs:   # the G-buffer arrives from the host: the rank uploads ITS band, the bands travel through an extra all-gather, the result comes back band-wise
+            inputs = [full.image(n).copy() for n in ("gbuffer", "depth", "geometric_normal", "velocity")]
+            band_result = np.zeros((H, W, 4), np.float16)
+            tiled.render_frame(host_inputs=tuple(a.ctypes.data for a in inputs), host_result=band_result.ctypes.data, **view)
+        else:
+            tiled.render_frame(**view)
     y0, y1 = hh * rank // world_size, hh * (rank + 1) // world_size
     bad = []
     names = ["rtdgi.spatial_filtered", "rtdgi.temporal_filtered", "rtdgi.irradiance"] + [n for n in full.image_names() if n.endswith(":0") or n.endswith(":1")]
@@ -60,6 +67,11 @@ def _worker(rank, world_size, port, enable_taa, H, ret, enable_rtr=False):
         ra, rb = a[y0 * s:y1 * s].view(np.uint8), b[y0 * s:y1 * s].view(np.uint8)
         if not np.array_equal(ra, rb):
             bad.append((n, int((ra != rb).any(-1).sum())))
+    if host_inputs:
+        y0f, y1f = 2 * (hh * rank // world_size), 2 * (hh * (rank + 1) // world_size)
+        want = full.image("taa.this_frame_out" if enable_taa else "rtdgi.spatial_filtered")
+        if not np.array_equal(band_result[y0f:y1f].view(np.uint16), want[y0f:y1f].view(np.uint16)):
+            bad.append(("host_result band", -1))
     ret[rank] = (bad, calls[0])
     dist.destroy_process_group()
 
@@ -131,3 +143,14 @@ def test_tile_sharded_reflections_match_single_process(emu_lib):
         bad, calls = ret[rank]
         assert calls == 2 * FRAMES, "two all-gathers per frame: this frame's GI for the reflection rays, then the history borders"
         assert not bad, f"rank {rank}: band differs from the single-process frame: {bad}"
+
+
+def test_tile_sharded_frames_with_host_inputs(emu_lib):
+    """host G-buffers in, result out, 2 ranks: each rank uploads only its band of the inputs, an all-gather distributes the bands (NVLink on the B200),
+    the frame is rendered tile-sharded and each rank hands back its band of the result — bit-identical to the single-process frame"""
+    ret = mp.Manager().dict()
+    mp.spawn(_worker, args=(2, _free_port(), False, H, ret, False, True), nprocs=2, join=True)
+    for rank in range(2):
+        bad, calls = ret[rank]
+        assert calls == 2 * FRAMES, "input bands + history borders"
+        assert not bad, f"rank {rank}: {bad}"

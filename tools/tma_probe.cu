@@ -48,6 +48,26 @@ __global__ void k_global_desc(const CUtensorMap* map, uint32_t* out, int x0, int
     mbar_wait(&bar, 0);
     for (int i = threadIdx.x; i < BW * BH; i += blockDim.x) out[i] = tile[i];
 }
+__global__ void k_mbar_only(uint32_t* out) {
+    __shared__ __align__(8) uint64_t bar;
+    if (threadIdx.x == 0) mbar_init(&bar, 1);
+    __syncthreads();
+    if (threadIdx.x == 0) mbar_expect_tx(&bar, 0);
+    mbar_wait(&bar, 0);
+    out[threadIdx.x] = 7u + threadIdx.x;
+}
+__global__ void k_bulk_1d(const uint32_t* src, uint32_t* out) {   // cp.async.bulk (no tensor map): 2 KB from global to shared
+    __shared__ __align__(128) uint32_t tile[512];
+    __shared__ __align__(8) uint64_t bar;
+    if (threadIdx.x == 0) mbar_init(&bar, 1);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        mbar_expect_tx(&bar, 2048);
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(tile)), "l"(src), "r"(2048), "r"(smem_u32(&bar)) : "memory");
+    }
+    mbar_wait(&bar, 0);
+    for (int i = threadIdx.x; i < 512; i += blockDim.x) out[i] = tile[i];
+}
 struct alignas(64) Wrapped { CUtensorMap map; int flag; int pad[15]; };
 
 template <int BW, int BH>
@@ -83,10 +103,20 @@ int main(int argc, char** argv) {
     const int BW = (variant & (1 | 32 | 64)) ? 64 : 68, BH = (variant & (2 | 32 | 64)) ? 8 : 10;
     CUtensorMap m; memset(&m, 0, sizeof m);
     cuuint64_t dims[2] = {W, H}, strides[1] = {W * 4}; cuuint32_t box[2] = {cuuint32_t(BW), cuuint32_t(BH)}, es[2] = {1, 1};
-    CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_UINT32, 2, d, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+    const int dtype = argc > 2 ? atoi(argv[2]) : int(CU_TENSOR_MAP_DATA_TYPE_UINT32), swz = argc > 3 ? atoi(argv[3]) : 0, rank = argc > 4 ? atoi(argv[4]) : 2;
+    cuuint64_t dims3[3] = {W, H, 1}, strides3[2] = {W * 4, cuuint64_t(W) * H * 4}; cuuint32_t box3[3] = {cuuint32_t(BW), cuuint32_t(BH), 1}, es3[3] = {1, 1, 1};
+    CUresult r = enc(&m, CUtensorMapDataType(dtype), rank, d, rank == 3 ? dims3 : dims, rank == 3 ? strides3 : strides, rank == 3 ? box3 : box, rank == 3 ? es3 : es, CU_TENSOR_MAP_INTERLEAVE_NONE, CUtensorMapSwizzle(swz),
                      (variant & 8) ? CU_TENSOR_MAP_L2_PROMOTION_NONE : CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    printf("  dtype %d swizzle %d rank %d\n", dtype, swz, rank);
     printf("variant %d: box %dx%d encode rc=%d query=%d\n", variant, BW, BH, int(r), int(q));
     const int x0 = (variant & 16) ? -2 : 30, y0 = (variant & 16) ? -1 : 7;
+    if (variant & 128) { k_mbar_only<<<1, 128>>>(out); cudaError_t e2 = cudaDeviceSynchronize(); printf("  mbarrier only: %s\n", cudaGetErrorString(e2)); return 0; }
+    if (variant & 256) {
+        k_bulk_1d<<<1, 128>>>(d, out); cudaError_t e2 = cudaDeviceSynchronize(); printf("  cp.async.bulk 1-D: %s\n", cudaGetErrorString(e2));
+        if (e2 == cudaSuccess) { std::vector<uint32_t> o(512); cudaMemcpy(o.data(), out, 2048, cudaMemcpyDeviceToHost); int bad = 0; for (int i = 0; i < 512; ++i) bad += o[i] != h[i]; printf("  mismatches: %d\n", bad); }
+        return 0;
+    }
+    { const unsigned char* mb = (const unsigned char*)&m; printf("  tensor map bytes:"); for (int i = 0; i < 128; ++i) { if (i % 32 == 0) printf("\n   "); printf(" %02x", mb[i]); } printf("\n"); }
     if (variant & 32) {          // NVIDIA's libcu++ wrapper, descriptor as __grid_constant__ parameter
         k_libcu<64, 8><<<1, 128>>>(m, out, x0, y0);
     } else if (variant & 64) {   // descriptor in global memory
