@@ -733,18 +733,28 @@ struct Weights25 { float w[25]; float w_sum; };   // w_sum: the float sum of w[]
 #define D10_BY 16
 #define D10_TW (D10_BX + 4)
 #define D10_TH (D10_BY + 4)
-KJB_KERNEL(512) k_rtdgi_temporal(Globals g, Img input_tex, Img history_tex, Img variance_history_tex, Img reprojection_tex, Img rt_history_invalidity_tex,
+KJB_KERNEL(512) k_rtdgi_temporal(const __grid_constant__ TileSource ts_input, const __grid_constant__ TileSource ts_history, int tile_mode_, Globals g, Img input_tex, Img history_tex,
+                                 Img variance_history_tex, Img reprojection_tex, Img rt_history_invalidity_tex,
                                  ImgW output_tex, ImgW history_output_tex, ImgW variance_history_output_tex, float4 ots, Weights25 wt, Rows kjb_rows) {
+    constexpr int PR = tile_pitch<8>(D10_TW);
+    __shared__ __align__(128) uint2 s_raw_in[PR * D10_TH];      // the two RGBA16F footprints as the copy engine delivers them (tile origin x = 32k - 2: 16-byte aligned)
+    __shared__ __align__(128) uint2 s_raw_hist[PR * D10_TH];
     __shared__ float4 s_in[D10_TH * D10_TW];
     __shared__ float s_hist_luma[D10_TH * D10_TW];
+    __shared__ __align__(8) uint64_t bar;
     const int W = output_tex.w, H = output_tex.h;
     const int bx0 = int(blockIdx.x) * D10_BX - 2, by0 = kjb_rows.y0 + int(blockIdx.y) * D10_BY - 2;
     const float ped = g.fc.pre_exposure_delta;
     const float4 history_mult = f4(ped, ped, ped, 1);
-    for (int i = int(threadIdx.y) * D10_BX + int(threadIdx.x); i < D10_TW * D10_TH; i += D10_BX * D10_BY) {
+    const int tid = int(threadIdx.y) * D10_BX + int(threadIdx.x);
+    tile_group_begin(&bar, 0, tile_mode_, tid);
+    uint32_t staged = tile_issue<uint2, D10_TW, D10_TH>(s_raw_in, ts_input, input_tex, bx0, by0, &bar, tile_mode_, tid, D10_BX * D10_BY);
+    staged += tile_issue<uint2, D10_TW, D10_TH>(s_raw_hist, ts_history, history_tex, bx0, by0, &bar, tile_mode_, tid, D10_BX * D10_BY);
+    tile_group_wait(&bar, 0, tile_mode_, staged, tid);
+    for (int i = tid; i < D10_TW * D10_TH; i += D10_BX * D10_BY) {
         const int tx = i % D10_TW, ty = i / D10_TW;
-        s_in[i] = linear_to_working(ld_rgba16f(input_tex, bx0 + tx, by0 + ty));
-        s_hist_luma[i] = linear_to_working(ld_rgba16f(history_tex, bx0 + tx, by0 + ty) * history_mult).x;
+        s_in[i] = linear_to_working(half4_to_float4(s_raw_in[ty * PR + tx]));
+        s_hist_luma[i] = linear_to_working(half4_to_float4(s_raw_hist[ty * PR + tx]) * history_mult).x;
     }
     __syncthreads();
     const int x = int(blockIdx.x) * D10_BX + int(threadIdx.x), y = kjb_rows.y0 + int(blockIdx.y) * D10_BY + int(threadIdx.y);
@@ -998,7 +1008,8 @@ int kjb_pass_rtdgi_temporal(kjb_context* c, const kjb_rtdgi_temporal_args* a) {
     for (int yy = -2; yy <= 2; ++yy) for (int xx = -2; xx <= 2; ++xx) wt.w[(yy + 2) * 5 + (xx + 2)] = kjb_exp(-3.0f * float(xx * xx + yy * yy) / float((2 + 1.) * (2 + 1.)));
     wt.w_sum = 0; for (int i = 0; i < 25; ++i) wt.w_sum += wt.w[i];
     KJB_ROWS(c, H);
-    KJB_LAUNCH_SYNC(c, k_rtdgi_temporal, KJB_GRID2D(W, H, D10_BX, D10_BY), c->g, img_ro(a->input_tex), img_ro(a->history_tex), img_ro(a->variance_history_tex), img_ro(a->reprojection_tex), img_ro(a->rt_history_invalidity_tex),
+    const TileSource ts_in = tile_source(c, a->input_tex, D10_TW, D10_TH), ts_hist = tile_source(c, a->history_tex, D10_TW, D10_TH);
+    KJB_LAUNCH_SYNC(c, k_rtdgi_temporal, KJB_GRID2D(W, H, D10_BX, D10_BY), ts_in, ts_hist, tile_mode({&ts_in, &ts_hist}), c->g, img_ro(a->input_tex), img_ro(a->history_tex), img_ro(a->variance_history_tex), img_ro(a->reprojection_tex), img_ro(a->rt_history_invalidity_tex),
                img_rw(a->output_tex), img_rw(a->history_output_tex), img_rw(a->variance_history_output_tex), F4A(a->output_tex_size), wt);
     KJB_PASS_EPILOGUE(c, P);
 }

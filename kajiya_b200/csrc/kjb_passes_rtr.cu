@@ -557,17 +557,45 @@ struct RtrTemporalImgs { Img input_tex, history_tex, depth_tex, ray_len_tex, rep
 #ifndef KJB_OCC_RTR_TEMPORAL
 #define KJB_OCC_RTR_TEMPORAL 4
 #endif
-KJB_KERNEL_OCC(256, KJB_OCC_RTR_TEMPORAL) k_rtr_temporal(Globals g, RtrTemporalImgs t, float4 ots, Rows kjb_rows) {
-    KJB_PX; if (x >= t.output_tex.w || y >= t.output_tex.h) return;
+// The block's (32+2)x(8+2) footprint of the resolved reflections (R11G11B10) and of the depth buffer is staged through the TMA engine (tile origin
+// 4 texels left of the block: 16-byte aligned rows); the R11G11B10 decode and the conversion to the crunched luma-chroma working space run once per
+// texel instead of once per tap of the 3x3 neighbourhood.
+#define R5_TW 40
+#define R5_AX 4
+#define R5_LW 34
+#define R5_TH 10
+KJB_KERNEL_OCC(256, KJB_OCC_RTR_TEMPORAL) k_rtr_temporal(const __grid_constant__ TileSource ts_input, const __grid_constant__ TileSource ts_depth, int tile_mode_, Globals g, RtrTemporalImgs t, float4 ots, Rows kjb_rows) {
+    constexpr int P4 = tile_pitch<4>(R5_TW);
+    __shared__ __align__(128) uint32_t s_raw[P4 * R5_TH];
+    __shared__ __align__(128) float s_depth[P4 * R5_TH];
+    __shared__ float4 s_work[R5_LW * R5_TH];
+    __shared__ __align__(8) uint64_t bar;
+    const int tid = int(threadIdx.y) * 32 + int(threadIdx.x);
+    const int bx0 = int(blockIdx.x) * 32, by0 = kjb_rows.y0 + int(blockIdx.y) * 8;
+    tile_group_begin(&bar, 0, tile_mode_, tid);
+    uint32_t staged = tile_issue<uint32_t, R5_TW, R5_TH>(s_raw, ts_input, t.input_tex, bx0 - R5_AX, by0 - 1, &bar, tile_mode_, tid, 256);
+    staged += tile_issue<float, R5_TW, R5_TH>(s_depth, ts_depth, t.depth_tex, bx0 - R5_AX, by0 - 1, &bar, tile_mode_, tid, 256);
+    tile_group_wait(&bar, 0, tile_mode_, staged, tid);
+    for (int i = tid; i < R5_LW * R5_TH; i += 256) {
+        const int lx = i % R5_LW, ly = i / R5_LW;
+        const uint32_t v = s_raw[ly * P4 + lx + (R5_AX - 1)];
+        // out-of-range taps read 0 from the R11G11B10 image with alpha 0, in-range ones alpha 1 (texel fetch of a 3-channel format) — as the oracle's load()
+        const bool in_image = inb(t.input_tex, bx0 - 1 + lx, by0 - 1 + ly);
+        s_work[i] = linear_to_working(in_image ? f4(f3(uf_to_f32(v & 2047u, 6), uf_to_f32((v >> 11) & 2047u, 6), uf_to_f32(v >> 22, 5)), 1) : f4(0.0f));
+    }
+    __syncthreads();
+    const int x = bx0 + int(threadIdx.x), y = by0 + int(threadIdx.y);
+    if (x >= t.output_tex.w || y >= t.output_tex.h || y >= kjb_rows.y1) return;
+    const int tx = int(threadIdx.x) + 1, ty = int(threadIdx.y) + 1;
     const kjb_view_constants& vc = g.fc.view_constants;
     const float ped = g.fc.pre_exposure_delta;
     const float4 history_mult = f4(ped, ped, ped, 1);
     const float3 eye = get_eye_position(vc), prev_eye = get_prev_eye_position(vc);
-    const float4 center = linear_to_working(f4(ld_r11g11b10(t.input_tex, x, y), 1));
+    const float4 center = s_work[ty * R5_LW + tx];
     const float refl_ray_length = kjb_clamp(ld_rg16f(t.ray_len_tex, x, y).x, 0.0f, 1e3f);
     const float s4[4] = {ots.x, ots.y, ots.z, ots.w};
     const float2 uv = get_uv(x, y, s4);
-    const float center_depth = ld_r32f(t.depth_tex, x, y);
+    const float center_depth = s_depth[ty * P4 + tx + (R5_AX - 1)];
     const ViewRayContext vrc = ViewRayContext::from_uv_and_depth(vc, uv, center_depth);
     const float3 reflector_vs = vrc.ray_hit_vs();
     const float2 cs0 = uv_to_cs(uv);
@@ -622,9 +650,8 @@ KJB_KERNEL_OCC(256, KJB_OCC_RTR_TEMPORAL) k_rtr_temporal(Globals g, RtrTemporalI
     const float history1_valid = quad_reproj_valid_packed == 15u ? 1.0f : 0.0f;
     float4 vsum = f4(0.0f), vsum2 = f4(0.0f); float wsum = 0;
     for (int yy = -1; yy <= 1; ++yy) for (int xx = -1; xx <= 1; ++xx) {
-        const float sample_depth = ld_r32f(t.depth_tex, x + xx, y + yy);
-        // out-of-range taps read 0 from the R11G11B10 image with alpha 1 (texel fetch of a 3-channel format) — match the oracle's load()
-        const float4 neigh = linear_to_working(inb(t.input_tex, x + xx, y + yy) ? f4(ld_r11g11b10(t.input_tex, x + xx, y + yy), 1) : f4(0.0f));
+        const float sample_depth = s_depth[(ty + yy) * P4 + (tx + xx) + (R5_AX - 1)];
+        const float4 neigh = s_work[(ty + yy) * R5_LW + (tx + xx)];
         float w = 1;
         w *= kjb_exp2(-200.0f * kjb_abs(center_depth / sample_depth - 1.0f));
         vsum = mad(neigh, w, vsum); vsum2 = mad(neigh * neigh, w, vsum2); wsum += w;
@@ -791,7 +818,8 @@ int kjb_pass_rtr_temporal(kjb_context* c, const kjb_rtr_temporal_args* a) {
     CHKE(a->gbuffer_tex, KJB_FMT_RGBA32_FLOAT, "gbuffer_tex", W, H); CHK(a->output_tex, KJB_FMT_RGBA16_FLOAT, "output_tex");
     RtrTemporalImgs t{img_ro(a->input_tex), img_ro(a->history_tex), img_ro(a->depth_tex), img_ro(a->ray_len_tex), img_ro(a->reprojection_tex), img_ro(a->refl_restir_invalidity_tex), img_ro(a->gbuffer_tex), img_rw(a->output_tex)};
     KJB_ROWS(c, H);
-    KJB_LAUNCH(c, k_rtr_temporal, KJB_GRID2D(W, H, 32, 8), c->g, t, F4A(a->output_tex_size));
+    const TileSource ts_in = tile_source(c, a->input_tex, R5_TW, R5_TH), ts_depth = tile_source(c, a->depth_tex, R5_TW, R5_TH);
+    KJB_LAUNCH_SYNC(c, k_rtr_temporal, KJB_GRID2D(W, H, 32, 8), ts_in, ts_depth, tile_mode({&ts_in, &ts_depth}), c->g, t, F4A(a->output_tex_size));
     KJB_PASS_EPILOGUE(c, P);
 }
 int kjb_pass_rtr_cleanup(kjb_context* c, const kjb_rtr_cleanup_args* a) {

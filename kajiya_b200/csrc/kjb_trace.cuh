@@ -205,23 +205,31 @@ KJB_DEV uint4 rchit_gbuffer(const Globals& g, const Ray& ray, const HitInfo& hit
     for (int k = 0; k < 3; ++k) uvs[k] = *reinterpret_cast<const float2*>(sc.vertices + mesh.vertex_uv_offset + ind[k] * 8);
     const float2 uv = uvs[0] * bary.x + uvs[1] * bary.y + uvs[2] * bary.z;
 
-    const float cone_width = ray_cone.width + ray_cone.spread_angle * hit_dist;
-    const float3 p0 = xform_point(o2w, vp[0]), p1 = xform_point(o2w, vp[1]), p2 = xform_point(o2w, vp[2]);
-    const float twice_uv_area = kjb_abs((uvs[1].x - uvs[0].x) * (uvs[2].y - uvs[0].y) - (uvs[2].x - uvs[0].x) * (uvs[1].y - uvs[0].y));
-    const float twice_triangle_area = length(cross(p1 - p0, p2 - p0));
-    const float lod_triangle_constant = 0.5f * kjb_log2(twice_uv_area / twice_triangle_area);
-
     const uint32_t material_id = vb_u32(sc, mesh.vertex_mat_offset + ind[0] * 4);
     const kjb_mesh_material& material = *reinterpret_cast<const kjb_mesh_material*>(sc.vertices + mesh.mat_data_offset + material_id * (uint32_t)sizeof(kjb_mesh_material));
 
-    const float2 albedo_uv = transform_material_uv(material.map_transforms, uv, 0);
-    const float albedo_lod = texture_lod(sc, material.maps[2], lod_triangle_constant, ray.dir, surf_normal_ws, cone_width);
-    const float3 albedo = xyz(tex_sample_level(sc, material.maps[2], albedo_uv, albedo_lod))
+    // A map that is a single texel (kajiya's 1x1 placeholders for materials without that texture) returns the same value for every uv and lod
+    // (tex_sample_level's first branch), so the ray-cone lod — four log2 per map plus the world-space triangle area — is evaluated only when a
+    // map of this material actually has texels to filter.  Same result either way; untextured scenes skip ~350 instructions per hit.
+    auto flat = [&](uint32_t tex) { if (tex >= sc.tex_count) return true; const uint4 d = sc.tex_desc[tex]; return (d.w & 0xffffu) == 1u && d.y == 1u && d.z == 1u; };
+    const bool any_filtered = !flat(material.maps[2]) || !flat(material.maps[1]) || !flat(material.maps[3]);
+    float cone_width = 0.0f, lod_triangle_constant = 0.0f;
+    if (any_filtered) {
+        cone_width = ray_cone.width + ray_cone.spread_angle * hit_dist;
+        const float3 p0 = xform_point(o2w, vp[0]), p1 = xform_point(o2w, vp[1]), p2 = xform_point(o2w, vp[2]);
+        const float twice_uv_area = kjb_abs((uvs[1].x - uvs[0].x) * (uvs[2].y - uvs[0].y) - (uvs[2].x - uvs[0].x) * (uvs[1].y - uvs[0].y));
+        const float twice_triangle_area = length(cross(p1 - p0, p2 - p0));
+        lod_triangle_constant = 0.5f * kjb_log2(twice_uv_area / twice_triangle_area);
+    }
+    auto sample_map = [&](uint32_t tex, uint32_t uv_slot) {
+        if (flat(tex)) return tex_sample_level(sc, tex, f2(0.0f), 0.0f);
+        return tex_sample_level(sc, tex, transform_material_uv(material.map_transforms, uv, uv_slot), texture_lod(sc, tex, lod_triangle_constant, ray.dir, surf_normal_ws, cone_width));
+    };
+
+    const float3 albedo = xyz(sample_map(material.maps[2], 0))
         * f3(material.base_color_mult[0], material.base_color_mult[1], material.base_color_mult[2]) * xyz(v_color);
 
-    const float2 spec_uv = transform_material_uv(material.map_transforms, uv, 2);
-    const float spec_lod = texture_lod(sc, material.maps[1], lod_triangle_constant, ray.dir, surf_normal_ws, cone_width);
-    const float4 metalness_roughness = tex_sample_level(sc, material.maps[1], spec_uv, spec_lod);
+    const float4 metalness_roughness = sample_map(material.maps[1], 2);
     const float perceptual_roughness = material.roughness_mult * metalness_roughness.x;
     float roughness = kjb_clamp(perceptual_roughness * perceptual_roughness, 1e-4f, 1.0f);
     float metalness = metalness_roughness.y * material.metalness_factor;
@@ -229,11 +237,9 @@ KJB_DEV uint4 rchit_gbuffer(const Globals& g, const Ray& ray, const HitInfo& hit
     const float rs = g.fc.render_override_material_roughness_scale;
     if (rs <= 1) roughness *= rs; else roughness = square(kjb_lerp(kjb_sqrt(roughness), 1.0f, 1.0f - 1.0f / rs));
 
-    const float2 emissive_uv = transform_material_uv(material.map_transforms, uv, 3);
-    const float emissive_lod = texture_lod(sc, material.maps[3], lod_triangle_constant, ray.dir, surf_normal_ws, cone_width);
     float3 emissive = f3(0.0f);
     if (0 == path_length || 0 == (material.flags & 1u)) {
-        emissive = f3(1.0f) * xyz(tex_sample_level(sc, material.maps[3], emissive_uv, emissive_lod))
+        emissive = f3(1.0f) * xyz(sample_map(material.maps[3], 3))
             * f3(material.emissive[0], material.emissive[1], material.emissive[2]) * inst.emissive_multiplier * g.fc.pre_exposure;
     }
     GbufferData gb;

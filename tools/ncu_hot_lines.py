@@ -14,10 +14,14 @@ for r in rows:
         line = int(r[0])
     except ValueError:
         continue
-    ie = r[hdr["Instructions Executed"]]
-    if not ie: continue
-    key = (cur_file.split("/")[-1], line)
-    agg[key] += int(float(ie)); samples[key] += int(float(r[hdr["# Samples"]] or 0))
+    try:   # source text with quotes / commas (inline asm) can shift the columns of a row: skip what does not parse
+        ie = r[hdr["Instructions Executed"]]
+        if not ie: continue
+        n_ie, n_s = int(float(ie)), int(float(r[hdr["# Samples"]] or 0))
+    except (ValueError, IndexError):
+        continue
+    key = ((cur_file or "?").split("/")[-1], line)
+    agg[key] += n_ie; samples[key] += n_s
     # first "Source" column = CUDA-C text for this row kind, second = SASS
     src_cols = [i for i, h in enumerate(rows[2]) if h == "Source"] if False else None
 tot = sum(agg.values())
