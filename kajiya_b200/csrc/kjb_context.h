@@ -172,8 +172,12 @@ inline bool check_img(kjb_context* c, const kjb_image& i, uint32_t fmt, const ch
 // Ray-tracing passes: 8 x 16 pixel blocks, so that a warp (32 consecutive threads) is an 8 x 4 pixel patch — compact footprints keep the
 // lanes of a warp on neighbouring BVH nodes and make hit / miss shading branch together more often than 32 x 1 or 16 x 2 strips.  The
 // serial twins (and the oracle's serial schedule, oracle/kj_ctx.h) walk the pixels in the same block order.
+#ifndef KJB_RAY_BX
 #define KJB_RAY_BX 8
+#endif
+#ifndef KJB_RAY_BY
 #define KJB_RAY_BY 16
+#endif
 // every kernel's last parameter is `Rows kjb_rows`: the row range of its grid this launch covers (tile sharding)
 #define KJB_ROWS(ctx, H) const kjb::Rows kjb__rows = (ctx)->rows_for(H)
 #define KJB_GRID2D(W, H, BX, BY) dim3(((W) + (BX) - 1) / (BX), (unsigned(kjb__rows.y1 - kjb__rows.y0) + (BY) - 1) / (BY), 1), dim3((BX), (BY), 1)

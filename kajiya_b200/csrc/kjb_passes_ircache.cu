@@ -113,36 +113,81 @@ KJB_KERNEL(32) k_ircache_age_serial(uint32_t* meta, uint32_t* gm, uint32_t* entr
 }
 
 // ------------------------------------------------------------------ I5 prefix_scan/*.hlsl: inclusive scan of <= 64 Ki u32 in one CTA
-// Replaces the reference's 3-pass 1 Mi-element scan (prefix_scan.rs:10-39).  Each of the 1024 threads owns n / 1024 CONSECUTIVE values: it sums
-// them, the 1024 thread totals are scanned with warp shuffles (SHFL.UP inside each warp, then once more over the 32 warp totals), and the
-// thread rewrites its values with the running sum — two barriers instead of the twenty-odd of a shared-memory Hillis-Steele scan per chunk.
+// Replaces the reference's 3-pass 1 Mi-element scan (prefix_scan.rs:10-39).  The array is cut into chunks of 8192; in chunk c thread t owns the 8
+// consecutive values at c * 8192 + t * 8, read as two 16-byte loads (a warp reads 1 KiB contiguous) — all chunks' loads are issued before the
+// first is consumed, so the kernel pays one memory round trip, not one per chunk.  Thread totals are scanned with warp shuffles (SHFL.UP inside
+// each warp, then warp c scans the 32 warp totals of chunk c), chunk totals carry forward; two block barriers in all.
+#define KJB_SCAN_CHUNKS 8
 KJB_KERNEL(1024) k_inclusive_prefix_scan(uint32_t* d, uint32_t n, Rows kjb_rows) {
-    __shared__ uint32_t warp_tot[32];
-    const uint32_t t = threadIdx.x, per = (n + 1023u) / 1024u;
-    const uint32_t b = t * per < n ? t * per : n, e = b + per < n ? b + per : n;
-    uint32_t s = 0;
-    for (uint32_t i = b; i < e; ++i) s += d[i];
+    __shared__ uint32_t warp_tot[KJB_SCAN_CHUNKS][32];
+    const uint32_t t = threadIdx.x;
+    const bool vec = (reinterpret_cast<uintptr_t>(d) & 15u) == 0;   // 16-byte loads need an aligned base (always true for kjb_buffer_alloc)
+    uint32_t v[KJB_SCAN_CHUNKS][8], s[KJB_SCAN_CHUNKS];
+#pragma unroll
+    for (uint32_t c = 0; c < KJB_SCAN_CHUNKS; ++c) {
+        const uint32_t b = c * 8192u + t * 8u;
+        if (vec && b + 8u <= n) {
+            const uint4 lo = *reinterpret_cast<const uint4*>(d + b), hi = *reinterpret_cast<const uint4*>(d + b + 4);
+            v[c][0] = lo.x; v[c][1] = lo.y; v[c][2] = lo.z; v[c][3] = lo.w; v[c][4] = hi.x; v[c][5] = hi.y; v[c][6] = hi.z; v[c][7] = hi.w;
+        } else {
+#pragma unroll
+            for (uint32_t k = 0; k < 8u; ++k) v[c][k] = b + k < n ? d[b + k] : 0u;
+        }
+    }
+#pragma unroll
+    for (uint32_t c = 0; c < KJB_SCAN_CHUNKS; ++c) {
+        uint32_t a = 0;
+#pragma unroll
+        for (uint32_t k = 0; k < 8u; ++k) { a += v[c][k]; v[c][k] = a; }     // inclusive within the thread's 8 values
+        s[c] = a;
+    }
+    uint32_t before[KJB_SCAN_CHUNKS];                                          // sum of everything in front of this thread's values of chunk c
 #if !defined(KJB_EMU)
     const uint32_t lane = t & 31u, warp = t >> 5;
-    uint32_t inc = s;
-    for (uint32_t off = 1; off < 32u; off <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, inc, off); if (lane >= off) inc += v; }
-    if (lane == 31u) warp_tot[warp] = inc;
-    __syncthreads();
-    if (warp == 0) {
-        uint32_t w = warp_tot[lane];
-        for (uint32_t off = 1; off < 32u; off <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, w, off); if (lane >= off) w += v; }
-        warp_tot[lane] = w;
+    uint32_t inc[KJB_SCAN_CHUNKS];
+#pragma unroll
+    for (uint32_t c = 0; c < KJB_SCAN_CHUNKS; ++c) {
+        uint32_t a = s[c];
+#pragma unroll
+        for (uint32_t off = 1; off < 32u; off <<= 1) { const uint32_t u = __shfl_up_sync(0xffffffffu, a, off); if (lane >= off) a += u; }
+        inc[c] = a;
+        if (lane == 31u) warp_tot[c][warp] = a;
     }
     __syncthreads();
-    uint32_t acc = (inc - s) + (warp ? warp_tot[warp - 1] : 0u);
+    if (warp < KJB_SCAN_CHUNKS) {
+        uint32_t a = warp_tot[warp][lane];
+#pragma unroll
+        for (uint32_t off = 1; off < 32u; off <<= 1) { const uint32_t u = __shfl_up_sync(0xffffffffu, a, off); if (lane >= off) a += u; }
+        warp_tot[warp][lane] = a;
+    }
+    __syncthreads();
+    uint32_t carry = 0;
+#pragma unroll
+    for (uint32_t c = 0; c < KJB_SCAN_CHUNKS; ++c) {
+        before[c] = carry + (warp ? warp_tot[c][warp - 1] : 0u) + (inc[c] - s[c]);
+        carry += warp_tot[c][31];
+    }
 #else
-    static thread_local uint32_t tot[1024];
+    static thread_local uint32_t tot[KJB_SCAN_CHUNKS * 1024];
     (void)warp_tot;
-    tot[t] = s; __syncthreads();
-    uint32_t acc = 0; for (uint32_t k = 0; k < t; ++k) acc += tot[k];
+    for (uint32_t c = 0; c < KJB_SCAN_CHUNKS; ++c) tot[c * 1024u + t] = s[c];
+    __syncthreads();
+    if (t == 0) { uint32_t a = 0; for (uint32_t i = 0; i < KJB_SCAN_CHUNKS * 1024u; ++i) { const uint32_t x = tot[i]; tot[i] = a; a += x; } }
+    __syncthreads();
+    for (uint32_t c = 0; c < KJB_SCAN_CHUNKS; ++c) before[c] = tot[c * 1024u + t];
     __syncthreads();
 #endif
-    for (uint32_t i = b; i < e; ++i) { acc += d[i]; d[i] = acc; }
+#pragma unroll
+    for (uint32_t c = 0; c < KJB_SCAN_CHUNKS; ++c) {
+        const uint32_t b = c * 8192u + t * 8u;
+        if (vec && b + 8u <= n) {
+            *reinterpret_cast<uint4*>(d + b) = make_uint4(v[c][0] + before[c], v[c][1] + before[c], v[c][2] + before[c], v[c][3] + before[c]);
+            *reinterpret_cast<uint4*>(d + b + 4) = make_uint4(v[c][4] + before[c], v[c][5] + before[c], v[c][6] + before[c], v[c][7] + before[c]);
+        } else {
+#pragma unroll
+            for (uint32_t k = 0; k < 8u; ++k) if (b + k < n) d[b + k] = v[c][k] + before[c];
+        }
+    }
 }
 
 // ------------------------------------------------------------------ I6 ircache_compact_entries.hlsl

@@ -211,7 +211,10 @@ KJB_DEV uint4 rchit_gbuffer(const Globals& g, const Ray& ray, const HitInfo& hit
     // A map that is a single texel (kajiya's 1x1 placeholders for materials without that texture) returns the same value for every uv and lod
     // (tex_sample_level's first branch), so the ray-cone lod — four log2 per map plus the world-space triangle area — is evaluated only when a
     // map of this material actually has texels to filter.  Same result either way; untextured scenes skip ~350 instructions per hit.
-    auto flat = [&](uint32_t tex) { if (tex >= sc.tex_count) return true; const uint4 d = sc.tex_desc[tex]; return (d.w & 0xffffu) == 1u && d.y == 1u && d.z == 1u; };
+#ifndef KJB_LOD_SKIP
+#define KJB_LOD_SKIP 1
+#endif
+    auto flat = [&](uint32_t tex) { if (!KJB_LOD_SKIP) return false; if (tex >= sc.tex_count) return true; const uint4 d = sc.tex_desc[tex]; return (d.w & 0xffffu) == 1u && d.y == 1u && d.z == 1u; };
     const bool any_filtered = !flat(material.maps[2]) || !flat(material.maps[1]) || !flat(material.maps[3]);
     float cone_width = 0.0f, lod_triangle_constant = 0.0f;
     if (any_filtered) {

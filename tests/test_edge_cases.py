@@ -236,3 +236,53 @@ def test_reference_accumulation_reset(oracle_lib, emu_lib):
     wa.render_reference(**moved); wb.render_reference(**moved)
     a, b = wa.image("refpt.accum"), wb.image("refpt.accum")
     assert np.array_equal(a.view(np.uint32), b.view(np.uint32)) and float(b[..., 3].max()) == 1.0
+
+
+SCAN_SIZES = [1, 7, 8, 9, 1023, 8191, 8192, 8193, 40000, 65535, 65536]
+
+
+def _scan_case(lib, n, seed=0, misalign=False):
+    """kjb_pass_inclusive_prefix_scan_u32 on n seeded values (wrapping u32 sums) -> (got, want)"""
+    d = lib.dll
+    class Buf(C.Structure):
+        _fields_ = [("data", C.c_void_p), ("size_bytes", C.c_uint64)]
+    class ScanArgs(C.Structure):
+        _fields_ = [("inout_buf", Buf), ("element_count", C.c_uint32)]
+    for f in ("kjb_buffer_alloc", "kjb_buffer_upload", "kjb_buffer_download", "kjb_buffer_free", "kjb_pass_inclusive_prefix_scan_u32"):
+        getattr(d, f).restype = C.c_int
+    d.kjb_buffer_alloc.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p]
+    d.kjb_buffer_upload.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64]
+    d.kjb_buffer_download.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p, C.c_uint64]
+    d.kjb_buffer_free.argtypes = [C.c_void_p, C.c_void_p]
+    d.kjb_pass_inclusive_prefix_scan_u32.argtypes = [C.c_void_p, C.c_void_p]
+    ctx = C.c_void_p(); assert d.kjb_create(0, C.byref(ctx)) == 0
+    rng = np.random.default_rng(seed + n)
+    vals = rng.integers(0, 2 ** 32 if n < 100 else 2 ** 18, size=n, dtype=np.uint64).astype(np.uint32)
+    buf = Buf(); assert d.kjb_buffer_alloc(ctx, 4 * n + 16, C.byref(buf)) == 0
+    view = Buf(buf.data + (4 if misalign else 0), 4 * n)     # a 4-byte-aligned sub-range exercises the scalar path of the CUDA kernel
+    assert d.kjb_buffer_upload(ctx, C.byref(view), 0, vals.ctypes.data, 4 * n) == 0
+    a = ScanArgs(view, n)
+    assert d.kjb_pass_inclusive_prefix_scan_u32(ctx, C.byref(a)) == 0, d.kjb_last_error(ctx)
+    assert d.kjb_sync(ctx) == 0
+    got = np.zeros(n, np.uint32); assert d.kjb_buffer_download(ctx, C.byref(view), 0, got.ctypes.data, 4 * n) == 0
+    assert d.kjb_buffer_free(ctx, C.byref(buf)) == 0
+    d.kjb_destroy(ctx)
+    return got, np.cumsum(vals.astype(np.uint64)).astype(np.uint32)
+
+
+@pytest.mark.parametrize("n", SCAN_SIZES)
+def test_prefix_scan_ragged_sizes(oracle_lib, emu_lib, n):
+    """"_prefix scan" (prefix_scan.rs:10-39) at ragged element counts, against numpy's cumulative sum (mod 2^32)"""
+    for lib in (oracle_lib, emu_lib):
+        got, want = _scan_case(lib, n)
+        assert np.array_equal(got, want), lib.backend
+    got, want = _scan_case(emu_lib, n, misalign=True)
+    assert np.array_equal(got, want)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("n", SCAN_SIZES)
+def test_gpu_prefix_scan_ragged_sizes(cuda_lib, n):
+    for mis in (False, True):
+        got, want = _scan_case(cuda_lib, n, misalign=mis)
+        assert np.array_equal(got, want), (n, mis)
