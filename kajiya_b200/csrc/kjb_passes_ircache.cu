@@ -49,12 +49,12 @@ KJB_DEV void ircache_scroll_cell(const Globals& g, const uint32_t* gm, uint32_t*
         if (m1 & IRCACHE_ENTRY_META_OCCUPIED) entry_cell[m0] = dst_cell_idx;
     } else { gm2[dst_cell_idx * 2] = 0; gm2[dst_cell_idx * 2 + 1] = 0; }
 }
-KJB_KERNEL(256) k_ircache_scroll_cascades(Globals g, const uint32_t* gm, uint32_t* gm2, uint32_t* entry_cell, float4* irradiance, uint32_t* life, uint32_t* pool, uint32_t* meta, Rows kjb_rows) {
+KJB_KERNEL(256) k_ircache_scroll_cascades(const __grid_constant__ Globals g, const uint32_t* gm, uint32_t* gm2, uint32_t* entry_cell, float4* irradiance, uint32_t* life, uint32_t* pool, uint32_t* meta, Rows kjb_rows) {
     const uint32_t i = tid1d(); if (i < KJB_IRCACHE_GRID_CELLS) ircache_scroll_cell(g, gm, gm2, entry_cell, irradiance, life, pool, meta, i);
 }
 // `_serial` twins (kjb_set_debug_serial): ONE thread walks the logical threads in launch order — the deterministic schedule the
 // CPU oracle uses, so the racy cache passes can be compared bit for bit on the real GPU (slow; test / repro aid only)
-KJB_KERNEL(32) k_ircache_scroll_cascades_serial(Globals g, const uint32_t* gm, uint32_t* gm2, uint32_t* entry_cell, float4* irradiance, uint32_t* life, uint32_t* pool, uint32_t* meta, Rows kjb_rows) {
+KJB_KERNEL(32) k_ircache_scroll_cascades_serial(const __grid_constant__ Globals g, const uint32_t* gm, uint32_t* gm2, uint32_t* entry_cell, float4* irradiance, uint32_t* life, uint32_t* pool, uint32_t* meta, Rows kjb_rows) {
     if (tid1d() != 0) return;
     for (uint32_t i = 0; i < KJB_IRCACHE_GRID_CELLS; ++i) ircache_scroll_cell(g, gm, gm2, entry_cell, irradiance, life, pool, meta, i);
 }
@@ -211,7 +211,7 @@ KJB_KERNEL(256) k_ircache_reset(const uint32_t* meta, const float4* irradiance, 
 }
 
 // ------------------------------------------------------------------ I8 trace_accessibility.rgen.hlsl:21-66
-KJB_KERNEL(128) k_ircache_trace_access(Globals g, const float4* spatial, const uint32_t* life, const uint32_t* meta, float4* aux, const uint32_t* indirection, Rows kjb_rows) {
+KJB_KERNEL(128) k_ircache_trace_access(const __grid_constant__ Globals g, const float4* spatial, const uint32_t* life, const uint32_t* meta, float4* aux, const uint32_t* indirection, Rows kjb_rows) {
     const uint32_t dispatch_idx = tid1d();
     const uint32_t alloc_count = meta[IRCACHE_META_TRACING_ALLOC_COUNT];
     if (dispatch_idx >= alloc_count * IRCACHE_OCTA_DIMS2 || dispatch_idx >= MAX_ENTRIES * IRCACHE_OCTA_DIMS2) return;
@@ -310,8 +310,8 @@ KJB_DEV void ircache_validate_sample(const Globals& g, const IrcacheBufs& b, con
         b.aux[output_idx + IRCACHE_OCTA_DIMS2] = prev_value_and_count;
     }
 }
-KJB_KERNEL(128) k_ircache_validate(Globals g, IrcacheBufs b, Img sky_cube_tex, const uint32_t* indirection, Rows kjb_rows) { ircache_validate_sample(g, b, sky_cube_tex, indirection, tid1d()); }
-KJB_KERNEL(32) k_ircache_validate_serial(Globals g, IrcacheBufs b, Img sky_cube_tex, const uint32_t* indirection, Rows kjb_rows) {
+KJB_KERNEL(128) k_ircache_validate(const __grid_constant__ Globals g, IrcacheBufs b, Img sky_cube_tex, const uint32_t* indirection, Rows kjb_rows) { ircache_validate_sample(g, b, sky_cube_tex, indirection, tid1d()); }
+KJB_KERNEL(32) k_ircache_validate_serial(const __grid_constant__ Globals g, IrcacheBufs b, Img sky_cube_tex, const uint32_t* indirection, Rows kjb_rows) {
     if (tid1d() != 0) return;
     const uint32_t n = b.meta[IRCACHE_META_TRACING_ALLOC_COUNT] * IRCACHE_VALIDATION_SAMPLES_PER_FRAME;
     for (uint32_t i = 0; i < n && i < MAX_ENTRIES * IRCACHE_VALIDATION_SAMPLES_PER_FRAME; ++i) ircache_validate_sample(g, b, sky_cube_tex, indirection, i);
@@ -351,15 +351,15 @@ KJB_DEV void ircache_trace_sample(const Globals& g, const IrcacheBufs& b, const 
     b.aux[output_idx + IRCACHE_OCTA_DIMS2] = f4(val_sel, reservoir.W);
     if (selected_new) b.aux[output_idx + IRCACHE_OCTA_DIMS2 * 2] = packed_entry;
 }
-KJB_KERNEL(128) k_ircache_trace(Globals g, IrcacheBufs b, Img sky_cube_tex, const uint32_t* indirection, Rows kjb_rows) { ircache_trace_sample(g, b, sky_cube_tex, indirection, tid1d()); }
-KJB_KERNEL(32) k_ircache_trace_serial(Globals g, IrcacheBufs b, Img sky_cube_tex, const uint32_t* indirection, Rows kjb_rows) {
+KJB_KERNEL(128) k_ircache_trace(const __grid_constant__ Globals g, IrcacheBufs b, Img sky_cube_tex, const uint32_t* indirection, Rows kjb_rows) { ircache_trace_sample(g, b, sky_cube_tex, indirection, tid1d()); }
+KJB_KERNEL(32) k_ircache_trace_serial(const __grid_constant__ Globals g, IrcacheBufs b, Img sky_cube_tex, const uint32_t* indirection, Rows kjb_rows) {
     if (tid1d() != 0) return;
     const uint32_t n = b.meta[IRCACHE_META_TRACING_ALLOC_COUNT] * IRCACHE_SAMPLES_PER_FRAME;
     for (uint32_t i = 0; i < n && i < MAX_ENTRIES * IRCACHE_SAMPLES_PER_FRAME; ++i) ircache_trace_sample(g, b, sky_cube_tex, indirection, i);
 }
 
 // ------------------------------------------------------------------ I11 sum_up_irradiance.hlsl:34-89
-KJB_KERNEL(256) k_ircache_sum(Globals g, const uint32_t* meta, float4* irradiance, const float4* aux, const uint32_t* indirection, Rows kjb_rows) {
+KJB_KERNEL(256) k_ircache_sum(const __grid_constant__ Globals g, const uint32_t* meta, float4* irradiance, const float4* aux, const uint32_t* indirection, Rows kjb_rows) {
     const uint32_t dispatch_idx = tid1d();
     const uint32_t alloc_count = meta[IRCACHE_META_TRACING_ALLOC_COUNT];
     if (dispatch_idx >= alloc_count || dispatch_idx >= MAX_ENTRIES || ircache_slot_is_stale_duplicate(indirection, alloc_count, dispatch_idx)) return;

@@ -5,7 +5,7 @@
 using namespace kjb;
 
 // ------------------------------------------------------------------ rt/trace_sun_shadow_mask.rgen.hlsl:19-60
-KJB_KERNEL(128) k_trace_sun_shadow_mask(Globals g, Img depth_tex, Img geometric_normal_tex, ImgW output_tex, Rows kjb_rows) {
+KJB_KERNEL(128) k_trace_sun_shadow_mask(const __grid_constant__ Globals g, Img depth_tex, Img geometric_normal_tex, ImgW output_tex, Rows kjb_rows) {
     KJB_PX; if (x >= output_tex.w || y >= output_tex.h) return;
     const kjb_view_constants& vc = g.fc.view_constants;
     const float2 uv = (f2(float(x), float(y)) + 0.5f) / f2(float(output_tex.w), float(output_tex.h));
@@ -26,7 +26,7 @@ KJB_KERNEL(128) k_trace_sun_shadow_mask(Globals g, Img depth_tex, Img geometric_
 
 // ------------------------------------------------------------------ light_gbuffer.hlsl:60-260 (debug_shading_mode 0, 2, 3, 4)
 struct LightGbufferImgs { Img gbuffer_tex, depth_tex, shadow_mask_tex, rtr_tex, rtdgi_tex, unconvolved_sky_cube_tex; ImgW temporal_output_tex, output_tex; int shadow_is_rg16f; };
-KJB_KERNEL(256) k_light_gbuffer(Globals g, LightGbufferImgs t, float4 ots, uint32_t mode, float real_sun_radius_cos, Rows kjb_rows) {
+KJB_KERNEL(256) k_light_gbuffer(const __grid_constant__ Globals g, LightGbufferImgs t, float4 ots, uint32_t mode, float real_sun_radius_cos, Rows kjb_rows) {
     KJB_PX; if (x >= t.output_tex.w || y >= t.output_tex.h) return;
     const kjb_view_constants& vc = g.fc.view_constants;
     const float s4[4] = {ots.x, ots.y, ots.z, ots.w};
@@ -132,7 +132,7 @@ KJB_DEV float sd_soft_color_clamp(float center, float history, float ex, float d
 
 // "shadow temporal": one 8x8 block per denoiser tile (megakernel.hlsl + ffx_denoiser_shadows_tileclassification.hlsl:316-461)
 struct ShadowTemporalImgs { Img shadow_mask_tex, bitpacked_shadow_mask_tex, prev_moments_tex, prev_accum_tex, reprojection_tex; ImgW output_moments_tex, temporal_output_tex, meta_output_tex; };
-KJB_KERNEL(64) k_shadow_temporal(Globals g, ShadowTemporalImgs t, float4 its, uint32_t ext_x, ShadowKernelWeights kw, Rows kjb_rows) {
+KJB_KERNEL(64) k_shadow_temporal(const __grid_constant__ Globals g, ShadowTemporalImgs t, float4 its, uint32_t ext_x, ShadowKernelWeights kw, Rows kjb_rows) {
     __shared__ float s_neighborhood[8][24];
     const int lx = int(threadIdx.x), ly = int(threadIdx.y);
     const int gx = int(blockIdx.x), gy = kjb_rows.y0 / 8 + int(blockIdx.y);
@@ -274,7 +274,7 @@ KJB_KERNEL(64) k_shadow_spatial(ShadowSpatialImgs t, float4 its, uint32_t ext_x,
 
 // ------------------------------------------------------------------ LightingRenderer::render_specular (renderers/lighting.rs:23-87)
 // "sample lights" (lighting/sample_lights.rgen.hlsl:18-63): one light sample + shadow ray per half-res pixel
-KJB_KERNEL(128) k_sample_lights(Globals g, Img depth_tex, ImgW out0_tex, ImgW out1_tex, ImgW out2_tex, float4 gts, Rows kjb_rows) {
+KJB_KERNEL(128) k_sample_lights(const __grid_constant__ Globals g, Img depth_tex, ImgW out0_tex, ImgW out1_tex, ImgW out2_tex, float4 gts, Rows kjb_rows) {
     KJB_PX; if (x >= out0_tex.w || y >= out0_tex.h) return;
     const kjb_view_constants& vc = g.fc.view_constants;
     const int2 hso = halfres_subsample_offset(g.fc.frame_index);
@@ -301,7 +301,7 @@ KJB_KERNEL(128) k_sample_lights(Globals g, Img depth_tex, ImgW out0_tex, ImgW ou
 
 // "spatial reuse lights" (lighting/spatial_reuse_lights.hlsl:33-168): 8 borrowed half-res samples per pixel, added into the resolved reflections
 struct ReuseLightsImgs { Img gbuffer_tex, depth_tex, hit0_tex, hit1_tex, hit2_tex, half_view_normal_tex, half_depth_tex; ImgW output_tex; };
-KJB_KERNEL(256) k_spatial_reuse_lights(Globals g, ReuseLightsImgs t, float4 ots, const int32_t* offs, Rows kjb_rows) {
+KJB_KERNEL(256) k_spatial_reuse_lights(const __grid_constant__ Globals g, ReuseLightsImgs t, float4 ots, const int32_t* offs, Rows kjb_rows) {
     KJB_PX; if (x >= t.output_tex.w || y >= t.output_tex.h) return;
     const kjb_view_constants& vc = g.fc.view_constants;
     const float s4[4] = {ots.x, ots.y, ots.z, ots.w};

@@ -6,7 +6,7 @@ using namespace kjb;
 
 // ------------------------------------------------------------------ primary-visibility G-buffer by ray casting
 // (stand-in for raster_simple_ps.hlsl:39-140; hit shading = rt/gbuffer.rchit.hlsl)
-KJB_KERNEL(128) k_raster_gbuffer(Globals g, ImgW gn, ImgW gb, ImgW dp, ImgW vel, const kjb_instance* prev_instances, uint32_t prev_instance_count, Rows kjb_rows) {
+KJB_KERNEL(128) k_raster_gbuffer(const __grid_constant__ Globals g, ImgW gn, ImgW gb, ImgW dp, ImgW vel, const kjb_instance* prev_instances, uint32_t prev_instance_count, Rows kjb_rows) {
     KJB_PX; if (x >= gb.w || y >= gb.h) return;
     const kjb_view_constants& vc = g.fc.view_constants;
     const float size[4] = {float(gb.w), float(gb.h), 1.0f / float(gb.w), 1.0f / float(gb.h)};
@@ -53,7 +53,7 @@ KJB_KERNEL(128) k_raster_gbuffer(Globals g, ImgW gn, ImgW gb, ImgW dp, ImgW vel,
 }
 
 // ------------------------------------------------------------------ calculate_reprojection_map.hlsl:17-142
-KJB_KERNEL(256) k_reprojection_map(Globals g, Img depth_tex, Img geometric_normal_tex, Img prev_depth_tex, Img velocity_tex, ImgW output_tex, float4 output_tex_size, Rows kjb_rows) {
+KJB_KERNEL(256) k_reprojection_map(const __grid_constant__ Globals g, Img depth_tex, Img geometric_normal_tex, Img prev_depth_tex, Img velocity_tex, ImgW output_tex, float4 output_tex_size, Rows kjb_rows) {
     KJB_PX; if (x >= output_tex.w || y >= output_tex.h) return;
     const kjb_view_constants& vc = g.fc.view_constants;
     const float ots[4] = {output_tex_size.x, output_tex_size.y, output_tex_size.z, output_tex_size.w};
@@ -127,7 +127,7 @@ KJB_DEV float3 cube_dir(int face, float2 uv) {
     }
     return normalize(d);
 }
-KJB_KERNEL(64) k_sky_cube(Globals g, ImgW out, Rows kjb_rows) {
+KJB_KERNEL(64) k_sky_cube(const __grid_constant__ Globals g, ImgW out, Rows kjb_rows) {
     KJB_PX; const int face = int(blockIdx.z); if (x >= out.w || y >= out.h) return;
     const float2 uv = (f2(float(x), float(y)) + 0.5f) / 64.0f;
     const float3 dir = cube_dir(face, uv);
@@ -176,14 +176,14 @@ KJB_KERNEL(256) k_extract_half_ssao(Img in, ImgW out, int2 off, Rows kjb_rows) {
     KJB_PX; if (x >= out.w || y >= out.h) return;
     st_r8s(out, x, y, ld_r8u(in, x * 2 + off.x, y * 2 + off.y));
 }
-KJB_KERNEL(256) k_extract_half_view_normal(Globals g, Img in, ImgW out, int2 off, Rows kjb_rows) {
+KJB_KERNEL(256) k_extract_half_view_normal(const __grid_constant__ Globals g, Img in, ImgW out, int2 off, Rows kjb_rows) {
     KJB_PX; if (x >= out.w || y >= out.h) return;
     const uint4 gbt = ld_rgba32u(in, x * 2 + off.x, y * 2 + off.y);
     const float3 normal_ws = unpack_normal_11_10_11_no_normalize(gbt.y);
     const float3 normal_vs = normalize(xyz(mul(g.fc.view_constants.world_to_view, f4(normal_ws, 0))));
     st_rgba8s(out, x, y, f4(normal_vs, 1));
 }
-KJB_KERNEL(256) k_extract_half_fused(Globals g, Img gbuffer, Img depth, Img ssao, ImgW out_normal, ImgW out_depth, ImgW out_ssao, int with_ssao, int2 off, float4* positions, float4 gts, Rows kjb_rows) {
+KJB_KERNEL(256) k_extract_half_fused(const __grid_constant__ Globals g, Img gbuffer, Img depth, Img ssao, ImgW out_normal, ImgW out_depth, ImgW out_ssao, int with_ssao, int2 off, float4* positions, float4 gts, Rows kjb_rows) {
     KJB_PX; if (x >= out_depth.w || y >= out_depth.h) return;
     const int sx = x * 2 + off.x, sy = y * 2 + off.y;
     const float d = ld_r32f(depth, sx, sy);

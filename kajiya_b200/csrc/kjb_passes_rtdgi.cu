@@ -180,7 +180,7 @@ KJB_DEV void rtdgi_validate_px(const Globals& g, const Img& half_view_normal_tex
     }
     st_r8u(out_tex, x, y, invalidity);
 }
-KJB_KERNEL(128) k_rtdgi_validate(Globals g, Img half_view_normal_tex, Img depth_tex, Img reprojected_gi_tex, ImgW reservoir_tex, Img reservoir_ray_history_tex,
+KJB_KERNEL(128) k_rtdgi_validate(const __grid_constant__ Globals g, Img half_view_normal_tex, Img depth_tex, Img reprojected_gi_tex, ImgW reservoir_tex, Img reservoir_ray_history_tex,
                                  Img sky_cube_tex, ImgW irradiance_history_tex, Img ray_orig_history_tex, ImgW out_tex, float4 gts, IrcacheBufs ircache, Rows kjb_rows) {
     KJB_PX; if (x >= out_tex.w || y >= out_tex.h) return;
     rtdgi_validate_px(g, half_view_normal_tex, depth_tex, reprojected_gi_tex, reservoir_tex, reservoir_ray_history_tex, sky_cube_tex, irradiance_history_tex, ray_orig_history_tex, out_tex, gts, ircache, x, y);
@@ -190,7 +190,7 @@ KJB_KERNEL(128) k_rtdgi_validate(Globals g, Img half_view_normal_tex, Img depth_
 #define KJB_SERIAL_TILES(W, H, ...) do { if (blockIdx.x | blockIdx.y | threadIdx.x | threadIdx.y) return; \
         for (int by = kjb_rows.y0; by < kjb_rows.y1; by += KJB_RAY_BY) for (int bx = 0; bx < (W); bx += KJB_RAY_BX) \
             for (int y = by; y < by + KJB_RAY_BY && y < kjb_rows.y1 && y < (H); ++y) for (int x = bx; x < bx + KJB_RAY_BX && x < (W); ++x) { __VA_ARGS__; } } while (0)
-KJB_KERNEL(32) k_rtdgi_validate_serial(Globals g, Img half_view_normal_tex, Img depth_tex, Img reprojected_gi_tex, ImgW reservoir_tex, Img reservoir_ray_history_tex,
+KJB_KERNEL(32) k_rtdgi_validate_serial(const __grid_constant__ Globals g, Img half_view_normal_tex, Img depth_tex, Img reprojected_gi_tex, ImgW reservoir_tex, Img reservoir_ray_history_tex,
                                        Img sky_cube_tex, ImgW irradiance_history_tex, Img ray_orig_history_tex, ImgW out_tex, float4 gts, IrcacheBufs ircache, Rows kjb_rows) {
     KJB_SERIAL_TILES(out_tex.w, out_tex.h, rtdgi_validate_px(g, half_view_normal_tex, depth_tex, reprojected_gi_tex, reservoir_tex, reservoir_ray_history_tex, sky_cube_tex, irradiance_history_tex,
                                                               ray_orig_history_tex, out_tex, gts, ircache, x, y));
@@ -232,14 +232,14 @@ KJB_DEV void rtdgi_trace_px(const Globals& g, const Img& half_view_normal_tex, c
     st_r8u(inv_out, x, y, ld_r8u(inv_in, rx, ry));
 }
 #ifndef KJB_OCC_TRACE
-#define KJB_OCC_TRACE 6   /* 78 registers, no spills: 78 -> 68 us */
+#define KJB_OCC_TRACE 8   /* 64 registers: 377 (4 blocks) / 356 (6) / 331 us (8) at 1080p atrium (profiles/r02j_variants.txt) */
 #endif
-KJB_KERNEL_OCC(128, KJB_OCC_TRACE) k_rtdgi_trace(Globals g, Img half_view_normal_tex, Img depth_tex, Img reprojected_gi_tex, Img reprojection_tex, Img sky_cube_tex,
+KJB_KERNEL_OCC(128, KJB_OCC_TRACE) k_rtdgi_trace(const __grid_constant__ Globals g, Img half_view_normal_tex, Img depth_tex, Img reprojected_gi_tex, Img reprojection_tex, Img sky_cube_tex,
                               ImgW cand_irr, ImgW cand_normal, ImgW cand_hit, Img inv_in, ImgW inv_out, float4 gts, IrcacheBufs ircache, Rows kjb_rows) {
     KJB_PX; if (x >= cand_irr.w || y >= cand_irr.h) return;
     rtdgi_trace_px(g, half_view_normal_tex, depth_tex, reprojected_gi_tex, reprojection_tex, sky_cube_tex, cand_irr, cand_normal, cand_hit, inv_in, inv_out, gts, ircache, x, y);
 }
-KJB_KERNEL(32) k_rtdgi_trace_serial(Globals g, Img half_view_normal_tex, Img depth_tex, Img reprojected_gi_tex, Img reprojection_tex, Img sky_cube_tex,
+KJB_KERNEL(32) k_rtdgi_trace_serial(const __grid_constant__ Globals g, Img half_view_normal_tex, Img depth_tex, Img reprojected_gi_tex, Img reprojection_tex, Img sky_cube_tex,
                                     ImgW cand_irr, ImgW cand_normal, ImgW cand_hit, Img inv_in, ImgW inv_out, float4 gts, IrcacheBufs ircache, Rows kjb_rows) {
     KJB_SERIAL_TILES(cand_irr.w, cand_irr.h, rtdgi_trace_px(g, half_view_normal_tex, depth_tex, reprojected_gi_tex, reprojection_tex, sky_cube_tex, cand_irr, cand_normal, cand_hit, inv_in, inv_out, gts, ircache, x, y));
 }
@@ -264,7 +264,7 @@ KJB_DEV float d5_edge(const Img& reprojection_tex, const Img& half_depth_tex, in
 }
 #define D5_BX 8
 #define D5_BY 32
-KJB_KERNEL(256) k_rtdgi_validity_integrate(Globals g, Img input_tex, Img history_tex, Img reprojection_tex, Img half_depth_tex, ImgW output_tex, float4 gts, Weights25v wt, Rows kjb_rows) {
+KJB_KERNEL(256) k_rtdgi_validity_integrate(const __grid_constant__ Globals g, Img input_tex, Img history_tex, Img reprojection_tex, Img half_depth_tex, ImgW output_tex, float4 gts, Weights25v wt, Rows kjb_rows) {
     __shared__ float in_tile[D5_BY + 4][D5_BX + 4];
     const int tx = int(threadIdx.x), ty = int(threadIdx.y);
     const int bx0 = int(blockIdx.x) * D5_BX, by0 = (kjb_rows.y0 & ~3) + int(blockIdx.y) * D5_BY;
@@ -314,7 +314,7 @@ struct RestirTemporalImgs {
 #ifndef KJB_OCC_RESTIR_TEMPORAL
 #define KJB_OCC_RESTIR_TEMPORAL 4   /* 64 registers: 45 -> 36 us */
 #endif
-KJB_KERNEL_OCC(256, KJB_OCC_RESTIR_TEMPORAL) k_rtdgi_restir_temporal(Globals g, RestirTemporalImgs t, float4 gts, float4* positions, Rows kjb_rows) {
+KJB_KERNEL_OCC(256, KJB_OCC_RESTIR_TEMPORAL) k_rtdgi_restir_temporal(const __grid_constant__ Globals g, RestirTemporalImgs t, float4 gts, float4* positions, Rows kjb_rows) {
     KJB_PX; if (x >= t.radiance_out_tex.w || y >= t.radiance_out_tex.h) return;
     const kjb_view_constants& vc = g.fc.view_constants;
     const uint32_t frame_index = g.fc.frame_index;
@@ -441,7 +441,7 @@ KJB_DEV float3 cached_or_hit_ws(const PosView& pv, const kjb_view_constants& vc,
     if (pv.p && (unsigned)px < (unsigned)pv.w && (unsigned)py < (unsigned)pv.h) return xyz(pv.p[py * pv.w + px]);
     return hit_ws_from_uv_depth(vc, uv, depth);
 }
-KJB_KERNEL(256) k_half_res_positions(Globals g, Img src, int packed, float4* out, float4 gts, Rows kjb_rows) {
+KJB_KERNEL(256) k_half_res_positions(const __grid_constant__ Globals g, Img src, int packed, float4* out, float4 gts, Rows kjb_rows) {
     KJB_PX; if (x >= src.w || y >= src.h) return;
     const int2 hso = halfres_subsample_offset(g.fc.frame_index);
     const float s4[4] = {gts.x, gts.y, gts.z, gts.w};
@@ -468,7 +468,7 @@ KJB_DEV float normal_influence_nonlinearity(float x, float b) { return x < -b ? 
 #ifndef KJB_OCC_RESTIR_SPATIAL
 #define KJB_OCC_RESTIR_SPATIAL 1   /* 74 registers; capping at 64 / 48 costs 5 % / 13 % */
 #endif
-KJB_KERNEL_OCC(256, KJB_OCC_RESTIR_SPATIAL) k_rtdgi_restir_spatial(Globals g, Img reservoir_input_tex, Img half_view_normal_tex, Img half_depth_tex, Img half_ssao_tex, Img temporal_reservoir_packed_tex,
+KJB_KERNEL_OCC(256, KJB_OCC_RESTIR_SPATIAL) k_rtdgi_restir_spatial(const __grid_constant__ Globals g, Img reservoir_input_tex, Img half_view_normal_tex, Img half_depth_tex, Img half_ssao_tex, Img temporal_reservoir_packed_tex,
                                        ImgW reservoir_output_tex, float4 gts, float4 ots, uint32_t pass_idx, uint32_t perform_occlusion_raymarch, uint32_t importance_only, PosView pos_a, PosView pos_b, Rows kjb_rows) {
     // The tap angles `(sample_i + ang_offset) * GOLDEN_ANGLE` depend on the pixel only through its 8x8 (pass 0) / 4x4 (later passes) screen tile
     // (ang_offset = hash of the tile): a 32x8 block covers at most 4x2 / 8x3 such tiles, so the block evaluates each tile's 8 / 5 sin-cos pairs
@@ -602,7 +602,7 @@ KJB_KERNEL_OCC(256, KJB_OCC_RESTIR_SPATIAL) k_rtdgi_restir_spatial(Globals g, Im
 }
 
 // ------------------------------------------------------------------ D8 restir_check.rgen.hlsl:21-66 (optional)
-KJB_KERNEL(128) k_rtdgi_restir_check(Globals g, Img half_depth_tex, Img temporal_reservoir_packed_tex, ImgW reservoir_input_tex, float4 gts, Rows kjb_rows) {
+KJB_KERNEL(128) k_rtdgi_restir_check(const __grid_constant__ Globals g, Img half_depth_tex, Img temporal_reservoir_packed_tex, ImgW reservoir_input_tex, float4 gts, Rows kjb_rows) {
     KJB_PX; if (x >= reservoir_input_tex.w || y >= reservoir_input_tex.h) return;
     const kjb_view_constants& vc = g.fc.view_constants;
     const int2 hso = halfres_subsample_offset(g.fc.frame_index);
@@ -630,7 +630,7 @@ struct PowTable4 { float v[4]; };   // v[i] = pow(float(i), 0.666), host-evaluat
 #ifndef KJB_OCC_RESTIR_RESOLVE
 #define KJB_OCC_RESTIR_RESOLVE 5   /* 48 registers, 5 blocks/SM: 117 -> 112 us at 1080p (profiles/r01r_variants.txt) */
 #endif
-KJB_KERNEL_OCC(256, KJB_OCC_RESTIR_RESOLVE) k_rtdgi_restir_resolve(Globals g, ResolveImgs t, ImgW irradiance_output_tex, float4 gts, float4 ots, PowTable4 pw, PosView pos_a, PosView pos_b, Rows kjb_rows) {
+KJB_KERNEL_OCC(256, KJB_OCC_RESTIR_RESOLVE) k_rtdgi_restir_resolve(const __grid_constant__ Globals g, ResolveImgs t, ImgW irradiance_output_tex, float4 gts, float4 ots, PowTable4 pw, PosView pos_a, PosView pos_b, Rows kjb_rows) {
     KJB_PX; if (x >= irradiance_output_tex.w || y >= irradiance_output_tex.h) return;
     const kjb_view_constants& vc = g.fc.view_constants;
     const int2 hso = halfres_subsample_offset(g.fc.frame_index);
@@ -806,7 +806,7 @@ KJB_KERNEL(512) k_rtdgi_temporal(const __grid_constant__ TileSource ts_input, co
 KJB_DEV float3 crunch(float3 v) { return v * kjb_rcp(max3(v.x, v.y, v.z) + 1.0f); }
 KJB_DEV float3 uncrunch(float3 v) { return v * kjb_rcp(1.0f - max3(v.x, v.y, v.z)); }
 struct PowTable8 { float v[8]; };   // v[i] = pow(float(i), 0.666): compile-time constants in the shader ("must be constant, so the pow can be const-folded"), host-evaluated here
-KJB_KERNEL(256) k_rtdgi_spatial(Globals g, Img input_tex, Img depth_tex, Img ssao_tex, Img geometric_normal_tex, ImgW output_tex, PowTable8 pw, Rows kjb_rows) {
+KJB_KERNEL(256) k_rtdgi_spatial(const __grid_constant__ Globals g, Img input_tex, Img depth_tex, Img ssao_tex, Img geometric_normal_tex, ImgW output_tex, PowTable8 pw, Rows kjb_rows) {
     KJB_PX; if (x >= output_tex.w || y >= output_tex.h) return;
     const float4 cin = ld_rgba16f(input_tex, x, y);
     const float center_validity = cin.w;

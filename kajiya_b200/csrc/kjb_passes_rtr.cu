@@ -166,14 +166,14 @@ KJB_DEV void rtr_trace_px(const Globals& g, const RtrTraceImgs& t, const BlueNoi
         st_rgba16f(t.out1_tex, x, y, f4(0.0f));
     }
 }
-KJB_KERNEL(128) k_rtr_trace(Globals g, RtrTraceImgs t, BlueNoiseSamplerTables bn, float4 gts, uint32_t reuse_rtdgi_rays, IrcacheBufs ircache, Rows kjb_rows) {
+KJB_KERNEL(128) k_rtr_trace(const __grid_constant__ Globals g, RtrTraceImgs t, BlueNoiseSamplerTables bn, float4 gts, uint32_t reuse_rtdgi_rays, IrcacheBufs ircache, Rows kjb_rows) {
     KJB_PX; if (x >= t.out0_tex.w || y >= t.out0_tex.h) return;
     rtr_trace_px(g, t, bn, gts, reuse_rtdgi_rays, ircache, x, y);
 }
 #define KJB_SERIAL_TILES(W, H, ...) do { if (blockIdx.x | blockIdx.y | threadIdx.x | threadIdx.y) return; \
         for (int by = kjb_rows.y0; by < kjb_rows.y1; by += KJB_RAY_BY) for (int bx = 0; bx < (W); bx += KJB_RAY_BX) \
             for (int y = by; y < by + KJB_RAY_BY && y < kjb_rows.y1 && y < (H); ++y) for (int x = bx; x < bx + KJB_RAY_BX && x < (W); ++x) { __VA_ARGS__; } } while (0)
-KJB_KERNEL(32) k_rtr_trace_serial(Globals g, RtrTraceImgs t, BlueNoiseSamplerTables bn, float4 gts, uint32_t reuse_rtdgi_rays, IrcacheBufs ircache, Rows kjb_rows) {
+KJB_KERNEL(32) k_rtr_trace_serial(const __grid_constant__ Globals g, RtrTraceImgs t, BlueNoiseSamplerTables bn, float4 gts, uint32_t reuse_rtdgi_rays, IrcacheBufs ircache, Rows kjb_rows) {
     KJB_SERIAL_TILES(t.out0_tex.w, t.out0_tex.h, rtr_trace_px(g, t, bn, gts, reuse_rtdgi_rays, ircache, x, y));
 }
 
@@ -221,11 +221,11 @@ KJB_DEV void rtr_validate_quad(const Globals& g, const RtrValidateImgs& t, float
         }
     }
 }
-KJB_KERNEL(128) k_rtr_validate(Globals g, RtrValidateImgs t, float4 gts, IrcacheBufs ircache, int QW, int QH, Rows kjb_rows) {
+KJB_KERNEL(128) k_rtr_validate(const __grid_constant__ Globals g, RtrValidateImgs t, float4 gts, IrcacheBufs ircache, int QW, int QH, Rows kjb_rows) {
     KJB_PX; if (x >= QW || y >= QH) return;
     rtr_validate_quad(g, t, gts, ircache, x, y);
 }
-KJB_KERNEL(32) k_rtr_validate_serial(Globals g, RtrValidateImgs t, float4 gts, IrcacheBufs ircache, int QW, int QH, Rows kjb_rows) {
+KJB_KERNEL(32) k_rtr_validate_serial(const __grid_constant__ Globals g, RtrValidateImgs t, float4 gts, IrcacheBufs ircache, int QW, int QH, Rows kjb_rows) {
     KJB_SERIAL_TILES(QW, QH, rtr_validate_quad(g, t, gts, ircache, x, y));
 }
 
@@ -266,7 +266,7 @@ KJB_DEV void find_best_reprojection_in_neighborhood(const Globals& g, const RtrR
 #ifndef KJB_OCC_RTR_RESTIR_TEMPORAL
 #define KJB_OCC_RTR_RESTIR_TEMPORAL 1
 #endif
-KJB_KERNEL_OCC(256, KJB_OCC_RTR_RESTIR_TEMPORAL) k_rtr_restir_temporal(Globals g, RtrRestirTemporalImgs t, float4 gts, Rows kjb_rows) {
+KJB_KERNEL_OCC(256, KJB_OCC_RTR_RESTIR_TEMPORAL) k_rtr_restir_temporal(const __grid_constant__ Globals g, RtrRestirTemporalImgs t, float4 gts, Rows kjb_rows) {
     KJB_PX; if (x >= t.irradiance_out_tex.w || y >= t.irradiance_out_tex.h) return;
     const kjb_view_constants& vc = g.fc.view_constants;
     const int2 hso = halfres_subsample_offset(g.fc.frame_index);
@@ -404,12 +404,12 @@ KJB_KERNEL_OCC(256, KJB_OCC_RTR_RESTIR_TEMPORAL) k_rtr_restir_temporal(Globals g
 // ------------------------------------------------------------------ R4 resolve.hlsl:78-663 (USE_RESTIR, BORROW_SAMPLES, CUT_CORNERS_IN_MATH)
 struct RtrResolveImgs { Img gbuffer_tex, depth_tex, hit1_tex, reprojection_tex, half_view_normal_tex, ray_len_history_tex, restir_irradiance_tex, restir_ray_tex, restir_reservoir_tex, restir_ray_orig_tex; ImgW output_tex, ray_len_output_tex; };
 #ifndef KJB_OCC_RTR_RESOLVE
-#define KJB_OCC_RTR_RESOLVE 2
+#define KJB_OCC_RTR_RESOLVE 4   /* 98 -> 64 registers (80 B of spills), 4 blocks per SM: 1034 (2 blocks) -> 828 (3) -> 787 us (4) at 1080p (profiles/r02i_variants.txt, r02j_variants.txt) */
 #endif
 // sin / cos of the tap angles `(sample_i + ang_offset) * GOLDEN_ANGLE + (px_idx_in_quad / 4) * TAU`: 4 quad slots x 8 taps = 32 distinct angles per FRAME
 // (ang_offset depends on the frame index only), so the host evaluates them once with the contract's kjb_sincos and every pixel looks its eight up
 struct ResolveTapAngles { float sn[32], cs[32]; };
-KJB_KERNEL_OCC(256, KJB_OCC_RTR_RESOLVE) k_rtr_resolve(Globals g, RtrResolveImgs t, float4 ots, float radius_sample_mult, ResolveTapAngles ta, Rows kjb_rows) {
+KJB_KERNEL_OCC(256, KJB_OCC_RTR_RESOLVE) k_rtr_resolve(const __grid_constant__ Globals g, RtrResolveImgs t, float4 ots, float radius_sample_mult, const __grid_constant__ ResolveTapAngles ta, Rows kjb_rows) {
     KJB_PX; if (x >= t.output_tex.w || y >= t.output_tex.h) return;
     const kjb_view_constants& vc = g.fc.view_constants;
     const int hpx = x / 2, hpy = y / 2;
@@ -689,7 +689,7 @@ KJB_KERNEL_OCC(256, KJB_OCC_RTR_TEMPORAL) k_rtr_temporal(const __grid_constant__
 }
 
 // ------------------------------------------------------------------ R6 spatial_cleanup.hlsl:19-65
-KJB_KERNEL(256) k_rtr_cleanup(Globals g, Img input_tex, Img depth_tex, Img geometric_normal_tex, ImgW output_tex, const int32_t* offs, Rows kjb_rows) {
+KJB_KERNEL(256) k_rtr_cleanup(const __grid_constant__ Globals g, Img input_tex, Img depth_tex, Img geometric_normal_tex, ImgW output_tex, const int32_t* offs, Rows kjb_rows) {
     KJB_PX; if (x >= output_tex.w || y >= output_tex.h) return;
     const kjb_view_constants& vc = g.fc.view_constants;
     const float4 center = ld_rgba16f(input_tex, x, y);

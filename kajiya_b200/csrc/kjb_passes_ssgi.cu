@@ -24,7 +24,7 @@ KJB_DEV float update_horizion_angle(float prev, float cur, float blend) { return
 struct SsaoFrameTables { float temporal_rotation, temporal_offset; };   // temporal_rotations[frame % 6], temporal_offsets[frame / 6 % 4]
 
 // ------------------------------------------------------------------ "ssao": ssgi.hlsl:214-341 (half-res, 6 samples per half slice)
-KJB_KERNEL(256) k_ssao(Globals g, Img gbuffer_tex, Img depth_tex, ImgW output_tex, float4 its, float4 ots, SsaoFrameTables ft, Rows kjb_rows) {
+KJB_KERNEL(256) k_ssao(const __grid_constant__ Globals g, Img gbuffer_tex, Img depth_tex, ImgW output_tex, float4 its, float4 ots, SsaoFrameTables ft, Rows kjb_rows) {
     KJB_PX; if (x >= output_tex.w || y >= output_tex.h) return;
     const kjb_view_constants& vc = g.fc.view_constants;
     const float s4[4] = {ots.x, ots.y, ots.z, ots.w};

@@ -27,7 +27,7 @@ KJB_DEV bool t1_should_dilate0(const Img& reprojection_tex, int x, int y, float2
 // WaveReadLaneAt(^2) / (^16) exchange of the dilation flag (reproject_history.hlsl:80-82) is two warp shuffles
 #define T1_BX 8
 #define T1_BY 32
-KJB_KERNEL(256) k_taa_reproject(Globals g, Img history_tex, Img reprojection_tex, Img depth_tex, ImgW output_tex, ImgW closest_velocity_output, float4 its, float4 ots, Rows kjb_rows) {
+KJB_KERNEL(256) k_taa_reproject(const __grid_constant__ Globals g, Img history_tex, Img reprojection_tex, Img depth_tex, ImgW output_tex, ImgW closest_velocity_output, float4 its, float4 ots, Rows kjb_rows) {
     const int x = int(blockIdx.x) * T1_BX + int(threadIdx.x), y = (kjb_rows.y0 & ~3) + int(blockIdx.y) * T1_BY + int(threadIdx.y);
     const int W = output_tex.w, H = output_tex.h;
     const float2 irs = f2(its.x, its.y) / f2(ots.x, ots.y);
@@ -212,7 +212,7 @@ KJB_KERNEL(256) k_taa_filter_history_tiled(const __grid_constant__ TileSource ts
 }
 
 // ------------------------------------------------------------------ T4 input_prob.hlsl:47-109
-KJB_KERNEL(256) k_taa_input_prob(Globals g, Img filtered_input_tex, Img filtered_input_dev_tex, Img filtered_history_tex, Img reprojection_tex, Img smooth_var_history_tex,
+KJB_KERNEL(256) k_taa_input_prob(const __grid_constant__ Globals g, Img filtered_input_tex, Img filtered_input_dev_tex, Img filtered_history_tex, Img reprojection_tex, Img smooth_var_history_tex,
                                  Img velocity_history_tex, ImgW output_tex, float4 its, Rows kjb_rows) {
     KJB_PX; if (x >= output_tex.w || y >= output_tex.h) return;
     float input_prob = 0;
@@ -386,7 +386,7 @@ KJB_DEV void taa_px(const Globals& g, const TaaImgs& t, float4 its, float4 ots, 
     const float2 vo = cvel / dt;
     st_rg16f(t.velocity_output_tex, x, y, vo.x, vo.y);
 }
-KJB_KERNEL(256) k_taa(Globals g, TaaImgs t, float4 its, float4 ots, W25t bw, Rows kjb_rows) {
+KJB_KERNEL(256) k_taa(const __grid_constant__ Globals g, TaaImgs t, float4 its, float4 ots, W25t bw, Rows kjb_rows) {
     KJB_PX; if (x >= t.temporal_output_tex.w || y >= t.temporal_output_tex.h) return;
     taa_px(g, t, its, ots, bw, x, y, [&](int xx, int yy) { return ld_rgba16f(t.history_tex, x + xx, y + yy); },
            [&](int bx, int by, int dx, int dy) { return taa_input_remap(ld_rgba16f(t.input_tex, bx + dx, by + dy)); });

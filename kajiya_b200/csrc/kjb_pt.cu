@@ -12,7 +12,7 @@ KJB_DEV float remap_unorm_to_gaussian(float xin, float truncation) {   // :60-72
     return kjb_sqrt(kjb_max(0.0f, kjb_sqrt(z * z - y * INV_ALPHA) - z)) * kjb_sign(x);
 }
 
-KJB_KERNEL(128) k_reference_pt(Globals g, ImgW output_tex, uint32_t indirect_only, Rows kjb_rows) {
+KJB_KERNEL(128) k_reference_pt(const __grid_constant__ Globals g, ImgW output_tex, uint32_t indirect_only, Rows kjb_rows) {
     KJB_PX; const int W = output_tex.w, H = output_tex.h; if (x >= W || y >= H) return;
     const kjb_view_constants& vc = g.fc.view_constants;
     const float4 prev = ld_rgba32f(as_ro(output_tex), x, y);
