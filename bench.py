@@ -367,7 +367,10 @@ def summarize(m, world_size, peak, ncu_table):
     return {"ms_per_step": frame_ms, "value": m["rays"] / (m["ms_total"] * 1e-3), "unit": "rays/s", "rays_per_frame": m["rays"] / K,
             "e2e": {"value": m["rays_e2e"] / (m["ms_e2e"] * 1e-3), "unit": "rays/s", "ms_per_step": m["ms_e2e"] / K, "h2d_bytes_per_step": int(m["h2d"]), "d2h_bytes_per_step": int(m["d2h"]),
                     "mode": "streaming: upload/compute/download queues, 2 frames in flight" if m["streaming"] else "blocking call per frame"},
-            "gpu_launches": int(m["launches"]), "roofline": roof}
+            "gpu_launches": int(m["launches"]), "roofline": roof,
+            "submission": ("frames submitted back to back; " + ("tile-sharded: direct launches, exchange on the comm queue" if world_size > 1 else
+                           "CUDA graph recordings per frame" + ("; irradiance-cache chain of frame N+1 on the async pass queue under the reflection filters + TAA of frame N "
+                           "(kjb_world_set_async_compute; per_pass_ms is measured with it off, one queue, direct launches)" if "enable_ircache" in WORKLOADS[m["workload"]][5] and not os.environ.get("KJB_NO_ASYNC") else "")))}
 
 
 def measure_fast_math(torch, workload, K, Wm, local_rank, nslots=8):

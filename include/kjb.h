@@ -234,6 +234,7 @@ int  kjb_memcpy_d2d_batch_on(kjb_context *ctx, uint32_t queue, const kjb_copy_de
 #define KJB_QUEUE_UPLOAD   1u
 #define KJB_QUEUE_DOWNLOAD 2u
 #define KJB_QUEUE_COMM     3u   /* collectives of tile-sharded frames, so that they overlap passes that do not depend on them */
+#define KJB_QUEUE_ASYNC    4u   /* a second, high-priority PASS queue ("async compute"): see kjb_set_pass_queue */
 #define KJB_MAX_EVENTS 64u
 int  kjb_image_upload_on(kjb_context *ctx, uint32_t queue, const kjb_image *dst, const void *host_src);
 int  kjb_image_download_on(kjb_context *ctx, uint32_t queue, const kjb_image *src, void *host_dst);
@@ -259,6 +260,17 @@ int  kjb_set_option(kjb_context *ctx, uint32_t option, uint32_t value);
  * topology), and submits the whole frame with ONE launch.  Calls that touch other queues or wait on the host must stay outside the pair. */
 int  kjb_graph_begin(kjb_context *ctx);
 int  kjb_graph_end(kjb_context *ctx);
+/* A frame driver that splits its frame into several recordings (because it orders other queues against the middle of the frame) keeps one
+ * instance per piece: the slot (0..3) selected here is the instance the following kjb_graph_begin / kjb_graph_end pairs update and launch. */
+int  kjb_graph_select(kjb_context *ctx, uint32_t slot);
+/* Async compute: the queue every FOLLOWING kjb_pass_* (and kjb_image_copy / clear helpers a pass driver issues) is enqueued on —
+ * KJB_QUEUE_COMPUTE (default) or KJB_QUEUE_ASYNC.  The two queues run concurrently; the caller orders them with kjb_event_record /
+ * kjb_queue_wait_event exactly like the copy queues.  Meant for small latency-bound pass chains that share no resource with what the
+ * compute queue is doing (the frame driver runs the irradiance-cache maintenance + cache rays of frame N+1 under the reflection filters and
+ * TAA of frame N, kjb_world.h).  Passes on the async queue are never part of a graph recording.  kjb_async_passes_supported: 1 when the two
+ * queues really overlap (CUDA build, serialised debugging off), 0 for the single-queue backends (CPU oracle, emulator, recorder). */
+int  kjb_set_pass_queue(kjb_context *ctx, uint32_t queue);
+int  kjb_async_passes_supported(kjb_context *ctx);
 int  kjb_graph_stats(kjb_context *ctx, uint64_t out_launches_instantiations[2]);
 int  kjb_set_scissor(kjb_context *ctx, uint32_t y0, uint32_t y1);
 /* Determinism aid: while on, every pass that touches the (racy by design) irradiance cache runs on ONE device thread in the launch

@@ -126,6 +126,13 @@ int  kjb_world_set_profiling(kjb_world *w, uint32_t on);
  * frame on (every lazily created resource exists by then), never while per-pass profiling is on or the frame is tile-sharded (its exchange lives on
  * another queue).  The environment variable KJB_NO_GRAPH=1 switches the default off (A/B timing). */
 int  kjb_world_set_cuda_graph(kjb_world *w, uint32_t on);
+/* Async compute (kjb_set_pass_queue, kjb.h): the irradiance-cache chain of a frame — cascade scroll, ageing, compaction, cache rays, sum — is ~10 small,
+ * latency-bound launches that need nothing of the frame's screen-space inputs, only that the PREVIOUS frame's cache users ("rtdgi validate/trace",
+ * "reflection trace/validate") are done.  With this on (default; CUDA backend, from the fifth frame, not while profiling / tile-sharded / serialised, not in a
+ * frame that rebuilt the acceleration structure or the sky) the chain is enqueued on the async queue: it runs under the previous frame's reflection
+ * filters and TAA and under this frame's reprojection passes, and the frame is submitted as three recordings around the two ordering points.  The pass
+ * call order (the reference's render-graph order) does not change.  KJB_NO_ASYNC=1 switches the default off (A/B timing). */
+int  kjb_world_set_async_compute(kjb_world *w, uint32_t on);
 /* "label\tcalls\ttotal_ms\n" per pass since profiling was switched on (synchronises). */
 const char *kjb_world_pass_timings(kjb_world *w);
 

@@ -117,7 +117,8 @@ class KjbLib:
             "kjb_set_debug_serial": (C.c_int, [P, C.c_uint32]),
             "kjb_tlas_stats": (C.c_int, [P, C.POINTER(C.c_uint64 * 2)]),
             "kjb_graph_stats": (C.c_int, [P, C.POINTER(C.c_uint64 * 2)]),
-            "kjb_world_set_cuda_graph": (C.c_int, [P, C.c_uint32]),
+            "kjb_graph_select": (C.c_int, [P, C.c_uint32]), "kjb_set_pass_queue": (C.c_int, [P, C.c_uint32]), "kjb_async_passes_supported": (C.c_int, [P]),
+            "kjb_world_set_cuda_graph": (C.c_int, [P, C.c_uint32]), "kjb_world_set_async_compute": (C.c_int, [P, C.c_uint32]),
             "kjb_set_option": (C.c_int, [P, C.c_uint32, C.c_uint32]),
             "kjb_timer_record": (C.c_int, [P, C.c_uint32]),
             "kjb_timer_elapsed_ms": (C.c_int, [P, C.c_uint32, C.c_uint32, C.POINTER(C.c_float)]),

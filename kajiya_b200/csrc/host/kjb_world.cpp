@@ -155,6 +155,10 @@ struct kjb_world {
         kjb_set_scissor(ctx, a, b);
     }
     bool use_graph = true, graph_open = false;   // kjb_world_set_cuda_graph
+    // Async compute (kjb_world_set_async_compute): the irradiance-cache chain of a frame (maintenance, cache rays, sum: ~10 small latency-bound launches)
+    // runs on the async pass queue.  It needs nothing of this frame's screen-space inputs, only that the LAST frame's cache users are done, so it
+    // executes under the reflection filters + TAA of the previous frame and under this frame's reprojection passes.
+    bool use_async = true, async_ok = false, async_frame = false, cache_users_done_marked = false;   // async_ok: the two pass queues may run concurrently this frame
     bool profiling = false; uint32_t timer_next = 0;
     std::vector<std::pair<std::string, std::pair<uint32_t, uint32_t>>> timer_pending;   // label -> (slot_begin, slot_end) of this frame
     std::map<std::string, std::pair<uint32_t, double>> pass_ms;                          // label -> (calls, total ms)
@@ -220,6 +224,7 @@ int kjb_world_create(kjb_context* ctx, const kjb_world_desc* desc, kjb_world** o
     w->ctx = ctx; w->desc = *desc;
     w->sun_size_multiplier = desc->hard_sun ? 0.0f : 1.0f;
     { const char* e = getenv("KJB_NO_GRAPH"); if (e && e[0] == '1') w->use_graph = false; }
+    { const char* e = getenv("KJB_NO_ASYNC"); if (e && e[0] == '1') w->use_async = false; }
     kjb_set_option(ctx, KJB_OPTION_HALF_RES_POSITION_CACHE, 1);   // this driver only writes half_depth / the packed reservoirs through the passes the option tracks
     if (w->desc.spatial_reuse_pass_count == 0) w->desc.spatial_reuse_pass_count = 2;
     w->W = desc->render_width; w->H = desc->render_height;
@@ -399,6 +404,7 @@ int kjb_world_last_frame_stats(kjb_world* w, uint64_t out[4]) {
 }
 int kjb_world_set_stop_after(kjb_world* w, const char* label) { w->stop_after = label ? label : ""; return 0; }
 int kjb_world_set_cuda_graph(kjb_world* w, uint32_t on) { w->use_graph = on != 0; return 0; }
+int kjb_world_set_async_compute(kjb_world* w, uint32_t on) { w->use_async = on != 0; return 0; }
 int kjb_world_set_profiling(kjb_world* w, uint32_t on) { w->flush_timers(); w->profiling = on != 0; if (on) w->pass_ms.clear(); return 0; }
 const char* kjb_world_pass_timings(kjb_world* w) {
     w->flush_timers();
@@ -638,6 +644,23 @@ static void tile_exchange_frame(kjb_world* w) {
     w->pass_end();
     w->rows_all();
     w->exchanged_this_frame = true;
+}
+
+// Event slots of the async irradiance-cache chain; graph instances: 0..2 = the three recordings of an async frame, 3 = a whole frame.
+static const uint32_t EV_CACHE_USERS_DONE = 18, EV_CACHE_READY = 19, EV_FORK = 20, EV_JOIN = 21;
+static void graph_open_slot(kjb_world* w, uint32_t slot) {
+    if (w->use_graph && !w->profiling && !w->tiled && w->frame_idx >= 4 && w->stop_after.empty() && !w->err && kjb_graph_select(w->ctx, slot) == 0 && kjb_graph_begin(w->ctx) == 0) w->graph_open = true;
+}
+static void graph_close(kjb_world* w) { if (w->graph_open) { w->graph_open = false; if (kjb_graph_end(w->ctx)) w->err = 1; } }
+// Called after the last pass of the frame that reads or writes the irradiance cache: from here on the next frame's cache chain may run.  The event is
+// recorded between two recordings (an event inside a recording is not visible to other queues).
+static void cache_users_done(kjb_world* w) {
+    if (w->cache_users_done_marked || !w->async_frame) return;
+    w->cache_users_done_marked = true;
+    const bool reopen = w->graph_open;
+    graph_close(w);
+    if (kjb_event_record(w->ctx, EV_CACHE_USERS_DONE, KJB_QUEUE_COMPUTE)) w->err = 1;
+    if (reopen) graph_open_slot(w, 2);
 }
 
 // ---------------------------------------------------------------- RtdgiRenderer::render (rtdgi.rs:173-554)
@@ -922,6 +945,13 @@ static kjb_image* rtr_render(kjb_world* w, kjb_image& gbuffer, kjb_image& depth,
     kjb_image& refl1_tex = w->img("rtdgi.candidate_hit", HW, HH, KJB_FMT_RGBA16_FLOAT);
     kjb_image& refl2_tex = w->img("rtdgi.candidate_normal", HW, HH, KJB_FMT_RGBA8_SNORM);
     kjb_image *rng_output_tex, *rng_history_tex; w->get_output_and_history(w->rtr_temporal_rng_tex, HW, HH, KJB_FMT_R32_UINT, rng_output_tex, rng_history_tex);
+    // "reflection trace" and "reflection validate" share no image (new candidates + rng vs the history reservoirs + invalidity mask; both only read the GI and
+    // touch the racy cache): two latency-bound ray passes, the second a quarter of the first — with async compute they run side by side (fork here, join
+    // after the second; inside a graph recording the fork becomes two branches of the graph).
+    bool forked = false;
+    if (w->async_ok && !w->err && !w->stopped) {
+        if ((kjb_event_record(ctx, EV_FORK, KJB_QUEUE_COMPUTE) | kjb_queue_wait_event(ctx, KJB_QUEUE_ASYNC, EV_FORK)) == 0) forked = true; else w->err = 1;
+    }
     {
         kjb_rtr_trace_args a{}; a.gbuffer_tex = gbuffer; a.depth_tex = depth; a.rtdgi_tex = rtdgi_irradiance; a.sky_cube_tex = sky_cube; a.ircache = ircache;
         a.out0_tex = refl0_tex; a.out1_tex = refl1_tex; a.out2_tex = refl2_tex; a.rng_out_tex = *rng_output_tex; memcpy(a.gbuffer_tex_size, gbuffer_size, 16);
@@ -942,9 +972,12 @@ static kjb_image* rtr_render(kjb_world* w, kjb_image& gbuffer, kjb_image& depth,
         a.ircache = ircache; a.ray_orig_history_tex = *ray_orig_history_tex; a.ray_history_tex = *ray_history_tex; a.rng_history_tex = *rng_history_tex;
         a.irradiance_history_tex = *irradiance_history_tex; a.reservoir_history_tex = *reservoir_history_tex; memcpy(a.gbuffer_tex_size, gbuffer_size, 16);
         w->rows((th.r_validate + 1) & ~1u, 1);
+        if (forked && kjb_set_pass_queue(ctx, KJB_QUEUE_ASYNC)) w->err = 1;
         RUN("reflection validate", kjb_pass_rtr_validate(ctx, &a));
         RUN_TOP("reflection validate", kjb_pass_rtr_validate(ctx, &a), 4);   // pixel (0,0): empty reservoirs (payload 0) dereference it from anywhere
+        if (forked && (kjb_set_pass_queue(ctx, KJB_QUEUE_COMPUTE) | kjb_event_record(ctx, EV_JOIN, KJB_QUEUE_ASYNC) | kjb_queue_wait_event(ctx, KJB_QUEUE_COMPUTE, EV_JOIN))) w->err = 1;
     }
+    cache_users_done(w);   // the reflection filters and everything after them leave the irradiance cache alone
     {
         kjb_rtr_restir_temporal_args a{}; a.gbuffer_tex = gbuffer; a.half_view_normal_tex = half_view_normal_tex; a.depth_tex = depth; a.candidate0_tex = refl0_tex; a.candidate1_tex = refl1_tex;
         a.candidate2_tex = refl2_tex; a.irradiance_history_tex = *irradiance_history_tex; a.ray_orig_history_tex = *ray_orig_history_tex; a.ray_history_tex = *ray_history_tex;
@@ -1037,7 +1070,13 @@ static kjb_image* taa_render(kjb_world* w, kjb_image& input_tex, kjb_image& repr
 int kjb_world_render_frame(kjb_world* w, const kjb_world_frame* f) {
     kjb_context* ctx = w->ctx;
     kjb_frame_constants fc;
+    uint64_t tlas_before[2] = {0, 0}, tlas_after[2] = {0, 0};
+    kjb_tlas_stats(ctx, tlas_before);
     if (begin_frame(w, f, fc, true)) return 1;
+    kjb_tlas_stats(ctx, tlas_after);
+    // what the async cache chain reads besides the cache itself: the acceleration structure and the convolved sky.  A frame that rebuilt / refitted
+    // the one or recomputes the other on the compute queue keeps the chain on the compute queue too (program order).
+    bool frame_inputs_changed = tlas_before[0] != tlas_after[0] || tlas_before[1] != tlas_after[1];
     const uint32_t W = w->W, H = w->H;
 
     w->rows_all();
@@ -1048,6 +1087,7 @@ int kjb_world_render_frame(kjb_world* w, const kjb_world_frame* f) {
         { kjb_sky_cube_args a{sky_cube}; RUN("sky cube", kjb_pass_sky_cube(ctx, &a)); }
         { kjb_convolve_sky_args a{sky_cube, convolved_sky_cube, 16}; RUN("convolve sky", kjb_pass_convolve_sky(ctx, &a)); }
         w->sky_valid = true; memcpy(w->sky_sun, fc.sun_direction, 12);
+        frame_inputs_changed = true;
     }
 
     // G-buffer + depth + geometric normal + velocity (world_render_passes.rs:40-82)
@@ -1101,7 +1141,10 @@ int kjb_world_render_frame(kjb_world* w, const kjb_world_frame* f) {
     }
     // From here to the end of the pass list everything runs on the compute queue: record it and submit the frame as one CUDA graph launch
     // (the inputs above may have come through the upload queue; the result download below goes through the download queue).
-    if (w->use_graph && !w->profiling && !w->tiled && w->frame_idx >= 4 && w->stop_after.empty() && !w->err) { if (kjb_graph_begin(ctx) == 0) w->graph_open = true; }
+    w->cache_users_done_marked = false;
+    w->async_ok = w->use_async && !w->profiling && !w->tiled && w->frame_idx >= 4 && w->stop_after.empty() && !w->err && kjb_async_passes_supported(ctx) == 1;
+    w->async_frame = w->async_ok && w->desc.enable_ircache && !frame_inputs_changed;
+    graph_open_slot(w, w->async_frame ? 0 : 3);
     // reprojection map + copy depth (renderers/reprojection.rs:6-52)
     kjb_image& reprojection_map = w->img("reprojection_map", W, H, KJB_FMT_RGBA16_SNORM);
     kjb_image& prev_depth = w->img("reprojection.prev_depth", W, H, KJB_FMT_R32_FLOAT);
@@ -1118,7 +1161,11 @@ int kjb_world_render_frame(kjb_world* w, const kjb_world_frame* f) {
 
     // ircache.prepare + trace_irradiance (world_render_passes.rs:99-122): cache rays use the convolved sky cube
     IrcacheState ircache_state;
-    if (w->desc.enable_ircache) { ircache_state = ircache_prepare(w); ircache_trace_irradiance(w, ircache_state, convolved_sky_cube); }
+    if (w->desc.enable_ircache) {
+        if (w->async_frame && (kjb_queue_wait_event(ctx, KJB_QUEUE_ASYNC, EV_CACHE_USERS_DONE) | kjb_set_pass_queue(ctx, KJB_QUEUE_ASYNC))) w->err = 1;
+        ircache_state = ircache_prepare(w); ircache_trace_irradiance(w, ircache_state, convolved_sky_cube);
+        if (w->async_frame && kjb_set_pass_queue(ctx, KJB_QUEUE_COMPUTE)) w->err = 1;
+    }
 
     // rtdgi.reproject (world_render_passes.rs:129, rtdgi.rs:143-171)
     kjb_image *temporal_output_tex, *history_tex; w->get_output_and_history(w->temporal2_tex, W, H, KJB_FMT_RGBA16_FLOAT, temporal_output_tex, history_tex);
@@ -1129,7 +1176,18 @@ int kjb_world_render_frame(kjb_world* w, const kjb_world_frame* f) {
         if (w->exchange_pending) { if (kjb_queue_wait_event(ctx, KJB_QUEUE_COMPUTE, EV_XCHG_DONE)) w->err = 1; w->exchange_pending = false; }   // first consumer of exchanged history
         RUN("rtdgi reproject", kjb_pass_rtdgi_reproject(ctx, &a));
     }
-    if (w->desc.enable_ircache) ircache_sum_up_irradiance(w, ircache_state);   // world_render_passes.rs:138-140
+    if (w->desc.enable_ircache) {   // world_render_passes.rs:138-140
+        if (w->async_frame && kjb_set_pass_queue(ctx, KJB_QUEUE_ASYNC)) w->err = 1;
+        ircache_sum_up_irradiance(w, ircache_state);
+        if (w->async_frame) {
+            if (kjb_event_record(ctx, EV_CACHE_READY, KJB_QUEUE_ASYNC) | kjb_set_pass_queue(ctx, KJB_QUEUE_COMPUTE)) w->err = 1;
+            // the cache's first user this frame ("rtdgi validate") waits for the chain: the wait sits between two recordings
+            const bool reopen = w->graph_open;
+            graph_close(w);
+            if (kjb_queue_wait_event(ctx, KJB_QUEUE_COMPUTE, EV_CACHE_READY)) w->err = 1;
+            if (reopen) graph_open_slot(w, 1);
+        }
+    }
     // rtdgi.render (world_render_passes.rs:146-160): diffuse rays use the convolved sky cube
     rtdgi_render(w, reprojected_history_tex, *temporal_output_tex, gbuffer, depth, geometric_normal, reprojection_map, convolved_sky_cube, ssao_tex, ircache_state.bindings());
 
@@ -1138,6 +1196,7 @@ int kjb_world_render_frame(kjb_world* w, const kjb_world_frame* f) {
         kjb_image gi{};
         if (kjb_world_get_image(w, "rtdgi.spatial_filtered", &gi) == 0) rtr_render(w, gbuffer, depth, geometric_normal, reprojection_map, sky_cube, gi, ircache_state.bindings());
     }
+    cache_users_done(w);   // without reflections the diffuse GI passes were the last users
 
     // light_gbuffer + taa.render (world_render_passes.rs:215-263)
     const char* result_name = "rtdgi.spatial_filtered";
@@ -1184,7 +1243,8 @@ int kjb_world_render_frame(kjb_world* w, const kjb_world_frame* f) {
         kjb_image taa_in{};
         if (kjb_world_get_image(w, result_name, &taa_in) == 0) { taa_render(w, taa_in, reprojection_map, depth); result_name = "taa.this_frame_out"; }
     }
-    if (w->graph_open) { w->graph_open = false; if (kjb_graph_end(ctx)) w->err = 1; }
+    graph_close(w);
+    if (!w->async_frame && w->desc.enable_ircache && !w->tiled && kjb_event_record(ctx, EV_CACHE_USERS_DONE, KJB_QUEUE_COMPUTE)) w->err = 1;   // a later async frame orders its chain after this frame
     if (w->tiled && !w->exchanged_this_frame) tile_exchange_frame(w);   // with TAA its history images travel too: exchange at the end of the frame
     if (streaming && !w->err) {
         kjb_image result{};

@@ -165,7 +165,8 @@ int kjb_create(int device, kjb_context** out) {
     kjb_context* c = new kjb_context();
     c->device = device;
 #if !defined(KJB_EMU)
-    if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; g_create_error = "kjb_create: stream creation failed"; return 1; }
+    if (cudaStreamCreateWithFlags(&c->compute_stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; g_create_error = "kjb_create: stream creation failed"; return 1; }
+    c->stream = c->compute_stream;
 #endif
     memset(&c->g, 0, sizeof(c->g));
     c->d_ray_counters = (unsigned long long*)dev_alloc(2 * sizeof(unsigned long long));
@@ -182,10 +183,10 @@ void kjb_destroy(kjb_context* c) {
     dev_free(c->d_tex_data); dev_free(c->d_tex_desc); dev_free(c->d_lights); dev_free(c->d_ray_counters); dev_free(c->d_prev_instances); dev_free(c->d_resolve_offsets);
 #if !defined(KJB_EMU)
     if (c->pinned_staging) cudaFreeHost(c->pinned_staging);
-    if (c->graph_exec) cudaGraphExecDestroy(c->graph_exec);
+    for (auto& ge : c->graph_execs) if (ge) cudaGraphExecDestroy(ge);
     for (auto& ev : c->queue_events) if (ev) cudaEventDestroy(ev);
     for (auto& st : c->copy_streams) if (st) cudaStreamDestroy(st);
-    if (c->stream) cudaStreamDestroy(c->stream);
+    if (c->compute_stream) cudaStreamDestroy(c->compute_stream);
 #endif
     delete c;
 }
@@ -196,7 +197,11 @@ int kjb_sync(kjb_context* c) {
 }
 const char* kjb_last_error(kjb_context* c) { return c ? c->last_error.c_str() : g_create_error.c_str(); }
 uint64_t kjb_launch_count(kjb_context* c) { return c->launches; }
+#if defined(KJB_EMU)
 void* kjb_stream(kjb_context* c) { return (void*)c->stream; }
+#else
+void* kjb_stream(kjb_context* c) { return (void*)c->compute_stream; }
+#endif
 uint32_t kjb_format_texel_bytes(uint32_t f) { return texel_bytes(f); }
 
 int kjb_image_alloc(kjb_context* c, uint32_t w, uint32_t h, uint32_t layers, uint32_t fmt, kjb_image* out) {
@@ -383,33 +388,51 @@ int kjb_rebuild_tlas(kjb_context* c, const kjb_instance* inst, uint32_t n) {
 #if defined(KJB_EMU)
 int kjb_graph_begin(kjb_context*) { return 0; }
 int kjb_graph_end(kjb_context*) { return 0; }
+int kjb_graph_select(kjb_context*, uint32_t slot) { return slot < 4 ? 0 : 1; }
+int kjb_set_pass_queue(kjb_context* c, uint32_t q) { return q == KJB_QUEUE_COMPUTE ? 0 : c->fail("kjb_set_pass_queue: this backend has one pass queue"); }
+int kjb_async_passes_supported(kjb_context*) { return 0; }
 #else
+// The recording always happens on the compute queue; passes enqueued on the async queue meanwhile (kjb_set_pass_queue) are launched, not recorded
+// (relaxed capture mode: other streams of the thread stay usable).
 int kjb_graph_begin(kjb_context* c) {
     if (c->graph_capturing) return c->fail("kjb_graph_begin: already recording");
-    if (cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeRelaxed) != cudaSuccess) { cudaGetLastError(); return c->fail("kjb_graph_begin: cudaStreamBeginCapture failed"); }
+    if (cudaStreamBeginCapture(c->compute_stream, cudaStreamCaptureModeRelaxed) != cudaSuccess) { cudaGetLastError(); return c->fail("kjb_graph_begin: cudaStreamBeginCapture failed"); }
     c->graph_capturing = true;
     return 0;
 }
 int kjb_graph_end(kjb_context* c) {
     if (!c->graph_capturing) return c->fail("kjb_graph_end: not recording");
     cudaGraph_t g = nullptr;
-    const cudaError_t e = cudaStreamEndCapture(c->stream, &g);
+    const cudaError_t e = cudaStreamEndCapture(c->compute_stream, &g);
     c->graph_capturing = false;
     if (e != cudaSuccess || !g) { cudaGetLastError(); return c->fail(std::string("kjb_graph_end: the recording was invalidated (") + cudaGetErrorString(e) + "): a pass inside the pair synchronised or touched another queue"); }
-    if (c->graph_exec) {
+    cudaGraphExec_t& exec = c->graph_execs[c->graph_slot];
+    if (exec) {
         cudaGraphExecUpdateResultInfo info;
-        if (cudaGraphExecUpdate(c->graph_exec, g, &info) != cudaSuccess) { cudaGetLastError(); cudaGraphExecDestroy(c->graph_exec); c->graph_exec = nullptr; }   // other pass list: new instance
+        if (cudaGraphExecUpdate(exec, g, &info) != cudaSuccess) { cudaGetLastError(); cudaGraphExecDestroy(exec); exec = nullptr; }   // other pass list: new instance
     }
-    if (!c->graph_exec) {
-        if (cudaGraphInstantiate(&c->graph_exec, g, 0) != cudaSuccess) { cudaGetLastError(); cudaGraphDestroy(g); c->graph_exec = nullptr; return c->fail("kjb_graph_end: cudaGraphInstantiate failed"); }
+    if (!exec) {
+        if (cudaGraphInstantiate(&exec, g, 0) != cudaSuccess) { cudaGetLastError(); cudaGraphDestroy(g); exec = nullptr; return c->fail("kjb_graph_end: cudaGraphInstantiate failed"); }
         c->graph_instantiations++;
     }
-    const cudaError_t le = cudaGraphLaunch(c->graph_exec, c->stream);
+    const cudaError_t le = cudaGraphLaunch(exec, c->compute_stream);
     cudaGraphDestroy(g);
     if (le != cudaSuccess) return c->fail(std::string("kjb_graph_end: cudaGraphLaunch failed: ") + cudaGetErrorString(le));
     c->graph_launches++;
     return 0;
 }
+int kjb_graph_select(kjb_context* c, uint32_t slot) {
+    if (slot >= 4) return c->fail("kjb_graph_select: 4 instances are kept");
+    if (c->graph_capturing) return c->fail("kjb_graph_select: a recording is open");
+    c->graph_slot = slot; return 0;
+}
+int kjb_set_pass_queue(kjb_context* c, uint32_t q) {
+    if (q != KJB_QUEUE_COMPUTE && q != KJB_QUEUE_ASYNC) return c->fail("kjb_set_pass_queue: passes run on the compute or the async queue");
+    if (q == KJB_QUEUE_ASYNC && c->debug_serial) return c->fail("kjb_set_pass_queue: serialised debugging keeps every pass on the compute queue");
+    cudaStream_t st = c->queue(q); if (!st) return c->fail("kjb_set_pass_queue: queue creation failed");
+    c->stream = st; return 0;
+}
+int kjb_async_passes_supported(kjb_context* c) { return c->debug_serial ? 0 : 1; }
 #endif
 int kjb_graph_stats(kjb_context* c, uint64_t out[2]) { out[0] = c->graph_launches; out[1] = c->graph_instantiations; return 0; }
 int kjb_tlas_stats(kjb_context* c, uint64_t out[2]) { out[0] = c->tlas_rebuilds; out[1] = c->tlas_refits; return 0; }
@@ -451,7 +474,7 @@ int kjb_timer_record(kjb_context* c, uint32_t slot) {
     if (slot >= 1024) return c->fail("kjb_timer_record: slot out of range");
     if (c->timer_events.size() <= slot) c->timer_events.resize(slot + 1, nullptr);
     if (!c->timer_events[slot] && cudaEventCreate(&c->timer_events[slot]) != cudaSuccess) return c->fail("kjb_timer_record: cudaEventCreate failed");
-    return cudaEventRecord(c->timer_events[slot], c->stream) != cudaSuccess;
+    return cudaEventRecord(c->timer_events[slot], c->compute_stream) != cudaSuccess;
 }
 int kjb_timer_elapsed_ms(kjb_context* c, uint32_t a, uint32_t b, float* out) {
     if (a >= c->timer_events.size() || b >= c->timer_events.size() || !c->timer_events[a] || !c->timer_events[b]) return c->fail("kjb_timer_elapsed_ms: slot was never recorded");

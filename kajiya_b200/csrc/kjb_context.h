@@ -44,19 +44,23 @@ struct kjb_context {
     int32_t* d_resolve_offsets = nullptr; std::vector<int32_t> h_resolve_offsets;   // SPATIAL_RESOLVE_OFFSETS as last pushed by the host
 #if !defined(KJB_EMU)
     std::vector<cudaEvent_t> timer_events;
-    cudaStream_t copy_streams[3] = {nullptr, nullptr, nullptr};   // KJB_QUEUE_UPLOAD, _DOWNLOAD, _COMM (created on first use)
+    cudaStream_t copy_streams[4] = {nullptr, nullptr, nullptr, nullptr};   // KJB_QUEUE_UPLOAD, _DOWNLOAD, _COMM, _ASYNC (created on first use)
+    cudaStream_t compute_stream = nullptr;                    // KJB_QUEUE_COMPUTE; `stream` is the queue passes are enqueued on right now (kjb_set_pass_queue)
     cudaEvent_t queue_events[64] = {};                        // kjb_event_record slots
     cudaStream_t queue(uint32_t q) {
-        if (q == 0) return stream;
-        if (q > 3) return nullptr;
-        if (!copy_streams[q - 1] && cudaStreamCreateWithFlags(&copy_streams[q - 1], cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+        if (q == 0) return compute_stream;
+        if (q > 4) return nullptr;
+        if (!copy_streams[q - 1]) {
+            int lo = 0, hi = 0; cudaDeviceGetStreamPriorityRange(&lo, &hi);   // the async pass queue carries little, latency-bound work: let its blocks in first
+            if (cudaStreamCreateWithPriority(&copy_streams[q - 1], cudaStreamNonBlocking, q == 4 ? hi : lo) != cudaSuccess) return nullptr;
+        }
         return copy_streams[q - 1];
     }
 #endif
 
 #if !defined(KJB_EMU)
     // CUDA Graph replay of a frame (kjb_graph_begin / kjb_graph_end): the instance kept between frames, updated in place while the topology holds
-    cudaGraphExec_t graph_exec = nullptr; bool graph_capturing = false;
+    cudaGraphExec_t graph_execs[4] = {nullptr, nullptr, nullptr, nullptr}; uint32_t graph_slot = 0; bool graph_capturing = false;   // kjb_graph_select
 #endif
     uint64_t graph_launches = 0, graph_instantiations = 0;
     kjb::Globals g;   // host copy, passed by value to every kernel
@@ -114,7 +118,7 @@ inline int dev_d2h(kjb_context* c, void* h, const void* d, size_t n) { return cu
 inline int dev_d2d(kjb_context* c, void* d, const void* s, size_t n) { return cudaMemcpyAsync(d, s, n, cudaMemcpyDeviceToDevice, c->stream) != cudaSuccess; }
 inline int dev_memset(kjb_context* c, void* d, int v, size_t n) { return cudaMemsetAsync(d, v, n, c->stream) != cudaSuccess; }
 inline int dev_sync(kjb_context* c) {   // every queue of the context
-    int rc = cudaStreamSynchronize(c->stream) != cudaSuccess;
+    int rc = cudaStreamSynchronize(c->compute_stream) != cudaSuccess;
     for (cudaStream_t st : c->copy_streams) if (st) rc |= cudaStreamSynchronize(st) != cudaSuccess;
     return rc;
 }

@@ -247,13 +247,23 @@ KJB_KERNEL(256) k_taa_prob_filter(Img input_tex, ImgW output_tex, Rows kjb_rows)
     for (int yy = -1; yy <= 1; ++yy) for (int xx = -1; xx <= 1; ++xx) prob = kjb_max(prob, ld_r16f(input_tex, x + xx, y + yy));
     st_raw<uint16_t>(output_tex, x, y, uint16_t(kjb_f32_to_f16(prob)));
 }
+// exponential_squish of a probability is a function of the texel alone, and each texel is a tap of 25 pixels: the block squishes its
+// (32 + 8) x (8 + 8) footprint once into shared memory (640 exp2 instead of 6400) and every pixel sums its 25 taps in the reference's order.
 KJB_KERNEL(256) k_taa_prob_filter2(Img input_tex, ImgW output_tex, Rows kjb_rows) {
-    KJB_PX; if (x >= output_tex.w || y >= output_tex.h) return;
-    float2 weighted_prob = f2(0.0f);
-    for (int yy = -2; yy <= 2; ++yy) for (int xx = -2; xx <= 2; ++xx) {
-        const float neighbor_prob = ld_r16f(input_tex, x + xx * 2, y + yy * 2);
-        weighted_prob += f2(kjb_exp2(-kjb_clamp(10.0f * neighbor_prob, 0.0f, 100.0f)), 1);     // exponential_squish
+    constexpr int TW = 32 + 8, TH = 8 + 8;
+    __shared__ float s_sq[TW * TH];
+    const int tid = int(threadIdx.y) * 32 + int(threadIdx.x);
+    const int bx0 = int(blockIdx.x) * 32 - 4, by0 = kjb_rows.y0 + int(blockIdx.y) * 8 - 4;
+    for (int i = tid; i < TW * TH; i += 256) {
+        const float neighbor_prob = ld_r16f(input_tex, bx0 + i % TW, by0 + i / TW);
+        s_sq[i] = kjb_exp2(-kjb_clamp(10.0f * neighbor_prob, 0.0f, 100.0f));     // exponential_squish
     }
+    __syncthreads();
+    const int x = int(blockIdx.x) * 32 + int(threadIdx.x), y = kjb_rows.y0 + int(blockIdx.y) * 8 + int(threadIdx.y);
+    if (x >= output_tex.w || y >= output_tex.h || y >= kjb_rows.y1) return;
+    float2 weighted_prob = f2(0.0f);
+    for (int yy = -2; yy <= 2; ++yy) for (int xx = -2; xx <= 2; ++xx)
+        weighted_prob += f2(s_sq[(int(threadIdx.y) + 4 + yy * 2) * TW + int(threadIdx.x) + 4 + xx * 2], 1);
     const float prob = kjb_max(0.0f, -1.0f / 10.0f * kjb_log2(1e-30f + weighted_prob.x / weighted_prob.y));   // exponential_unsquish
     st_raw<uint16_t>(output_tex, x, y, uint16_t(kjb_f32_to_f16(prob)));
 }
@@ -481,7 +491,7 @@ int kjb_pass_taa_prob_filter2(kjb_context* c, const kjb_taa_prob_filter_args* a)
     const char* P = "taa prob filter2"; const uint32_t W = a->output_tex.width, H = a->output_tex.height;
     CHK(a->output_tex, KJB_FMT_R16_FLOAT, "output_tex"); CHKE(a->input_tex, KJB_FMT_R16_FLOAT, "input_tex", W, H);
     KJB_ROWS(c, H);
-    KJB_LAUNCH(c, k_taa_prob_filter2, KJB_GRID2D(W, H, 32, 8), img_ro(a->input_tex), img_rw(a->output_tex));
+    KJB_LAUNCH_SYNC(c, k_taa_prob_filter2, KJB_GRID2D(W, H, 32, 8), img_ro(a->input_tex), img_rw(a->output_tex));
     KJB_PASS_EPILOGUE(c, P);
 }
 int kjb_pass_taa(kjb_context* c, const kjb_taa_args* a) {

@@ -205,6 +205,10 @@ class World:
         """one CUDA graph launch per frame instead of ~40 kernel launches (default on; applies from the fifth frame)"""
         self._check(self.d.kjb_world_set_cuda_graph(self.w, int(on)))
 
+    def set_async_compute(self, on):
+        """irradiance-cache chain on the async pass queue, under the previous frame's reflection filters + TAA (default on; CUDA backend)"""
+        self._check(self.d.kjb_world_set_async_compute(self.w, int(on)))
+
     def graph_stats(self):
         s = (C.c_uint64 * 2)()
         self._check(self.d.kjb_graph_stats(self.ctx, C.byref(s)))

@@ -77,6 +77,9 @@ int kjb_memcpy_d2d_batch(kjb_context*, const kjb_copy_desc* c, uint32_t n) { for
 int kjb_set_scissor(kjb_context* c, uint32_t y0, uint32_t y1) { c->scissor_y0 = y0; c->scissor_y1 = y1; return 0; }
 int kjb_graph_begin(kjb_context*) { return 0; }
 int kjb_graph_end(kjb_context*) { return 0; }
+int kjb_graph_select(kjb_context*, uint32_t) { return 0; }
+int kjb_set_pass_queue(kjb_context*, uint32_t q) { return q == 0 ? 0 : 1; }
+int kjb_async_passes_supported(kjb_context*) { return 0; }
 int kjb_graph_stats(kjb_context*, uint64_t out[2]) { out[0] = out[1] = 0; return 0; }
 int kjb_tlas_stats(kjb_context*, uint64_t out[2]) { out[0] = out[1] = 0; return 0; }   // the oracle rebuilds its median-split BVH whenever a transform changes
 int kjb_set_debug_serial(kjb_context* c, uint32_t on) { c->cache_passes_parallel = on == 0; return 0; }   // default (never called): serial

@@ -55,6 +55,9 @@ int kjb_scene_set_textures(kjb_context*, const kjb_texture_desc*, uint32_t) { re
 int kjb_rebuild_tlas(kjb_context*, const kjb_instance* inst, uint32_t n) { rec("kjb_rebuild_tlas", inst, n * sizeof(kjb_instance)); return 0; }
 int kjb_graph_begin(kjb_context*) { return 0; }
 int kjb_graph_end(kjb_context*) { return 0; }
+int kjb_graph_select(kjb_context*, uint32_t) { return 0; }
+int kjb_set_pass_queue(kjb_context*, uint32_t q) { return q == 0 ? 0 : 1; }
+int kjb_async_passes_supported(kjb_context*) { return 0; }
 int kjb_graph_stats(kjb_context*, uint64_t out[2]) { out[0] = out[1] = 0; return 0; }
 int kjb_tlas_stats(kjb_context*, uint64_t out[2]) { out[0] = out[1] = 0; return 0; }
 int kjb_set_frame_constants(kjb_context*, const kjb_frame_constants* fc, const kjb_triangle_light*, uint32_t) { rec("kjb_set_frame_constants", fc, sizeof(*fc)); return 0; }

@@ -8,7 +8,11 @@ agg = collections.Counter(); samples = collections.Counter(); text = {}; opc = c
 for r in rows:
     if not r: continue
     if r[0] == "File Path": cur_file = r[1]; continue
-    if r[0] == "Line No": hdr = {h: i for i, h in enumerate(r)}; continue
+    if r[0] == "Line No":
+        hdr = {h: i for i, h in enumerate(r)}
+        samp = next((i for i, h in enumerate(r) if h == "# Samples"), None)
+        if samp is None: samp = next((i for i, h in enumerate(r) if "Sampling" in h and "All" in h), None)   # column name differs between ncu versions
+        continue
     if r[0] == "Function Name" or hdr is None: continue
     try:
         line = int(r[0])
@@ -17,7 +21,7 @@ for r in rows:
     try:   # source text with quotes / commas (inline asm) can shift the columns of a row: skip what does not parse
         ie = r[hdr["Instructions Executed"]]
         if not ie: continue
-        n_ie, n_s = int(float(ie)), int(float(r[hdr["# Samples"]] or 0))
+        n_ie, n_s = int(float(ie)), (int(float(r[samp] or 0)) if samp is not None else 0)
     except (ValueError, IndexError):
         continue
     key = ((cur_file or "?").split("/")[-1], line)
