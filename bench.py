@@ -235,6 +235,7 @@ def measure_frames(lib, torch, dist, workload, K, Wm, rank, world_size, local_ra
     barrier()
     st = w.stats()
     rays = st["closest_rays"] + st["any_hit_rays"]
+    closest_share = st["closest_rays"] / max(rays, 1)
     launches = lib.dll.kjb_launch_count(w.ctx) - launches0
 
     # ---- per-pass timing (CUDA events around every pass, same K frames)
@@ -279,7 +280,7 @@ def measure_frames(lib, torch, dist, workload, K, Wm, rank, world_size, local_ra
         pm = torch.tensor([per_pass[k] for k in labels], device="cuda", dtype=torch.float64); dist.all_reduce(pm, op=dist.ReduceOp.MAX)
         per_pass = dict(zip(labels, pm.tolist()))   # slowest rank per pass
     return dict(workload=workload, W=W, H=H, F=F, Hh=Hh, O=O, K=K, ms_total=ms_total, ms_e2e=ms_e2e, rays=rays, rays_e2e=rays_e2e, rays_traced=rays_traced, launches=launches,
-                per_pass=per_pass, calls=calls, h2d=h2d, d2h=res_bytes, nslots=nslots, windows=windows, view=view, streaming=streaming)
+                per_pass=per_pass, calls=calls, h2d=h2d, d2h=res_bytes, closest_share=closest_share, nslots=nslots, windows=windows, view=view, streaming=streaming)
 
 
 def frame_rays_untiled(lib, workload, K, Wm, local_rank, nslots):
@@ -365,6 +366,8 @@ def summarize(m, world_size, peak, ncu_table):
         ach = tab["warp_inst"] / (per_pass[dom] * 1e-3) / 1e9
         roof["issue_slots"] = {"warp_inst_per_launch": tab["warp_inst"], "achieved_ginst_s": ach, "peak_ginst_s": 148 * 4 * sm_mhz * 1e-3, "frac": ach / (148 * 4 * sm_mhz * 1e-3), "source": tab.get("source")}
     return {"ms_per_step": frame_ms, "value": m["rays"] / (m["ms_total"] * 1e-3), "unit": "rays/s", "rays_per_frame": m["rays"] / K,
+            "ray_kinds": {"closest_hit_per_frame": m["rays"] / K * m.get("closest_share", 0.0), "any_hit_per_frame": m["rays"] / K * (1.0 - m.get("closest_share", 0.0)),
+                          "note": "closest-hit rays carry shading (material fetch, sun shadow ray, cache lookup); any-hit rays are visibility only"},
             "e2e": {"value": m["rays_e2e"] / (m["ms_e2e"] * 1e-3), "unit": "rays/s", "ms_per_step": m["ms_e2e"] / K, "h2d_bytes_per_step": int(m["h2d"]), "d2h_bytes_per_step": int(m["d2h"]),
                     "mode": "streaming: upload/compute/download queues, 2 frames in flight" if m["streaming"] else "blocking call per frame"},
             "gpu_launches": int(m["launches"]), "roofline": roof,
@@ -445,8 +448,8 @@ def run_cuda(args):
     headline = args.workload
     if args.configs == "all":
         names = [headline] + [c for c in CONFIG_SET if c != headline]
-    elif args.configs == "auto":   # N = 1: every BASELINE configuration; N > 1: the headline and configs[1]
-        names = [headline] + ([c for c in CONFIG_SET if c != headline] if world_size == 1 else [c for c in ("cornell_1080p_rtdgi_1s1t",) if c != headline])
+    elif args.configs == "auto":   # N = 1: every BASELINE configuration; N > 1: all frame configurations (configs[0], the 256x256 path tracer, does not shard)
+        names = [headline] + [c for c in CONFIG_SET if c != headline and (world_size == 1 or c != "cornell_256_reference_pt")]
     else:
         names = [headline]
     clocks = ClockSampler(local_rank); clocks.start()

@@ -128,7 +128,7 @@ int  kjb_world_set_profiling(kjb_world *w, uint32_t on);
 int  kjb_world_set_cuda_graph(kjb_world *w, uint32_t on);
 /* Async compute (kjb_set_pass_queue, kjb.h): the irradiance-cache chain of a frame — cascade scroll, ageing, compaction, cache rays, sum — is ~10 small,
  * latency-bound launches that need nothing of the frame's screen-space inputs, only that the PREVIOUS frame's cache users ("rtdgi validate/trace",
- * "reflection trace/validate") are done.  With this on (default; CUDA backend, from the fifth frame, not while profiling / tile-sharded / serialised, not in a
+ * "reflection trace/validate") are done.  With this on (default; CUDA backend, from the fifth frame, not while profiling / serialised, not in a
  * frame that rebuilt the acceleration structure or the sky) the chain is enqueued on the async queue: it runs under the previous frame's reflection
  * filters and TAA and under this frame's reprojection passes, and the frame is submitted as three recordings around the two ordering points.  The pass
  * call order (the reference's render-graph order) does not change.  KJB_NO_ASYNC=1 switches the default off (A/B timing). */

@@ -1142,7 +1142,7 @@ int kjb_world_render_frame(kjb_world* w, const kjb_world_frame* f) {
     // From here to the end of the pass list everything runs on the compute queue: record it and submit the frame as one CUDA graph launch
     // (the inputs above may have come through the upload queue; the result download below goes through the download queue).
     w->cache_users_done_marked = false;
-    w->async_ok = w->use_async && !w->profiling && !w->tiled && w->frame_idx >= 4 && w->stop_after.empty() && !w->err && kjb_async_passes_supported(ctx) == 1;
+    w->async_ok = w->use_async && !w->profiling && w->frame_idx >= 4 && w->stop_after.empty() && !w->err && kjb_async_passes_supported(ctx) == 1;   // tile-sharded frames too (direct launches)
     w->async_frame = w->async_ok && w->desc.enable_ircache && !frame_inputs_changed;
     graph_open_slot(w, w->async_frame ? 0 : 3);
     // reprojection map + copy depth (renderers/reprojection.rs:6-52)
@@ -1244,7 +1244,7 @@ int kjb_world_render_frame(kjb_world* w, const kjb_world_frame* f) {
         if (kjb_world_get_image(w, result_name, &taa_in) == 0) { taa_render(w, taa_in, reprojection_map, depth); result_name = "taa.this_frame_out"; }
     }
     graph_close(w);
-    if (!w->async_frame && w->desc.enable_ircache && !w->tiled && kjb_event_record(ctx, EV_CACHE_USERS_DONE, KJB_QUEUE_COMPUTE)) w->err = 1;   // a later async frame orders its chain after this frame
+    if (!w->async_frame && w->desc.enable_ircache && kjb_event_record(ctx, EV_CACHE_USERS_DONE, KJB_QUEUE_COMPUTE)) w->err = 1;   // a later async frame orders its chain after this frame
     if (w->tiled && !w->exchanged_this_frame) tile_exchange_frame(w);   // with TAA its history images travel too: exchange at the end of the frame
     if (streaming && !w->err) {
         kjb_image result{};

@@ -180,7 +180,10 @@ KJB_DEV void rtdgi_validate_px(const Globals& g, const Img& half_view_normal_tex
     }
     st_r8u(out_tex, x, y, invalidity);
 }
-KJB_KERNEL(128) k_rtdgi_validate(const __grid_constant__ Globals g, Img half_view_normal_tex, Img depth_tex, Img reprojected_gi_tex, ImgW reservoir_tex, Img reservoir_ray_history_tex,
+#ifndef KJB_OCC_VALIDATE
+#define KJB_OCC_VALIDATE 8   /* 72 -> 64 registers: 147 -> 137 us at 1080p (profiles/r02n_variants.txt) */
+#endif
+KJB_KERNEL_OCC(128, KJB_OCC_VALIDATE) k_rtdgi_validate(const __grid_constant__ Globals g, Img half_view_normal_tex, Img depth_tex, Img reprojected_gi_tex, ImgW reservoir_tex, Img reservoir_ray_history_tex,
                                  Img sky_cube_tex, ImgW irradiance_history_tex, Img ray_orig_history_tex, ImgW out_tex, float4 gts, IrcacheBufs ircache, Rows kjb_rows) {
     KJB_PX; if (x >= out_tex.w || y >= out_tex.h) return;
     rtdgi_validate_px(g, half_view_normal_tex, depth_tex, reprojected_gi_tex, reservoir_tex, reservoir_ray_history_tex, sky_cube_tex, irradiance_history_tex, ray_orig_history_tex, out_tex, gts, ircache, x, y);

@@ -166,7 +166,10 @@ KJB_DEV void rtr_trace_px(const Globals& g, const RtrTraceImgs& t, const BlueNoi
         st_rgba16f(t.out1_tex, x, y, f4(0.0f));
     }
 }
-KJB_KERNEL(128) k_rtr_trace(const __grid_constant__ Globals g, RtrTraceImgs t, BlueNoiseSamplerTables bn, float4 gts, uint32_t reuse_rtdgi_rays, IrcacheBufs ircache, Rows kjb_rows) {
+#ifndef KJB_OCC_RTR_TRACE
+#define KJB_OCC_RTR_TRACE 8   /* 80 -> 64 registers: 296 -> 276 us at 1080p (profiles/r02n_variants.txt) */
+#endif
+KJB_KERNEL_OCC(128, KJB_OCC_RTR_TRACE) k_rtr_trace(const __grid_constant__ Globals g, RtrTraceImgs t, BlueNoiseSamplerTables bn, float4 gts, uint32_t reuse_rtdgi_rays, IrcacheBufs ircache, Rows kjb_rows) {
     KJB_PX; if (x >= t.out0_tex.w || y >= t.out0_tex.h) return;
     rtr_trace_px(g, t, bn, gts, reuse_rtdgi_rays, ircache, x, y);
 }
@@ -221,7 +224,10 @@ KJB_DEV void rtr_validate_quad(const Globals& g, const RtrValidateImgs& t, float
         }
     }
 }
-KJB_KERNEL(128) k_rtr_validate(const __grid_constant__ Globals g, RtrValidateImgs t, float4 gts, IrcacheBufs ircache, int QW, int QH, Rows kjb_rows) {
+#ifndef KJB_OCC_RTR_VALIDATE
+#define KJB_OCC_RTR_VALIDATE 8   /* 183 -> 163 us */
+#endif
+KJB_KERNEL_OCC(128, KJB_OCC_RTR_VALIDATE) k_rtr_validate(const __grid_constant__ Globals g, RtrValidateImgs t, float4 gts, IrcacheBufs ircache, int QW, int QH, Rows kjb_rows) {
     KJB_PX; if (x >= QW || y >= QH) return;
     rtr_validate_quad(g, t, gts, ircache, x, y);
 }
@@ -264,7 +270,7 @@ KJB_DEV void find_best_reprojection_in_neighborhood(const Globals& g, const RtrR
     }
 }
 #ifndef KJB_OCC_RTR_RESTIR_TEMPORAL
-#define KJB_OCC_RTR_RESTIR_TEMPORAL 1
+#define KJB_OCC_RTR_RESTIR_TEMPORAL 4   /* 107 -> 64 registers: 95 (1 block) -> 81 (3) -> 77 us (4) at 1080p (profiles/r02m_variants.txt, r02n_variants.txt) */
 #endif
 KJB_KERNEL_OCC(256, KJB_OCC_RTR_RESTIR_TEMPORAL) k_rtr_restir_temporal(const __grid_constant__ Globals g, RtrRestirTemporalImgs t, float4 gts, Rows kjb_rows) {
     KJB_PX; if (x >= t.irradiance_out_tex.w || y >= t.irradiance_out_tex.h) return;
