@@ -382,6 +382,23 @@ int kjb_pass_ircache_validate(kjb_context *ctx, const kjb_ircache_trace_args *a)
 int kjb_pass_ircache_trace(kjb_context *ctx, const kjb_ircache_trace_args *a);
 typedef struct kjb_ircache_sum_args { kjb_buffer life_buf, meta_buf, irradiance_buf, aux_buf, entry_indirection_buf; } kjb_ircache_sum_args;   /* "ircache sum" */
 int kjb_pass_ircache_sum(kjb_context *ctx, const kjb_ircache_sum_args *a);
+/* Multi-GPU (tile-sharded frames): the irradiance cache is ONE global structure fed by every ray of the frame; a rank only traces the rays of
+ * its band.  Every rank keeps a replica and, after the frame's last cache user, the ranks exchange what their rays asked of the cache: one 32-byte record per
+ * live entry — (cell, life, this frame's vote count, the vote that won locally).  Merging a record keeps the cell alive (life = min), allocates it where the
+ * local rays never went, and draws the surviving reposition vote with probability count_remote / (count_local + count_remote), i.e. the uniform vote over
+ * the union of all ranks' rays (lookup.hlsl:268-309, IRCACHE_USE_UNIFORM_VOTING).  After the merge every replica holds the same set of live cells with the
+ * positions the whole frame voted for, which is what the single-GPU cache holds.  Not a reference pass (kajiya is single-GPU). */
+#define KJB_IRCACHE_SHARE_RECORD_BYTES 32u
+#define KJB_IRCACHE_SHARE_BLOCK_BYTES(max_records) (16u + (max_records) * KJB_IRCACHE_SHARE_RECORD_BYTES)   /* header {count, 0, 0, 0} + records */
+typedef struct kjb_ircache_share_args {
+    kjb_ircache_bindings ircache;
+    kjb_buffer block;            /* export: this rank's block (written).  merge: ONE other rank's block (read) */
+    uint32_t max_records;        /* records beyond this stay local (the cache then degrades towards independent replicas) */
+    uint32_t seed;               /* merge: frame index * rank count + source rank — decorrelates the vote draws */
+} kjb_ircache_share_args;
+int kjb_pass_ircache_export_requests(kjb_context *ctx, const kjb_ircache_share_args *a);
+int kjb_pass_ircache_merge_requests(kjb_context *ctx, const kjb_ircache_share_args *a);
+
 
 /* ------------------------------------------------------------------ rtdgi (renderers/rtdgi.rs) */
 typedef struct kjb_rtdgi_reproject_args {            /* "rtdgi reproject", fullres_reproject.hlsl:10-15, rtdgi.rs:156-164 */

@@ -138,7 +138,8 @@ struct kjb_world {
     int err = 0;
     // ---- tile sharding: this world owns half-res rows [ty0, ty1) of every frame
     bool tiled = false; uint32_t trank = 0, tcount = 1, ty0 = 0, ty1 = 0;
-    kjb_buffer xchg_send[3]{}, xchg_recv[3]{}; uint64_t xchg_bytes_per_rank[3] = {0, 0, 0};   // [0] end-of-frame history borders, [1] mid-frame GI bands (reflections on), [2] host-supplied inputs
+    kjb_buffer xchg_send[4]{}, xchg_recv[4]{}; uint64_t xchg_bytes_per_rank[4] = {0, 0, 0, 0};   // [0] end-of-frame history borders, [1] mid-frame GI bands (reflections on), [2] host-supplied inputs, [3] irradiance-cache requests
+    kjb_ircache_bindings frame_cache{}; bool cache_share_pending = false;   // this frame's cache bindings (tile-sharded frames exchange the cache requests after the last user)
     void band(uint32_t r, uint32_t rows, uint32_t& b0, uint32_t& b1) const { b0 = uint32_t(uint64_t(rows) * r / tcount); b1 = uint32_t(uint64_t(rows) * (r + 1) / tcount); }
     // restrict the next pass to the owned band grown by `e` half-res rows; `scale` = 2 for full-res passes
     uint32_t cur_row0 = 0;   // first row of the scissor last set by rows()
@@ -246,7 +247,7 @@ void kjb_world_destroy(kjb_world* w) {
     if (!w) return;
     kjb_sync(w->ctx);   // every queue: nothing of this world is in flight any more
     for (auto& kv : w->images) kjb_image_free(w->ctx, &kv.second);
-    for (int k = 0; k < 3; ++k) { if (w->xchg_send[k].data) kjb_buffer_free(w->ctx, &w->xchg_send[k]); if (w->xchg_recv[k].data) kjb_buffer_free(w->ctx, &w->xchg_recv[k]); }
+    for (int k = 0; k < 4; ++k) { if (w->xchg_send[k].data) kjb_buffer_free(w->ctx, &w->xchg_send[k]); if (w->xchg_recv[k].data) kjb_buffer_free(w->ctx, &w->xchg_recv[k]); }
     delete w;
 }
 
@@ -652,14 +653,46 @@ static void graph_open_slot(kjb_world* w, uint32_t slot) {
     if (w->use_graph && !w->profiling && !w->tiled && w->frame_idx >= 4 && w->stop_after.empty() && !w->err && kjb_graph_select(w->ctx, slot) == 0 && kjb_graph_begin(w->ctx) == 0) w->graph_open = true;
 }
 static void graph_close(kjb_world* w) { if (w->graph_open) { w->graph_open = false; if (kjb_graph_end(w->ctx)) w->err = 1; } }
+// Tile-sharded frames: the replicas of the irradiance cache exchange what this frame's rays asked of them (kjb.h, kjb_pass_ircache_export_requests): one small
+// all-gather + one merge launch per other rank.  With async compute it runs on the async queue — right in front of the next frame's cache chain, under the
+// reflection filters and TAA of this frame.
+static const uint32_t EV_CACHE_SHARED = 22, CACHE_SHARE_MAX_RECORDS = 32768;
+static void ircache_share(kjb_world* w) {
+    kjb_context* ctx = w->ctx;
+    const uint32_t n = w->tcount;
+    const uint64_t block = (uint64_t(KJB_IRCACHE_SHARE_BLOCK_BYTES(CACHE_SHARE_MAX_RECORDS)) + 255) / 256 * 256;
+    if (w->xchg_bytes_per_rank[3] != block) {
+        if (kjb_buffer_alloc(ctx, block, &w->xchg_send[3]) || kjb_buffer_alloc(ctx, block * n, &w->xchg_recv[3])) { w->err = 1; return; }
+        w->xchg_bytes_per_rank[3] = block;
+    }
+    const uint32_t queue = w->async_ok ? KJB_QUEUE_ASYNC : KJB_QUEUE_COMPUTE;
+    int rc = 0;
+    if (queue == KJB_QUEUE_ASYNC) rc |= kjb_queue_wait_event(ctx, KJB_QUEUE_ASYNC, EV_CACHE_USERS_DONE) | kjb_set_pass_queue(ctx, KJB_QUEUE_ASYNC);
+    w->pass_begin("tile ircache all-gather");
+    kjb_ircache_share_args a{}; a.ircache = w->frame_cache; a.max_records = CACHE_SHARE_MAX_RECORDS;
+    a.block = w->xchg_send[3];
+    rc |= kjb_pass_ircache_export_requests(ctx, &a);
+    rc |= kjb_allgather_on(ctx, queue, w->xchg_send[3].data, w->xchg_recv[3].data, block);
+    for (uint32_t r = 0; r < n && !rc; ++r) {
+        if (r == w->trank) continue;
+        a.block = kjb_buffer{(char*)w->xchg_recv[3].data + block * r, block}; a.seed = w->frame_idx * n + r;
+        rc |= kjb_pass_ircache_merge_requests(ctx, &a);
+    }
+    w->pass_end();
+    if (queue == KJB_QUEUE_ASYNC) { rc |= kjb_event_record(ctx, EV_CACHE_SHARED, KJB_QUEUE_ASYNC) | kjb_set_pass_queue(ctx, KJB_QUEUE_COMPUTE); w->cache_share_pending = true; }
+    if (rc) w->err = 1;
+}
 // Called after the last pass of the frame that reads or writes the irradiance cache: from here on the next frame's cache chain may run.  The event is
 // recorded between two recordings (an event inside a recording is not visible to other queues).
 static void cache_users_done(kjb_world* w) {
-    if (w->cache_users_done_marked || !w->async_frame) return;
+    if (w->cache_users_done_marked || w->err || w->stopped) return;
     w->cache_users_done_marked = true;
+    const bool share = w->tiled && w->desc.enable_ircache && w->frame_cache.meta_buf.data != nullptr;
+    if (!w->async_frame && !(share && w->async_ok)) { if (share) ircache_share(w); return; }   // (program order: the event is recorded at the end of the frame)
     const bool reopen = w->graph_open;
     graph_close(w);
     if (kjb_event_record(w->ctx, EV_CACHE_USERS_DONE, KJB_QUEUE_COMPUTE)) w->err = 1;
+    if (share) ircache_share(w);
     if (reopen) graph_open_slot(w, 2);
 }
 
@@ -1141,7 +1174,7 @@ int kjb_world_render_frame(kjb_world* w, const kjb_world_frame* f) {
     }
     // From here to the end of the pass list everything runs on the compute queue: record it and submit the frame as one CUDA graph launch
     // (the inputs above may have come through the upload queue; the result download below goes through the download queue).
-    w->cache_users_done_marked = false;
+    w->cache_users_done_marked = false; w->frame_cache = kjb_ircache_bindings{};
     w->async_ok = w->use_async && !w->profiling && w->frame_idx >= 4 && w->stop_after.empty() && !w->err && kjb_async_passes_supported(ctx) == 1;   // tile-sharded frames too (direct launches)
     w->async_frame = w->async_ok && w->desc.enable_ircache && !frame_inputs_changed;
     graph_open_slot(w, w->async_frame ? 0 : 3);
@@ -1162,8 +1195,10 @@ int kjb_world_render_frame(kjb_world* w, const kjb_world_frame* f) {
     // ircache.prepare + trace_irradiance (world_render_passes.rs:99-122): cache rays use the convolved sky cube
     IrcacheState ircache_state;
     if (w->desc.enable_ircache) {
+        if (w->cache_share_pending) { if (kjb_queue_wait_event(ctx, w->async_frame ? KJB_QUEUE_ASYNC : KJB_QUEUE_COMPUTE, EV_CACHE_SHARED)) w->err = 1; w->cache_share_pending = false; }
         if (w->async_frame && (kjb_queue_wait_event(ctx, KJB_QUEUE_ASYNC, EV_CACHE_USERS_DONE) | kjb_set_pass_queue(ctx, KJB_QUEUE_ASYNC))) w->err = 1;
         ircache_state = ircache_prepare(w); ircache_trace_irradiance(w, ircache_state, convolved_sky_cube);
+        w->frame_cache = ircache_state.bindings();
         if (w->async_frame && kjb_set_pass_queue(ctx, KJB_QUEUE_COMPUTE)) w->err = 1;
     }
 

@@ -388,6 +388,61 @@ KJB_KERNEL(256) k_ircache_sum(const __grid_constant__ Globals g, const uint32_t*
 }
 
 // ================================================================== C-ABI entry points
+// ------------------------------------------------------------------ tile-sharded frames: exchange of cache requests between the ranks' replicas (kjb.h)
+KJB_KERNEL(256) k_ircache_export_requests(IrcacheBufs b, uint32_t* block, uint32_t max_records, Rows kjb_rows) {
+    const uint32_t e = tid1d();
+    if (e >= b.meta[IRCACHE_META_ENTRY_COUNT] || e >= MAX_ENTRIES) return;
+    const uint32_t life = b.life[e];
+    // Entries of rank <= 1 only: the ones a screen ray asked for (the diffuse and reflection rays look the cache up with query rank 1, rtdgi/trace_diffuse,
+    // rtr/reflection).  Entries of higher rank exist because a cache ray of THIS replica landed there; every replica derives its own from the (now shared)
+    // rank-1 set, as the single cache does — exporting them would make the union grow with the number of ranks.
+    if (!is_ircache_entry_life_valid(life) || ircache_entry_life_to_rank(life) > 1u) return;
+    const uint32_t slot = atom_add(&block[0], 1u);            // the header may end up above max_records: readers clamp
+    if (slot >= max_records) return;
+    uint32_t* rec = block + 4 + slot * 8u;
+    const float4 v = b.reposition_proposal[e];
+    rec[0] = b.entry_cell[e]; rec[1] = life; rec[2] = b.reposition_count[e]; rec[3] = 0u;
+    rec[4] = kjb_f2u(v.x); rec[5] = kjb_f2u(v.y); rec[6] = kjb_f2u(v.z); rec[7] = kjb_f2u(v.w);
+}
+// one launch per source rank: a cell appears at most once per block, so records of one launch never meet in the same entry
+KJB_KERNEL(256) k_ircache_merge_requests(IrcacheBufs b, const uint32_t* block, uint32_t max_records, uint32_t seed, Rows kjb_rows) {
+    const uint32_t i = tid1d();
+    const uint32_t n = block[0] < max_records ? block[0] : max_records;
+    if (i >= n) return;
+    const uint32_t* rec = block + 4 + i * 8u;
+    const uint32_t cell_idx = rec[0], life_r = rec[1], count_r = rec[2];
+    if (cell_idx >= KJB_IRCACHE_GRID_CELLS || !is_ircache_entry_life_valid(life_r)) return;
+    const float4 vote = f4(kjb_u2f(rec[4]), kjb_u2f(rec[5]), kjb_u2f(rec[6]), kjb_u2f(rec[7]));
+    bool fresh = false;
+    if ((b.grid_meta[cell_idx * 2 + 1] & IRCACHE_ENTRY_META_OCCUPIED) == 0) {      // no local ray asked for this cell: allocate it as the lookup would (lookup.hlsl:19-74)
+        const uint32_t prev = atom_or(&b.grid_meta[cell_idx * 2 + 1], IRCACHE_ENTRY_META_OCCUPIED | IRCACHE_ENTRY_META_JUST_ALLOCATED);
+        if ((prev & IRCACHE_ENTRY_META_OCCUPIED) == 0) {
+            const uint32_t alloc_idx = atom_add(&b.meta[IRCACHE_META_ALLOC_COUNT], 1u);
+            if (alloc_idx >= 1024u * 64u) {
+                atom_add(&b.meta[IRCACHE_META_ALLOC_COUNT], uint32_t(-1));
+                atom_and(&b.grid_meta[cell_idx * 2 + 1], ~(IRCACHE_ENTRY_META_OCCUPIED | IRCACHE_ENTRY_META_JUST_ALLOCATED));
+                return;
+            }
+            const uint32_t entry_idx = b.pool[alloc_idx];
+            atom_max(&b.meta[IRCACHE_META_ENTRY_COUNT], entry_idx + 1);
+            b.life[entry_idx] = life_r; b.entry_cell[entry_idx] = cell_idx; b.grid_meta[cell_idx * 2 + 0] = entry_idx;
+            b.reposition_proposal[entry_idx] = vote; b.reposition_count[entry_idx] = count_r;
+            fresh = true;
+        }
+    }
+    if (fresh || (b.grid_meta[cell_idx * 2 + 1] & IRCACHE_ENTRY_META_OCCUPIED) == 0) return;
+    const uint32_t entry_idx = b.grid_meta[cell_idx * 2 + 0];
+    const uint32_t prev_life = b.life[entry_idx];
+    if (prev_life >= IRCACHE_ENTRY_LIFE_RECYCLE) return;
+    if (life_r < prev_life) atom_min(&b.life[entry_idx], life_r);
+    if (count_r > 0u) {
+        const uint32_t prev_votes = atom_add(&b.reposition_count[entry_idx], count_r);
+        uint32_t rng = hash1(cell_idx ^ hash1(seed));
+        const float dart = rand01(rng);
+        if (dart * (float(prev_votes) + float(count_r)) <= float(count_r)) b.reposition_proposal[entry_idx] = vote;
+    }
+}
+
 #define BUF(b, T, min_elems, name) if (!(b).data || (b).size_bytes < uint64_t(min_elems) * sizeof(T)) return c->fail(std::string(P) + ": buffer '" name "' is null or too small")
 #define U32P(b) ((uint32_t*)(b).data)
 #define F4P(b) ((float4*)(b).data)
@@ -502,6 +557,28 @@ int kjb_pass_ircache_sum(kjb_context* c, const kjb_ircache_sum_args* a) {
     BUF(a->entry_indirection_buf, uint32_t, MAX_ENTRIES + 1, "entry_indirection_buf");
     NO_SCISSOR;
     KJB_LAUNCH(c, k_ircache_sum, DIMS1D(MAX_ENTRIES, 256), c->g, U32P(a->meta_buf), F4P(a->irradiance_buf), F4P(a->aux_buf), U32P(a->entry_indirection_buf));
+    KJB_PASS_EPILOGUE(c, P);
+}
+
+static bool share_bindings_ok(const kjb_ircache_bindings& b) {
+    return b.meta_buf.data && b.pool_buf.data && b.reposition_proposal_buf.data && b.reposition_proposal_count_buf.data && b.grid_meta_buf.data && b.entry_cell_buf.data && b.life_buf.data;
+}
+int kjb_pass_ircache_export_requests(kjb_context* c, const kjb_ircache_share_args* a) {
+    const char* P = "tile ircache export";
+    if (!share_bindings_ok(a->ircache)) return c->fail(std::string(P) + ": the irradiance cache is not bound");
+    BUF(a->block, uint8_t, KJB_IRCACHE_SHARE_BLOCK_BYTES(uint64_t(a->max_records)), "block");
+    NO_SCISSOR;
+    if (dev_memset(c, a->block.data, 0, 16)) return c->fail(std::string(P) + ": memset failed");
+    KJB_LAUNCH_ORDERED(c, k_ircache_export_requests, DIMS1D(MAX_ENTRIES, 256), ircache_bufs(a->ircache), U32P(a->block), a->max_records);
+    KJB_PASS_EPILOGUE(c, P);
+}
+int kjb_pass_ircache_merge_requests(kjb_context* c, const kjb_ircache_share_args* a) {
+    const char* P = "tile ircache merge";
+    if (!share_bindings_ok(a->ircache)) return c->fail(std::string(P) + ": the irradiance cache is not bound");
+    BUF(a->block, uint8_t, KJB_IRCACHE_SHARE_BLOCK_BYTES(uint64_t(a->max_records)), "block");
+    if (a->max_records == 0) return 0;
+    NO_SCISSOR;
+    KJB_LAUNCH_ORDERED(c, k_ircache_merge_requests, DIMS1D(a->max_records, 256), ircache_bufs(a->ircache), (const uint32_t*)a->block.data, a->max_records, a->seed);
     KJB_PASS_EPILOGUE(c, P);
 }
 

@@ -396,31 +396,28 @@ KJB_DEV void taa_px(const Globals& g, const TaaImgs& t, float4 its, float4 ots, 
     const float2 vo = cvel / dt;
     st_rg16f(t.velocity_output_tex, x, y, vo.x, vo.y);
 }
-KJB_KERNEL(256) k_taa(const __grid_constant__ Globals g, TaaImgs t, float4 its, float4 ots, W25t bw, Rows kjb_rows) {
-    KJB_PX; if (x >= t.temporal_output_tex.w || y >= t.temporal_output_tex.h) return;
-    taa_px(g, t, its, ots, bw, x, y, [&](int xx, int yy) { return ld_rgba16f(t.history_tex, x + xx, y + yy); },
-           [&](int bx, int by, int dx, int dy) { return taa_input_remap(ld_rgba16f(t.input_tex, bx + dx, by + dy)); });
-}
-// Tiled variant for the native-resolution case (input extent == output extent, so the input tap (bx + dx, by + dy) is (x + dx, y + dy)):
-// history (32+4)x(8+4) and input (32+2)x(8+2) footprints through one TMA group; f16 -> f32 of the history and taa_input_remap of the
-// input run once per texel instead of once per tap (25 and 18 taps per pixel).
+// Tiled variant: the history (32+4)x(8+4) footprint — and, at native resolution (NATIVE: input extent == output extent, so the input tap
+// (bx + dx, by + dy) is (x + dx, y + dy)), the input (32+2)x(8+2) footprint — through one TMA group; f16 -> f32 of the history and taa_input_remap
+// of the input run once per texel instead of once per tap (25 and 18 taps per pixel).  With temporal upsampling the input taps of a block do not form
+// a fixed footprint and stay global loads; the history, which is always at output resolution, is still staged.
 #define T7_HW 36
 #define T7_HH 12
-KJB_KERNEL(256) k_taa_tiled(const __grid_constant__ TileSource ts_history, const __grid_constant__ TileSource ts_input, int use_tma, Globals g, TaaImgs t, float4 its, float4 ots, W25t bw, Rows kjb_rows) {
+template <bool NATIVE>
+KJB_DEVONLY void taa_tiled_block(const TileSource& ts_history, const TileSource& ts_input, int use_tma, const Globals& g, const TaaImgs& t, float4 its, float4 ots, const W25t& bw, const Rows& kjb_rows) {
     constexpr int PH = tile_pitch<8>(T7_HW), PI = tile_pitch<8>(T2_TW);
     __shared__ __align__(128) uint2 s_hraw[PH * T7_HH];
-    __shared__ __align__(128) uint2 s_iraw[PI * T2_TH];
+    __shared__ __align__(128) uint2 s_iraw[NATIVE ? PI * T2_TH : 2];
     __shared__ float4 s_hist[T7_HW * T7_HH];
-    __shared__ float s_y[T2_LW * T2_TH], s_cb[T2_LW * T2_TH], s_cr[T2_LW * T2_TH];
+    __shared__ float s_y[NATIVE ? T2_LW * T2_TH : 1], s_cb[NATIVE ? T2_LW * T2_TH : 1], s_cr[NATIVE ? T2_LW * T2_TH : 1];
     __shared__ __align__(8) uint64_t bar;
     const int tid = int(threadIdx.y) * 32 + int(threadIdx.x);
     const int bx0 = int(blockIdx.x) * 32, by0 = kjb_rows.y0 + int(blockIdx.y) * 8;
     tile_group_begin(&bar, 0, use_tma, tid);
     uint32_t staged = tile_issue<uint2, T7_HW, T7_HH>(s_hraw, ts_history, t.history_tex, bx0 - 2, by0 - 2, &bar, use_tma, tid, 256);
-    staged += tile_issue<uint2, T2_TW, T2_TH>(s_iraw, ts_input, t.input_tex, bx0 - T2_AX, by0 - 1, &bar, use_tma, tid, 256);
+    if (NATIVE) staged += tile_issue<uint2, T2_TW, T2_TH>(s_iraw, ts_input, t.input_tex, bx0 - T2_AX, by0 - 1, &bar, use_tma, tid, 256);
     tile_group_wait(&bar, 0, use_tma, staged, tid);
     for (int i = tid; i < T7_HW * T7_HH; i += 256) s_hist[i] = half4_to_float4(s_hraw[(i / T7_HW) * PH + (i % T7_HW)]);
-    for (int i = tid; i < T2_LW * T2_TH; i += 256) {
+    if (NATIVE) for (int i = tid; i < T2_LW * T2_TH; i += 256) {
         const float3 c = taa_input_remap(half4_to_float4(s_iraw[(i / T2_LW) * PI + (i % T2_LW) + (T2_AX - 1)]));
         s_y[i] = c.x; s_cb[i] = c.y; s_cr[i] = c.z;
     }
@@ -428,8 +425,15 @@ KJB_KERNEL(256) k_taa_tiled(const __grid_constant__ TileSource ts_history, const
     const int x = bx0 + int(threadIdx.x), y = by0 + int(threadIdx.y);
     if (x >= t.temporal_output_tex.w || y >= t.temporal_output_tex.h || y >= kjb_rows.y1) return;
     const int tx = int(threadIdx.x), ty = int(threadIdx.y);
-    taa_px(g, t, its, ots, bw, x, y, [&](int xx, int yy) { return s_hist[(ty + 2 + yy) * T7_HW + (tx + 2 + xx)]; },
-           [&](int bx, int by, int dx, int dy) { const int ti = (by - by0 + 1 + dy) * T2_LW + (bx - bx0 + 1 + dx); return f3(s_y[ti], s_cb[ti], s_cr[ti]); });
+    auto hist = [&](int xx, int yy) { return s_hist[(ty + 2 + yy) * T7_HW + (tx + 2 + xx)]; };
+    if (NATIVE) taa_px(g, t, its, ots, bw, x, y, hist, [&](int bx, int by, int dx, int dy) { const int ti = (by - by0 + 1 + dy) * T2_LW + (bx - bx0 + 1 + dx); return f3(s_y[ti], s_cb[ti], s_cr[ti]); });
+    else taa_px(g, t, its, ots, bw, x, y, hist, [&](int bx, int by, int dx, int dy) { return taa_input_remap(ld_rgba16f(t.input_tex, bx + dx, by + dy)); });
+}
+KJB_KERNEL(256) k_taa_tiled(const __grid_constant__ TileSource ts_history, const __grid_constant__ TileSource ts_input, int use_tma, const __grid_constant__ Globals g, const __grid_constant__ TaaImgs t, float4 its, float4 ots, const __grid_constant__ W25t bw, Rows kjb_rows) {
+    taa_tiled_block<true>(ts_history, ts_input, use_tma, g, t, its, ots, bw, kjb_rows);
+}
+KJB_KERNEL(256) k_taa_tiled_upsampling(const __grid_constant__ TileSource ts_history, int use_tma, const __grid_constant__ Globals g, const __grid_constant__ TaaImgs t, float4 its, float4 ots, const __grid_constant__ W25t bw, Rows kjb_rows) {
+    taa_tiled_block<false>(ts_history, ts_history, use_tma, g, t, its, ots, bw, kjb_rows);
 }
 
 #define F4A(a) f4((a)[0], (a)[1], (a)[2], (a)[3])
@@ -510,8 +514,10 @@ int kjb_pass_taa(kjb_context* c, const kjb_taa_args* a) {
     if (a->input_tex.width == W && a->input_tex.height == H) {
         const TileSource ts_h = tile_source(c, a->history_tex, T7_HW, T7_HH), ts_i = tile_source(c, a->input_tex, T2_TW, T2_TH);
         KJB_LAUNCH_SYNC(c, k_taa_tiled, KJB_GRID2D(W, H, 32, 8), ts_h, ts_i, tile_mode({&ts_h, &ts_i}), c->g, t, F4A(a->input_tex_size), F4A(a->output_tex_size), bw);
-    } else
-        KJB_LAUNCH(c, k_taa, KJB_GRID2D(W, H, 32, 8), c->g, t, F4A(a->input_tex_size), F4A(a->output_tex_size), bw);
+    } else {
+        const TileSource ts_h = tile_source(c, a->history_tex, T7_HW, T7_HH);
+        KJB_LAUNCH_SYNC(c, k_taa_tiled_upsampling, KJB_GRID2D(W, H, 32, 8), ts_h, tile_mode({&ts_h}), c->g, t, F4A(a->input_tex_size), F4A(a->output_tex_size), bw);
+    }
     KJB_PASS_EPILOGUE(c, P);
 }
 

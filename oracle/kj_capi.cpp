@@ -80,6 +80,8 @@ int kjb_graph_end(kjb_context*) { return 0; }
 int kjb_graph_select(kjb_context*, uint32_t) { return 0; }
 int kjb_set_pass_queue(kjb_context*, uint32_t q) { return q == 0 ? 0 : 1; }
 int kjb_async_passes_supported(kjb_context*) { return 0; }
+int kjb_pass_ircache_export_requests(kjb_context*, const kjb_ircache_share_args*) { return 1; }   // tile-sharded frames run on the CUDA backend (and its emulator) only
+int kjb_pass_ircache_merge_requests(kjb_context*, const kjb_ircache_share_args*) { return 1; }
 int kjb_graph_stats(kjb_context*, uint64_t out[2]) { out[0] = out[1] = 0; return 0; }
 int kjb_tlas_stats(kjb_context*, uint64_t out[2]) { out[0] = out[1] = 0; return 0; }   // the oracle rebuilds its median-split BVH whenever a transform changes
 int kjb_set_debug_serial(kjb_context* c, uint32_t on) { c->cache_passes_parallel = on == 0; return 0; }   // default (never called): serial

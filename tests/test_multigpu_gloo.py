@@ -120,8 +120,10 @@ def _worker_ircache(rank, world_size, port, ret):
 
 
 def test_tile_sharded_frames_with_replicated_irradiance_cache(emu_lib):
-    """Tolerance: the band's mean GI within 10 % of the single-process frame's, RMS difference below 25 % of the mean (the cache's contribution is
-    noise-like until it converges), each rank's cache holds a comparable number of live entries (it only sees its band's rays: 30 %..110 %)."""
+    """Every rank keeps a replica of the cache and the replicas exchange their rays' requests each frame (kjb_pass_ircache_export_requests / _merge_requests):
+    the band's mean GI within 10 % of the single-process frame's, RMS difference below 25 % of the mean (48 px wide frame: the noise of the band mean is
+    several percent), and — the point of the exchange — every replica holds the single cache's number of live entries to within 5 % (without the exchange a
+    replica only sees its band's rays: 65-85 %)."""
     ret = mp.Manager().dict()
     mp.spawn(_worker_ircache, args=(2, _free_port(), ret), nprocs=2, join=True)
     for rank in range(2):
@@ -130,7 +132,7 @@ def test_tile_sharded_frames_with_replicated_irradiance_cache(emu_lib):
         assert finite and mb > 0
         assert abs(ma - mb) <= 0.10 * mb, (rank, ma, mb)
         assert rms <= 0.25 * mb, (rank, rms, mb)
-        assert 0.3 * lb <= la <= 1.1 * lb, (rank, la, lb)
+        assert 0.95 * lb <= la <= 1.05 * lb, (rank, la, lb)
 
 
 def test_tile_sharded_reflections_match_single_process(emu_lib):
@@ -154,3 +156,15 @@ def test_tile_sharded_frames_with_host_inputs(emu_lib):
         bad, calls = ret[rank]
         assert calls == 2 * FRAMES, "input bands + history borders"
         assert not bad, f"rank {rank}: {bad}"
+
+
+def test_tile_sharded_reflections_on_eight_narrow_bands(emu_lib):
+    """8 ranks x 288 rows: bands of 18 half-res rows against reflection halos of 70+ — every rank needs rows from several ranks away, both border strips of a
+    band coincide, the GI all-gather feeds rays that land in any band.  rtdgi + reflections + taa, bit for bit (the geometry of 8 GPUs at 1080p / 1440p, where
+    the bench's own parity check can only be statistical because the irradiance cache is on)."""
+    ret = mp.Manager().dict()
+    mp.spawn(_worker, args=(8, _free_port(), True, 288, ret, True), nprocs=8, join=True)
+    for rank in range(8):
+        bad, calls = ret[rank]
+        assert calls == 2 * FRAMES
+        assert not bad, f"rank {rank}: band differs from the single-process frame: {bad}"

@@ -14,7 +14,7 @@ KERNEL_TO_PASS = {
     "k_rtr_trace": "reflection trace", "k_rtr_validate": "reflection validate", "k_rtr_restir_temporal": "rtr restir temporal", "k_rtr_resolve": "reflection resolve",
     "k_rtr_temporal": "reflection temporal", "k_rtr_cleanup": "reflection cleanup",
     "k_taa_reproject": "reproject taa", "k_taa_filter_input_tiled": "taa filter input", "k_taa_filter_history_tiled": "taa filter history", "k_taa_filter_history": "taa filter history",
-    "k_taa_input_prob": "taa input prob", "k_taa_prob_filter": "taa prob filter", "k_taa_prob_filter2": "taa prob filter2", "k_taa_tiled": "taa", "k_taa": "taa",
+    "k_taa_input_prob": "taa input prob", "k_taa_prob_filter": "taa prob filter", "k_taa_prob_filter2": "taa prob filter2", "k_taa_tiled": "taa", "k_taa_tiled_upsampling": "taa",
     "k_ircache_validate": "ircache validate", "k_ircache_trace": "ircache trace", "k_ircache_trace_access": "ircache trace access", "k_ircache_sum": "ircache sum",
 }
 
