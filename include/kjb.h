@@ -217,7 +217,7 @@ int  kjb_comm_init_nccl(kjb_context *ctx, const void *unique_id_128_bytes, uint3
 int  kjb_comm_set_callback(kjb_context *ctx, kjb_allgather_fn fn, void *user, uint32_t rank, uint32_t nranks);
 int  kjb_comm_rank(kjb_context *ctx, uint32_t *rank, uint32_t *nranks);
 int  kjb_allgather(kjb_context *ctx, const void *send, void *recv, uint64_t bytes_per_rank);
-int  kjb_allgather_on(kjb_context *ctx, uint32_t queue, const void *send, void *recv, uint64_t bytes_per_rank);   /* same, enqueued on `queue` */     /* enqueued on the stream */
+int  kjb_allgather_on(kjb_context *ctx, uint32_t queue, const void *send, void *recv, uint64_t bytes_per_rank);   /* same, enqueued on `queue`; in place when send == recv + rank * bytes_per_rank */     /* enqueued on the stream */
 int  kjb_memcpy_d2d(kjb_context *ctx, void *dst, const void *src, uint64_t bytes);
 /* Many device-to-device copies in ONE launch (the pack / unpack of the tile border exchange is dozens of small row strips). */
 typedef struct kjb_copy_desc { void *dst; const void *src; uint64_t bytes; } kjb_copy_desc;

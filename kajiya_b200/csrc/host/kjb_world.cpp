@@ -550,6 +550,14 @@ static int tile_exchange(kjb_world* w, const std::vector<XchgItem>& items_in, ui
     const uint32_t n = w->tcount;
     uint32_t band_max = 0, band_min = 0xffffffffu;
     for (uint32_t r = 0; r < n; ++r) { uint32_t b0, b1; w->band(r, w->HH, b0, b1); band_max = std::max(band_max, b1 - b0); band_min = std::min(band_min, b1 - b0); }
+    // One whole-band image and equal bands (this frame's GI for the reflection rays at 2 / 4 GPUs): the image IS the concatenation of the ranks' bands, so the
+    // all-gather runs in place on it — no staging buffers, no pack / unpack launches.
+    if (items_in.size() == 1 && items_in[0].border == 0 && band_max == band_min && n > 1) {
+        const kjb_image& img = items_in[0].img;
+        const uint64_t band_bytes = uint64_t(img.width) * kjb_format_texel_bytes(img.format) * band_max * items_in[0].scale;
+        if (band_bytes * n == uint64_t(img.width) * kjb_format_texel_bytes(img.format) * img.height)
+            return kjb_allgather_on(ctx, queue, (const char*)img.data + band_bytes * w->trank, img.data, band_bytes);
+    }
     // narrow bands (many ranks): when the two border strips of a band touch or overlap, send the band once instead of twice
     std::vector<XchgItem> items = items_in;
     for (XchgItem& it : items) if (it.border && 2 * it.border >= band_min * it.scale) it.border = 0;
@@ -687,7 +695,8 @@ static void ircache_share(kjb_world* w) {
 static void cache_users_done(kjb_world* w) {
     if (w->cache_users_done_marked || w->err || w->stopped) return;
     w->cache_users_done_marked = true;
-    const bool share = w->tiled && w->desc.enable_ircache && w->frame_cache.meta_buf.data != nullptr;
+    static const bool no_share = [] { const char* e = getenv("KJB_NO_CACHE_SHARE"); return e && e[0] == '1'; }();   // A/B switch: independent replicas
+    const bool share = w->tiled && w->desc.enable_ircache && w->frame_cache.meta_buf.data != nullptr && !no_share;
     if (!w->async_frame && !(share && w->async_ok)) { if (share) ircache_share(w); return; }   // (program order: the event is recorded at the end of the frame)
     const bool reopen = w->graph_open;
     graph_close(w);

@@ -1,6 +1,7 @@
 // Multi-GPU transport for tile-sharded frames: one ncclAllGather per frame on the context's stream.
 // NCCL is dlopen'ed (no link-time dependency: the library must load in the GPU-less build container); the communicator is
 // created from a unique id the caller distributes (bench.py uses torch.distributed for that plumbing only).
+#include <vector>
 #include "kjb_context.h"
 #if !defined(KJB_EMU)
 #include <dlfcn.h>
@@ -35,17 +36,25 @@ struct NcclApi {
 #endif
 }  // namespace
 
-// ---- batched device-to-device copy: blockIdx.y selects the copy, KJB_COPY_CTAS CTAs stride over it with 16-byte accesses when
-// both ends and the size allow, bytes otherwise
+// ---- batched device-to-device copy: blockIdx.y selects the copy, gridDim.x CTAs stride over it with 16-byte accesses (four in flight per thread)
+// when both ends and the size allow, bytes otherwise.  gridDim.x follows the largest copy of the batch: one CTA per 64 KiB, at most 256 — a whole band
+// of a full-res image (8 MB) is then copied by the whole GPU instead of by 24 CTAs.
 #define KJB_COPY_BATCH 96u
 #define KJB_COPY_CTAS 24u
+#define KJB_COPY_CTAS_MAX 256u
 struct CopyBatch { kjb_copy_desc d[KJB_COPY_BATCH]; uint32_t count; };
 KJB_KERNEL(256) k_copy_batch(CopyBatch b, kjb::Rows kjb_rows) {
     const kjb_copy_desc cd = b.d[blockIdx.y];
     const uint64_t tid = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x, nthreads = uint64_t(gridDim.x) * blockDim.x;
     if (((uintptr_t(cd.dst) | uintptr_t(cd.src) | cd.bytes) & 15u) == 0) {
         const uint4* s = reinterpret_cast<const uint4*>(cd.src); uint4* d = reinterpret_cast<uint4*>(cd.dst);
-        for (uint64_t i = tid; i < cd.bytes / 16; i += nthreads) d[i] = s[i];
+        const uint64_t n = cd.bytes / 16;
+        uint64_t i = tid;
+        for (; i + 3 * nthreads < n; i += 4 * nthreads) {
+            const uint4 a0 = s[i], a1 = s[i + nthreads], a2 = s[i + 2 * nthreads], a3 = s[i + 3 * nthreads];
+            d[i] = a0; d[i + nthreads] = a1; d[i + 2 * nthreads] = a2; d[i + 3 * nthreads] = a3;
+        }
+        for (; i < n; i += nthreads) d[i] = s[i];
     } else {
         const uint8_t* s = reinterpret_cast<const uint8_t*>(cd.src); uint8_t* d = reinterpret_cast<uint8_t*>(cd.dst);
         for (uint64_t i = tid; i < cd.bytes; i += nthreads) d[i] = s[i];
@@ -90,6 +99,14 @@ int kjb_allgather_on(kjb_context* c, uint32_t queue, const void* send, void* rec
 #endif
     if (!c->ag_fn) return c->fail("kjb_allgather: no transport registered (kjb_comm_init_nccl / kjb_comm_set_callback)");
     if (dev_sync(c)) return c->fail("kjb_allgather: sync failed");
+#if !defined(KJB_EMU)
+    if (send == (const char*)recv + uint64_t(c->rank) * bytes) return c->fail("kjb_allgather: the callback transport of the CUDA build does not gather in place");
+#else
+    if (send == (const char*)recv + uint64_t(c->rank) * bytes) {   // in place (this rank's part already sits in `recv`): host transports get a separate copy of it
+        std::vector<uint8_t> tmp((const uint8_t*)send, (const uint8_t*)send + bytes);
+        return c->ag_fn(c->ag_user, tmp.data(), recv, bytes);
+    }
+#endif
     return c->ag_fn(c->ag_user, send, recv, bytes);
 }
 int kjb_allgather(kjb_context* c, const void* send, void* recv, uint64_t bytes) { return kjb_allgather_on(c, KJB_QUEUE_COMPUTE, send, recv, bytes); }
@@ -101,14 +118,16 @@ int kjb_memcpy_d2d_batch_on(kjb_context* c, uint32_t queue, const kjb_copy_desc*
 #endif
     for (uint32_t i0 = 0; i0 < count; i0 += KJB_COPY_BATCH) {
         CopyBatch b; b.count = count - i0 < KJB_COPY_BATCH ? count - i0 : KJB_COPY_BATCH;
-        bool any = false;
-        for (uint32_t i = 0; i < b.count; ++i) { b.d[i] = copies[i0 + i]; any = any || copies[i0 + i].bytes; }
+        bool any = false; uint64_t largest = 0;
+        for (uint32_t i = 0; i < b.count; ++i) { b.d[i] = copies[i0 + i]; any = any || copies[i0 + i].bytes; largest = largest > copies[i0 + i].bytes ? largest : copies[i0 + i].bytes; }
         if (!any) continue;
+        uint32_t ctas = uint32_t((largest + 65535u) / 65536u); ctas = ctas < 1u ? 1u : (ctas > KJB_COPY_CTAS_MAX ? KJB_COPY_CTAS_MAX : ctas);
+        if (ctas < KJB_COPY_CTAS && b.count < 16u) ctas = KJB_COPY_CTAS;   // few small copies: latency matters more than CTA count
         const kjb::Rows rows = {0, 1};
 #if defined(KJB_EMU)
-        kjb_emu::launch(dim3(KJB_COPY_CTAS, b.count), dim3(256), [&]() { k_copy_batch(b, rows); });
+        kjb_emu::launch(dim3(ctas > 4u ? 4u : ctas, b.count), dim3(256), [&]() { k_copy_batch(b, rows); });
 #else
-        k_copy_batch<<<dim3(KJB_COPY_CTAS, b.count), dim3(256), 0, st>>>(b, rows);
+        k_copy_batch<<<dim3(ctas, b.count), dim3(256), 0, st>>>(b, rows);
 #endif
         c->launches++;
     }
