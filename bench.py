@@ -345,19 +345,32 @@ def parity_check(lib, torch, dist, workload, rank, world_size, local_rank, frame
     dist.broadcast_object_list(uid, src=0)
     wt.comm_init_nccl(uid[0], rank, world_size)
     wu, _, _, _ = build_world(lib, workload, device=local_rank, tile=None)
+    statistical = bool(WORKLOADS[workload][5].get("enable_ircache"))
+    # statistical mode: a SECOND untiled world rendered alongside gives the run-to-run spread of the single-GPU renderer itself (same racy kernels, same frames) —
+    # the yardstick the tiled-vs-untiled difference is held against
+    wu2 = build_world(lib, workload, device=local_rank, tile=None)[0] if statistical else None
     for _ in range(frames):
         wt.render_frame(**view); wu.render_frame(**view)
+        if wu2 is not None:
+            wu2.render_frame(**view)
     name = result_image_name(workload)
-    statistical = bool(WORKLOADS[workload][5].get("enable_ircache"))
+    floor_mean = floor_rms = 0.0
+    if wu2 is not None:
+        _, _, floor_mean, floor_rms, _ = band_compare(wu.image(name), wu2.image(name), H, rank, world_size, True)
+        wu2.close()
     ok, exact, rel_mean, rel_rms, sha = band_compare(wu.image(name), wt.image(name), H, rank, world_size, statistical)
+    if statistical:
+        ok = rel_mean < 0.08 and rel_rms < max(0.25, 1.5 * floor_rms)
     wt.close(); wu.close()
     det = band_compare.last_detail
-    v = torch.tensor([1.0 if ok else 0.0, 1.0 if exact else 0.0, rel_mean, rel_rms, det["rel_rms_unclipped"], det["max_untiled"], det["max_tiled"], float(det["nonfinite"])], device="cuda", dtype=torch.float64)
+    v = torch.tensor([1.0 if ok else 0.0, 1.0 if exact else 0.0, rel_mean, rel_rms, det["rel_rms_unclipped"], det["max_untiled"], det["max_tiled"], float(det["nonfinite"]), floor_mean, floor_rms], device="cuda", dtype=torch.float64)
     lo = v.clone(); dist.all_reduce(lo, op=dist.ReduceOp.MIN)
     hi = v.clone(); dist.all_reduce(hi, op=dist.ReduceOp.MAX)
-    return {"ok": bool(lo[0].item() > 0.5), "mode": "statistical (irradiance cache: per-rank replicas exchanging their requests, racy by design; band mean within 8 %, RMS of 16x16 block means below 25 %)" if statistical else "bit-exact (every rank's band of the tiled frame == the untiled frame)",
+    return {"ok": bool(lo[0].item() > 0.5), "mode": "statistical (irradiance cache: per-rank replicas exchanging their requests, racy by design; band mean within 8 %, RMS of 16x16 block means below max(25 %, 1.5 x the spread of two single-GPU renders))" if statistical else "bit-exact (every rank's band of the tiled frame == the untiled frame)",
             "bands_bit_identical": bool(lo[1].item() > 0.5), "worst_band_mean_rel_diff": hi[2].item(), "worst_band_rel_rms": hi[3].item(), "worst_band_rel_rms_unclipped": hi[4].item(),
-            "max_texel_untiled": hi[5].item(), "max_texel_tiled": hi[6].item(), "nonfinite_texels": int(hi[7].item()), "frames": frames,
+            "max_texel_untiled": hi[5].item(), "max_texel_tiled": hi[6].item(), "nonfinite_texels": int(hi[7].item()),
+            "untiled_vs_untiled": {"worst_band_mean_rel_diff": hi[8].item(), "worst_band_rel_rms": hi[9].item(), "note": "two single-GPU renders of the same frames on this rank: the renderer's own run-to-run spread"} if statistical else None,
+            "frames": frames,
             "band_sha256_rank0": sha, "image": name}
 
 
