@@ -286,3 +286,82 @@ def test_gpu_prefix_scan_ragged_sizes(cuda_lib, n):
     for mis in (False, True):
         got, want = _scan_case(cuda_lib, n, misalign=mis)
         assert np.array_equal(got, want), (n, mis)
+
+
+class _Buf(C.Structure):
+    _fields_ = [("data", C.c_void_p), ("size_bytes", C.c_uint64)]
+
+
+class _CacheBindings(C.Structure):   # kjb_ircache_bindings (kjb.h): the reference's binding order
+    _fields_ = [(n, _Buf) for n in ("meta_buf", "pool_buf", "reposition_proposal_buf", "reposition_proposal_count_buf", "grid_meta_buf", "entry_cell_buf",
+                                    "spatial_buf", "irradiance_buf", "life_buf")]
+
+
+def _cache_bindings(w):
+    """kjb_ircache_bindings of a world's cache from the buffers the frame driver keeps by name"""
+    Buf, Bindings = _Buf, _CacheBindings
+    b = Bindings()
+    for field, _ in Bindings._fields_:
+        name = "ircache." + field
+        if field == "grid_meta_buf" and w._cache_parity:
+            name = "ircache.grid_meta_buf2"
+        img = w.image_handle(name)
+        setattr(b, field, Buf(img.data, img.width * img.height * w.lib.dll.kjb_format_texel_bytes(img.format)))
+    return Bindings, Buf, b
+
+
+def test_cache_request_exchange_between_two_replicas(emu_lib):
+    """kjb_pass_ircache_export_requests / kjb_pass_ircache_merge_requests (the multi-GPU cache exchange, kjb.h): cache A has seen one half of the screen's
+    rays, cache B the other half (two views).  After A's records are merged into B, every cell a screen ray of A keeps alive is occupied in B with a life no
+    older than A's; the number of live entries grows by exactly the cells B did not have; merging the same block again changes nothing but vote counts."""
+    scene, view = scenes.cornell_box()
+    kw = dict(enable_ircache=True, spatial_reuse_pass_count=1)
+    wa, wb = _empty_world(emu_lib, 96, 64, **kw), _empty_world(emu_lib, 96, 64, **kw)
+    for w in (wa, wb):
+        scenes.populate(w, scene)
+    vb = dict(view, camera_position=(1.2, 1.4, 4.0))
+    frames = 3
+    for _ in range(frames):
+        wa.render_frame(**view); wb.render_frame(**vb)
+    d = emu_lib.dll
+    for w in (wa, wb):
+        w._cache_parity = frames % 2 == 0     # ircache_parity flips every frame after the first: which of the two grid_meta buffers is current
+    BA, Buf, ba = _cache_bindings(wa)
+    _, _, bb = _cache_bindings(wb)
+
+    class ShareArgs(C.Structure):
+        _fields_ = [("ircache", BA), ("block", Buf), ("max_records", C.c_uint32), ("seed", C.c_uint32)]
+    for f in ("kjb_pass_ircache_export_requests", "kjb_pass_ircache_merge_requests", "kjb_buffer_alloc"):
+        getattr(d, f).restype = C.c_int
+    d.kjb_pass_ircache_export_requests.argtypes = [C.c_void_p, C.c_void_p]; d.kjb_pass_ircache_merge_requests.argtypes = [C.c_void_p, C.c_void_p]
+    d.kjb_buffer_alloc.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p]
+    R = 4096
+    block = Buf(); assert d.kjb_buffer_alloc(wa.ctx, 16 + R * 32, C.byref(block)) == 0
+    a = ShareArgs(ba, block, R, 0)
+    assert d.kjb_pass_ircache_export_requests(wa.ctx, C.byref(a)) == 0, d.kjb_last_error(wa.ctx)
+    wa.sync()
+    rec = np.ctypeslib.as_array((C.c_uint32 * (4 + R * 8)).from_address(block.data)).copy()      # emulator: device memory is host memory
+    n = int(rec[0]); assert 0 < n <= R
+    cells, lives = rec[4:4 + n * 8].reshape(n, 8)[:, 0], rec[4:4 + n * 8].reshape(n, 8)[:, 1]
+    assert len(set(cells.tolist())) == n and (lives < 8).all()                                    # one record per cell; ranks 0 and 1 only
+
+    def state(w, b):
+        gm = np.ctypeslib.as_array((C.c_uint32 * (b.grid_meta_buf.size_bytes // 4)).from_address(b.grid_meta_buf.data)).reshape(-1, 2)
+        life = np.ctypeslib.as_array((C.c_uint32 * (b.life_buf.size_bytes // 4)).from_address(b.life_buf.data))
+        meta = np.ctypeslib.as_array((C.c_uint32 * 8).from_address(b.meta_buf.data))
+        return gm, life, meta
+    gm_b, life_b, meta_b = state(wb, bb)
+    occupied_before = (gm_b[cells, 1] & 1) != 0
+    alloc_before = int(meta_b[3])
+    m = ShareArgs(bb, block, R, 7)
+    assert d.kjb_pass_ircache_merge_requests(wb.ctx, C.byref(m)) == 0, d.kjb_last_error(wb.ctx)
+    wb.sync()
+    assert ((gm_b[cells, 1] & 1) != 0).all()                                                      # every requested cell now lives in B
+    assert int(meta_b[3]) == alloc_before + int((~occupied_before).sum())                         # allocations == the cells B lacked
+    assert (life_b[gm_b[cells, 0]] <= lives).all()                                                # kept alive at least as well as in A
+    alloc_after = int(meta_b[3]); life_after = life_b.copy()
+    assert d.kjb_pass_ircache_merge_requests(wb.ctx, C.byref(m)) == 0
+    wb.sync()
+    assert int(meta_b[3]) == alloc_after and np.array_equal(life_b, life_after)                   # idempotent
+    wb.render_frame(**vb); wb.render_frame(**vb)                                                  # the merged cache keeps working
+    assert np.isfinite(wb.image("rtdgi.spatial_filtered").astype(np.float32)).all()
