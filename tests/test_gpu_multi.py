@@ -1,4 +1,5 @@
-"""Tile-sharded frames on real GPUs over NCCL (needs >= 2 GPUs: `gpurun --gpus 2 -- python -m pytest tests/test_gpu_multi.py -m gpu`).
+"""Tile-sharded frames on real GPUs over NCCL (needs >= 2 GPUs: `gpurun --gpus 2 -- python -m pytest tests/test_gpu_multi.py -m gpu` — plain pytest, NOT under
+torchrun: the test spawns its own ranks, and torchrun's agent-store environment would send their rendezvous to a store that does not exist).
 Each rank's band must equal, bit for bit, the same rows of a single-GPU full-frame render done by the same process."""
 import ctypes as C, os, socket, sys
 import numpy as np, pytest
@@ -13,6 +14,7 @@ def _worker(rank, world_size, port, ret):
     import torch.distributed as dist
     sys.path.insert(0, ROOT); sys.path.insert(0, HERE)
     os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    os.environ.pop("TORCHELASTIC_USE_AGENT_STORE", None)     # started from inside a torchrun worker: rendezvous through OUR store, not the agent's
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world_size, device_id=torch.device("cuda", rank))
     import kajiya_b200
