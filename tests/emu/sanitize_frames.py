@@ -26,3 +26,27 @@ w2=parity.make_world(lib, scene, 53, 37)
 for f in range(4): w2.render_frame(**view2)
 for f in range(2): w2.render_reference(**view2)
 print("cornell ok")
+# native-resolution full path at a 16-byte-aligned extent (the tiled TAA / temporal kernels with both footprints), then the multi-GPU cache-request exchange
+# between two caches (kjb_pass_ircache_export_requests / _merge_requests)
+import ctypes as C
+sys.path.insert(0, os.path.join(ROOT, 'tests'))
+import test_edge_cases as T
+scene3, view3 = scenes.atrium()
+kw3 = dict(enable_ircache=True, enable_rtr=True, enable_taa=True, spatial_reuse_pass_count=2)
+wa, wb = parity.make_world(lib, scene3, 64, 40, **kw3), parity.make_world(lib, scene3, 64, 40, **kw3)
+vb = dict(view3); px, py, pz = view3['camera_position']; vb['camera_position'] = (px + 0.6, py, pz - 0.4)
+for f in range(3): wa.render_frame(**view3); wb.render_frame(**vb)
+for w_ in (wa, wb): w_._cache_parity = False      # three frames: the first grid_meta buffer is current
+_, Buf, ba = T._cache_bindings(wa); _, _, bb = T._cache_bindings(wb)
+class ShareArgs(C.Structure):
+    _fields_ = [("ircache", T._CacheBindings), ("block", Buf), ("max_records", C.c_uint32), ("seed", C.c_uint32)]
+d = lib.dll
+for fn in ("kjb_pass_ircache_export_requests", "kjb_pass_ircache_merge_requests", "kjb_buffer_alloc"): getattr(d, fn).restype = C.c_int
+d.kjb_pass_ircache_export_requests.argtypes = [C.c_void_p, C.c_void_p]; d.kjb_pass_ircache_merge_requests.argtypes = [C.c_void_p, C.c_void_p]; d.kjb_buffer_alloc.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p]
+R = 512   # fewer than the live entries: the export must stop at the cap
+block = Buf(); assert d.kjb_buffer_alloc(wa.ctx, 16 + R * 32, C.byref(block)) == 0
+assert d.kjb_pass_ircache_export_requests(wa.ctx, C.byref(ShareArgs(ba, block, R, 0))) == 0
+wa.sync()
+assert d.kjb_pass_ircache_merge_requests(wb.ctx, C.byref(ShareArgs(bb, block, R, 3))) == 0
+wb.sync(); wb.render_frame(**vb); wb.render_frame(**vb)
+print("native full path + cache exchange ok", wb.stats())
