@@ -119,18 +119,19 @@ def _worker_ircache(rank, world_size, port, ret):
     dist.destroy_process_group()
 
 
-def test_tile_sharded_frames_with_replicated_irradiance_cache(emu_lib):
+@pytest.mark.parametrize("world_size", [2, 4])
+def test_tile_sharded_frames_with_replicated_irradiance_cache(world_size, emu_lib):
     """Every rank keeps a replica of the cache and the replicas exchange their rays' requests each frame (kjb_pass_ircache_export_requests / _merge_requests):
     the band's mean GI within 10 % of the single-process frame's, RMS difference below 25 % of the mean (48 px wide frame: the noise of the band mean is
     several percent), and — the point of the exchange — every replica holds the single cache's number of live entries to within 5 % (without the exchange a
     replica only sees its band's rays: 65-85 %)."""
     ret = mp.Manager().dict()
-    mp.spawn(_worker_ircache, args=(2, _free_port(), ret), nprocs=2, join=True)
-    for rank in range(2):
+    mp.spawn(_worker_ircache, args=(world_size, _free_port(), ret), nprocs=world_size, join=True)
+    for rank in range(world_size):
         finite, ma, mb, rms, (la, lb) = ret[rank]
         print(f"rank {rank}: band mean {ma:.4f} vs {mb:.4f}, rms {rms:.4f}, live entries {la} vs {lb}")
         assert finite and mb > 0
-        assert abs(ma - mb) <= 0.10 * mb, (rank, ma, mb)
+        assert abs(ma - mb) <= (0.10 if world_size == 2 else 0.15) * mb, (rank, ma, mb)   # narrower bands: fewer texels in the mean
         assert rms <= 0.25 * mb, (rank, rms, mb)
         assert 0.95 * lb <= la <= 1.05 * lb, (rank, la, lb)
 
