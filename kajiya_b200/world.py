@@ -21,6 +21,8 @@ class World:
         desc = WorldDesc(width, height, (upscale or (0, 0))[0], (upscale or (0, 0))[1], spatial_reuse_pass_count, int(use_raytraced_reservoir_visibility),
                          int(enable_ircache), int(enable_rtr), int(enable_taa), 0, 0, tile_rank, tile_count, int(enable_ssao), int(enable_lighting), int(hard_sun))
         self.w = C.c_void_p()
+        if tile_count > 1 and enable_lighting:   # kjb_world_create refuses it (rc 1, no context error string: the frame driver sits above the C-ABI)
+            raise KjbError("tile-sharded frames do not include the lit composite (enable_lighting): DESIGN.md §7")
         self._check(self.d.kjb_world_create(self.ctx, C.byref(desc), C.byref(self.w)))
         self.width, self.height = width, height
         self._keep = []
