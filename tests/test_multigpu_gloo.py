@@ -88,7 +88,7 @@ def test_tile_sharded_frames_match_single_process(world_size, enable_taa, height
         assert not bad, f"rank {rank}: band differs from the single-process frame: {bad}"
 
 
-def _worker_ircache(rank, world_size, port, ret):
+def _worker_ircache(rank, world_size, port, ret, full_path=False):
     """tiles + irradiance cache: every rank owns a replica of the cache, so only statistical agreement with the single-process frame is promised"""
     sys.path.insert(0, ROOT); sys.path.insert(0, HERE)
     os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port); os.environ["KJB_EMU_THREADS"] = "2"
@@ -100,6 +100,8 @@ def _worker_ircache(rank, world_size, port, ret):
     scene, view = scenes.cornell_box()
     Wi, Hi, frames = 48, 768, 8      # bands of 192 half-res rows against halos of 52: each replica misses the rays of ~35 % of the frame
     kw = dict(enable_ircache=True, spatial_reuse_pass_count=1)
+    if full_path:   # the bench's headline feature set: reflections (mid-frame GI gather, in place) + TAA + the cache exchange, all in one tile-sharded frame
+        kw.update(enable_rtr=True, enable_taa=True, spatial_reuse_pass_count=2)
     tiled = parity.make_world(lib, scene, Wi, Hi, tile=(rank, world_size), **kw)
 
     def allgather(send, recv, n):
@@ -113,7 +115,8 @@ def _worker_ircache(rank, world_size, port, ret):
     for _ in range(frames):
         tiled.render_frame(**view); full.render_frame(**view)
     y0, y1 = Hi * rank // world_size, Hi * (rank + 1) // world_size
-    a = tiled.image("rtdgi.spatial_filtered")[y0:y1, :, :3].astype(np.float64); b = full.image("rtdgi.spatial_filtered")[y0:y1, :, :3].astype(np.float64)
+    name = "taa.this_frame_out" if full_path else "rtdgi.spatial_filtered"
+    a = tiled.image(name)[y0:y1, :, :3].astype(np.float64); b = full.image(name)[y0:y1, :, :3].astype(np.float64)
     live = int(tiled.image("ircache.meta_buf").ravel()[3]), int(full.image("ircache.meta_buf").ravel()[3])
     ret[rank] = (bool(np.isfinite(a).all()), float(a.mean()), float(b.mean()), float(np.sqrt(((a - b) ** 2).mean())), live)
     dist.destroy_process_group()
@@ -169,3 +172,17 @@ def test_tile_sharded_reflections_on_eight_narrow_bands(emu_lib):
         bad, calls = ret[rank]
         assert calls == 2 * FRAMES
         assert not bad, f"rank {rank}: band differs from the single-process frame: {bad}"
+
+
+def test_tile_sharded_full_path_with_cache_exchange(emu_lib):
+    """The headline feature set on 2 ranks — rtdgi (2 spatial passes) + irradiance cache + reflections + TAA: four exchanges per frame (input-free: GI bands in
+    place, history borders, cache requests).  Statistical like every cache-on comparison: finite, band mean of the TAA output within 10 %, RMS below 25 % of
+    the mean, every replica within 5 % of the single cache's live entries."""
+    ret = mp.Manager().dict()
+    mp.spawn(_worker_ircache, args=(2, _free_port(), ret, True), nprocs=2, join=True)
+    for rank in range(2):
+        finite, ma, mb, rms, (la, lb) = ret[rank]
+        print(f"rank {rank}: band mean {ma:.4f} vs {mb:.4f}, rms {rms:.4f}, live entries {la} vs {lb}")
+        assert finite and mb > 0
+        assert abs(ma - mb) <= 0.10 * mb and rms <= 0.25 * mb, (rank, ma, mb, rms)
+        assert 0.95 * lb <= la <= 1.05 * lb, (rank, la, lb)
